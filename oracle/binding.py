@@ -1,0 +1,297 @@
+"""ctypes binding of the CPU oracle (oracle/ppf_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+PARITY UNPINNED (see oracle/ppf_oracle.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libppf_oracle.so")
+
+FEATURE_PCL_PFH, FEATURE_DROST_COS, FEATURE_DROST_ANGLE = 0, 1, 2
+ALPHA_MODE_A, ALPHA_MODE_B = 0, 1
+
+HYP_DTYPE = np.dtype(
+    [("pose", np.float32, (12,)), ("votes", np.uint32), ("model_index", np.uint32),
+     ("alpha_bin", np.uint32), ("scene_index", np.uint32)]
+)
+assert HYP_DTYPE.itemsize == 64
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (g++, no external dependencies)."""
+    src = [os.path.join(_HERE, f) for f in ("ppf_oracle.cpp", "ppf_oracle.h", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    fp, vp, sz = C.POINTER(C.c_float), C.c_void_p, C.c_size_t
+    L.oracle_pair_feature.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+    L.oracle_pair_feature.restype = C.c_int
+    L.oracle_alpha.argtypes = [vp, vp, vp]
+    L.oracle_alpha.restype = C.c_float
+    L.oracle_ref_frame.argtypes = [vp, vp, vp, vp]
+    L.oracle_ppf_estimation.argtypes = [C.c_int, vp, sz, vp]
+    L.oracle_ppf_estimation.restype = sz
+    L.oracle_hashmap_create.argtypes = [C.c_float, C.c_float]
+    L.oracle_hashmap_create.restype = vp
+    L.oracle_hashmap_destroy.argtypes = [vp]
+    L.oracle_hashmap_set_features.argtypes = [vp, vp, sz]
+    L.oracle_hashmap_model_diameter.argtypes = [vp]
+    L.oracle_hashmap_model_diameter.restype = C.c_float
+    L.oracle_hashmap_num_entries.argtypes = [vp]
+    L.oracle_hashmap_num_entries.restype = sz
+    L.oracle_hashmap_num_keys.argtypes = [vp]
+    L.oracle_hashmap_num_keys.restype = sz
+    L.oracle_hashmap_quantise.argtypes = [vp, vp, vp]
+    L.oracle_hashmap_query.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, sz]
+    L.oracle_hashmap_query.restype = sz
+    L.oracle_hashmap_query_key.argtypes = [vp, vp, vp, sz]
+    L.oracle_hashmap_query_key.restype = sz
+    L.oracle_hashmap_dump_keys.argtypes = [vp, vp, vp]
+    L.oracle_num_alpha_bins.argtypes = [C.c_float]
+    L.oracle_num_alpha_bins.restype = C.c_uint32
+    L.oracle_alpha_bin.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+    L.oracle_alpha_bin.restype = C.c_uint32
+    L.oracle_scene_pairs.argtypes = [vp, C.c_int, vp, sz, sz, vp, vp, vp]
+    L.oracle_scene_pairs.restype = sz
+    L.oracle_vote_accumulate.argtypes = [vp, C.c_int, C.c_int, sz, vp, sz, sz, vp]
+    L.oracle_vote_accumulate.restype = C.c_uint64
+    L.oracle_vote_accumulate_from_pairs.argtypes = [vp, C.c_int, sz, sz, vp, vp, vp]
+    L.oracle_vote_accumulate_from_pairs.restype = C.c_uint64
+    L.oracle_vote.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, sz, sz, sz, sz, C.c_int, vp, vp]
+    L.oracle_vote.restype = C.c_int
+    L.oracle_peak_pose.argtypes = [C.c_int, C.c_float, vp, sz, C.c_uint32, vp, sz, vp]
+    L.oracle_cluster.argtypes = [vp, sz, C.c_float, C.c_float, vp, vp, vp, vp]
+    L.oracle_cluster.restype = sz
+    L.oracle_poses_within.argtypes = [vp, vp, C.c_float, C.c_float]
+    L.oracle_poses_within.restype = C.c_int
+    L.oracle_transform.argtypes = [vp, sz, vp, vp]
+    L.oracle_register.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, sz, sz, C.c_float, C.c_float,
+                                  C.c_int, vp, vp, vp, vp]
+    L.oracle_register.restype = sz
+    L.oracle_max_threads.restype = C.c_int
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pair_feature(p1, n1, p2, n2, mode=FEATURE_PCL_PFH):
+    a = [_f32(x) for x in (p1, n1, p2, n2)]
+    f = np.zeros(4, np.float32)
+    ok = lib().oracle_pair_feature(mode, *[_p(x) for x in a], _p(f))
+    return bool(ok), f
+
+
+def alpha(p_r, n_r, p):
+    a = [_f32(x) for x in (p_r, n_r, p)]
+    return float(lib().oracle_alpha(*[_p(x) for x in a]))
+
+
+def ref_frame(p_r, n_r):
+    a = [_f32(x) for x in (p_r, n_r)]
+    R = np.zeros(9, np.float32)
+    t = np.zeros(3, np.float32)
+    lib().oracle_ref_frame(_p(a[0]), _p(a[1]), _p(R), _p(t))
+    return R.reshape(3, 3), t
+
+
+def ppf_estimation(cloud, mode=FEATURE_PCL_PFH):
+    """PPFEstimation::compute -> (N*N, 5) float32, NaN rows for invalid pairs."""
+    cloud = _f32(cloud)
+    n = cloud.shape[0]
+    out = np.empty((n * n, 5), np.float32)
+    lib().oracle_ppf_estimation(mode, _p(cloud), n, _p(out))
+    return out
+
+
+def num_alpha_bins(angle_step):
+    return int(lib().oracle_num_alpha_bins(np.float32(angle_step)))
+
+
+def alpha_bin(alpha_m, alpha_s, angle_step, mode=ALPHA_MODE_A):
+    return int(lib().oracle_alpha_bin(mode, np.float32(angle_step), np.float32(alpha_m),
+                                      np.float32(alpha_s)))
+
+
+class HashMap:
+    """pcl::PPFHashMapSearch restated (unordered_multimap + alpha_m matrix)."""
+
+    def __init__(self, angle_step=np.float32(12.0 / 180.0 * np.pi), dist_step=np.float32(0.01)):
+        self.angle_step = np.float32(angle_step)
+        self.dist_step = np.float32(dist_step)
+        self._h = lib().oracle_hashmap_create(self.angle_step, self.dist_step)
+        self.n = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_hashmap_destroy(self._h)
+            self._h = None
+
+    def set_input_feature_cloud(self, feats):
+        feats = _f32(feats).reshape(-1, 5)
+        lib().oracle_hashmap_set_features(self._h, _p(feats), feats.shape[0])
+        self.n = int(np.sqrt(np.float32(feats.shape[0])))
+        return self
+
+    @property
+    def model_diameter(self):
+        return float(lib().oracle_hashmap_model_diameter(self._h))
+
+    @property
+    def num_entries(self):
+        return int(lib().oracle_hashmap_num_entries(self._h))
+
+    @property
+    def num_keys(self):
+        return int(lib().oracle_hashmap_num_keys(self._h))
+
+    def quantise(self, f):
+        f = _f32(f)
+        d = np.zeros(4, np.int32)
+        lib().oracle_hashmap_quantise(self._h, _p(f), _p(d))
+        return d
+
+    def query(self, f1, f2, f3, f4):
+        cap = 1024
+        while True:
+            out = np.zeros((cap, 2), np.uint64)
+            n = lib().oracle_hashmap_query(self._h, f1, f2, f3, f4, _p(out), cap)
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def query_key(self, d):
+        d = np.ascontiguousarray(d, np.int32)
+        cap = 1024
+        while True:
+            out = np.zeros((cap, 2), np.uint64)
+            n = lib().oracle_hashmap_query_key(self._h, _p(d), _p(out), cap)
+            if n <= cap:
+                return out[:n]
+            cap = n
+
+    def dump_keys(self):
+        k = self.num_keys
+        keys = np.zeros((k, 4), np.int32)
+        lengths = np.zeros(k, np.uint32)
+        lib().oracle_hashmap_dump_keys(self._h, _p(keys), _p(lengths))
+        return keys, lengths
+
+    def scene_pairs(self, scene, s_r, mode=FEATURE_PCL_PFH):
+        scene = _f32(scene)
+        n = scene.shape[0]
+        inr = np.zeros(n, np.uint8)
+        d = np.zeros((n, 4), np.int32)
+        a = np.zeros(n, np.float32)
+        lib().oracle_scene_pairs(self._h, mode, _p(scene), n, s_r, _p(inr), _p(d), _p(a))
+        return inr, d, a
+
+    def vote_accumulate(self, n_m, scene, s_r, mode=FEATURE_PCL_PFH, alpha_mode=ALPHA_MODE_A):
+        scene = _f32(scene)
+        acc = np.zeros((n_m, num_alpha_bins(self.angle_step)), np.uint32)
+        votes = lib().oracle_vote_accumulate(self._h, mode, alpha_mode, n_m, _p(scene),
+                                             scene.shape[0], s_r, _p(acc))
+        return acc, int(votes)
+
+    def vote_accumulate_from_pairs(self, n_m, d, alpha_s, alpha_mode=ALPHA_MODE_A):
+        d = np.ascontiguousarray(d, np.int32).reshape(-1, 4)
+        alpha_s = _f32(alpha_s)
+        acc = np.zeros((n_m, num_alpha_bins(self.angle_step)), np.uint32)
+        votes = lib().oracle_vote_accumulate_from_pairs(self._h, alpha_mode, n_m, d.shape[0], _p(d),
+                                                        _p(alpha_s), _p(acc))
+        return acc, int(votes)
+
+    def vote(self, model, scene, ref_first=0, ref_step=1, ref_count=None, n_threads=1,
+             mode=FEATURE_PCL_PFH, alpha_mode=ALPHA_MODE_A):
+        model, scene = _f32(model), _f32(scene)
+        if ref_count is None:
+            ref_count = (scene.shape[0] - ref_first + ref_step - 1) // ref_step
+        hyps = np.zeros(ref_count, HYP_DTYPE)
+        stats = np.zeros(4, np.uint64)
+        rc = lib().oracle_vote(self._h, mode, alpha_mode, _p(model), model.shape[0], _p(scene),
+                               scene.shape[0], ref_first, ref_step, ref_count, n_threads,
+                               _p(hyps), _p(stats))
+        if rc != 0:
+            raise RuntimeError("oracle_vote failed (model/table size mismatch?)")
+        return hyps, dict(zip(("pairs_examined", "pairs_in_radius", "nonempty_lookups", "votes"),
+                              (int(x) for x in stats)))
+
+    def register(self, model, scene, ref_rate=5, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi,
+                 n_threads=1, mode=FEATURE_PCL_PFH, alpha_mode=ALPHA_MODE_A):
+        model, scene = _f32(model), _f32(scene)
+        final = np.zeros(16, np.float32)
+        poses = np.zeros((3, 16), np.float32)
+        votes = np.zeros(3, np.uint32)
+        stats = np.zeros(4, np.uint64)
+        n = lib().oracle_register(self._h, mode, alpha_mode, _p(model), model.shape[0], _p(scene),
+                                  scene.shape[0], ref_rate, np.float32(pos_thr), np.float32(rot_thr),
+                                  n_threads, _p(final), _p(poses), _p(votes), _p(stats))
+        return final.reshape(4, 4), poses[:n].reshape(n, 4, 4), votes[:n], stats
+
+
+def peak_pose(model, model_index, bin_, scene, s_r, angle_step, alpha_mode=ALPHA_MODE_A):
+    model, scene = _f32(model), _f32(scene)
+    pose = np.zeros(12, np.float32)
+    lib().oracle_peak_pose(alpha_mode, np.float32(angle_step), _p(model), model_index, bin_,
+                           _p(scene), s_r, _p(pose))
+    return pose.reshape(3, 4)
+
+
+def cluster(hyps, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
+    hyps = np.ascontiguousarray(hyps, HYP_DTYPE)
+    n = hyps.shape[0]
+    poses = np.zeros((3, 16), np.float32)
+    votes = np.zeros(3, np.uint32)
+    assign = np.zeros(n, np.uint32)
+    ncl = C.c_size_t(0)
+    k = lib().oracle_cluster(_p(hyps), n, np.float32(pos_thr), np.float32(rot_thr), _p(poses),
+                             _p(votes), _p(assign), C.byref(ncl))
+    return poses[:k].reshape(k, 4, 4), votes[:k], assign, int(ncl.value)
+
+
+def poses_within(a, b, pos_thr, rot_thr):
+    a, b = _f32(a).reshape(-1)[:12], _f32(b).reshape(-1)[:12]
+    return bool(lib().oracle_poses_within(_p(a), _p(b), np.float32(pos_thr), np.float32(rot_thr)))
+
+
+def transform(cloud, pose16):
+    cloud = _f32(cloud)
+    M = _f32(pose16).reshape(16)
+    out = np.zeros((cloud.shape[0], 3), np.float32)
+    lib().oracle_transform(_p(cloud), cloud.shape[0], _p(M), _p(out))
+    return out
+
+
+def max_threads():
+    return int(lib().oracle_max_threads())

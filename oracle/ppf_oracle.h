@@ -1,0 +1,135 @@
+/*
+ * ppf_oracle.h — C interface of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library, and only as the checker / the timed host baseline.
+ *
+ * PARITY UNPINNED: the arithmetic restated here lives in PCL (features/src/pfh.cpp,
+ * features/impl/ppf.hpp, registration/impl/ppf_registration.hpp,
+ * registration/src/ppf_registration.cpp), which is neither vendored in the reference
+ * nor installable in the build container, and the reference ships no tests or golden
+ * vectors for the path.  The restatement follows SURVEY.md Appendix A.
+ *
+ * All clouds are row-major float32 N×6 = [x y z nx ny nz], the layout the reference
+ * hands to its PPF engine (reference include/CloudProcessing.h:163-190).
+ */
+#ifndef PPF_ORACLE_H
+#define PPF_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* feature functor: what PCL executes, and the two Drost alternates */
+enum { ORACLE_FEATURE_PCL_PFH = 0, ORACLE_FEATURE_DROST_COS = 1, ORACLE_FEATURE_DROST_ANGLE = 2 };
+/* alpha binning: mode A = PCL >= 1.12 (canonical), mode B = PCL 1.8-1.11 */
+enum { ORACLE_ALPHA_MODE_A = 0, ORACLE_ALPHA_MODE_B = 1 };
+
+/* A.1 / A.1' : one pair feature.  Returns 1 when the pair is valid. */
+int oracle_pair_feature(int feature_mode, const float *p1, const float *n1, const float *p2,
+                        const float *n2, float *f /*[4]*/);
+
+/* A.2 : planar angle of point p in the frame that moves (p_r, n_r) to the origin / x-axis. */
+float oracle_alpha(const float *p_r, const float *n_r, const float *p);
+
+/* A.2 : rigid frame of a reference point; R row-major [9], t [3]. */
+void oracle_ref_frame(const float *p_r, const float *n_r, float *R, float *t);
+
+/* A.2 : PPFEstimation::computeFeature over all ordered pairs.  out is N*N*5 floats
+ * {f1,f2,f3,f4,alpha_m}, row-major [i*N+j]; invalid pairs (i==j or failure) are all-NaN.
+ * Returns the number of valid pairs. */
+size_t oracle_ppf_estimation(int feature_mode, const float *cloud, size_t n, float *out);
+
+/* A.3 : PPFHashMapSearch */
+typedef struct oracle_hashmap oracle_hashmap;
+oracle_hashmap *oracle_hashmap_create(float angle_step, float dist_step);
+void oracle_hashmap_destroy(oracle_hashmap *hm);
+/* setInputFeatureCloud: feats = count*5 floats, count = n*n. NaN pairs are skipped. */
+void oracle_hashmap_set_features(oracle_hashmap *hm, const float *feats, size_t count);
+float oracle_hashmap_model_diameter(const oracle_hashmap *hm);
+size_t oracle_hashmap_num_entries(const oracle_hashmap *hm);
+size_t oracle_hashmap_num_keys(const oracle_hashmap *hm);
+/* quantisation used by the map: d[4] = floor(f/step) */
+void oracle_hashmap_quantise(const oracle_hashmap *hm, const float *f, int32_t *d);
+/* nearestNeighborSearch: writes up to cap (i,j) pairs, canonical order (i asc, j asc).
+ * Returns the full bucket length. */
+size_t oracle_hashmap_query(const oracle_hashmap *hm, float f1, float f2, float f3, float f4,
+                            uint64_t *pairs /*[cap][2]*/, size_t cap);
+size_t oracle_hashmap_query_key(const oracle_hashmap *hm, const int32_t *d, uint64_t *pairs,
+                                size_t cap);
+/* dump every distinct key (4 ints each) and its bucket length; arrays sized num_keys */
+void oracle_hashmap_dump_keys(const oracle_hashmap *hm, int32_t *keys, uint32_t *lengths);
+
+/* A.4 : number of alpha bins */
+uint32_t oracle_num_alpha_bins(float angle_step);
+/* A.4 : bin of one (alpha_m, alpha_s) pair. Returns UINT32_MAX for NaN. */
+uint32_t oracle_alpha_bin(int alpha_mode, float angle_step, float alpha_m, float alpha_s);
+
+/* A.4 : per-scene-pair quantities of one reference point (debug / parity):
+ * for every scene point s writes in_radius[s] (0/1; 0 for s==s_r and for failed pairs),
+ * d[s][4] and alpha_s[s].  Returns the number of in-radius valid pairs. */
+size_t oracle_scene_pairs(const oracle_hashmap *hm, int feature_mode, const float *scene,
+                          size_t n_s, size_t s_r, uint8_t *in_radius, int32_t *d,
+                          float *alpha_s);
+
+/* A.4 : the accumulator of one reference point, acc is n_m * n_alpha uint32, zeroed here.
+ * Returns total votes cast. */
+uint64_t oracle_vote_accumulate(const oracle_hashmap *hm, int feature_mode, int alpha_mode,
+                                size_t n_m, const float *scene, size_t n_s, size_t s_r,
+                                uint32_t *acc);
+/* integer half only: accumulate from externally supplied per-pair keys and alpha_s
+ * (used to check the device's index work bit-exactly given the device's own float results) */
+uint64_t oracle_vote_accumulate_from_pairs(const oracle_hashmap *hm, int alpha_mode, size_t n_m,
+                                           size_t n_pairs, const int32_t *d /*[n][4]*/,
+                                           const float *alpha_s, uint32_t *acc);
+
+/* one hypothesis per reference point (64 bytes, same record the device emits) */
+typedef struct oracle_hypothesis {
+    float pose[12];  /* 3x4 row-major, model -> scene */
+    uint32_t votes;
+    uint32_t model_index;  /* i*  */
+    uint32_t alpha_bin;    /* j*  */
+    uint32_t scene_index;  /* s_r */
+} oracle_hypothesis;
+
+/* A.4 : voting loop over reference points ref_first, ref_first+ref_step, ... (ref_count of
+ * them).  n_threads <= 1 is PCL as shipped; > 1 uses OpenMP over reference points with
+ * thread-private accumulators.  stats (optional, [4]) receives pairs examined, pairs in
+ * radius, non-empty lookups, votes. */
+int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, const float *model,
+                size_t n_m, const float *scene, size_t n_s, size_t ref_first, size_t ref_step,
+                size_t ref_count, int n_threads, oracle_hypothesis *hyps, uint64_t *stats);
+
+/* A.4 : pose of one peak (model_index, alpha_bin) for scene reference s_r */
+void oracle_peak_pose(int alpha_mode, float angle_step, const float *model, size_t model_index,
+                      uint32_t alpha_bin, const float *scene, size_t s_r, float *pose12);
+
+/* A.5 : clusterPoses.  out_poses [3][16] row-major 4x4, out_votes [3]; returns #results.
+ * assignment (optional, [n]) receives the cluster creation index of every input hypothesis
+ * (in input order), n_clusters (optional) the number of clusters. */
+size_t oracle_cluster(const oracle_hypothesis *hyps, size_t n, float pos_thr, float rot_thr,
+                      float *out_poses, uint32_t *out_votes, uint32_t *assignment,
+                      size_t *n_clusters);
+
+/* A.5 : posesWithinErrorBounds on two 3x4 poses */
+int oracle_poses_within(const float *a12, const float *b12, float pos_thr, float rot_thr);
+
+/* A.4 tail : transformPointCloud (xyz only) ; out is n*3 floats */
+void oracle_transform(const float *cloud, size_t n, const float *pose16, float *out_xyz);
+
+/* PPFRegistration::align in one call. final16 = getFinalTransformation(); returns #results */
+size_t oracle_register(const oracle_hashmap *hm, int feature_mode, int alpha_mode,
+                       const float *model, size_t n_m, const float *scene, size_t n_s,
+                       size_t ref_rate, float pos_thr, float rot_thr, int n_threads,
+                       float *final16, float *out_poses, uint32_t *out_votes, uint64_t *stats);
+
+int oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
