@@ -1,0 +1,196 @@
+/*
+ * b200ppf.h — C ABI of libb200ppf.so, the B200 (sm_100a) Point-Pair-Feature pose engine.
+ *
+ * This is the drop-in boundary for the PPF path that EmilyJrxx/YOLO_PPF_Pose_Estimation
+ * drives after its YOLO crop (reference include/CloudProcessing.h:222-261 train,
+ * :106-121 load, :428-533 match, fed by :163-190; called from
+ * src/YOLO_cropping_ppf_test.cpp:113-127).  BASELINE.json fixes the operator surface to
+ * PCL's:  pcl::PPFEstimation<PointNormal,PointNormal,PPFSignature>::compute,
+ * pcl::PPFHashMapSearch::setInputFeatureCloud / nearestNeighborSearch and
+ * pcl::PPFRegistration::setInputSource / setInputTarget / setSearchMethod / align.
+ * PCL is not vendored in the reference; "[PCL] file" citations below name the upstream
+ * file each entry point replaces (restated in SURVEY.md Appendix A).  The header-only
+ * PCL-shaped C++ shim over this ABI is include/pcl_compat/.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative B200PPF_ERR_*;
+ *     b200ppf_last_error() gives the message.  Nothing throws or aborts across the ABI
+ *     (PCL's own convention on this path is PCL_ERROR + early return).
+ *   - there is NO CPU fallback: b200ppf_create fails when no sm_100 device is usable.
+ *   - a context is bound to one CUDA device and owns one stream; use one context per
+ *     thread / per GPU (one process per GPU under torchrun).  Calls are synchronous unless
+ *     the name ends in _device (asynchronous on the context stream, results stay in HBM).
+ *   - host clouds are float32 AoS with a caller-given stride: pcl::PointNormal is
+ *     stride 12 / normal offset 4; the reference's N x 6 cv::Mat is stride 6 / offset 3.
+ */
+#ifndef B200PPF_H
+#define B200PPF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PPF_VERSION 100
+
+#define B200PPF_OK 0
+#define B200PPF_ERR_INVALID (-1)     /* bad argument */
+#define B200PPF_ERR_CUDA (-2)        /* CUDA runtime / kernel failure */
+#define B200PPF_ERR_NOMEM (-3)       /* device or host allocation failed */
+#define B200PPF_ERR_STATE (-4)       /* object used before it is ready / size mismatch */
+#define B200PPF_ERR_UNSUPPORTED (-5) /* e.g. discretisation too fine for 32-bit keys */
+
+/* feature functor: PCL_PFH is what PCL's PPF classes execute ([PCL] features/src/pfh.cpp
+ * computePairFeatures); DROST_* are the textbook tuple ([PCL] features/src/ppf.cpp
+ * computePPFPairFeature as cosines, or as angles). */
+#define B200PPF_FEATURE_PCL_PFH 0
+#define B200PPF_FEATURE_DROST_COS 1
+#define B200PPF_FEATURE_DROST_ANGLE 2
+/* alpha binning of the voting loop: A = PCL >= 1.12, B = PCL 1.8-1.11 legacy */
+#define B200PPF_ALPHA_MODE_A 0
+#define B200PPF_ALPHA_MODE_B 1
+
+typedef struct b200ppf_ctx b200ppf_ctx;
+typedef struct b200ppf_cloud b200ppf_cloud;       /* device point+normal cloud (float4 SoA) */
+typedef struct b200ppf_features b200ppf_features; /* device PointCloud<PPFSignature>, N*N   */
+typedef struct b200ppf_table b200ppf_table;       /* device CSR table = PPFHashMapSearch    */
+
+/* pcl::PPFSignature ([PCL] common/include/pcl/impl/point_types.hpp): 20 bytes */
+typedef struct b200ppf_signature {
+    float f1, f2, f3, f4, alpha_m;
+} b200ppf_signature;
+
+/* PPFRegistration::PoseWithVotes plus the peak it came from: 64 bytes, the record the
+ * voting kernel emits per scene reference point and the unit of the multi-GPU all-gather */
+typedef struct b200ppf_hypothesis {
+    float pose[12]; /* 3x4 row-major, model -> scene */
+    uint32_t votes;
+    uint32_t model_index; /* i* */
+    uint32_t alpha_bin;   /* j* */
+    uint32_t scene_index; /* s_r */
+} b200ppf_hypothesis;
+
+typedef struct b200ppf_table_info {
+    uint64_t n_model;     /* model points */
+    uint64_t n_entries;   /* valid ordered pairs stored */
+    uint64_t n_keys;      /* non-empty buckets */
+    uint64_t key_space;   /* dense packed-key range per slice */
+    uint32_t n_slices;    /* model-row slices (accumulator tiles), 1 for small models */
+    uint32_t slice_rows;  /* model rows per slice */
+    uint32_t n_alpha;     /* accumulator columns = floor(2*pi/angle_step) */
+    uint32_t key_bits;    /* bits sorted */
+    int32_t lo[4];        /* lower bound of each quantised component */
+    int32_t size[4];      /* extent of each quantised component */
+    float angle_step, dist_step;
+    float max_dist;       /* getModelDiameter() */
+    float reserved;
+} b200ppf_table_info;
+
+/* per-stage device times of the last call on this context, milliseconds (CUDA events) */
+typedef struct b200ppf_timings {
+    float upload_ms, features_ms, keys_ms, sort_ms, csr_ms, vote_ms, pose_ms, cluster_ms,
+        transform_ms, download_ms;
+} b200ppf_timings;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int b200ppf_create(int device, b200ppf_ctx **out);
+void b200ppf_destroy(b200ppf_ctx *ctx);
+const char *b200ppf_last_error(const b200ppf_ctx *ctx); /* ctx may be NULL: global message */
+int b200ppf_version(void);
+int b200ppf_set_feature_mode(b200ppf_ctx *ctx, int feature_mode);
+int b200ppf_set_alpha_mode(b200ppf_ctx *ctx, int alpha_mode);
+int b200ppf_get_device(const b200ppf_ctx *ctx);
+void *b200ppf_get_stream(const b200ppf_ctx *ctx); /* cudaStream_t */
+int b200ppf_synchronize(b200ppf_ctx *ctx);
+int b200ppf_get_timings(const b200ppf_ctx *ctx, b200ppf_timings *out);
+/* number of kernels this context has launched so far */
+uint64_t b200ppf_launch_count(const b200ppf_ctx *ctx);
+
+/* ---- clouds: replaces setInputCloud/setInputNormals/setInputSource/setInputTarget ------- */
+/* host may be pageable or pinned; points with a NaN coordinate or normal are dropped
+ * (SURVEY.md A.8 rule 5) and *out keeps the surviving order. */
+int b200ppf_cloud_upload(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride_floats,
+                         size_t normal_offset_floats, b200ppf_cloud **out);
+size_t b200ppf_cloud_size(const b200ppf_cloud *cloud);
+void b200ppf_cloud_free(b200ppf_cloud *cloud);
+
+/* ---- K1: [PCL] features/include/pcl/features/impl/ppf.hpp PPFEstimation::computeFeature -- */
+int b200ppf_features_compute(b200ppf_ctx *ctx, const b200ppf_cloud *model, b200ppf_features **out);
+int b200ppf_features_upload(b200ppf_ctx *ctx, const b200ppf_signature *host, size_t count,
+                            b200ppf_features **out);
+int b200ppf_features_download(b200ppf_ctx *ctx, const b200ppf_features *f, size_t first,
+                              size_t count, b200ppf_signature *host);
+size_t b200ppf_features_count(const b200ppf_features *f);
+void b200ppf_features_free(b200ppf_features *f);
+
+/* ---- K2: [PCL] registration/src/ppf_registration.cpp PPFHashMapSearch ------------------- */
+/* setInputFeatureCloud: n = sqrt(count) model points. */
+int b200ppf_table_build(b200ppf_ctx *ctx, const b200ppf_features *f, float angle_step,
+                        float dist_step, b200ppf_table **out);
+/* K1+K2 fused: the same table straight from the model cloud, no N*N*20-byte feature cloud */
+int b200ppf_table_build_from_cloud(b200ppf_ctx *ctx, const b200ppf_cloud *model, float angle_step,
+                                   float dist_step, b200ppf_table **out);
+int b200ppf_table_get_info(const b200ppf_table *t, b200ppf_table_info *info);
+/* nearestNeighborSearch: up to cap (i,j) pairs in canonical order (i asc, j asc);
+ * *n_found receives the full bucket length. */
+int b200ppf_table_query(b200ppf_ctx *ctx, const b200ppf_table *t, float f1, float f2, float f3,
+                        float f4, uint64_t *pairs, size_t cap, size_t *n_found);
+int b200ppf_table_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int32_t *d4,
+                            uint64_t *pairs, size_t cap, size_t *n_found);
+/* the public alpha_m_[i][j] member, row-major n*n floats (NaN where the pair is invalid) */
+int b200ppf_table_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host);
+/* raw CSR export (parity tests, serialisation): offsets has n_slices*key_space+1 entries;
+ * the three entry arrays have n_entries elements.  Any pointer may be NULL. */
+int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *offsets,
+                         uint32_t *entry_i, uint32_t *entry_j, float *entry_alpha_m);
+void b200ppf_table_free(b200ppf_table *t);
+
+/* ---- K3: [PCL] registration/impl/ppf_registration.hpp computeTransformation, voting loop - */
+/* One hypothesis per scene reference point ref_first + k*ref_step, k < ref_count (the slice a
+ * rank owns when reference points are sharded across GPUs). */
+int b200ppf_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
+                 const b200ppf_cloud *scene, size_t ref_first, size_t ref_step, size_t ref_count,
+                 b200ppf_hypothesis *hyps_host);
+int b200ppf_vote_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
+                        const b200ppf_cloud *scene, size_t ref_first, size_t ref_step,
+                        size_t ref_count, b200ppf_hypothesis *hyps_device);
+/* counters of the last vote on this context: pairs examined, pairs in radius (the metric's
+ * "pairs voted"), non-empty bucket lookups, votes cast */
+int b200ppf_vote_stats(b200ppf_ctx *ctx, uint64_t *stats4);
+/* parity hooks: what the device computed for one reference point */
+int b200ppf_vote_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene,
+                             size_t s_r, uint8_t *in_radius, int32_t *d4, float *alpha_s);
+int b200ppf_vote_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t,
+                                   const b200ppf_cloud *scene, size_t s_r, uint32_t *acc);
+
+/* parity hook for the voting loop's alpha binning: evaluates the hot-loop form (fast) and the
+ * literal PCL form (exact) for n (alpha_m, alpha_s) pairs — on the device when ctx is given, with
+ * the host build of the same inline functions when ctx is NULL. */
+int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+                             const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact);
+
+/* ---- K4: [PCL] ppf_registration.hpp clusterPoses / posesWithinErrorBounds ---------------- */
+int b200ppf_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_host, size_t n, float pos_thr,
+                    float rot_thr, float *poses16, uint32_t *votes, size_t *n_out);
+int b200ppf_cluster_device(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n,
+                           float pos_thr, float rot_thr, float *poses16, uint32_t *votes,
+                           size_t *n_out);
+/* cluster creation index of every hypothesis of the last cluster call (input order) */
+int b200ppf_cluster_assignment(b200ppf_ctx *ctx, uint32_t *assignment, size_t n,
+                               size_t *n_clusters);
+
+/* ---- K5: tail of computeTransformation, pcl::transformPointCloud (xyz only) -------------- */
+int b200ppf_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose16,
+                      float *out_host, size_t out_stride_floats);
+
+/* ---- PPFRegistration::align in one call: vote + cluster, final16 = results.front() -------- */
+int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
+                     const b200ppf_cloud *scene, size_t ref_rate, float pos_thr, float rot_thr,
+                     float *final16, float *poses16, uint32_t *votes, size_t *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PPF_H */

@@ -1,0 +1,421 @@
+"""GPU parity tests: every stage of the CUDA path, through the C ABI, against the CPU oracle.
+
+Fixtures are the reference's own data frozen under tests/golden (tools/make_fixtures.py); nothing
+here reads /root/reference.  Rules and tolerances: tests/parity.py.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ANGLE_STEP, DIST_STEP, ROOT
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev_bottle(ctx, bottle):
+    return ctx.upload_cloud(bottle)
+
+
+@pytest.fixture(scope="module")
+def dev_crop(ctx, scene_crop):
+    return ctx.upload_cloud(scene_crop)
+
+
+@pytest.fixture(scope="module")
+def table_from_oracle_features(ctx, oracle_bottle):
+    """PPFHashMapSearch::setInputFeatureCloud on the oracle's own signatures: identical floats in."""
+    feats, _ = oracle_bottle
+    return ctx.table_build(ctx.features_upload(feats), ANGLE_STEP, DIST_STEP)
+
+
+@pytest.fixture(scope="module")
+def table_fused(ctx, dev_bottle):
+    return ctx.table_build_from_cloud(dev_bottle, ANGLE_STEP, DIST_STEP)
+
+
+# ---- K1 ------------------------------------------------------------------------------------------
+
+def test_k1_features_vs_oracle(ctx, bottle, dev_bottle, oracle_bottle):
+    feats, _ = oracle_bottle
+    F = ctx.features_compute(dev_bottle)
+    assert F.count == bottle.shape[0] ** 2
+    rep = parity.compare_features(bottle, F.download(), feats, ANGLE_STEP, DIST_STEP)
+    print("K1 parity:", rep)
+    assert rep["swap_ambiguous"] < 50 and rep["key_flips"] < 200
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_k1_drost_modes(bottle, oracle, mode):
+    from yolo_ppf_pose_estimation_b200 import capi
+    c = capi.Context(0, feature_mode=mode)
+    sub = bottle[::4]
+    F = c.features_compute(c.upload_cloud(sub)).download()
+    ref = oracle.ppf_estimation(sub, mode=mode)
+    assert np.array_equal(np.isnan(F[:, 0]), np.isnan(ref[:, 0]))
+    v = ~np.isnan(ref[:, 0])
+    assert np.array_equal(F[v, 3], ref[v, 3])
+    assert np.abs(F[v, :3].astype(np.float64) - ref[v, :3]).max() < 4e-6
+    assert parity.circ_diff(F[v, 4], ref[v, 4]).max() < parity.ALPHA_TOL
+
+
+def test_k1_partial_download_and_bounds(ctx, dev_bottle):
+    F = ctx.features_compute(dev_bottle)
+    n = dev_bottle.size
+    row7 = F.download(7 * n, n)
+    assert np.isnan(row7[7]).all() and not np.isnan(row7[8]).any()
+    from yolo_ppf_pose_estimation_b200.capi import B200PPFError
+    with pytest.raises(B200PPFError):
+        F.download(n * n - 1, 2)
+
+
+# ---- K2 ------------------------------------------------------------------------------------------
+
+def test_k2_buckets_bit_exact(oracle_bottle, table_from_oracle_features):
+    """Same signatures in -> identical keys, bucket contents in canonical (i, j) order, alpha_m, diameter."""
+    feats, hm = oracle_bottle
+    t = table_from_oracle_features
+    ti = t.info
+    assert ti.n_entries == hm.num_entries == 294306
+    assert ti.n_keys == hm.num_keys == 10448
+    assert np.float32(ti.max_dist) == np.float32(hm.model_diameter)
+    assert ti.n_alpha == 29 and ti.n_slices == 1
+    buckets = parity.table_buckets(t)
+    keys, lengths = hm.dump_keys()
+    assert len(buckets) == len(keys)
+    n = ti.n_model
+    for key, length in zip(keys, lengths):
+        bi, bj, ba = buckets[tuple(int(x) for x in key)]
+        ref = hm.query_key(key)
+        assert length == len(bi)
+        assert np.array_equal(bi, ref[:, 0].astype(np.uint32)) and np.array_equal(bj, ref[:, 1].astype(np.uint32))
+        assert np.array_equal(ba.view(np.uint32), feats[bi.astype(np.int64) * n + bj, 4].view(np.uint32))
+
+
+def test_k2_nearest_neighbor_search(oracle_bottle, table_from_oracle_features):
+    feats, hm = oracle_bottle
+    rng = np.random.default_rng(3)
+    valid = np.flatnonzero(~np.isnan(feats[:, 0]))
+    for p in rng.choice(valid, 20, replace=False):
+        f = feats[p]
+        got = table_from_oracle_features.query(*[float(x) for x in f[:4]])
+        want = hm.query(*[float(x) for x in f[:4]])
+        assert np.array_equal(got, want)
+    # a feature no model pair has -> empty
+    assert len(table_from_oracle_features.query(0.0, 0.0, 0.0, 10.0)) == 0
+    assert len(table_from_oracle_features.query(float("nan"), 0.0, 0.0, 0.1)) == 0
+
+
+def test_k2_alpha_m_matrix(oracle_bottle, table_from_oracle_features):
+    feats, _ = oracle_bottle
+    n = table_from_oracle_features.info.n_model
+    A = table_from_oracle_features.alpha_m()
+    ref = feats[:, 4].reshape(n, n)
+    assert np.array_equal(np.isnan(A), np.isnan(ref))
+    assert np.array_equal(A[~np.isnan(ref)].view(np.uint32), ref[~np.isnan(ref)].view(np.uint32))
+
+
+def test_k2_fused_equals_two_step(ctx, dev_bottle, table_fused):
+    """K1+K2 fused build == compute() then setInputFeatureCloud() on the device's own signatures."""
+    two = ctx.table_build(ctx.features_compute(dev_bottle), ANGLE_STEP, DIST_STEP)
+    a, b = parity.table_buckets(table_fused), parity.table_buckets(two)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert all(np.array_equal(x.view(np.uint32), y.view(np.uint32)) for x, y in zip(a[k], b[k]))
+    assert table_fused.info.n_entries == two.info.n_entries
+    assert table_fused.info.max_dist == two.info.max_dist
+
+
+def test_k2_fused_vs_oracle_key_rule(bottle, oracle_bottle, table_fused):
+    """Device-computed keys vs oracle keys: flips only within 1e-5 of a bin edge."""
+    feats, hm = oracle_bottle
+    n = bottle.shape[0]
+    off, ei, ej, ea = table_fused.export()
+    ti = table_fused.info
+    assert ti.n_slices == 1
+    lens = np.diff(off.astype(np.int64))
+    packed = np.repeat(np.arange(ti.key_space), lens)
+    dev_keys = table_fused.unpack_key(packed)
+    idx = ei.astype(np.int64) * n + ej
+    assert len(np.unique(idx)) == len(idx) == ti.n_entries == hm.num_entries
+    ref_keys = parity.quantise(feats[idx, :4], ANGLE_STEP, DIST_STEP)
+    flip = dev_keys != ref_keys
+    edge = parity.near_edge(feats[idx, :4], ANGLE_STEP, DIST_STEP)
+    amb = parity.swap_margin(bottle, ei.astype(np.int64), ej.astype(np.int64)) < parity.EDGE_TOL
+    assert not ((flip & ~edge).any(axis=1) & ~amb).any()
+    assert flip.any(axis=1).sum() < 200
+    assert np.float32(ti.max_dist) == np.float32(hm.model_diameter)
+
+
+def test_k2_sliced_table_same_buckets(bottle, oracle_bottle):
+    """Forcing several accumulator slices must not change bucket contents."""
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+from yolo_ppf_pose_estimation_b200 import capi
+import parity
+from conftest import ANGLE_STEP, DIST_STEP, load_cloud
+from oracle import binding as ob
+m = load_cloud('bottle_1cm'); s = load_cloud('scene_crop_1cm')
+feats = ob.ppf_estimation(m)
+c = capi.Context(0)
+t = c.table_build(c.features_upload(feats), ANGLE_STEP, DIST_STEP)
+assert t.info.n_slices == 4, t.info.n_slices
+hm = ob.HashMap(ANGLE_STEP, DIST_STEP).set_input_feature_cloud(feats)
+b = parity.table_buckets(t)
+keys, lengths = hm.dump_keys()
+assert len(b) == len(keys)
+for key in keys:
+    bi, bj, ba = b[tuple(int(x) for x in key)]
+    ref = hm.query_key(key)
+    assert np.array_equal(bi, ref[:,0].astype(np.uint32)) and np.array_equal(bj, ref[:,1].astype(np.uint32))
+dm, ds = c.upload_cloud(m), c.upload_cloud(s)
+for s_r in (0, 401, 933):
+    inr, d, a = c.vote_debug_pairs(t, ds, s_r)
+    acc = c.vote_debug_accumulator(t, ds, s_r)
+    ref, votes = hm.vote_accumulate_from_pairs(m.shape[0], d[inr > 0], a[inr > 0])
+    assert np.array_equal(acc, ref), s_r
+hy = c.vote(dm, t, ds, 0, 5)
+for h in hy[::17]:
+    acc = c.vote_debug_accumulator(t, ds, int(h['scene_index']))
+    flat = int(np.argmax(acc)); assert h['votes'] == acc.reshape(-1)[flat]
+    assert (h['model_index'], h['alpha_bin']) == divmod(flat, acc.shape[1]) or h['votes'] == 0
+print('SLICED_OK')
+"""
+    env = dict(os.environ, B200PPF_SLICE_ROWS="150")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "SLICED_OK" in r.stdout, r.stdout + r.stderr
+
+
+# ---- K3 ------------------------------------------------------------------------------------------
+
+REFS = (0, 5, 250, 600, 933)
+
+
+def test_k3_scene_pairs_vs_oracle(ctx, scene_crop, dev_crop, oracle_bottle, table_from_oracle_features):
+    _, hm = oracle_bottle
+    radius = np.float32(hm.model_diameter) * np.float32(0.5)
+    for s_r in REFS:
+        inr, d, a = ctx.vote_debug_pairs(table_from_oracle_features, dev_crop, s_r)
+        rin, rd, ra = hm.scene_pairs(scene_crop, s_r)
+        dist = np.linalg.norm(scene_crop[:, :3].astype(np.float64) - scene_crop[s_r, :3], axis=1)
+        radius_edge = np.abs(dist - float(radius)) < parity.EDGE_TOL
+        assert np.array_equal(inr[~radius_edge], rin[~radius_edge])
+        both = (inr > 0) & (rin > 0)
+        assert parity.circ_diff(a[both], ra[both]).max() <= parity.ALPHA_TOL
+        flip = (d[both] != rd[both])
+        if flip.any():
+            # recompute the oracle's float features for the flipped pairs and apply the edge rule
+            idx = np.flatnonzero(both)[flip.any(axis=1)]
+            for s in idx:
+                ok, f = oracle_pair(scene_crop, s_r, s)
+                amb = parity.swap_margin(scene_crop, np.array([s_r]), np.array([s]))[0] < parity.EDGE_TOL
+                edge = parity.near_edge(f, ANGLE_STEP, DIST_STEP)
+                assert amb or not ((d[s] != rd[s]) & ~edge).any(), (s_r, s, f, d[s], rd[s])
+        assert flip.any(axis=1).mean() < 0.02
+
+
+def oracle_pair(cloud, a, b):
+    from oracle import binding as ob
+    return ob.pair_feature(cloud[a, :3], cloud[a, 3:], cloud[b, :3], cloud[b, 3:])
+
+
+def test_k3_accumulator_bit_exact(ctx, bottle, dev_crop, oracle_bottle, table_from_oracle_features):
+    """Index half of the voting loop: with the device's own per-pair (key, alpha_s) the oracle's
+    bucket walk + alpha binning must reproduce the device accumulator exactly."""
+    _, hm = oracle_bottle
+    for s_r in REFS:
+        inr, d, a = ctx.vote_debug_pairs(table_from_oracle_features, dev_crop, s_r)
+        acc = ctx.vote_debug_accumulator(table_from_oracle_features, dev_crop, s_r)
+        ref, votes = hm.vote_accumulate_from_pairs(bottle.shape[0], d[inr > 0], a[inr > 0])
+        assert votes == int(acc.sum())
+        assert np.array_equal(acc, ref), f"accumulator differs for reference {s_r}"
+
+
+def test_k3_accumulator_vs_oracle_floats(ctx, bottle, scene_crop, dev_crop, oracle_bottle, table_from_oracle_features):
+    """Whole loop vs the oracle (its own floats): counts may differ only through edge pairs."""
+    _, hm = oracle_bottle
+    for s_r in REFS:
+        acc = ctx.vote_debug_accumulator(table_from_oracle_features, dev_crop, s_r).astype(np.int64)
+        ref, votes = hm.vote_accumulate(bottle.shape[0], scene_crop, s_r)
+        l1 = np.abs(acc - ref.astype(np.int64)).sum()
+        assert l1 <= 0.01 * max(votes, 1) + 8, (s_r, l1, votes)
+
+
+def test_k3_hypotheses(ctx, bottle, scene_crop, dev_bottle, dev_crop, oracle, oracle_bottle, table_from_oracle_features):
+    _, hm = oracle_bottle
+    hy = ctx.vote(dev_bottle, table_from_oracle_features, dev_crop, 0, 5)
+    ref, stats = hm.vote(bottle, scene_crop, 0, 5, n_threads=oracle.max_threads())
+    assert len(hy) == len(ref) == (scene_crop.shape[0] + 4) // 5
+    assert np.array_equal(hy["scene_index"], ref["scene_index"])
+    st = ctx.vote_stats()
+    assert st["pairs_examined"] == len(hy) * (scene_crop.shape[0] - 1)
+    assert abs(st["pairs_in_radius"] - stats["pairs_in_radius"]) <= 0.001 * stats["pairs_in_radius"] + 2
+    assert abs(st["votes"] - stats["votes"]) <= 0.002 * stats["votes"]
+    same_peak = (hy["model_index"] == ref["model_index"]) & (hy["alpha_bin"] == ref["alpha_bin"])
+    assert same_peak.mean() > 0.9, same_peak.mean()
+    dv = np.abs(hy["votes"].astype(np.int64) - ref["votes"].astype(np.int64))
+    assert (dv <= 0.05 * ref["votes"] + 3).all()
+    assert (hy["votes"][same_peak] == ref["votes"][same_peak]).mean() > 0.8
+    # same peak -> same pose up to libm ulps
+    dp = np.abs(hy["pose"][same_peak] - ref["pose"][same_peak]).max()
+    assert dp < 2e-5, dp
+    # the peak is the first maximum of the device's own accumulator (PCL tie-break)
+    for h in hy[::23]:
+        acc = ctx.vote_debug_accumulator(table_from_oracle_features, dev_crop, int(h["scene_index"]))
+        flat = int(np.argmax(acc))
+        assert h["votes"] == acc.reshape(-1)[flat]
+        if h["votes"]:
+            assert (int(h["model_index"]), int(h["alpha_bin"])) == divmod(flat, acc.shape[1])
+        # and its pose is the oracle's pose for that peak
+        P = oracle.peak_pose(bottle, int(h["model_index"]), int(h["alpha_bin"]), scene_crop, int(h["scene_index"]),
+                             ANGLE_STEP)
+        assert np.abs(P.reshape(-1) - h["pose"]).max() < 2e-5
+
+
+def test_k3_sharding_invariance(ctx, dev_bottle, dev_crop, table_fused):
+    """Reference points are independent: any split of the index set gives the same records."""
+    full = ctx.vote(dev_bottle, table_fused, dev_crop, 0, 1)
+    n = len(full)
+    parts = []
+    for g in range(4):
+        lo, hi = g * n // 4, (g + 1) * n // 4
+        parts.append(ctx.vote(dev_bottle, table_fused, dev_crop, lo, 1, hi - lo))
+    cat = np.concatenate(parts)
+    assert cat.tobytes() == full.tobytes()
+    strided = ctx.vote(dev_bottle, table_fused, dev_crop, 3, 7)
+    assert strided.tobytes() == full[3::7].tobytes()
+
+
+def test_k3_alpha_bins_on_device(ctx):
+    from yolo_ppf_pose_estimation_b200 import capi
+    rng = np.random.default_rng(5)
+    am = rng.uniform(-np.pi, np.pi, 1 << 20).astype(np.float32)
+    as_ = rng.uniform(-np.pi, np.pi, 1 << 20).astype(np.float32)
+    for step in (ANGLE_STEP, np.float32(0.25), np.float32(np.pi / 180)):
+        for mode in (0, 1):
+            fd, ed = capi.debug_alpha_bins(am, as_, step, mode, ctx)
+            fh, eh = capi.debug_alpha_bins(am, as_, step, mode, None)
+            assert np.array_equal(fd, ed) and np.array_equal(ed, eh) and np.array_equal(fh, eh)
+
+
+def test_k3_alpha_mode_b(bottle, scene_crop, oracle, oracle_bottle):
+    from yolo_ppf_pose_estimation_b200 import capi
+    feats, hm = oracle_bottle
+    c = capi.Context(0, alpha_mode=capi.ALPHA_MODE_B)
+    t = c.table_build(c.features_upload(feats), ANGLE_STEP, DIST_STEP)
+    ds = c.upload_cloud(scene_crop)
+    for s_r in (5, 600):
+        inr, d, a = c.vote_debug_pairs(t, ds, s_r)
+        acc = c.vote_debug_accumulator(t, ds, s_r)
+        ref, _ = hm.vote_accumulate_from_pairs(bottle.shape[0], d[inr > 0], a[inr > 0], alpha_mode=oracle.ALPHA_MODE_B)
+        assert np.array_equal(acc, ref)
+
+
+# ---- K4 / K5 / align ------------------------------------------------------------------------------
+
+def test_k4_cluster_vs_oracle(ctx, bottle, scene_crop, oracle, oracle_bottle):
+    _, hm = oracle_bottle
+    hyps, _ = hm.vote(bottle, scene_crop, 0, 1, n_threads=oracle.max_threads())
+    for pos_thr, rot_thr in ((0.01, 20 / 180 * np.pi), (0.006, 12 / 180 * np.pi), (0.2, 30 / 180 * np.pi)):
+        poses, votes = ctx.cluster(hyps, pos_thr, rot_thr)
+        rposes, rvotes, rassign, rncl = oracle.cluster(hyps, pos_thr, rot_thr)
+        assign, ncl = ctx.cluster_assignment(len(hyps))
+        assert ncl == rncl
+        assert np.array_equal(assign, rassign)
+        assert np.array_equal(votes, rvotes)
+        assert np.abs(poses - rposes).max() < 1e-5
+
+
+def test_k4_small_and_degenerate(ctx, oracle):
+    from yolo_ppf_pose_estimation_b200.capi import HYP_DTYPE
+    h = np.zeros(1, HYP_DTYPE)
+    h["pose"][0] = np.eye(4, dtype=np.float32)[:3].reshape(-1)
+    h["votes"] = 7
+    poses, votes = ctx.cluster(h)
+    assert len(poses) == 1 and votes[0] == 7 and np.allclose(poses[0], np.eye(4), atol=1e-6)
+    # all-identical poses collapse into one cluster with summed votes
+    h = np.repeat(h, 2500)
+    h["votes"] = np.arange(2500) % 11
+    h["scene_index"] = np.arange(2500)
+    poses, votes = ctx.cluster(h)
+    rp, rv, ra, rn = oracle.cluster(h)
+    assert len(poses) == 1 and votes[0] == h["votes"].sum() == rv[0]
+    poses, votes = ctx.cluster(h[:0])
+    assert len(poses) == 0
+
+
+def test_k5_transform(ctx, bottle, dev_bottle, oracle):
+    M = np.eye(4, dtype=np.float32)
+    M[:3, :3] = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    M[:3, 3] = (0.1, -0.2, 0.3)
+    out = ctx.transform(dev_bottle, M)
+    assert np.array_equal(out, oracle.transform(bottle, M))
+
+
+def test_align_final_pose_vs_oracle(ctx, bottle, scene_crop, dev_bottle, dev_crop, oracle, oracle_bottle, table_fused):
+    """PPFRegistration::align end to end, device floats throughout: final pose within 1 mm / 0.5 deg."""
+    _, hm = oracle_bottle
+    final, poses, votes = ctx.register(dev_bottle, table_fused, dev_crop, ref_rate=5)
+    rfinal, rposes, rvotes, _ = hm.register(bottle, scene_crop, ref_rate=5, n_threads=oracle.max_threads())
+    dt, dr = parity.pose_error(final, rfinal)
+    assert dt < parity.POSE_T_TOL and dr < parity.POSE_R_TOL_DEG, (dt, dr)
+    assert len(poses) == len(rposes)
+    assert np.abs(votes.astype(np.int64) - rvotes.astype(np.int64)).max() <= 0.02 * rvotes.max() + 3
+
+
+def test_align_recovers_known_pose(ctx, bottle, dev_bottle, table_fused):
+    """Model matched against a rigidly moved copy of itself returns the motion (GT known exactly)."""
+    from scipy.spatial.transform import Rotation as Rot
+    R = Rot.from_rotvec([0.3, -0.5, 0.8]).as_matrix()
+    t = np.array([0.1, -0.05, 0.3])
+    s = bottle.astype(np.float64).copy()
+    s[:, :3] = s[:, :3] @ R.T + t
+    s[:, 3:] = s[:, 3:] @ R.T
+    final, _, _ = ctx.register(dev_bottle, table_fused, ctx.upload_cloud(s.astype(np.float32)), ref_rate=5)
+    G = np.eye(4)
+    G[:3, :3], G[:3, 3] = R, t
+    dt, dr = parity.pose_error(final, G)
+    assert dt < 3e-3 and dr < 1.0, (dt, dr)
+
+
+# ---- edge cases and errors ----------------------------------------------------------------------------
+
+def test_errors_and_edges(ctx, bottle, dev_bottle, dev_crop, table_fused):
+    from yolo_ppf_pose_estimation_b200.capi import B200PPFError
+    with pytest.raises(B200PPFError):  # reference range beyond the scene
+        ctx.vote(dev_bottle, table_fused, dev_crop, 0, 1, dev_crop.size + 1)
+    with pytest.raises(B200PPFError):  # model / table mismatch
+        ctx.vote(dev_crop, table_fused, dev_crop, 0, 1, 1)
+    with pytest.raises(B200PPFError):  # not n*n signatures
+        ctx.table_build(ctx.features_upload(np.zeros((10, 5), np.float32)), ANGLE_STEP, DIST_STEP)
+    with pytest.raises(B200PPFError):
+        ctx.table_build_from_cloud(dev_bottle, 0.0, DIST_STEP)
+    with pytest.raises(B200PPFError):  # discretisation too fine for 32-bit packed keys
+        ctx.table_build_from_cloud(dev_bottle, 1e-4, 1e-6)
+    # NaN points are dropped at upload
+    c = bottle[:50].copy()
+    c[3, 0] = np.nan
+    c[10, 4] = np.nan
+    assert ctx.upload_cloud(c).size == 48
+    # PointNormal layout (stride 12, normals at 4) == N x 6 layout
+    pn = np.zeros((bottle.shape[0], 12), np.float32)
+    pn[:, :3], pn[:, 3], pn[:, 4:7] = bottle[:, :3], 1.0, bottle[:, 3:]
+    a = ctx.vote(ctx.upload_cloud(pn), table_fused, dev_crop, 0, 50)
+    b = ctx.vote(dev_bottle, table_fused, dev_crop, 0, 50)
+    assert a.tobytes() == b.tobytes()
+    # duplicate points and a 2-point model: invalid pairs are skipped, nothing crashes
+    dup = np.concatenate([bottle[:40], bottle[:3]])
+    t = ctx.table_build_from_cloud(ctx.upload_cloud(dup), ANGLE_STEP, DIST_STEP)
+    assert t.info.n_entries <= 43 * 42 - 6
+    t2 = ctx.table_build_from_cloud(ctx.upload_cloud(bottle[:2]), ANGLE_STEP, DIST_STEP)
+    assert t2.info.n_entries <= 2
+    # a scene far away from everything: zero votes, hypotheses still emitted (PCL pushes one per reference)
+    far = bottle[:30].copy()
+    far[:, :3] = far[:, :3] * 100.0
+    hy = ctx.vote(dev_bottle, table_fused, ctx.upload_cloud(far), 0, 1)
+    assert len(hy) == 30 and (hy["votes"] == 0).all() and (hy["model_index"] == 0).all()

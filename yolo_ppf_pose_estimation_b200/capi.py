@@ -1,0 +1,394 @@
+"""ctypes binding of libb200ppf.so (include/b200ppf.h) — the only way Python reaches the kernels.
+
+There is no CPU fallback: loading fails loudly when the library has not been built, and
+Context() fails loudly when no sm_100 GPU is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+FEATURE_PCL_PFH, FEATURE_DROST_COS, FEATURE_DROST_ANGLE = 0, 1, 2
+ALPHA_MODE_A, ALPHA_MODE_B = 0, 1
+
+HYP_DTYPE = np.dtype(
+    [("pose", np.float32, (12,)), ("votes", np.uint32), ("model_index", np.uint32),
+     ("alpha_bin", np.uint32), ("scene_index", np.uint32)]
+)
+SIG_DTYPE = np.dtype([("f1", np.float32), ("f2", np.float32), ("f3", np.float32), ("f4", np.float32),
+                      ("alpha_m", np.float32)])
+assert HYP_DTYPE.itemsize == 64 and SIG_DTYPE.itemsize == 20
+
+
+class TableInfo(C.Structure):
+    _fields_ = [("n_model", C.c_uint64), ("n_entries", C.c_uint64), ("n_keys", C.c_uint64),
+                ("key_space", C.c_uint64), ("n_slices", C.c_uint32), ("slice_rows", C.c_uint32),
+                ("n_alpha", C.c_uint32), ("key_bits", C.c_uint32), ("lo", C.c_int32 * 4),
+                ("size", C.c_int32 * 4), ("angle_step", C.c_float), ("dist_step", C.c_float),
+                ("max_dist", C.c_float), ("reserved", C.c_float)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("upload_ms", "features_ms", "keys_ms", "sort_ms", "csr_ms", "vote_ms",
+                                         "pose_ms", "cluster_ms", "transform_ms", "download_ms")]
+
+
+# every symbol include/b200ppf.h declares: (name, restype, argtypes)
+_vp, _sz, _f, _i = C.c_void_p, C.c_size_t, C.c_float, C.c_int
+SYMBOLS = {
+    "b200ppf_create": (_i, [_i, C.POINTER(_vp)]),
+    "b200ppf_destroy": (None, [_vp]),
+    "b200ppf_last_error": (C.c_char_p, [_vp]),
+    "b200ppf_version": (_i, []),
+    "b200ppf_set_feature_mode": (_i, [_vp, _i]),
+    "b200ppf_set_alpha_mode": (_i, [_vp, _i]),
+    "b200ppf_get_device": (_i, [_vp]),
+    "b200ppf_get_stream": (_vp, [_vp]),
+    "b200ppf_synchronize": (_i, [_vp]),
+    "b200ppf_get_timings": (_i, [_vp, C.POINTER(Timings)]),
+    "b200ppf_launch_count": (C.c_uint64, [_vp]),
+    "b200ppf_cloud_upload": (_i, [_vp, _vp, _sz, _sz, _sz, C.POINTER(_vp)]),
+    "b200ppf_cloud_size": (_sz, [_vp]),
+    "b200ppf_cloud_free": (None, [_vp]),
+    "b200ppf_features_compute": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "b200ppf_features_upload": (_i, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200ppf_features_download": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    "b200ppf_features_count": (_sz, [_vp]),
+    "b200ppf_features_free": (None, [_vp]),
+    "b200ppf_table_build": (_i, [_vp, _vp, _f, _f, C.POINTER(_vp)]),
+    "b200ppf_table_build_from_cloud": (_i, [_vp, _vp, _f, _f, C.POINTER(_vp)]),
+    "b200ppf_table_get_info": (_i, [_vp, C.POINTER(TableInfo)]),
+    "b200ppf_table_query": (_i, [_vp, _vp, _f, _f, _f, _f, _vp, _sz, C.POINTER(_sz)]),
+    "b200ppf_table_query_key": (_i, [_vp, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "b200ppf_table_alpha_m": (_i, [_vp, _vp, _vp]),
+    "b200ppf_table_export": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200ppf_table_free": (None, [_vp]),
+    "b200ppf_vote": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "b200ppf_vote_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "b200ppf_vote_stats": (_i, [_vp, _vp]),
+    "b200ppf_vote_debug_pairs": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "b200ppf_vote_debug_accumulator": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "b200ppf_debug_alpha_bins": (_i, [_vp, _f, _i, _vp, _vp, _sz, _vp, _vp]),
+    "b200ppf_cluster": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
+    "b200ppf_cluster_device": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
+    "b200ppf_cluster_assignment": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "b200ppf_transform": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "b200ppf_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
+}
+
+_lib = None
+
+
+class B200PPFError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200ppf error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    """Load libb200ppf.so from the in-tree build directory (never from site-packages)."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} is missing: run `python -m yolo_ppf_pose_estimation_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU fallback.")
+        L = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError here == missing export
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _as_ptr(x):
+    """numpy array, int address (e.g. torch.Tensor.data_ptr()) or None -> c_void_p"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return _p(x)
+    return C.c_void_p(int(x))
+
+
+class Context:
+    """One GPU, one stream.  One context per process/rank."""
+
+    def __init__(self, device: int = 0, feature_mode: int = FEATURE_PCL_PFH, alpha_mode: int = ALPHA_MODE_A):
+        self._h = C.c_void_p()
+        rc = lib().b200ppf_create(device, C.byref(self._h))
+        if rc != 0:
+            raise B200PPFError(rc, lib().b200ppf_last_error(None).decode())
+        self.check(lib().b200ppf_set_feature_mode(self._h, feature_mode))
+        self.check(lib().b200ppf_set_alpha_mode(self._h, alpha_mode))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().b200ppf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise B200PPFError(rc, lib().b200ppf_last_error(self._h).decode())
+
+    @property
+    def device(self):
+        return lib().b200ppf_get_device(self._h)
+
+    @property
+    def stream(self):
+        return lib().b200ppf_get_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().b200ppf_launch_count(self._h))
+
+    def set_alpha_mode(self, mode):
+        self.check(lib().b200ppf_set_alpha_mode(self._h, mode))
+
+    def set_feature_mode(self, mode):
+        self.check(lib().b200ppf_set_feature_mode(self._h, mode))
+
+    def synchronize(self):
+        self.check(lib().b200ppf_synchronize(self._h))
+
+    def timings(self):
+        t = Timings()
+        self.check(lib().b200ppf_get_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    # ---- clouds -------------------------------------------------------------------------------
+    def upload_cloud(self, cloud, stride=None, normal_offset=None):
+        """cloud: (N, 6) [x y z nx ny nz] float32 (the reference's cv::Mat layout) or (N, 12) PointNormal."""
+        if isinstance(cloud, np.ndarray):
+            cloud = np.ascontiguousarray(cloud, np.float32)
+            n = cloud.shape[0]
+            stride = cloud.shape[1] if stride is None else stride
+            ptr = _p(cloud)
+        else:  # raw (pinned) host address
+            ptr, n = cloud
+            ptr = C.c_void_p(int(ptr))
+        if normal_offset is None:
+            normal_offset = 4 if stride == 12 else 3
+        h = C.c_void_p()
+        self.check(lib().b200ppf_cloud_upload(self._h, ptr, n, stride, normal_offset, C.byref(h)))
+        return Cloud(self, h)
+
+    # ---- K1 / K2 -------------------------------------------------------------------------------
+    def features_compute(self, model: "Cloud") -> "Features":
+        h = C.c_void_p()
+        self.check(lib().b200ppf_features_compute(self._h, model._h, C.byref(h)))
+        return Features(self, h)
+
+    def features_upload(self, feats) -> "Features":
+        feats = np.ascontiguousarray(feats, np.float32).reshape(-1, 5)
+        h = C.c_void_p()
+        self.check(lib().b200ppf_features_upload(self._h, _p(feats), feats.shape[0], C.byref(h)))
+        return Features(self, h)
+
+    def table_build(self, feats: "Features", angle_step, dist_step) -> "Table":
+        h = C.c_void_p()
+        self.check(lib().b200ppf_table_build(self._h, feats._h, np.float32(angle_step), np.float32(dist_step),
+                                             C.byref(h)))
+        return Table(self, h)
+
+    def table_build_from_cloud(self, model: "Cloud", angle_step, dist_step) -> "Table":
+        h = C.c_void_p()
+        self.check(lib().b200ppf_table_build_from_cloud(self._h, model._h, np.float32(angle_step),
+                                                        np.float32(dist_step), C.byref(h)))
+        return Table(self, h)
+
+    # ---- K3 -----------------------------------------------------------------------------------
+    def vote(self, model, table, scene, ref_first=0, ref_step=1, ref_count=None):
+        if ref_count is None:
+            ref_count = (scene.size - ref_first + ref_step - 1) // ref_step
+        hyps = np.zeros(ref_count, HYP_DTYPE)
+        self.check(lib().b200ppf_vote(self._h, model._h, table._h, scene._h, ref_first, ref_step, ref_count,
+                                      _p(hyps)))
+        return hyps
+
+    def vote_device(self, model, table, scene, ref_first, ref_step, ref_count, hyps_device_ptr):
+        """Asynchronous on the context stream; hyps_device_ptr is a device address (64 B per reference)."""
+        self.check(lib().b200ppf_vote_device(self._h, model._h, table._h, scene._h, ref_first, ref_step,
+                                             ref_count, _as_ptr(hyps_device_ptr)))
+
+    def vote_stats(self):
+        s = np.zeros(4, np.uint64)
+        self.check(lib().b200ppf_vote_stats(self._h, _p(s)))
+        return dict(zip(("pairs_examined", "pairs_in_radius", "nonempty_lookups", "votes"), (int(x) for x in s)))
+
+    def vote_debug_pairs(self, table, scene, s_r):
+        n = scene.size
+        inr = np.zeros(n, np.uint8)
+        d = np.zeros((n, 4), np.int32)
+        a = np.zeros(n, np.float32)
+        self.check(lib().b200ppf_vote_debug_pairs(self._h, table._h, scene._h, s_r, _p(inr), _p(d), _p(a)))
+        return inr, d, a
+
+    def vote_debug_accumulator(self, table, scene, s_r):
+        info = table.info
+        acc = np.zeros((info.n_model, info.n_alpha), np.uint32)
+        self.check(lib().b200ppf_vote_debug_accumulator(self._h, table._h, scene._h, s_r, _p(acc)))
+        return acc
+
+    # ---- K4 / K5 / align ------------------------------------------------------------------------
+    def cluster(self, hyps, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi, device_ptr=None, n=None):
+        poses = np.zeros((3, 16), np.float32)
+        votes = np.zeros(3, np.uint32)
+        k = C.c_size_t(0)
+        if device_ptr is not None:
+            self.check(lib().b200ppf_cluster_device(self._h, _as_ptr(device_ptr), n, np.float32(pos_thr),
+                                                    np.float32(rot_thr), _p(poses), _p(votes), C.byref(k)))
+        else:
+            hyps = np.ascontiguousarray(hyps, HYP_DTYPE)
+            self.check(lib().b200ppf_cluster(self._h, _p(hyps), hyps.shape[0], np.float32(pos_thr),
+                                             np.float32(rot_thr), _p(poses), _p(votes), C.byref(k)))
+        return poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
+
+    def cluster_assignment(self, n):
+        a = np.zeros(n, np.uint32)
+        ncl = C.c_size_t(0)
+        self.check(lib().b200ppf_cluster_assignment(self._h, _p(a), n, C.byref(ncl)))
+        return a, int(ncl.value)
+
+    def transform(self, cloud, pose16):
+        M = np.ascontiguousarray(pose16, np.float32).reshape(16)
+        out = np.zeros((cloud.size, 3), np.float32)
+        self.check(lib().b200ppf_transform(self._h, cloud._h, _p(M), _p(out), 3))
+        return out
+
+    def register(self, model, table, scene, ref_rate=5, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
+        final = np.zeros(16, np.float32)
+        poses = np.zeros((3, 16), np.float32)
+        votes = np.zeros(3, np.uint32)
+        k = C.c_size_t(0)
+        self.check(lib().b200ppf_register(self._h, model._h, table._h, scene._h, ref_rate, np.float32(pos_thr),
+                                          np.float32(rot_thr), _p(final), _p(poses), _p(votes), C.byref(k)))
+        return final.reshape(4, 4), poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
+
+
+def debug_alpha_bins(alpha_m, alpha_s, angle_step, alpha_mode=ALPHA_MODE_A, ctx: "Context | None" = None):
+    """(fast, exact) alpha bins; host build of the inline functions when ctx is None, device otherwise."""
+    am = np.ascontiguousarray(alpha_m, np.float32)
+    as_ = np.ascontiguousarray(alpha_s, np.float32)
+    fast = np.zeros(am.shape[0], np.uint32)
+    exact = np.zeros(am.shape[0], np.uint32)
+    rc = lib().b200ppf_debug_alpha_bins(ctx._h if ctx else None, np.float32(angle_step), alpha_mode, _p(am), _p(as_),
+                                        am.shape[0], _p(fast), _p(exact))
+    if rc != 0:
+        raise B200PPFError(rc, lib().b200ppf_last_error(ctx._h if ctx else None).decode())
+    return fast, exact
+
+
+class _Handle:
+    _free = None
+
+    def __init__(self, ctx, h):
+        self.ctx, self._h = ctx, h
+
+    def free(self):
+        if self._h is not None and self._h.value:
+            getattr(lib(), self._free)(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Cloud(_Handle):
+    _free = "b200ppf_cloud_free"
+
+    @property
+    def size(self):
+        return int(lib().b200ppf_cloud_size(self._h))
+
+
+class Features(_Handle):
+    _free = "b200ppf_features_free"
+
+    @property
+    def count(self):
+        return int(lib().b200ppf_features_count(self._h))
+
+    def download(self, first=0, count=None):
+        count = self.count - first if count is None else count
+        out = np.zeros((count, 5), np.float32)
+        self.ctx.check(lib().b200ppf_features_download(self.ctx._h, self._h, first, count, _p(out)))
+        return out
+
+
+class Table(_Handle):
+    _free = "b200ppf_table_free"
+
+    @property
+    def info(self) -> TableInfo:
+        ti = TableInfo()
+        self.ctx.check(lib().b200ppf_table_get_info(self._h, C.byref(ti)))
+        return ti
+
+    def query(self, f1, f2, f3, f4):
+        cap = 4096
+        while True:
+            out = np.zeros((cap, 2), np.uint64)
+            n = C.c_size_t(0)
+            self.ctx.check(lib().b200ppf_table_query(self.ctx._h, self._h, f1, f2, f3, f4, _p(out), cap, C.byref(n)))
+            if n.value <= cap:
+                return out[:n.value]
+            cap = n.value
+
+    def query_key(self, d):
+        d = np.ascontiguousarray(d, np.int32)
+        cap = 4096
+        while True:
+            out = np.zeros((cap, 2), np.uint64)
+            n = C.c_size_t(0)
+            self.ctx.check(lib().b200ppf_table_query_key(self.ctx._h, self._h, _p(d), _p(out), cap, C.byref(n)))
+            if n.value <= cap:
+                return out[:n.value]
+            cap = n.value
+
+    def alpha_m(self):
+        n = self.info.n_model
+        out = np.zeros((n, n), np.float32)
+        self.ctx.check(lib().b200ppf_table_alpha_m(self.ctx._h, self._h, _p(out)))
+        return out
+
+    def export(self):
+        """-> offsets (n_slices*key_space+1), entry_i, entry_j, entry_alpha_m"""
+        ti = self.info
+        off = np.zeros(ti.n_slices * ti.key_space + 1, np.uint32)
+        ei = np.zeros(ti.n_entries, np.uint32)
+        ej = np.zeros(ti.n_entries, np.uint32)
+        ea = np.zeros(ti.n_entries, np.float32)
+        self.ctx.check(lib().b200ppf_table_export(self.ctx._h, self._h, _p(off), _p(ei), _p(ej), _p(ea)))
+        return off, ei, ej, ea
+
+    def unpack_key(self, packed):
+        """packed key (within one slice) -> the four quantised components PCL hashes"""
+        ti = self.info
+        packed = np.asarray(packed, np.int64)
+        c = packed % ti.size[2]
+        r = packed // ti.size[2]
+        b = r % ti.size[1]
+        r = r // ti.size[1]
+        a = r % ti.size[0]
+        e = r // ti.size[0]
+        return np.stack([a + ti.lo[0], b + ti.lo[1], c + ti.lo[2], e + ti.lo[3]], axis=-1).astype(np.int32)

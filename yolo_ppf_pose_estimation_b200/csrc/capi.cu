@@ -1,0 +1,497 @@
+// capi.cu — the extern "C" surface declared in include/b200ppf.h.
+#include <cmath>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "ppf_common.cuh"
+
+namespace b200ppf {
+
+static std::mutex g_err_mutex;
+static std::string g_error;
+
+int fail_msg(b200ppf_ctx *ctx, int code, const char *msg) {
+    if (ctx) ctx->error = msg;
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    g_error = msg;
+    return code;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace b200ppf
+
+using namespace b200ppf;
+
+#define CHECK_CTX(ctx)                                   \
+    if (!(ctx)) return fail_msg(nullptr, B200PPF_ERR_INVALID, "null context"); \
+    DeviceGuard _guard((ctx)->device)
+
+extern "C" {
+
+int b200ppf_version(void) { return B200PPF_VERSION; }
+
+int b200ppf_create(int device, b200ppf_ctx **out) {
+    if (!out) return fail_msg(nullptr, B200PPF_ERR_INVALID, "b200ppf_create: null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail_msg(nullptr, B200PPF_ERR_CUDA,
+                        "b200ppf_create: no CUDA device is visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail_msg(nullptr, B200PPF_ERR_INVALID, "b200ppf_create: device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail_msg(nullptr, B200PPF_ERR_CUDA, "b200ppf_create: cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail_msg(nullptr, B200PPF_ERR_UNSUPPORTED,
+                        "b200ppf_create: kernels are built for sm_100a (Blackwell B200) only");
+    b200ppf_ctx *ctx = new (std::nothrow) b200ppf_ctx();
+    if (!ctx) return fail_msg(nullptr, B200PPF_ERR_NOMEM, "b200ppf_create: out of host memory");
+    ctx->device = device;
+    DeviceGuard guard(device);
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail_msg(nullptr, B200PPF_ERR_CUDA, "b200ppf_create: cudaStreamCreate failed");
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return B200PPF_OK;
+}
+
+void b200ppf_destroy(b200ppf_ctx *ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->d_peaks) cudaFree(ctx->d_peaks);
+    if (ctx->d_hyps) cudaFree(ctx->d_hyps);
+    if (ctx->d_assign) cudaFree(ctx->d_assign);
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *b200ppf_last_error(const b200ppf_ctx *ctx) {
+    if (ctx) return ctx->error.c_str();
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_error;
+    return copy.c_str();
+}
+
+int b200ppf_set_feature_mode(b200ppf_ctx *ctx, int mode) {
+    if (!ctx) return fail_msg(nullptr, B200PPF_ERR_INVALID, "null context");
+    if (mode < 0 || mode > 2) return fail_msg(ctx, B200PPF_ERR_INVALID, "unknown feature mode");
+    ctx->feature_mode = mode;
+    return B200PPF_OK;
+}
+
+int b200ppf_set_alpha_mode(b200ppf_ctx *ctx, int mode) {
+    if (!ctx) return fail_msg(nullptr, B200PPF_ERR_INVALID, "null context");
+    if (mode < 0 || mode > 1) return fail_msg(ctx, B200PPF_ERR_INVALID, "unknown alpha mode");
+    ctx->alpha_mode = mode;
+    return B200PPF_OK;
+}
+
+int b200ppf_get_device(const b200ppf_ctx *ctx) { return ctx ? ctx->device : -1; }
+void *b200ppf_get_stream(const b200ppf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t b200ppf_launch_count(const b200ppf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b200ppf_synchronize(b200ppf_ctx *ctx) {
+    CHECK_CTX(ctx);
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200PPF_OK;
+}
+
+int b200ppf_get_timings(const b200ppf_ctx *ctx, b200ppf_timings *out) {
+    if (!ctx || !out) return fail_msg(nullptr, B200PPF_ERR_INVALID, "null argument");
+    *out = ctx->timings;
+    return B200PPF_OK;
+}
+
+/* ---- clouds ------------------------------------------------------------------------------- */
+
+int b200ppf_cloud_upload(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride, size_t noff,
+                         b200ppf_cloud **out) {
+    CHECK_CTX(ctx);
+    if (!out) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: null output pointer");
+    *out = nullptr;
+    if (n && !host) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: null host pointer");
+    if (stride < 6 || noff < 3 || noff + 3 > stride)
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: stride/normal offset do not describe [x y z .. nx ny nz]");
+    // AoS -> float4 SoA staging (pinned), dropping NaN points (SURVEY.md A.8 rule 5)
+    float4 *stage = nullptr;
+    PPF_CUDA(ctx, cudaMallocHost(&stage, std::max<size_t>(1, 2 * n) * sizeof(float4)));
+    b200ppf_cloud *c = new (std::nothrow) b200ppf_cloud();
+    if (!c) {
+        cudaFreeHost(stage);
+        return fail_msg(ctx, B200PPF_ERR_NOMEM, "cloud upload: out of host memory");
+    }
+    c->ctx = ctx;
+    size_t m = 0;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float4 *sp = stage, *sn = stage + n;
+    for (size_t i = 0; i < n; ++i) {
+        const float *p = host + i * stride, *q = p + noff;
+        if (std::isnan(p[0]) || std::isnan(p[1]) || std::isnan(p[2]) || std::isnan(q[0]) || std::isnan(q[1]) ||
+            std::isnan(q[2]))
+            continue;
+        sp[m] = make_float4(p[0], p[1], p[2], 1.0f);
+        sn[m] = make_float4(q[0], q[1], q[2], 0.0f);
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], p[k]);
+            hi[k] = std::max(hi[k], p[k]);
+        }
+        ++m;
+    }
+    c->n = m;
+    for (int k = 0; k < 3; ++k) {
+        c->bbox_min[k] = m ? lo[k] : 0.0f;
+        c->bbox_max[k] = m ? hi[k] : 0.0f;
+    }
+    cudaError_t e = cudaMalloc(&c->pos, std::max<size_t>(1, m) * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&c->nrm, std::max<size_t>(1, m) * sizeof(float4));
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (e == cudaSuccess && m) e = cudaMemcpyAsync(c->pos, sp, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && m) e = cudaMemcpyAsync(c->nrm, sn, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(stage);
+    if (e != cudaSuccess) {
+        b200ppf_cloud_free(c);
+        return fail_msg(ctx, e == cudaErrorMemoryAllocation ? B200PPF_ERR_NOMEM : B200PPF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaEventElapsedTime(&ctx->timings.upload_ms, ctx->ev[0], ctx->ev[1]);
+    *out = c;
+    return B200PPF_OK;
+}
+
+size_t b200ppf_cloud_size(const b200ppf_cloud *cloud) { return cloud ? cloud->n : 0; }
+
+void b200ppf_cloud_free(b200ppf_cloud *c) {
+    if (!c) return;
+    DeviceGuard guard(c->ctx ? c->ctx->device : 0);
+    if (c->pos) cudaFree(c->pos);
+    if (c->nrm) cudaFree(c->nrm);
+    delete c;
+}
+
+/* ---- K1 ----------------------------------------------------------------------------------- */
+
+int b200ppf_features_compute(b200ppf_ctx *ctx, const b200ppf_cloud *model, b200ppf_features **out) {
+    CHECK_CTX(ctx);
+    if (!model || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "features compute: null argument");
+    *out = nullptr;
+    if (model->n > 65535) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "features compute: more than 65535 model points");
+    b200ppf_features *f = new (std::nothrow) b200ppf_features();
+    if (!f) return fail_msg(ctx, B200PPF_ERR_NOMEM, "features compute: out of host memory");
+    f->ctx = ctx;
+    f->count = model->n * model->n;
+    cudaError_t e = cudaMalloc(&f->d, std::max<size_t>(1, f->count) * sizeof(b200ppf_signature));
+    if (e != cudaSuccess) {
+        delete f;
+        return fail_msg(ctx, B200PPF_ERR_NOMEM, "features compute: device allocation of the N*N*20-byte feature cloud failed");
+    }
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    int rc = k1_features_compute(ctx, model, f->d);
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (rc == B200PPF_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        rc = fail_msg(ctx, B200PPF_ERR_CUDA, "features compute: kernel failed");
+    if (rc != B200PPF_OK) {
+        b200ppf_features_free(f);
+        return rc;
+    }
+    cudaEventElapsedTime(&ctx->timings.features_ms, ctx->ev[0], ctx->ev[1]);
+    *out = f;
+    return B200PPF_OK;
+}
+
+int b200ppf_features_upload(b200ppf_ctx *ctx, const b200ppf_signature *host, size_t count, b200ppf_features **out) {
+    CHECK_CTX(ctx);
+    if (!out || (count && !host)) return fail_msg(ctx, B200PPF_ERR_INVALID, "features upload: null argument");
+    *out = nullptr;
+    b200ppf_features *f = new (std::nothrow) b200ppf_features();
+    if (!f) return fail_msg(ctx, B200PPF_ERR_NOMEM, "features upload: out of host memory");
+    f->ctx = ctx;
+    f->count = count;
+    cudaError_t e = cudaMalloc(&f->d, std::max<size_t>(1, count) * sizeof(b200ppf_signature));
+    if (e == cudaSuccess && count)
+        e = cudaMemcpyAsync(f->d, host, count * sizeof(b200ppf_signature), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        b200ppf_features_free(f);
+        return fail_msg(ctx, e == cudaErrorMemoryAllocation ? B200PPF_ERR_NOMEM : B200PPF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = f;
+    return B200PPF_OK;
+}
+
+int b200ppf_features_download(b200ppf_ctx *ctx, const b200ppf_features *f, size_t first, size_t count,
+                              b200ppf_signature *host) {
+    CHECK_CTX(ctx);
+    if (!f || (count && !host)) return fail_msg(ctx, B200PPF_ERR_INVALID, "features download: null argument");
+    if (first > f->count || count > f->count - first)
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "features download: range exceeds the feature cloud");
+    if (count) {
+        PPF_CUDA(ctx, cudaMemcpyAsync(host, f->d + first, count * sizeof(b200ppf_signature), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return B200PPF_OK;
+}
+
+size_t b200ppf_features_count(const b200ppf_features *f) { return f ? f->count : 0; }
+
+void b200ppf_features_free(b200ppf_features *f) {
+    if (!f) return;
+    DeviceGuard guard(f->ctx ? f->ctx->device : 0);
+    if (f->d) cudaFree(f->d);
+    delete f;
+}
+
+/* ---- K2 ----------------------------------------------------------------------------------- */
+
+int b200ppf_table_build(b200ppf_ctx *ctx, const b200ppf_features *f, float angle_step, float dist_step,
+                        b200ppf_table **out) {
+    CHECK_CTX(ctx);
+    if (!f || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: null argument");
+    *out = nullptr;
+    return k2_build(ctx, f, nullptr, angle_step, dist_step, out);
+}
+
+int b200ppf_table_build_from_cloud(b200ppf_ctx *ctx, const b200ppf_cloud *model, float angle_step, float dist_step,
+                                   b200ppf_table **out) {
+    CHECK_CTX(ctx);
+    if (!model || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: null argument");
+    *out = nullptr;
+    return k2_build(ctx, nullptr, model, angle_step, dist_step, out);
+}
+
+int b200ppf_table_get_info(const b200ppf_table *t, b200ppf_table_info *info) {
+    if (!t || !info) return fail_msg(nullptr, B200PPF_ERR_INVALID, "table info: null argument");
+    *info = t->info;
+    return B200PPF_OK;
+}
+
+int b200ppf_table_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int32_t *d4, uint64_t *pairs, size_t cap,
+                            size_t *n_found) {
+    CHECK_CTX(ctx);
+    if (!t || !d4 || !n_found || (cap && !pairs)) return fail_msg(ctx, B200PPF_ERR_INVALID, "table query: null argument");
+    return k2_query_key(ctx, t, d4, pairs, cap, n_found);
+}
+
+int b200ppf_table_query(b200ppf_ctx *ctx, const b200ppf_table *t, float f1, float f2, float f3, float f4,
+                        uint64_t *pairs, size_t cap, size_t *n_found) {
+    CHECK_CTX(ctx);
+    if (!t || !n_found || (cap && !pairs)) return fail_msg(ctx, B200PPF_ERR_INVALID, "table query: null argument");
+    *n_found = 0;
+    const float f[4] = {f1, f2, f3, f4};
+    if (std::isnan(f1) || std::isnan(f2) || std::isnan(f3) || std::isnan(f4)) return B200PPF_OK;
+    int d[4];
+    quantise(t->kp, f, d);  // same IEEE divide + floor as the device
+    return k2_query_key(ctx, t, d, pairs, cap, n_found);
+}
+
+int b200ppf_table_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host) {
+    CHECK_CTX(ctx);
+    if (!t || !host) return fail_msg(ctx, B200PPF_ERR_INVALID, "alpha_m export: null argument");
+    return k2_alpha_m(ctx, t, host);
+}
+
+int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *offsets, uint32_t *entry_i,
+                         uint32_t *entry_j, float *entry_alpha_m) {
+    CHECK_CTX(ctx);
+    if (!t) return fail_msg(ctx, B200PPF_ERR_INVALID, "table export: null table");
+    const size_t total = (size_t)t->info.key_space * t->info.n_slices + 1, ne = t->info.n_entries;
+    if (offsets) PPF_CUDA(ctx, cudaMemcpyAsync(offsets, t->offsets, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> idx;
+    std::vector<uint2> ent;
+    if ((entry_i || entry_j) && ne) {
+        idx.resize(ne);
+        PPF_CUDA(ctx, cudaMemcpyAsync(idx.data(), t->entry_idx, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (entry_alpha_m && ne) {
+        ent.resize(ne);
+        PPF_CUDA(ctx, cudaMemcpyAsync(ent.data(), t->entries, ne * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t n = (uint32_t)t->info.n_model;
+    for (size_t e = 0; e < idx.size(); ++e) {
+        if (entry_i) entry_i[e] = idx[e] / n;
+        if (entry_j) entry_j[e] = idx[e] % n;
+    }
+    for (size_t e = 0; e < ent.size(); ++e) memcpy(&entry_alpha_m[e], &ent[e].y, sizeof(float));
+    return B200PPF_OK;
+}
+
+void b200ppf_table_free(b200ppf_table *t) {
+    if (!t) return;
+    DeviceGuard guard(t->ctx ? t->ctx->device : 0);
+    if (t->offsets) cudaFree(t->offsets);
+    if (t->entries) cudaFree(t->entries);
+    if (t->entry_idx) cudaFree(t->entry_idx);
+    delete t;
+}
+
+/* ---- K3 ----------------------------------------------------------------------------------- */
+
+int b200ppf_vote_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
+                        const b200ppf_cloud *scene, size_t ref_first, size_t ref_step, size_t ref_count,
+                        b200ppf_hypothesis *hyps_device) {
+    CHECK_CTX(ctx);
+    if (ref_count && !hyps_device) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: null output pointer");
+    return k3_vote(ctx, model, t, scene, ref_first, ref_step, ref_count, hyps_device);
+}
+
+int b200ppf_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
+                 size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *hyps_host) {
+    CHECK_CTX(ctx);
+    if (ref_count && !hyps_host) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: null output pointer");
+    if (ctx->hyps_cap < ref_count) {
+        if (ctx->d_hyps) cudaFree(ctx->d_hyps);
+        ctx->d_hyps = nullptr;
+        ctx->hyps_cap = 0;
+        PPF_CUDA(ctx, cudaMalloc(&ctx->d_hyps, ref_count * sizeof(b200ppf_hypothesis)));
+        ctx->hyps_cap = ref_count;
+    }
+    int rc = k3_vote(ctx, model, t, scene, ref_first, ref_step, ref_count, ctx->d_hyps);
+    if (rc) return rc;
+    if (ref_count)
+        PPF_CUDA(ctx, cudaMemcpyAsync(hyps_host, ctx->d_hyps, ref_count * sizeof(b200ppf_hypothesis),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ref_count) {
+        cudaEventElapsedTime(&ctx->timings.vote_ms, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->timings.pose_ms, ctx->ev[1], ctx->ev[2]);
+    }
+    return B200PPF_OK;
+}
+
+int b200ppf_vote_stats(b200ppf_ctx *ctx, uint64_t *stats4) {
+    CHECK_CTX(ctx);
+    if (!stats4) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote stats: null output pointer");
+    stats4[0] = stats4[1] = stats4[2] = stats4[3] = 0;
+    if (!ctx->d_stats) return B200PPF_OK;
+    unsigned long long h[4];
+    PPF_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; ++k) stats4[k] = h[k];
+    return B200PPF_OK;
+}
+
+int b200ppf_vote_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
+                             uint8_t *in_radius, int32_t *d4, float *alpha_s) {
+    CHECK_CTX(ctx);
+    if (!in_radius || !d4 || !alpha_s) return fail_msg(ctx, B200PPF_ERR_INVALID, "debug pairs: null output pointer");
+    return k3_debug_pairs(ctx, t, scene, s_r, in_radius, d4, alpha_s);
+}
+
+int b200ppf_vote_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
+                                   uint32_t *acc) {
+    CHECK_CTX(ctx);
+    if (!acc) return fail_msg(ctx, B200PPF_ERR_INVALID, "debug accumulator: null output pointer");
+    return k3_debug_accumulator(ctx, t, scene, s_r, acc);
+}
+
+int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+                             const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact) {
+    if (!(angle_step > 0.0f) || alpha_mode < 0 || alpha_mode > 1 || (n && (!alpha_m || !alpha_s || !fast || !exact)))
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "debug alpha bins: bad argument");
+    if (n == 0) return B200PPF_OK;
+    if (!ctx) return k3_debug_alpha_bins(nullptr, angle_step, alpha_mode, alpha_m, alpha_s, n, fast, exact);
+    DeviceGuard guard(ctx->device);
+    return k3_debug_alpha_bins(ctx, angle_step, alpha_mode, alpha_m, alpha_s, n, fast, exact);
+}
+
+/* ---- K4 ----------------------------------------------------------------------------------- */
+
+int b200ppf_cluster_device(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n, float pos_thr,
+                           float rot_thr, float *poses16, uint32_t *votes, size_t *n_out) {
+    CHECK_CTX(ctx);
+    if (!poses16 || !votes || !n_out || (n && !hyps_device)) return fail_msg(ctx, B200PPF_ERR_INVALID, "cluster: null argument");
+    return k4_cluster(ctx, hyps_device, n, pos_thr, rot_thr, poses16, votes, n_out);
+}
+
+int b200ppf_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_host, size_t n, float pos_thr, float rot_thr,
+                    float *poses16, uint32_t *votes, size_t *n_out) {
+    CHECK_CTX(ctx);
+    if (!poses16 || !votes || !n_out || (n && !hyps_host)) return fail_msg(ctx, B200PPF_ERR_INVALID, "cluster: null argument");
+    *n_out = 0;
+    if (n == 0) return B200PPF_OK;
+    b200ppf_hypothesis *d = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&d, n * sizeof(b200ppf_hypothesis), ctx->stream));
+    PPF_CUDA(ctx, cudaMemcpyAsync(d, hyps_host, n * sizeof(b200ppf_hypothesis), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = k4_cluster(ctx, d, n, pos_thr, rot_thr, poses16, votes, n_out);
+    cudaFreeAsync(d, ctx->stream);
+    return rc;
+}
+
+int b200ppf_cluster_assignment(b200ppf_ctx *ctx, uint32_t *assignment, size_t n, size_t *n_clusters) {
+    CHECK_CTX(ctx);
+    if (n_clusters) *n_clusters = ctx->n_clusters;
+    if (!assignment) return B200PPF_OK;
+    if (n != ctx->assign_n || !ctx->d_assign)
+        return fail_msg(ctx, B200PPF_ERR_STATE, "cluster assignment: size does not match the last cluster call");
+    PPF_CUDA(ctx, cudaMemcpyAsync(assignment, ctx->d_assign, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200PPF_OK;
+}
+
+/* ---- K5 ----------------------------------------------------------------------------------- */
+
+int b200ppf_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose16, float *out_host,
+                      size_t out_stride_floats) {
+    CHECK_CTX(ctx);
+    if (!cloud || !pose16 || (cloud->n && !out_host)) return fail_msg(ctx, B200PPF_ERR_INVALID, "transform: null argument");
+    return k5_transform(ctx, cloud, pose16, out_host, out_stride_floats);
+}
+
+/* ---- align -------------------------------------------------------------------------------- */
+
+int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
+                     const b200ppf_cloud *scene, size_t ref_rate, float pos_thr, float rot_thr, float *final16,
+                     float *poses16, uint32_t *votes, size_t *n_out) {
+    CHECK_CTX(ctx);
+    if (!scene || !poses16 || !votes || !n_out) return fail_msg(ctx, B200PPF_ERR_INVALID, "register: null argument");
+    *n_out = 0;
+    if (ref_rate == 0) ref_rate = 1;
+    const size_t ref_count = (scene->n + ref_rate - 1) / ref_rate;
+    if (ref_count == 0) return fail_msg(ctx, B200PPF_ERR_STATE, "register: empty scene");
+    if (ctx->hyps_cap < ref_count) {
+        if (ctx->d_hyps) cudaFree(ctx->d_hyps);
+        ctx->d_hyps = nullptr;
+        ctx->hyps_cap = 0;
+        PPF_CUDA(ctx, cudaMalloc(&ctx->d_hyps, ref_count * sizeof(b200ppf_hypothesis)));
+        ctx->hyps_cap = ref_count;
+    }
+    int rc = k3_vote(ctx, model, t, scene, 0, ref_rate, ref_count, ctx->d_hyps);
+    if (rc) return rc;
+    cudaEvent_t v0 = ctx->ev[0], v1 = ctx->ev[1], v2 = ctx->ev[2];
+    // k4 reuses ev[0..1]; take the vote timings first
+    PPF_CUDA(ctx, cudaEventSynchronize(v2));
+    cudaEventElapsedTime(&ctx->timings.vote_ms, v0, v1);
+    cudaEventElapsedTime(&ctx->timings.pose_ms, v1, v2);
+    rc = k4_cluster(ctx, ctx->d_hyps, ref_count, pos_thr, rot_thr, poses16, votes, n_out);
+    if (rc) return rc;
+    if (*n_out && final16) memcpy(final16, poses16, 16 * sizeof(float));
+    return B200PPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,491 @@
+// k2_table.cu — K2: the model hash table as a radix-sorted CSR (replaces PPFHashMapSearch).
+//
+// [PCL] registration/src/ppf_registration.cpp PPFHashMapSearch::setInputFeatureCloud builds an
+// unordered_multimap<HashKeyStruct,(i,j)> with one heap node per ordered model pair plus the
+// alpha_m_[i][j] matrix.  Here:
+//   keys    quantise exactly as PCL: d = floor(f / step) per component, packed densely into one
+//           32-bit integer (no hashing, hence no collisions), prefixed by the accumulator slice
+//           of model row i so that one CSR serves every slice;
+//   sort    stable LSD radix sort of (key, pair index, alpha_m)  -> buckets ascend in (i, j),
+//           the canonical order nearestNeighborSearch reports;
+//   CSR     offsets[key] by binary search over the sorted keys; entries {row offset, alpha_m}
+//           8 bytes each — all the voting kernel gathers; j survives only in entry_idx.
+// NaN signatures (diagonal / failed pairs) are dropped: no finite query can reach the key PCL
+// files them under (A.3).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "ppf_common.cuh"
+
+namespace b200ppf {
+
+namespace {
+
+constexpr uint32_t INVALID_KEY = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t slice_of(uint32_t i, uint32_t slice_rows) { return i / slice_rows; }
+
+// per-component min/max of the quantised features and max f4 (table built from a feature cloud)
+__global__ void feature_range_kernel(const float *__restrict__ feats, size_t count, float angle_step,
+                                     float dist_step, int *__restrict__ range /* lo[4], hi[4] */,
+                                     int *__restrict__ max_f4_bits) {
+    int lo[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX}, hi[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};
+    int mx = -1;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < count; p += (size_t)gridDim.x * blockDim.x) {
+        const float *s = feats + p * 5;
+        float f[4] = {s[0], s[1], s[2], s[3]};
+        if (f[0] != f[0] || f[1] != f[1] || f[2] != f[2] || f[3] != f[3]) continue;
+        int d[4];
+        d[0] = (int)floorf(f[0] / angle_step);
+        d[1] = (int)floorf(f[1] / angle_step);
+        d[2] = (int)floorf(f[2] / angle_step);
+        d[3] = (int)floorf(f[3] / dist_step);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lo[k] = min(lo[k], d[k]);
+            hi[k] = max(hi[k], d[k]);
+        }
+        if (f[3] > 0.0f) mx = max(mx, __float_as_int(f[3]));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = min(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], o));
+            hi[k] = max(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], o));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (lo[k] != INT_MAX) atomicMin(&range[k], lo[k]);
+            if (hi[k] != INT_MIN) atomicMax(&range[4 + k], hi[k]);
+        }
+        if (mx >= 0) atomicMax(max_f4_bits, mx);
+    }
+}
+
+// keys + alpha from a materialised feature cloud
+__global__ void keys_from_features_kernel(const float *__restrict__ feats, uint32_t n, KeyParams kp,
+                                          uint32_t *__restrict__ keys, uint32_t *__restrict__ alpha_bits) {
+    const size_t count = (size_t)n * n;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < count; p += (size_t)gridDim.x * blockDim.x) {
+        const float *s = feats + p * 5;
+        float f[4] = {s[0], s[1], s[2], s[3]};
+        uint32_t key = INVALID_KEY;
+        if (f[0] == f[0] && f[1] == f[1] && f[2] == f[2] && f[3] == f[3]) {
+            int d[4];
+            quantise(kp, f, d);
+            uint32_t k;
+            if (pack_key(kp, d, k)) key = slice_of((uint32_t)(p / n), kp.slice_rows) * kp.key_space + k;
+        }
+        keys[p] = key;
+        alpha_bits[p] = __float_as_uint(s[4]);
+    }
+}
+
+// K1+K2 fused: keys + alpha straight from the model cloud (no 20-byte signatures in HBM).
+// Same tiling as K1: TI reference rows (point + frame in shared memory) x 256 j per block.
+constexpr int FTI = 4;
+constexpr int FTJ = 256;
+struct RefStage {
+    float px, py, pz, nx, ny, nz;
+    Frame F;
+};
+
+__global__ void __launch_bounds__(FTJ)
+keys_from_cloud_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, uint32_t n, int feature_mode,
+                       KeyParams kp, uint32_t *__restrict__ keys, uint32_t *__restrict__ alpha_bits,
+                       int *__restrict__ max_f4_bits, int *__restrict__ out_of_range) {
+    __shared__ RefStage ref[FTI];
+    const uint32_t i0 = blockIdx.y * FTI;
+    const uint32_t j = blockIdx.x * FTJ + threadIdx.x;
+    if (threadIdx.x < FTI && i0 + threadIdx.x < n) {
+        float4 p = pos[i0 + threadIdx.x], q = nrm[i0 + threadIdx.x];
+        RefStage &r = ref[threadIdx.x];
+        r.px = p.x; r.py = p.y; r.pz = p.z;
+        r.nx = q.x; r.ny = q.y; r.nz = q.z;
+        ref_frame(make_v3(p.x, p.y, p.z), make_v3(q.x, q.y, q.z), r.F);
+    }
+    float4 pj = make_float4(0, 0, 0, 0), nj = make_float4(0, 0, 0, 0);
+    if (j < n) {
+        pj = pos[j];
+        nj = nrm[j];
+    }
+    __syncthreads();
+    int mx = -1;
+#pragma unroll 1
+    for (int r = 0; r < FTI; ++r) {
+        const uint32_t i = i0 + r;
+        if (i >= n) break;
+        if (j < n) {
+            uint32_t key = INVALID_KEY;
+            float alpha = CUDART_NAN_F;
+            if (i != j) {
+                float f[4];
+                V3 pi = make_v3(ref[r].px, ref[r].py, ref[r].pz), ni = make_v3(ref[r].nx, ref[r].ny, ref[r].nz);
+                if (pair_features(feature_mode, pi, ni, v3_of(pj), v3_of(nj), f)) {
+                    alpha = planar_alpha(ref[r].F, v3_of(pj));
+                    int d[4];
+                    quantise(kp, f, d);
+                    uint32_t k;
+                    if (pack_key(kp, d, k)) key = slice_of(i, kp.slice_rows) * kp.key_space + k;
+                    else if (f[0] == f[0] && f[1] == f[1] && f[2] == f[2]) *out_of_range = 1;
+                    if (f[3] > 0.0f) mx = max(mx, __float_as_int(f[3]));
+                }
+            }
+            keys[(size_t)i * n + j] = key;
+            alpha_bits[(size_t)i * n + j] = __float_as_uint(alpha);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(max_f4_bits, mx);
+}
+
+// offsets[k] = first sorted position whose key is >= k, for k in [0, total_keys]
+__global__ void csr_offsets_kernel(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t total_keys,
+                                   uint32_t *__restrict__ offsets) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > total_keys) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (sorted_keys[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    offsets[k] = lo;
+}
+
+__global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint32_t total_keys,
+                                      unsigned long long *__restrict__ count) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ne = k < total_keys && offsets[k + 1] > offsets[k];
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, ne);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+__global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const uint32_t *__restrict__ sorted_alpha,
+                               uint32_t n_entries, uint32_t n, uint32_t slice_rows, uint32_t n_alpha,
+                               uint2 *__restrict__ entries) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_entries) return;
+    uint32_t i = sorted_idx[p] / n;
+    uint32_t local = i - (i / slice_rows) * slice_rows;
+    entries[p] = make_uint2(local * n_alpha, sorted_alpha[p]);
+}
+
+__global__ void alpha_scatter_kernel(const uint32_t *__restrict__ entry_idx, const uint2 *__restrict__ entries,
+                                     uint32_t n_entries, float *__restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_entries) return;
+    out[entry_idx[p]] = __uint_as_float(entries[p].y);
+}
+
+__global__ void fill_nan_kernel(float *__restrict__ out, size_t count) {
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < count; p += (size_t)gridDim.x * blockDim.x)
+        out[p] = CUDART_NAN_F;
+}
+
+int ceil_log2(uint64_t v) {
+    int b = 0;
+    while ((1ull << b) < v) ++b;
+    return b;
+}
+
+}  // namespace
+
+// accumulator geometry shared with K3 (k3_vote.cu): bytes of shared memory left for the
+// accumulator once the candidate / work queues are taken out
+size_t k3_accumulator_budget(const b200ppf_ctx *ctx);
+
+int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud *model, float angle_step,
+             float dist_step, b200ppf_table **out) {
+    if (!(angle_step > 0.0f) || !(dist_step > 0.0f))
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: discretisation steps must be positive");
+    size_t n;
+    if (feat) {
+        n = (size_t)(unsigned int)std::sqrt((float)feat->count);  // PCL: n = sqrt(size)
+        if (n * n != feat->count)
+            return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: feature cloud size is not a square (n*n pairs expected)");
+    } else {
+        n = model->n;
+    }
+    if (n == 0) return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: empty model");
+    if (n > 65535) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "table build: more than 65535 model points (pair index is 32-bit)");
+    const size_t count = n * n;
+
+    b200ppf_table *t = new b200ppf_table();
+    t->ctx = ctx;
+    t->feature_mode = ctx->feature_mode;
+    b200ppf_table_info &info = t->info;
+    info.n_model = n;
+    info.angle_step = angle_step;
+    info.dist_step = dist_step;
+    info.n_alpha = (uint32_t)std::floor(2.0 * M_PI / (double)angle_step);
+    if (info.n_alpha == 0) {
+        delete t;
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: angle step larger than 2*pi");
+    }
+    // accumulator slices: rows per slice bounded by the shared-memory budget of the voting kernel
+    {
+        size_t budget = k3_accumulator_budget(ctx);
+        size_t rows_max = budget / ((size_t)info.n_alpha * sizeof(uint32_t));
+        if (rows_max == 0) {
+            delete t;
+            return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "table build: angle step too fine for one accumulator row in shared memory");
+        }
+        if (const char *e = getenv("B200PPF_SLICE_ROWS")) {
+            size_t v = (size_t)atoll(e);
+            if (v > 0 && v < rows_max) rows_max = v;
+        }
+        uint32_t n_slices = (uint32_t)((n + rows_max - 1) / rows_max);
+        info.n_slices = n_slices;
+        info.slice_rows = (uint32_t)((n + n_slices - 1) / n_slices);
+    }
+
+    KeyParams &kp = t->kp;
+    kp.angle_step = angle_step;
+    kp.dist_step = dist_step;
+    kp.slice_rows = info.slice_rows;
+    kp.n_slices = info.n_slices;
+
+    int *d_range = nullptr;  // lo[4], hi[4], max_f4_bits, out_of_range
+    PPF_CUDA(ctx, cudaMallocAsync(&d_range, 10 * sizeof(int), ctx->stream));
+    int h_range[10] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, INT_MIN, -1, 0};
+    PPF_CUDA(ctx, cudaMemcpyAsync(d_range, h_range, sizeof(h_range), cudaMemcpyHostToDevice, ctx->stream));
+
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (feat) {
+        int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)ctx->sm_count * 16);
+        PPF_LAUNCH(ctx, feature_range_kernel, blocks, 256, 0, reinterpret_cast<const float *>(feat->d), count,
+                   angle_step, dist_step, d_range, d_range + 8);
+        PPF_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));
+        PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 4; ++k) {
+            if (h_range[k] == INT_MAX) {  // no valid pair at all
+                kp.lo[k] = 0;
+                kp.size[k] = 1;
+            } else {
+                kp.lo[k] = h_range[k];
+                kp.size[k] = h_range[4 + k] - h_range[k] + 1;
+            }
+        }
+    } else {
+        // analytic bounds by feature functor; d4 bounded by the bounding-box diagonal
+        auto q = [](float v, float step) { return (int)std::floor(v / step); };
+        const float pi_hi = 3.2f;
+        if (ctx->feature_mode == B200PPF_FEATURE_PCL_PFH) {
+            kp.lo[0] = q(-pi_hi, angle_step) - 1; kp.size[0] = q(pi_hi, angle_step) + 1 - kp.lo[0] + 1;
+            kp.lo[1] = q(-1.0f, angle_step) - 1;  kp.size[1] = q(1.0f, angle_step) + 1 - kp.lo[1] + 1;
+            kp.lo[2] = kp.lo[1];                  kp.size[2] = kp.size[1];
+        } else if (ctx->feature_mode == B200PPF_FEATURE_DROST_COS) {
+            for (int k = 0; k < 3; ++k) {
+                kp.lo[k] = q(-1.0f, angle_step) - 1;
+                kp.size[k] = q(1.0f, angle_step) + 1 - kp.lo[k] + 1;
+            }
+        } else {
+            for (int k = 0; k < 3; ++k) {
+                kp.lo[k] = -1;
+                kp.size[k] = q(pi_hi, angle_step) + 1 - kp.lo[k] + 1;
+            }
+        }
+        double diag = 0;
+        for (int k = 0; k < 3; ++k) {
+            double e = (double)model->bbox_max[k] - (double)model->bbox_min[k];
+            diag += e * e;
+        }
+        diag = std::sqrt(diag) * 1.001 + 1e-6;
+        kp.lo[3] = 0;
+        kp.size[3] = (int)std::floor(diag / dist_step) + 2;
+    }
+    {
+        unsigned __int128 ks = 1;
+        for (int k = 0; k < 4; ++k) ks *= (unsigned __int128)(uint32_t)kp.size[k];
+        unsigned __int128 total = ks * info.n_slices + 1;
+        if (total >= ((unsigned __int128)1 << 31)) {
+            cudaFreeAsync(d_range, ctx->stream);
+            delete t;
+            return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "table build: discretisation too fine (packed key space exceeds 2^31)");
+        }
+        kp.key_space = (uint32_t)ks;
+    }
+    for (int k = 0; k < 4; ++k) {
+        info.lo[k] = kp.lo[k];
+        info.size[k] = kp.size[k];
+    }
+    info.key_space = kp.key_space;
+    const uint32_t total_keys = kp.key_space * info.n_slices;
+    info.key_bits = (uint32_t)ceil_log2((uint64_t)total_keys + 1);
+
+    t->bp = make_bin_params(angle_step, ctx->alpha_mode);
+
+    // ---- keys ---------------------------------------------------------------------------------
+    uint32_t *keys[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr}, *alp[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; ++b) {
+            if (keys[b]) cudaFreeAsync(keys[b], ctx->stream);
+            if (idx[b]) cudaFreeAsync(idx[b], ctx->stream);
+            if (alp[b]) cudaFreeAsync(alp[b], ctx->stream);
+        }
+        if (d_range) cudaFreeAsync(d_range, ctx->stream);
+    };
+#define K2_TRY(expr)                       \
+    do {                                   \
+        int _rc = (expr);                  \
+        if (_rc != B200PPF_OK) {           \
+            cleanup();                     \
+            b200ppf_table_free(t);         \
+            return _rc;                    \
+        }                                  \
+    } while (0)
+#define K2_CUDA(expr)                                                               \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            cleanup();                                                              \
+            b200ppf_table_free(t);                                                  \
+            char _b[256];                                                           \
+            snprintf(_b, sizeof(_b), "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+            return fail_msg(ctx, _e == cudaErrorMemoryAllocation ? B200PPF_ERR_NOMEM : B200PPF_ERR_CUDA, _b); \
+        }                                                                           \
+    } while (0)
+    for (int b = 0; b < 2; ++b) {
+        K2_CUDA(cudaMallocAsync(&keys[b], count * sizeof(uint32_t), ctx->stream));
+        K2_CUDA(cudaMallocAsync(&idx[b], count * sizeof(uint32_t), ctx->stream));
+        K2_CUDA(cudaMallocAsync(&alp[b], count * sizeof(uint32_t), ctx->stream));
+    }
+    if (feat) {
+        int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)ctx->sm_count * 32);
+        auto launch = [&]() -> int {
+            PPF_LAUNCH(ctx, keys_from_features_kernel, blocks, 256, 0, reinterpret_cast<const float *>(feat->d),
+                       (uint32_t)n, kp, keys[0], alp[0]);
+            return B200PPF_OK;
+        };
+        K2_TRY(launch());
+    } else {
+        dim3 grid((unsigned)((n + FTJ - 1) / FTJ), (unsigned)((n + FTI - 1) / FTI));
+        auto launch = [&]() -> int {
+            PPF_LAUNCH(ctx, keys_from_cloud_kernel, grid, FTJ, 0, model->pos, model->nrm, (uint32_t)n,
+                       ctx->feature_mode, kp, keys[0], alp[0], d_range + 8, d_range + 9);
+            return B200PPF_OK;
+        };
+        K2_TRY(launch());
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+
+    // ---- sort -----------------------------------------------------------------------------------
+    bool in_alt = false;
+    K2_TRY(radix_sort_u32(ctx, keys[0], keys[1], idx[0], idx[1], alp[0], alp[1], count, (int)info.key_bits,
+                          /*v0_iota=*/true, &in_alt));
+    const int s = in_alt ? 1 : 0;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+
+    // ---- CSR ------------------------------------------------------------------------------------
+    K2_CUDA(cudaMalloc(&t->offsets, ((size_t)total_keys + 1) * sizeof(uint32_t)));
+    {
+        auto launch = [&]() -> int {
+            PPF_LAUNCH(ctx, csr_offsets_kernel, (total_keys + 1 + 255) / 256, 256, 0, keys[s], (uint32_t)count,
+                       total_keys, t->offsets);
+            return B200PPF_OK;
+        };
+        K2_TRY(launch());
+    }
+    uint32_t n_entries = 0;
+    K2_CUDA(cudaMemcpyAsync(&n_entries, t->offsets + total_keys, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    K2_CUDA(cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));
+    K2_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!feat && h_range[9] != 0) {
+        cleanup();
+        b200ppf_table_free(t);
+        return fail_msg(ctx, B200PPF_ERR_STATE, "table build: a model pair feature left the analytic key range (non-unit normals?)");
+    }
+    info.n_entries = n_entries;
+    {
+        int bits = h_range[8];
+        float mx;
+        memcpy(&mx, &bits, sizeof(float));
+        info.max_dist = bits < 0 ? -1.0f : mx;  // PCL: max_dist_ starts at -1
+    }
+    K2_CUDA(cudaMalloc(&t->entries, std::max<size_t>(1, n_entries) * sizeof(uint2)));
+    K2_CUDA(cudaMalloc(&t->entry_idx, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
+    unsigned long long *d_cnt = nullptr;
+    K2_CUDA(cudaMallocAsync(&d_cnt, sizeof(unsigned long long), ctx->stream));
+    K2_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        auto launch = [&]() -> int {
+            if (n_entries) {
+                PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
+                           info.slice_rows, info.n_alpha, t->entries);
+                PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            PPF_LAUNCH(ctx, count_nonempty_kernel, (total_keys + 255) / 256, 256, 0, t->offsets, total_keys, d_cnt);
+            return B200PPF_OK;
+        };
+        K2_TRY(launch());
+    }
+    unsigned long long h_cnt = 0;
+    K2_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    K2_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_cnt, ctx->stream);
+    info.n_keys = h_cnt;
+    cleanup();
+    cudaEventElapsedTime(&ctx->timings.keys_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timings.sort_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timings.csr_ms, ctx->ev[2], ctx->ev[3]);
+#undef K2_TRY
+#undef K2_CUDA
+    *out = t;
+    return B200PPF_OK;
+}
+
+int k2_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int32_t *d4, uint64_t *pairs, size_t cap,
+                 size_t *n_found) {
+    *n_found = 0;
+    uint32_t key;
+    int d[4] = {d4[0], d4[1], d4[2], d4[3]};
+    if (!pack_key(t->kp, d, key)) return B200PPF_OK;
+    const uint32_t n = (uint32_t)t->info.n_model;
+    size_t written = 0, total = 0;
+    std::vector<uint32_t> tmp;
+    for (uint32_t s = 0; s < t->info.n_slices; ++s) {
+        uint32_t off[2];
+        PPF_CUDA(ctx, cudaMemcpyAsync(off, t->offsets + (size_t)s * t->kp.key_space + key, sizeof(off),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        uint32_t len = off[1] - off[0];
+        total += len;
+        size_t take = std::min<size_t>(len, cap - std::min(cap, written));
+        if (take) {
+            tmp.resize(take);
+            PPF_CUDA(ctx, cudaMemcpyAsync(tmp.data(), t->entry_idx + off[0], take * sizeof(uint32_t),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (size_t e = 0; e < take; ++e) {
+                pairs[2 * (written + e)] = tmp[e] / n;
+                pairs[2 * (written + e) + 1] = tmp[e] % n;
+            }
+            written += take;
+        }
+    }
+    *n_found = total;
+    return B200PPF_OK;
+}
+
+int k2_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host) {
+    const size_t n = t->info.n_model, count = n * n;
+    float *d = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&d, count * sizeof(float), ctx->stream));
+    int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)ctx->sm_count * 16);
+    PPF_LAUNCH(ctx, fill_nan_kernel, blocks, 256, 0, d, count);
+    if (t->info.n_entries)
+        PPF_LAUNCH(ctx, alpha_scatter_kernel, (unsigned)((t->info.n_entries + 255) / 256), 256, 0, t->entry_idx,
+                   t->entries, (uint32_t)t->info.n_entries, d);
+    PPF_CUDA(ctx, cudaMemcpyAsync(host, d, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PPF_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
+    return B200PPF_OK;
+}
+
+}  // namespace b200ppf

@@ -1,0 +1,460 @@
+// k3_vote.cu — K3 ppf_vote_argmax: scene voting, peak pick and pose assembly.
+//
+// Replaces the voting loop of PPFRegistration::computeTransformation
+// ([PCL] registration/include/pcl/registration/impl/ppf_registration.hpp):
+//   for every scene reference point s_r: frame T_sg; every scene point within max_dist/2 gives a
+//   pair feature -> bucket -> for every (i, alpha_m) in the bucket acc[i][bin(alpha_m - alpha_s)]++;
+//   first maximum of acc (lowest flat index wins ties) -> pose = T_sg^-1 * Rx(theta) * T_mg.
+//
+// One CTA per (reference point, accumulator slice).  The accumulator slice — up to ~1800 model
+// rows x n_alpha 32-bit counters — lives in shared memory for the CTA's whole life, votes are
+// shared-memory atomics, the peak is a warp-shuffle argmax, and slices merge through one 64-bit
+// atomicMax per CTA on a packed (votes, ~flat index) word, which reproduces PCL's tie-break.
+// The CTA works in three phases that keep all 32 lanes busy:
+//   A  scan   coalesced float4 sweep over the scene positions, distance predicate only,
+//             survivors compacted into a shared candidate queue with one warp-aggregated atomic;
+//   B  pair   one thread per candidate: pair feature, key, CSR bucket bounds, alpha_s -> work item;
+//   C  vote   warps pull work items and walk the bucket 32 entries at a time: one coalesced 8-byte
+//             gather {row offset, alpha_m} and one shared atomic per vote.
+// Roofline: 8 B gathered + 1 shared atomic per vote, 8 B of CSR offsets per
+// in-radius pair; shared-atomic throughput is the binding limit, not HBM.
+#include <algorithm>
+#include <cmath>
+
+#include "ppf_common.cuh"
+
+namespace b200ppf {
+
+namespace {
+
+constexpr int VOTE_THREADS = 256;
+constexpr int VOTE_WARPS = VOTE_THREADS / 32;
+constexpr int CAND_CAP = 2048;    // in-radius candidates buffered between flushes
+constexpr int SCAN_TILES = 4;     // scene tiles swept between two capacity checks
+constexpr int ITEM_CAP = VOTE_THREADS;
+static_assert(CAND_CAP >= 2 * SCAN_TILES * VOTE_THREADS, "flush threshold must leave a full sweep of room");
+
+struct WorkItem {
+    uint32_t off, len;
+    float alpha_s;
+};
+
+constexpr size_t QUEUE_BYTES = CAND_CAP * sizeof(uint32_t) + ITEM_CAP * sizeof(WorkItem);
+constexpr size_t STATIC_RESERVE = 2048;  // static shared + the 1 KB the system reserves per CTA
+
+struct VoteArgs {
+    const float4 *pos, *nrm;
+    uint32_t n_s;
+    uint32_t ref_first, ref_step, ref_count;
+    const uint32_t *offsets;
+    const uint2 *entries;
+    KeyParams kp;
+    BinParams bp;
+    int feature_mode;
+    float radius;
+    uint32_t n_model;
+    unsigned long long *peaks;
+    unsigned long long *stats;
+    uint32_t *acc_dump;  // debug: full accumulator of reference 0 (n_model * n_alpha)
+};
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
+    return __shfl_xor_sync(0xFFFFFFFFu, v, o);
+}
+
+__global__ void __launch_bounds__(VOTE_THREADS)
+ppf_vote_kernel(const VoteArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Frame s_sg;
+    __shared__ uint32_t s_ncand, s_nitems, s_next;
+    __shared__ unsigned long long s_best[VOTE_WARPS];
+    __shared__ unsigned long long s_stat[4];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t slice = blockIdx.y;
+    const uint32_t slice_base = slice * a.kp.slice_rows;
+    const uint32_t rows = min(a.kp.slice_rows, a.n_model - slice_base);
+    const uint32_t acc_len = rows * a.bp.n_alpha;
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *cand = acc + (size_t)a.kp.slice_rows * a.bp.n_alpha;
+    WorkItem *items = reinterpret_cast<WorkItem *>(cand + CAND_CAP);
+
+    const uint32_t s_r = a.ref_first + blockIdx.x * a.ref_step;
+    const float4 pr4 = a.pos[s_r], nr4 = a.nrm[s_r];
+    const V3 p_r = v3_of(pr4), n_r = v3_of(nr4);
+    if (tid == 0) {
+        ref_frame(p_r, n_r, s_sg);
+        s_ncand = 0;
+        s_nitems = 0;
+        s_next = 0;
+    }
+    if (tid < 4) s_stat[tid] = 0;
+    for (uint32_t k = tid; k < acc_len; k += VOTE_THREADS) acc[k] = 0;
+    __syncthreads();
+
+    const uint32_t *slice_offsets = a.offsets + (size_t)slice * a.kp.key_space;
+    uint32_t st_in_radius = 0, st_nonempty = 0, st_votes = 0;
+
+    // phases B + C over the buffered candidates
+    auto flush = [&]() {
+        const uint32_t ncand = s_ncand;
+        for (uint32_t c0 = 0; c0 < ncand; c0 += VOTE_THREADS) {
+            // ---- B: pair features -> work items -------------------------------------------------
+            const uint32_t c = c0 + tid;
+            bool push = false;
+            WorkItem it;
+            it.off = it.len = 0;
+            it.alpha_s = 0.0f;
+            if (c < ncand) {
+                const uint32_t s = cand[c];
+                const float4 p4 = a.pos[s], n4 = a.nrm[s];
+                float f[4];
+                if (pair_features(a.feature_mode, p_r, n_r, v3_of(p4), v3_of(n4), f)) {
+                    ++st_in_radius;
+                    int d[4];
+                    quantise(a.kp, f, d);
+                    uint32_t key;
+                    if (pack_key(a.kp, d, key)) {
+                        const uint32_t o0 = __ldg(slice_offsets + key), o1 = __ldg(slice_offsets + key + 1);
+                        if (o1 > o0) {
+                            it.off = o0;
+                            it.len = o1 - o0;
+                            it.alpha_s = planar_alpha(s_sg, v3_of(p4));
+                            push = true;
+                            ++st_nonempty;
+                        }
+                    }
+                }
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, push);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&s_nitems, __popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+                if (push) items[base + __popc(m & ((1u << lane) - 1u))] = it;
+            }
+            __syncthreads();
+            // ---- C: votes ---------------------------------------------------------------------
+            const uint32_t nitems = s_nitems;
+            for (;;) {
+                uint32_t w = 0;
+                if (lane == 0) w = atomicAdd(&s_next, 1u);
+                w = __shfl_sync(0xFFFFFFFFu, w, 0);
+                if (w >= nitems) break;
+                const WorkItem wi = items[w];
+                const uint2 *e = a.entries + wi.off;
+                for (uint32_t k = lane; k < wi.len; k += 32) {
+                    const uint2 en = __ldg(e + k);
+                    const uint32_t bin = alpha_bin_fast(a.bp, __uint_as_float(en.y), wi.alpha_s);
+                    if (bin != 0xFFFFFFFFu) {
+                        atomicAdd(&acc[en.x + bin], 1u);
+                        ++st_votes;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_nitems = 0;
+                s_next = 0;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) s_ncand = 0;
+        __syncthreads();
+    };
+
+    // ---- A: sweep the scene -----------------------------------------------------------------------
+    for (uint32_t base = 0; base < a.n_s; base += SCAN_TILES * VOTE_THREADS) {
+#pragma unroll
+        for (int t = 0; t < SCAN_TILES; ++t) {
+            const uint32_t s = base + t * VOTE_THREADS + tid;
+            bool in = false;
+            if (s < a.n_s && s != s_r) {
+                const float4 p4 = __ldg(a.pos + s);
+                const V3 d = make_v3(p4.x - p_r.x, p4.y - p_r.y, p4.z - p_r.z);
+                in = norm3(d) < a.radius;  // radius predicate on f4 itself (SURVEY.md A.8 rule 7)
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
+            if (m) {
+                uint32_t b = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&s_ncand, __popc(m));
+                b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
+                if (in) cand[b + __popc(m & ((1u << lane) - 1u))] = s;
+            }
+        }
+        __syncthreads();
+        const uint32_t buffered = s_ncand;
+        __syncthreads();  // nobody may start the next sweep's atomics before everyone has read
+        if (buffered > CAND_CAP - SCAN_TILES * VOTE_THREADS) flush();
+    }
+    flush();
+
+    // ---- peak: first maximum in (i, bin) order == max of (votes, ~flat) ---------------------------
+    unsigned long long best = 0;
+    for (uint32_t k = tid; k < acc_len; k += VOTE_THREADS) {
+        const uint32_t v = acc[k];
+        if (v) {
+            const unsigned long long c =
+                ((unsigned long long)v << 32) | (unsigned long long)(0xFFFFFFFFu - (slice_base * a.bp.n_alpha + k));
+            best = max(best, c);
+        }
+        if (a.acc_dump) a.acc_dump[(size_t)slice_base * a.bp.n_alpha + k] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, shfl_xor_u64(best, o));
+    // stats: warp reduce then shared
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        st_in_radius += __shfl_xor_sync(0xFFFFFFFFu, st_in_radius, o);
+        st_nonempty += __shfl_xor_sync(0xFFFFFFFFu, st_nonempty, o);
+        st_votes += __shfl_xor_sync(0xFFFFFFFFu, st_votes, o);
+    }
+    if (lane == 0) {
+        s_best[warp] = best;
+        atomicAdd(&s_stat[1], (unsigned long long)st_in_radius);
+        atomicAdd(&s_stat[2], (unsigned long long)st_nonempty);
+        atomicAdd(&s_stat[3], (unsigned long long)st_votes);
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 1; w < VOTE_WARPS; ++w) best = max(best, s_best[w]);
+        if (best) atomicMax(a.peaks + blockIdx.x, best);
+        if (slice == 0) {
+            atomicAdd(a.stats + 0, (unsigned long long)(a.n_s - 1));
+            atomicAdd(a.stats + 1, s_stat[1]);
+        }
+        atomicAdd(a.stats + 2, s_stat[2]);
+        atomicAdd(a.stats + 3, s_stat[3]);
+    }
+}
+
+// pose of every peak: one thread per reference point
+__global__ void ppf_peak_pose_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm,
+                                     const float4 *__restrict__ mpos, const float4 *__restrict__ mnrm,
+                                     uint32_t ref_first, uint32_t ref_step, uint32_t ref_count,
+                                     const unsigned long long *__restrict__ peaks, BinParams bp,
+                                     b200ppf_hypothesis *__restrict__ out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ref_count) return;
+    const uint32_t s_r = ref_first + r * ref_step;
+    const unsigned long long pk = peaks[r];
+    const uint32_t votes = (uint32_t)(pk >> 32);
+    const uint32_t flat = votes ? 0xFFFFFFFFu - (uint32_t)(pk & 0xFFFFFFFFu) : 0u;
+    const uint32_t i = flat / bp.n_alpha, bin = flat - i * bp.n_alpha;
+    Frame sg, mg;
+    ref_frame(v3_of(spos[s_r]), v3_of(snrm[s_r]), sg);
+    ref_frame(v3_of(mpos[i]), v3_of(mnrm[i]), mg);
+    b200ppf_hypothesis h;
+    compose_pose(sg, peak_theta(bp.mode, bp.angle_step, bin), mg, h.pose);
+    h.votes = votes;
+    h.model_index = i;
+    h.alpha_bin = bin;
+    h.scene_index = s_r;
+    out[r] = h;
+}
+
+// parity hook: per-scene-point quantities of one reference point, exactly as phases A/B see them
+__global__ void ppf_debug_pairs_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, uint32_t n_s,
+                                       uint32_t s_r, KeyParams kp, int feature_mode, float radius,
+                                       uint8_t *__restrict__ in_radius, int *__restrict__ d4,
+                                       float *__restrict__ alpha_s) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_s) return;
+    in_radius[s] = 0;
+    d4[4 * s] = d4[4 * s + 1] = d4[4 * s + 2] = d4[4 * s + 3] = 0;
+    alpha_s[s] = 0.0f;
+    if (s == s_r) return;
+    const V3 p_r = v3_of(pos[s_r]), n_r = v3_of(nrm[s_r]);
+    const V3 p = v3_of(pos[s]), n = v3_of(nrm[s]);
+    const V3 d = make_v3(p.x - p_r.x, p.y - p_r.y, p.z - p_r.z);
+    if (!(norm3(d) < radius)) return;
+    float f[4];
+    if (!pair_features(feature_mode, p_r, n_r, p, n, f)) return;
+    int q[4];
+    quantise(kp, f, q);
+    Frame sg;
+    ref_frame(p_r, n_r, sg);
+    in_radius[s] = 1;
+    d4[4 * s] = q[0];
+    d4[4 * s + 1] = q[1];
+    d4[4 * s + 2] = q[2];
+    d4[4 * s + 3] = q[3];
+    alpha_s[s] = planar_alpha(sg, p);
+}
+
+__global__ void debug_alpha_bins_kernel(BinParams bp, const float *__restrict__ am, const float *__restrict__ as,
+                                        uint32_t n, uint32_t *__restrict__ fast, uint32_t *__restrict__ exact) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    fast[p] = alpha_bin_fast(bp, am[p], as[p]);
+    exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, am[p], as[p]);
+}
+
+size_t vote_smem_bytes(const b200ppf_table *t) {
+    return (size_t)t->info.slice_rows * t->info.n_alpha * sizeof(uint32_t) + QUEUE_BYTES;
+}
+
+int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_first,
+                size_t ref_step, size_t ref_count, uint32_t *acc_dump) {
+    VoteArgs a;
+    a.pos = scene->pos;
+    a.nrm = scene->nrm;
+    a.n_s = (uint32_t)scene->n;
+    a.ref_first = (uint32_t)ref_first;
+    a.ref_step = (uint32_t)ref_step;
+    a.ref_count = (uint32_t)ref_count;
+    a.offsets = t->offsets;
+    a.entries = t->entries;
+    a.kp = t->kp;
+    a.bp = t->bp;
+    a.bp.mode = ctx->alpha_mode;
+    a.feature_mode = t->feature_mode;
+    a.radius = t->info.max_dist * 0.5f;
+    a.n_model = (uint32_t)t->info.n_model;
+    a.peaks = ctx->d_peaks;
+    a.stats = ctx->d_stats;
+    a.acc_dump = acc_dump;
+    const size_t smem = vote_smem_bytes(t);
+    PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ref_count, t->info.n_slices);
+    PPF_LAUNCH(ctx, ppf_vote_kernel, grid, VOTE_THREADS, smem, a);
+    return B200PPF_OK;
+}
+
+int ensure_vote_scratch(b200ppf_ctx *ctx, size_t ref_count) {
+    if (!ctx->d_stats) PPF_CUDA(ctx, cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)));
+    if (ctx->peaks_cap < ref_count) {
+        if (ctx->d_peaks) cudaFree(ctx->d_peaks);
+        ctx->d_peaks = nullptr;
+        ctx->peaks_cap = 0;
+        PPF_CUDA(ctx, cudaMalloc(&ctx->d_peaks, ref_count * sizeof(unsigned long long)));
+        ctx->peaks_cap = ref_count;
+    }
+    PPF_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    PPF_CUDA(ctx, cudaMemsetAsync(ctx->d_peaks, 0, ref_count * sizeof(unsigned long long), ctx->stream));
+    return B200PPF_OK;
+}
+
+int check_vote_inputs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_first,
+                      size_t ref_step, size_t ref_count) {
+    if (!t || !scene) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: null table or scene");
+    if (ref_step == 0) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: reference step must be >= 1");
+    if (ref_count && ref_first + (ref_count - 1) * ref_step >= scene->n)
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: reference index range exceeds the scene");
+    if (scene->n >= 0xFFFFFFFFull) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "vote: scene too large");
+    if (vote_smem_bytes(t) + STATIC_RESERVE > ctx->smem_optin)
+        return fail_msg(ctx, B200PPF_ERR_STATE, "vote: table was sliced for a larger shared-memory budget than this device has");
+    return B200PPF_OK;
+}
+
+}  // namespace
+
+BinParams make_bin_params(float angle_step, int alpha_mode) {
+    BinParams bp;
+    bp.angle_step = angle_step;
+    bp.inv_step = 1.0f / angle_step;
+    bp.n_alpha = (uint32_t)floor(2.0 * M_PI / (double)angle_step);
+    bp.mode = alpha_mode;
+    bp.mode_b_offset = (int)floor(M_PI / (double)angle_step);
+    bp.guard = std::max(2e-4f, 1e-5f * bp.inv_step);
+    return bp;
+}
+
+int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+                        const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact) {
+    const BinParams bp = make_bin_params(angle_step, alpha_mode);
+    if (!ctx) {  // host build of the same inline functions
+        for (size_t p = 0; p < n; ++p) {
+            fast[p] = alpha_bin_fast(bp, alpha_m[p], alpha_s[p]);
+            exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, alpha_m[p], alpha_s[p]);
+        }
+        return B200PPF_OK;
+    }
+    float *d_am = nullptr, *d_as = nullptr;
+    uint32_t *d_f = nullptr, *d_e = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&d_am, n * sizeof(float), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&d_as, n * sizeof(float), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&d_f, n * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&d_e, n * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMemcpyAsync(d_am, alpha_m, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PPF_CUDA(ctx, cudaMemcpyAsync(d_as, alpha_s, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PPF_LAUNCH(ctx, debug_alpha_bins_kernel, (unsigned)((n + 255) / 256), 256, 0, bp, d_am, d_as, (uint32_t)n, d_f, d_e);
+    PPF_CUDA(ctx, cudaMemcpyAsync(fast, d_f, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaMemcpyAsync(exact, d_e, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_am, ctx->stream);
+    cudaFreeAsync(d_as, ctx->stream);
+    cudaFreeAsync(d_f, ctx->stream);
+    cudaFreeAsync(d_e, ctx->stream);
+    return B200PPF_OK;
+}
+
+size_t k3_accumulator_budget(const b200ppf_ctx *ctx) {
+    size_t total = ctx->smem_optin ? ctx->smem_optin : kSmemPerBlockMax;
+    return total - QUEUE_BYTES - STATIC_RESERVE;
+}
+
+int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
+            size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *hyps_device) {
+    int rc = check_vote_inputs(ctx, t, scene, ref_first, ref_step, ref_count);
+    if (rc) return rc;
+    if (!model || model->n != t->info.n_model)
+        return fail_msg(ctx, B200PPF_ERR_STATE, "vote: model cloud does not match the table (setInputSource vs setSearchMethod)");
+    if (ref_count == 0) return B200PPF_OK;
+    rc = ensure_vote_scratch(ctx, ref_count);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    rc = launch_vote(ctx, t, scene, ref_first, ref_step, ref_count, nullptr);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    BinParams bp = t->bp;
+    bp.mode = ctx->alpha_mode;
+    PPF_LAUNCH(ctx, ppf_peak_pose_kernel, (unsigned)((ref_count + 127) / 128), 128, 0, scene->pos, scene->nrm,
+               model->pos, model->nrm, (uint32_t)ref_first, (uint32_t)ref_step, (uint32_t)ref_count, ctx->d_peaks, bp,
+               hyps_device);
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    return B200PPF_OK;
+}
+
+int k3_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
+                   uint8_t *in_radius, int32_t *d4, float *alpha_s) {
+    if (!t || !scene || s_r >= scene->n) return fail_msg(ctx, B200PPF_ERR_INVALID, "debug pairs: bad arguments");
+    const size_t n = scene->n;
+    uint8_t *d_in = nullptr;
+    int *d_d = nullptr;
+    float *d_a = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&d_in, n, ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&d_d, n * 4 * sizeof(int), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&d_a, n * sizeof(float), ctx->stream));
+    PPF_LAUNCH(ctx, ppf_debug_pairs_kernel, (unsigned)((n + 255) / 256), 256, 0, scene->pos, scene->nrm, (uint32_t)n,
+               (uint32_t)s_r, t->kp, t->feature_mode, t->info.max_dist * 0.5f, d_in, d_d, d_a);
+    PPF_CUDA(ctx, cudaMemcpyAsync(in_radius, d_in, n, cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaMemcpyAsync(d4, d_d, n * 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaMemcpyAsync(alpha_s, d_a, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_in, ctx->stream);
+    cudaFreeAsync(d_d, ctx->stream);
+    cudaFreeAsync(d_a, ctx->stream);
+    return B200PPF_OK;
+}
+
+int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
+                         uint32_t *acc) {
+    int rc = check_vote_inputs(ctx, t, scene, s_r, 1, 1);
+    if (rc) return rc;
+    rc = ensure_vote_scratch(ctx, 1);
+    if (rc) return rc;
+    const size_t len = (size_t)t->info.n_model * t->info.n_alpha;
+    uint32_t *d_acc = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&d_acc, len * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMemsetAsync(d_acc, 0, len * sizeof(uint32_t), ctx->stream));
+    rc = launch_vote(ctx, t, scene, s_r, 1, 1, d_acc);
+    if (rc) return rc;
+    PPF_CUDA(ctx, cudaMemcpyAsync(acc, d_acc, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(d_acc, ctx->stream);
+    return B200PPF_OK;
+}
+
+}  // namespace b200ppf

@@ -1,0 +1,125 @@
+// ppf_common.cuh — host-side objects behind the opaque handles of include/b200ppf.h
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/b200ppf.h"
+#include "ppf_math.cuh"
+
+namespace b200ppf {
+
+static_assert(sizeof(b200ppf_hypothesis) == 64, "hypothesis record is the 64-byte all-gather unit");
+static_assert(sizeof(b200ppf_signature) == 20, "pcl::PPFSignature is 20 bytes");
+
+// smallest accumulator budget we plan slices against (bytes of dynamic shared memory)
+constexpr size_t kSmemPerBlockMax = 227 * 1024;
+
+}  // namespace b200ppf
+
+struct b200ppf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int feature_mode = B200PPF_FEATURE_PCL_PFH;
+    int alpha_mode = B200PPF_ALPHA_MODE_A;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    std::string error;
+    b200ppf_timings timings{};
+    uint64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // vote scratch (grown on demand, kept across calls)
+    unsigned long long *d_stats = nullptr;  // [4]
+    unsigned long long *d_peaks = nullptr;  // packed (votes<<32 | ~flat) per reference
+    size_t peaks_cap = 0;
+    b200ppf_hypothesis *d_hyps = nullptr;  // staging for host-output votes
+    size_t hyps_cap = 0;
+    // cluster scratch of the last cluster call
+    uint32_t *d_assign = nullptr;  // cluster creation index per hypothesis (input order)
+    size_t assign_n = 0;
+    uint32_t n_clusters = 0;
+};
+
+struct b200ppf_cloud {
+    b200ppf_ctx *ctx = nullptr;
+    size_t n = 0;
+    float4 *pos = nullptr;  // x y z 1
+    float4 *nrm = nullptr;  // nx ny nz 0
+    float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
+};
+
+struct b200ppf_features {
+    b200ppf_ctx *ctx = nullptr;
+    size_t count = 0;              // n*n
+    b200ppf_signature *d = nullptr;  // row-major [i*n+j]
+};
+
+struct b200ppf_table {
+    b200ppf_ctx *ctx = nullptr;
+    b200ppf_table_info info{};
+    b200ppf::KeyParams kp{};
+    b200ppf::BinParams bp{};
+    uint32_t *offsets = nullptr;  // [n_slices*key_space + 1]
+    uint2 *entries = nullptr;     // {row offset = (i - slice_base)*n_alpha, alpha_m bits} per entry
+    uint32_t *entry_idx = nullptr;  // i*n + j per entry (API queries, alpha_m_ export)
+    int feature_mode = 0;
+};
+
+namespace b200ppf {
+
+#define PPF_CUDA(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            char _b[512];                                                                     \
+            snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                     __FILE__, __LINE__);                                                     \
+            return ::b200ppf::fail_msg(ctx, _e == cudaErrorMemoryAllocation ? B200PPF_ERR_NOMEM \
+                                                                             : B200PPF_ERR_CUDA, \
+                                       _b);                                                   \
+        }                                                                                     \
+    } while (0)
+
+int fail_msg(b200ppf_ctx *ctx, int code, const char *msg);
+
+// launch bookkeeping: every kernel launch of the library goes through this macro
+#define PPF_LAUNCH(ctx, kernel, grid, block, smem, ...)                            \
+    do {                                                                           \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+        (ctx)->launches++;                                                         \
+        PPF_CUDA(ctx, cudaGetLastError());                                         \
+    } while (0)
+
+// ---- stage entry points implemented in the k*.cu files (host functions) ----------------------
+int k1_features_compute(b200ppf_ctx *ctx, const b200ppf_cloud *model, b200ppf_signature *out);
+int k2_build(b200ppf_ctx *ctx, const b200ppf_features *f, const b200ppf_cloud *model, float angle_step,
+             float dist_step, b200ppf_table **out);
+int k2_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int32_t *d4, uint64_t *pairs, size_t cap,
+                 size_t *n_found);
+int k2_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host);
+int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
+            size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *hyps_device);
+int k3_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
+                   uint8_t *in_radius, int32_t *d4, float *alpha_s);
+int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
+                         uint32_t *acc);
+int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+                         const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact);
+BinParams make_bin_params(float angle_step, int alpha_mode);
+int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n, float pos_thr, float rot_thr,
+               float *poses16, uint32_t *votes, size_t *n_out);
+int k5_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose16, float *out_host,
+                 size_t out_stride_floats);
+
+// hand-written LSD radix sort (radix_sort.cu): keys ascending, stable, two 32-bit payload streams.
+// All buffers are device pointers of n elements; *_alt are the ping-pong partners.  On return
+// *result_in_alt tells which set holds the sorted data.  bits = number of key bits to sort.
+// v0_iota: treat v0 as the identity permutation on entry (its contents are never read).
+int radix_sort_u32(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_t *v0, uint32_t *v0_alt,
+                   uint32_t *v1, uint32_t *v1_alt, size_t n, int bits, bool v0_iota, bool *result_in_alt);
+
+}  // namespace b200ppf

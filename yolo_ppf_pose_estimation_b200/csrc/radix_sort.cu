@@ -1,0 +1,203 @@
+// radix_sort.cu — hand-written stable LSD radix sort (8-bit digits) for sm_100a.
+//
+// Used by K2 (order the N_m^2 model pairs by packed feature key -> CSR buckets, replacing the
+// unordered_multimap of [PCL] registration/src/ppf_registration.cpp) and by K4 (order pose
+// hypotheses by votes, replacing the std::sort of clusterPoses).
+//
+// Layout: the input is cut into warp segments of SEG consecutive elements.  One warp owns one
+// segment in both the histogram and the scatter kernel, walking it in rounds of 32 coalesced
+// elements; lanes holding the same digit find each other with match.any, so ranks inside a
+// round are stable by lane order, rounds are sequential, segments are ordered by the column
+// scan — the sort is stable without any atomics.
+//   hist[seg][256]  (segment-major: coalesced 1 KB rows)  --column scan-->  global bases
+// HBM traffic per pass: keys read twice, payloads read once, everything written once.
+#include "ppf_common.cuh"
+
+namespace b200ppf {
+
+namespace {
+
+constexpr int RADIX = 256;
+constexpr int SEG = 2048;           // elements per warp segment
+constexpr int WARPS = 8;            // warps (segments) per block
+constexpr int SCAN_CHUNK = 256;     // histogram rows per column-scan chunk
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__global__ void __launch_bounds__(WARPS * 32)
+radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t nseg, int shift,
+                  uint32_t *__restrict__ hist) {
+    __shared__ uint32_t cnt[WARPS][RADIX];
+    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t seg = blockIdx.x * WARPS + w;
+    for (int d = lane; d < RADIX; d += 32) cnt[w][d] = 0;
+    __syncwarp();
+    if (seg >= nseg) return;
+    const uint32_t begin = seg * (uint32_t)SEG;
+    const uint32_t end = min(n, begin + (uint32_t)SEG);  // begin < n, no overflow: n < 2^32 - SEG
+    for (uint32_t base = begin; base < end; base += 32) {
+        uint32_t idx = base + lane;
+        bool valid = idx < end;
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid) {
+            uint32_t digit = (keys[idx] >> shift) & (RADIX - 1);
+            uint32_t peers = __match_any_sync(mask, digit);
+            if ((uint32_t)(__ffs(peers) - 1) == lane) cnt[w][digit] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    uint32_t *row = hist + (size_t)seg * RADIX;
+    for (int d = lane; d < RADIX; d += 32) row[d] = cnt[w][d];
+}
+
+// column scan, step 1: per chunk of rows, per digit totals
+__global__ void __launch_bounds__(RADIX)
+radix_col_reduce_kernel(const uint32_t *__restrict__ hist, uint32_t nseg, uint32_t *__restrict__ chunk_tot) {
+    const uint32_t d = threadIdx.x;
+    const uint32_t r0 = blockIdx.x * SCAN_CHUNK, r1 = min(nseg, r0 + SCAN_CHUNK);
+    uint32_t s = 0;
+    for (uint32_t r = r0; r < r1; ++r) s += hist[(size_t)r * RADIX + d];
+    chunk_tot[(size_t)blockIdx.x * RADIX + d] = s;
+}
+
+// step 2 (one block): exclusive scan over chunks per digit, then over digits
+__global__ void __launch_bounds__(RADIX)
+radix_col_scan_chunks_kernel(uint32_t *__restrict__ chunk_tot, uint32_t nchunks, uint32_t *__restrict__ digit_base) {
+    __shared__ uint32_t tot[RADIX];
+    const uint32_t d = threadIdx.x;
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        uint32_t t = chunk_tot[(size_t)c * RADIX + d];
+        chunk_tot[(size_t)c * RADIX + d] = run;
+        run += t;
+    }
+    tot[d] = run;
+    __syncthreads();
+    // exclusive scan of 256 totals: warp 0, 8 values per lane
+    if (d < 32) {
+        uint32_t v[8], s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = tot[d * 8 + k];
+            s += v[k];
+        }
+        uint32_t incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (d >= (uint32_t)o) incl += t;
+        }
+        uint32_t excl = incl - s;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            digit_base[d * 8 + k] = excl;
+            excl += v[k];
+        }
+    }
+}
+
+// step 3: rewrite every histogram row as global bases
+__global__ void __launch_bounds__(RADIX)
+radix_col_apply_kernel(uint32_t *__restrict__ hist, uint32_t nseg, const uint32_t *__restrict__ chunk_tot,
+                       const uint32_t *__restrict__ digit_base) {
+    const uint32_t d = threadIdx.x;
+    const uint32_t r0 = blockIdx.x * SCAN_CHUNK, r1 = min(nseg, r0 + SCAN_CHUNK);
+    uint32_t run = chunk_tot[(size_t)blockIdx.x * RADIX + d] + digit_base[d];
+    for (uint32_t r = r0; r < r1; ++r) {
+        uint32_t t = hist[(size_t)r * RADIX + d];
+        hist[(size_t)r * RADIX + d] = run;
+        run += t;
+    }
+}
+
+template <bool IOTA, bool HAS_V0, bool HAS_V1>
+__global__ void __launch_bounds__(WARPS * 32)
+radix_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v0,
+                     const uint32_t *__restrict__ v1, uint32_t n, uint32_t nseg, int shift,
+                     const uint32_t *__restrict__ hist, uint32_t *__restrict__ keys_out,
+                     uint32_t *__restrict__ v0_out, uint32_t *__restrict__ v1_out) {
+    __shared__ uint32_t base[WARPS][RADIX];
+    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t seg = blockIdx.x * WARPS + w;
+    if (seg >= nseg) return;
+    const uint32_t *row = hist + (size_t)seg * RADIX;
+    for (int d = lane; d < RADIX; d += 32) base[w][d] = row[d];
+    __syncwarp();
+    const uint32_t begin = seg * (uint32_t)SEG;
+    const uint32_t end = min(n, begin + (uint32_t)SEG);
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t b = begin; b < end; b += 32) {
+        uint32_t idx = b + lane;
+        bool valid = idx < end;
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
+        uint32_t key = 0, digit = 0, peers = 0, pos = 0;
+        if (valid) {
+            key = keys[idx];
+            digit = (key >> shift) & (RADIX - 1);
+            peers = __match_any_sync(mask, digit);
+            pos = base[w][digit] + __popc(peers & lt);
+        }
+        __syncwarp();
+        if (valid && (uint32_t)(__ffs(peers) - 1) == lane) base[w][digit] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            keys_out[pos] = key;
+            if (HAS_V0) v0_out[pos] = IOTA ? idx : v0[idx];
+            if (HAS_V1) v1_out[pos] = v1[idx];
+        }
+    }
+}
+
+}  // namespace
+
+// v0_iota: on entry v0 is taken to be the identity permutation 0..n-1 (its contents are not read).
+int radix_sort_u32(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_t *v0, uint32_t *v0_alt,
+                   uint32_t *v1, uint32_t *v1_alt, size_t n, int bits, bool v0_iota, bool *result_in_alt) {
+    *result_in_alt = false;
+    if (n == 0 || bits <= 0) return B200PPF_OK;
+    if (n >= 0xFFFFFFFFull - SEG) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "radix sort: more than 2^32 elements");
+    const uint32_t nseg = (uint32_t)((n + SEG - 1) / SEG);
+    const uint32_t nblocks = (nseg + WARPS - 1) / WARPS;
+    const uint32_t nchunks = (nseg + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    uint32_t *hist = nullptr, *chunk_tot = nullptr, *digit_base = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&hist, (size_t)nseg * RADIX * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&chunk_tot, (size_t)nchunks * RADIX * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&digit_base, RADIX * sizeof(uint32_t), ctx->stream));
+
+    const bool has_v0 = v0 != nullptr && v0_alt != nullptr, has_v1 = v1 != nullptr && v1_alt != nullptr;
+    bool iota = has_v0 && v0_iota;
+    uint32_t *ki = keys, *ko = keys_alt, *v0i = v0, *v0o = v0_alt, *v1i = v1, *v1o = v1_alt;
+    bool in_alt = false;
+    for (int shift = 0; shift < bits; shift += 8) {
+        PPF_LAUNCH(ctx, radix_hist_kernel, nblocks, WARPS * 32, 0, ki, (uint32_t)n, nseg, shift, hist);
+        PPF_LAUNCH(ctx, radix_col_reduce_kernel, nchunks, RADIX, 0, hist, nseg, chunk_tot);
+        PPF_LAUNCH(ctx, radix_col_scan_chunks_kernel, 1, RADIX, 0, chunk_tot, nchunks, digit_base);
+        PPF_LAUNCH(ctx, radix_col_apply_kernel, nchunks, RADIX, 0, hist, nseg, chunk_tot, digit_base);
+#define SCATTER(I, A, B)                                                                                      \
+    PPF_LAUNCH(ctx, (radix_scatter_kernel<I, A, B>), nblocks, WARPS * 32, 0, ki, v0i, v1i, (uint32_t)n, nseg, \
+               shift, hist, ko, v0o, v1o)
+        if (has_v0 && has_v1) {
+            if (iota) SCATTER(true, true, true); else SCATTER(false, true, true);
+        } else if (has_v0) {
+            if (iota) SCATTER(true, true, false); else SCATTER(false, true, false);
+        } else if (has_v1) {
+            SCATTER(false, false, true);
+        } else {
+            SCATTER(false, false, false);
+        }
+#undef SCATTER
+        iota = false;
+        uint32_t *t;
+        t = ki; ki = ko; ko = t;
+        t = v0i; v0i = v0o; v0o = t;
+        t = v1i; v1i = v1o; v1o = t;
+        in_alt = !in_alt;
+    }
+    PPF_CUDA(ctx, cudaFreeAsync(hist, ctx->stream));
+    PPF_CUDA(ctx, cudaFreeAsync(chunk_tot, ctx->stream));
+    PPF_CUDA(ctx, cudaFreeAsync(digit_base, ctx->stream));
+    *result_in_alt = in_alt;
+    return B200PPF_OK;
+}
+
+}  // namespace b200ppf
