@@ -53,6 +53,19 @@ def swap_margin(cloud, i, j):
     return np.abs(np.arccos(np.clip(a1, -1, 1)) - np.arccos(np.clip(a2, -1, 1)))
 
 
+def alpha_tolerance(cloud, i, j):
+    """alpha = atan2(-z, y) of point j in the frame of (i): the frame's entries carry a few float
+    ulps of sin/cos error (~|p| * 1e-7 absolute on y, z), which the angle magnifies by 1/rho, rho =
+    distance of point j from the normal line through point i.  Tolerance = ALPHA_TOL + 6e-7*|p|/rho."""
+    p = cloud[:, :3].astype(np.float64)
+    n = cloud[:, 3:6].astype(np.float64)
+    d = p[j] - p[i]
+    along = np.einsum("...k,...k->...", d, n[i])
+    rho = np.linalg.norm(d - along[..., None] * n[i], axis=-1)
+    scale = np.maximum(np.linalg.norm(p[i], axis=-1), np.linalg.norm(p[j], axis=-1)) + 1e-3
+    return ALPHA_TOL + 6e-7 * scale / np.maximum(rho, 1e-12)
+
+
 def pose_error(A, B):
     """(translation distance [m], rotation angle [deg]) between two 4x4 / 3x4 poses."""
     A = np.asarray(A, np.float64).reshape(-1, 4)[:3]
@@ -82,7 +95,8 @@ def compare_features(cloud, F_dev, F_ref, angle_step, dist_step):
     bad = (diff > FEAT_TOL[:3]).any(axis=1) & ok
     assert not bad.any(), f"{bad.sum()} pair features beyond tolerance, worst {diff[ok].max(axis=0)}"
     da = circ_diff(F_dev[v, 4], F_ref[v, 4])
-    assert (da[ok] <= ALPHA_TOL).all(), f"alpha_m beyond tolerance: {da[ok].max()}"
+    atol = alpha_tolerance(cloud, i, j)
+    assert (da[ok] <= atol[ok]).all(), f"alpha_m beyond tolerance: {(da[ok] / atol[ok]).max()} x tol"
     # key agreement rule
     qd = quantise(F_dev[v, :4], angle_step, dist_step)
     qr = quantise(F_ref[v, :4], angle_step, dist_step)

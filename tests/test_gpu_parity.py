@@ -60,7 +60,9 @@ def test_k1_drost_modes(bottle, oracle, mode):
     v = ~np.isnan(ref[:, 0])
     assert np.array_equal(F[v, 3], ref[v, 3])
     assert np.abs(F[v, :3].astype(np.float64) - ref[v, :3]).max() < 4e-6
-    assert parity.circ_diff(F[v, 4], ref[v, 4]).max() < parity.ALPHA_TOL
+    vi = np.flatnonzero(v)
+    atol = parity.alpha_tolerance(sub, vi // len(sub), vi % len(sub))
+    assert (parity.circ_diff(F[v, 4], ref[v, 4]) <= atol).all()
 
 
 def test_k1_partial_download_and_bounds(ctx, dev_bottle):
@@ -206,7 +208,9 @@ def test_k3_scene_pairs_vs_oracle(ctx, scene_crop, dev_crop, oracle_bottle, tabl
         radius_edge = np.abs(dist - float(radius)) < parity.EDGE_TOL
         assert np.array_equal(inr[~radius_edge], rin[~radius_edge])
         both = (inr > 0) & (rin > 0)
-        assert parity.circ_diff(a[both], ra[both]).max() <= parity.ALPHA_TOL
+        idx_both = np.flatnonzero(both)
+        atol = parity.alpha_tolerance(scene_crop, np.full(len(idx_both), s_r), idx_both)
+        assert (parity.circ_diff(a[both], ra[both]) <= atol).all()
         flip = (d[both] != rd[both])
         if flip.any():
             # recompute the oracle's float features for the flipped pairs and apply the edge rule
