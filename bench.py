@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — scene point-pairs voted per second (and ms per 6-D pose) of the PPF hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2] [--impl reference]
+
+A step is one PPFRegistration::align of the workload's scene against its (pre-built, resident)
+model table: K3 voting over this rank's shard of scene reference points, K3b pose assembly, the
+all-gather of 64-byte hypotheses (N > 1, NCCL), K4 clustering.  Building the model table is the
+reference's *offline* training step (include/CloudProcessing.h:222-261 / :106-121) and is reported
+separately (table_build_ms), not inside the step.
+
+  value     in-radius scene point pairs (PCL's inner-loop trip count, "pairs voted") per second,
+            scene + table resident in HBM, per-step CUDA events on the context stream, max over ranks
+  e2e       the same through the host-buffer C ABI: every step uploads the scene from pinned host
+            memory, runs align and reads the poses back
+  roofline  the voting kernel: algorithmic bytes / its CUDA-event duration vs measured HBM
+  cpu_baseline  the CPU oracle (port of PCL's loop, 1 thread = PCL as shipped) on a bounded sample
+
+--impl reference times the CPU oracle with every host thread on the same workload (bounded sample
+of reference points per step).  The oracle is test infrastructure: it is only ever the baseline here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scene_point_pairs_voted_per_sec"
+UNIT = "pairs/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def oracle_table(wl):
+    from oracle import binding as ob
+    ob.build()
+    feats = ob.ppf_estimation(wl.model)
+    hm = ob.HashMap(wl.angle_step, wl.dist_step).set_input_feature_cloud(feats)
+    return ob, hm
+
+
+def cpu_sample_refs(wl, n_sample):
+    """Evenly spread sample of reference slots (same refs every run)."""
+    n_sample = min(n_sample, wl.n_ref)
+    step = max(1, wl.n_ref // n_sample)
+    return 0, step * wl.ref_rate, n_sample
+
+
+def run_reference(args, wl):
+    """The reference arm: CPU oracle, all host threads, bounded sample of reference points per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ob, hm = oracle_table(wl)
+    threads = ob.max_threads()
+    first, step, count = cpu_sample_refs(wl, args.cpu_sample)
+    times, pairs = [], 0
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        hyps, st = hm.vote(wl.model, wl.scene, first, step, count, n_threads=threads)
+        ob.cluster(hyps, wl.pos_thr, wl.rot_thr)
+        dt = time.perf_counter() - t0
+        if k >= args.warmup:
+            times.append(dt)
+            pairs = st["pairs_in_radius"]
+    ms = 1e3 * float(np.mean(times))
+    value = pairs / (ms * 1e-3)
+    sample = f"{count} of {wl.n_ref} reference points per step (every {step // wl.ref_rate}-th), full scene, vote + cluster"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": wl.data, "config": {"workload": f"{wl.name}: {wl.description}", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_pose_extrapolated": ms * wl.n_ref / count,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+    from yolo_ppf_pose_estimation_b200 import capi, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = capi.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    n_ref = wl.n_ref
+    first, step, count = workloads.shard(n_ref, rank, world)
+    chunk = (n_ref + world - 1) // world
+    with torch.cuda.stream(stream):
+        local_buf = torch.zeros((chunk, 16), dtype=torch.float32, device=dev)
+        gathered = torch.zeros((world * chunk, 16), dtype=torch.float32, device=dev) if world > 1 else local_buf
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- offline stage: model upload + table build (reported, not part of the step) ---------------
+    dm = ctx.upload_cloud(wl.model)
+    t0 = time.perf_counter()
+    table = ctx.table_build_from_cloud(dm, wl.angle_step, wl.dist_step)
+    table_build_ms = 1e3 * (time.perf_counter() - t0)
+    tim = ctx.timings()
+    info = table.info
+    ds_resident = ctx.upload_cloud(wl.scene)
+    scene_pinned = torch.from_numpy(np.ascontiguousarray(wl.scene, np.float32)).pin_memory()
+    n_s = wl.scene.shape[0]
+
+    def align(ds):
+        """vote (this rank's shard) -> all-gather -> cluster; returns (poses, votes)."""
+        ctx.vote_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, local_buf.data_ptr())
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, local_buf)
+                # rank-major [world][chunk] -> reference order k = c*world + g
+                ordered = gathered.view(world, chunk, 16).transpose(0, 1).contiguous()
+            ptr = ordered.data_ptr()
+            res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=ptr, n=n_ref)
+            del ordered
+            return res
+        return ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=local_buf.data_ptr(), n=n_ref)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(make_scene, k_steps):
+        """per-step CUDA events on the context stream; L2 flushed between steps outside the brackets"""
+        total, vote_ms, launches = 0.0, [], 0
+        for _ in range(k_steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.launch_count
+            e0.record(stream)
+            poses, votes = align(make_scene())
+            e1.record(stream)
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+            launches += ctx.launch_count - l0
+            vote_ms.append(ctx.timings()["vote_ms"])
+        return total, vote_ms, launches, poses, votes
+
+    # ---- resident-input measurement ---------------------------------------------------------------
+    barrier()
+    timed_steps(lambda: ds_resident, args.warmup)
+    stats = ctx.vote_stats()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0 and os.environ.get("BENCH_CLOCKS", "1") != "0":
+        sampler.start()
+    total_ms, vote_ms, launches, poses, votes = timed_steps(lambda: ds_resident, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-buffer API: H2D scene every step, poses read back -------------
+    def upload():
+        return ctx.upload_cloud((scene_pinned.data_ptr(), n_s), stride=6, normal_offset=3)
+    timed_steps(upload, min(args.warmup, 3))
+    barrier()
+    e2e_total_ms, _, _, _, _ = timed_steps(upload, args.steps)
+    barrier()
+
+    # whole-job numbers: max over ranks of the time, sum over ranks of the work
+    t = torch.tensor([total_ms, e2e_total_ms, float(np.mean(vote_ms))], dtype=torch.float64, device=dev)
+    w = torch.tensor([stats["pairs_in_radius"], stats["votes"], stats["pairs_examined"], stats["nonempty_lookups"]],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    total_ms, e2e_total_ms, vote_kernel_ms = (float(x) for x in t.cpu())
+    pairs, nvotes, examined, nonempty = (float(x) for x in w.cpu())
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = pairs / (ms_per_step * 1e-3)
+        e2e_ms = e2e_total_ms / args.steps
+        peak, peak_src = measured_peaks()
+        # algorithmic bytes of one voting launch on one rank (DESIGN.md "K3 roofline"):
+        #   8 B gathered per vote; per in-radius pair and slice 8 B of CSR offsets + 32 B of point/normal;
+        #   16 B per scene point per resident wave of CTAs for the position sweep
+        my_pairs, my_votes = stats["pairs_in_radius"], stats["votes"]
+        ctas = count * info.n_slices
+        waves = max(1, -(-ctas // (148 * 2)))
+        alg_bytes = 8.0 * my_votes + 40.0 * my_pairs * info.n_slices + 16.0 * n_s * waves
+        k3_ms = float(np.mean(vote_ms))
+        achieved = alg_bytes / (k3_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": wl.data,
+            "config": {"workload": f"{wl.name}: {wl.description}", "n_model": int(info.n_model), "n_scene": n_s,
+                       "n_ref": n_ref, "angle_step_deg": 12, "dist_step": float(wl.dist_step),
+                       "table_entries": int(info.n_entries), "accumulator_slices": int(info.n_slices),
+                       "sharding": f"reference points interleaved over {world} rank(s), table + scene replicated, "
+                                   f"all-gather of 64 B hypotheses" if world > 1 else "single GPU",
+                       "l2": "256 MiB memset between steps, outside the per-step CUDA-event brackets"},
+            "ms_per_pose": ms_per_step,
+            "votes_per_sec": nvotes / (ms_per_step * 1e-3),
+            "pairs_examined_per_sec": examined / (ms_per_step * 1e-3),
+            "work_per_step": {"pairs_in_radius": pairs, "votes": nvotes, "pairs_examined": examined},
+            "result": {"votes": [int(v) for v in votes], "translation": [float(x) for x in poses[0][:3, 3]] if len(poses) else None},
+            "table_build_ms": table_build_ms,
+            "table_build_stage_ms": {k: tim[k] for k in ("keys_ms", "sort_ms", "csr_ms")},
+            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(2 * 16 * n_s), "d2h_bytes_per_step": int(3 * 16 * 4 + 8 * 4 + 8)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "ppf_vote_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": k3_ms, "kernel_ms_max_over_ranks": vote_kernel_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "votes_per_sec_in_kernel": my_votes / (k3_ms * 1e-3),
+                         "note": "shared-memory atomics, not HBM, bind this kernel: 1 shared atomic per vote"},
+        }
+        if world == 1 and not args.no_cpu:
+            ob, hm = oracle_table(wl)
+            f0, st0, cnt = cpu_sample_refs(wl, args.cpu_sample)
+            t0 = time.perf_counter()
+            _, cst = hm.vote(wl.model, wl.scene, f0, st0, cnt, n_threads=1)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": cst["pairs_in_radius"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{cnt} of {n_ref} reference points (every {st0 // wl.ref_rate}-th), full scene, "
+                                              f"voting loop only, {dt:.1f} s", "votes_per_sec": cst["votes"] / dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--cpu-sample", type=int, default=192, help="reference points in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    from yolo_ppf_pose_estimation_b200 import workloads
+    wl = workloads.load(args.workload)
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,8 +90,8 @@ typedef struct b200ppf_table_info {
 
 /* per-stage device times of the last call on this context, milliseconds (CUDA events) */
 typedef struct b200ppf_timings {
-    float upload_ms, features_ms, keys_ms, sort_ms, csr_ms, vote_ms, pose_ms, cluster_ms,
-        transform_ms, download_ms;
+    float upload_ms, features_ms, keys_ms, sort_ms, csr_ms, grid_ms, vote_ms, pose_ms, cluster_ms,
+        transform_ms;
 } b200ppf_timings;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -104,7 +104,7 @@ int b200ppf_set_alpha_mode(b200ppf_ctx *ctx, int alpha_mode);
 int b200ppf_get_device(const b200ppf_ctx *ctx);
 void *b200ppf_get_stream(const b200ppf_ctx *ctx); /* cudaStream_t */
 int b200ppf_synchronize(b200ppf_ctx *ctx);
-int b200ppf_get_timings(const b200ppf_ctx *ctx, b200ppf_timings *out);
+int b200ppf_get_timings(b200ppf_ctx *ctx, b200ppf_timings *out);
 /* number of kernels this context has launched so far */
 uint64_t b200ppf_launch_count(const b200ppf_ctx *ctx);
 

@@ -257,7 +257,8 @@ def test_k3_hypotheses(ctx, bottle, scene_crop, dev_bottle, dev_crop, oracle, or
     assert len(hy) == len(ref) == (scene_crop.shape[0] + 4) // 5
     assert np.array_equal(hy["scene_index"], ref["scene_index"])
     st = ctx.vote_stats()
-    assert st["pairs_examined"] == len(hy) * (scene_crop.shape[0] - 1)
+    # candidates met in the 27-cell neighbourhoods: at least the in-radius ones, far fewer than brute force
+    assert st["pairs_in_radius"] <= st["pairs_examined"] < len(hy) * (scene_crop.shape[0] - 1)
     assert abs(st["pairs_in_radius"] - stats["pairs_in_radius"]) <= 0.001 * stats["pairs_in_radius"] + 2
     assert abs(st["votes"] - stats["votes"]) <= 0.002 * stats["votes"]
     same_peak = (hy["model_index"] == ref["model_index"]) & (hy["alpha_bin"] == ref["alpha_bin"])

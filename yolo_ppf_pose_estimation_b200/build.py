@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 BUILD_DIR = os.path.join(_HERE, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libb200ppf.so")
 
-SOURCES = ["capi.cu", "radix_sort.cu", "k1_features.cu", "k2_table.cu", "k3_vote.cu", "k4_cluster.cu",
+SOURCES = ["capi.cu", "radix_sort.cu", "k1_features.cu", "k2_table.cu", "k3_vote.cu", "scene_grid.cu", "k4_cluster.cu",
            "k5_transform.cu"]
 HEADERS = ["ppf_common.cuh", "ppf_math.cuh", os.path.join("..", "..", "include", "b200ppf.h")]
 

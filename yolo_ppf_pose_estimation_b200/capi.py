@@ -33,8 +33,8 @@ class TableInfo(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ("upload_ms", "features_ms", "keys_ms", "sort_ms", "csr_ms", "vote_ms",
-                                         "pose_ms", "cluster_ms", "transform_ms", "download_ms")]
+    _fields_ = [(n, C.c_float) for n in ("upload_ms", "features_ms", "keys_ms", "sort_ms", "csr_ms", "grid_ms",
+                                         "vote_ms", "pose_ms", "cluster_ms", "transform_ms")]
 
 
 # every symbol include/b200ppf.h declares: (name, restype, argtypes)

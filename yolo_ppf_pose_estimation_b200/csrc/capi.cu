@@ -70,6 +70,7 @@ int b200ppf_create(int device, b200ppf_ctx **out) {
         return fail_msg(nullptr, B200PPF_ERR_CUDA, "b200ppf_create: cudaStreamCreate failed");
     }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto &ev : ctx->ev_vote) cudaEventCreate(&ev);
     *out = ctx;
     return B200PPF_OK;
 }
@@ -83,6 +84,8 @@ void b200ppf_destroy(b200ppf_ctx *ctx) {
     if (ctx->d_hyps) cudaFree(ctx->d_hyps);
     if (ctx->d_assign) cudaFree(ctx->d_assign);
     for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_vote)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -120,8 +123,16 @@ int b200ppf_synchronize(b200ppf_ctx *ctx) {
     return B200PPF_OK;
 }
 
-int b200ppf_get_timings(const b200ppf_ctx *ctx, b200ppf_timings *out) {
+int b200ppf_get_timings(b200ppf_ctx *ctx, b200ppf_timings *out) {
     if (!ctx || !out) return fail_msg(nullptr, B200PPF_ERR_INVALID, "null argument");
+    if (ctx->vote_timed) {  // the vote is asynchronous: resolve its events on demand
+        DeviceGuard guard(ctx->device);
+        if (cudaEventSynchronize(ctx->ev_vote[3]) == cudaSuccess) {
+            cudaEventElapsedTime(&ctx->timings.grid_ms, ctx->ev_vote[0], ctx->ev_vote[1]);
+            cudaEventElapsedTime(&ctx->timings.vote_ms, ctx->ev_vote[1], ctx->ev_vote[2]);
+            cudaEventElapsedTime(&ctx->timings.pose_ms, ctx->ev_vote[2], ctx->ev_vote[3]);
+        }
+    }
     *out = ctx->timings;
     return B200PPF_OK;
 }
@@ -377,10 +388,6 @@ int b200ppf_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_tab
         PPF_CUDA(ctx, cudaMemcpyAsync(hyps_host, ctx->d_hyps, ref_count * sizeof(b200ppf_hypothesis),
                                       cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ref_count) {
-        cudaEventElapsedTime(&ctx->timings.vote_ms, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&ctx->timings.pose_ms, ctx->ev[1], ctx->ev[2]);
-    }
     return B200PPF_OK;
 }
 
@@ -483,11 +490,6 @@ int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf
     }
     int rc = k3_vote(ctx, model, t, scene, 0, ref_rate, ref_count, ctx->d_hyps);
     if (rc) return rc;
-    cudaEvent_t v0 = ctx->ev[0], v1 = ctx->ev[1], v2 = ctx->ev[2];
-    // k4 reuses ev[0..1]; take the vote timings first
-    PPF_CUDA(ctx, cudaEventSynchronize(v2));
-    cudaEventElapsedTime(&ctx->timings.vote_ms, v0, v1);
-    cudaEventElapsedTime(&ctx->timings.pose_ms, v1, v2);
     rc = k4_cluster(ctx, ctx->d_hyps, ref_count, pos_thr, rot_thr, poses16, votes, n_out);
     if (rc) return rc;
     if (*n_out && final16) memcpy(final16, poses16, 16 * sizeof(float));

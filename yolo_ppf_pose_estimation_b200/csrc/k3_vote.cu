@@ -8,16 +8,17 @@
 //
 // One CTA per (reference point, accumulator slice).  The accumulator slice — up to ~1800 model
 // rows x n_alpha 32-bit counters — lives in shared memory for the CTA's whole life, votes are
-// shared-memory atomics, the peak is a warp-shuffle argmax, and slices merge through one 64-bit
-// atomicMax per CTA on a packed (votes, ~flat index) word, which reproduces PCL's tie-break.
-// The CTA works in three phases that keep all 32 lanes busy:
-//   A  scan   coalesced float4 sweep over the scene positions, distance predicate only,
-//             survivors compacted into a shared candidate queue with one warp-aggregated atomic;
+// shared-memory reductions (red.shared.add), the peak is a warp-shuffle argmax, and slices merge
+// through one 64-bit atomicMax per CTA on a packed (votes, ~flat index) word, which reproduces
+// PCL's tie-break.  Three phases keep the lanes busy:
+//   A  sweep  the 27-cell neighbourhood of the reference point in the cell-sorted scene
+//             (scene_grid.cu) is 9 contiguous runs of float4 positions; the radius predicate
+//             survivors are compacted into a shared candidate queue (one warp-aggregated atomic);
 //   B  pair   one thread per candidate: pair feature, key, CSR bucket bounds, alpha_s -> work item;
-//   C  vote   warps pull work items and walk the bucket 32 entries at a time: one coalesced 8-byte
-//             gather {row offset, alpha_m} and one shared atomic per vote.
+//   C  vote   warps pull work items and walk the bucket 4 x 32 entries at a time: four coalesced
+//             8-byte gathers {row offset, alpha_m} in flight per lane, one shared reduction per vote.
 // Roofline: 8 B gathered + 1 shared atomic per vote, 8 B of CSR offsets per
-// in-radius pair; shared-atomic throughput is the binding limit, not HBM.
+// in-radius pair; instruction issue and shared-atomic throughput bind, not HBM.
 #include <algorithm>
 #include <cmath>
 
@@ -27,12 +28,12 @@ namespace b200ppf {
 
 namespace {
 
-constexpr int VOTE_THREADS = 256;
+constexpr int VOTE_THREADS = 512;
 constexpr int VOTE_WARPS = VOTE_THREADS / 32;
-constexpr int CAND_CAP = 2048;    // in-radius candidates buffered between flushes
-constexpr int SCAN_TILES = 4;     // scene tiles swept between two capacity checks
+constexpr int CAND_CAP = 2048;  // in-radius candidates buffered between flushes
 constexpr int ITEM_CAP = VOTE_THREADS;
-static_assert(CAND_CAP >= 2 * SCAN_TILES * VOTE_THREADS, "flush threshold must leave a full sweep of room");
+constexpr int VOTE_UNROLL = 4;
+static_assert(CAND_CAP >= 2 * VOTE_THREADS, "flush threshold must leave one sweep iteration of room");
 
 struct WorkItem {
     uint32_t off, len;
@@ -43,7 +44,11 @@ constexpr size_t QUEUE_BYTES = CAND_CAP * sizeof(uint32_t) + ITEM_CAP * sizeof(W
 constexpr size_t STATIC_RESERVE = 2048;  // static shared + the 1 KB the system reserves per CTA
 
 struct VoteArgs {
-    const float4 *pos, *nrm;
+    const float4 *pos, *nrm;    // scene, original order (reference points are addressed by index)
+    const float4 *gpos, *gnrm;  // scene, cell-sorted
+    const uint32_t *gorig;      // cell-sorted position -> original index
+    const uint32_t *cell_start;
+    GridParams gp;
     uint32_t n_s;
     uint32_t ref_first, ref_step, ref_count;
     const uint32_t *offsets;
@@ -52,6 +57,7 @@ struct VoteArgs {
     BinParams bp;
     int feature_mode;
     float radius;
+    float radius_sq_bound;  // smallest float x with sqrtf(x) >= radius:  sqrtf(d2) < radius <=> d2 < bound
     uint32_t n_model;
     unsigned long long *peaks;
     unsigned long long *stats;
@@ -62,11 +68,45 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return __shfl_xor_sync(0xFFFFFFFFu, v, o);
 }
 
-__global__ void __launch_bounds__(VOTE_THREADS)
+__device__ __forceinline__ void red_shared_inc(uint32_t shared_addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(shared_addr) : "memory");
+}
+
+// one vote: bin of (alpha_m - alpha_s) and a shared-memory increment.  Mode A's hot form is
+// branch-free; the literal double-precision form decides only inside the guard band
+// (ppf_math.cuh, alpha_bin_fast — same arithmetic, laid out for the loop).
+template <int MODE>
+__device__ __forceinline__ uint32_t vote_one(const BinParams &bp, uint32_t acc_addr, uint2 en, float alpha_s) {
+    const float alpha_m = __uint_as_float(en.y);
+    uint32_t bin;
+    if (MODE == ALPHA_MODE_B) {
+        bin = alpha_bin_fast(bp, alpha_m, alpha_s);
+    } else {
+        const float d = alpha_m - alpha_s;
+        float w = d;
+        if (d <= -3.14159274f) w = d + 6.28318548f;
+        else if (d >= 3.14159274f) w = d - 6.28318548f;
+        const float q = (w + 3.14159274f) * bp.inv_step;
+        const float fl = floorf(q);
+        const float fr = q - fl;
+        int b = (int)fl;
+        b = max(b, 0);
+        bin = min((uint32_t)b, bp.n_alpha - 1u);
+        if (!(fr > bp.guard && fr < 1.0f - bp.guard))  // rare; also catches NaN
+            bin = alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
+    }
+    if (bin == 0xFFFFFFFFu) return 0u;
+    red_shared_inc(acc_addr + ((en.x + bin) << 2));
+    return 1u;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(VOTE_THREADS, 2)
 ppf_vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Frame s_sg;
     __shared__ uint32_t s_ncand, s_nitems, s_next;
+    __shared__ uint32_t s_run_start[9], s_run_end[9];
     __shared__ unsigned long long s_best[VOTE_WARPS];
     __shared__ unsigned long long s_stat[4];
 
@@ -78,6 +118,7 @@ ppf_vote_kernel(const VoteArgs a) {
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *cand = acc + (size_t)a.kp.slice_rows * a.bp.n_alpha;
     WorkItem *items = reinterpret_cast<WorkItem *>(cand + CAND_CAP);
+    const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
 
     const uint32_t s_r = a.ref_first + blockIdx.x * a.ref_step;
     const float4 pr4 = a.pos[s_r], nr4 = a.nrm[s_r];
@@ -89,11 +130,26 @@ ppf_vote_kernel(const VoteArgs a) {
         s_next = 0;
     }
     if (tid < 4) s_stat[tid] = 0;
+    if (tid >= 32 && tid < 41) {
+        // the 3 x-adjacent cells of row (cy+dy, cz+dz) are one contiguous run of the sorted scene
+        const int r = (int)tid - 32;
+        const int cx = grid_cell_coord(a.gp, p_r.x, 0), cy = grid_cell_coord(a.gp, p_r.y, 1),
+                  cz = grid_cell_coord(a.gp, p_r.z, 2);
+        const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+        uint32_t b = 0, e = 0;
+        if (y >= 0 && y < a.gp.dims[1] && z >= 0 && z < a.gp.dims[2]) {
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.gp.dims[0] - 1);
+            b = a.cell_start[grid_cell_linear(a.gp, x0, y, z)];
+            e = a.cell_start[grid_cell_linear(a.gp, x1, y, z) + 1];
+        }
+        s_run_start[r] = b;
+        s_run_end[r] = e;
+    }
     for (uint32_t k = tid; k < acc_len; k += VOTE_THREADS) acc[k] = 0;
     __syncthreads();
 
     const uint32_t *slice_offsets = a.offsets + (size_t)slice * a.kp.key_space;
-    uint32_t st_in_radius = 0, st_nonempty = 0, st_votes = 0;
+    uint32_t st_examined = 0, st_in_radius = 0, st_nonempty = 0, st_votes = 0;
 
     // phases B + C over the buffered candidates
     auto flush = [&]() {
@@ -107,7 +163,7 @@ ppf_vote_kernel(const VoteArgs a) {
             it.alpha_s = 0.0f;
             if (c < ncand) {
                 const uint32_t s = cand[c];
-                const float4 p4 = a.pos[s], n4 = a.nrm[s];
+                const float4 p4 = __ldg(a.gpos + s), n4 = __ldg(a.gnrm + s);
                 float f[4];
                 if (pair_features(a.feature_mode, p_r, n_r, v3_of(p4), v3_of(n4), f)) {
                     ++st_in_radius;
@@ -143,12 +199,17 @@ ppf_vote_kernel(const VoteArgs a) {
                 if (w >= nitems) break;
                 const WorkItem wi = items[w];
                 const uint2 *e = a.entries + wi.off;
-                for (uint32_t k = lane; k < wi.len; k += 32) {
-                    const uint2 en = __ldg(e + k);
-                    const uint32_t bin = alpha_bin_fast(a.bp, __uint_as_float(en.y), wi.alpha_s);
-                    if (bin != 0xFFFFFFFFu) {
-                        atomicAdd(&acc[en.x + bin], 1u);
-                        ++st_votes;
+                for (uint32_t k0 = 0; k0 < wi.len; k0 += 32 * VOTE_UNROLL) {
+                    uint2 en[VOTE_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < VOTE_UNROLL; ++u) {
+                        const uint32_t k = k0 + u * 32 + lane;
+                        en[u] = k < wi.len ? __ldg(e + k) : make_uint2(0u, 0u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < VOTE_UNROLL; ++u) {
+                        const uint32_t k = k0 + u * 32 + lane;
+                        if (k < wi.len) st_votes += vote_one<MODE>(a.bp, acc_addr, en[u], wi.alpha_s);
                     }
                 }
             }
@@ -163,16 +224,20 @@ ppf_vote_kernel(const VoteArgs a) {
         __syncthreads();
     };
 
-    // ---- A: sweep the scene -----------------------------------------------------------------------
-    for (uint32_t base = 0; base < a.n_s; base += SCAN_TILES * VOTE_THREADS) {
-#pragma unroll
-        for (int t = 0; t < SCAN_TILES; ++t) {
-            const uint32_t s = base + t * VOTE_THREADS + tid;
+    // ---- A: sweep the 27-cell neighbourhood ---------------------------------------------------------
+    for (int r = 0; r < 9; ++r) {
+        const uint32_t rb = s_run_start[r], re = s_run_end[r];
+        for (uint32_t base = rb; base < re; base += VOTE_THREADS) {
+            const uint32_t s = base + tid;
             bool in = false;
-            if (s < a.n_s && s != s_r) {
-                const float4 p4 = __ldg(a.pos + s);
-                const V3 d = make_v3(p4.x - p_r.x, p4.y - p_r.y, p4.z - p_r.z);
-                in = norm3(d) < a.radius;  // radius predicate on f4 itself (SURVEY.md A.8 rule 7)
+            if (s < re) {
+                const float4 p4 = __ldg(a.gpos + s);
+                const float dx = p4.x - p_r.x, dy = p4.y - p_r.y, dz = p4.z - p_r.z;
+                const float d2 = (dx * dx + dy * dy) + dz * dz;
+                // radius predicate on f4 itself (SURVEY.md A.8 rule 7): sqrtf(d2) < radius, evaluated
+                // through the equivalent threshold on d2 (sqrtf is monotone and correctly rounded)
+                in = d2 < a.radius_sq_bound && __ldg(a.gorig + s) != s_r;
+                ++st_examined;
             }
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
             if (m) {
@@ -181,11 +246,11 @@ ppf_vote_kernel(const VoteArgs a) {
                 b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
                 if (in) cand[b + __popc(m & ((1u << lane) - 1u))] = s;
             }
+            __syncthreads();
+            const uint32_t buffered = s_ncand;
+            __syncthreads();  // nobody may start the next sweep's atomics before everyone has read
+            if (buffered > CAND_CAP - VOTE_THREADS) flush();
         }
-        __syncthreads();
-        const uint32_t buffered = s_ncand;
-        __syncthreads();  // nobody may start the next sweep's atomics before everyone has read
-        if (buffered > CAND_CAP - SCAN_TILES * VOTE_THREADS) flush();
     }
     flush();
 
@@ -202,15 +267,16 @@ ppf_vote_kernel(const VoteArgs a) {
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, shfl_xor_u64(best, o));
-    // stats: warp reduce then shared
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+        st_examined += __shfl_xor_sync(0xFFFFFFFFu, st_examined, o);
         st_in_radius += __shfl_xor_sync(0xFFFFFFFFu, st_in_radius, o);
         st_nonempty += __shfl_xor_sync(0xFFFFFFFFu, st_nonempty, o);
         st_votes += __shfl_xor_sync(0xFFFFFFFFu, st_votes, o);
     }
     if (lane == 0) {
         s_best[warp] = best;
+        atomicAdd(&s_stat[0], (unsigned long long)st_examined);
         atomicAdd(&s_stat[1], (unsigned long long)st_in_radius);
         atomicAdd(&s_stat[2], (unsigned long long)st_nonempty);
         atomicAdd(&s_stat[3], (unsigned long long)st_votes);
@@ -221,7 +287,7 @@ ppf_vote_kernel(const VoteArgs a) {
         for (int w = 1; w < VOTE_WARPS; ++w) best = max(best, s_best[w]);
         if (best) atomicMax(a.peaks + blockIdx.x, best);
         if (slice == 0) {
-            atomicAdd(a.stats + 0, (unsigned long long)(a.n_s - 1));
+            atomicAdd(a.stats + 0, s_stat[0]);
             atomicAdd(a.stats + 1, s_stat[1]);
         }
         atomicAdd(a.stats + 2, s_stat[2]);
@@ -295,11 +361,32 @@ size_t vote_smem_bytes(const b200ppf_table *t) {
     return (size_t)t->info.slice_rows * t->info.n_alpha * sizeof(uint32_t) + QUEUE_BYTES;
 }
 
+// smallest float x with sqrtf(x) >= r (host sqrtf and device sqrtf are both correctly rounded)
+float radius_sq_bound(float r) {
+    if (!(r > 0.0f)) return 0.0f;
+    float x = r * r;
+    while (std::sqrt(x) >= r) x = std::nextafter(x, 0.0f);
+    while (std::sqrt(x) < r) x = std::nextafter(x, INFINITY);
+    return x;
+}
+
 int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_first,
                 size_t ref_step, size_t ref_count, uint32_t *acc_dump) {
+    const float radius = t->info.max_dist * 0.5f;
+    SceneGrid grid;
+    int rc = scene_grid_build(ctx, scene, radius, &grid);
+    if (rc) {
+        scene_grid_free(ctx, &grid);
+        return rc;
+    }
     VoteArgs a;
     a.pos = scene->pos;
     a.nrm = scene->nrm;
+    a.gpos = grid.pos;
+    a.gnrm = grid.nrm;
+    a.gorig = grid.orig;
+    a.cell_start = grid.cell_start;
+    a.gp = grid.gp;
     a.n_s = (uint32_t)scene->n;
     a.ref_first = (uint32_t)ref_first;
     a.ref_step = (uint32_t)ref_step;
@@ -310,15 +397,24 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     a.bp = t->bp;
     a.bp.mode = ctx->alpha_mode;
     a.feature_mode = t->feature_mode;
-    a.radius = t->info.max_dist * 0.5f;
+    a.radius = radius;
+    a.radius_sq_bound = radius_sq_bound(radius);
     a.n_model = (uint32_t)t->info.n_model;
     a.peaks = ctx->d_peaks;
     a.stats = ctx->d_stats;
     a.acc_dump = acc_dump;
     const size_t smem = vote_smem_bytes(t);
-    PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)ref_count, t->info.n_slices);
-    PPF_LAUNCH(ctx, ppf_vote_kernel, grid, VOTE_THREADS, smem, a);
+    dim3 grid_dim((unsigned)ref_count, t->info.n_slices);
+    cudaEventRecord(ctx->ev_vote[1], ctx->stream);  // grid build ends, voting starts
+    if (ctx->alpha_mode == ALPHA_MODE_B) {
+        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<ALPHA_MODE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPF_LAUNCH(ctx, ppf_vote_kernel<ALPHA_MODE_B>, grid_dim, VOTE_THREADS, smem, a);
+    } else {
+        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<ALPHA_MODE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPF_LAUNCH(ctx, ppf_vote_kernel<ALPHA_MODE_A>, grid_dim, VOTE_THREADS, smem, a);
+    }
+    cudaEventRecord(ctx->ev_vote[2], ctx->stream);
+    scene_grid_free(ctx, &grid);
     return B200PPF_OK;
 }
 
@@ -404,16 +500,16 @@ int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t
     if (ref_count == 0) return B200PPF_OK;
     rc = ensure_vote_scratch(ctx, ref_count);
     if (rc) return rc;
-    cudaEventRecord(ctx->ev[0], ctx->stream);
-    rc = launch_vote(ctx, t, scene, ref_first, ref_step, ref_count, nullptr);
+    cudaEventRecord(ctx->ev_vote[0], ctx->stream);
+    rc = launch_vote(ctx, t, scene, ref_first, ref_step, ref_count, nullptr);  // records ev_vote[1], [2]
     if (rc) return rc;
-    cudaEventRecord(ctx->ev[1], ctx->stream);
     BinParams bp = t->bp;
     bp.mode = ctx->alpha_mode;
     PPF_LAUNCH(ctx, ppf_peak_pose_kernel, (unsigned)((ref_count + 127) / 128), 128, 0, scene->pos, scene->nrm,
                model->pos, model->nrm, (uint32_t)ref_first, (uint32_t)ref_step, (uint32_t)ref_count, ctx->d_peaks, bp,
                hyps_device);
-    cudaEventRecord(ctx->ev[2], ctx->stream);
+    cudaEventRecord(ctx->ev_vote[3], ctx->stream);
+    ctx->vote_timed = true;
     return B200PPF_OK;
 }
 

@@ -8,15 +8,19 @@
 //   the three best clusters (votes descending, ties by creation order) are averaged
 //   (mean translation, mean quaternion coefficients, normalised).
 //
-// The greedy rule is sequential in the sorted order, but only through the set of leaders.  The
-// device version walks the sorted list in batches of BATCH poses:
-//   match    every (batch pose, existing leader) pair is tested in parallel — leaders are staged
-//            in shared memory a tile at a time, the lowest matching leader wins via atomicMin;
-//   resolve  one CTA settles the poses no earlier leader claimed: the first still-unclaimed pose
-//            of the batch becomes a leader, every later unclaimed pose tests against it in
-//            parallel, repeat.  The serial depth is the number of NEW leaders per batch.
-// Exactly the PCL assignment results, with O(P*C) tests spread over the whole chip.
+// PCL's loop is O(P * C) and serial.  The same assignment is computed here in parallel:
+//   * "pose k founds a cluster  <=>  no EARLIER leader is within bounds of k" is the
+//     lexicographically-first maximal independent set of the within-bounds graph in sorted order.
+//     It is resolved in rounds: an undecided pose becomes a MEMBER as soon as an earlier within-bounds
+//     pose is a LEADER, and a LEADER as soon as every earlier within-bounds pose is a MEMBER.
+//     Decisions only ever use final states, so the fixpoint is PCL's result whatever the timing.
+//   * within-bounds needs |dt| < pos_thr, so poses are hashed by translation cell (edge >=
+//     pos_thr) and only the 27 neighbouring cells are searched: O(P) tests for realistic inputs
+//     instead of P^2/2.  Hash collisions only add candidates that the exact test rejects.
+//   * a MEMBER's cluster is the lowest-ranked LEADER within bounds; cluster creation indices are
+//     the exclusive prefix sum of the leader flags.
 #include <algorithm>
+#include <cmath>
 
 #include "ppf_common.cuh"
 
@@ -24,9 +28,9 @@ namespace b200ppf {
 
 namespace {
 
-constexpr int BATCH = 1024;
-constexpr int LEADER_TILE = 128;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t ST_UNDECIDED = 0, ST_LEADER = 1, ST_MEMBER = 2;
+constexpr int SCAN_BLOCK = 1024;
 
 struct PoseRows {  // 3x4 row-major pose as three float4 rows
     float4 r0, r1, r2;
@@ -38,14 +42,38 @@ __device__ __forceinline__ void rows_to_array(const PoseRows &p, float *a) {
     a[8] = p.r2.x; a[9] = p.r2.y; a[10] = p.r2.z; a[11] = p.r2.w;
 }
 
-__global__ void cluster_keys_kernel(const b200ppf_hypothesis *__restrict__ hyps, uint32_t n,
+struct HashParams {
+    float inv_cell;
+    uint32_t mask;  // table size - 1 (power of two)
+};
+
+__device__ __forceinline__ int cell_of(float v, float inv_cell) { return __float2int_rd(v * inv_cell); }
+
+__device__ __forceinline__ uint32_t cell_hash(int x, int y, int z, uint32_t mask) {
+    uint32_t h = ((uint32_t)x * 73856093u) ^ ((uint32_t)y * 19349663u) ^ ((uint32_t)z * 83492791u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    return h & mask;
+}
+
+__global__ void cluster_max_votes_kernel(const b200ppf_hypothesis *__restrict__ hyps, uint32_t n,
+                                         uint32_t *__restrict__ max_votes) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = p < n ? hyps[p].votes : 0u;
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(max_votes, v);
+}
+
+__global__ void cluster_keys_kernel(const b200ppf_hypothesis *__restrict__ hyps, uint32_t n, uint32_t max_votes,
                                     uint32_t *__restrict__ keys) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n) keys[p] = ~hyps[p].votes;  // ascending ~votes == descending votes
+    if (p < n) keys[p] = max_votes - hyps[p].votes;  // ascending key == descending votes
 }
 
 __global__ void cluster_gather_kernel(const b200ppf_hypothesis *__restrict__ hyps, const uint32_t *__restrict__ order,
-                                      uint32_t n, PoseRows *__restrict__ poses, uint32_t *__restrict__ votes) {
+                                      uint32_t n, HashParams hp, PoseRows *__restrict__ poses,
+                                      uint32_t *__restrict__ votes, uint32_t *__restrict__ cell_keys) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const b200ppf_hypothesis &h = hyps[order[k]];
@@ -55,111 +83,177 @@ __global__ void cluster_gather_kernel(const b200ppf_hypothesis *__restrict__ hyp
     p.r2 = make_float4(h.pose[8], h.pose[9], h.pose[10], h.pose[11]);
     poses[k] = p;
     votes[k] = h.votes;
+    cell_keys[k] = cell_hash(cell_of(h.pose[3], hp.inv_cell), cell_of(h.pose[7], hp.inv_cell),
+                             cell_of(h.pose[11], hp.inv_cell), hp.mask);
 }
 
-// batch poses [b0, b1) against the leaders that existed before the batch
-__global__ void __launch_bounds__(256)
-cluster_match_kernel(const PoseRows *__restrict__ poses, uint32_t b0, uint32_t b1,
-                     const PoseRows *__restrict__ leader_pose, const uint32_t *__restrict__ n_leaders_ptr,
-                     float pos_thr, float rot_thr, uint32_t *__restrict__ match /* [BATCH] */) {
-    __shared__ PoseRows tile[LEADER_TILE];
-    const uint32_t n_leaders = *n_leaders_ptr;
-    const uint32_t l0 = blockIdx.x * LEADER_TILE;
-    if (l0 >= n_leaders) return;
-    const uint32_t tl = min((uint32_t)LEADER_TILE, n_leaders - l0);
-    for (uint32_t t = threadIdx.x; t < tl; t += blockDim.x) tile[t] = leader_pose[l0 + t];
-    __syncthreads();
-    for (uint32_t k = b0 + threadIdx.x; k < b1; k += blockDim.x) {
-        if (match[k - b0] <= l0) continue;  // an earlier tile already claimed it (benign race: only a shortcut)
-        float a[12], b[12];
-        rows_to_array(poses[k], a);
-        for (uint32_t t = 0; t < tl; ++t) {
-            // cheap translation reject first
-            const float dx = a[3] - tile[t].r0.w, dy = a[7] - tile[t].r1.w, dz = a[11] - tile[t].r2.w;
-            if (!(sqrtf((dx * dx + dy * dy) + dz * dz) < pos_thr)) continue;
-            rows_to_array(tile[t], b);
-            if (poses_within(a, b, pos_thr, rot_thr)) {
-                atomicMin(&match[k - b0], l0 + t);
-                break;
-            }
-        }
+__global__ void cluster_cell_offsets_kernel(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t n_cells,
+                                            uint32_t *__restrict__ cell_start) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (sorted_keys[mid] < c) lo = mid + 1; else hi = mid;
     }
+    cell_start[c] = lo;
 }
 
-// settle one batch (single CTA of BATCH threads)
-__global__ void __launch_bounds__(BATCH)
-cluster_resolve_kernel(const PoseRows *__restrict__ poses, uint32_t b0, uint32_t b1, PoseRows *__restrict__ leader_pose,
-                       uint32_t *__restrict__ n_leaders_ptr, float pos_thr, float rot_thr,
-                       uint32_t *__restrict__ match, uint32_t *__restrict__ assign_sorted) {
-    __shared__ uint32_t open_mask[BATCH / 32];
-    __shared__ PoseRows cur;
-    __shared__ uint32_t s_leaders;
-    const uint32_t t = threadIdx.x, k = b0 + t;
-    const bool live = k < b1;
-    uint32_t m = live ? match[t] : 0u;
+// visit every earlier (rank < k) pose that is within bounds of pose k; f(rank j) returns true to stop
+template <class F>
+__device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restrict__ poses,
+                                                        const uint32_t *__restrict__ cell_start,
+                                                        const uint32_t *__restrict__ cell_rank, HashParams hp,
+                                                        uint32_t k, const float *a, float pos_thr, float rot_thr, F f) {
+    const int cx = cell_of(a[3], hp.inv_cell), cy = cell_of(a[7], hp.inv_cell), cz = cell_of(a[11], hp.inv_cell);
+    uint32_t seen[27];
+    int n_seen = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const uint32_t h = cell_hash(cx + dx, cy + dy, cz + dz, hp.mask);
+                bool dup = false;  // two neighbour cells may share a bucket: visit it once
+                for (int q = 0; q < n_seen; ++q) dup |= (seen[q] == h);
+                if (dup) continue;
+                seen[n_seen++] = h;
+                const uint32_t b = cell_start[h], e = cell_start[h + 1];
+                for (uint32_t s = b; s < e; ++s) {
+                    const uint32_t j = cell_rank[s];
+                    if (j >= k) break;  // ranks ascend inside a bucket (stable sort)
+                    const PoseRows pj = poses[j];
+                    const float ddx = a[3] - pj.r0.w, ddy = a[7] - pj.r1.w, ddz = a[11] - pj.r2.w;
+                    if (!(sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz) < pos_thr)) continue;
+                    float bb[12];
+                    rows_to_array(pj, bb);
+                    if (poses_within(a, bb, pos_thr, rot_thr) && f(j)) return;
+                }
+            }
+}
+
+// one round of the ordered independent-set resolution
+__global__ void __launch_bounds__(128)
+cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
+                     const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
+                     volatile uint32_t *state, uint32_t *__restrict__ undecided) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || state[k] != ST_UNDECIDED) return;
     float a[12];
-    if (live) rows_to_array(poses[k], a);
-    if (t == 0) s_leaders = *n_leaders_ptr;
-    const uint32_t open = __ballot_sync(0xFFFFFFFFu, live && m == NONE);
-    if ((t & 31) == 0) open_mask[t >> 5] = open;
-    __syncthreads();
-    uint32_t w0 = 0;
-    for (;;) {
-        // first still-unclaimed pose of the batch (every thread scans the same shared words)
-        uint32_t first = NONE;
-        for (uint32_t w = w0; w < BATCH / 32; ++w) {
-            const uint32_t bits = open_mask[w];
-            if (bits) {
-                first = w * 32 + (__ffs(bits) - 1);
-                w0 = w;
-                break;
-            }
+    rows_to_array(poses[k], a);
+    bool blocked = false, member = false;
+    for_each_earlier_within(poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, [&](uint32_t j) {
+        const uint32_t sj = state[j];
+        if (sj == ST_LEADER) {
+            member = true;
+            return true;
         }
-        if (first == NONE) break;
-        __syncthreads();  // everyone has read open_mask before it changes
-        if (t == first) {
-            m = s_leaders;
-            cur = poses[k];
-            leader_pose[m] = cur;
-            s_leaders = m + 1;
-            atomicAnd(&open_mask[t >> 5], ~(1u << (t & 31)));
-        }
-        __syncthreads();
-        if (live && m == NONE && t > first) {
-            float b[12];
-            rows_to_array(cur, b);
-            if (poses_within(a, b, pos_thr, rot_thr)) {
-                m = s_leaders - 1;
-                atomicAnd(&open_mask[t >> 5], ~(1u << (t & 31)));
-            }
-        }
-        __syncthreads();
-    }
-    if (live) assign_sorted[k] = m;
-    match[t] = NONE;  // ready for the next batch
-    __syncthreads();
-    if (t == 0) *n_leaders_ptr = s_leaders;
+        if (sj == ST_UNDECIDED) blocked = true;
+        return false;
+    });
+    if (member) state[k] = ST_MEMBER;
+    else if (!blocked) state[k] = ST_LEADER;
+    else atomicAdd(undecided, 1u);
 }
 
-__global__ void cluster_votes_kernel(const uint32_t *__restrict__ assign_sorted, const uint32_t *__restrict__ votes,
-                                     const uint32_t *__restrict__ order, uint32_t n,
-                                     uint32_t *__restrict__ cluster_votes, uint32_t *__restrict__ cluster_size,
-                                     uint32_t *__restrict__ assign_input) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+// exclusive prefix sum of the leader flags -> cluster creation index of every leader
+__global__ void __launch_bounds__(SCAN_BLOCK)
+leader_count_kernel(const uint32_t *__restrict__ state, uint32_t n, uint32_t *__restrict__ block_sums) {
+    const uint32_t k = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const int c = __syncthreads_count(k < n && state[k] == ST_LEADER);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = (uint32_t)c;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+leader_scan_blocks_kernel(uint32_t *__restrict__ block_sums, uint32_t n_blocks, uint32_t *__restrict__ total) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += SCAN_BLOCK) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31) >= (uint32_t)o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_tot[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (threadIdx.x >= (uint32_t)o) wi += t;
+            }
+            warp_tot[threadIdx.x] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+        if (i < n_blocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+leader_index_kernel(const uint32_t *__restrict__ state, uint32_t n, const uint32_t *__restrict__ block_sums,
+                    uint32_t *__restrict__ leader_id) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t k = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t v = (k < n && state[k] == ST_LEADER) ? 1u : 0u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_tot[threadIdx.x], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (threadIdx.x >= (uint32_t)o) wi += t;
+        }
+        warp_tot[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    if (k < n) leader_id[k] = v ? block_sums[blockIdx.x] + warp_tot[warp] + __popc(m & ((1u << lane) - 1u)) : NONE;
+}
+
+// every pose -> its cluster (leaders: their own; members: the lowest-ranked leader within bounds)
+__global__ void __launch_bounds__(128)
+cluster_assign_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
+                      const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
+                      const uint32_t *__restrict__ state, const uint32_t *__restrict__ leader_id,
+                      const uint32_t *__restrict__ votes, const uint32_t *__restrict__ order,
+                      uint32_t *__restrict__ assign_sorted, uint32_t *__restrict__ assign_input,
+                      uint32_t *__restrict__ cluster_votes, uint32_t *__restrict__ cluster_size) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const uint32_t c = assign_sorted[k];
+    uint32_t c;
+    if (state[k] == ST_LEADER) {
+        c = leader_id[k];
+    } else {
+        float a[12];
+        rows_to_array(poses[k], a);
+        uint32_t best = NONE;
+        for_each_earlier_within(poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, [&](uint32_t j) {
+            if (state[j] == ST_LEADER) best = min(best, j);
+            return false;
+        });
+        c = best != NONE ? leader_id[best] : 0u;  // a MEMBER always has an earlier leader; guard only
+    }
+    assign_sorted[k] = c;
+    assign_input[order[k]] = c;
     atomicAdd(&cluster_votes[c], votes[k]);
     atomicAdd(&cluster_size[c], 1u);
-    assign_input[order[k]] = c;
 }
 
 // three best clusters: votes descending, creation index ascending (one CTA)
 __global__ void __launch_bounds__(1024)
-cluster_top3_kernel(const uint32_t *__restrict__ cluster_votes, const uint32_t *__restrict__ n_leaders_ptr,
+cluster_top3_kernel(const uint32_t *__restrict__ cluster_votes, const uint32_t *__restrict__ n_clusters_ptr,
                     uint32_t *__restrict__ top /* [3] cluster ids, NONE if absent */) {
     __shared__ unsigned long long s_best[32];
     __shared__ uint32_t chosen[3];
-    const uint32_t nc = *n_leaders_ptr;
+    const uint32_t nc = *n_clusters_ptr;
     for (int round = 0; round < 3; ++round) {
         unsigned long long best = 0;
         for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
@@ -230,11 +324,6 @@ cluster_average_kernel(const PoseRows *__restrict__ poses, const uint32_t *__res
     }
 }
 
-__global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
 }  // namespace
 
 int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, float pos_thr, float rot_thr,
@@ -244,29 +333,43 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     if (n_ >= 0x7FFFFFFFull) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "cluster: too many hypotheses");
     const uint32_t n = (uint32_t)n_;
     cudaStream_t st = ctx->stream;
-    uint32_t *keys[2] = {nullptr, nullptr}, *order[2] = {nullptr, nullptr};
-    PoseRows *poses = nullptr, *leader_pose = nullptr;
-    uint32_t *votes = nullptr, *assign_sorted = nullptr, *match = nullptr, *cl_votes = nullptr, *cl_size = nullptr;
-    uint32_t *small = nullptr;  // n_leaders, top[3], out_votes[3]
-    float *d_out = nullptr;
     cudaEventRecord(ctx->ev[0], st);
-    for (int b = 0; b < 2; ++b) {
-        PPF_CUDA(ctx, cudaMallocAsync(&keys[b], n * sizeof(uint32_t), st));
-        PPF_CUDA(ctx, cudaMallocAsync(&order[b], n * sizeof(uint32_t), st));
+
+    // translation hash grid: cell edge >= pos_thr (margin absorbs the rounding of the cell coordinate)
+    HashParams hp;
+    {
+        double cell = std::isinf(pos_thr) ? 1e30 : (pos_thr > 0.0f ? (double)pos_thr * 1.001 : 1e-6);
+        cell = std::max(cell, 1e-6);
+        hp.inv_cell = (float)(1.0 / cell);
+        int bits = 8;
+        while ((1u << bits) < 2u * n && bits < 22) ++bits;
+        hp.mask = (1u << bits) - 1u;
     }
-    PPF_CUDA(ctx, cudaMallocAsync(&poses, n * sizeof(PoseRows), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&leader_pose, n * sizeof(PoseRows), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&votes, n * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&assign_sorted, n * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&match, BATCH * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&cl_votes, n * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&cl_size, n * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&small, 8 * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMallocAsync(&d_out, 3 * 16 * sizeof(float), st));
-    PPF_CUDA(ctx, cudaMemsetAsync(cl_votes, 0, n * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMemsetAsync(cl_size, 0, n * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMemsetAsync(small, 0, 8 * sizeof(uint32_t), st));
-    PPF_CUDA(ctx, cudaMemsetAsync(d_out, 0, 3 * 16 * sizeof(float), st));
+    const uint32_t n_cells = hp.mask + 1u;
+    const uint32_t n_scan_blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+
+    // one pooled allocation for all scratch
+    uint32_t *keys[2], *order[2], *ckeys[2], *crank[2];
+    uint32_t *votes, *state, *leader_id, *assign_sorted, *cl_votes, *cl_size, *cell_start, *block_sums, *small;
+    PoseRows *poses;
+    float *d_out;
+    size_t words = 0;
+    auto take = [&](size_t w) { size_t o = words; words += (w + 3) & ~size_t(3); return o; };
+    const size_t o_keys0 = take(n), o_keys1 = take(n), o_ord0 = take(n), o_ord1 = take(n), o_ck0 = take(n),
+                 o_ck1 = take(n), o_cr0 = take(n), o_cr1 = take(n), o_votes = take(n), o_state = take(n),
+                 o_lid = take(n), o_as = take(n), o_cv = take(n), o_cs = take(n), o_cell = take((size_t)n_cells + 1),
+                 o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12);
+    uint32_t *pool = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&pool, words * sizeof(uint32_t), st));
+    keys[0] = pool + o_keys0; keys[1] = pool + o_keys1; order[0] = pool + o_ord0; order[1] = pool + o_ord1;
+    ckeys[0] = pool + o_ck0; ckeys[1] = pool + o_ck1; crank[0] = pool + o_cr0; crank[1] = pool + o_cr1;
+    votes = pool + o_votes; state = pool + o_state; leader_id = pool + o_lid; assign_sorted = pool + o_as;
+    cl_votes = pool + o_cv; cl_size = pool + o_cs; cell_start = pool + o_cell; block_sums = pool + o_bs;
+    small = pool + o_small; d_out = reinterpret_cast<float *>(pool + o_out);
+    poses = reinterpret_cast<PoseRows *>(pool + o_poses);
+    // state .. cl_size are contiguous: one memset clears state (UNDECIDED), leader ids, assignments, cluster sums
+    PPF_CUDA(ctx, cudaMemsetAsync(state, 0, (o_cell - o_state) * sizeof(uint32_t), st));
+    PPF_CUDA(ctx, cudaMemsetAsync(small, 0, (16 + 48) * sizeof(uint32_t), st));
     if (ctx->assign_n < n) {
         if (ctx->d_assign) cudaFree(ctx->d_assign);
         ctx->d_assign = nullptr;
@@ -275,58 +378,69 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     }
     ctx->assign_n = n;
 
+    // small[0] = max votes, small[1] = undecided counter, small[2] = n_clusters, small[3..5] = top, small[6..8] = votes
     const unsigned g = (n + 255) / 256;
-    PPF_LAUNCH(ctx, cluster_keys_kernel, g, 256, 0, hyps, n, keys[0]);
+    uint32_t h_small[16];
+    PPF_LAUNCH(ctx, cluster_max_votes_kernel, g, 256, 0, hyps, n, small);
+    PPF_CUDA(ctx, cudaMemcpyAsync(h_small, small, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PPF_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t max_votes = h_small[0];
+    int vote_bits = 1;
+    while (vote_bits < 32 && (max_votes >> vote_bits)) ++vote_bits;
+    PPF_LAUNCH(ctx, cluster_keys_kernel, g, 256, 0, hyps, n, max_votes, keys[0]);
     bool in_alt = false;
-    int rc = radix_sort_u32(ctx, keys[0], keys[1], order[0], order[1], nullptr, nullptr, n, 32, /*v0_iota=*/true, &in_alt);
+    int rc = radix_sort_u32(ctx, keys[0], keys[1], order[0], order[1], nullptr, nullptr, n, vote_bits, /*v0_iota=*/true,
+                            &in_alt);
     if (rc) return rc;
     const uint32_t *ord = order[in_alt ? 1 : 0];
-    PPF_LAUNCH(ctx, cluster_gather_kernel, g, 256, 0, hyps, ord, n, poses, votes);
-    PPF_LAUNCH(ctx, fill_u32_kernel, (BATCH + 255) / 256, 256, 0, match, (uint32_t)BATCH, NONE);
-    uint32_t *n_leaders = small;
-    for (uint32_t b0 = 0; b0 < n; b0 += BATCH) {
-        const uint32_t b1 = std::min(n, b0 + BATCH);
-        if (b0 > 0) {
-            const unsigned tiles = (b0 + LEADER_TILE - 1) / LEADER_TILE;  // upper bound on existing leaders
-            PPF_LAUNCH(ctx, cluster_match_kernel, tiles, 256, 0, poses, b0, b1, leader_pose, n_leaders, pos_thr, rot_thr,
-                       match);
+    PPF_LAUNCH(ctx, cluster_gather_kernel, g, 256, 0, hyps, ord, n, hp, poses, votes, ckeys[0]);
+    int cell_bits = 0;
+    while ((1u << cell_bits) < n_cells) ++cell_bits;
+    rc = radix_sort_u32(ctx, ckeys[0], ckeys[1], crank[0], crank[1], nullptr, nullptr, n, cell_bits, /*v0_iota=*/true,
+                        &in_alt);
+    if (rc) return rc;
+    const uint32_t *cell_keys_sorted = ckeys[in_alt ? 1 : 0], *cell_rank = crank[in_alt ? 1 : 0];
+    PPF_LAUNCH(ctx, cluster_cell_offsets_kernel, (n_cells + 1 + 255) / 256, 256, 0, cell_keys_sorted, n, n_cells,
+               cell_start);
+
+    // ordered independent-set rounds until nothing is undecided
+    const unsigned gr = (n + 127) / 128;
+    for (int iter = 0;; ++iter) {
+        const int rounds = iter == 0 ? 3 : 4;
+        for (int r = 0; r < rounds; ++r) {
+            PPF_CUDA(ctx, cudaMemsetAsync(small + 1, 0, sizeof(uint32_t), st));
+            PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, cell_rank, hp, n, pos_thr, rot_thr,
+                       state, small + 1);
         }
-        PPF_LAUNCH(ctx, cluster_resolve_kernel, 1, BATCH, 0, poses, b0, b1, leader_pose, n_leaders, pos_thr, rot_thr,
-                   match, assign_sorted);
+        PPF_CUDA(ctx, cudaMemcpyAsync(h_small + 1, small + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PPF_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_small[1] == 0) break;
+        if (iter > (int)n) return fail_msg(ctx, B200PPF_ERR_CUDA, "cluster: leader resolution did not converge");
     }
-    PPF_LAUNCH(ctx, cluster_votes_kernel, g, 256, 0, assign_sorted, votes, ord, n, cl_votes, cl_size, ctx->d_assign);
-    PPF_LAUNCH(ctx, cluster_top3_kernel, 1, 1024, 0, cl_votes, n_leaders, small + 1);
-    PPF_LAUNCH(ctx, cluster_average_kernel, 3, 256, 0, poses, assign_sorted, n, small + 1, cl_votes, cl_size, d_out,
-               small + 4);
-    uint32_t h_small[8];
+    PPF_LAUNCH(ctx, leader_count_kernel, n_scan_blocks, SCAN_BLOCK, 0, state, n, block_sums);
+    PPF_LAUNCH(ctx, leader_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, n_scan_blocks, small + 2);
+    PPF_LAUNCH(ctx, leader_index_kernel, n_scan_blocks, SCAN_BLOCK, 0, state, n, block_sums, leader_id);
+    PPF_LAUNCH(ctx, cluster_assign_kernel, gr, 128, 0, poses, cell_start, cell_rank, hp, n, pos_thr, rot_thr, state,
+               leader_id, votes, ord, assign_sorted, ctx->d_assign, cl_votes, cl_size);
+    PPF_LAUNCH(ctx, cluster_top3_kernel, 1, 1024, 0, cl_votes, small + 2, small + 3);
+    PPF_LAUNCH(ctx, cluster_average_kernel, 3, 256, 0, poses, assign_sorted, n, small + 3, cl_votes, cl_size, d_out,
+               small + 6);
     float h_out[48];
     PPF_CUDA(ctx, cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
     PPF_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, st));
     cudaEventRecord(ctx->ev[1], st);
     PPF_CUDA(ctx, cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ctx->timings.cluster_ms, ctx->ev[0], ctx->ev[1]);
-    ctx->n_clusters = h_small[0];
+    ctx->n_clusters = h_small[2];
     size_t k = 0;
     for (int r = 0; r < 3; ++r) {
-        if (h_small[1 + r] == NONE) break;
+        if (h_small[3 + r] == NONE) break;
         memcpy(poses16 + 16 * k, h_out + 16 * r, 16 * sizeof(float));
-        votes_out[k] = h_small[4 + r];
+        votes_out[k] = h_small[6 + r];
         ++k;
     }
     *n_out = k;
-    for (int b = 0; b < 2; ++b) {
-        cudaFreeAsync(keys[b], st);
-        cudaFreeAsync(order[b], st);
-    }
-    cudaFreeAsync(poses, st);
-    cudaFreeAsync(leader_pose, st);
-    cudaFreeAsync(votes, st);
-    cudaFreeAsync(assign_sorted, st);
-    cudaFreeAsync(match, st);
-    cudaFreeAsync(cl_votes, st);
-    cudaFreeAsync(cl_size, st);
-    cudaFreeAsync(small, st);
-    cudaFreeAsync(d_out, st);
+    cudaFreeAsync(pool, st);
     return B200PPF_OK;
 }
 

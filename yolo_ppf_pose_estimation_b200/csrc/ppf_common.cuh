@@ -32,6 +32,8 @@ struct b200ppf_ctx {
     b200ppf_timings timings{};
     uint64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_vote[4] = {nullptr, nullptr, nullptr, nullptr};  // last vote: start / grid built / voted / poses done
+    bool vote_timed = false;
     // vote scratch (grown on demand, kept across calls)
     unsigned long long *d_stats = nullptr;  // [4]
     unsigned long long *d_peaks = nullptr;  // packed (votes<<32 | ~flat) per reference
@@ -114,6 +116,33 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n
                float *poses16, uint32_t *votes, size_t *n_out);
 int k5_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose16, float *out_host,
                  size_t out_stride_floats);
+
+// uniform grid over the scene (scene_grid.cu): cells of edge >= search radius, x fastest
+struct GridParams {
+    float origin[3];
+    float inv_cell;
+    int dims[3];
+};
+
+__host__ __device__ __forceinline__ int grid_cell_coord(const GridParams &g, float v, int axis) {
+    int c = (int)floorf((v - g.origin[axis]) * g.inv_cell);
+    return c < 0 ? 0 : (c >= g.dims[axis] ? g.dims[axis] - 1 : c);
+}
+
+__host__ __device__ __forceinline__ uint32_t grid_cell_linear(const GridParams &g, int x, int y, int z) {
+    return ((uint32_t)z * (uint32_t)g.dims[1] + (uint32_t)y) * (uint32_t)g.dims[0] + (uint32_t)x;
+}
+
+struct SceneGrid {
+    GridParams gp{};
+    uint32_t n_cells = 0;
+    uint32_t *cell_start = nullptr;  // [n_cells + 1] into the cell-sorted arrays
+    float4 *pos = nullptr, *nrm = nullptr;  // cell-sorted copies of the scene
+    uint32_t *orig = nullptr;        // cell-sorted position -> original scene index
+};
+
+int scene_grid_build(b200ppf_ctx *ctx, const b200ppf_cloud *scene, float radius, SceneGrid *out);
+void scene_grid_free(b200ppf_ctx *ctx, SceneGrid *g);
 
 // hand-written LSD radix sort (radix_sort.cu): keys ascending, stable, two 32-bit payload streams.
 // All buffers are device pointers of n elements; *_alt are the ping-pong partners.  On return
