@@ -47,29 +47,81 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    NVML is polled from a thread every 50 ms (a polling `nvidia-smi -lms` process was measured to
+    slow this launch-heavy step by ~20 %: its queries contend with kernel launches for driver locks);
+    nvidia-smi is only the fallback when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.proc, self.path = device, None, None
+        self.thread, self.stop_flag, self.samples = None, False, []
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.device
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.device])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.handle = nv, h
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            if self.samples:
+                seen = set()
+                for _, r in self.samples:
+                    for n, bit in names.items():
+                        if r & bit:
+                            seen.add(n)
+                out.update(sm_mhz=float(np.median([s for s, _ in self.samples])), sm_max_mhz=float(self.max_mhz),
+                           reasons=sorted(seen), samples=len(self.samples), source="nvml thread, 50 ms")
+            return out
         if not self.proc:
             return out
-        time.sleep(0.15)
+        time.sleep(0.6)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -93,7 +145,8 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi -lms 500")
         return out
 
 
@@ -146,7 +199,7 @@ def run_reference(args, wl):
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
-    from yolo_ppf_pose_estimation_b200 import capi, workloads
+    from yolo_ppf_pose_estimation_b200 import capi, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,11 +215,10 @@ def run_b200(args, wl):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     n_ref = wl.n_ref
-    first, step, count = workloads.shard(n_ref, rank, world)
-    chunk = (n_ref + world - 1) // world
+    first, step, count = sharding.shard(n_ref, rank, world)
+    chunk = sharding.chunk_size(n_ref, world)
     with torch.cuda.stream(stream):
         local_buf = torch.zeros((chunk, 16), dtype=torch.float32, device=dev)
-        gathered = torch.zeros((world * chunk, 16), dtype=torch.float32, device=dev) if world > 1 else local_buf
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # ---- offline stage: model upload + table build (reported, not part of the step) ---------------
@@ -185,11 +237,8 @@ def run_b200(args, wl):
         ctx.vote_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, local_buf.data_ptr())
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, local_buf)
-                # rank-major [world][chunk] -> reference order k = c*world + g
-                ordered = gathered.view(world, chunk, 16).transpose(0, 1).contiguous()
-            ptr = ordered.data_ptr()
-            res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=ptr, n=n_ref)
+                ordered = sharding.all_gather_hypotheses(local_buf, n_ref, world, dist)
+            res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=ordered.data_ptr(), n=n_ref)
             del ordered
             return res
         return ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=local_buf.data_ptr(), n=n_ref)

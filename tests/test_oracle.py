@@ -1,0 +1,277 @@
+"""CPU tests of the oracle (oracle/ppf_oracle.cpp): hand-computed known answers, an independent
+float64 restatement of the feature arithmetic, the key statistics SURVEY.md Appendix C measured
+with its own numpy restatement, the frozen golden vectors, and the structural rules (tie-breaks,
+clustering, thread/grid invariance).  PARITY UNPINNED: none of this is PCL output.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ANGLE_STEP, DIST_STEP, GOLDEN
+import parity
+
+
+# ---- hand-computed known answers ---------------------------------------------------------------------
+
+def test_pair_feature_known_answers(oracle):
+    z = (0, 0, 1)
+    ok, f = oracle.pair_feature((0, 0, 0), z, (1, 0, 0), z)
+    assert ok and np.allclose(f, [0, 0, 0, 1], atol=1e-7)
+    # n2 parallel to d: the swap makes u = n2 parallel to d -> |d x u| = 0 -> failure, all zero
+    ok, f = oracle.pair_feature((0, 0, 0), z, (1, 0, 0), (1, 0, 0))
+    assert not ok and np.all(f == 0)
+    # coincident points fail
+    ok, f = oracle.pair_feature((1, 2, 3), z, (1, 2, 3), z)
+    assert not ok
+    # tilted target normal: d = 2x, n1 = z, n2 = (sin t, 0, cos t): a1 = 0, a2 = sin t -> swap
+    t = 0.3
+    ok, f = oracle.pair_feature((0, 0, 0), z, (2, 0, 0), (np.sin(t), 0, np.cos(t)))
+    assert ok and np.isclose(f[3], 2.0) and np.isclose(f[2], -np.sin(t), atol=1e-7)
+    # after the swap u = n2, d = -2x: v = d x u / |.| = (0, cos t, 0)/cos t = +y ; f2 = v . n1 = 0
+    assert abs(f[1]) < 1e-7
+    # w = u x v = (-cos t, 0, sin t); f1 = atan2(w . n1, u . n1) = atan2(sin t, cos t) = t
+    assert np.isclose(f[0], t, atol=1e-6)
+
+
+def test_drost_features(oracle):
+    ok, f = oracle.pair_feature((0, 0, 0), (0, 0, 1), (0, 3, 4), (0, 1, 0), mode=oracle.FEATURE_DROST_COS)
+    assert ok and np.allclose(f, [0.8, 0.6, 0.0, 5.0], atol=1e-7)
+    ok, f = oracle.pair_feature((0, 0, 0), (0, 0, 1), (0, 3, 4), (0, 1, 0), mode=oracle.FEATURE_DROST_ANGLE)
+    assert ok and np.allclose(f, [np.arccos(0.8), np.arccos(0.6), np.pi / 2, 5.0], atol=1e-6)
+
+
+def test_alpha_known_answers(oracle):
+    x = (1, 0, 0)  # normal already on +x: rotation angle 0, axis = y, frame = identity
+    assert oracle.alpha((0, 0, 0), x, (0, 1, 0)) == 0.0
+    assert np.isclose(oracle.alpha((0, 0, 0), x, (0, 0, 1)), -np.pi / 2, atol=1e-7)
+    assert np.isclose(oracle.alpha((0, 0, 0), x, (5, 1, 1)), -np.pi / 4, atol=1e-7)
+    # translation of the reference point is removed first
+    assert np.isclose(oracle.alpha((1, 2, 3), x, (1, 2, 4)), -np.pi / 2, atol=1e-7)
+    R, t = oracle.ref_frame((0, 0, 0), (0, 0, 1))  # z -> x: rotation by 90 degrees about +y... (n x x̂ = +y)
+    assert np.allclose(R @ np.array([0, 0, 1.0]), [1, 0, 0], atol=1e-6)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6)
+
+
+def _features64(p1, n1, p2, n2):
+    """independent float64 restatement of computePairFeatures"""
+    d = p2 - p1
+    f4 = np.linalg.norm(d)
+    a1, a2 = n1 @ d / f4, n2 @ d / f4
+    if np.arccos(abs(a1)) > np.arccos(abs(a2)):
+        u, nt, d, f3 = n2, n1, -d, -a2
+    else:
+        u, nt, f3 = n1, n2, a1
+    v = np.cross(d, u)
+    v /= np.linalg.norm(v)
+    w = np.cross(u, v)
+    return np.array([np.arctan2(w @ nt, u @ nt), v @ nt, f3, f4])
+
+
+def _alpha64(pr, nr, p):
+    ang = np.arccos(nr[0])
+    axis = np.cross(nr, [1.0, 0, 0])
+    axis /= np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    m = R @ (p - pr)
+    return np.arctan2(-m[2], m[1])  # net effect of PCL's sign dance, negated twice (A.2)
+
+
+def test_features_against_float64_restatement(oracle, bottle):
+    rng = np.random.default_rng(11)
+    c = bottle.astype(np.float64)
+    checked = 0
+    for _ in range(400):
+        i, j = rng.choice(len(c), 2, replace=False)
+        if parity.swap_margin(bottle, np.array([i]), np.array([j]))[0] < 1e-4:
+            continue
+        ok, f = oracle.pair_feature(bottle[i, :3], bottle[i, 3:], bottle[j, :3], bottle[j, 3:])
+        assert ok
+        ref = _features64(c[i, :3], c[i, 3:], c[j, :3], c[j, 3:])
+        assert parity.circ_diff(np.float32(f[0]), np.float32(ref[0])) < 2e-5
+        assert np.abs(f[1:] - ref[1:]).max() < 2e-5
+        a = oracle.alpha(bottle[i, :3], bottle[i, 3:], bottle[j, :3])
+        tol = parity.alpha_tolerance(bottle, np.array([i]), np.array([j]))[0] * 4
+        assert parity.circ_diff(np.float32(-a), np.float32(-(-_alpha64(c[i, :3], c[i, 3:], c[j, :3])))) < tol \
+            or parity.circ_diff(np.float32(a), np.float32(-_alpha64(c[i, :3], c[i, 3:], c[j, :3]))) < tol
+        checked += 1
+    assert checked > 300
+
+
+# ---- table ----------------------------------------------------------------------------------------
+
+def test_key_statistics_match_survey(oracle_bottle):
+    """SURVEY.md Appendix C (independent numpy restatement): 543-pt bottle, 12 deg, 0.01 m."""
+    feats, hm = oracle_bottle
+    assert feats.shape == (543 * 543, 5)
+    assert int(np.isnan(feats[:, 0]).sum()) == 543          # only the diagonal is invalid
+    assert hm.num_entries == 294306 and hm.num_keys == 10448
+    keys, lengths = hm.dump_keys()
+    assert lengths.sum() == 294306 and lengths.max() == 1686 and abs(lengths.mean() - 28.2) < 0.05
+    assert keys.min(axis=0).tolist() == [-15, -5, -5, 0] and keys.max(axis=0).tolist() == [14, 4, 4, 18]
+    assert abs(hm.model_diameter - 0.1838) < 1e-3
+    assert np.float32(hm.model_diameter) == np.nanmax(feats[:, 3])
+
+
+def test_hashmap_query_and_quantisation(oracle_bottle):
+    feats, hm = oracle_bottle
+    n = 543
+    p = 17 * n + 301
+    f = feats[p]
+    d = hm.quantise(f[:4])
+    assert d.tolist() == parity.quantise(f[:4], ANGLE_STEP, DIST_STEP).tolist()
+    bucket = hm.query(*[float(x) for x in f[:4]])
+    assert [17, 301] in bucket.tolist()
+    assert (np.diff(bucket[:, 0].astype(np.int64) * n + bucket[:, 1].astype(np.int64)) > 0).all()  # canonical order
+    same = parity.quantise(feats[~np.isnan(feats[:, 0]), :4], ANGLE_STEP, DIST_STEP)
+    assert len(bucket) == int((same == d).all(axis=1).sum())
+    assert len(hm.query(0.0, 0.0, 0.0, 99.0)) == 0
+
+
+def test_num_alpha_bins_and_binning(oracle):
+    assert oracle.num_alpha_bins(ANGLE_STEP) == 29          # float(12 deg) > 2*pi/30: floor gives 29
+    assert oracle.num_alpha_bins(np.float32(0.25)) == 25
+    rng = np.random.default_rng(2)
+    for _ in range(2000):
+        am, as_ = rng.uniform(-np.pi, np.pi, 2).astype(np.float32)
+        b = oracle.alpha_bin(am, as_, ANGLE_STEP)
+        a = float(np.float32(am - as_))
+        if a < -np.pi:
+            a = float(np.float32(a + 2 * np.pi))
+        elif a > np.pi:
+            a = float(np.float32(a - 2 * np.pi))
+        assert b == min(int(np.floor((a + np.pi) / float(ANGLE_STEP))), 28)
+        bb = oracle.alpha_bin(am, as_, ANGLE_STEP, mode=oracle.ALPHA_MODE_B)
+        assert bb == int(np.floor(np.float32(am - as_)) + np.floor(np.pi / float(ANGLE_STEP)))
+    assert oracle.alpha_bin(np.float32("nan"), 0.0, ANGLE_STEP) == 0xFFFFFFFF
+
+
+# ---- voting ---------------------------------------------------------------------------------------
+
+def test_golden_vectors(oracle, oracle_bottle, bottle, scene_crop):
+    g = np.load(os.path.join(GOLDEN, "oracle_golden.npz"))
+    feats, hm = oracle_bottle
+    assert np.allclose(feats[g["pair_index"]], g["pair_features"], atol=1e-6, equal_nan=True)
+    keys, lengths = hm.dump_keys()
+    order = np.lexsort(keys.T[::-1])
+    assert np.array_equal(keys[order], g["keys"]) and np.array_equal(lengths[order], g["key_lengths"])
+    hyps, stats = hm.vote(bottle, scene_crop, 0, 5, n_threads=1)
+    assert np.array_equal(hyps["votes"], g["hyp_votes"])
+    assert np.array_equal(hyps["model_index"], g["hyp_model_index"])
+    assert np.array_equal(hyps["alpha_bin"], g["hyp_alpha_bin"])
+    assert np.allclose(hyps["pose"], g["hyp_pose"], atol=1e-6)
+    assert [stats[k] for k in ("pairs_examined", "pairs_in_radius", "nonempty_lookups", "votes")] == g["vote_stats"].tolist()
+    poses, votes, assign, ncl = oracle.cluster(hyps)
+    assert ncl == int(g["n_clusters"]) and np.array_equal(votes, g["cluster_votes"])
+    assert np.array_equal(assign, g["cluster_assign"]) and np.allclose(poses, g["cluster_poses"], atol=1e-6)
+    acc, _ = hm.vote_accumulate(543, scene_crop, 250)
+    flat = acc.reshape(-1)
+    assert np.array_equal(np.flatnonzero(flat), g["acc250_nonzero_index"])
+    assert np.array_equal(flat[flat > 0], g["acc250_nonzero_value"])
+
+
+def test_peak_is_first_maximum_and_pose(oracle, oracle_bottle, bottle, scene_crop):
+    _, hm = oracle_bottle
+    hyps, _ = hm.vote(bottle, scene_crop, 0, 40, n_threads=oracle.max_threads())
+    for h in hyps:
+        acc, votes = hm.vote_accumulate(543, scene_crop, int(h["scene_index"]))
+        flat = int(np.argmax(acc))  # first occurrence of the maximum in (i, bin) order
+        assert h["votes"] == acc.reshape(-1)[flat]
+        assert (int(h["model_index"]), int(h["alpha_bin"])) == divmod(flat, acc.shape[1])
+        P = oracle.peak_pose(bottle, int(h["model_index"]), int(h["alpha_bin"]), scene_crop, int(h["scene_index"]), ANGLE_STEP)
+        assert np.array_equal(P.reshape(-1), h["pose"])
+        R = P[:, :3].astype(np.float64)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-5)
+    # the split "pairs -> accumulate" equals the fused accumulate
+    inr, d, a = hm.scene_pairs(scene_crop, 250)
+    acc2, v2 = hm.vote_accumulate_from_pairs(543, d[inr > 0], a[inr > 0])
+    acc1, v1 = hm.vote_accumulate(543, scene_crop, 250)
+    assert v1 == v2 and np.array_equal(acc1, acc2)
+
+
+def test_threads_and_grid_do_not_change_results(oracle, oracle_bottle, bottle, scene_full):
+    _, hm = oracle_bottle
+    sub = scene_full[:6000]  # > 2048 points: the oracle switches to its uniform grid
+    a, sa = hm.vote(bottle, sub, 0, 300, n_threads=1)
+    b, sb = hm.vote(bottle, sub, 0, 300, n_threads=4)
+    assert a.tobytes() == b.tobytes()
+    assert sa == sb
+    for h in a[::5]:
+        acc, votes = hm.vote_accumulate(543, sub, int(h["scene_index"]))  # brute force over all points
+        assert h["votes"] == acc.max()
+
+
+def test_self_match_recovers_pose(oracle, oracle_bottle, bottle):
+    from scipy.spatial.transform import Rotation as Rot
+    _, hm = oracle_bottle
+    R = Rot.from_rotvec([0.3, -0.5, 0.8]).as_matrix()
+    t = np.array([0.1, -0.05, 0.3])
+    s = bottle.astype(np.float64).copy()
+    s[:, :3] = s[:, :3] @ R.T + t
+    s[:, 3:] = s[:, 3:] @ R.T
+    final, poses, votes, _ = hm.register(bottle, s.astype(np.float32), ref_rate=10, n_threads=oracle.max_threads())
+    G = np.eye(4)
+    G[:3, :3], G[:3, 3] = R, t
+    dt, dr = parity.pose_error(final, G)
+    assert dt < 3e-3 and dr < 1.0
+    assert np.array_equal(oracle.transform(bottle, final), (bottle[:, :3] @ final[:3, :3].T + final[:3, 3]).astype(np.float32)) \
+        or np.abs(oracle.transform(bottle, final) - (bottle[:, :3].astype(np.float64) @ final[:3, :3].T + final[:3, 3])).max() < 1e-6
+
+
+# ---- clustering --------------------------------------------------------------------------------------
+
+def _hyp(oracle, poses, votes):
+    h = np.zeros(len(poses), oracle.HYP_DTYPE)
+    for k, (P, v) in enumerate(zip(poses, votes)):
+        h["pose"][k] = np.asarray(P, np.float32)[:3].reshape(-1)
+        h["votes"][k] = v
+        h["scene_index"][k] = k
+    return h
+
+
+def _pose(rotvec, t):
+    from scipy.spatial.transform import Rotation as Rot
+    M = np.eye(4)
+    M[:3, :3] = Rot.from_rotvec(rotvec).as_matrix()
+    M[:3, 3] = t
+    return M
+
+
+def test_cluster_rules(oracle):
+    A = _pose([0, 0, 0.1], [0, 0, 0])
+    A2 = _pose([0, 0, 0.15], [0.004, 0, 0])       # within 1 cm / 20 deg of A
+    B = _pose([0, 0, 0.1], [0.05, 0, 0])          # too far from A
+    C = _pose([0, 0, 0.1 + 0.5], [0.001, 0, 0])   # rotation beyond 20 deg of A
+    h = _hyp(oracle, [B, A2, A, C], [5, 7, 9, 1])
+    poses, votes, assign, ncl = oracle.cluster(h)
+    # sorted by votes: A(9) leads cluster 0, A2(7) joins it, B(5) founds 1, C(1) founds 2
+    assert ncl == 3 and assign.tolist() == [1, 0, 0, 2]
+    assert votes.tolist() == [16, 5, 1]
+    assert np.allclose(poses[0][:3, 3], [0.002, 0, 0], atol=1e-7)
+    # the averaged rotation sits between the two members
+    assert parity.pose_error(poses[0], _pose([0, 0, 0.125], [0.002, 0, 0]))[1] < 0.05
+    # ties in votes keep the input order (A.8 rule 1): the earlier hypothesis becomes the leader
+    h = _hyp(oracle, [A, B, A2], [4, 4, 4])
+    _, votes, assign, ncl = oracle.cluster(h)
+    assert assign.tolist() == [0, 1, 0] and votes.tolist() == [8, 4]
+    # ties in cluster votes keep creation order (A.8 rule 2); only three results are returned
+    D = _pose([0, 0, 0], [1, 1, 1])
+    E = _pose([0, 0, 0], [2, 2, 2])
+    h = _hyp(oracle, [A, B, D, E], [3, 3, 3, 3])
+    poses, votes, assign, ncl = oracle.cluster(h)
+    assert ncl == 4 and len(poses) == 3 and assign.tolist() == [0, 1, 2, 3]
+    assert np.allclose(poses[2][:3, 3], [1, 1, 1])
+    # a pose compares against the cluster LEADER only: A-A2-A3 chain, A3 within A2 but not within A
+    A3 = _pose([0, 0, 0.15], [0.012, 0, 0])
+    h = _hyp(oracle, [A, A2, A3], [9, 8, 7])
+    _, _, assign, ncl = oracle.cluster(h)
+    assert assign.tolist() == [0, 0, 1]
+
+
+def test_poses_within_thresholds(oracle):
+    A = _pose([0, 0, 0], [0, 0, 0])
+    assert oracle.poses_within(A, _pose([0, 0, 0.3], [0.009, 0, 0]), 0.01, 0.35)
+    assert not oracle.poses_within(A, _pose([0, 0, 0.3], [0.011, 0, 0]), 0.01, 0.35)
+    assert not oracle.poses_within(A, _pose([0, 0, 0.36], [0, 0, 0]), 0.01, 0.35)
+    assert oracle.poses_within(A, _pose([0, 3.0, 0], [0, 0, 0]), 0.01, 3.1)   # angle is in [0, pi]

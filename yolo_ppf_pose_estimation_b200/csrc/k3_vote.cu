@@ -68,36 +68,40 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return __shfl_xor_sync(0xFFFFFFFFu, v, o);
 }
 
-__device__ __forceinline__ void red_shared_inc(uint32_t shared_addr) {
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(shared_addr) : "memory");
+// shared-memory increment without a return value (ATOMS.POPC.INC on the CTA's shared window)
+__device__ __forceinline__ void red_shared_inc(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
-// one vote: bin of (alpha_m - alpha_s) and a shared-memory increment.  Mode A's hot form is
-// branch-free; the literal double-precision form decides only inside the guard band
-// (ppf_math.cuh, alpha_bin_fast — same arithmetic, laid out for the loop).
+// One vote of the hot loop (alpha mode A): fp32 estimate of the bin and an unconditional increment.
+// When the estimate lies inside the guard band (or is NaN) the increment is steered to a scratch
+// word instead of the accumulator — ATOMS cannot be predicated, and a select is cheaper than a
+// divergent branch — and true is returned: the caller then settles the entry with the literal
+// double-precision form (alpha_bin_exact).  Same arithmetic as alpha_bin_fast in ppf_math.cuh.
+__device__ __forceinline__ bool vote_fast_a(const BinParams &bp, uint32_t acc_addr, uint32_t scratch_addr, uint2 en,
+                                            float alpha_s) {
+    const float d = __uint_as_float(en.y) - alpha_s;
+    float w = d;
+    if (d <= -3.14159274f) w = d + 6.28318548f;
+    else if (d >= 3.14159274f) w = d - 6.28318548f;
+    const float q = (w + 3.14159274f) * bp.inv_step;
+    const float fl = floorf(q);
+    const float fr = q - fl;
+    const bool ok = (fr > bp.guard) && (fr < 1.0f - bp.guard);
+    const uint32_t bin = min((uint32_t)max((int)fl, 0), bp.n_alpha - 1u);
+    red_shared_inc(ok ? acc_addr + ((en.x + bin) << 2) : scratch_addr);
+    return !ok;
+}
+
+// the rare path, and every vote of alpha mode B: literal form
 template <int MODE>
-__device__ __forceinline__ uint32_t vote_one(const BinParams &bp, uint32_t acc_addr, uint2 en, float alpha_s) {
-    const float alpha_m = __uint_as_float(en.y);
-    uint32_t bin;
-    if (MODE == ALPHA_MODE_B) {
-        bin = alpha_bin_fast(bp, alpha_m, alpha_s);
-    } else {
-        const float d = alpha_m - alpha_s;
-        float w = d;
-        if (d <= -3.14159274f) w = d + 6.28318548f;
-        else if (d >= 3.14159274f) w = d - 6.28318548f;
-        const float q = (w + 3.14159274f) * bp.inv_step;
-        const float fl = floorf(q);
-        const float fr = q - fl;
-        int b = (int)fl;
-        b = max(b, 0);
-        bin = min((uint32_t)b, bp.n_alpha - 1u);
-        if (!(fr > bp.guard && fr < 1.0f - bp.guard))  // rare; also catches NaN
-            bin = alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
-    }
-    if (bin == 0xFFFFFFFFu) return 0u;
-    red_shared_inc(acc_addr + ((en.x + bin) << 2));
-    return 1u;
+__device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_addr, uint2 en, float alpha_s,
+                                           uint32_t &skipped) {
+    const uint32_t bin = MODE == ALPHA_MODE_B
+                             ? alpha_bin_fast(bp, __uint_as_float(en.y), alpha_s)
+                             : alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, __uint_as_float(en.y), alpha_s);
+    if (bin == 0xFFFFFFFFu) ++skipped;  // NaN alpha: no vote
+    else red_shared_inc(acc_addr + ((en.x + bin) << 2));
 }
 
 template <int MODE>
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(VOTE_THREADS, 2)
 ppf_vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Frame s_sg;
-    __shared__ uint32_t s_ncand, s_nitems, s_next;
+    __shared__ uint32_t s_ncand, s_nitems, s_next, s_scratch;
     __shared__ uint32_t s_run_start[9], s_run_end[9];
     __shared__ unsigned long long s_best[VOTE_WARPS];
     __shared__ unsigned long long s_stat[4];
@@ -119,6 +123,7 @@ ppf_vote_kernel(const VoteArgs a) {
     uint32_t *cand = acc + (size_t)a.kp.slice_rows * a.bp.n_alpha;
     WorkItem *items = reinterpret_cast<WorkItem *>(cand + CAND_CAP);
     const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
+    const uint32_t scratch_addr = (uint32_t)__cvta_generic_to_shared(&s_scratch);
 
     const uint32_t s_r = a.ref_first + blockIdx.x * a.ref_step;
     const float4 pr4 = a.pos[s_r], nr4 = a.nrm[s_r];
@@ -149,7 +154,7 @@ ppf_vote_kernel(const VoteArgs a) {
     __syncthreads();
 
     const uint32_t *slice_offsets = a.offsets + (size_t)slice * a.kp.key_space;
-    uint32_t st_examined = 0, st_in_radius = 0, st_nonempty = 0, st_votes = 0;
+    uint32_t st_examined = 0, st_in_radius = 0, st_nonempty = 0, st_votes = 0, st_skipped = 0;
 
     // phases B + C over the buffered candidates
     auto flush = [&]() {
@@ -198,19 +203,34 @@ ppf_vote_kernel(const VoteArgs a) {
                 w = __shfl_sync(0xFFFFFFFFu, w, 0);
                 if (w >= nitems) break;
                 const WorkItem wi = items[w];
-                const uint2 *e = a.entries + wi.off;
-                for (uint32_t k0 = 0; k0 < wi.len; k0 += 32 * VOTE_UNROLL) {
-                    uint2 en[VOTE_UNROLL];
+                const uint2 *e = a.entries + wi.off + lane;
+                if (lane == 0) st_votes += wi.len;
+                uint32_t k0 = 0;
+                if (MODE == ALPHA_MODE_A) {
+                    // full 4 x 32 chunks: four gathers in flight, four branch-free votes
+                    for (; k0 + 32 * VOTE_UNROLL <= wi.len; k0 += 32 * VOTE_UNROLL) {
+                        uint2 en[VOTE_UNROLL];
 #pragma unroll
-                    for (int u = 0; u < VOTE_UNROLL; ++u) {
-                        const uint32_t k = k0 + u * 32 + lane;
-                        en[u] = k < wi.len ? __ldg(e + k) : make_uint2(0u, 0u);
-                    }
+                        for (int u = 0; u < VOTE_UNROLL; ++u) en[u] = __ldg(e + k0 + u * 32);
+                        bool risky[VOTE_UNROLL];
 #pragma unroll
-                    for (int u = 0; u < VOTE_UNROLL; ++u) {
-                        const uint32_t k = k0 + u * 32 + lane;
-                        if (k < wi.len) st_votes += vote_one<MODE>(a.bp, acc_addr, en[u], wi.alpha_s);
+                        for (int u = 0; u < VOTE_UNROLL; ++u)
+                            risky[u] = vote_fast_a(a.bp, acc_addr, scratch_addr, en[u], wi.alpha_s);
+                        bool any = false;
+#pragma unroll
+                        for (int u = 0; u < VOTE_UNROLL; ++u) any |= risky[u];
+                        if (any) {
+#pragma unroll
+                            for (int u = 0; u < VOTE_UNROLL; ++u)
+                                if (risky[u]) vote_exact<MODE>(a.bp, acc_addr, en[u], wi.alpha_s, st_skipped);
+                        }
                     }
+                }
+                // tail (and alpha mode B)
+                for (uint32_t k = k0 + lane; k < wi.len; k += 32) {
+                    const uint2 en = __ldg(e + (k - lane));
+                    if (MODE == ALPHA_MODE_B || vote_fast_a(a.bp, acc_addr, scratch_addr, en, wi.alpha_s))
+                        vote_exact<MODE>(a.bp, acc_addr, en, wi.alpha_s, st_skipped);
                 }
             }
             __syncthreads();
@@ -273,13 +293,14 @@ ppf_vote_kernel(const VoteArgs a) {
         st_in_radius += __shfl_xor_sync(0xFFFFFFFFu, st_in_radius, o);
         st_nonempty += __shfl_xor_sync(0xFFFFFFFFu, st_nonempty, o);
         st_votes += __shfl_xor_sync(0xFFFFFFFFu, st_votes, o);
+        st_skipped += __shfl_xor_sync(0xFFFFFFFFu, st_skipped, o);
     }
     if (lane == 0) {
         s_best[warp] = best;
         atomicAdd(&s_stat[0], (unsigned long long)st_examined);
         atomicAdd(&s_stat[1], (unsigned long long)st_in_radius);
         atomicAdd(&s_stat[2], (unsigned long long)st_nonempty);
-        atomicAdd(&s_stat[3], (unsigned long long)st_votes);
+        atomicAdd(&s_stat[3], (unsigned long long)(st_votes - st_skipped));
     }
     __syncthreads();
     if (tid == 0) {

@@ -70,10 +70,3 @@ def load(name: str) -> Workload:
         return Workload("c3s", "synthetic 2 500-pt model vs 25 000-pt scene, all reference points",
                         synth.synth_model(2500, 1), synth.synth_scene(25000, 2, model_seed=1), 1, "synthetic")
     raise ValueError(f"unknown workload {name!r}")
-
-
-def shard(n_ref: int, rank: int, world: int):
-    """Interleaved reference-point shard of one rank: (first, step, count) in units of reference
-    slots k (scene index = k * ref_rate).  Interleaving balances scene-density differences."""
-    count = (n_ref - rank + world - 1) // world if rank < n_ref else 0
-    return rank, world, count
