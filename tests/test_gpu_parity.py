@@ -424,3 +424,36 @@ def test_errors_and_edges(ctx, bottle, dev_bottle, dev_crop, table_fused):
     far[:, :3] = far[:, :3] * 100.0
     hy = ctx.vote(dev_bottle, table_fused, ctx.upload_cloud(far), 0, 1)
     assert len(hy) == 30 and (hy["votes"] == 0).all() and (hy["model_index"] == 0).all()
+
+
+# ---- the PCL-shaped C++ surface ------------------------------------------------------------------------
+
+def test_cpp_pcl_shim_end_to_end(tmp_path, ctx, bottle, scene_crop, dev_bottle, dev_crop, oracle_bottle):
+    """tests/cpp/pcl_shim_example.cpp — PPFEstimation::compute -> PPFHashMapSearch::setInputFeatureCloud
+    -> PPFRegistration::align through include/pcl_compat — gives the C-ABI result."""
+    from yolo_ppf_pose_estimation_b200 import build
+    lib = build.build()
+    bottle.astype(np.float32).tofile(tmp_path / "bottle_1cm.f32")
+    scene_crop.astype(np.float32).tofile(tmp_path / "scene_crop_1cm.f32")
+    exe = tmp_path / "pcl_shim_example"
+    cmd = ["/usr/bin/g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include", "pcl_compat"), "-I",
+           os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "pcl_shim_example.cpp"), "-o", str(exe),
+           "-L", os.path.dirname(lib), "-lb200ppf", f"-Wl,-rpath,{os.path.dirname(lib)}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    M = np.array([[float(x) for x in ln.split()] for ln in lines[:4]], np.float32)
+    # the same pipeline through the C ABI: two-step table from the device's own signatures
+    t = ctx.table_build(ctx.features_compute(dev_bottle), ANGLE_STEP, DIST_STEP)
+    final, poses, votes = ctx.register(dev_bottle, t, dev_crop, ref_rate=5)
+    assert np.array_equal(M, final)
+    _, hm = oracle_bottle
+    info = dict(zip(lines[4].split()[::2], lines[4].split()[1::2]))
+    assert np.float32(info["model_diameter"]) == np.float32(hm.model_diameter)
+    assert int(info["features"]) == 543 * 543 and int(info["output"]) == 543 and int(info["candidates"]) == len(poses)
+    out0 = np.array([float(x) for x in lines[6].split()[1:]], np.float32)
+    assert np.array_equal(out0, ctx.transform(dev_bottle, final)[0])
+    bucket = lines[5].split()
+    assert int(bucket[1]) >= 1 and (int(bucket[3]), int(bucket[4])) <= (0, 1)

@@ -75,7 +75,7 @@ def _alpha64(pr, nr, p):
     K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
     R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
     m = R @ (p - pr)
-    return np.arctan2(-m[2], m[1])  # net effect of PCL's sign dance, negated twice (A.2)
+    return np.arctan2(-m[2], m[1])  # net effect of PCL's sign dance
 
 
 def test_features_against_float64_restatement(oracle, bottle):
@@ -93,8 +93,7 @@ def test_features_against_float64_restatement(oracle, bottle):
         assert np.abs(f[1:] - ref[1:]).max() < 2e-5
         a = oracle.alpha(bottle[i, :3], bottle[i, 3:], bottle[j, :3])
         tol = parity.alpha_tolerance(bottle, np.array([i]), np.array([j]))[0] * 4
-        assert parity.circ_diff(np.float32(-a), np.float32(-(-_alpha64(c[i, :3], c[i, 3:], c[j, :3])))) < tol \
-            or parity.circ_diff(np.float32(a), np.float32(-_alpha64(c[i, :3], c[i, 3:], c[j, :3]))) < tol
+        assert parity.circ_diff(np.float32(a), np.float32(_alpha64(c[i, :3], c[i, 3:], c[j, :3]))) < tol
         checked += 1
     assert checked > 300
 

@@ -83,6 +83,7 @@ void b200ppf_destroy(b200ppf_ctx *ctx) {
     if (ctx->d_peaks) cudaFree(ctx->d_peaks);
     if (ctx->d_hyps) cudaFree(ctx->d_hyps);
     if (ctx->d_assign) cudaFree(ctx->d_assign);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_vote)
@@ -147,14 +148,19 @@ int b200ppf_cloud_upload(b200ppf_ctx *ctx, const float *host, size_t n, size_t s
     if (n && !host) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: null host pointer");
     if (stride < 6 || noff < 3 || noff + 3 > stride)
         return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: stride/normal offset do not describe [x y z .. nx ny nz]");
-    // AoS -> float4 SoA staging (pinned), dropping NaN points (SURVEY.md A.8 rule 5)
-    float4 *stage = nullptr;
-    PPF_CUDA(ctx, cudaMallocHost(&stage, std::max<size_t>(1, 2 * n) * sizeof(float4)));
-    b200ppf_cloud *c = new (std::nothrow) b200ppf_cloud();
-    if (!c) {
-        cudaFreeHost(stage);
-        return fail_msg(ctx, B200PPF_ERR_NOMEM, "cloud upload: out of host memory");
+    // AoS -> float4 SoA staging in the context's grow-only pinned buffer, dropping NaN points
+    // (SURVEY.md A.8 rule 5)
+    const size_t need = std::max<size_t>(1, 2 * n) * sizeof(float4);
+    if (ctx->stage_bytes < need) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        PPF_CUDA(ctx, cudaMallocHost(&ctx->stage, need));
+        ctx->stage_bytes = need;
     }
+    float4 *stage = static_cast<float4 *>(ctx->stage);
+    b200ppf_cloud *c = new (std::nothrow) b200ppf_cloud();
+    if (!c) return fail_msg(ctx, B200PPF_ERR_NOMEM, "cloud upload: out of host memory");
     c->ctx = ctx;
     size_t m = 0;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -177,14 +183,14 @@ int b200ppf_cloud_upload(b200ppf_ctx *ctx, const float *host, size_t n, size_t s
         c->bbox_min[k] = m ? lo[k] : 0.0f;
         c->bbox_max[k] = m ? hi[k] : 0.0f;
     }
-    cudaError_t e = cudaMalloc(&c->pos, std::max<size_t>(1, m) * sizeof(float4));
-    if (e == cudaSuccess) e = cudaMalloc(&c->nrm, std::max<size_t>(1, m) * sizeof(float4));
+    // one stream-ordered allocation holds both arrays (pos | nrm)
+    cudaError_t e = cudaMallocAsync(&c->pos, std::max<size_t>(1, 2 * m) * sizeof(float4), ctx->stream);
+    if (e == cudaSuccess) c->nrm = c->pos + m;
     cudaEventRecord(ctx->ev[0], ctx->stream);
     if (e == cudaSuccess && m) e = cudaMemcpyAsync(c->pos, sp, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && m) e = cudaMemcpyAsync(c->nrm, sn, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFreeHost(stage);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the staging buffer is reused by the next upload
     if (e != cudaSuccess) {
         b200ppf_cloud_free(c);
         return fail_msg(ctx, e == cudaErrorMemoryAllocation ? B200PPF_ERR_NOMEM : B200PPF_ERR_CUDA, cudaGetErrorString(e));
@@ -199,8 +205,10 @@ size_t b200ppf_cloud_size(const b200ppf_cloud *cloud) { return cloud ? cloud->n 
 void b200ppf_cloud_free(b200ppf_cloud *c) {
     if (!c) return;
     DeviceGuard guard(c->ctx ? c->ctx->device : 0);
-    if (c->pos) cudaFree(c->pos);
-    if (c->nrm) cudaFree(c->nrm);
+    if (c->pos) {  // pos | nrm share one stream-ordered allocation
+        if (c->ctx) cudaFreeAsync(c->pos, c->ctx->stream);
+        else cudaFree(c->pos);
+    }
     delete c;
 }
 

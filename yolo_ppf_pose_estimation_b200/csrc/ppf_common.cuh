@@ -44,6 +44,9 @@ struct b200ppf_ctx {
     uint32_t *d_assign = nullptr;  // cluster creation index per hypothesis (input order)
     size_t assign_n = 0;
     uint32_t n_clusters = 0;
+    // grow-only pinned staging buffer of cloud uploads
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
 };
 
 struct b200ppf_cloud {

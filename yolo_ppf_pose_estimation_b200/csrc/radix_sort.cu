@@ -4,7 +4,7 @@
 // unordered_multimap of [PCL] registration/src/ppf_registration.cpp) and by K4 (order pose
 // hypotheses by votes, replacing the std::sort of clusterPoses).
 //
-// Layout: the input is cut into warp segments of SEG consecutive elements.  One warp owns one
+// Layout: the input is cut into warp segments of seg_len consecutive elements (128..2048).  One warp owns one
 // segment in both the histogram and the scatter kernel, walking it in rounds of 32 coalesced
 // elements; lanes holding the same digit find each other with match.any, so ranks inside a
 // round are stable by lane order, rounds are sequential, segments are ordered by the column
@@ -18,14 +18,15 @@ namespace b200ppf {
 namespace {
 
 constexpr int RADIX = 256;
-constexpr int SEG = 2048;           // elements per warp segment
+constexpr int SEG_MAX = 2048;       // elements per warp segment (large inputs)
+constexpr int SEG_MIN = 128;        // small inputs get short segments so that every SM has warps to run
 constexpr int WARPS = 8;            // warps (segments) per block
 constexpr int SCAN_CHUNK = 256;     // histogram rows per column-scan chunk
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 __global__ void __launch_bounds__(WARPS * 32)
-radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t nseg, int shift,
+radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t nseg, uint32_t seg_len, int shift,
                   uint32_t *__restrict__ hist) {
     __shared__ uint32_t cnt[WARPS][RADIX];
     const uint32_t w = threadIdx.x >> 5, lane = lane_id();
@@ -33,8 +34,8 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t nseg, 
     for (int d = lane; d < RADIX; d += 32) cnt[w][d] = 0;
     __syncwarp();
     if (seg >= nseg) return;
-    const uint32_t begin = seg * (uint32_t)SEG;
-    const uint32_t end = min(n, begin + (uint32_t)SEG);  // begin < n, no overflow: n < 2^32 - SEG
+    const uint32_t begin = seg * seg_len;
+    const uint32_t end = min(n, begin + seg_len);  // begin < n, no overflow: n < 2^32 - SEG_MAX
     for (uint32_t base = begin; base < end; base += 32) {
         uint32_t idx = base + lane;
         bool valid = idx < end;
@@ -113,7 +114,7 @@ radix_col_apply_kernel(uint32_t *__restrict__ hist, uint32_t nseg, const uint32_
 template <bool IOTA, bool HAS_V0, bool HAS_V1>
 __global__ void __launch_bounds__(WARPS * 32)
 radix_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v0,
-                     const uint32_t *__restrict__ v1, uint32_t n, uint32_t nseg, int shift,
+                     const uint32_t *__restrict__ v1, uint32_t n, uint32_t nseg, uint32_t seg_len, int shift,
                      const uint32_t *__restrict__ hist, uint32_t *__restrict__ keys_out,
                      uint32_t *__restrict__ v0_out, uint32_t *__restrict__ v1_out) {
     __shared__ uint32_t base[WARPS][RADIX];
@@ -123,8 +124,8 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restri
     const uint32_t *row = hist + (size_t)seg * RADIX;
     for (int d = lane; d < RADIX; d += 32) base[w][d] = row[d];
     __syncwarp();
-    const uint32_t begin = seg * (uint32_t)SEG;
-    const uint32_t end = min(n, begin + (uint32_t)SEG);
+    const uint32_t begin = seg * seg_len;
+    const uint32_t end = min(n, begin + seg_len);
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t b = begin; b < end; b += 32) {
         uint32_t idx = b + lane;
@@ -155,8 +156,12 @@ int radix_sort_u32(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_
                    uint32_t *v1, uint32_t *v1_alt, size_t n, int bits, bool v0_iota, bool *result_in_alt) {
     *result_in_alt = false;
     if (n == 0 || bits <= 0) return B200PPF_OK;
-    if (n >= 0xFFFFFFFFull - SEG) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "radix sort: more than 2^32 elements");
-    const uint32_t nseg = (uint32_t)((n + SEG - 1) / SEG);
+    if (n >= 0xFFFFFFFFull - SEG_MAX) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "radix sort: more than 2^32 elements");
+    // segment length: ~16 warps per SM for small inputs, SEG_MAX once there is enough work
+    uint32_t seg_len = (uint32_t)(n / ((size_t)ctx->sm_count * 16));
+    seg_len = (seg_len + 31u) & ~31u;
+    seg_len = seg_len < SEG_MIN ? SEG_MIN : (seg_len > SEG_MAX ? SEG_MAX : seg_len);
+    const uint32_t nseg = (uint32_t)((n + seg_len - 1) / seg_len);
     const uint32_t nblocks = (nseg + WARPS - 1) / WARPS;
     const uint32_t nchunks = (nseg + SCAN_CHUNK - 1) / SCAN_CHUNK;
     uint32_t *hist = nullptr, *chunk_tot = nullptr, *digit_base = nullptr;
@@ -169,13 +174,13 @@ int radix_sort_u32(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_
     uint32_t *ki = keys, *ko = keys_alt, *v0i = v0, *v0o = v0_alt, *v1i = v1, *v1o = v1_alt;
     bool in_alt = false;
     for (int shift = 0; shift < bits; shift += 8) {
-        PPF_LAUNCH(ctx, radix_hist_kernel, nblocks, WARPS * 32, 0, ki, (uint32_t)n, nseg, shift, hist);
+        PPF_LAUNCH(ctx, radix_hist_kernel, nblocks, WARPS * 32, 0, ki, (uint32_t)n, nseg, seg_len, shift, hist);
         PPF_LAUNCH(ctx, radix_col_reduce_kernel, nchunks, RADIX, 0, hist, nseg, chunk_tot);
         PPF_LAUNCH(ctx, radix_col_scan_chunks_kernel, 1, RADIX, 0, chunk_tot, nchunks, digit_base);
         PPF_LAUNCH(ctx, radix_col_apply_kernel, nchunks, RADIX, 0, hist, nseg, chunk_tot, digit_base);
 #define SCATTER(I, A, B)                                                                                      \
     PPF_LAUNCH(ctx, (radix_scatter_kernel<I, A, B>), nblocks, WARPS * 32, 0, ki, v0i, v1i, (uint32_t)n, nseg, \
-               shift, hist, ko, v0o, v1o)
+               seg_len, shift, hist, ko, v0o, v1o)
         if (has_v0 && has_v1) {
             if (iota) SCATTER(true, true, true); else SCATTER(false, true, true);
         } else if (has_v0) {
