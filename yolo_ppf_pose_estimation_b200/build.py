@@ -49,6 +49,7 @@ def _fingerprint() -> str:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("B200PPF_NVCC_EXTRA", "").encode())
     return h.hexdigest()
 
 
@@ -60,11 +61,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == fp:
         return LIB_PATH
     nvcc, cxx = _nvcc(), _host_cxx()
+    extra = os.environ.get("B200PPF_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DB200PPF_VOTE_THREADS=256
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", cxx] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc, "-ccbin", cxx] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -93,7 +93,7 @@ def lib() -> C.CDLL:
     """Load libb200ppf.so from the in-tree build directory (never from site-packages)."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("B200PPF_LIB", _build.LIB_PATH)  # override = tuning variants of the same library
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} is missing: run `python -m yolo_ppf_pose_estimation_b200.build` "

@@ -341,14 +341,14 @@ int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *off
     const size_t total = (size_t)t->info.key_space * t->info.n_slices + 1, ne = t->info.n_entries;
     if (offsets) PPF_CUDA(ctx, cudaMemcpyAsync(offsets, t->offsets, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<uint32_t> idx;
-    std::vector<uint2> ent;
+    std::vector<float> ent;
     if ((entry_i || entry_j) && ne) {
         idx.resize(ne);
         PPF_CUDA(ctx, cudaMemcpyAsync(idx.data(), t->entry_idx, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (entry_alpha_m && ne) {
         ent.resize(ne);
-        PPF_CUDA(ctx, cudaMemcpyAsync(ent.data(), t->entries, ne * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+        PPF_CUDA(ctx, cudaMemcpyAsync(ent.data(), t->entry_alpha, ne * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     }
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const uint32_t n = (uint32_t)t->info.n_model;
@@ -356,7 +356,7 @@ int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *off
         if (entry_i) entry_i[e] = idx[e] / n;
         if (entry_j) entry_j[e] = idx[e] % n;
     }
-    for (size_t e = 0; e < ent.size(); ++e) memcpy(&entry_alpha_m[e], &ent[e].y, sizeof(float));
+    for (size_t e = 0; e < ent.size(); ++e) entry_alpha_m[e] = ent[e];
     return B200PPF_OK;
 }
 
@@ -366,6 +366,7 @@ void b200ppf_table_free(b200ppf_table *t) {
     if (t->offsets) cudaFree(t->offsets);
     if (t->entries) cudaFree(t->entries);
     if (t->entry_idx) cudaFree(t->entry_idx);
+    if (t->entry_alpha) cudaFree(t->entry_alpha);
     delete t;
 }
 

@@ -164,21 +164,28 @@ __global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
 }
 
+// entry = {accumulator word offset of model row i inside its slice, alpha_m in fixed point}; the float
+// alpha_m is kept beside it for the literal form of the guard-band votes and for the API exports.
 __global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const uint32_t *__restrict__ sorted_alpha,
-                               uint32_t n_entries, uint32_t n, uint32_t slice_rows, uint32_t n_alpha,
-                               uint2 *__restrict__ entries) {
+                               uint32_t n_entries, uint32_t n, uint32_t slice_rows, uint32_t row_stride,
+                               uint2 *__restrict__ entries, float *__restrict__ entry_alpha,
+                               int *__restrict__ bad_alpha) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_entries) return;
     uint32_t i = sorted_idx[p] / n;
     uint32_t local = i - (i / slice_rows) * slice_rows;
-    entries[p] = make_uint2(local * n_alpha, sorted_alpha[p]);
+    const float alpha = __uint_as_float(sorted_alpha[p]);
+    // atan2f range; anything else cannot come from PPFEstimation and would not wrap like PCL's floats
+    if (!(alpha >= -3.14159274f && alpha <= 3.14159274f)) *bad_alpha = 1;
+    entries[p] = make_uint2(local * row_stride, alpha_to_fix(alpha));
+    entry_alpha[p] = alpha;
 }
 
-__global__ void alpha_scatter_kernel(const uint32_t *__restrict__ entry_idx, const uint2 *__restrict__ entries,
+__global__ void alpha_scatter_kernel(const uint32_t *__restrict__ entry_idx, const float *__restrict__ entry_alpha,
                                      uint32_t n_entries, float *__restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_entries) return;
-    out[entry_idx[p]] = __uint_as_float(entries[p].y);
+    out[entry_idx[p]] = entry_alpha[p];
 }
 
 __global__ void fill_nan_kernel(float *__restrict__ out, size_t count) {
@@ -229,7 +236,8 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     // accumulator slices: rows per slice bounded by the shared-memory budget of the voting kernel
     {
         size_t budget = k3_accumulator_budget(ctx);
-        size_t rows_max = budget / ((size_t)info.n_alpha * sizeof(uint32_t));
+        // rows are n_alpha + 1 words wide (PCL's out-of-range bin gets its own cell)
+        size_t rows_max = budget / (((size_t)info.n_alpha + 1) * sizeof(uint32_t));
         if (rows_max == 0) {
             delete t;
             return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "table build: angle step too fine for one accumulator row in shared memory");
@@ -249,9 +257,9 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     kp.slice_rows = info.slice_rows;
     kp.n_slices = info.n_slices;
 
-    int *d_range = nullptr;  // lo[4], hi[4], max_f4_bits, out_of_range
-    PPF_CUDA(ctx, cudaMallocAsync(&d_range, 10 * sizeof(int), ctx->stream));
-    int h_range[10] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, INT_MIN, -1, 0};
+    int *d_range = nullptr;  // lo[4], hi[4], max_f4_bits, out_of_range, bad_alpha, pad
+    PPF_CUDA(ctx, cudaMallocAsync(&d_range, 12 * sizeof(int), ctx->stream));
+    int h_range[12] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, INT_MIN, -1, 0, 0, 0};
     PPF_CUDA(ctx, cudaMemcpyAsync(d_range, h_range, sizeof(h_range), cudaMemcpyHostToDevice, ctx->stream));
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
@@ -408,6 +416,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     }
     K2_CUDA(cudaMalloc(&t->entries, std::max<size_t>(1, n_entries) * sizeof(uint2)));
     K2_CUDA(cudaMalloc(&t->entry_idx, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
+    K2_CUDA(cudaMalloc(&t->entry_alpha, std::max<size_t>(1, n_entries) * sizeof(float)));
     unsigned long long *d_cnt = nullptr;
     K2_CUDA(cudaMallocAsync(&d_cnt, sizeof(unsigned long long), ctx->stream));
     K2_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
@@ -415,7 +424,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         auto launch = [&]() -> int {
             if (n_entries) {
                 PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
-                           info.slice_rows, info.n_alpha, t->entries);
+                           info.slice_rows, t->bp.row_stride, t->entries, t->entry_alpha, d_range + 10);
                 PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
                                               cudaMemcpyDeviceToDevice, ctx->stream));
             }
@@ -426,9 +435,16 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     }
     unsigned long long h_cnt = 0;
     K2_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    K2_CUDA(cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev[3], ctx->stream);
     K2_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFreeAsync(d_cnt, ctx->stream);
+    if (h_range[10] != 0) {
+        cleanup();
+        b200ppf_table_free(t);
+        return fail_msg(ctx, B200PPF_ERR_INVALID,
+                        "table build: an alpha_m lies outside [-pi, pi] (not produced by PPFEstimation::compute)");
+    }
     info.n_keys = h_cnt;
     cleanup();
     cudaEventElapsedTime(&ctx->timings.keys_ms, ctx->ev[0], ctx->ev[1]);
@@ -481,7 +497,7 @@ int k2_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host) {
     PPF_LAUNCH(ctx, fill_nan_kernel, blocks, 256, 0, d, count);
     if (t->info.n_entries)
         PPF_LAUNCH(ctx, alpha_scatter_kernel, (unsigned)((t->info.n_entries + 255) / 256), 256, 0, t->entry_idx,
-                   t->entries, (uint32_t)t->info.n_entries, d);
+                   t->entry_alpha, (uint32_t)t->info.n_entries, d);
     PPF_CUDA(ctx, cudaMemcpyAsync(host, d, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     PPF_CUDA(ctx, cudaFreeAsync(d, ctx->stream));

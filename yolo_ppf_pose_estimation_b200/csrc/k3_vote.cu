@@ -28,16 +28,30 @@ namespace b200ppf {
 
 namespace {
 
-constexpr int VOTE_THREADS = 512;
+#ifndef B200PPF_VOTE_THREADS
+#define B200PPF_VOTE_THREADS 512
+#endif
+#ifndef B200PPF_VOTE_MINBLOCKS
+#define B200PPF_VOTE_MINBLOCKS 2
+#endif
+constexpr int VOTE_THREADS = B200PPF_VOTE_THREADS;
 constexpr int VOTE_WARPS = VOTE_THREADS / 32;
-constexpr int CAND_CAP = 2048;  // in-radius candidates buffered between flushes
-constexpr int ITEM_CAP = VOTE_THREADS;
+#ifndef B200PPF_CAND_CAP
+#define B200PPF_CAND_CAP 2048
+#endif
+#ifndef B200PPF_ITEM_CAP
+#define B200PPF_ITEM_CAP B200PPF_VOTE_THREADS
+#endif
+constexpr int CAND_CAP = B200PPF_CAND_CAP;  // in-radius candidates buffered between flushes
+constexpr int ITEM_CAP = B200PPF_ITEM_CAP;  // candidates turned into work items per B/C round (<= VOTE_THREADS)
+static_assert(ITEM_CAP <= VOTE_THREADS, "one thread per candidate in phase B");
 constexpr int VOTE_UNROLL = 4;
 static_assert(CAND_CAP >= 2 * VOTE_THREADS, "flush threshold must leave one sweep iteration of room");
 
 struct WorkItem {
     uint32_t off, len;
-    float alpha_s;
+    float alpha_s;  // PCL's float (literal form of the guard-band votes)
+    uint32_t c_s;   // alpha_to_fix(alpha_s) - 2^31 (fixed-point hot loop)
 };
 
 constexpr size_t QUEUE_BYTES = CAND_CAP * sizeof(uint32_t) + ITEM_CAP * sizeof(WorkItem);
@@ -53,6 +67,7 @@ struct VoteArgs {
     uint32_t ref_first, ref_step, ref_count;
     const uint32_t *offsets;
     const uint2 *entries;
+    const float *entry_alpha;
     KeyParams kp;
     BinParams bp;
     int feature_mode;
@@ -73,39 +88,39 @@ __device__ __forceinline__ void red_shared_inc(uint32_t addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
-// One vote of the hot loop (alpha mode A): fp32 estimate of the bin and an unconditional increment.
-// When the estimate lies inside the guard band (or is NaN) the increment is steered to a scratch
-// word instead of the accumulator — ATOMS cannot be predicated, and a select is cheaper than a
-// divergent branch — and true is returned: the caller then settles the entry with the literal
-// double-precision form (alpha_bin_exact).  Same arithmetic as alpha_bin_fast in ppf_math.cuh.
-__device__ __forceinline__ bool vote_fast_a(const BinParams &bp, uint32_t acc_addr, uint32_t scratch_addr, uint2 en,
-                                            float alpha_s) {
-    const float d = __uint_as_float(en.y) - alpha_s;
-    float w = d;
-    if (d <= -3.14159274f) w = d + 6.28318548f;
-    else if (d >= 3.14159274f) w = d - 6.28318548f;
-    const float q = (w + 3.14159274f) * bp.inv_step;
-    const float fl = floorf(q);
-    const float fr = q - fl;
-    const bool ok = (fr > bp.guard) && (fr < 1.0f - bp.guard);
-    const uint32_t bin = min((uint32_t)max((int)fl, 0), bp.n_alpha - 1u);
-    red_shared_inc(ok ? acc_addr + ((en.x + bin) << 2) : scratch_addr);
-    return !ok;
+// One vote of the hot loop (alpha mode A), in fixed point (ppf_math.cuh, alpha_bin_fixed):
+//   X = A_m - C_s  (wraps like the angle),  hi = mulhi(X, T_fix) = bin.position,  (bin, frac) = hi * 2^(32-s).
+// The increment is unconditional — ATOMS cannot be predicated and a select is cheaper than a
+// divergent branch — but when frac lies in the guard band around a bin edge (or X in the band
+// around the +-pi seam), or the lane is past the end of the bucket, it is steered to a scratch
+// word; a guard-band hit returns true and the caller settles that entry with the literal
+// double-precision form.  ~10 integer instructions per vote, nothing on the XU pipe.
+template <bool SEAM>
+__device__ __forceinline__ bool vote_fixed(const BinParams &bp, uint32_t acc_addr, uint32_t scratch_addr, uint2 en,
+                                           uint32_t c_s, bool valid) {
+    const uint32_t x = en.y - c_s;
+    const uint32_t hi = __umulhi(x, bp.fix_mul);
+    const unsigned long long p2 = (unsigned long long)hi * bp.frac_mul;  // runtime multiplier: stays an IMAD (FMA pipe)
+    const uint32_t bin = (uint32_t)(p2 >> 32), frac = (uint32_t)p2;
+    bool sure = (frac - bp.fix_guard) < (0u - 2u * bp.fix_guard);
+    if (SEAM) sure = sure && ((x + bp.seam_guard) >= 2u * bp.seam_guard);
+    red_shared_inc((sure && valid) ? acc_addr + ((en.x + bin) << 2) : scratch_addr);
+    return valid && !sure;
 }
 
-// the rare path, and every vote of alpha mode B: literal form
+// the rare path, and every vote of alpha mode B: literal form on PCL's floats
 template <int MODE>
-__device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_addr, uint2 en, float alpha_s,
-                                           uint32_t &skipped) {
+__device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_addr, uint32_t rowoff, float alpha_m,
+                                           float alpha_s, uint32_t &skipped) {
     const uint32_t bin = MODE == ALPHA_MODE_B
-                             ? alpha_bin_fast(bp, __uint_as_float(en.y), alpha_s)
-                             : alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, __uint_as_float(en.y), alpha_s);
+                             ? alpha_bin_fast(bp, alpha_m, alpha_s)
+                             : alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
     if (bin == 0xFFFFFFFFu) ++skipped;  // NaN alpha: no vote
-    else red_shared_inc(acc_addr + ((en.x + bin) << 2));
+    else red_shared_inc(acc_addr + ((rowoff + bin) << 2));
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(VOTE_THREADS, 2)
+template <int MODE, bool SEAM>
+__global__ void __launch_bounds__(VOTE_THREADS, B200PPF_VOTE_MINBLOCKS)
 ppf_vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Frame s_sg;
@@ -118,9 +133,10 @@ ppf_vote_kernel(const VoteArgs a) {
     const uint32_t slice = blockIdx.y;
     const uint32_t slice_base = slice * a.kp.slice_rows;
     const uint32_t rows = min(a.kp.slice_rows, a.n_model - slice_base);
-    const uint32_t acc_len = rows * a.bp.n_alpha;
+    const uint32_t stride = a.bp.row_stride;             // n_alpha + 1 words per model row
+    const uint32_t acc_len = rows * stride;
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *cand = acc + (size_t)a.kp.slice_rows * a.bp.n_alpha;
+    uint32_t *cand = acc + (size_t)a.kp.slice_rows * stride;
     WorkItem *items = reinterpret_cast<WorkItem *>(cand + CAND_CAP);
     const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
     const uint32_t scratch_addr = (uint32_t)__cvta_generic_to_shared(&s_scratch);
@@ -159,14 +175,15 @@ ppf_vote_kernel(const VoteArgs a) {
     // phases B + C over the buffered candidates
     auto flush = [&]() {
         const uint32_t ncand = s_ncand;
-        for (uint32_t c0 = 0; c0 < ncand; c0 += VOTE_THREADS) {
+        for (uint32_t c0 = 0; c0 < ncand; c0 += ITEM_CAP) {
             // ---- B: pair features -> work items -------------------------------------------------
             const uint32_t c = c0 + tid;
             bool push = false;
             WorkItem it;
             it.off = it.len = 0;
             it.alpha_s = 0.0f;
-            if (c < ncand) {
+            it.c_s = 0;
+            if (tid < ITEM_CAP && c < ncand) {
                 const uint32_t s = cand[c];
                 const float4 p4 = __ldg(a.gpos + s), n4 = __ldg(a.gnrm + s);
                 float f[4];
@@ -181,6 +198,7 @@ ppf_vote_kernel(const VoteArgs a) {
                             it.off = o0;
                             it.len = o1 - o0;
                             it.alpha_s = planar_alpha(s_sg, v3_of(p4));
+                            it.c_s = alpha_to_fix(it.alpha_s) - 0x80000000u;
                             push = true;
                             ++st_nonempty;
                         }
@@ -203,34 +221,51 @@ ppf_vote_kernel(const VoteArgs a) {
                 w = __shfl_sync(0xFFFFFFFFu, w, 0);
                 if (w >= nitems) break;
                 const WorkItem wi = items[w];
-                const uint2 *e = a.entries + wi.off + lane;
+                const uint2 *e = a.entries + wi.off;
                 if (lane == 0) st_votes += wi.len;
-                uint32_t k0 = 0;
                 if (MODE == ALPHA_MODE_A) {
-                    // full 4 x 32 chunks: four gathers in flight, four branch-free votes
-                    for (; k0 + 32 * VOTE_UNROLL <= wi.len; k0 += 32 * VOTE_UNROLL) {
+                    // 4 x 32 entries per step: four 8-byte gathers in flight per lane, four branch-free
+                    // votes.  The last, partial step clamps its loads to the final entry and votes into
+                    // the scratch word from the lanes past the end.
+                    const uint32_t last = wi.len - 1;
+                    uint32_t k0 = lane;
+                    for (; k0 + 32 * (VOTE_UNROLL - 1) <= last; k0 += 32 * VOTE_UNROLL) {
                         uint2 en[VOTE_UNROLL];
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u) en[u] = __ldg(e + k0 + u * 32);
                         bool risky[VOTE_UNROLL];
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u)
-                            risky[u] = vote_fast_a(a.bp, acc_addr, scratch_addr, en[u], wi.alpha_s);
+                            risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s, true);
                         bool any = false;
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u) any |= risky[u];
                         if (any) {
 #pragma unroll
                             for (int u = 0; u < VOTE_UNROLL; ++u)
-                                if (risky[u]) vote_exact<MODE>(a.bp, acc_addr, en[u], wi.alpha_s, st_skipped);
+                                if (risky[u])
+                                    vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
+                                                     wi.alpha_s, st_skipped);
                         }
                     }
-                }
-                // tail (and alpha mode B)
-                for (uint32_t k = k0 + lane; k < wi.len; k += 32) {
-                    const uint2 en = __ldg(e + (k - lane));
-                    if (MODE == ALPHA_MODE_B || vote_fast_a(a.bp, acc_addr, scratch_addr, en, wi.alpha_s))
-                        vote_exact<MODE>(a.bp, acc_addr, en, wi.alpha_s, st_skipped);
+                    if (k0 - lane <= last) {  // warp-uniform: a partial step remains
+                        uint2 en[VOTE_UNROLL];
+#pragma unroll
+                        for (int u = 0; u < VOTE_UNROLL; ++u) en[u] = __ldg(e + min(k0 + u * 32, last));
+                        bool risky[VOTE_UNROLL];
+#pragma unroll
+                        for (int u = 0; u < VOTE_UNROLL; ++u)
+                            risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s, k0 + u * 32 <= last);
+#pragma unroll
+                        for (int u = 0; u < VOTE_UNROLL; ++u)
+                            if (risky[u])
+                                vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
+                                                 wi.alpha_s, st_skipped);
+                    }
+                } else {
+                    for (uint32_t k = lane; k < wi.len; k += 32)
+                        vote_exact<MODE>(a.bp, acc_addr, __ldg(e + k).x, __ldg(a.entry_alpha + wi.off + k), wi.alpha_s,
+                                         st_skipped);
                 }
             }
             __syncthreads();
@@ -245,45 +280,70 @@ ppf_vote_kernel(const VoteArgs a) {
     };
 
     // ---- A: sweep the 27-cell neighbourhood ---------------------------------------------------------
-    for (int r = 0; r < 9; ++r) {
-        const uint32_t rb = s_run_start[r], re = s_run_end[r];
-        for (uint32_t base = rb; base < re; base += VOTE_THREADS) {
-            const uint32_t s = base + tid;
-            bool in = false;
-            if (s < re) {
-                const float4 p4 = __ldg(a.gpos + s);
-                const float dx = p4.x - p_r.x, dy = p4.y - p_r.y, dz = p4.z - p_r.z;
-                const float d2 = (dx * dx + dy * dy) + dz * dz;
-                // radius predicate on f4 itself (SURVEY.md A.8 rule 7): sqrtf(d2) < radius, evaluated
-                // through the equivalent threshold on d2 (sqrtf is monotone and correctly rounded)
-                in = d2 < a.radius_sq_bound && __ldg(a.gorig + s) != s_r;
-                ++st_examined;
+    auto test_and_queue = [&](uint32_t s, uint32_t re) {
+        bool in = false;
+        if (s < re) {
+            const float4 p4 = __ldg(a.gpos + s);
+            const float dx = p4.x - p_r.x, dy = p4.y - p_r.y, dz = p4.z - p_r.z;
+            const float d2 = (dx * dx + dy * dy) + dz * dz;
+            // radius predicate on f4 itself (SURVEY.md A.8 rule 7): sqrtf(d2) < radius, evaluated
+            // through the equivalent threshold on d2 (sqrtf is monotone and correctly rounded)
+            in = d2 < a.radius_sq_bound && __ldg(a.gorig + s) != s_r;
+            ++st_examined;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
+        if (m) {
+            uint32_t b = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&s_ncand, __popc(m));
+            b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
+            if (in) cand[b + __popc(m & ((1u << lane) - 1u))] = s;
+        }
+    };
+    uint32_t neighbourhood = 0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) neighbourhood += s_run_end[r] - s_run_start[r];
+    if (neighbourhood <= CAND_CAP) {
+        // the common case: every point of the 27 cells fits the queue — no barriers inside the sweep
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t rb = s_run_start[r], re = s_run_end[r];
+            for (uint32_t base = rb; base < re; base += VOTE_THREADS) test_and_queue(base + tid, re);
+        }
+        __syncthreads();
+    } else {
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t rb = s_run_start[r], re = s_run_end[r];
+            for (uint32_t base = rb; base < re; base += VOTE_THREADS) {
+                test_and_queue(base + tid, re);
+                __syncthreads();
+                const uint32_t buffered = s_ncand;
+                __syncthreads();  // nobody may start the next sweep's atomics before everyone has read
+                if (buffered > CAND_CAP - VOTE_THREADS) flush();
             }
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
-            if (m) {
-                uint32_t b = 0;
-                if (lane == (uint32_t)(__ffs(m) - 1)) b = atomicAdd(&s_ncand, __popc(m));
-                b = __shfl_sync(0xFFFFFFFFu, b, __ffs(m) - 1);
-                if (in) cand[b + __popc(m & ((1u << lane) - 1u))] = s;
-            }
-            __syncthreads();
-            const uint32_t buffered = s_ncand;
-            __syncthreads();  // nobody may start the next sweep's atomics before everyone has read
-            if (buffered > CAND_CAP - VOTE_THREADS) flush();
         }
     }
     flush();
 
     // ---- peak: first maximum in (i, bin) order == max of (votes, ~flat) ---------------------------
+    // one thread per model row: fold PCL's out-of-range bin n_alpha into n_alpha - 1, then scan the row
+    const uint32_t n_alpha = a.bp.n_alpha;
     unsigned long long best = 0;
-    for (uint32_t k = tid; k < acc_len; k += VOTE_THREADS) {
-        const uint32_t v = acc[k];
-        if (v) {
-            const unsigned long long c =
-                ((unsigned long long)v << 32) | (unsigned long long)(0xFFFFFFFFu - (slice_base * a.bp.n_alpha + k));
-            best = max(best, c);
+    for (uint32_t r = tid; r < rows; r += VOTE_THREADS) {
+        uint32_t *row = acc + r * stride;
+        row[n_alpha - 1] += row[n_alpha];
+        uint32_t bv = 0, bc = 0;
+        for (uint32_t c = 0; c < n_alpha; ++c) {
+            const uint32_t v = row[c];
+            if (v > bv) {  // strict: the first maximum of the row
+                bv = v;
+                bc = c;
+            }
+            if (a.acc_dump) a.acc_dump[(size_t)(slice_base + r) * n_alpha + c] = v;
         }
-        if (a.acc_dump) a.acc_dump[(size_t)slice_base * a.bp.n_alpha + k] = v;
+        if (bv) {
+            const unsigned long long cnd =
+                ((unsigned long long)bv << 32) | (unsigned long long)(0xFFFFFFFFu - ((slice_base + r) * n_alpha + bc));
+            best = max(best, cnd);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, shfl_xor_u64(best, o));
@@ -374,12 +434,12 @@ __global__ void debug_alpha_bins_kernel(BinParams bp, const float *__restrict__ 
                                         uint32_t n, uint32_t *__restrict__ fast, uint32_t *__restrict__ exact) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    fast[p] = alpha_bin_fast(bp, am[p], as[p]);
+    fast[p] = alpha_bin_hot(bp, am[p], as[p]);
     exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, am[p], as[p]);
 }
 
 size_t vote_smem_bytes(const b200ppf_table *t) {
-    return (size_t)t->info.slice_rows * t->info.n_alpha * sizeof(uint32_t) + QUEUE_BYTES;
+    return (size_t)t->info.slice_rows * (t->info.n_alpha + 1) * sizeof(uint32_t) + QUEUE_BYTES;
 }
 
 // smallest float x with sqrtf(x) >= r (host sqrtf and device sqrtf are both correctly rounded)
@@ -414,6 +474,7 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     a.ref_count = (uint32_t)ref_count;
     a.offsets = t->offsets;
     a.entries = t->entries;
+    a.entry_alpha = t->entry_alpha;
     a.kp = t->kp;
     a.bp = t->bp;
     a.bp.mode = ctx->alpha_mode;
@@ -427,13 +488,16 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     const size_t smem = vote_smem_bytes(t);
     dim3 grid_dim((unsigned)ref_count, t->info.n_slices);
     cudaEventRecord(ctx->ev_vote[1], ctx->stream);  // grid build ends, voting starts
-    if (ctx->alpha_mode == ALPHA_MODE_B) {
-        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<ALPHA_MODE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PPF_LAUNCH(ctx, ppf_vote_kernel<ALPHA_MODE_B>, grid_dim, VOTE_THREADS, smem, a);
-    } else {
-        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<ALPHA_MODE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PPF_LAUNCH(ctx, ppf_vote_kernel<ALPHA_MODE_A>, grid_dim, VOTE_THREADS, smem, a);
-    }
+#define LAUNCH_VOTE(M, S)                                                                                          \
+    do {                                                                                                            \
+        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                           (int)smem));                                                             \
+        PPF_LAUNCH(ctx, (ppf_vote_kernel<M, S>), grid_dim, VOTE_THREADS, smem, a);                                  \
+    } while (0)
+    if (ctx->alpha_mode == ALPHA_MODE_B) LAUNCH_VOTE(ALPHA_MODE_B, false);
+    else if (a.bp.seam_guard) LAUNCH_VOTE(ALPHA_MODE_A, true);
+    else LAUNCH_VOTE(ALPHA_MODE_A, false);
+#undef LAUNCH_VOTE
     cudaEventRecord(ctx->ev_vote[2], ctx->stream);
     scene_grid_free(ctx, &grid);
     return B200PPF_OK;
@@ -475,6 +539,23 @@ BinParams make_bin_params(float angle_step, int alpha_mode) {
     bp.mode = alpha_mode;
     bp.mode_b_offset = (int)floor(M_PI / (double)angle_step);
     bp.guard = std::max(2e-4f, 1e-5f * bp.inv_step);
+    bp.row_stride = bp.n_alpha + 1;
+    // fixed-point hot loop: T bins per turn, multiplier with as many fractional bits as fit 32 bits
+    const double T = 2.0 * M_PI / (double)angle_step;
+    int kbits = 1;
+    while ((double)(1ull << kbits) <= T + 1.0) ++kbits;  // integer bits of T
+    bp.fix_shift = (uint32_t)std::min(31, std::max(1, 32 - kbits - 1));
+    bp.fix_mul = (uint32_t)llrint(T * (double)(1ull << bp.fix_shift));
+    bp.frac_mul = 1u << (32u - bp.fix_shift);
+    // PCL's float rounding moves alpha by <= 3.6e-7 rad; guard = 4e-6 rad on both sides of an edge
+    const double guard_rad = 4e-6;
+    const double guard_bins = std::min(0.25, guard_rad / (double)angle_step);
+    bp.fix_guard = (uint32_t)(guard_bins * 4294967296.0);
+    // the +-pi seam sits at X = 0 (mod 2^32): below it the position inside the last bin is frac(T).
+    // If frac(T) itself is inside the bin guard the seam is already covered.
+    const double fracT = T - floor(T);
+    const bool covered = fracT < guard_bins || fracT > 1.0 - guard_bins;
+    bp.seam_guard = covered ? 0u : (uint32_t)(guard_rad / (2.0 * M_PI) * 4294967296.0);
     return bp;
 }
 
@@ -483,7 +564,7 @@ int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, cons
     const BinParams bp = make_bin_params(angle_step, alpha_mode);
     if (!ctx) {  // host build of the same inline functions
         for (size_t p = 0; p < n; ++p) {
-            fast[p] = alpha_bin_fast(bp, alpha_m[p], alpha_s[p]);
+            fast[p] = alpha_bin_hot(bp, alpha_m[p], alpha_s[p]);
             exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, alpha_m[p], alpha_s[p]);
         }
         return B200PPF_OK;

@@ -69,7 +69,8 @@ struct b200ppf_table {
     b200ppf::KeyParams kp{};
     b200ppf::BinParams bp{};
     uint32_t *offsets = nullptr;  // [n_slices*key_space + 1]
-    uint2 *entries = nullptr;     // {row offset = (i - slice_base)*n_alpha, alpha_m bits} per entry
+    uint2 *entries = nullptr;     // {accumulator word offset of row (i - slice_base), alpha_m as fixed-point turns} per entry
+    float *entry_alpha = nullptr;  // alpha_m as PCL's float (guard-band votes, alpha_m_ export)
     uint32_t *entry_idx = nullptr;  // i*n + j per entry (API queries, alpha_m_ export)
     int feature_mode = 0;
 };

@@ -191,8 +191,47 @@ struct BinParams {
     int mode;
     int mode_b_offset;  // floor(pi / angle_step)
     float guard;        // max(2e-4, 1e-5 / angle_step): > 20x the fp32 estimate's error bound
+    // fixed-point form of the hot loop (alpha_bin_fixed below)
+    uint32_t row_stride;   // accumulator row stride = n_alpha + 1 (PCL's out-of-range bin n_alpha gets a cell, merged later)
+    uint32_t fix_mul;      // round(T * 2^fix_shift), T = 2*pi/angle_step bins per turn
+    uint32_t fix_shift;    // fractional bits of fix_mul: high word of X*fix_mul = bin . (fix_shift-bit position inside the bin)
+    uint32_t frac_mul;     // 2^(32 - fix_shift): a second multiply splits that word into (bin, position << (32-fix_shift))
+    uint32_t fix_guard;    // guard band around bin edges, in 2^-32 bins (>= 10x the worst disagreement with PCL's floats)
+    uint32_t seam_guard;   // guard band around the +-pi seam in 2^-32 turns; 0 when the bin guard already covers it
 };
 
+// ---- fixed-point alpha arithmetic -------------------------------------------------------------
+// An angle a in [-pi, pi] is held as A = round((a + pi) / (2*pi) * 2^32) (mod 2^32), one "turn" per
+// 2^32, so differences wrap for free.  For a model entry A_m and a scene pair constant
+// C_s = A_s - 2^31:   X = A_m - C_s  ==  ((alpha_m - alpha_s + pi) mod 2*pi) / (2*pi) * 2^32,
+// which is exactly the quantity PCL bins: floor((wrap(alpha_m - alpha_s) + pi) / step) = floor(X/2^32 * T).
+// The high word of X * fix_mul is the bin followed by fix_shift bits of position inside the bin.  This evaluates the EXACT real-number bin; PCL rounds the
+// difference to float (<= 3.6e-7 rad off), so whenever the position lies within fix_guard of an
+// edge (or X within seam_guard of the +-pi seam) the literal double form decides instead.
+__host__ __device__ __forceinline__ uint32_t alpha_to_fix(float a) {
+    const double K = 4294967296.0 / 6.283185307179586476925286766559;
+    const double v = ((double)a + 3.14159265358979323846) * K;
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(unsigned long long)__double2ll_rn(v);
+#else
+    return (uint32_t)(unsigned long long)llrint(v);
+#endif
+}
+
+// returns the bin in [0, n_alpha] (n_alpha = PCL's out-of-range bin) or 0xFFFFFFFF when the guard
+// bands say "decide with the literal form"
+__host__ __device__ __forceinline__ uint32_t alpha_bin_fixed(const BinParams &bp, uint32_t a_m, uint32_t c_s) {
+    const uint32_t x = a_m - c_s;
+    const uint32_t hi = (uint32_t)(((unsigned long long)x * bp.fix_mul) >> 32);
+    // two multiplies instead of shifts: they run on the FMA pipe, the ALU pipe is the busy one
+    const unsigned long long p2 = (unsigned long long)hi * bp.frac_mul;
+    const uint32_t bin = (uint32_t)(p2 >> 32), frac = (uint32_t)p2;
+    bool ok = (frac - bp.fix_guard) < (0u - 2u * bp.fix_guard);
+    if (bp.seam_guard) ok = ok && ((x + bp.seam_guard) >= 2u * bp.seam_guard);
+    return ok ? bin : 0xFFFFFFFFu;
+}
+
+// fp32 form (used by alpha mode B and kept as a cross-check of mode A)
 __host__ __device__ __forceinline__ uint32_t alpha_bin_fast(const BinParams &bp, float alpha_m, float alpha_s) {
     float d = alpha_m - alpha_s;
     if (bp.mode == ALPHA_MODE_B) {
@@ -213,6 +252,17 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_fast(const BinParams &bp,
     if (fl < 0.0f) return 0u;  // only reachable for |alpha_m - alpha_s| > 3*pi; same as the literal form
     uint32_t bin = (uint32_t)(int)fl;
     return bin >= bp.n_alpha ? bp.n_alpha - 1 : bin;
+}
+
+// what the voting kernel computes for one vote (mode A: fixed-point estimate, literal form inside
+// the guard bands; mode B: the legacy formula, already cheap).  Domain: alpha_m, alpha_s in
+// [-pi, pi] as produced by atan2f — the table build rejects anything else.
+__host__ __device__ __forceinline__ uint32_t alpha_bin_hot(const BinParams &bp, float alpha_m, float alpha_s) {
+    if (bp.mode == ALPHA_MODE_B) return alpha_bin_fast(bp, alpha_m, alpha_s);
+    if (alpha_m != alpha_m || alpha_s != alpha_s) return 0xFFFFFFFFu;
+    const uint32_t b = alpha_bin_fixed(bp, alpha_to_fix(alpha_m), alpha_to_fix(alpha_s) - 0x80000000u);
+    if (b == 0xFFFFFFFFu) return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
+    return b >= bp.n_alpha ? bp.n_alpha - 1 : b;
 }
 
 __host__ __device__ __forceinline__ float peak_theta(int mode, float angle_step, uint32_t bin) {
