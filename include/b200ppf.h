@@ -171,6 +171,10 @@ int b200ppf_vote_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t,
 int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
                              const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact);
 
+/* roofline denominator the HBM/tensor peaks do not cover: measured rate of shared-memory reductions
+ * (one per vote).  pattern 0 = conflict-free, 1 = random words (the voting kernel's), 2 = one word. */
+int b200ppf_microbench_atoms(b200ppf_ctx *ctx, int pattern, double *atoms_per_sec);
+
 /* ---- K4: [PCL] ppf_registration.hpp clusterPoses / posesWithinErrorBounds ---------------- */
 int b200ppf_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_host, size_t n, float pos_thr,
                     float rot_thr, float *poses16, uint32_t *votes, size_t *n_out);

@@ -73,6 +73,7 @@ SYMBOLS = {
     "b200ppf_vote_debug_pairs": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "b200ppf_vote_debug_accumulator": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "b200ppf_debug_alpha_bins": (_i, [_vp, _f, _i, _vp, _vp, _sz, _vp, _vp]),
+    "b200ppf_microbench_atoms": (_i, [_vp, _i, C.POINTER(C.c_double)]),
     "b200ppf_cluster": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_cluster_device": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_cluster_assignment": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
@@ -245,6 +246,12 @@ class Context:
         acc = np.zeros((info.n_model, info.n_alpha), np.uint32)
         self.check(lib().b200ppf_vote_debug_accumulator(self._h, table._h, scene._h, s_r, _p(acc)))
         return acc
+
+    def microbench_atoms(self, pattern=1):
+        """measured shared-memory reduction rate (atomics/s): 0 conflict-free, 1 random words, 2 one word"""
+        v = C.c_double(0.0)
+        self.check(lib().b200ppf_microbench_atoms(self._h, pattern, C.byref(v)))
+        return v.value
 
     # ---- K4 / K5 / align ------------------------------------------------------------------------
     def cluster(self, hyps, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi, device_ptr=None, n=None):

@@ -436,6 +436,12 @@ int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode,
     return k3_debug_alpha_bins(ctx, angle_step, alpha_mode, alpha_m, alpha_s, n, fast, exact);
 }
 
+int b200ppf_microbench_atoms(b200ppf_ctx *ctx, int pattern, double *atoms_per_sec) {
+    CHECK_CTX(ctx);
+    if (!atoms_per_sec || pattern < 0 || pattern > 2) return fail_msg(ctx, B200PPF_ERR_INVALID, "microbench: bad argument");
+    return microbench_atoms(ctx, pattern, atoms_per_sec);
+}
+
 /* ---- K4 ----------------------------------------------------------------------------------- */
 
 int b200ppf_cluster_device(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n, float pos_thr,

@@ -248,19 +248,12 @@ ppf_vote_kernel(const VoteArgs a) {
                                                      wi.alpha_s, st_skipped);
                         }
                     }
-                    if (k0 - lane <= last) {  // warp-uniform: a partial step remains
-                        uint2 en[VOTE_UNROLL];
-#pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u) en[u] = __ldg(e + min(k0 + u * 32, last));
-                        bool risky[VOTE_UNROLL];
-#pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u)
-                            risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s, k0 + u * 32 <= last);
-#pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u)
-                            if (risky[u])
-                                vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
-                                                 wi.alpha_s, st_skipped);
+                    // remainder (< 128 entries): one entry per lane per step; lanes past the end re-read the
+                    // last entry and vote into the scratch word
+                    for (; k0 - lane <= last; k0 += 32) {  // warp-uniform condition
+                        const uint2 en = __ldg(e + min(k0, last));
+                        if (vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en, wi.c_s, k0 <= last))
+                            vote_exact<MODE>(a.bp, acc_addr, en.x, __ldg(a.entry_alpha + wi.off + k0), wi.alpha_s, st_skipped);
                     }
                 } else {
                     for (uint32_t k = lane; k < wi.len; k += 32)

@@ -116,6 +116,7 @@ int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf
 int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
                          const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact);
 BinParams make_bin_params(float angle_step, int alpha_mode);
+int microbench_atoms(b200ppf_ctx *ctx, int pattern, double *atoms_per_sec);
 int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n, float pos_thr, float rot_thr,
                float *poses16, uint32_t *votes, size_t *n_out);
 int k5_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose16, float *out_host,

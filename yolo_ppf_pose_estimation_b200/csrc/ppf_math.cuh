@@ -260,6 +260,10 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_fast(const BinParams &bp,
 __host__ __device__ __forceinline__ uint32_t alpha_bin_hot(const BinParams &bp, float alpha_m, float alpha_s) {
     if (bp.mode == ALPHA_MODE_B) return alpha_bin_fast(bp, alpha_m, alpha_s);
     if (alpha_m != alpha_m || alpha_s != alpha_s) return 0xFFFFFFFFu;
+    // the fixed-point form holds one turn: both angles must be atan2f results (|a| <= float(pi)), which
+    // is what the table and the scene frames produce; anything else takes the literal form
+    if (!(fabsf(alpha_m) <= 3.14159274f && fabsf(alpha_s) <= 3.14159274f))
+        return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
     const uint32_t b = alpha_bin_fixed(bp, alpha_to_fix(alpha_m), alpha_to_fix(alpha_s) - 0x80000000u);
     if (b == 0xFFFFFFFFu) return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
     return b >= bp.n_alpha ? bp.n_alpha - 1 : b;
