@@ -85,7 +85,7 @@ typedef struct b200ppf_table_info {
     int32_t size[4];      /* extent of each quantised component */
     float angle_step, dist_step;
     float max_dist;       /* getModelDiameter() */
-    float reserved;
+    uint32_t phase_cells; /* alpha_m phase cells per bucket (1: buckets are not subdivided) */
 } b200ppf_table_info;
 
 /* per-stage device times of the last call on this context, milliseconds (CUDA events) */
@@ -142,7 +142,8 @@ int b200ppf_table_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int3
 /* the public alpha_m_[i][j] member, row-major n*n floats (NaN where the pair is invalid) */
 int b200ppf_table_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host);
 /* raw CSR export (parity tests, serialisation): offsets has n_slices*key_space+1 entries;
- * the three entry arrays have n_entries elements.  Any pointer may be NULL. */
+ * the three entry arrays have n_entries elements, in canonical (i, j) order inside every bucket.
+ * Any pointer may be NULL. */
 int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *offsets,
                          uint32_t *entry_i, uint32_t *entry_j, float *entry_alpha_m);
 void b200ppf_table_free(b200ppf_table *t);

@@ -1,7 +1,9 @@
 // capi.cu — the extern "C" surface declared in include/b200ppf.h.
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "ppf_common.cuh"
@@ -352,6 +354,27 @@ int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *off
     }
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const uint32_t n = (uint32_t)t->info.n_model;
+    if (t->info.phase_cells > 1 && ne) {
+        // buckets are stored in (phase cell, i, j) order: report them in the canonical (i, j) order
+        std::vector<uint32_t> off(total), all_idx(ne);
+        PPF_CUDA(ctx, cudaMemcpyAsync(off.data(), t->offsets, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PPF_CUDA(ctx, cudaMemcpyAsync(all_idx.data(), t->entry_idx, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<std::pair<uint32_t, uint32_t>> order;
+        for (size_t k = 0; k + 1 < total; ++k) {
+            const uint32_t b = off[k], e = off[k + 1];
+            if (e - b < 2) continue;
+            order.resize(e - b);
+            for (uint32_t p = b; p < e; ++p) order[p - b] = std::make_pair(all_idx[p], p);
+            std::sort(order.begin(), order.end());
+            for (uint32_t p = b; p < e; ++p) {
+                if (!idx.empty()) idx[p] = order[p - b].first;
+                if (entry_alpha_m) entry_alpha_m[p] = ent[order[p - b].second];
+            }
+            if (entry_alpha_m)
+                for (uint32_t p = b; p < e; ++p) ent[p] = entry_alpha_m[p];
+        }
+    }
     for (size_t e = 0; e < idx.size(); ++e) {
         if (entry_i) entry_i[e] = idx[e] / n;
         if (entry_j) entry_j[e] = idx[e] % n;
@@ -364,7 +387,9 @@ void b200ppf_table_free(b200ppf_table *t) {
     if (!t) return;
     DeviceGuard guard(t->ctx ? t->ctx->device : 0);
     if (t->offsets) cudaFree(t->offsets);
-    if (t->entries) cudaFree(t->entries);
+    if (t->sub_offsets) cudaFree(t->sub_offsets);
+    if (t->entry_w) cudaFree(t->entry_w);
+    if (t->entry_am) cudaFree(t->entry_am);
     if (t->entry_idx) cudaFree(t->entry_idx);
     if (t->entry_alpha) cudaFree(t->entry_alpha);
     delete t;

@@ -6,10 +6,15 @@
 //   keys    quantise exactly as PCL: d = floor(f / step) per component, packed densely into one
 //           32-bit integer (no hashing, hence no collisions), prefixed by the accumulator slice
 //           of model row i so that one CSR serves every slice;
-//   sort    stable LSD radix sort of (key, pair index, alpha_m)  -> buckets ascend in (i, j),
-//           the canonical order nearestNeighborSearch reports;
-//   CSR     offsets[key] by binary search over the sorted keys; entries {row offset, alpha_m}
-//           8 bytes each — all the voting kernel gathers; j survives only in entry_idx.
+//   phase   when 2*pi/angle_step is an integer up to the guard band (PCL's 12 degrees is), the sort
+//           key is extended by the phase cell of alpha_m — the position of (alpha_m + pi)/step inside
+//           its bin, 16 cells — so that a bucket is ordered (cell, i, j) and the voting kernel can
+//           shift whole ranges of it by one constant (ppf_math.cuh "constant-shift voting");
+//   sort    stable LSD radix sort of (key.cell, pair index, alpha_m);
+//   CSR     offsets[key] (buckets) and sub_offsets[key.cell] by binary search over the sorted keys;
+//           per entry a 4-byte hot word (wrap field | accumulator byte offset of (row, bin of alpha_m)),
+//           alpha_m in fixed point and as PCL's float; j survives only in entry_idx.  The API
+//           exports restore the canonical (i, j) order inside a bucket.
 // NaN signatures (diagonal / failed pairs) are dropped: no finite query can reach the key PCL
 // files them under (A.3).
 #include <algorithm>
@@ -25,6 +30,17 @@ namespace {
 constexpr uint32_t INVALID_KEY = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t slice_of(uint32_t i, uint32_t slice_rows) { return i / slice_rows; }
+
+// sort key: (slice, packed feature key, phase cell of alpha_m)
+__device__ __forceinline__ uint32_t sort_key(const KeyParams &kp, const BinParams &bp, uint32_t i, uint32_t k, float alpha) {
+    uint32_t key = slice_of(i, kp.slice_rows) * kp.key_space + k;
+    if (bp.cells_log2) {
+        // alpha outside atan2f's range is rejected later (entries_kernel); any cell will do for it
+        const uint32_t cell = alpha == alpha ? phase_cell(bp, phase_of_fix(bp, alpha_to_fix(alpha))) : 0u;
+        key = (key << bp.cells_log2) | cell;
+    }
+    return key;
+}
 
 // per-component min/max of the quantised features and max f4 (table built from a feature cloud)
 __global__ void feature_range_kernel(const float *__restrict__ feats, size_t count, float angle_step,
@@ -67,7 +83,7 @@ __global__ void feature_range_kernel(const float *__restrict__ feats, size_t cou
 }
 
 // keys + alpha from a materialised feature cloud
-__global__ void keys_from_features_kernel(const float *__restrict__ feats, uint32_t n, KeyParams kp,
+__global__ void keys_from_features_kernel(const float *__restrict__ feats, uint32_t n, KeyParams kp, BinParams bp,
                                           uint32_t *__restrict__ keys, uint32_t *__restrict__ alpha_bits) {
     const size_t count = (size_t)n * n;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < count; p += (size_t)gridDim.x * blockDim.x) {
@@ -78,7 +94,7 @@ __global__ void keys_from_features_kernel(const float *__restrict__ feats, uint3
             int d[4];
             quantise(kp, f, d);
             uint32_t k;
-            if (pack_key(kp, d, k)) key = slice_of((uint32_t)(p / n), kp.slice_rows) * kp.key_space + k;
+            if (pack_key(kp, d, k)) key = sort_key(kp, bp, (uint32_t)(p / n), k, s[4]);
         }
         keys[p] = key;
         alpha_bits[p] = __float_as_uint(s[4]);
@@ -96,7 +112,7 @@ struct RefStage {
 
 __global__ void __launch_bounds__(FTJ)
 keys_from_cloud_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, uint32_t n, int feature_mode,
-                       KeyParams kp, uint32_t *__restrict__ keys, uint32_t *__restrict__ alpha_bits,
+                       KeyParams kp, BinParams bp, uint32_t *__restrict__ keys, uint32_t *__restrict__ alpha_bits,
                        int *__restrict__ max_f4_bits, int *__restrict__ out_of_range) {
     __shared__ RefStage ref[FTI];
     const uint32_t i0 = blockIdx.y * FTI;
@@ -130,7 +146,7 @@ keys_from_cloud_kernel(const float4 *__restrict__ pos, const float4 *__restrict_
                     int d[4];
                     quantise(kp, f, d);
                     uint32_t k;
-                    if (pack_key(kp, d, k)) key = slice_of(i, kp.slice_rows) * kp.key_space + k;
+                    if (pack_key(kp, d, k)) key = sort_key(kp, bp, i, k, alpha);
                     else if (f[0] == f[0] && f[1] == f[1] && f[2] == f[2]) *out_of_range = 1;
                     if (f[3] > 0.0f) mx = max(mx, __float_as_int(f[3]));
                 }
@@ -143,17 +159,34 @@ keys_from_cloud_kernel(const float4 *__restrict__ pos, const float4 *__restrict_
     if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(max_f4_bits, mx);
 }
 
-// offsets[k] = first sorted position whose key is >= k, for k in [0, total_keys]
+// offsets[k] = first sorted position whose sort key is >= k << shift, for k in [0, total_keys]
 __global__ void csr_offsets_kernel(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t total_keys,
-                                   uint32_t *__restrict__ offsets) {
+                                   uint32_t shift, uint32_t *__restrict__ offsets) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > total_keys) return;
+    const uint32_t want = k << shift;
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
         uint32_t mid = lo + ((hi - lo) >> 1);
-        if (sorted_keys[mid] < k) lo = mid + 1; else hi = mid;
+        if (sorted_keys[mid] < want) lo = mid + 1; else hi = mid;
     }
     offsets[k] = lo;
+}
+
+// sub_offsets[k'] for k' = key << shift | cell: the search is confined to the key's own bucket
+__global__ void csr_sub_offsets_kernel(const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ offsets,
+                                       uint32_t total_sub, uint32_t shift, uint32_t *__restrict__ sub_offsets) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > total_sub) return;
+    uint32_t lo = offsets[k >> shift];
+    if (k < total_sub) {
+        uint32_t hi = offsets[(k >> shift) + 1];
+        while (lo < hi) {
+            uint32_t mid = lo + ((hi - lo) >> 1);
+            if (sorted_keys[mid] < k) lo = mid + 1; else hi = mid;
+        }
+    }
+    sub_offsets[k] = lo;
 }
 
 __global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint32_t total_keys,
@@ -164,12 +197,13 @@ __global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
 }
 
-// entry = {accumulator word offset of model row i inside its slice, alpha_m in fixed point}; the float
-// alpha_m is kept beside it for the literal form of the guard-band votes and for the API exports.
+// per entry: the hot word (accumulator byte offset of model row i inside its slice, plus — phase-sorted
+// tables — the bin of alpha_m and the wrap field), alpha_m in fixed point for the per-entry path, and
+// the float alpha_m for the literal form of the guard-band votes and for the API exports.
 __global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const uint32_t *__restrict__ sorted_alpha,
-                               uint32_t n_entries, uint32_t n, uint32_t slice_rows, uint32_t row_stride,
-                               uint2 *__restrict__ entries, float *__restrict__ entry_alpha,
-                               int *__restrict__ bad_alpha) {
+                               uint32_t n_entries, uint32_t n, uint32_t slice_rows, BinParams bp,
+                               uint32_t *__restrict__ entry_w, uint32_t *__restrict__ entry_am,
+                               float *__restrict__ entry_alpha, int *__restrict__ bad_alpha) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_entries) return;
     uint32_t i = sorted_idx[p] / n;
@@ -177,7 +211,9 @@ __global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const ui
     const float alpha = __uint_as_float(sorted_alpha[p]);
     // atan2f range; anything else cannot come from PPFEstimation and would not wrap like PCL's floats
     if (!(alpha >= -3.14159274f && alpha <= 3.14159274f)) *bad_alpha = 1;
-    entries[p] = make_uint2(local * row_stride, alpha_to_fix(alpha));
+    const uint32_t a_fix = alpha_to_fix(alpha), row_bytes = local * bp.row_stride * 4u;
+    entry_w[p] = bp.bulk ? hot_word(bp, row_bytes, phase_of_fix(bp, a_fix)) : row_bytes;
+    entry_am[p] = a_fix;
     entry_alpha[p] = alpha;
 }
 
@@ -306,6 +342,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         kp.lo[3] = 0;
         kp.size[3] = (int)std::floor(diag / dist_step) + 2;
     }
+    t->bp = make_bin_params(angle_step, ctx->alpha_mode);
     {
         unsigned __int128 ks = 1;
         for (int k = 0; k < 4; ++k) ks *= (unsigned __int128)(uint32_t)kp.size[k];
@@ -316,6 +353,13 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
             return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "table build: discretisation too fine (packed key space exceeds 2^31)");
         }
         kp.key_space = (uint32_t)ks;
+        // phase cells multiply the sort-key space: halve them until it fits 31 bits and 1 Gi offsets
+        if (const char *e = getenv("B200PPF_PHASE_CELLS_LOG2")) {
+            int v = atoi(e);
+            if (v >= 0 && (uint32_t)v < t->bp.cells_log2) t->bp.cells_log2 = (uint32_t)v;
+        }
+        while (t->bp.cells_log2 > 0 && (total << t->bp.cells_log2) >= ((unsigned __int128)1 << 30)) --t->bp.cells_log2;
+        if (t->bp.cells_log2 == 0) t->bp.bulk = 0;
     }
     for (int k = 0; k < 4; ++k) {
         info.lo[k] = kp.lo[k];
@@ -323,9 +367,10 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     }
     info.key_space = kp.key_space;
     const uint32_t total_keys = kp.key_space * info.n_slices;
-    info.key_bits = (uint32_t)ceil_log2((uint64_t)total_keys + 1);
-
-    t->bp = make_bin_params(angle_step, ctx->alpha_mode);
+    const uint32_t cells_log2 = t->bp.cells_log2;
+    const uint32_t total_sub = total_keys << cells_log2;
+    info.key_bits = (uint32_t)ceil_log2((uint64_t)total_sub + 1);
+    info.phase_cells = 1u << cells_log2;
 
     // ---- keys ---------------------------------------------------------------------------------
     uint32_t *keys[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr}, *alp[2] = {nullptr, nullptr};
@@ -366,7 +411,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         int blocks = (int)std::min<size_t>((count + 255) / 256, (size_t)ctx->sm_count * 32);
         auto launch = [&]() -> int {
             PPF_LAUNCH(ctx, keys_from_features_kernel, blocks, 256, 0, reinterpret_cast<const float *>(feat->d),
-                       (uint32_t)n, kp, keys[0], alp[0]);
+                       (uint32_t)n, kp, t->bp, keys[0], alp[0]);
             return B200PPF_OK;
         };
         K2_TRY(launch());
@@ -374,7 +419,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         dim3 grid((unsigned)((n + FTJ - 1) / FTJ), (unsigned)((n + FTI - 1) / FTI));
         auto launch = [&]() -> int {
             PPF_LAUNCH(ctx, keys_from_cloud_kernel, grid, FTJ, 0, model->pos, model->nrm, (uint32_t)n,
-                       ctx->feature_mode, kp, keys[0], alp[0], d_range + 8, d_range + 9);
+                       ctx->feature_mode, kp, t->bp, keys[0], alp[0], d_range + 8, d_range + 9);
             return B200PPF_OK;
         };
         K2_TRY(launch());
@@ -390,10 +435,14 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
 
     // ---- CSR ------------------------------------------------------------------------------------
     K2_CUDA(cudaMalloc(&t->offsets, ((size_t)total_keys + 1) * sizeof(uint32_t)));
+    if (cells_log2) K2_CUDA(cudaMalloc(&t->sub_offsets, ((size_t)total_sub + 1) * sizeof(uint32_t)));
     {
         auto launch = [&]() -> int {
             PPF_LAUNCH(ctx, csr_offsets_kernel, (total_keys + 1 + 255) / 256, 256, 0, keys[s], (uint32_t)count,
-                       total_keys, t->offsets);
+                       total_keys, cells_log2, t->offsets);
+            if (cells_log2)
+                PPF_LAUNCH(ctx, csr_sub_offsets_kernel, (total_sub + 1 + 255) / 256, 256, 0, keys[s], t->offsets, total_sub,
+                           cells_log2, t->sub_offsets);
             return B200PPF_OK;
         };
         K2_TRY(launch());
@@ -414,7 +463,8 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         memcpy(&mx, &bits, sizeof(float));
         info.max_dist = bits < 0 ? -1.0f : mx;  // PCL: max_dist_ starts at -1
     }
-    K2_CUDA(cudaMalloc(&t->entries, std::max<size_t>(1, n_entries) * sizeof(uint2)));
+    K2_CUDA(cudaMalloc(&t->entry_w, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
+    K2_CUDA(cudaMalloc(&t->entry_am, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
     K2_CUDA(cudaMalloc(&t->entry_idx, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
     K2_CUDA(cudaMalloc(&t->entry_alpha, std::max<size_t>(1, n_entries) * sizeof(float)));
     unsigned long long *d_cnt = nullptr;
@@ -424,7 +474,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         auto launch = [&]() -> int {
             if (n_entries) {
                 PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
-                           info.slice_rows, t->bp.row_stride, t->entries, t->entry_alpha, d_range + 10);
+                           info.slice_rows, t->bp, t->entry_w, t->entry_am, t->entry_alpha, d_range + 10);
                 PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
                                               cudaMemcpyDeviceToDevice, ctx->stream));
             }
@@ -474,10 +524,11 @@ int k2_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int32_t *d4, ui
         total += len;
         size_t take = std::min<size_t>(len, cap - std::min(cap, written));
         if (take) {
-            tmp.resize(take);
-            PPF_CUDA(ctx, cudaMemcpyAsync(tmp.data(), t->entry_idx + off[0], take * sizeof(uint32_t),
+            tmp.resize(len);  // the whole bucket: its canonical prefix is only known once it is sorted
+            PPF_CUDA(ctx, cudaMemcpyAsync(tmp.data(), t->entry_idx + off[0], (size_t)len * sizeof(uint32_t),
                                           cudaMemcpyDeviceToHost, ctx->stream));
             PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            std::sort(tmp.begin(), tmp.end());  // phase-sorted buckets -> canonical (i, j) order
             for (size_t e = 0; e < take; ++e) {
                 pairs[2 * (written + e)] = tmp[e] / n;
                 pairs[2 * (written + e) + 1] = tmp[e] % n;

@@ -6,7 +6,7 @@
 //   pair feature -> bucket -> for every (i, alpha_m) in the bucket acc[i][bin(alpha_m - alpha_s)]++;
 //   first maximum of acc (lowest flat index wins ties) -> pose = T_sg^-1 * Rx(theta) * T_mg.
 //
-// One CTA per (reference point, accumulator slice).  The accumulator slice — up to ~1800 model
+// One CTA per (reference point, accumulator slice).  The accumulator slice — up to ~1600 model
 // rows x n_alpha 32-bit counters — lives in shared memory for the CTA's whole life, votes are
 // shared-memory reductions (red.shared.add), the peak is a warp-shuffle argmax, and slices merge
 // through one 64-bit atomicMax per CTA on a packed (votes, ~flat index) word, which reproduces
@@ -14,11 +14,16 @@
 //   A  sweep  the 27-cell neighbourhood of the reference point in the cell-sorted scene
 //             (scene_grid.cu) is 9 contiguous runs of float4 positions; the radius predicate
 //             survivors are compacted into a shared candidate queue (one warp-aggregated atomic);
-//   B  pair   one thread per candidate: pair feature, key, CSR bucket bounds, alpha_s -> work item;
-//   C  vote   warps pull work items and walk the bucket 4 x 32 entries at a time: four coalesced
-//             8-byte gathers {row offset, alpha_m} in flight per lane, one shared reduction per vote.
-// Roofline: 8 B gathered + 1 shared atomic per vote, 8 B of CSR offsets per
-// in-radius pair; instruction issue and shared-atomic throughput bind, not HBM.
+//   B  pair   one thread per candidate: pair feature, key, alpha_s -> up to three work items.
+//             Buckets are ordered by the phase cell of alpha_m (k2_table.cu): the cells below the
+//             scene pair's phase and the cells above it are two "shift" items whose every vote lands
+//             at (entry's hot word - one constant); the scene phase's own cell is a "per-entry" item;
+//   C  vote   warps pull work items.  Shift items: 4 x 32 hot words in flight per lane, a vote is
+//             load / subtract / add / max / mask / red.shared (ppf_math.cuh "constant-shift voting").
+//             Per-entry items: fixed-point alpha binning with guard bands, the literal
+//             double-precision form inside the bands.
+// Roofline: 4 B (shift) or 8 B (per-entry) gathered + 1 shared atomic per vote,
+// 16 B of CSR offsets per in-radius pair; shared-atomic / L1 throughput binds, not HBM.
 #include <algorithm>
 #include <cmath>
 
@@ -44,17 +49,28 @@ constexpr int VOTE_WARPS = VOTE_THREADS / 32;
 #endif
 constexpr int CAND_CAP = B200PPF_CAND_CAP;  // in-radius candidates buffered between flushes
 constexpr int ITEM_CAP = B200PPF_ITEM_CAP;  // candidates turned into work items per B/C round (<= VOTE_THREADS)
+constexpr int ITEM_SLOTS = ITEM_CAP;
 static_assert(ITEM_CAP <= VOTE_THREADS, "one thread per candidate in phase B");
-constexpr int VOTE_UNROLL = 4;
+#ifndef B200PPF_VOTE_UNROLL
+#define B200PPF_VOTE_UNROLL 4
+#endif
+constexpr int VOTE_UNROLL = B200PPF_VOTE_UNROLL;
 static_assert(CAND_CAP >= 2 * VOTE_THREADS, "flush threshold must leave one sweep iteration of room");
 
-struct WorkItem {
+// One in-radius scene pair with a non-empty bucket.  The bucket's entries [off, off + len) are walked in
+// steps of 32: steps below k_below lie wholly under the scene pair's phase (shift constant c_below),
+// steps from k_above on wholly over it (c_below minus one bin), the steps in between — the scene
+// phase's own cell rounded out to step bounds, or the whole bucket — take the per-entry path.
+struct __align__(16) WorkItem {
     uint32_t off, len;
-    float alpha_s;  // PCL's float (literal form of the guard-band votes)
-    uint32_t c_s;   // alpha_to_fix(alpha_s) - 2^31 (fixed-point hot loop)
+    uint32_t k_below, k_above;  // multiples of 32; k_above may exceed len
+    uint32_t c_below;           // constant subtracted from the hot words below the scene phase (shift q + 1)
+    uint32_t c_s;               // per-entry path: alpha_to_fix(alpha_s) - 2^31
+    float alpha_s;              // per-entry path: PCL's float (literal form of the guard-band votes)
+    uint32_t pad;
 };
 
-constexpr size_t QUEUE_BYTES = CAND_CAP * sizeof(uint32_t) + ITEM_CAP * sizeof(WorkItem);
+constexpr size_t QUEUE_BYTES = CAND_CAP * sizeof(uint32_t) + ITEM_SLOTS * sizeof(WorkItem);
 constexpr size_t STATIC_RESERVE = 2048;  // static shared + the 1 KB the system reserves per CTA
 
 struct VoteArgs {
@@ -65,8 +81,9 @@ struct VoteArgs {
     GridParams gp;
     uint32_t n_s;
     uint32_t ref_first, ref_step, ref_count;
-    const uint32_t *offsets;
-    const uint2 *entries;
+    const uint32_t *sub_offsets;  // phase-cell bounds (bucket bounds when the table has no phase cells)
+    const uint32_t *entry_w;
+    const uint32_t *entry_am;
     const float *entry_alpha;
     KeyParams kp;
     BinParams bp;
@@ -87,14 +104,24 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 __device__ __forceinline__ void red_shared_inc(uint32_t addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
+// the same, predicated on k < len (the partial last step of a shift item)
+__device__ __forceinline__ void red_shared_inc_if_lt(uint32_t addr, uint32_t k, uint32_t len) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"(k), "r"(len)
+                 : "memory");
+}
 
-// One vote of the hot loop (alpha mode A), in fixed point (ppf_math.cuh, alpha_bin_fixed):
+// One vote of a shift item (ppf_math.cuh "constant-shift voting"): c0 = item constant, c1 = c0 - wrap_add
+__device__ __forceinline__ uint32_t shift_address(uint32_t w, uint32_t c0, uint32_t c1, uint32_t lowmask) {
+    const uint32_t t = w - c0, t2 = w - c1;
+    return max(t, t2) & lowmask;
+}
+
+// One vote of the per-entry path (alpha mode A), in fixed point (ppf_math.cuh, alpha_bin_fixed):
 //   X = A_m - C_s  (wraps like the angle),  hi = mulhi(X, T_fix) = bin.position,  (bin, frac) = hi * 2^(32-s).
-// The increment is unconditional — ATOMS cannot be predicated and a select is cheaper than a
-// divergent branch — but when frac lies in the guard band around a bin edge (or X in the band
-// around the +-pi seam), or the lane is past the end of the bucket, it is steered to a scratch
-// word; a guard-band hit returns true and the caller settles that entry with the literal
-// double-precision form.  ~10 integer instructions per vote, nothing on the XU pipe.
+// The increment is unconditional — a select is cheaper than a divergent branch — but when frac lies
+// in the guard band around a bin edge (or X in the band around the +-pi seam), or the lane is past
+// the end of the bucket, it is steered to a scratch word; a guard-band hit returns true and the
+// caller settles that entry with the literal double-precision form.
 template <bool SEAM>
 __device__ __forceinline__ bool vote_fixed(const BinParams &bp, uint32_t acc_addr, uint32_t scratch_addr, uint2 en,
                                            uint32_t c_s, bool valid) {
@@ -119,7 +146,7 @@ __device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_add
     else red_shared_inc(acc_addr + ((rowoff + bin) << 2));
 }
 
-template <int MODE, bool SEAM>
+template <int MODE, bool SEAM, bool BULK>
 __global__ void __launch_bounds__(VOTE_THREADS, B200PPF_VOTE_MINBLOCKS)
 ppf_vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,9 +162,10 @@ ppf_vote_kernel(const VoteArgs a) {
     const uint32_t rows = min(a.kp.slice_rows, a.n_model - slice_base);
     const uint32_t stride = a.bp.row_stride;             // n_alpha + 1 words per model row
     const uint32_t acc_len = rows * stride;
-    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *cand = acc + (size_t)a.kp.slice_rows * stride;
+    // queues first: the accumulator's shared address must be >= 4 * N_T (shift items subtract up to that)
+    uint32_t *cand = reinterpret_cast<uint32_t *>(smem_raw);
     WorkItem *items = reinterpret_cast<WorkItem *>(cand + CAND_CAP);
+    uint32_t *acc = reinterpret_cast<uint32_t *>(items + ITEM_SLOTS);
     const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
     const uint32_t scratch_addr = (uint32_t)__cvta_generic_to_shared(&s_scratch);
 
@@ -169,7 +197,9 @@ ppf_vote_kernel(const VoteArgs a) {
     for (uint32_t k = tid; k < acc_len; k += VOTE_THREADS) acc[k] = 0;
     __syncthreads();
 
-    const uint32_t *slice_offsets = a.offsets + (size_t)slice * a.kp.key_space;
+    const uint32_t lf = a.bp.cells_log2;
+    const uint32_t *slice_offsets = a.sub_offsets + (((size_t)slice * a.kp.key_space) << lf);
+    const uint32_t lowmask = (1u << a.bp.low_bits) - 1u;
     uint32_t st_examined = 0, st_in_radius = 0, st_nonempty = 0, st_votes = 0, st_skipped = 0;
 
     // phases B + C over the buffered candidates
@@ -178,11 +208,9 @@ ppf_vote_kernel(const VoteArgs a) {
         for (uint32_t c0 = 0; c0 < ncand; c0 += ITEM_CAP) {
             // ---- B: pair features -> work items -------------------------------------------------
             const uint32_t c = c0 + tid;
-            bool push = false;
-            WorkItem it;
-            it.off = it.len = 0;
-            it.alpha_s = 0.0f;
-            it.c_s = 0;
+            // the bucket [o0, oF) splits at the scene phase's cell [oa, ob): below it, inside it, above it
+            uint32_t o0 = 0, oa = 0, ob = 0, oF = 0, q = 0, c_s = 0;
+            float alpha_s = 0.0f;
             if (tid < ITEM_CAP && c < ncand) {
                 const uint32_t s = cand[c];
                 const float4 p4 = __ldg(a.gpos + s), n4 = __ldg(a.gnrm + s);
@@ -193,24 +221,44 @@ ppf_vote_kernel(const VoteArgs a) {
                     quantise(a.kp, f, d);
                     uint32_t key;
                     if (pack_key(a.kp, d, key)) {
-                        const uint32_t o0 = __ldg(slice_offsets + key), o1 = __ldg(slice_offsets + key + 1);
-                        if (o1 > o0) {
-                            it.off = o0;
-                            it.len = o1 - o0;
-                            it.alpha_s = planar_alpha(s_sg, v3_of(p4));
-                            it.c_s = alpha_to_fix(it.alpha_s) - 0x80000000u;
-                            push = true;
+                        const uint32_t *so = slice_offsets + ((size_t)key << lf);
+                        o0 = __ldg(so);
+                        oF = __ldg(so + (1u << lf));
+                        oa = ob = oF;  // empty bucket: no item
+                        if (oF > o0) {
+                            alpha_s = planar_alpha(s_sg, v3_of(p4));
+                            c_s = alpha_to_fix(alpha_s) - 0x80000000u;
                             ++st_nonempty;
+                            uint32_t cell;
+                            if (BULK && phase_split(a.bp, c_s, q, cell)) {
+                                oa = __ldg(so + cell);
+                                ob = __ldg(so + cell + 1);
+                            } else {  // the whole bucket takes the per-entry path
+                                oa = o0;
+                                ob = oF;
+                            }
                         }
                     }
                 }
             }
+            const bool push = oF > o0;
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, push);
             if (m) {
                 uint32_t base = 0;
                 if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&s_nitems, __popc(m));
                 base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-                if (push) items[base + __popc(m & ((1u << lane) - 1u))] = it;
+                if (push) {
+                    WorkItem it;
+                    it.off = o0;
+                    it.len = oF - o0;
+                    it.k_below = (oa - o0) & ~31u;
+                    it.k_above = (ob - o0 + 31u) & ~31u;
+                    it.c_below = ((q + 1u) << a.bp.low_bits) + 4u * (q + 1u) - acc_addr;
+                    it.c_s = c_s;
+                    it.alpha_s = alpha_s;
+                    it.pad = 0;
+                    items[base + __popc(m & ((1u << lane) - 1u))] = it;
+                }
             }
             __syncthreads();
             // ---- C: votes ---------------------------------------------------------------------
@@ -221,44 +269,68 @@ ppf_vote_kernel(const VoteArgs a) {
                 w = __shfl_sync(0xFFFFFFFFu, w, 0);
                 if (w >= nitems) break;
                 const WorkItem wi = items[w];
-                const uint2 *e = a.entries + wi.off;
-                if (lane == 0) st_votes += wi.len;
-                if (MODE == ALPHA_MODE_A) {
-                    // 4 x 32 entries per step: four 8-byte gathers in flight per lane, four branch-free
-                    // votes.  The last, partial step clamps its loads to the final entry and votes into
-                    // the scratch word from the lanes past the end.
-                    const uint32_t last = wi.len - 1;
-                    uint32_t k0 = lane;
-                    for (; k0 + 32 * (VOTE_UNROLL - 1) <= last; k0 += 32 * VOTE_UNROLL) {
-                        uint2 en[VOTE_UNROLL];
+                const uint32_t len = wi.len;
+                const uint32_t *wp = a.entry_w + wi.off;
+                if (lane == 0) st_votes += len;
+                // shift steps [kb, ke): every vote is hot word - constant (wrapped through the max)
+                auto shift_range = [&](uint32_t kb, uint32_t ke, uint32_t c0v) {
+                    const uint32_t c1v = c0v - a.bp.wrap_add;
+                    uint32_t k0 = kb + lane;
+                    for (; k0 - lane + 32 * VOTE_UNROLL <= ke; k0 += 32 * VOTE_UNROLL) {  // warp-uniform: a full batch
+                        uint32_t hw[VOTE_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u) en[u] = __ldg(e + k0 + u * 32);
-                        bool risky[VOTE_UNROLL];
+                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(wp + k0 + u * 32);
+#pragma unroll
+                        for (int u = 0; u < VOTE_UNROLL; ++u) red_shared_inc(shift_address(hw[u], c0v, c1v, lowmask));
+                    }
+                    if (k0 - lane < ke) {  // warp-uniform: a partial batch remains; loads clamp, votes are predicated
+                        uint32_t hw[VOTE_UNROLL];
+#pragma unroll
+                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(wp + min(k0 + u * 32, ke - 1));
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u)
-                            risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s, true);
-                        bool any = false;
+                            red_shared_inc_if_lt(shift_address(hw[u], c0v, c1v, lowmask), k0 + u * 32, ke);
+                    }
+                };
+                const uint32_t k_mid_end = min(wi.k_above, len);
+                if (BULK) {
+                    if (wi.k_below) shift_range(0u, wi.k_below, wi.c_below);
+                    if (wi.k_above < len) shift_range(wi.k_above, len, wi.c_below - ((1u << a.bp.low_bits) + 4u));
+                }
+                if (wi.k_below < k_mid_end) {
+                    if (MODE == ALPHA_MODE_A) {
+                        // per-entry steps: 4 x 32 entries per batch, branch-free votes; loads past the end clamp
+                        // to the final entry and vote into the scratch word
+                        const uint32_t last = k_mid_end - 1;
+                        const uint32_t *ap = a.entry_am + wi.off;
+                        for (uint32_t k0 = wi.k_below + lane; k0 - lane <= last; k0 += 32 * VOTE_UNROLL) {  // warp-uniform
+                            uint2 en[VOTE_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u) any |= risky[u];
-                        if (any) {
+                            for (int u = 0; u < VOTE_UNROLL; ++u) {
+                                const uint32_t kk = min(k0 + u * 32, last);
+                                en[u] = make_uint2(__ldg(wp + kk), __ldg(ap + kk));
+                            }
+                            bool risky[VOTE_UNROLL];
+                            bool any = false;
 #pragma unroll
-                            for (int u = 0; u < VOTE_UNROLL; ++u)
-                                if (risky[u])
-                                    vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
-                                                     wi.alpha_s, st_skipped);
+                            for (int u = 0; u < VOTE_UNROLL; ++u) {
+                                en[u].x = hot_word_row_words(a.bp, en[u].x);
+                                risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s, k0 + u * 32 <= last);
+                                any |= risky[u];
+                            }
+                            if (any) {
+#pragma unroll
+                                for (int u = 0; u < VOTE_UNROLL; ++u)
+                                    if (risky[u])
+                                        vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
+                                                         wi.alpha_s, st_skipped);
+                            }
                         }
+                    } else {
+                        for (uint32_t k = wi.k_below + lane; k < k_mid_end; k += 32)
+                            vote_exact<MODE>(a.bp, acc_addr, hot_word_row_words(a.bp, __ldg(wp + k)),
+                                             __ldg(a.entry_alpha + wi.off + k), wi.alpha_s, st_skipped);
                     }
-                    // remainder (< 128 entries): one entry per lane per step; lanes past the end re-read the
-                    // last entry and vote into the scratch word
-                    for (; k0 - lane <= last; k0 += 32) {  // warp-uniform condition
-                        const uint2 en = __ldg(e + min(k0, last));
-                        if (vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en, wi.c_s, k0 <= last))
-                            vote_exact<MODE>(a.bp, acc_addr, en.x, __ldg(a.entry_alpha + wi.off + k0), wi.alpha_s, st_skipped);
-                    }
-                } else {
-                    for (uint32_t k = lane; k < wi.len; k += 32)
-                        vote_exact<MODE>(a.bp, acc_addr, __ldg(e + k).x, __ldg(a.entry_alpha + wi.off + k), wi.alpha_s,
-                                         st_skipped);
                 }
             }
             __syncthreads();
@@ -427,7 +499,7 @@ __global__ void debug_alpha_bins_kernel(BinParams bp, const float *__restrict__ 
                                         uint32_t n, uint32_t *__restrict__ fast, uint32_t *__restrict__ exact) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    fast[p] = alpha_bin_hot(bp, am[p], as[p]);
+    fast[p] = alpha_bin_phase(bp, am[p], as[p]);
     exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, am[p], as[p]);
 }
 
@@ -465,8 +537,9 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     a.ref_first = (uint32_t)ref_first;
     a.ref_step = (uint32_t)ref_step;
     a.ref_count = (uint32_t)ref_count;
-    a.offsets = t->offsets;
-    a.entries = t->entries;
+    a.sub_offsets = t->sub_offsets ? t->sub_offsets : t->offsets;
+    a.entry_w = t->entry_w;
+    a.entry_am = t->entry_am;
     a.entry_alpha = t->entry_alpha;
     a.kp = t->kp;
     a.bp = t->bp;
@@ -481,15 +554,16 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     const size_t smem = vote_smem_bytes(t);
     dim3 grid_dim((unsigned)ref_count, t->info.n_slices);
     cudaEventRecord(ctx->ev_vote[1], ctx->stream);  // grid build ends, voting starts
-#define LAUNCH_VOTE(M, S)                                                                                          \
+#define LAUNCH_VOTE(M, S, B)                                                                                       \
     do {                                                                                                            \
-        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<M, S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                            (int)smem));                                                             \
-        PPF_LAUNCH(ctx, (ppf_vote_kernel<M, S>), grid_dim, VOTE_THREADS, smem, a);                                  \
+        PPF_LAUNCH(ctx, (ppf_vote_kernel<M, S, B>), grid_dim, VOTE_THREADS, smem, a);                               \
     } while (0)
-    if (ctx->alpha_mode == ALPHA_MODE_B) LAUNCH_VOTE(ALPHA_MODE_B, false);
-    else if (a.bp.seam_guard) LAUNCH_VOTE(ALPHA_MODE_A, true);
-    else LAUNCH_VOTE(ALPHA_MODE_A, false);
+    if (ctx->alpha_mode == ALPHA_MODE_B) LAUNCH_VOTE(ALPHA_MODE_B, false, false);
+    else if (a.bp.bulk) LAUNCH_VOTE(ALPHA_MODE_A, false, true);  // an integer T has no separate seam band
+    else if (a.bp.seam_guard) LAUNCH_VOTE(ALPHA_MODE_A, true, false);
+    else LAUNCH_VOTE(ALPHA_MODE_A, false, false);
 #undef LAUNCH_VOTE
     cudaEventRecord(ctx->ev_vote[2], ctx->stream);
     scene_grid_free(ctx, &grid);
@@ -549,6 +623,29 @@ BinParams make_bin_params(float angle_step, int alpha_mode) {
     const double fracT = T - floor(T);
     const bool covered = fracT < guard_bins || fracT > 1.0 - guard_bins;
     bp.seam_guard = covered ? 0u : (uint32_t)(guard_rad / (2.0 * M_PI) * 4294967296.0);
+    // phase-sorted buckets / constant-shift voting (ppf_math.cuh): T must be an integer up to the guard band
+    bp.bulk = 0;
+    bp.n_turn = (uint32_t)llrint(T);
+    bp.cells_log2 = 0;
+    bp.low_bits = 31;
+    bp.field_bias = 0;
+    bp.wrap_add = 0;
+    bp.phase_guard = 0;
+    const double off_int = fabs(T - (double)bp.n_turn);
+    int fbits = 1;
+    while ((1u << fbits) < 2u * bp.n_turn) ++fbits;
+    if (alpha_mode == ALPHA_MODE_A && bp.n_turn >= 2 && fbits <= 13 && off_int < 0.25 * guard_bins) {
+        const double unit = (double)(1u << bp.fix_shift);
+        bp.bulk = 1;
+        bp.cells_log2 = 4;
+        bp.low_bits = 32u - (uint32_t)fbits;
+        bp.field_bias = (1u << fbits) - bp.n_turn;
+        bp.wrap_add = (bp.n_turn << bp.low_bits) + 4u * bp.n_turn;
+        bp.phase_guard = (uint32_t)ceil(guard_bins * unit) + (uint32_t)ceil(off_int * unit) + 16u;
+        // the guard must stay a small part of a phase cell
+        while (bp.cells_log2 > 0 && 8ull * bp.phase_guard > (1ull << (bp.fix_shift - bp.cells_log2))) --bp.cells_log2;
+        if (bp.cells_log2 == 0) bp.bulk = 0;
+    }
     return bp;
 }
 
@@ -557,7 +654,7 @@ int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, cons
     const BinParams bp = make_bin_params(angle_step, alpha_mode);
     if (!ctx) {  // host build of the same inline functions
         for (size_t p = 0; p < n; ++p) {
-            fast[p] = alpha_bin_hot(bp, alpha_m[p], alpha_s[p]);
+            fast[p] = alpha_bin_phase(bp, alpha_m[p], alpha_s[p]);
             exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, alpha_m[p], alpha_s[p]);
         }
         return B200PPF_OK;

@@ -68,8 +68,10 @@ struct b200ppf_table {
     b200ppf_table_info info{};
     b200ppf::KeyParams kp{};
     b200ppf::BinParams bp{};
-    uint32_t *offsets = nullptr;  // [n_slices*key_space + 1]
-    uint2 *entries = nullptr;     // {accumulator word offset of row (i - slice_base), alpha_m as fixed-point turns} per entry
+    uint32_t *offsets = nullptr;      // [n_slices*key_space + 1] bucket bounds
+    uint32_t *sub_offsets = nullptr;  // [(n_slices*key_space << cells_log2) + 1] phase-cell bounds (phase-sorted tables)
+    uint32_t *entry_w = nullptr;      // hot word per entry (ppf_math.cuh hot_word; plain row byte offset otherwise)
+    uint32_t *entry_am = nullptr;     // alpha_m as fixed-point turns (per-entry path)
     float *entry_alpha = nullptr;  // alpha_m as PCL's float (guard-band votes, alpha_m_ export)
     uint32_t *entry_idx = nullptr;  // i*n + j per entry (API queries, alpha_m_ export)
     int feature_mode = 0;

@@ -198,7 +198,54 @@ struct BinParams {
     uint32_t frac_mul;     // 2^(32 - fix_shift): a second multiply splits that word into (bin, position << (32-fix_shift))
     uint32_t fix_guard;    // guard band around bin edges, in 2^-32 bins (>= 10x the worst disagreement with PCL's floats)
     uint32_t seam_guard;   // guard band around the +-pi seam in 2^-32 turns; 0 when the bin guard already covers it
+    // phase-sorted buckets (alpha mode A, T within the guard of an integer N_T): see "constant-shift voting" below
+    uint32_t bulk;         // 1 when the table carries phase cells and hot words
+    uint32_t n_turn;       // N_T = round(T): alpha positions per turn
+    uint32_t cells_log2;   // log2 of the phase cells per bucket (0: buckets are not subdivided)
+    uint32_t low_bits;     // a hot word = wrap field (32 - low_bits bits) | byte offset of (row, B_e) (low_bits bits)
+    uint32_t field_bias;   // 2^field_bits - N_T: the field holds B_e + field_bias
+    uint32_t wrap_add;     // (N_T << low_bits) + 4 * N_T
+    uint32_t phase_guard;  // guard band around the scene phase, in 2^-fix_shift bins
 };
+
+// ---- constant-shift voting ---------------------------------------------------------------------
+// With u_e = (alpha_m + pi) / step = B_e + f_e (integer bin, phase in [0,1)) and the scene pair's
+// c = (alpha_s / step) mod T = q + phi, PCL's bin is floor((u_e - c) mod T).  When T is an integer
+// N_T (up to the guard band) this is (B_e - q - [f_e < phi]) mod N_T: inside a bucket whose entries
+// are ordered by phase cell, every entry of the cells below phi's cell shifts by q + 1, every entry
+// of the cells above it by q, and only phi's own cell needs the per-entry arithmetic.  A hot word
+// packs the wrap test and the accumulator address into one 32-bit value so that a vote of those two
+// ranges is: load, subtract the per-range constant, add, max, mask, shared-memory reduction.
+//   word  = (B_e + 2^b - N_T) << low_bits | (row byte offset + 4 * B_e)
+//   const = q' << low_bits | (4 * q' - accumulator base)          (q' = q or q + 1)
+//   t = word - const ; address = max(t, t + wrap_add) & (2^low_bits - 1)
+// 2^b = smallest power of two >= 2 * N_T: the field of t is >= 2^b - N_T exactly when B_e >= q'
+// (no wrap), and adding N_T overflows the field exactly then, so the unsigned max picks the wrapped
+// sum only when B_e < q'.
+__host__ __device__ __forceinline__ uint32_t phase_of_fix(const BinParams &bp, uint32_t a_fix) {
+    return (uint32_t)(((unsigned long long)a_fix * bp.fix_mul) >> 32);  // B . f with fix_shift fractional bits
+}
+__host__ __device__ __forceinline__ uint32_t phase_cell(const BinParams &bp, uint32_t u) {
+    return (u & ((1u << bp.fix_shift) - 1u)) >> (bp.fix_shift - bp.cells_log2);
+}
+__host__ __device__ __forceinline__ uint32_t hot_word(const BinParams &bp, uint32_t row_bytes, uint32_t u) {
+    uint32_t B = u >> bp.fix_shift;
+    if (B >= bp.n_turn) B -= bp.n_turn;  // T a hair above N_T: the sliver is the start of the turn
+    return ((B + bp.field_bias) << bp.low_bits) | (row_bytes + 4u * B);
+}
+__host__ __device__ __forceinline__ uint32_t hot_word_row_words(const BinParams &bp, uint32_t w) {
+    return ((w & ((1u << bp.low_bits) - 1u)) >> 2) - ((w >> bp.low_bits) - bp.field_bias);
+}
+// scene side: returns false when the whole bucket must take the per-entry path
+__host__ __device__ __forceinline__ bool phase_split(const BinParams &bp, uint32_t c_s, uint32_t &q, uint32_t &cell) {
+    const uint32_t c = phase_of_fix(bp, c_s);
+    q = c >> bp.fix_shift;
+    const uint32_t phi = c & ((1u << bp.fix_shift) - 1u);
+    const uint32_t cellw = 1u << (bp.fix_shift - bp.cells_log2);
+    cell = phi >> (bp.fix_shift - bp.cells_log2);
+    const uint32_t in = phi & (cellw - 1u);
+    return q < bp.n_turn && in >= bp.phase_guard && in < cellw - bp.phase_guard;
+}
 
 // ---- fixed-point alpha arithmetic -------------------------------------------------------------
 // An angle a in [-pi, pi] is held as A = round((a + pi) / (2*pi) * 2^32) (mod 2^32), one "turn" per
@@ -266,6 +313,28 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_hot(const BinParams &bp, 
         return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
     const uint32_t b = alpha_bin_fixed(bp, alpha_to_fix(alpha_m), alpha_to_fix(alpha_s) - 0x80000000u);
     if (b == 0xFFFFFFFFu) return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
+    return b >= bp.n_alpha ? bp.n_alpha - 1 : b;
+}
+
+// what the voting kernel computes for one (entry, scene pair) of a phase-sorted table: the
+// constant-shift form outside the scene phase's cell, the per-entry form inside it
+__host__ __device__ __forceinline__ uint32_t alpha_bin_phase(const BinParams &bp, float alpha_m, float alpha_s) {
+    if (!bp.bulk || bp.mode == ALPHA_MODE_B) return alpha_bin_hot(bp, alpha_m, alpha_s);
+    if (alpha_m != alpha_m || alpha_s != alpha_s) return 0xFFFFFFFFu;
+    if (!(fabsf(alpha_m) <= 3.14159274f && fabsf(alpha_s) <= 3.14159274f)) return alpha_bin_hot(bp, alpha_m, alpha_s);
+    const uint32_t u = phase_of_fix(bp, alpha_to_fix(alpha_m));
+    uint32_t q, cell;
+    if (!phase_split(bp, alpha_to_fix(alpha_s) - 0x80000000u, q, cell)) return alpha_bin_hot(bp, alpha_m, alpha_s);
+    const uint32_t ce = phase_cell(bp, u);
+    if (ce == cell) return alpha_bin_hot(bp, alpha_m, alpha_s);
+    // the kernel's own integer path, address arithmetic included (accumulator base 4 * N_T, row 0)
+    const uint32_t w = hot_word(bp, 0u, u);
+    const uint32_t qp = q + (ce < cell ? 1u : 0u);
+    const uint32_t base = 4u * bp.n_turn;
+    const uint32_t cst = (qp << bp.low_bits) + 4u * qp - base;
+    const uint32_t t = w - cst, t2 = t + bp.wrap_add;
+    const uint32_t addr = (t > t2 ? t : t2) & ((1u << bp.low_bits) - 1u);
+    const uint32_t b = (addr - base) >> 2;
     return b >= bp.n_alpha ? bp.n_alpha - 1 : b;
 }
 
