@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <unordered_map>
@@ -195,12 +196,25 @@ struct Key {
         return d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && d[3] == o.d[3];
     }
 };
-struct KeyHash { /* PCL >= 1.9: h1 ^ (h2<<1) ^ (h3<<2) ^ (h4<<3) */
+struct KeyHash {
+    /* PCL >= 1.9: h1 ^ (h2<<1) ^ (h3<<2) ^ (h4<<3).  That function takes only a few hundred distinct
+     * values, so every insert and lookup walks a chain of thousands of unrelated keys and the table
+     * build is quadratic (minutes at 2 000 model points, hours at 10 000).  Above
+     * ORACLE_PCL_HASH_MAX_POINTS model points the oracle therefore mixes the four integers properly.
+     * Only speed and iteration order change: bucket contents (what every consumer reads, sorted or
+     * order-independent) are those of PCL's container. */
+    bool mixed = false;
     size_t operator()(const Key &k) const {
         std::hash<int> h;
-        return h(k.d[0]) ^ (h(k.d[1]) << 1) ^ (h(k.d[2]) << 2) ^ (h(k.d[3]) << 3);
+        if (!mixed) return h(k.d[0]) ^ (h(k.d[1]) << 1) ^ (h(k.d[2]) << 2) ^ (h(k.d[3]) << 3);
+        uint64_t x = (uint64_t)(uint32_t)k.d[0] * 0x9E3779B97F4A7C15ull;
+        x = (x ^ (uint32_t)k.d[1]) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (uint32_t)k.d[2]) * 0x94D049BB133111EBull;
+        x = (x ^ (uint32_t)k.d[3]) * 0x9E3779B97F4A7C15ull;
+        return (size_t)(x ^ (x >> 31));
     }
 };
+constexpr size_t ORACLE_PCL_HASH_MAX_POINTS = 1024;
 
 }  // namespace
 
@@ -524,8 +538,13 @@ oracle_hashmap *oracle_hashmap_create(float angle_step, float dist_step) {
 void oracle_hashmap_destroy(oracle_hashmap *hm) { delete hm; }
 
 void oracle_hashmap_set_features(oracle_hashmap *hm, const float *feats, size_t count) {
-    hm->map.clear();
     unsigned int n = static_cast<unsigned int>(std::sqrt(static_cast<float>(count)));
+    {
+        KeyHash kh;
+        kh.mixed = n > ORACLE_PCL_HASH_MAX_POINTS && !std::getenv("ORACLE_FORCE_PCL_HASH");
+        hm->map = decltype(hm->map)(0, kh);
+        if (kh.mixed) hm->map.reserve(count);
+    }
     hm->n = n;
     hm->max_dist = -1.0f;
     hm->alpha_m.assign(n, std::vector<float>());

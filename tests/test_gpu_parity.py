@@ -296,6 +296,47 @@ def test_k3_sharding_invariance(ctx, dev_bottle, dev_crop, table_fused):
     assert strided.tobytes() == full[3::7].tobytes()
 
 
+def test_k3_large_model_two_slices(ctx, oracle, bottle_5mm, scene_crop, dev_crop):
+    """2 009-point bottle: two accumulator slices of ~1 000 rows, the 1024-thread launch shape, long
+    buckets (the constant-shift ranges dominate).  Accumulators bit-exact, peaks first-maximum."""
+    feats = oracle.ppf_estimation(bottle_5mm)
+    hm = oracle.HashMap(ANGLE_STEP, DIST_STEP).set_input_feature_cloud(feats)
+    t = ctx.table_build(ctx.features_upload(feats), ANGLE_STEP, DIST_STEP)
+    assert t.info.n_slices == 2 and t.info.phase_cells == 16 and t.info.n_entries == hm.num_entries
+    for s_r in (0, 433, 933):
+        inr, d, a = ctx.vote_debug_pairs(t, dev_crop, s_r)
+        acc = ctx.vote_debug_accumulator(t, dev_crop, s_r)
+        ref, votes = hm.vote_accumulate_from_pairs(bottle_5mm.shape[0], d[inr > 0], a[inr > 0])
+        assert votes == int(acc.sum())
+        assert np.array_equal(acc, ref), f"accumulator differs for reference {s_r}"
+    dm = ctx.upload_cloud(bottle_5mm)
+    hy = ctx.vote(dm, t, dev_crop, 0, 50)
+    for h in hy[::3]:
+        acc = ctx.vote_debug_accumulator(t, dev_crop, int(h["scene_index"]))
+        flat = int(np.argmax(acc))
+        assert h["votes"] == acc.reshape(-1)[flat]
+        if h["votes"]:
+            assert (int(h["model_index"]), int(h["alpha_bin"])) == divmod(flat, acc.shape[1])
+
+
+@pytest.mark.parametrize("step_deg", [6.0, 14.3239448782706, 25.0])
+def test_k3_other_angle_steps(ctx, oracle, bottle, dev_crop, step_deg):
+    """6 degrees: 60 phase positions per turn (constant-shift path, 7-bit wrap field); 0.25 rad and
+    25 degrees: 2*pi/step is not an integer, every bucket takes the per-entry path (seam band on)."""
+    step = np.float32(step_deg) / np.float32(180.0) * np.float32(np.pi)
+    feats = oracle.ppf_estimation(bottle)
+    hm = oracle.HashMap(step, DIST_STEP).set_input_feature_cloud(feats)
+    t = ctx.table_build(ctx.features_upload(feats), step, DIST_STEP)
+    assert t.info.n_entries == hm.num_entries
+    assert (t.info.phase_cells > 1) == (step_deg == 6.0)
+    for s_r in (5, 600):
+        inr, d, a = ctx.vote_debug_pairs(t, dev_crop, s_r)
+        acc = ctx.vote_debug_accumulator(t, dev_crop, s_r)
+        ref, votes = hm.vote_accumulate_from_pairs(bottle.shape[0], d[inr > 0], a[inr > 0])
+        assert votes == int(acc.sum())
+        assert np.array_equal(acc, ref), f"accumulator differs for reference {s_r}"
+
+
 def test_k3_alpha_bins_on_device(ctx):
     from yolo_ppf_pose_estimation_b200 import capi
     rng = np.random.default_rng(5)

@@ -463,8 +463,11 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         memcpy(&mx, &bits, sizeof(float));
         info.max_dist = bits < 0 ? -1.0f : mx;  // PCL: max_dist_ starts at -1
     }
-    K2_CUDA(cudaMalloc(&t->entry_w, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
-    K2_CUDA(cudaMalloc(&t->entry_am, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
+    // the voting kernel reads whole batches: ENTRY_PAD readable (zero) words follow the last entry
+    K2_CUDA(cudaMalloc(&t->entry_w, ((size_t)n_entries + ENTRY_PAD) * sizeof(uint32_t)));
+    K2_CUDA(cudaMalloc(&t->entry_am, ((size_t)n_entries + ENTRY_PAD) * sizeof(uint32_t)));
+    K2_CUDA(cudaMemsetAsync(t->entry_w + n_entries, 0, ENTRY_PAD * sizeof(uint32_t), ctx->stream));
+    K2_CUDA(cudaMemsetAsync(t->entry_am + n_entries, 0, ENTRY_PAD * sizeof(uint32_t), ctx->stream));
     K2_CUDA(cudaMalloc(&t->entry_idx, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
     K2_CUDA(cudaMalloc(&t->entry_alpha, std::max<size_t>(1, n_entries) * sizeof(float)));
     unsigned long long *d_cnt = nullptr;

@@ -33,44 +33,38 @@ namespace b200ppf {
 
 namespace {
 
-#ifndef B200PPF_VOTE_THREADS
-#define B200PPF_VOTE_THREADS 512
-#endif
 #ifndef B200PPF_VOTE_MINBLOCKS
 #define B200PPF_VOTE_MINBLOCKS 2
 #endif
-constexpr int VOTE_THREADS = B200PPF_VOTE_THREADS;
-constexpr int VOTE_WARPS = VOTE_THREADS / 32;
+// Two launch shapes: 512 threads with two CTAs per SM when the accumulator slice leaves room for both,
+// 1024 threads with one CTA per SM (the same 32 warps) for the large slices of sliced tables.
+constexpr int VOTE_THREADS_SMALL = 512;
+constexpr int VOTE_THREADS_LARGE = 1024;
 #ifndef B200PPF_CAND_CAP
 #define B200PPF_CAND_CAP 2048
 #endif
-#ifndef B200PPF_ITEM_CAP
-#define B200PPF_ITEM_CAP B200PPF_VOTE_THREADS
-#endif
 constexpr int CAND_CAP = B200PPF_CAND_CAP;  // in-radius candidates buffered between flushes
-constexpr int ITEM_CAP = B200PPF_ITEM_CAP;  // candidates turned into work items per B/C round (<= VOTE_THREADS)
-constexpr int ITEM_SLOTS = ITEM_CAP;
-static_assert(ITEM_CAP <= VOTE_THREADS, "one thread per candidate in phase B");
 #ifndef B200PPF_VOTE_UNROLL
 #define B200PPF_VOTE_UNROLL 4
 #endif
 constexpr int VOTE_UNROLL = B200PPF_VOTE_UNROLL;
-static_assert(CAND_CAP >= 2 * VOTE_THREADS, "flush threshold must leave one sweep iteration of room");
+static_assert(CAND_CAP >= 2 * VOTE_THREADS_LARGE, "flush threshold must leave one sweep iteration of room");
 
-// One in-radius scene pair with a non-empty bucket.  The bucket's entries [off, off + len) are walked in
-// steps of 32: steps below k_below lie wholly under the scene pair's phase (shift constant c_below),
-// steps from k_above on wholly over it (c_below minus one bin), the steps in between — the scene
-// phase's own cell rounded out to step bounds, or the whole bucket — take the per-entry path.
+// One in-radius scene pair with a non-empty bucket [off, off + len): the entries below k_below lie under
+// the scene pair's phase (shift constant c_below), those from k_above on over it (c_below minus one
+// bin), the ones in between — the scene phase's own cell, or the whole bucket — take the per-entry path.
 struct __align__(16) WorkItem {
     uint32_t off, len;
-    uint32_t k_below, k_above;  // multiples of 32; k_above may exceed len
+    uint32_t k_below, k_above;  // the scene phase's own cell is [k_below, k_above); the whole bucket when it does not split
     uint32_t c_below;           // constant subtracted from the hot words below the scene phase (shift q + 1)
     uint32_t c_s;               // per-entry path: alpha_to_fix(alpha_s) - 2^31
     float alpha_s;              // per-entry path: PCL's float (literal form of the guard-band votes)
     uint32_t pad;
 };
 
-constexpr size_t QUEUE_BYTES = CAND_CAP * sizeof(uint32_t) + ITEM_SLOTS * sizeof(WorkItem);
+// candidate queue + one work item per thread (phase B turns THREADS candidates into items per round)
+constexpr size_t queue_bytes(int threads) { return CAND_CAP * sizeof(uint32_t) + (size_t)threads * sizeof(WorkItem); }
+constexpr size_t SMALL_SHAPE_SMEM_MAX = 111 * 1024;  // two such CTAs (+ static + system reserve) share one SM
 constexpr size_t STATIC_RESERVE = 2048;  // static shared + the 1 KB the system reserves per CTA
 
 struct VoteArgs {
@@ -146,14 +140,14 @@ __device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_add
     else red_shared_inc(acc_addr + ((rowoff + bin) << 2));
 }
 
-template <int MODE, bool SEAM, bool BULK>
-__global__ void __launch_bounds__(VOTE_THREADS, B200PPF_VOTE_MINBLOCKS)
+template <int MODE, bool SEAM, bool BULK, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : B200PPF_VOTE_MINBLOCKS)
 ppf_vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Frame s_sg;
     __shared__ uint32_t s_ncand, s_nitems, s_next, s_scratch;
     __shared__ uint32_t s_run_start[9], s_run_end[9];
-    __shared__ unsigned long long s_best[VOTE_WARPS];
+    __shared__ unsigned long long s_best[(THREADS / 32)];
     __shared__ unsigned long long s_stat[4];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -165,7 +159,7 @@ ppf_vote_kernel(const VoteArgs a) {
     // queues first: the accumulator's shared address must be >= 4 * N_T (shift items subtract up to that)
     uint32_t *cand = reinterpret_cast<uint32_t *>(smem_raw);
     WorkItem *items = reinterpret_cast<WorkItem *>(cand + CAND_CAP);
-    uint32_t *acc = reinterpret_cast<uint32_t *>(items + ITEM_SLOTS);
+    uint32_t *acc = reinterpret_cast<uint32_t *>(items + THREADS);
     const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
     const uint32_t scratch_addr = (uint32_t)__cvta_generic_to_shared(&s_scratch);
 
@@ -194,7 +188,7 @@ ppf_vote_kernel(const VoteArgs a) {
         s_run_start[r] = b;
         s_run_end[r] = e;
     }
-    for (uint32_t k = tid; k < acc_len; k += VOTE_THREADS) acc[k] = 0;
+    for (uint32_t k = tid; k < acc_len; k += THREADS) acc[k] = 0;
     __syncthreads();
 
     const uint32_t lf = a.bp.cells_log2;
@@ -205,13 +199,13 @@ ppf_vote_kernel(const VoteArgs a) {
     // phases B + C over the buffered candidates
     auto flush = [&]() {
         const uint32_t ncand = s_ncand;
-        for (uint32_t c0 = 0; c0 < ncand; c0 += ITEM_CAP) {
+        for (uint32_t c0 = 0; c0 < ncand; c0 += THREADS) {
             // ---- B: pair features -> work items -------------------------------------------------
             const uint32_t c = c0 + tid;
             // the bucket [o0, oF) splits at the scene phase's cell [oa, ob): below it, inside it, above it
             uint32_t o0 = 0, oa = 0, ob = 0, oF = 0, q = 0, c_s = 0;
             float alpha_s = 0.0f;
-            if (tid < ITEM_CAP && c < ncand) {
+            if (tid < THREADS && c < ncand) {
                 const uint32_t s = cand[c];
                 const float4 p4 = __ldg(a.gpos + s), n4 = __ldg(a.gnrm + s);
                 float f[4];
@@ -251,8 +245,8 @@ ppf_vote_kernel(const VoteArgs a) {
                     WorkItem it;
                     it.off = o0;
                     it.len = oF - o0;
-                    it.k_below = (oa - o0) & ~31u;
-                    it.k_above = (ob - o0 + 31u) & ~31u;
+                    it.k_below = oa - o0;
+                    it.k_above = ob - o0;
                     it.c_below = ((q + 1u) << a.bp.low_bits) + 4u * (q + 1u) - acc_addr;
                     it.c_s = c_s;
                     it.alpha_s = alpha_s;
@@ -272,7 +266,8 @@ ppf_vote_kernel(const VoteArgs a) {
                 const uint32_t len = wi.len;
                 const uint32_t *wp = a.entry_w + wi.off;
                 if (lane == 0) st_votes += len;
-                // shift steps [kb, ke): every vote is hot word - constant (wrapped through the max)
+                // shift range [kb, ke): every vote is hot word - constant (wrapped through the max).  The entry
+                // arrays carry ENTRY_PAD readable words past the end, so the partial batch loads unclamped.
                 auto shift_range = [&](uint32_t kb, uint32_t ke, uint32_t c0v) {
                     const uint32_t c1v = c0v - a.bp.wrap_add;
                     uint32_t k0 = kb + lane;
@@ -283,51 +278,46 @@ ppf_vote_kernel(const VoteArgs a) {
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u) red_shared_inc(shift_address(hw[u], c0v, c1v, lowmask));
                     }
-                    if (k0 - lane < ke) {  // warp-uniform: a partial batch remains; loads clamp, votes are predicated
+                    if (k0 - lane < ke) {  // warp-uniform: a partial batch remains; votes are predicated
                         uint32_t hw[VOTE_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(wp + min(k0 + u * 32, ke - 1));
+                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(wp + k0 + u * 32);
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u)
                             red_shared_inc_if_lt(shift_address(hw[u], c0v, c1v, lowmask), k0 + u * 32, ke);
                     }
                 };
-                const uint32_t k_mid_end = min(wi.k_above, len);
                 if (BULK) {
                     if (wi.k_below) shift_range(0u, wi.k_below, wi.c_below);
                     if (wi.k_above < len) shift_range(wi.k_above, len, wi.c_below - ((1u << a.bp.low_bits) + 4u));
                 }
-                if (wi.k_below < k_mid_end) {
+                if (wi.k_below < wi.k_above) {
                     if (MODE == ALPHA_MODE_A) {
-                        // per-entry steps: 4 x 32 entries per batch, branch-free votes; loads past the end clamp
-                        // to the final entry and vote into the scratch word
-                        const uint32_t last = k_mid_end - 1;
+                        // per-entry range: branch-free fixed-point votes, 32 entries per step (two steps in
+                        // flight); lanes past the end read the padding and vote into the scratch word
                         const uint32_t *ap = a.entry_am + wi.off;
-                        for (uint32_t k0 = wi.k_below + lane; k0 - lane <= last; k0 += 32 * VOTE_UNROLL) {  // warp-uniform
-                            uint2 en[VOTE_UNROLL];
+                        for (uint32_t k0 = wi.k_below + lane; k0 - lane < wi.k_above; k0 += 64) {  // warp-uniform
+                            uint2 en[2];
 #pragma unroll
-                            for (int u = 0; u < VOTE_UNROLL; ++u) {
-                                const uint32_t kk = min(k0 + u * 32, last);
-                                en[u] = make_uint2(__ldg(wp + kk), __ldg(ap + kk));
-                            }
-                            bool risky[VOTE_UNROLL];
-                            bool any = false;
+                            for (int u = 0; u < 2; ++u) en[u] = make_uint2(__ldg(wp + k0 + u * 32), __ldg(ap + k0 + u * 32));
+                            bool risky[2];
 #pragma unroll
-                            for (int u = 0; u < VOTE_UNROLL; ++u) {
-                                en[u].x = hot_word_row_words(a.bp, en[u].x);
-                                risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s, k0 + u * 32 <= last);
-                                any |= risky[u];
+                            for (int u = 0; u < 2; ++u) {
+                                risky[u] = false;
+                                if (k0 - lane + u * 32 < wi.k_above) {  // warp-uniform
+                                    en[u].x = hot_word_row_words(a.bp, en[u].x);
+                                    risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s,
+                                                                k0 + u * 32 < wi.k_above);
+                                }
                             }
-                            if (any) {
 #pragma unroll
-                                for (int u = 0; u < VOTE_UNROLL; ++u)
-                                    if (risky[u])
-                                        vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
-                                                         wi.alpha_s, st_skipped);
-                            }
+                            for (int u = 0; u < 2; ++u)
+                                if (risky[u])
+                                    vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
+                                                     wi.alpha_s, st_skipped);
                         }
                     } else {
-                        for (uint32_t k = wi.k_below + lane; k < k_mid_end; k += 32)
+                        for (uint32_t k = wi.k_below + lane; k < wi.k_above; k += 32)
                             vote_exact<MODE>(a.bp, acc_addr, hot_word_row_words(a.bp, __ldg(wp + k)),
                                              __ldg(a.entry_alpha + wi.off + k), wi.alpha_s, st_skipped);
                     }
@@ -371,18 +361,18 @@ ppf_vote_kernel(const VoteArgs a) {
         // the common case: every point of the 27 cells fits the queue — no barriers inside the sweep
         for (int r = 0; r < 9; ++r) {
             const uint32_t rb = s_run_start[r], re = s_run_end[r];
-            for (uint32_t base = rb; base < re; base += VOTE_THREADS) test_and_queue(base + tid, re);
+            for (uint32_t base = rb; base < re; base += THREADS) test_and_queue(base + tid, re);
         }
         __syncthreads();
     } else {
         for (int r = 0; r < 9; ++r) {
             const uint32_t rb = s_run_start[r], re = s_run_end[r];
-            for (uint32_t base = rb; base < re; base += VOTE_THREADS) {
+            for (uint32_t base = rb; base < re; base += THREADS) {
                 test_and_queue(base + tid, re);
                 __syncthreads();
                 const uint32_t buffered = s_ncand;
                 __syncthreads();  // nobody may start the next sweep's atomics before everyone has read
-                if (buffered > CAND_CAP - VOTE_THREADS) flush();
+                if (buffered > CAND_CAP - THREADS) flush();
             }
         }
     }
@@ -392,7 +382,7 @@ ppf_vote_kernel(const VoteArgs a) {
     // one thread per model row: fold PCL's out-of-range bin n_alpha into n_alpha - 1, then scan the row
     const uint32_t n_alpha = a.bp.n_alpha;
     unsigned long long best = 0;
-    for (uint32_t r = tid; r < rows; r += VOTE_THREADS) {
+    for (uint32_t r = tid; r < rows; r += THREADS) {
         uint32_t *row = acc + r * stride;
         row[n_alpha - 1] += row[n_alpha];
         uint32_t bv = 0, bc = 0;
@@ -430,7 +420,7 @@ ppf_vote_kernel(const VoteArgs a) {
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int w = 1; w < VOTE_WARPS; ++w) best = max(best, s_best[w]);
+        for (int w = 1; w < (THREADS / 32); ++w) best = max(best, s_best[w]);
         if (best) atomicMax(a.peaks + blockIdx.x, best);
         if (slice == 0) {
             atomicAdd(a.stats + 0, s_stat[0]);
@@ -503,9 +493,15 @@ __global__ void debug_alpha_bins_kernel(BinParams bp, const float *__restrict__ 
     exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, am[p], as[p]);
 }
 
-size_t vote_smem_bytes(const b200ppf_table *t) {
-    return (size_t)t->info.slice_rows * (t->info.n_alpha + 1) * sizeof(uint32_t) + QUEUE_BYTES;
+size_t accumulator_bytes(const b200ppf_table *t) {
+    return (size_t)t->info.slice_rows * (t->info.n_alpha + 1) * sizeof(uint32_t);
 }
+// launch shape of a table: 512 x 2 CTAs/SM when the slice is small enough, else 1024 x 1
+int vote_threads(const b200ppf_table *t) {
+    return accumulator_bytes(t) + queue_bytes(VOTE_THREADS_SMALL) <= SMALL_SHAPE_SMEM_MAX ? VOTE_THREADS_SMALL
+                                                                                        : VOTE_THREADS_LARGE;
+}
+size_t vote_smem_bytes(const b200ppf_table *t) { return accumulator_bytes(t) + queue_bytes(vote_threads(t)); }
 
 // smallest float x with sqrtf(x) >= r (host sqrtf and device sqrtf are both correctly rounded)
 float radius_sq_bound(float r) {
@@ -554,16 +550,23 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     const size_t smem = vote_smem_bytes(t);
     dim3 grid_dim((unsigned)ref_count, t->info.n_slices);
     cudaEventRecord(ctx->ev_vote[1], ctx->stream);  // grid build ends, voting starts
-#define LAUNCH_VOTE(M, S, B)                                                                                       \
+#define LAUNCH_VOTE_T(M, S, B, T)                                                                                  \
     do {                                                                                                            \
-        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<M, S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+        PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<M, S, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem));                                                             \
-        PPF_LAUNCH(ctx, (ppf_vote_kernel<M, S, B>), grid_dim, VOTE_THREADS, smem, a);                               \
+        PPF_LAUNCH(ctx, (ppf_vote_kernel<M, S, B, T>), grid_dim, T, smem, a);                                       \
     } while (0)
+#define LAUNCH_VOTE(M, S, B)                                                            \
+    do {                                                                                 \
+        if (threads == VOTE_THREADS_SMALL) LAUNCH_VOTE_T(M, S, B, VOTE_THREADS_SMALL);  \
+        else LAUNCH_VOTE_T(M, S, B, VOTE_THREADS_LARGE);                                \
+    } while (0)
+    const int threads = vote_threads(t);
     if (ctx->alpha_mode == ALPHA_MODE_B) LAUNCH_VOTE(ALPHA_MODE_B, false, false);
     else if (a.bp.bulk) LAUNCH_VOTE(ALPHA_MODE_A, false, true);  // an integer T has no separate seam band
     else if (a.bp.seam_guard) LAUNCH_VOTE(ALPHA_MODE_A, true, false);
     else LAUNCH_VOTE(ALPHA_MODE_A, false, false);
+#undef LAUNCH_VOTE_T
 #undef LAUNCH_VOTE
     cudaEventRecord(ctx->ev_vote[2], ctx->stream);
     scene_grid_free(ctx, &grid);
@@ -680,7 +683,7 @@ int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, cons
 
 size_t k3_accumulator_budget(const b200ppf_ctx *ctx) {
     size_t total = ctx->smem_optin ? ctx->smem_optin : kSmemPerBlockMax;
-    return total - QUEUE_BYTES - STATIC_RESERVE;
+    return total - queue_bytes(VOTE_THREADS_LARGE) - STATIC_RESERVE;
 }
 
 int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,

@@ -18,6 +18,8 @@ static_assert(sizeof(b200ppf_signature) == 20, "pcl::PPFSignature is 20 bytes");
 
 // smallest accumulator budget we plan slices against (bytes of dynamic shared memory)
 constexpr size_t kSmemPerBlockMax = 227 * 1024;
+// readable words behind the last table entry (the voting kernel loads whole batches of 8 x 32)
+constexpr size_t ENTRY_PAD = 256;
 
 }  // namespace b200ppf
 
