@@ -217,6 +217,72 @@ __global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const ui
     entry_alpha[p] = alpha;
 }
 
+// Bank spreading.  Every vote of a shift range lands at (hot word - one constant), so the shared-memory
+// bank of a vote is the bank of the hot word's own address up to a rotation common to the whole
+// range.  Inside each phase cell the entries are therefore re-ordered by (rank within their bank
+// class, bank): any 32 consecutive entries then hold each bank at most twice where random order
+// holds the fullest bank ~3.5 times — the voting kernel's ATOMS wavefronts drop accordingly.  The
+// order inside a cell is free: exports re-sort to (i, j), vote counts do not depend on it.
+// One warp per non-empty cell; ranks follow the (i, j) order, so the result is deterministic.
+constexpr int SPREAD_WARPS = 8;
+__global__ void __launch_bounds__(SPREAD_WARPS * 32)
+bank_spread_kernel(const uint32_t *__restrict__ sub_offsets, uint32_t total_sub, const uint32_t *__restrict__ w_in,
+                   const uint32_t *__restrict__ am_in, const uint32_t *__restrict__ alpha_in,
+                   const uint32_t *__restrict__ idx_in, uint32_t *__restrict__ w_out, uint32_t *__restrict__ am_out,
+                   float *__restrict__ alpha_out, uint32_t *__restrict__ idx_out) {
+    __shared__ uint32_t s_count[SPREAD_WARPS][32], s_run[SPREAD_WARPS][32];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t *count = s_count[wib], *run = s_run[wib];
+    const uint32_t n_warps = gridDim.x * SPREAD_WARPS;
+    for (uint32_t c0 = (blockIdx.x * SPREAD_WARPS + wib) * 32; c0 < total_sub; c0 += n_warps * 32) {
+        const uint32_t c = c0 + lane;
+        uint32_t b = 0, e = 0;
+        if (c < total_sub) {
+            b = sub_offsets[c];
+            e = sub_offsets[c + 1];
+        }
+        uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, e > b);
+        while (nonempty) {
+            const int src = __ffs(nonempty) - 1;
+            nonempty &= nonempty - 1;
+            const uint32_t cb = __shfl_sync(0xFFFFFFFFu, b, src), ce = __shfl_sync(0xFFFFFFFFu, e, src);
+            count[lane] = 0;
+            run[lane] = 0;
+            __syncwarp();
+            for (uint32_t k = cb + lane; k < ce; k += 32) atomicAdd(&count[(w_in[k] >> 2) & 31u], 1u);
+            __syncwarp();
+            for (uint32_t k0 = cb; k0 < ce; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const bool valid = k < ce;
+                const uint32_t w = valid ? w_in[k] : 0u;
+                const uint32_t bank = valid ? ((w >> 2) & 31u) : 32u + lane;  // idle lanes match nobody
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, bank);
+                uint32_t r = 0;
+                if (valid) r = run[bank] + __popc(same & ((1u << lane) - 1u));
+                __syncwarp();
+                if (valid && lane == (uint32_t)(31 - __clz(same))) run[bank] = r + 1;  // highest lane of the class
+                __syncwarp();
+                if (valid) {
+                    // entries ordered before (r, bank): every class contributes min(count, r), plus the lower
+                    // banks that still have an entry of rank r
+                    uint32_t dest = 0;
+#pragma unroll 8
+                    for (uint32_t bb = 0; bb < 32; ++bb) {
+                        const uint32_t cnt = count[bb];
+                        dest += min(cnt, r) + ((bb < bank && cnt > r) ? 1u : 0u);
+                    }
+                    const uint32_t o = cb + dest;
+                    w_out[o] = w;
+                    am_out[o] = am_in[k];
+                    alpha_out[o] = __uint_as_float(alpha_in[k]);
+                    idx_out[o] = idx_in[k];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void alpha_scatter_kernel(const uint32_t *__restrict__ entry_idx, const float *__restrict__ entry_alpha,
                                      uint32_t n_entries, float *__restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -476,10 +542,23 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     {
         auto launch = [&]() -> int {
             if (n_entries) {
-                PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
-                           info.slice_rows, t->bp, t->entry_w, t->entry_am, t->entry_alpha, d_range + 10);
-                PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
-                                              cudaMemcpyDeviceToDevice, ctx->stream));
+                if (cells_log2 && !getenv("B200PPF_NO_BANK_SPREAD")) {
+                    // entries in (key, cell, i, j) order into the free halves of the sort buffers, then the
+                    // bank-spreading permutation inside every phase cell writes the table's arrays
+                    uint32_t *w_tmp = keys[1 - s], *am_tmp = idx[1 - s], *alpha_tmp = alp[1 - s];
+                    PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
+                               info.slice_rows, t->bp, w_tmp, am_tmp, reinterpret_cast<float *>(alpha_tmp), d_range + 10);
+                    const unsigned blocks = (unsigned)std::min<size_t>(((size_t)total_sub + 32 * SPREAD_WARPS - 1) /
+                                                                           (32 * SPREAD_WARPS),
+                                                                       (size_t)ctx->sm_count * 16);
+                    PPF_LAUNCH(ctx, bank_spread_kernel, blocks, SPREAD_WARPS * 32, 0, t->sub_offsets, total_sub, w_tmp, am_tmp,
+                               alpha_tmp, idx[s], t->entry_w, t->entry_am, t->entry_alpha, t->entry_idx);
+                } else {
+                    PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
+                               info.slice_rows, t->bp, t->entry_w, t->entry_am, t->entry_alpha, d_range + 10);
+                    PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
+                                                  cudaMemcpyDeviceToDevice, ctx->stream));
+                }
             }
             PPF_LAUNCH(ctx, count_nonempty_kernel, (total_keys + 255) / 256, 256, 0, t->offsets, total_keys, d_cnt);
             return B200PPF_OK;

@@ -146,6 +146,7 @@ ppf_vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Frame s_sg;
     __shared__ uint32_t s_ncand, s_nitems, s_next, s_scratch;
+    __shared__ uint32_t s_cls[8];  // work items per length class of the current round
     __shared__ uint32_t s_run_start[9], s_run_end[9];
     __shared__ unsigned long long s_best[(THREADS / 32)];
     __shared__ unsigned long long s_stat[4];
@@ -173,6 +174,7 @@ ppf_vote_kernel(const VoteArgs a) {
         s_next = 0;
     }
     if (tid < 4) s_stat[tid] = 0;
+    if (tid >= 64 && tid < 72) s_cls[tid - 64] = 0;
     if (tid >= 32 && tid < 41) {
         // the 3 x-adjacent cells of row (cy+dy, cz+dz) are one contiguous run of the sorted scene
         const int r = (int)tid - 32;
@@ -235,24 +237,40 @@ ppf_vote_kernel(const VoteArgs a) {
                     }
                 }
             }
+            // Items enter the queue longest class first (classes = powers of two of the bucket length): the
+            // warps then finish on short items and the CTA's barrier is not held up by one long bucket.
             const bool push = oF > o0;
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, push);
-            if (m) {
-                uint32_t base = 0;
-                if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&s_nitems, __popc(m));
-                base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+            const uint32_t cls = push ? (uint32_t)min(7, max(0, 23 - (int)__clz(oF - o0))) : 8u + (lane & 7u);
+            uint32_t rank = 0;
+            {
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, cls);
                 if (push) {
-                    WorkItem it;
-                    it.off = o0;
-                    it.len = oF - o0;
-                    it.k_below = oa - o0;
-                    it.k_above = ob - o0;
-                    it.c_below = ((q + 1u) << a.bp.low_bits) + 4u * (q + 1u) - acc_addr;
-                    it.c_s = c_s;
-                    it.alpha_s = alpha_s;
-                    it.pad = 0;
-                    items[base + __popc(m & ((1u << lane) - 1u))] = it;
+                    const int leader = __ffs(same) - 1;
+                    if ((int)lane == leader) rank = atomicAdd(&s_cls[cls], __popc(same));
+                    rank = __shfl_sync(same, rank, leader) + __popc(same & ((1u << lane) - 1u));
                 }
+            }
+            __syncthreads();
+            if (push) {
+                uint32_t slot = rank;
+#pragma unroll
+                for (uint32_t k = 7; k > 0; --k) slot += (k > cls) ? s_cls[k] : 0u;
+                WorkItem it;
+                it.off = o0;
+                it.len = oF - o0;
+                it.k_below = oa - o0;
+                it.k_above = ob - o0;
+                it.c_below = ((q + 1u) << a.bp.low_bits) + 4u * (q + 1u) - acc_addr;
+                it.c_s = c_s;
+                it.alpha_s = alpha_s;
+                it.pad = 0;
+                items[slot] = it;
+            }
+            if (tid == 0) {
+                uint32_t total = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) total += s_cls[k];
+                s_nitems = total;
             }
             __syncthreads();
             // ---- C: votes ---------------------------------------------------------------------
@@ -328,6 +346,7 @@ ppf_vote_kernel(const VoteArgs a) {
                 s_nitems = 0;
                 s_next = 0;
             }
+            if (tid >= 64 && tid < 72) s_cls[tid - 64] = 0;
             __syncthreads();
         }
         if (tid == 0) s_ncand = 0;
