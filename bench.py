@@ -160,9 +160,30 @@ def oracle_table(wl):
 
 def cpu_sample_refs(wl, n_sample):
     """Evenly spread sample of reference slots (same refs every run)."""
-    n_sample = min(n_sample, wl.n_ref)
+    n_sample = max(1, min(n_sample, wl.n_ref))
     step = max(1, wl.n_ref // n_sample)
     return 0, step * wl.ref_rate, n_sample
+
+
+def pick_cpu_sample(hm, wl, threads, budget_s, requested):
+    """Bounded sample of reference points whose pass takes about budget_s seconds on `threads` threads.
+    The per-reference cost spans 10 ms (bottle) to tens of seconds (10 000-point model, dense spots), so
+    the size is calibrated by timed passes over geometrically growing spread samples."""
+    if requested:
+        return cpu_sample_refs(wl, requested)
+    cap = min(4096, wl.n_ref)
+    n = min(cap, max(4, threads))
+    while True:
+        f0, st0, cnt = cpu_sample_refs(wl, n)
+        t0 = time.perf_counter()
+        hm.vote(wl.model, wl.scene, f0, st0, cnt, n_threads=threads)
+        dt = max(time.perf_counter() - t0, 1e-4)
+        if dt >= 0.25 * budget_s or n >= cap:
+            break
+        n = min(cap, max(2 * n, int(0.6 * budget_s / dt * n)))
+    if dt > budget_s:  # even the smallest sample overshoots: shrink proportionally
+        n = max(1, int(n * budget_s / dt))
+    return cpu_sample_refs(wl, n)
 
 
 def run_reference(args, wl):
@@ -172,7 +193,8 @@ def run_reference(args, wl):
         return
     ob, hm = oracle_table(wl)
     threads = ob.max_threads()
-    first, step, count = cpu_sample_refs(wl, args.cpu_sample)
+    # the whole --steps K --warmup W run should end within a few minutes: ~150 s of voting in total
+    first, step, count = pick_cpu_sample(hm, wl, threads, 150.0 / (args.warmup + args.steps), args.cpu_sample)
     times, pairs = [], 0
     for k in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -301,14 +323,25 @@ def run_b200(args, wl):
         e2e_ms = e2e_total_ms / args.steps
         peak, peak_src = measured_peaks()
         # algorithmic bytes of one voting launch on one rank (DESIGN.md "K3 roofline"):
-        #   8 B gathered per vote; per in-radius pair and slice 8 B of CSR offsets + 32 B of point/normal;
+        #   4 B gathered per vote (the hot word; the 1/16 of votes on the per-entry path gather 8 B: 4.25 B mean);
+        #   per in-radius pair and slice 16 B of CSR offsets + 32 B of point/normal;
         #   16 B per scene point per resident wave of CTAs for the position sweep
         my_pairs, my_votes = stats["pairs_in_radius"], stats["votes"]
         ctas = count * info.n_slices
         waves = max(1, -(-ctas // (148 * 2)))
-        alg_bytes = 8.0 * my_votes + 40.0 * my_pairs * info.n_slices + 16.0 * n_s * waves
+        per_vote = 4.0 + 4.0 / max(1, info.phase_cells) if info.phase_cells > 1 else 8.0
+        alg_bytes = per_vote * my_votes + 48.0 * my_pairs * info.n_slices + 16.0 * n_s * waves
         k3_ms = float(np.mean(vote_ms))
         achieved = alg_bytes / (k3_ms * 1e-3) / 1e9
+        # the denominator HBM peaks do not cover: shared-memory reductions per second, measured here
+        # (csrc/microbench.cu: 2 x 512-thread CTAs per SM, 64 KB accumulators; random words = the voting pattern)
+        atoms_peak_random = ctx.microbench_atoms(1)
+        atoms_peak_spread = ctx.microbench_atoms(0)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k3_dram_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(wl.name)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -331,15 +364,24 @@ def run_b200(args, wl):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "ppf_vote_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
+                         "peak_source": peak_src,
                          "kernel_ms": k3_ms, "kernel_ms_max_over_ranks": vote_kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "votes_per_sec_in_kernel": my_votes / (k3_ms * 1e-3),
-                         "note": "shared-memory atomics, not HBM, bind this kernel: 1 shared atomic per vote"},
+                         "atomic": {"achieved": my_votes / (k3_ms * 1e-3), "unit": "shared-memory reductions/s",
+                                    "peak": atoms_peak_random, "frac": my_votes / (k3_ms * 1e-3) / atoms_peak_random,
+                                    "peak_conflict_free": atoms_peak_spread,
+                                    "peak_source": "measured in this run (b200ppf_microbench_atoms, random words in a 64 KB accumulator)"},
+                         "note": "the gathered table bytes are served by L2 (DRAM traffic is the table + scene once), so "
+                                 "'achieved' can exceed the HBM copy peak; what binds is the L1 data pipe: one "
+                                 "shared-memory reduction per vote — see 'atomic'"},
         }
         if world == 1 and not args.no_cpu:
             ob, hm = oracle_table(wl)
-            f0, st0, cnt = cpu_sample_refs(wl, args.cpu_sample)
+            f0, st0, cnt = pick_cpu_sample(hm, wl, 1, 15.0, args.cpu_sample)
             t0 = time.perf_counter()
             _, cst = hm.vote(wl.model, wl.scene, f0, st0, cnt, n_threads=1)
             dt = time.perf_counter() - t0
@@ -358,7 +400,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--cpu-sample", type=int, default=192, help="reference points in the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="reference points in the CPU sample (0 = sized from a timing probe: ~15 s of CPU work per pass)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -319,6 +319,36 @@ def test_k3_large_model_two_slices(ctx, oracle, bottle_5mm, scene_crop, dev_crop
             assert (int(h["model_index"]), int(h["alpha_bin"])) == divmod(flat, acc.shape[1])
 
 
+def test_c2_full_scene(ctx, bottle, scene_full, dev_bottle, oracle_bottle, table_from_oracle_features):
+    """BASELINE config 2 at full size (44 893 reference points): accumulators of sampled reference points
+    bit-exact against the oracle, every sampled peak the first maximum of its accumulator, and the
+    size-independent property that an interleaved 3-way split of the reference points reproduces the
+    single-launch records byte for byte."""
+    _, hm = oracle_bottle
+    t = table_from_oracle_features
+    ds = ctx.upload_cloud(scene_full)
+    full = ctx.vote(dev_bottle, t, ds, 0, 1)
+    st = ctx.vote_stats()
+    assert len(full) == scene_full.shape[0] and np.array_equal(full["scene_index"], np.arange(len(full)))
+    assert st["votes"] > 7.0e9 and st["pairs_in_radius"] > 1.4e7
+    rng = np.random.default_rng(11)
+    for s_r in rng.choice(len(full), 10, replace=False):
+        inr, d, a = ctx.vote_debug_pairs(t, ds, int(s_r))
+        acc = ctx.vote_debug_accumulator(t, ds, int(s_r))
+        ref, votes = hm.vote_accumulate_from_pairs(bottle.shape[0], d[inr > 0], a[inr > 0])
+        assert votes == int(acc.sum()) and np.array_equal(acc, ref), f"accumulator differs for reference {s_r}"
+        flat = int(np.argmax(acc))
+        h = full[int(s_r)]
+        assert h["votes"] == acc.reshape(-1)[flat]
+        if h["votes"]:
+            assert (int(h["model_index"]), int(h["alpha_bin"])) == divmod(flat, acc.shape[1])
+    parts = [ctx.vote(dev_bottle, t, ds, g, 3) for g in range(3)]
+    merged = np.empty_like(full)
+    for g in range(3):
+        merged[g::3] = parts[g]
+    assert merged.tobytes() == full.tobytes()
+
+
 @pytest.mark.parametrize("step_deg", [6.0, 14.3239448782706, 25.0])
 def test_k3_other_angle_steps(ctx, oracle, bottle, dev_crop, step_deg):
     """6 degrees: 60 phase positions per turn (constant-shift path, 7-bit wrap field); 0.25 rad and

@@ -1,24 +1,27 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, bench (C2 + probes), microbench, ncu launch list and one full capture.
-# usage (from the repo root on the GPU box): bash tools/gpu_round.sh TAG
+# One gpurun call: GPU parity tests, bench lines (C2 default with the CPU leg, C1, C2-5mm, C3), ncu launch list and
+# one full capture of the voting kernel.  usage (repo root on the GPU box): bash tools/gpu_round.sh TAG
 TAG=${1:-r1}
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $O/pytest_$TAG.log
-python bench.py --steps 10 --warmup 3 > $O/bench_c2_$TAG.json 2> $O/bench_c2_$TAG.err
-tail -c 600 $O/bench_c2_$TAG.err
-python - <<'PY' 2>&1 | tee gpurun_out/atoms_$TAG.json
-import json
-from yolo_ppf_pose_estimation_b200 import capi
-c = capi.Context(0)
-print(json.dumps({f"pattern{p}": c.microbench_atoms(p) for p in (0, 1, 2)}))
-PY
-timeout 600 python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu > $O/bench_c3_$TAG.json 2> $O/bench_c3_$TAG.err
-tail -c 600 $O/bench_c3_$TAG.err
-timeout 300 python bench.py --workload c2_5mm --steps 3 --warmup 3 --no-cpu > $O/bench_c2_5mm_$TAG.json 2> $O/bench_c2_5mm_$TAG.err
+grep -q failed $O/pytest_$TAG.log && exit 1
+python bench.py --steps 10 --warmup 3 > $O/bench_c2_$TAG.json 2> $O/bench_c2_$TAG.err; tail -c 600 $O/bench_c2_$TAG.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_c2_ref_$TAG.json 2> $O/bench_c2_ref_$TAG.err
 timeout 300 python bench.py --workload c1 --steps 10 --warmup 3 > $O/bench_c1_$TAG.json 2> $O/bench_c1_$TAG.err
+timeout 300 python bench.py --workload c2_5mm --steps 3 --warmup 3 --no-cpu > $O/bench_c2_5mm_$TAG.json 2> $O/bench_c2_5mm_$TAG.err
+timeout 900 python bench.py --workload c3 --steps 2 --warmup 3 > $O/bench_c3_$TAG.json 2> $O/bench_c3_$TAG.err; tail -c 600 $O/bench_c3_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_launches_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ppf_vote_kernel -s 3 -c 1 -f -o $O/prof_vote_$TAG \
-    python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_full_$TAG.log 2>&1
-ls -la $O | tail -20
+bash tools/gpu_prof.sh $TAG c2
+for f in c2 c2_ref c1 c2_5mm c3; do python - <<PY
+import json
+try:
+    d = json.load(open("$O/bench_${f}_$TAG.json"))
+    r = d.get("roofline", {})
+    print("$f", "value", "%.4g" % d["value"], "ms/step", round(d["ms_per_step"], 3), "e2e", "%.4g" % d["e2e"]["value"],
+          "k3_ms", r.get("kernel_ms"), "atomic_frac", (r.get("atomic") or {}).get("frac"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
+except Exception as e:
+    print("$f", "no line:", e)
+PY
+done

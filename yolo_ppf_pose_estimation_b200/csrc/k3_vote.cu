@@ -289,12 +289,21 @@ ppf_vote_kernel(const VoteArgs a) {
                 auto shift_range = [&](uint32_t kb, uint32_t ke, uint32_t c0v) {
                     const uint32_t c1v = c0v - a.bp.wrap_add;
                     uint32_t k0 = kb + lane;
-                    for (; k0 - lane + 32 * VOTE_UNROLL <= ke; k0 += 32 * VOTE_UNROLL) {  // warp-uniform: a full batch
+                    // long ranges: 8 x 32 hot words in flight per lane (the gathers are latency-bound)
+                    for (; k0 - lane + 64 * VOTE_UNROLL <= ke; k0 += 64 * VOTE_UNROLL) {  // warp-uniform: a double batch
+                        uint32_t hw[2 * VOTE_UNROLL];
+#pragma unroll
+                        for (int u = 0; u < 2 * VOTE_UNROLL; ++u) hw[u] = __ldg(wp + k0 + u * 32);
+#pragma unroll
+                        for (int u = 0; u < 2 * VOTE_UNROLL; ++u) red_shared_inc(shift_address(hw[u], c0v, c1v, lowmask));
+                    }
+                    if (k0 - lane + 32 * VOTE_UNROLL <= ke) {  // warp-uniform: one more full batch
                         uint32_t hw[VOTE_UNROLL];
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(wp + k0 + u * 32);
 #pragma unroll
                         for (int u = 0; u < VOTE_UNROLL; ++u) red_shared_inc(shift_address(hw[u], c0v, c1v, lowmask));
+                        k0 += 32 * VOTE_UNROLL;
                     }
                     if (k0 - lane < ke) {  // warp-uniform: a partial batch remains; votes are predicated
                         uint32_t hw[VOTE_UNROLL];
