@@ -150,10 +150,10 @@ class ClockSampler:
         return out
 
 
-def oracle_table(wl):
+def oracle_table(wl, model=None):
     from oracle import binding as ob
     ob.build()
-    feats = ob.ppf_estimation(wl.model)
+    feats = ob.ppf_estimation(wl.model if model is None else model)
     hm = ob.HashMap(wl.angle_step, wl.dist_step).set_input_feature_cloud(feats)
     return ob, hm
 
@@ -191,22 +191,28 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ob, hm = oracle_table(wl)
+    library = wl.library()
+    tables = [oracle_table(wl, m) for m in library]
+    ob, hm = tables[0]
     threads = ob.max_threads()
     # the whole --steps K --warmup W run should end within a few minutes: ~150 s of voting in total
-    first, step, count = pick_cpu_sample(hm, wl, threads, 150.0 / (args.warmup + args.steps), args.cpu_sample)
+    first, step, count = pick_cpu_sample(hm, wl, threads, 150.0 / (args.warmup + args.steps) / len(library), args.cpu_sample)
     times, pairs = [], 0
     for k in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        hyps, st = hm.vote(wl.model, wl.scene, first, step, count, n_threads=threads)
-        ob.cluster(hyps, wl.pos_thr, wl.rot_thr)
+        step_pairs = 0
+        for m, (_, hm_k) in zip(library, tables):
+            hyps, st = hm_k.vote(m, wl.scene, first, step, count, n_threads=threads)
+            ob.cluster(hyps, wl.pos_thr, wl.rot_thr)
+            step_pairs += st["pairs_in_radius"]
         dt = time.perf_counter() - t0
         if k >= args.warmup:
             times.append(dt)
-            pairs = st["pairs_in_radius"]
+            pairs = step_pairs
     ms = 1e3 * float(np.mean(times))
     value = pairs / (ms * 1e-3)
-    sample = f"{count} of {wl.n_ref} reference points per step (every {step // wl.ref_rate}-th), full scene, vote + cluster"
+    sample = (f"{count} of {wl.n_ref} reference points per step (every {step // wl.ref_rate}-th), full scene, vote + cluster"
+              + (f", for each of the {len(library)} models" if len(library) > 1 else ""))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -237,33 +243,51 @@ def run_b200(args, wl):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     n_ref = wl.n_ref
-    first, step, count = sharding.shard(n_ref, rank, world)
-    chunk = sharding.chunk_size(n_ref, world)
+    library = wl.library()
+    lib_mode = len(library) > 1
+    if lib_mode:
+        # model library (c4): model-parallel — rank r aligns models r, r + world, ... against the replicated scene,
+        # every reference point each; no hypothesis exchange, only the final poses are gathered
+        my_models = [k for k in range(len(library)) if k % world == rank]
+        first, step, count = 0, 1, n_ref
+        chunk = n_ref
+    else:
+        my_models = [0]
+        first, step, count = sharding.shard(n_ref, rank, world)
+        chunk = sharding.chunk_size(n_ref, world)
     with torch.cuda.stream(stream):
         local_buf = torch.zeros((chunk, 16), dtype=torch.float32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # ---- offline stage: model upload + table build (reported, not part of the step) ---------------
-    dm = ctx.upload_cloud(wl.model)
+    dms = [ctx.upload_cloud(library[k]) for k in my_models]
     t0 = time.perf_counter()
-    table = ctx.table_build_from_cloud(dm, wl.angle_step, wl.dist_step)
+    tables = [ctx.table_build_from_cloud(dm, wl.angle_step, wl.dist_step) for dm in dms]
     table_build_ms = 1e3 * (time.perf_counter() - t0)
     tim = ctx.timings()
-    info = table.info
+    info = tables[0].info if tables else None
     ds_resident = ctx.upload_cloud(wl.scene)
     scene_pinned = torch.from_numpy(np.ascontiguousarray(wl.scene, np.float32)).pin_memory()
     n_s = wl.scene.shape[0]
 
-    def align(ds):
-        """vote (this rank's shard) -> all-gather -> cluster; returns (poses, votes)."""
-        ctx.vote_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, local_buf.data_ptr())
-        if world > 1:
-            with torch.cuda.stream(stream):
-                ordered = sharding.all_gather_hypotheses(local_buf, n_ref, world, dist)
-            res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=ordered.data_ptr(), n=n_ref)
-            del ordered
-            return res
-        return ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=local_buf.data_ptr(), n=n_ref)
+    def align(ds, collect=None):
+        """vote (this rank's shard) -> all-gather -> cluster, once per model of this rank; returns the last (poses, votes)."""
+        res = (np.zeros((0, 4, 4), np.float32), np.zeros(0, np.uint32))
+        for dm, table in zip(dms, tables):
+            ctx.vote_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, local_buf.data_ptr())
+            if collect is not None:  # untimed bookkeeping pass: work counters and kernel time of every model
+                st = ctx.vote_stats()
+                for k, v in st.items():
+                    collect[k] = collect.get(k, 0) + v
+                collect["vote_ms"] = collect.get("vote_ms", 0.0) + ctx.timings()["vote_ms"]
+            if world > 1 and not lib_mode:
+                with torch.cuda.stream(stream):
+                    ordered = sharding.all_gather_hypotheses(local_buf, n_ref, world, dist)
+                res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=ordered.data_ptr(), n=n_ref)
+                del ordered
+            else:
+                res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=local_buf.data_ptr(), n=n_ref)
+        return res
 
     def barrier():
         if world > 1:
@@ -284,13 +308,17 @@ def run_b200(args, wl):
             e1.synchronize()
             total += e0.elapsed_time(e1)
             launches += ctx.launch_count - l0
-            vote_ms.append(ctx.timings()["vote_ms"])
+            if not lib_mode:
+                vote_ms.append(ctx.timings()["vote_ms"])
         return total, vote_ms, launches, poses, votes
 
     # ---- resident-input measurement ---------------------------------------------------------------
     barrier()
     timed_steps(lambda: ds_resident, args.warmup)
-    stats = ctx.vote_stats()
+    stats = {}
+    align(ds_resident, collect=stats)
+    for k in ("pairs_in_radius", "votes", "pairs_examined", "nonempty_lookups", "vote_ms"):
+        stats.setdefault(k, 0)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0 and os.environ.get("BENCH_CLOCKS", "1") != "0":
@@ -308,7 +336,9 @@ def run_b200(args, wl):
     barrier()
 
     # whole-job numbers: max over ranks of the time, sum over ranks of the work
-    t = torch.tensor([total_ms, e2e_total_ms, float(np.mean(vote_ms))], dtype=torch.float64, device=dev)
+    if lib_mode:
+        vote_ms = [stats["vote_ms"]]
+    t = torch.tensor([total_ms, e2e_total_ms, float(np.mean(vote_ms)) if vote_ms else 0.0], dtype=torch.float64, device=dev)
     w = torch.tensor([stats["pairs_in_radius"], stats["votes"], stats["pairs_examined"], stats["nonempty_lookups"]],
                      dtype=torch.float64, device=dev)
     if world > 1:
@@ -327,7 +357,7 @@ def run_b200(args, wl):
         #   per in-radius pair and slice 16 B of CSR offsets + 32 B of point/normal;
         #   16 B per scene point per resident wave of CTAs for the position sweep
         my_pairs, my_votes = stats["pairs_in_radius"], stats["votes"]
-        ctas = count * info.n_slices
+        ctas = count * info.n_slices * len(my_models)
         waves = max(1, -(-ctas // (148 * 2)))
         per_vote = 4.0 + 4.0 / max(1, info.phase_cells) if info.phase_cells > 1 else 8.0
         alg_bytes = per_vote * my_votes + 48.0 * my_pairs * info.n_slices + 16.0 * n_s * waves
@@ -349,10 +379,12 @@ def run_b200(args, wl):
             "config": {"workload": f"{wl.name}: {wl.description}", "n_model": int(info.n_model), "n_scene": n_s,
                        "n_ref": n_ref, "angle_step_deg": 12, "dist_step": float(wl.dist_step),
                        "table_entries": int(info.n_entries), "accumulator_slices": int(info.n_slices),
-                       "sharding": f"reference points interleaved over {world} rank(s), table + scene replicated, "
-                                   f"all-gather of 64 B hypotheses" if world > 1 else "single GPU",
+                       "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode
+                                    else f"reference points interleaved over {world} rank(s), table + scene replicated, "
+                                         f"all-gather of 64 B hypotheses" if world > 1 else "single GPU"),
+                       "models_per_step": len(library),
                        "l2": "256 MiB memset between steps, outside the per-step CUDA-event brackets"},
-            "ms_per_pose": ms_per_step,
+            "ms_per_pose": ms_per_step / len(library),
             "votes_per_sec": nvotes / (ms_per_step * 1e-3),
             "pairs_examined_per_sec": examined / (ms_per_step * 1e-3),
             "work_per_step": {"pairs_in_radius": pairs, "votes": nvotes, "pairs_examined": examined},
@@ -379,7 +411,7 @@ def run_b200(args, wl):
                                  "'achieved' can exceed the HBM copy peak; what binds is the L1 data pipe: one "
                                  "shared-memory reduction per vote — see 'atomic'"},
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and not lib_mode:
             ob, hm = oracle_table(wl)
             f0, st0, cnt = pick_cpu_sample(hm, wl, 1, 15.0, args.cpu_sample)
             t0 = time.perf_counter()

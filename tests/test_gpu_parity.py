@@ -349,6 +349,24 @@ def test_c2_full_scene(ctx, bottle, scene_full, dev_bottle, oracle_bottle, table
     assert merged.tobytes() == full.tobytes()
 
 
+def test_k3_dense_scene_flushes_candidate_queue(ctx, bottle, oracle_bottle, table_from_oracle_features):
+    """A scene dense enough that one reference point has far more than 2 048 in-radius neighbours: the sweep
+    has to flush its candidate queue several times (the barrier-ful branch of phase A)."""
+    from yolo_ppf_pose_estimation_b200 import synth
+    _, hm = oracle_bottle
+    dense = synth.synth_scene(24000, 5).copy()
+    c = np.array([0.0, 0.0, 1.5], np.float32)
+    dense[:, :3] = (dense[:, :3] - c) * np.float32(0.12) + c   # 2 m scene squeezed into ~25 cm
+    ds = ctx.upload_cloud(dense)
+    for s_r in (7, 12000):
+        inr, d, a = ctx.vote_debug_pairs(table_from_oracle_features, ds, s_r)
+        assert inr.sum() > 2 * 2048
+        acc = ctx.vote_debug_accumulator(table_from_oracle_features, ds, s_r)
+        ref, votes = hm.vote_accumulate_from_pairs(bottle.shape[0], d[inr > 0], a[inr > 0])
+        assert votes == int(acc.sum()) and np.array_equal(acc, ref)
+    assert ctx.vote_stats()["pairs_in_radius"] == int(inr.sum())
+
+
 @pytest.mark.parametrize("step_deg", [6.0, 14.3239448782706, 25.0])
 def test_k3_other_angle_steps(ctx, oracle, bottle, dev_crop, step_deg):
     """6 degrees: 60 phase positions per turn (constant-shift path, 7-bit wrap field); 0.25 rad and

@@ -35,8 +35,22 @@ __device__ __forceinline__ uint32_t slice_of(uint32_t i, uint32_t slice_rows) { 
 __device__ __forceinline__ uint32_t sort_key(const KeyParams &kp, const BinParams &bp, uint32_t i, uint32_t k, float alpha) {
     uint32_t key = slice_of(i, kp.slice_rows) * kp.key_space + k;
     if (bp.cells_log2) {
-        // alpha outside atan2f's range is rejected later (entries_kernel); any cell will do for it
-        const uint32_t cell = alpha == alpha ? phase_cell(bp, phase_of_fix(bp, alpha_to_fix(alpha))) : 0u;
+        // Phase cell of alpha_m in fp32: frac((alpha + pi) / step) * cells.  The estimate is within 1e-6 rad of
+        // the fixed-point phase the voting kernel reasons with; an entry that lands on the other side of a
+        // cell edge because of it is harmless, since the kernel sends the whole bucket down the per-entry
+        // path whenever the scene phase is within phase_guard (>= 4e-6 rad) of a cell edge — otherwise such
+        // an entry compares with the scene phase exactly like the edge itself does.  (alpha outside
+        // atan2f's range is rejected later, entries_kernel; any cell will do for it.)
+        // The one edge that must be exact is the circular one (phase 0 == phase 1: an entry moved across it
+        // would sit below every scene phase instead of above): close to it the fixed-point phase decides.
+        uint32_t cell = 0;
+        if (alpha == alpha) {
+            const float u = (alpha + 3.14159274f) * bp.inv_step;
+            const float fr = u - floorf(u);
+            const float thr = fmaxf(1e-4f, 2e-6f * (float)bp.n_turn);  // >> the fp32 error of u (a few ulps of T)
+            if (fr < thr || fr > 1.0f - thr) cell = phase_cell(bp, phase_of_fix(bp, alpha_to_fix(alpha)));
+            else cell = min((uint32_t)(fr * (float)(1u << bp.cells_log2)), (1u << bp.cells_log2) - 1u);
+        }
         key = (key << bp.cells_log2) | cell;
     }
     return key;

@@ -160,3 +160,35 @@ def synth_scene(n: int, seed: int = 2, model_seed: int = 1, model_profile: int =
     # fixed pseudo-random order so that reference-point shards see the same mix of surfaces
     order = np.argsort(uniform(seed, 70, m), kind="stable")
     return s[order].astype(np.float32)
+
+
+def library_pose(k: int, seed: int = 3) -> np.ndarray:
+    """Ground-truth pose of library model k in synth_library_scene: rotation from the seed, instances on a 4 x 2 grid."""
+    T = gt_pose(seed * 1000 + k)
+    T[:3, 3] = (-0.6 + 0.4 * (k % 4), -0.25 + 0.35 * (k // 4), 0.9 + 0.1 * (k % 3))
+    return T
+
+
+def synth_library_scene(n: int = 1 << 20, seed: int = 3, n_models: int = 8, model_points: int = 2000) -> np.ndarray:
+    """(n, 6) float32 scene of BASELINE config 4: n = 1024 x 1024 points (the Azure Kinect WFOV-unbinned depth
+    size, include/StaticImageProperties.h:65-66 of the reference) holding one camera-facing instance of each of
+    the n_models library models synth_model(model_points, 10 + k, profile k) under library_pose(k) — 1.5 % of
+    the points each — plus the ground plane, walls and clutter of synth_scene, with the same sensor noise."""
+    per_model = int(round(0.015 * n))
+    rest = synth_scene(n - n_models * per_model, seed, model_fraction=0.0).astype(np.float64)
+    parts = [rest]
+    for k in range(n_models):
+        T = library_pose(k, seed)
+        cand = synth_model(4 * per_model + 64, 10 + k + 7919, k).astype(np.float64)
+        p = cand[:, :3] @ T[:3, :3].T + T[:3, 3]
+        nn = cand[:, 3:] @ T[:3, :3].T
+        sel = np.flatnonzero(np.einsum("ij,ij->i", nn, -p) > 0)[:per_model]
+        inst = np.concatenate([p[sel], nn[sel]], axis=1)
+        m = inst.shape[0]
+        for c in range(3):
+            inst[:, c] += 0.0005 * normal(seed, 200 + 10 * k + c, m)
+        parts.append(inst)
+    s = np.concatenate(parts, axis=0)
+    s = s[: n] if s.shape[0] >= n else np.concatenate([s, rest[: n - s.shape[0]]], axis=0)
+    order = np.argsort(uniform(seed, 71, s.shape[0]), kind="stable")
+    return s[order].astype(np.float32)

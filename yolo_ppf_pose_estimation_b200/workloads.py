@@ -5,6 +5,8 @@
   c2_5mm  2 009-point bottle vs the same scene (needs two accumulator slices)
   c3  synthetic 10 000-point model vs 100 000-point scene, rate 1
   c3s a quarter-scale c3 (2 500 / 25 000) for quick runs
+  c4  synthetic 8-model library (2 000 pts each) vs a 1 048 576-point scene, reference rate 20, one align per model
+  c4s an eighth-scale c4 scene (131 072 pts) for quick runs
 
 c1/c2 clouds are the reference's own data frozen under tests/golden (tools/make_fixtures.py: the
 bottle PLY voxel-averaged, data/1_depth.exr back-projected with the reference's intrinsics because
@@ -40,6 +42,10 @@ class Workload:
     dist_step: np.float32 = DIST_STEP
     pos_thr: np.float32 = POS_THR
     rot_thr: np.float32 = ROT_THR
+    models: list = None  # model library (c4); None = the single `model`
+
+    def library(self):
+        return self.models if self.models else [self.model]
 
     @property
     def n_ref(self):
@@ -69,4 +75,10 @@ def load(name: str) -> Workload:
     if name == "c3s":
         return Workload("c3s", "synthetic 2 500-pt model vs 25 000-pt scene, all reference points",
                         synth.synth_model(2500, 1), synth.synth_scene(25000, 2, model_seed=1), 1, "synthetic")
+    if name in ("c4", "c4s"):
+        n_s, rate = ((1 << 20), 20) if name == "c4" else ((1 << 17), 20)
+        models = [synth.synth_model(2000, 10 + k, k) for k in range(8)]
+        return Workload(name, f"synthetic 8-model library (2 000 pts each) vs {n_s}-pt scene (1024 x 1024 WFOV size), "
+                              f"every 20th scene point a reference (the reference's 1/0.05), one align per model",
+                        models[0], synth.synth_library_scene(n_s, 3), rate, "synthetic", models=models)
     raise ValueError(f"unknown workload {name!r}")
