@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """bench.py — scene point-pairs voted per second (and ms per 6-D pose) of the PPF hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c3] [--impl reference]
+
+Default workload = c3, the configuration BASELINE.json's metric and target are quoted on ("10k-point model vs
+100k-point scene, every scene point as reference, sharded across 1/2/4/8 B200"; north_star: ">= 50x the host-CPU
+PCL PPFRegistration throughput on a 100k-point scene at 1 B200"); it fits one GPU.  --workload c1 | c2 | c2_5mm |
+c3s | c4 | c4s select the other BASELINE configurations (workloads.py); c2 is the reference's own fixture.
 
 A step is one PPFRegistration::align of the workload's scene against its (pre-built, resident)
 model table: K3 voting over this rank's shard of scene reference points, K3b pose assembly, the
@@ -428,10 +433,10 @@ def run_b200(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default="c3", help="c1 | c2 | c2_5mm | c3 (default) | c3s | c4 | c4s (workloads.py)")
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="reference points in the CPU sample (0 = sized from a timing probe: ~15 s of CPU work per pass)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

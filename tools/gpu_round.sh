@@ -6,15 +6,18 @@ O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $O/pytest_$TAG.log
 grep -q failed $O/pytest_$TAG.log && exit 1
-python bench.py --steps 10 --warmup 3 > $O/bench_c2_$TAG.json 2> $O/bench_c2_$TAG.err; tail -c 600 $O/bench_c2_$TAG.err
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_c2_ref_$TAG.json 2> $O/bench_c2_ref_$TAG.err
+python bench.py > $O/bench_c3_$TAG.json 2> $O/bench_c3_$TAG.err; tail -c 600 $O/bench_c3_$TAG.err
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_c3_ref_$TAG.json 2> $O/bench_c3_ref_$TAG.err
+python bench.py --workload c2 --steps 10 --warmup 3 > $O/bench_c2_$TAG.json 2> $O/bench_c2_$TAG.err; tail -c 600 $O/bench_c2_$TAG.err
+timeout 300 python bench.py --workload c2 --impl reference --steps 3 --warmup 1 > $O/bench_c2_ref_$TAG.json 2> $O/bench_c2_ref_$TAG.err
 timeout 300 python bench.py --workload c1 --steps 10 --warmup 3 > $O/bench_c1_$TAG.json 2> $O/bench_c1_$TAG.err
 timeout 300 python bench.py --workload c2_5mm --steps 3 --warmup 3 --no-cpu > $O/bench_c2_5mm_$TAG.json 2> $O/bench_c2_5mm_$TAG.err
-timeout 900 python bench.py --workload c3 --steps 2 --warmup 3 > $O/bench_c3_$TAG.json 2> $O/bench_c3_$TAG.err; tail -c 600 $O/bench_c3_$TAG.err
+timeout 300 python bench.py --workload c4 --steps 2 --warmup 3 > $O/bench_c4_$TAG.json 2> $O/bench_c4_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_launches_$TAG.log 2>&1
 bash tools/gpu_prof.sh $TAG c2
-for f in c2 c2_ref c1 c2_5mm c3; do python - <<PY
+bash tools/gpu_prof.sh $TAG c3
+for f in c3 c3_ref c2 c2_ref c1 c2_5mm c4; do python - <<PY
 import json
 try:
     d = json.load(open("$O/bench_${f}_$TAG.json"))
