@@ -1,16 +1,20 @@
 // radix_sort.cu — hand-written stable LSD radix sort (8-bit digits) for sm_100a.
 //
 // Used by K2 (order the N_m^2 model pairs by packed feature key -> CSR buckets, replacing the
-// unordered_multimap of [PCL] registration/src/ppf_registration.cpp) and by K4 (order pose
-// hypotheses by votes, replacing the std::sort of clusterPoses).
+// unordered_multimap of [PCL] registration/src/ppf_registration.cpp), by the scene grid and by K4
+// (order pose hypotheses by votes, replacing the std::sort of clusterPoses).
 //
-// Layout: the input is cut into warp segments of seg_len consecutive elements (128..2048).  One warp owns one
-// segment in both the histogram and the scatter kernel, walking it in rounds of 32 coalesced
-// elements; lanes holding the same digit find each other with match.any, so ranks inside a
-// round are stable by lane order, rounds are sequential, segments are ordered by the column
-// scan — the sort is stable without any atomics.
-//   hist[seg][256]  (segment-major: coalesced 1 KB rows)  --column scan-->  global bases
-// HBM traffic per pass: keys read twice, payloads read once, everything written once.
+// One pass = tile histogram -> column scan -> tile scatter.  A tile is WARPS x ROUNDS x 32 consecutive
+// elements (4096 for large inputs, 512 for small ones so that every SM has a block to run); element
+// order inside a tile is (warp, round, lane).
+//   hist     per-tile digit counts with shared-memory atomics -> hist[tile][256] (coalesced 1 KB rows)
+//   scan     column scan over tiles (three small kernels) -> global base of every (tile, digit)
+//   scatter  the tile is sorted locally first: per-warp digit counts (match.any), a (digit, warp) scan in
+//            shared memory, stable ranks by (warp, round, lane), keys and payloads staged in shared memory
+//            at their tile-local sorted position; then the block copies the tile out digit run by digit
+//            run — consecutive threads write consecutive addresses instead of 32 scattered 4-byte stores.
+// No global atomics; stable.  HBM traffic per pass: keys read twice, payloads read once, everything
+// written once, in runs of (tile / 256 ... tile) elements.
 #include "ppf_common.cuh"
 
 namespace b200ppf {
@@ -18,37 +22,28 @@ namespace b200ppf {
 namespace {
 
 constexpr int RADIX = 256;
-constexpr int SEG_MAX = 2048;       // elements per warp segment (large inputs)
-constexpr int SEG_MIN = 128;        // small inputs get short segments so that every SM has warps to run
-constexpr int WARPS = 8;            // warps (segments) per block
+constexpr int WARPS = 8;            // warps per block / tile
+constexpr int ROUNDS_BIG = 16;      // 4096-element tiles
+constexpr int ROUNDS_SMALL = 2;     // 512-element tiles
 constexpr int SCAN_CHUNK = 256;     // histogram rows per column-scan chunk
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+template <int ROUNDS>
 __global__ void __launch_bounds__(WARPS * 32)
-radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t nseg, uint32_t seg_len, int shift,
-                  uint32_t *__restrict__ hist) {
-    __shared__ uint32_t cnt[WARPS][RADIX];
-    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t seg = blockIdx.x * WARPS + w;
-    for (int d = lane; d < RADIX; d += 32) cnt[w][d] = 0;
-    __syncwarp();
-    if (seg >= nseg) return;
-    const uint32_t begin = seg * seg_len;
-    const uint32_t end = min(n, begin + seg_len);  // begin < n, no overflow: n < 2^32 - SEG_MAX
-    for (uint32_t base = begin; base < end; base += 32) {
-        uint32_t idx = base + lane;
-        bool valid = idx < end;
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
-        if (valid) {
-            uint32_t digit = (keys[idx] >> shift) & (RADIX - 1);
-            uint32_t peers = __match_any_sync(mask, digit);
-            if ((uint32_t)(__ffs(peers) - 1) == lane) cnt[w][digit] += __popc(peers);
-        }
-        __syncwarp();
-    }
-    uint32_t *row = hist + (size_t)seg * RADIX;
-    for (int d = lane; d < RADIX; d += 32) row[d] = cnt[w][d];
+radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t *__restrict__ hist) {
+    constexpr uint32_t TILE = WARPS * ROUNDS * 32;
+    __shared__ uint32_t cnt[RADIX];
+    for (int d = threadIdx.x; d < RADIX; d += WARPS * 32) cnt[d] = 0;
+    __syncthreads();
+    const uint32_t begin = blockIdx.x * TILE;
+    const uint32_t end = min(n, begin + TILE);  // begin < n, no overflow: n < 2^32 - TILE
+#pragma unroll 4
+    for (uint32_t idx = begin + threadIdx.x; idx < end; idx += WARPS * 32)
+        atomicAdd(&cnt[(keys[idx] >> shift) & (RADIX - 1)], 1u);
+    __syncthreads();
+    uint32_t *row = hist + (size_t)blockIdx.x * RADIX;
+    for (int d = threadIdx.x; d < RADIX; d += WARPS * 32) row[d] = cnt[d];
 }
 
 // column scan, step 1: per chunk of rows, per digit totals
@@ -111,76 +106,142 @@ radix_col_apply_kernel(uint32_t *__restrict__ hist, uint32_t nseg, const uint32_
     }
 }
 
-template <bool IOTA, bool HAS_V0, bool HAS_V1>
+template <int ROUNDS, bool IOTA, bool HAS_V0, bool HAS_V1>
 __global__ void __launch_bounds__(WARPS * 32)
 radix_scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ v0,
-                     const uint32_t *__restrict__ v1, uint32_t n, uint32_t nseg, uint32_t seg_len, int shift,
-                     const uint32_t *__restrict__ hist, uint32_t *__restrict__ keys_out,
-                     uint32_t *__restrict__ v0_out, uint32_t *__restrict__ v1_out) {
-    __shared__ uint32_t base[WARPS][RADIX];
-    const uint32_t w = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t seg = blockIdx.x * WARPS + w;
-    if (seg >= nseg) return;
-    const uint32_t *row = hist + (size_t)seg * RADIX;
-    for (int d = lane; d < RADIX; d += 32) base[w][d] = row[d];
-    __syncwarp();
-    const uint32_t begin = seg * seg_len;
-    const uint32_t end = min(n, begin + seg_len);
+                     const uint32_t *__restrict__ v1, uint32_t n, int shift, const uint32_t *__restrict__ hist,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ v0_out, uint32_t *__restrict__ v1_out) {
+    constexpr uint32_t TILE = WARPS * ROUNDS * 32;
+    extern __shared__ uint32_t smem[];
+    uint32_t *s_key = smem;                                  // [TILE] tile-local sorted order
+    uint32_t *s_v0 = s_key + TILE;                           // [TILE]
+    uint32_t *s_v1 = s_v0 + (HAS_V0 ? TILE : 0);             // [TILE]
+    uint32_t *run = s_v1 + (HAS_V1 ? TILE : 0);              // [WARPS][RADIX] next local slot of (warp, digit)
+    uint32_t *dstart = run + WARPS * RADIX;                  // [RADIX] first local slot of a digit
+    uint32_t *gbase = dstart + RADIX;                        // [RADIX] global base of (this tile, digit)
+    __shared__ uint32_t s_tot[8];
+
+    const uint32_t tid = threadIdx.x, w = tid >> 5, lane = lane_id();
+    const uint32_t begin = blockIdx.x * TILE;
+    const uint32_t end = min(n, begin + TILE);
     const uint32_t lt = (1u << lane) - 1u;
-    for (uint32_t b = begin; b < end; b += 32) {
-        uint32_t idx = b + lane;
-        bool valid = idx < end;
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
-        uint32_t key = 0, digit = 0, peers = 0, pos = 0;
+    for (uint32_t k = tid; k < WARPS * RADIX; k += WARPS * 32) run[k] = 0;
+    gbase[tid] = hist[(size_t)blockIdx.x * RADIX + tid];
+    __syncthreads();
+
+    // 1. keys into registers; per-warp digit counts
+    uint32_t key[ROUNDS];
+    uint32_t *mine = run + w * RADIX;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint32_t idx = begin + (w * ROUNDS + r) * 32 + lane;
+        const bool valid = idx < end;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
+        key[r] = 0;
         if (valid) {
-            key = keys[idx];
-            digit = (key >> shift) & (RADIX - 1);
+            key[r] = keys[idx];
+            const uint32_t digit = (key[r] >> shift) & (RADIX - 1);
+            const uint32_t peers = __match_any_sync(mask, digit);
+            if ((uint32_t)(__ffs(peers) - 1) == lane) mine[digit] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // 2. (digit, warp) exclusive scan: thread d owns digit d
+    {
+        uint32_t c[WARPS], tot = 0;
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ++ww) {
+            c[ww] = run[ww * RADIX + tid];
+            tot += c[ww];
+        }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_tot[w] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ++ww) before += (ww < (int)w) ? s_tot[ww] : 0u;
+        uint32_t excl = before + incl - tot;
+        dstart[tid] = excl;
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ++ww) {
+            run[ww * RADIX + tid] = excl;
+            excl += c[ww];
+        }
+    }
+    __syncthreads();
+    // 3. stable tile-local positions; stage keys and payloads in sorted order
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint32_t idx = begin + (w * ROUNDS + r) * 32 + lane;
+        const bool valid = idx < end;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
+        uint32_t digit = 0, peers = 0, pos = 0;
+        if (valid) {
+            digit = (key[r] >> shift) & (RADIX - 1);
             peers = __match_any_sync(mask, digit);
-            pos = base[w][digit] + __popc(peers & lt);
+            pos = mine[digit] + __popc(peers & lt);
         }
         __syncwarp();
-        if (valid && (uint32_t)(__ffs(peers) - 1) == lane) base[w][digit] += __popc(peers);
+        if (valid && (uint32_t)(__ffs(peers) - 1) == lane) mine[digit] += __popc(peers);
         __syncwarp();
         if (valid) {
-            keys_out[pos] = key;
-            if (HAS_V0) v0_out[pos] = IOTA ? idx : v0[idx];
-            if (HAS_V1) v1_out[pos] = v1[idx];
+            s_key[pos] = key[r];
+            if (HAS_V0) s_v0[pos] = IOTA ? idx : v0[idx];
+            if (HAS_V1) s_v1[pos] = v1[idx];
         }
+    }
+    __syncthreads();
+    // 4. copy out: local slot p of digit d goes to gbase[d] + (p - dstart[d]); runs are contiguous
+    const uint32_t count = end - begin;
+    for (uint32_t p = tid; p < count; p += WARPS * 32) {
+        const uint32_t k = s_key[p];
+        const uint32_t dg = (k >> shift) & (RADIX - 1);
+        const uint32_t o = gbase[dg] + (p - dstart[dg]);
+        keys_out[o] = k;
+        if (HAS_V0) v0_out[o] = s_v0[p];
+        if (HAS_V1) v1_out[o] = s_v1[p];
     }
 }
 
 }  // namespace
 
 // v0_iota: on entry v0 is taken to be the identity permutation 0..n-1 (its contents are not read).
-int radix_sort_u32(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_t *v0, uint32_t *v0_alt,
-                   uint32_t *v1, uint32_t *v1_alt, size_t n, int bits, bool v0_iota, bool *result_in_alt) {
-    *result_in_alt = false;
-    if (n == 0 || bits <= 0) return B200PPF_OK;
-    if (n >= 0xFFFFFFFFull - SEG_MAX) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "radix sort: more than 2^32 elements");
-    // segment length: ~16 warps per SM for small inputs, SEG_MAX once there is enough work
-    uint32_t seg_len = (uint32_t)(n / ((size_t)ctx->sm_count * 16));
-    seg_len = (seg_len + 31u) & ~31u;
-    seg_len = seg_len < SEG_MIN ? SEG_MIN : (seg_len > SEG_MAX ? SEG_MAX : seg_len);
-    const uint32_t nseg = (uint32_t)((n + seg_len - 1) / seg_len);
-    const uint32_t nblocks = (nseg + WARPS - 1) / WARPS;
-    const uint32_t nchunks = (nseg + SCAN_CHUNK - 1) / SCAN_CHUNK;
+namespace {
+
+template <int ROUNDS>
+int radix_sort_impl(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_t *v0, uint32_t *v0_alt, uint32_t *v1,
+                    uint32_t *v1_alt, size_t n, int bits, bool v0_iota, bool *result_in_alt) {
+    constexpr uint32_t TILE = WARPS * ROUNDS * 32;
+    const uint32_t ntiles = (uint32_t)((n + TILE - 1) / TILE);
+    const uint32_t nchunks = (ntiles + SCAN_CHUNK - 1) / SCAN_CHUNK;
     uint32_t *hist = nullptr, *chunk_tot = nullptr, *digit_base = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&hist, (size_t)nseg * RADIX * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&hist, (size_t)ntiles * RADIX * sizeof(uint32_t), ctx->stream));
     PPF_CUDA(ctx, cudaMallocAsync(&chunk_tot, (size_t)nchunks * RADIX * sizeof(uint32_t), ctx->stream));
     PPF_CUDA(ctx, cudaMallocAsync(&digit_base, RADIX * sizeof(uint32_t), ctx->stream));
 
     const bool has_v0 = v0 != nullptr && v0_alt != nullptr, has_v1 = v1 != nullptr && v1_alt != nullptr;
     bool iota = has_v0 && v0_iota;
+    const size_t smem = ((size_t)TILE * (1 + (has_v0 ? 1 : 0) + (has_v1 ? 1 : 0)) + WARPS * RADIX + 2 * RADIX) * sizeof(uint32_t);
     uint32_t *ki = keys, *ko = keys_alt, *v0i = v0, *v0o = v0_alt, *v1i = v1, *v1o = v1_alt;
     bool in_alt = false;
     for (int shift = 0; shift < bits; shift += 8) {
-        PPF_LAUNCH(ctx, radix_hist_kernel, nblocks, WARPS * 32, 0, ki, (uint32_t)n, nseg, seg_len, shift, hist);
-        PPF_LAUNCH(ctx, radix_col_reduce_kernel, nchunks, RADIX, 0, hist, nseg, chunk_tot);
+        PPF_LAUNCH(ctx, radix_hist_kernel<ROUNDS>, ntiles, WARPS * 32, 0, ki, (uint32_t)n, shift, hist);
+        PPF_LAUNCH(ctx, radix_col_reduce_kernel, nchunks, RADIX, 0, hist, ntiles, chunk_tot);
         PPF_LAUNCH(ctx, radix_col_scan_chunks_kernel, 1, RADIX, 0, chunk_tot, nchunks, digit_base);
-        PPF_LAUNCH(ctx, radix_col_apply_kernel, nchunks, RADIX, 0, hist, nseg, chunk_tot, digit_base);
-#define SCATTER(I, A, B)                                                                                      \
-    PPF_LAUNCH(ctx, (radix_scatter_kernel<I, A, B>), nblocks, WARPS * 32, 0, ki, v0i, v1i, (uint32_t)n, nseg, \
-               seg_len, shift, hist, ko, v0o, v1o)
+        PPF_LAUNCH(ctx, radix_col_apply_kernel, nchunks, RADIX, 0, hist, ntiles, chunk_tot, digit_base);
+#define SCATTER(I, A, B)                                                                                                \
+    do {                                                                                                                 \
+        PPF_CUDA(ctx, cudaFuncSetAttribute(radix_scatter_kernel<ROUNDS, I, A, B>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+        PPF_LAUNCH(ctx, (radix_scatter_kernel<ROUNDS, I, A, B>), ntiles, WARPS * 32, smem, ki, v0i, v1i, (uint32_t)n,    \
+                   shift, hist, ko, v0o, v1o);                                                                           \
+    } while (0)
         if (has_v0 && has_v1) {
             if (iota) SCATTER(true, true, true); else SCATTER(false, true, true);
         } else if (has_v0) {
@@ -203,6 +264,20 @@ int radix_sort_u32(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_
     PPF_CUDA(ctx, cudaFreeAsync(digit_base, ctx->stream));
     *result_in_alt = in_alt;
     return B200PPF_OK;
+}
+
+}  // namespace
+
+int radix_sort_u32(b200ppf_ctx *ctx, uint32_t *keys, uint32_t *keys_alt, uint32_t *v0, uint32_t *v0_alt,
+                   uint32_t *v1, uint32_t *v1_alt, size_t n, int bits, bool v0_iota, bool *result_in_alt) {
+    *result_in_alt = false;
+    if (n == 0 || bits <= 0) return B200PPF_OK;
+    if (n >= 0xFFFFFFFFull - WARPS * ROUNDS_BIG * 32)
+        return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "radix sort: more than 2^32 elements");
+    // 4096-element tiles once every SM gets a few of them, 512-element tiles for small inputs
+    if (n >= (size_t)ctx->sm_count * 4 * WARPS * ROUNDS_BIG * 32)
+        return radix_sort_impl<ROUNDS_BIG>(ctx, keys, keys_alt, v0, v0_alt, v1, v1_alt, n, bits, v0_iota, result_in_alt);
+    return radix_sort_impl<ROUNDS_SMALL>(ctx, keys, keys_alt, v0, v0_alt, v1, v1_alt, n, bits, v0_iota, result_in_alt);
 }
 
 }  // namespace b200ppf
