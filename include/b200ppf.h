@@ -41,6 +41,7 @@ extern "C" {
 #define B200PPF_ERR_NOMEM (-3)       /* device or host allocation failed */
 #define B200PPF_ERR_STATE (-4)       /* object used before it is ready / size mismatch */
 #define B200PPF_ERR_UNSUPPORTED (-5) /* e.g. discretisation too fine for 32-bit keys */
+#define B200PPF_ERR_IO (-6)          /* table file missing, truncated, corrupt or of another version */
 
 /* feature functor: PCL_PFH is what PCL's PPF classes execute ([PCL] features/src/pfh.cpp
  * computePairFeatures); DROST_* are the textbook tuple ([PCL] features/src/ppf.cpp
@@ -147,6 +148,16 @@ int b200ppf_table_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host)
 int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *offsets,
                          uint32_t *entry_i, uint32_t *entry_j, float *entry_alpha_m);
 void b200ppf_table_free(b200ppf_table *t);
+
+/* Trained-model persistence.  The reference never trains at run time: it deserialises a detector it
+ * trained offline (include/CloudProcessing.h:242-258 detector.write(FileStorage) -> XML, :106-121
+ * detector.read(fsload.root()), CLI argument 6 of src/YOLO_cropping_ppf_test.cpp:48,117).  save writes
+ * the device table — parameters, bucket and phase-cell offsets, entry arrays — to one little-endian
+ * binary file with a magic, a format version and a 64-bit checksum; load rebuilds it on ctx's device
+ * without re-running K1/K2 and fails with B200PPF_ERR_IO on a missing, truncated, corrupt or
+ * other-version file and with B200PPF_ERR_STATE when the file's feature / alpha mode differs from ctx's. */
+int b200ppf_table_save(b200ppf_ctx *ctx, const b200ppf_table *t, const char *path);
+int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out);
 
 /* ---- K3: [PCL] registration/impl/ppf_registration.hpp computeTransformation, voting loop - */
 /* One hypothesis per scene reference point ref_first + k*ref_step, k < ref_count (the slice a

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstddef>
 #include <utility>
+#include <string>
 #include <vector>
 
 #include "../b200_context.h"
@@ -76,6 +77,42 @@ public:
         }
         b200ppf_table_info info;
         b200ppf_table_get_info(table_.h, &info);
+        max_dist_ = info.max_dist;
+        internals_initialized_ = true;
+        return true;
+    }
+
+    // extension: trained-model persistence — what the reference does with detector.write(FileStorage) /
+    // detector.read() (include/CloudProcessing.h:242-258, :106-121).  load() replaces the table without
+    // re-running PPFEstimation; the discretisation steps become the file's; alpha_m_ stays empty.
+    bool saveTrained(const std::string &path) const {
+        b200ppf_ctx *ctx = b200::defaultContext();
+        if (!ctx || !internals_initialized_) {
+            PCL_ERROR("[pcl::PPFHashMapSearch::saveTrained] the search object has no table\n");
+            return false;
+        }
+        if (b200ppf_table_save(ctx, table_.h, path.c_str()) != B200PPF_OK) {
+            PCL_ERROR("[pcl::PPFHashMapSearch::saveTrained] %s\n", b200ppf_last_error(ctx));
+            return false;
+        }
+        return true;
+    }
+    bool loadTrained(const std::string &path) {
+        internals_initialized_ = false;
+        table_.reset();
+        alpha_m_.clear();
+        max_dist_ = -1.0f;
+        b200ppf_ctx *ctx = b200::defaultContext();
+        if (!ctx) return false;
+        if (b200ppf_table_load(ctx, path.c_str(), &table_.h) != B200PPF_OK) {
+            PCL_ERROR("[pcl::PPFHashMapSearch::loadTrained] %s\n", b200ppf_last_error(ctx));
+            table_.reset();
+            return false;
+        }
+        b200ppf_table_info info;
+        b200ppf_table_get_info(table_.h, &info);
+        angle_discretization_step_ = info.angle_step;
+        distance_discretization_step_ = info.dist_step;
         max_dist_ = info.max_dist;
         internals_initialized_ = true;
         return true;

@@ -80,5 +80,21 @@ int main(int argc, char **argv) {
     std::printf("bucket_of_pair_0_1 %zu first %zu %zu\n", nn.size(), nn.empty() ? 0 : nn[0].first,
                 nn.empty() ? 0 : nn[0].second);
     std::printf("output0 %.9g %.9g %.9g\n", cloud_output[0].x, cloud_output[0].y, cloud_output[0].z);
+
+    // the reference's run-time order (src/YOLO_cropping_ppf_test.cpp:117-122): LoadTrainedDetector, then match
+    const std::string file = dir + "/trained.b200ppf";
+    pcl::PPFHashMapSearch::Ptr loaded(new pcl::PPFHashMapSearch());
+    if (!hashmap_search->saveTrained(file) || !loaded->loadTrained(file)) return 4;
+    pcl::PPFRegistration<pcl::PointNormal, pcl::PointNormal> again;
+    again.setSceneReferencePointSamplingRate(5);
+    again.setSearchMethod(loaded);
+    again.setInputSource(model);
+    again.setInputTarget(scene);
+    pcl::PointCloud<pcl::PointNormal> out2;
+    again.align(out2);
+    const bool same = again.hasConverged() && again.getFinalTransformation() == mat &&
+                      loaded->getModelDiameter() == hashmap_search->getModelDiameter() &&
+                      loaded->getDistanceDiscretizationStep() == 0.01f;
+    std::printf("reloaded_table_same_pose %d\n", same ? 1 : 0);
     return 0;
 }

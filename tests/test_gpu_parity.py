@@ -193,6 +193,40 @@ print('SLICED_OK')
     assert "SLICED_OK" in r.stdout, r.stdout + r.stderr
 
 
+def test_k2_table_save_load(tmp_path, ctx, dev_bottle, dev_crop, table_fused):
+    """LoadTrainedDetector path: a saved table reloads to the same buckets and the same votes; corrupt,
+    truncated, foreign and mode-mismatched files are refused."""
+    from yolo_ppf_pose_estimation_b200 import capi
+    path = str(tmp_path / "bottle.b200ppf")
+    table_fused.save(path)
+    t2 = ctx.table_load(path)
+    a, b = table_fused.info, t2.info
+    for f, _ in capi.TableInfo._fields_:
+        va, vb = getattr(a, f), getattr(b, f)
+        assert (list(va) == list(vb)) if hasattr(va, "__len__") else (va == vb), f
+    ba, bb = parity.table_buckets(table_fused), parity.table_buckets(t2)
+    assert ba.keys() == bb.keys()
+    for k in ba:
+        assert all(np.array_equal(x.view(np.uint32), y.view(np.uint32)) for x, y in zip(ba[k], bb[k]))
+    h1 = ctx.vote(dev_bottle, table_fused, dev_crop, 0, 5)
+    h2 = ctx.vote(dev_bottle, t2, dev_crop, 0, 5)
+    assert h1.tobytes() == h2.tobytes()
+    raw = open(path, "rb").read()
+    bad = tmp_path / "bad.b200ppf"
+    for blob, msg in ((raw[:len(raw) // 2], "truncated"), (raw + b"x", "trailing"), (b"PLY" + raw[3:], "not a b200ppf"),
+                      (raw[:-9] + bytes([raw[-9] ^ 1]) + raw[-8:], "checksum")):
+        bad.write_bytes(blob)
+        with pytest.raises(capi.B200PPFError) as e:
+            ctx.table_load(str(bad))
+        assert msg in str(e.value), (msg, str(e.value))
+    with pytest.raises(capi.B200PPFError):
+        ctx.table_load(str(tmp_path / "missing.b200ppf"))
+    cb = capi.Context(0, alpha_mode=capi.ALPHA_MODE_B)
+    with pytest.raises(capi.B200PPFError) as e:
+        cb.table_load(path)
+    assert "mode differs" in str(e.value)
+
+
 # ---- K3 ------------------------------------------------------------------------------------------
 
 REFS = (0, 5, 250, 600, 933)
@@ -602,3 +636,4 @@ def test_cpp_pcl_shim_end_to_end(tmp_path, ctx, bottle, scene_crop, dev_bottle, 
     assert np.array_equal(out0, ctx.transform(dev_bottle, final)[0])
     bucket = lines[5].split()
     assert int(bucket[1]) >= 1 and (int(bucket[3]), int(bucket[4])) <= (0, 1)
+    assert lines[7].split() == ["reloaded_table_same_pose", "1"]

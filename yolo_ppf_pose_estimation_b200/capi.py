@@ -67,6 +67,8 @@ SYMBOLS = {
     "b200ppf_table_alpha_m": (_i, [_vp, _vp, _vp]),
     "b200ppf_table_export": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b200ppf_table_free": (None, [_vp]),
+    "b200ppf_table_save": (_i, [_vp, _vp, C.c_char_p]),
+    "b200ppf_table_load": (_i, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "b200ppf_vote": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "b200ppf_vote_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "b200ppf_vote_stats": (_i, [_vp, _vp]),
@@ -214,6 +216,12 @@ class Context:
                                                         np.float32(dist_step), C.byref(h)))
         return Table(self, h)
 
+    def table_load(self, path) -> "Table":
+        """LoadTrainedDetector: rebuild a saved table on this context's device (no K1/K2)."""
+        h = C.c_void_p()
+        self.check(lib().b200ppf_table_load(self._h, os.fsencode(path), C.byref(h)))
+        return Table(self, h)
+
     # ---- K3 -----------------------------------------------------------------------------------
     def vote(self, model, table, scene, ref_first=0, ref_step=1, ref_count=None):
         if ref_count is None:
@@ -350,6 +358,9 @@ class Table(_Handle):
         ti = TableInfo()
         self.ctx.check(lib().b200ppf_table_get_info(self._h, C.byref(ti)))
         return ti
+
+    def save(self, path):
+        self.ctx.check(lib().b200ppf_table_save(self.ctx._h, self._h, os.fsencode(path)))
 
     def query(self, f1, f2, f3, f4):
         cap = 4096

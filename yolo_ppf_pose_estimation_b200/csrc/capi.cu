@@ -1,6 +1,8 @@
 // capi.cu — the extern "C" surface declared in include/b200ppf.h.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstring>
 #include <mutex>
 #include <new>
 #include <utility>
@@ -380,6 +382,163 @@ int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *off
         if (entry_j) entry_j[e] = idx[e] % n;
     }
     for (size_t e = 0; e < ent.size(); ++e) entry_alpha_m[e] = ent[e];
+    return B200PPF_OK;
+}
+
+/* ---- table file ------------------------------------------------------------------------------- */
+namespace {
+
+constexpr uint64_t TABLE_MAGIC = 0x4C42543030325042ull;  // "BP200TBL" little-endian
+constexpr uint32_t TABLE_FORMAT = 2;                      // 2: phase-sorted buckets, hot words
+
+struct TableFileHeader {
+    uint64_t magic;
+    uint32_t format, header_bytes;
+    uint32_t feature_mode, alpha_mode;
+    uint64_t n_offsets, n_sub_offsets, n_entries;  // array lengths in 32-bit words (entries: without the padding)
+    uint64_t checksum;                              // over info, kp, bp and the six arrays, in file order
+    b200ppf_table_info info;
+    b200ppf::KeyParams kp;
+    b200ppf::BinParams bp;
+};
+
+// 64-bit multiplicative checksum over 8-byte words (tail bytes zero-extended)
+uint64_t mix_bytes(uint64_t h, const void *data, size_t bytes) {
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    size_t k = 0;
+    for (; k + 8 <= bytes; k += 8) {
+        uint64_t w;
+        memcpy(&w, p + k, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    if (k < bytes) {
+        uint64_t w = 0;
+        memcpy(&w, p + k, bytes - k);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    return h;
+}
+
+struct FileCloser {
+    FILE *f;
+    ~FileCloser() {
+        if (f) fclose(f);
+    }
+};
+
+}  // namespace
+
+int b200ppf_table_save(b200ppf_ctx *ctx, const b200ppf_table *t, const char *path) {
+    CHECK_CTX(ctx);
+    if (!t || !path) return fail_msg(ctx, B200PPF_ERR_INVALID, "table save: null argument");
+    DeviceGuard guard(ctx->device);
+    TableFileHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = TABLE_MAGIC;
+    h.format = TABLE_FORMAT;
+    h.header_bytes = (uint32_t)sizeof(h);
+    h.feature_mode = (uint32_t)t->feature_mode;
+    h.alpha_mode = (uint32_t)t->bp.mode;
+    h.info = t->info;
+    h.kp = t->kp;
+    h.bp = t->bp;
+    const uint64_t total_keys = (uint64_t)t->info.key_space * t->info.n_slices;
+    h.n_offsets = total_keys + 1;
+    h.n_sub_offsets = t->sub_offsets ? (total_keys << t->bp.cells_log2) + 1 : 0;
+    h.n_entries = t->info.n_entries;
+    const uint32_t *arrays[6] = {t->offsets, t->sub_offsets, t->entry_w, t->entry_am,
+                                 reinterpret_cast<const uint32_t *>(t->entry_alpha), t->entry_idx};
+    const uint64_t lengths[6] = {h.n_offsets, h.n_sub_offsets, h.n_entries, h.n_entries, h.n_entries, h.n_entries};
+    std::vector<std::vector<uint32_t>> host(6);
+    for (int a = 0; a < 6; ++a) {
+        host[a].resize(lengths[a]);
+        if (lengths[a])
+            PPF_CUDA(ctx, cudaMemcpyAsync(host[a].data(), arrays[a], lengths[a] * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+    }
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t sum = mix_bytes(0x42323030u, &h.info, sizeof(h.info));
+    sum = mix_bytes(sum, &h.kp, sizeof(h.kp));
+    sum = mix_bytes(sum, &h.bp, sizeof(h.bp));
+    for (int a = 0; a < 6; ++a) sum = mix_bytes(sum, host[a].data(), host[a].size() * sizeof(uint32_t));
+    h.checksum = sum;
+    FileCloser fc{fopen(path, "wb")};
+    if (!fc.f) return fail_msg(ctx, B200PPF_ERR_IO, "table save: cannot open the file for writing");
+    bool ok = fwrite(&h, sizeof(h), 1, fc.f) == 1;
+    for (int a = 0; a < 6 && ok; ++a)
+        if (!host[a].empty()) ok = fwrite(host[a].data(), sizeof(uint32_t), host[a].size(), fc.f) == host[a].size();
+    ok = ok && fflush(fc.f) == 0;
+    if (!ok) return fail_msg(ctx, B200PPF_ERR_IO, "table save: short write");
+    return B200PPF_OK;
+}
+
+int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out) {
+    CHECK_CTX(ctx);
+    if (!path || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "table load: null argument");
+    *out = nullptr;
+    DeviceGuard guard(ctx->device);
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) return fail_msg(ctx, B200PPF_ERR_IO, "table load: cannot open the file");
+    TableFileHeader h;
+    if (fread(&h, sizeof(h), 1, fc.f) != 1) return fail_msg(ctx, B200PPF_ERR_IO, "table load: truncated header");
+    if (h.magic != TABLE_MAGIC) return fail_msg(ctx, B200PPF_ERR_IO, "table load: not a b200ppf table file");
+    if (h.format != TABLE_FORMAT || h.header_bytes != sizeof(h))
+        return fail_msg(ctx, B200PPF_ERR_IO, "table load: file written by another format version");
+    if ((int)h.feature_mode != ctx->feature_mode || (int)h.alpha_mode != ctx->alpha_mode)
+        return fail_msg(ctx, B200PPF_ERR_STATE, "table load: the file's feature / alpha mode differs from the context's");
+    const uint64_t total_keys = (uint64_t)h.info.key_space * h.info.n_slices;
+    const bool sane = h.n_offsets == total_keys + 1 && total_keys < (1ull << 31) && h.bp.cells_log2 <= 8 &&
+                      h.n_sub_offsets == (h.bp.cells_log2 ? (total_keys << h.bp.cells_log2) + 1 : 0) &&
+                      h.n_entries == h.info.n_entries && h.n_entries <= 0xFFFFFFFFull && h.info.n_model <= 65535 &&
+                      h.info.n_alpha >= 1 && h.bp.n_alpha == h.info.n_alpha && h.bp.row_stride == h.info.n_alpha + 1 &&
+                      h.kp.slice_rows == h.info.slice_rows && h.kp.n_slices == h.info.n_slices;
+    if (!sane) return fail_msg(ctx, B200PPF_ERR_IO, "table load: inconsistent header");
+    const uint64_t lengths[6] = {h.n_offsets, h.n_sub_offsets, h.n_entries, h.n_entries, h.n_entries, h.n_entries};
+    std::vector<std::vector<uint32_t>> host(6);
+    uint64_t sum = mix_bytes(0x42323030u, &h.info, sizeof(h.info));
+    sum = mix_bytes(sum, &h.kp, sizeof(h.kp));
+    sum = mix_bytes(sum, &h.bp, sizeof(h.bp));
+    for (int a = 0; a < 6; ++a) {
+        host[a].resize(lengths[a]);
+        if (lengths[a] && fread(host[a].data(), sizeof(uint32_t), lengths[a], fc.f) != lengths[a])
+            return fail_msg(ctx, B200PPF_ERR_IO, "table load: truncated file");
+        sum = mix_bytes(sum, host[a].data(), host[a].size() * sizeof(uint32_t));
+    }
+    if (fgetc(fc.f) != EOF) return fail_msg(ctx, B200PPF_ERR_IO, "table load: trailing bytes");
+    if (sum != h.checksum) return fail_msg(ctx, B200PPF_ERR_IO, "table load: checksum mismatch (corrupt file)");
+    // offsets must be monotone and end at n_entries: the voting kernel trusts them
+    if (host[0].back() != h.n_entries || (h.n_sub_offsets && host[1].back() != h.n_entries))
+        return fail_msg(ctx, B200PPF_ERR_IO, "table load: offsets do not cover the entries");
+
+    b200ppf_table *t = new (std::nothrow) b200ppf_table();
+    if (!t) return fail_msg(ctx, B200PPF_ERR_NOMEM, "table load: out of host memory");
+    t->ctx = ctx;
+    t->info = h.info;
+    t->kp = h.kp;
+    t->bp = h.bp;
+    t->feature_mode = (int)h.feature_mode;
+    uint32_t **dev[6] = {&t->offsets, &t->sub_offsets, &t->entry_w, &t->entry_am,
+                         reinterpret_cast<uint32_t **>(&t->entry_alpha), &t->entry_idx};
+    for (int a = 0; a < 6; ++a) {
+        if (a == 1 && !h.n_sub_offsets) continue;
+        const size_t pad = (a == 2 || a == 3) ? b200ppf::ENTRY_PAD : 0;
+        const size_t words = std::max<size_t>(1, lengths[a] + pad);
+        cudaError_t e = cudaMalloc(dev[a], words * sizeof(uint32_t));
+        if (e == cudaSuccess && pad) e = cudaMemsetAsync(*dev[a] + lengths[a], 0, pad * sizeof(uint32_t), ctx->stream);
+        if (e == cudaSuccess && lengths[a])
+            e = cudaMemcpyAsync(*dev[a], host[a].data(), lengths[a] * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            b200ppf_table_free(t);
+            return fail_msg(ctx, e == cudaErrorMemoryAllocation ? B200PPF_ERR_NOMEM : B200PPF_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        b200ppf_table_free(t);
+        return fail_msg(ctx, B200PPF_ERR_CUDA, "table load: upload failed");
+    }
+    *out = t;
     return B200PPF_OK;
 }
 
