@@ -92,7 +92,7 @@ typedef struct b200ppf_table_info {
 /* per-stage device times of the last call on this context, milliseconds (CUDA events) */
 typedef struct b200ppf_timings {
     float upload_ms, features_ms, keys_ms, sort_ms, csr_ms, grid_ms, vote_ms, pose_ms, cluster_ms,
-        transform_ms;
+        transform_ms, icp_ms;
 } b200ppf_timings;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -200,6 +200,23 @@ int b200ppf_cluster_assignment(b200ppf_ctx *ctx, uint32_t *assignment, size_t n,
 /* ---- K5: tail of computeTransformation, pcl::transformPointCloud (xyz only) -------------- */
 int b200ppf_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose16,
                       float *out_host, size_t out_stride_floats);
+
+/* ---- K6 ("next" row): ICP refinement of the best poses ---------------------------------------
+ * The step the reference runs right after matching: include/CloudProcessing.h:465-470 / :518-523,
+ *     ICP icp(100, 0.005f, 2.5f, 8);  icp.registerModelToScene(models[id], pc_scene, resultsSub);
+ * (opencv_contrib surface_matching/src/icp.cpp: multi-resolution "picky" point-to-plane ICP).
+ * poses16: n_poses row-major 4x4 doubles, model -> scene, refined in place (Pose3D::appendPose);
+ * residuals (n_poses) and iterations (total over poses) may be NULL.  params NULL = the reference's
+ * (100, 0.005, 2.5, 8).  All poses are refined concurrently, one CTA each, in a single launch. */
+typedef struct b200ppf_icp_params {
+    int max_iterations;    /* ICP(iterations = 100, ...) */
+    float tolerance;       /* 0.005 */
+    float rejection_scale; /* 2.5; <= 0 disables the robust rejection */
+    int num_levels;        /* 8 */
+} b200ppf_icp_params;
+int b200ppf_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cloud *scene,
+                       const b200ppf_icp_params *params, double *poses16, size_t n_poses,
+                       double *residuals, uint64_t *iterations);
 
 /* ---- PPFRegistration::align in one call: vote + cluster, final16 = results.front() -------- */
 int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,

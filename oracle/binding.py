@@ -27,7 +27,7 @@ assert HYP_DTYPE.itemsize == 64
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (g++, no external dependencies)."""
-    src = [os.path.join(_HERE, f) for f in ("ppf_oracle.cpp", "ppf_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ppf_oracle.cpp", "icp_oracle.cpp", "ppf_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -295,3 +295,21 @@ def transform(cloud, pose16):
 
 def max_threads():
     return int(lib().oracle_max_threads())
+
+
+def icp_refine(model, scene, poses, max_iterations=100, tolerance=0.005, rejection_scale=2.5, num_levels=8):
+    """ICP::registerModelToScene(model, scene, poses) of the reference (icp_oracle.cpp).
+    poses: (P, 4, 4) model -> scene.  Returns (refined (P,4,4) float64, residuals (P,), iterations run)."""
+    model, scene = _f32(model), _f32(scene)
+    P = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 4, 4)).copy()
+    res = np.zeros(P.shape[0], np.float64)
+    iters = C.c_uint64(0)
+    L = lib()
+    L.oracle_icp_refine.restype = C.c_int
+    L.oracle_icp_refine.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_int,
+                                    C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint64)]
+    rc = L.oracle_icp_refine(_p(model), model.shape[0], _p(scene), scene.shape[0], max_iterations, tolerance,
+                             rejection_scale, num_levels, _p(P), P.shape[0], _p(res), C.byref(iters))
+    if rc != 0:
+        raise RuntimeError("oracle_icp_refine failed")
+    return P, res, int(iters.value)

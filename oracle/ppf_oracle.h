@@ -129,6 +129,15 @@ size_t oracle_register(const oracle_hashmap *hm, int feature_mode, int alpha_mod
 
 int oracle_max_threads(void);
 
+/* "Next" row of the path: the ICP refinement the reference runs on the top PPF
+ * poses — reference include/CloudProcessing.h:465-470 / :518-523, ICP(100, 0.005f, 2.5f, 8) and
+ * registerModelToScene(model, scene, poses).  Restated in icp_oracle.cpp from opencv_contrib
+ * surface_matching/src/icp.cpp as recalled (parity unpinned).  poses16: n_poses row-major 4x4 doubles,
+ * model -> scene, refined in place; residuals[n_poses] and the total iteration count are optional. */
+int oracle_icp_refine(const float *model, size_t n_model, const float *scene, size_t n_scene, int max_iterations,
+                      float tolerance, float rejection_scale, int num_levels, double *poses16, size_t n_poses,
+                      double *residuals, uint64_t *iterations_run);
+
 #ifdef __cplusplus
 }
 #endif

@@ -607,6 +607,58 @@ def test_errors_and_edges(ctx, bottle, dev_bottle, dev_crop, table_fused):
 
 # ---- the PCL-shaped C++ surface ------------------------------------------------------------------------
 
+def _icp_case(n_model=20000, n_scene=40000):
+    """Model, YOLO-crop-like scene around the instance, ground truth and five perturbed start poses."""
+    from yolo_ppf_pose_estimation_b200 import synth
+    model = synth.synth_model(n_model, 1)
+    G = synth.gt_pose(2)
+    sc = synth.synth_scene(n_scene, 2, model_seed=1)
+    centre = G[:3, 3] + G[:3, :3] @ np.array([0.0, 0.0, 0.09])
+    scene = sc[np.linalg.norm(sc[:, :3] - centre, axis=1) < 0.25]
+    starts = []
+    for k, (ang, tr) in enumerate(((0.03, 0.003), (0.1, 0.01), (0.2, 0.02), (0.05, 0.03), (0.0, 0.0))):
+        axis = np.array([0.3, 1.0, 0.2 + 0.3 * k])
+        axis /= np.linalg.norm(axis)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        D = np.eye(4)
+        D[:3, :3] = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        D[:3, 3] = (tr, -tr, 0.5 * tr)
+        C, Ci = np.eye(4), np.eye(4)
+        C[:3, 3], Ci[:3, 3] = centre, -centre
+        starts.append(C @ D @ Ci @ G)
+    return model, scene, G, np.array(starts)
+
+
+def test_k6_icp_vs_oracle(ctx, oracle):
+    """The reference's ICP(100, 0.005, 2.5, 8).registerModelToScene on five start poses at once: same
+    iteration count and poses as the oracle (double reductions differ in order only), and the scene's ground
+    truth recovered to the noise level."""
+    model, scene, G, starts = _icp_case()
+    dm, ds = ctx.upload_cloud(model), ctx.upload_cloud(scene)
+    P, res, it = ctx.icp_refine(dm, ds, starts)
+    R, rres, rit = oracle.icp_refine(model, scene, starts)
+    assert abs(it - rit) <= 2, (it, rit)
+    for k in range(len(starts)):
+        dt, dr = parity.pose_error(P[k], R[k])
+        assert dt < 2e-5 and dr < 0.005, (k, dt, dr)          # 20 um / 0.005 degrees between GPU and oracle
+        assert abs(res[k] - rres[k]) <= 1e-6 * max(1.0, rres[k])
+        dt, da = axis_pose_error(P[k], G)
+        assert dt < 5e-4 and da < 0.3, (k, dt, da)            # 0.5 mm sensor noise in the scene
+    assert ctx.timings()["icp_ms"] > 0
+    # fewer levels / no rejection / one pose: the parameters reach the kernel
+    P1, _, it1 = ctx.icp_refine(dm, ds, starts[:1], max_iterations=10, rejection_scale=0.0, num_levels=3)
+    R1, _, rit1 = oracle.icp_refine(model, scene, starts[:1], max_iterations=10, rejection_scale=0.0, num_levels=3)
+    assert it1 == rit1 and parity.pose_error(P1[0], R1[0])[0] < 2e-5
+    # a thinner model (2 500 points): the coarsest levels hold ~20 samples; still the same trajectory
+    thin = model[::8]
+    Ps, _, its = ctx.icp_refine(ctx.upload_cloud(thin), ds, starts[:2])
+    Rs, _, rits = oracle.icp_refine(thin, scene, starts[:2])
+    assert abs(its - rits) <= 2
+    for k in range(2):
+        dt, dr = parity.pose_error(Ps[k], Rs[k])
+        assert dt < 1e-4 and dr < 0.02, (k, dt, dr)
+
+
 def test_cpp_pcl_shim_end_to_end(tmp_path, ctx, bottle, scene_crop, dev_bottle, dev_crop, oracle_bottle):
     """tests/cpp/pcl_shim_example.cpp — PPFEstimation::compute -> PPFHashMapSearch::setInputFeatureCloud
     -> PPFRegistration::align through include/pcl_compat — gives the C-ABI result."""

@@ -274,3 +274,30 @@ def test_poses_within_thresholds(oracle):
     assert not oracle.poses_within(A, _pose([0, 0, 0.3], [0.011, 0, 0]), 0.01, 0.35)
     assert not oracle.poses_within(A, _pose([0, 0, 0.36], [0, 0, 0]), 0.01, 0.35)
     assert oracle.poses_within(A, _pose([0, 3.0, 0], [0, 0, 0]), 0.01, 3.1)   # angle is in [0, pi]
+
+
+def test_icp_oracle_recovers_ground_truth(oracle):
+    """ICP "next" row: the restated OpenCV ICP pulls perturbed poses (up to 3 cm / 11 degrees) back onto the
+    synthetic scene's ground truth to the 0.5 mm noise level; an exact start stays put."""
+    from yolo_ppf_pose_estimation_b200 import synth
+    model = synth.synth_model(20000, 1)
+    G = synth.gt_pose(2)
+    sc = synth.synth_scene(40000, 2, model_seed=1)
+    centre = G[:3, 3] + G[:3, :3] @ np.array([0.0, 0.0, 0.09])
+    scene = sc[np.linalg.norm(sc[:, :3] - centre, axis=1) < 0.25]
+    axis = np.array([0.3, 1.0, 0.2]) / np.linalg.norm([0.3, 1.0, 0.2])
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    starts = []
+    for ang, tr in ((0.2, 0.02), (0.0, 0.0)):
+        D = np.eye(4)
+        D[:3, :3] = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        D[:3, 3] = (tr, -tr, 0.5 * tr)
+        C, Ci = np.eye(4), np.eye(4)
+        C[:3, 3], Ci[:3, 3] = centre, -centre
+        starts.append(C @ D @ Ci @ G)
+    P, res, it = oracle.icp_refine(model, scene, starts)
+    assert it > 10 and (res < 0.01).all()
+    for k in range(2):
+        dt = np.linalg.norm(P[k][:3, 3] - G[:3, 3])
+        da = np.degrees(np.arccos(np.clip(P[k][:3, 2] @ G[:3, 2], -1, 1)))   # surface of revolution: axis only
+        assert dt < 5e-4 and da < 0.3, (k, dt, da)

@@ -4,7 +4,7 @@
 NAME=$1; shift
 D=$(mktemp -d)
 SRC=yolo_ppf_pose_estimation_b200/csrc
-for f in capi radix_sort k1_features k2_table k3_vote scene_grid k4_cluster k5_transform microbench; do
+for f in capi radix_sort k1_features k2_table k3_vote scene_grid k4_cluster k5_transform k6_icp microbench; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
        -Xcompiler -fPIC -Xcompiler -O2 "$@" -c $SRC/$f.cu -o $D/$f.o &
 done

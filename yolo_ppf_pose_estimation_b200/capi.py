@@ -34,7 +34,12 @@ class TableInfo(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("upload_ms", "features_ms", "keys_ms", "sort_ms", "csr_ms", "grid_ms",
-                                         "vote_ms", "pose_ms", "cluster_ms", "transform_ms")]
+                                         "vote_ms", "pose_ms", "cluster_ms", "transform_ms", "icp_ms")]
+
+
+class IcpParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("tolerance", C.c_float), ("rejection_scale", C.c_float),
+                ("num_levels", C.c_int)]
 
 
 # every symbol include/b200ppf.h declares: (name, restype, argtypes)
@@ -79,6 +84,7 @@ SYMBOLS = {
     "b200ppf_cluster": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_cluster_device": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_cluster_assignment": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "b200ppf_icp_refine": (_i, [_vp, _vp, _vp, C.POINTER(IcpParams), _vp, _sz, _vp, C.POINTER(C.c_uint64)]),
     "b200ppf_transform": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "b200ppf_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
 }
@@ -215,6 +221,17 @@ class Context:
         self.check(lib().b200ppf_table_build_from_cloud(self._h, model._h, np.float32(angle_step),
                                                         np.float32(dist_step), C.byref(h)))
         return Table(self, h)
+
+    def icp_refine(self, model: "Cloud", scene: "Cloud", poses, max_iterations=100, tolerance=0.005,
+                   rejection_scale=2.5, num_levels=8):
+        """ICP::registerModelToScene(model, scene, poses): -> (refined (P,4,4) float64, residuals, iterations)"""
+        P = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 4, 4)).copy()
+        res = np.zeros(P.shape[0], np.float64)
+        it = C.c_uint64(0)
+        prm = IcpParams(max_iterations, tolerance, rejection_scale, num_levels)
+        self.check(lib().b200ppf_icp_refine(self._h, model._h, scene._h, C.byref(prm), _p(P), P.shape[0], _p(res),
+                                            C.byref(it)))
+        return P, res, int(it.value)
 
     def table_load(self, path) -> "Table":
         """LoadTrainedDetector: rebuild a saved table on this context's device (no K1/K2)."""

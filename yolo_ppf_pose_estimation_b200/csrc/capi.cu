@@ -671,6 +671,18 @@ int b200ppf_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float 
 
 /* ---- align -------------------------------------------------------------------------------- */
 
+int b200ppf_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cloud *scene,
+                       const b200ppf_icp_params *params, double *poses16, size_t n_poses, double *residuals,
+                       uint64_t *iterations) {
+    CHECK_CTX(ctx);
+    if (!model || !scene || (n_poses && !poses16)) return fail_msg(ctx, B200PPF_ERR_INVALID, "icp: null argument");
+    DeviceGuard guard(ctx->device);
+    b200ppf_icp_params p = {100, 0.005f, 2.5f, 8};  // the reference's ICP(100, 0.005f, 2.5f, 8)
+    if (params) p = *params;
+    return k6_icp_refine(ctx, model, scene, p.max_iterations, p.tolerance, p.rejection_scale, p.num_levels, poses16,
+                         n_poses, residuals, iterations);
+}
+
 int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
                      const b200ppf_cloud *scene, size_t ref_rate, float pos_thr, float rot_thr, float *final16,
                      float *poses16, uint32_t *votes, size_t *n_out) {

@@ -1,0 +1,603 @@
+// k6_icp.cu — K6: ICP refinement of the top PPF poses ("next" row of the path).
+//
+// Replaces, for the step that follows PPF matching in the reference
+// (include/CloudProcessing.h:465-470 / :518-523: ICP icp(100, 0.005f, 2.5f, 8);
+//  icp.registerModelToScene(models[id], pc_scene, resultsSub)), opencv_contrib's
+// surface_matching/src/icp.cpp — the multi-resolution "picky" point-to-plane ICP (Birdal & Ilic):
+//   both clouds centred on the mean of their centroids and scaled by n / mean distance to the origin;
+//   coarse to fine over num_levels, level L on every round(n / round(n / 2^L))-th point of both clouds with
+//   tolerance * (L+1)^2 and max_iterations / (L+1) iterations; pose <- PoseX * pose per level; the
+//   normalisation is undone at the end.  The tests' CPU restatement of the same source is the checker.
+//
+// One persistent CTA of 1024 threads per pose hypothesis runs the whole refinement — every pyramid level and
+// every iteration — in ONE launch: the reference refines its five best poses, and an iteration is far too small
+// (<= 20 k points) to be worth a kernel launch, let alone several.  Per iteration, inside the CTA:
+//   nearest scene sample of every moved model sample   uniform grid over the level's scene samples, growing
+//                                                      shells, exact (ties: lowest index), float distances
+//   robust threshold  median + scale * 1.4826 * MAD    two exact radix selects (4 x 8-bit shared histograms)
+//   one model sample per scene sample                  64-bit atomicMin on (distance bits, model sample)
+//   point-to-plane normal equations                    27 doubles reduced by shuffles + shared memory
+//   6 x 6 solve, Euler -> pose, error, stop test       thread 0, double precision
+//   move the level's samples                           all threads
+// Arithmetic follows the original operation for operation (float where cv::Mat is CV_32F, double elsewhere,
+// -fmad=false), so the only differences are libm's double sin/cos and the order of the reductions.
+#include "ppf_common.cuh"
+
+namespace b200ppf {
+
+namespace {
+
+constexpr int ICP_THREADS = 1024;
+constexpr int ICP_WARPS = ICP_THREADS / 32;
+constexpr uint32_t ICP_CELLS_MAX = 1u << 16;  // grid cells per level (scanned by the CTA)
+constexpr int NEQ = 28;                       // 21 (upper A) + 6 (b) + 1 (squared error)
+
+struct IcpArgs {
+    const float4 *mpos, *mnrm;
+    const float4 *spos, *snrm;
+    uint32_t n_model, n_scene;
+    int max_iterations, num_levels;
+    float tolerance, rejection_scale;
+    double *poses;       // [n_poses][16] in: start, out: refined
+    double *residuals;   // [n_poses]
+    unsigned long long *iterations;
+    // per-pose scratch (pose p uses slice p)
+    float *src_norm, *dst_norm;  // [n_model][6], [n_scene][6]  normalised clouds
+    float *src_t;                // [n_model][6]  level samples under the level's start pose
+    float *moved;                // [n_model][3]
+    int *nn;                     // [n_model]
+    float *d2;                   // [n_model]
+    unsigned long long *winner;  // [n_scene]
+    uint32_t *cell_start;        // [ICP_CELLS_MAX + 1]
+    uint32_t *cell_fill;         // [ICP_CELLS_MAX]
+    uint32_t *items;             // [n_scene]
+};
+
+struct GridDev {
+    double lo[3], cell;
+    int dim[3];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// sum K doubles per thread over the CTA; the totals land in out[0..K) (shared), visible after the call
+template <int K>
+__device__ void block_sum(const double *v, double *out, double (*scratch)[NEQ]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double s = warp_sum(v[k]);
+        if (lane == 0) scratch[w][k] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+        for (int k = 0; k < K; ++k) {
+            const double s = warp_sum(lane < ICP_WARPS ? scratch[lane][k] : 0.0);
+            if (lane == 0) out[k] = s;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void transform_point(const double *P, const float *s, float *d, bool with_normal) {
+    const double x = s[0], y = s[1], z = s[2];
+    double w = P[12] * x + P[13] * y + P[14] * z + P[15];
+    if (w == 0.0) w = 1.0;
+    d[0] = (float)((P[0] * x + P[1] * y + P[2] * z + P[3]) / w);
+    d[1] = (float)((P[4] * x + P[5] * y + P[6] * z + P[7]) / w);
+    d[2] = (float)((P[8] * x + P[9] * y + P[10] * z + P[11]) / w);
+    if (with_normal) {
+        const double nx = s[3], ny = s[4], nz = s[5];
+        double rx = P[0] * nx + P[1] * ny + P[2] * nz;
+        double ry = P[4] * nx + P[5] * ny + P[6] * nz;
+        double rz = P[8] * nx + P[9] * ny + P[10] * nz;
+        const double len = sqrt(rx * rx + ry * ry + rz * rz);
+        if (len > 1e-12) {
+            rx /= len;
+            ry /= len;
+            rz /= len;
+        }
+        d[3] = (float)rx;
+        d[4] = (float)ry;
+        d[5] = (float)rz;
+    }
+}
+
+__device__ __forceinline__ void mat4_mul(const double *a, const double *b, double *c) {
+    for (int r = 0; r < 4; ++r)
+        for (int k = 0; k < 4; ++k) {
+            double s = 0.0;
+            for (int q = 0; q < 4; ++q) s += a[r * 4 + q] * b[q * 4 + k];
+            c[r * 4 + k] = s;
+        }
+}
+
+__device__ bool solve6(double *A, double *b, double *x) {
+    int perm[6] = {0, 1, 2, 3, 4, 5};
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(A[perm[r] * 6 + c]) > fabs(A[perm[piv] * 6 + c])) piv = r;
+        const int t = perm[c];
+        perm[c] = perm[piv];
+        perm[piv] = t;
+        const double d = A[perm[c] * 6 + c];
+        if (!(fabs(d) > 1e-300)) return false;
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = A[perm[r] * 6 + c] / d;
+            for (int k = c; k < 6; ++k) A[perm[r] * 6 + k] -= f * A[perm[c] * 6 + k];
+            b[perm[r]] -= f * b[perm[c]];
+        }
+    }
+    for (int c = 5; c >= 0; --c) {
+        double s = b[perm[c]];
+        for (int k = c + 1; k < 6; ++k) s -= A[perm[c] * 6 + k] * x[k];
+        x[c] = s / A[perm[c] * 6 + c];
+    }
+    for (int c = 0; c < 6; ++c)
+        if (!isfinite(x[c])) return false;
+    return true;
+}
+
+__device__ void pose_from_euler(const double *rpy, const double *t, double *P) {
+    const double cx = cos(rpy[0]), sx = sin(rpy[0]);
+    const double cy = cos(rpy[1]), sy = sin(rpy[1]);
+    const double cz = cos(rpy[2]), sz = sin(rpy[2]);
+    const double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
+    const double Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy};
+    const double Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+    double T[9], R[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) T[r * 3 + c] = Ry[r * 3] * Rz[c] + Ry[r * 3 + 1] * Rz[3 + c] + Ry[r * 3 + 2] * Rz[6 + c];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = Rx[r * 3] * T[c] + Rx[r * 3 + 1] * T[3 + c] + Rx[r * 3 + 2] * T[6 + c];
+    for (int k = 0; k < 16; ++k) P[k] = 0.0;
+    P[15] = 1.0;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) P[r * 4 + c] = R[r * 3 + c];
+        P[r * 4 + 3] = t[r];
+    }
+}
+
+// k-th smallest (0-based) of the non-negative floats f(i), i < m: 4 passes of 8-bit shared histograms
+template <class F>
+__device__ float block_select(uint32_t m, uint32_t k, F f, uint32_t *hist, uint32_t *s_sel /*[2]: prefix, k*/) {
+    if (threadIdx.x == 0) {
+        s_sel[0] = 0;
+        s_sel[1] = k;
+    }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (uint32_t d = threadIdx.x; d < 256; d += ICP_THREADS) hist[d] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_sel[0];
+        for (uint32_t i = threadIdx.x; i < m; i += ICP_THREADS) {
+            const uint32_t bits = __float_as_uint(f(i));
+            if (shift == 24 || (bits >> (shift + 8)) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t kk = s_sel[1], d = 0;
+            while (d < 255 && hist[d] <= kk) kk -= hist[d++];
+            s_sel[0] = (prefix << 8) | d;
+            s_sel[1] = kk;
+        }
+        __syncthreads();
+    }
+    return __uint_as_float(s_sel[0]);
+}
+
+__device__ __forceinline__ int grid_coord(const GridDev &g, double v, int c) {
+    const int k = (int)floor((v - g.lo[c]) / g.cell);
+    return k < 0 ? 0 : (k >= g.dim[c] ? g.dim[c] - 1 : k);
+}
+
+__global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArgs a) {
+    __shared__ double s_red[ICP_WARPS][NEQ];
+    __shared__ double s_tot[NEQ];
+    __shared__ double s_pose[16], s_posex[16], s_mean[3];
+    __shared__ double s_scale, s_fold, s_fperc, s_fmin;
+    __shared__ GridDev s_grid;
+    __shared__ uint32_t s_hist[256], s_sel[2], s_carry;
+    __shared__ float s_thr;
+    __shared__ int s_flag, s_iter;
+    __shared__ float s_bb[ICP_WARPS][6];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t p = blockIdx.x;
+    const uint32_t n = a.n_model, nd = a.n_scene;
+    float *src = a.src_norm + (size_t)p * n * 6, *dst = a.dst_norm + (size_t)p * nd * 6;
+    float *src_t = a.src_t + (size_t)p * n * 6, *moved = a.moved + (size_t)p * n * 3;
+    int *nn = a.nn + (size_t)p * n;
+    float *d2 = a.d2 + (size_t)p * n;
+    unsigned long long *winner = a.winner + (size_t)p * nd;
+    uint32_t *cell_start = a.cell_start + (size_t)p * (ICP_CELLS_MAX + 1);
+    uint32_t *cell_fill = a.cell_fill + (size_t)p * ICP_CELLS_MAX;
+    uint32_t *items = a.items + (size_t)p * nd;
+    double start_pose[16];
+    for (int k = 0; k < 16; ++k) start_pose[k] = a.poses[(size_t)p * 16 + k];
+
+    // ---- srcTemp = transformPCPose(model, start); centre both clouds, scale ------------------------------------
+    double acc[NEQ];
+    for (int k = 0; k < NEQ; ++k) acc[k] = 0.0;
+    for (uint32_t i = tid; i < n; i += ICP_THREADS) {
+        const float4 q = a.mpos[i], r = a.mnrm[i];
+        const float in[6] = {q.x, q.y, q.z, r.x, r.y, r.z};
+        float out[6];
+        transform_point(start_pose, in, out, true);
+        for (int c = 0; c < 6; ++c) src[6 * (size_t)i + c] = out[c];
+        acc[0] += out[0];
+        acc[1] += out[1];
+        acc[2] += out[2];
+    }
+    for (uint32_t i = tid; i < nd; i += ICP_THREADS) {
+        const float4 q = a.spos[i], r = a.snrm[i];
+        dst[6 * (size_t)i] = q.x;
+        dst[6 * (size_t)i + 1] = q.y;
+        dst[6 * (size_t)i + 2] = q.z;
+        dst[6 * (size_t)i + 3] = r.x;
+        dst[6 * (size_t)i + 4] = r.y;
+        dst[6 * (size_t)i + 5] = r.z;
+        acc[3] += q.x;
+        acc[4] += q.y;
+        acc[5] += q.z;
+    }
+    block_sum<6>(acc, s_tot, s_red);
+    if (tid == 0)
+        for (int c = 0; c < 3; ++c) s_mean[c] = 0.5 * (s_tot[c] / (double)n + s_tot[3 + c] / (double)nd);
+    __syncthreads();
+    acc[0] = acc[1] = 0.0;
+    for (uint32_t i = tid; i < n; i += ICP_THREADS) {
+        float *q = src + 6 * (size_t)i;
+        for (int c = 0; c < 3; ++c) q[c] = (float)((double)q[c] - s_mean[c]);
+        acc[0] += sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]);
+    }
+    for (uint32_t i = tid; i < nd; i += ICP_THREADS) {
+        float *q = dst + 6 * (size_t)i;
+        for (int c = 0; c < 3; ++c) q[c] = (float)((double)q[c] - s_mean[c]);
+        acc[1] += sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]);
+    }
+    block_sum<2>(acc, s_tot, s_red);
+    if (tid == 0) {
+        s_scale = (double)n / ((s_tot[0] + s_tot[1]) * 0.5);
+        for (int k = 0; k < 16; ++k) s_pose[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        s_fmin = 0.0;
+    }
+    __syncthreads();
+    const double scale = s_scale;
+    for (uint32_t i = tid; i < n; i += ICP_THREADS)
+        for (int c = 0; c < 3; ++c) src[6 * (size_t)i + c] = (float)((double)src[6 * (size_t)i + c] * scale);
+    for (uint32_t i = tid; i < nd; i += ICP_THREADS)
+        for (int c = 0; c < 3; ++c) dst[6 * (size_t)i + c] = (float)((double)dst[6 * (size_t)i + c] * scale);
+    __syncthreads();
+
+    double residual = 0.0;
+    unsigned long long iterations = 0;
+    for (int level = a.num_levels - 1; level >= 0; --level) {
+        const double div = pow(2.0, (double)level);
+        const int num_samples = (int)nearbyint((double)n / div);
+        const double tol_p = (double)a.tolerance * (double)(level + 1) * (double)(level + 1);
+        const int max_it = (int)nearbyint((double)a.max_iterations / (double)(level + 1));
+        if (num_samples < 1) continue;
+        const int step = max(1, (int)nearbyint((double)n / (double)num_samples));
+        const uint32_t m = (n + step - 1) / step, md = (nd + step - 1) / step;
+        if (m == 0 || md == 0) continue;
+
+        // ---- level samples of the model under the pose so far; bounding box of the scene samples ---------------
+        float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        for (uint32_t i = tid; i < m; i += ICP_THREADS) {
+            float out[6];
+            transform_point(s_pose, src + 6 * (size_t)i * step, out, true);
+            for (int c = 0; c < 6; ++c) src_t[6 * (size_t)i + c] = out[c];
+            for (int c = 0; c < 3; ++c) moved[3 * (size_t)i + c] = out[c];
+        }
+        for (uint32_t j = tid; j < md; j += ICP_THREADS)
+            for (int c = 0; c < 3; ++c) {
+                const float v = dst[6 * (size_t)j * step + c];
+                lo[c] = fminf(lo[c], v);
+                hi[c] = fmaxf(hi[c], v);
+            }
+        for (int c = 0; c < 3; ++c)
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[c] = fminf(lo[c], __shfl_xor_sync(0xFFFFFFFFu, lo[c], o));
+                hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xFFFFFFFFu, hi[c], o));
+            }
+        if (lane == 0)
+            for (int c = 0; c < 3; ++c) {
+                s_bb[warp][c] = lo[c];
+                s_bb[warp][3 + c] = hi[c];
+            }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < ICP_WARPS; ++w)
+                for (int c = 0; c < 3; ++c) {
+                    lo[c] = fminf(lo[c], s_bb[w][c]);
+                    hi[c] = fmaxf(hi[c], s_bb[w][3 + c]);
+                }
+            // ~1 sample per cell, at most ICP_CELLS_MAX cells
+            const double ex = fmax((double)hi[0] - lo[0], 1e-9), ey = fmax((double)hi[1] - lo[1], 1e-9),
+                         ez = fmax((double)hi[2] - lo[2], 1e-9);
+            double cell = cbrt(ex * ey * ez / fmax(1.0, fmin((double)md, (double)ICP_CELLS_MAX / 8.0)));
+            cell = fmax(cell, fmax(ex, fmax(ey, ez)) / 256.0);
+            for (;;) {
+                s_grid.dim[0] = (int)floor(ex / cell) + 1;
+                s_grid.dim[1] = (int)floor(ey / cell) + 1;
+                s_grid.dim[2] = (int)floor(ez / cell) + 1;
+                if ((unsigned long long)s_grid.dim[0] * s_grid.dim[1] * s_grid.dim[2] <= ICP_CELLS_MAX) break;
+                cell *= 1.26;
+            }
+            s_grid.cell = cell;
+            for (int c = 0; c < 3; ++c) s_grid.lo[c] = lo[c];
+            for (int k = 0; k < 16; ++k) s_posex[k] = (k % 5 == 0) ? 1.0 : 0.0;
+            s_fold = 9999999999.0;
+            s_fperc = 0.0;
+            s_fmin = 9999999999.0;
+            s_iter = 0;
+            s_carry = 0;
+        }
+        __syncthreads();
+        const GridDev g = s_grid;
+        const uint32_t cells = (uint32_t)g.dim[0] * g.dim[1] * g.dim[2];
+        // ---- counting sort of the scene samples by cell ------------------------------------------------------------
+        for (uint32_t c = tid; c < cells; c += ICP_THREADS) cell_fill[c] = 0;
+        __syncthreads();
+        for (uint32_t j = tid; j < md; j += ICP_THREADS) {
+            const float *q = dst + 6 * (size_t)j * step;
+            const uint32_t c = ((uint32_t)grid_coord(g, q[2], 2) * g.dim[1] + grid_coord(g, q[1], 1)) * g.dim[0] +
+                               grid_coord(g, q[0], 0);
+            atomicAdd(&cell_fill[c], 1u);
+        }
+        __syncthreads();
+        for (uint32_t base = 0; base < cells; base += ICP_THREADS) {  // exclusive scan, 1024 cells per round
+            const uint32_t c = base + tid;
+            const uint32_t v = c < cells ? cell_fill[c] : 0u;
+            uint32_t incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            if (lane == 31) s_hist[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t w = s_hist[lane], wi = w;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                    if ((int)lane >= o) wi += t;
+                }
+                s_hist[lane] = wi - w;
+                if (lane == 31) s_hist[32] = wi;
+            }
+            __syncthreads();
+            const uint32_t excl = s_carry + s_hist[warp] + incl - v;
+            if (c < cells) {
+                cell_start[c] = excl;
+                cell_fill[c] = excl;
+            }
+            __syncthreads();
+            if (tid == 0) s_carry += s_hist[32];
+            __syncthreads();
+        }
+        if (tid == 0) cell_start[cells] = md;
+        __syncthreads();
+        for (uint32_t j = tid; j < md; j += ICP_THREADS) {
+            const float *q = dst + 6 * (size_t)j * step;
+            const uint32_t c = ((uint32_t)grid_coord(g, q[2], 2) * g.dim[1] + grid_coord(g, q[1], 1)) * g.dim[0] +
+                               grid_coord(g, q[0], 0);
+            items[atomicAdd(&cell_fill[c], 1u)] = j;
+        }
+        __syncthreads();
+
+        // ---- iterations --------------------------------------------------------------------------------------------
+        for (;;) {
+            if (tid == 0)
+                s_flag = (!(s_fperc < (1.0 + tol_p) && s_fperc > (1.0 - tol_p)) && s_iter < max_it) ? 1 : 0;
+            __syncthreads();
+            if (!s_flag) break;
+            // nearest scene sample of every moved model sample
+            const int max_r = max(g.dim[0], max(g.dim[1], g.dim[2]));
+            for (uint32_t i = tid; i < m; i += ICP_THREADS) {
+                const float qx = moved[3 * (size_t)i], qy = moved[3 * (size_t)i + 1], qz = moved[3 * (size_t)i + 2];
+                const int cx = grid_coord(g, qx, 0), cy = grid_coord(g, qy, 1), cz = grid_coord(g, qz, 2);
+                int best = -1;
+                float best_d2 = 3.402823466e38f;
+                for (int r = 0; r <= max_r; ++r) {
+                    if (best >= 0) {
+                        const double reach = (double)(r - 1) * g.cell;
+                        if (reach > 0 && reach * reach > (double)best_d2) break;
+                    }
+                    for (int z = cz - r; z <= cz + r; ++z) {
+                        if (z < 0 || z >= g.dim[2]) continue;
+                        for (int y = cy - r; y <= cy + r; ++y) {
+                            if (y < 0 || y >= g.dim[1]) continue;
+                            const bool shell_zy = (z == cz - r || z == cz + r || y == cy - r || y == cy + r);
+                            const int xs = shell_zy ? 1 : max(1, 2 * r);  // interior rows: only the two end cells
+                            for (int x = cx - r; x <= cx + r; x += xs) {
+                                if (x < 0 || x >= g.dim[0]) continue;
+                                const uint32_t c = ((uint32_t)z * g.dim[1] + y) * g.dim[0] + x;
+                                for (uint32_t s = cell_start[c]; s < cell_start[c + 1]; ++s) {
+                                    const uint32_t j = items[s];
+                                    const float *q = dst + 6 * (size_t)j * step;
+                                    const float dx = qx - q[0], dy = qy - q[1], dz = qz - q[2];
+                                    const float dd = dx * dx + dy * dy + dz * dz;
+                                    if (dd < best_d2 || (dd == best_d2 && (int)j < best)) {
+                                        best_d2 = dd;
+                                        best = (int)j;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                nn[i] = best;
+                d2[i] = best_d2;
+            }
+            for (uint32_t j = tid; j < md; j += ICP_THREADS) winner[j] = ~0ull;
+            __syncthreads();
+            // robust rejection threshold on the squared distances
+            float thr = 3.402823466e38f;
+            if (a.rejection_scale > 0.0f) {
+                const uint32_t k = (m - 1) / 2;
+                const float med = block_select(m, k, [&](uint32_t i) { return d2[i]; }, s_hist, s_sel);
+                const float mad = block_select(
+                    m, k, [&](uint32_t i) { return (float)fabs((double)d2[i] - (double)med); }, s_hist, s_sel);
+                const float s = 1.48257968f * mad;
+                thr = a.rejection_scale * s + med;
+            }
+            // of several model samples on one scene sample the closest survives (lowest index on ties)
+            for (uint32_t i = tid; i < m; i += ICP_THREADS)
+                if (a.rejection_scale <= 0.0f || d2[i] < thr)
+                    atomicMin(&winner[nn[i]], ((unsigned long long)__float_as_uint(d2[i]) << 32) | i);
+            __syncthreads();
+            // point-to-plane normal equations over the surviving pairs
+            for (int k = 0; k < NEQ; ++k) acc[k] = 0.0;
+            uint32_t matches = 0;
+            for (uint32_t j = tid; j < md; j += ICP_THREADS) {
+                const unsigned long long wv = winner[j];
+                if (wv == ~0ull) continue;
+                const float *s = src_t + 6 * (size_t)(uint32_t)wv;
+                const float *d = dst + 6 * (size_t)j * step;
+                const double sp[3] = {s[0], s[1], s[2]}, dp[3] = {d[0], d[1], d[2]}, nr[3] = {d[3], d[4], d[5]};
+                const double row[6] = {sp[1] * nr[2] - sp[2] * nr[1], sp[2] * nr[0] - sp[0] * nr[2],
+                                       sp[0] * nr[1] - sp[1] * nr[0], nr[0], nr[1], nr[2]};
+                const double rhs = (dp[0] - sp[0]) * nr[0] + (dp[1] - sp[1]) * nr[1] + (dp[2] - sp[2]) * nr[2];
+                int q = 0;
+                for (int r = 0; r < 6; ++r)
+                    for (int c = r; c < 6; ++c) acc[q++] += row[r] * row[c];
+                for (int r = 0; r < 6; ++r) acc[21 + r] += row[r] * rhs;
+                for (int c = 0; c < 6; ++c) {
+                    const double e = (double)s[c] - (double)d[c];
+                    acc[27] += e * e;
+                }
+                ++matches;
+            }
+            block_sum<NEQ>(acc, s_tot, s_red);
+            const int any = __syncthreads_or(matches != 0);
+            if (tid == 0) {
+                bool ok = any != 0;
+                double x[6];
+                if (ok) {
+                    double A[36], bb[6];
+                    int q = 0;
+                    for (int r = 0; r < 6; ++r)
+                        for (int c = r; c < 6; ++c) {
+                            A[r * 6 + c] = s_tot[q];
+                            A[c * 6 + r] = s_tot[q];
+                            ++q;
+                        }
+                    for (int r = 0; r < 6; ++r) bb[r] = s_tot[21 + r];
+                    ok = solve6(A, bb, x);
+                }
+                if (ok) {
+                    pose_from_euler(x, x + 3, s_posex);
+                    const double fval = sqrt(s_tot[27]) / (double)m;
+                    s_fperc = fval / s_fold;
+                    s_fold = fval;
+                    if (fval < s_fmin) s_fmin = fval;
+                    ++s_iter;
+                }
+                s_flag = ok ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_flag) break;
+            ++iterations;
+            for (uint32_t i = tid; i < m; i += ICP_THREADS) {
+                float out[3];
+                transform_point(s_posex, src_t + 6 * (size_t)i, out, false);
+                for (int c = 0; c < 3; ++c) moved[3 * (size_t)i + c] = out[c];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            double np[16];
+            mat4_mul(s_posex, s_pose, np);
+            for (int k = 0; k < 16; ++k) s_pose[k] = np[k];
+        }
+        residual = s_fmin;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        // undo the normalisation, then Pose3D::appendPose: refined = delta * start
+        double delta[16], out[16];
+        for (int k = 0; k < 16; ++k) delta[k] = s_pose[k];
+        for (int r = 0; r < 3; ++r) {
+            const double rm = delta[r * 4] * s_mean[0] + delta[r * 4 + 1] * s_mean[1] + delta[r * 4 + 2] * s_mean[2];
+            delta[r * 4 + 3] = delta[r * 4 + 3] / s_scale + s_mean[r] - rm;
+        }
+        mat4_mul(delta, start_pose, out);
+        for (int k = 0; k < 16; ++k) a.poses[(size_t)p * 16 + k] = out[k];
+        if (a.residuals) a.residuals[p] = residual;
+        if (a.iterations) atomicAdd(a.iterations, iterations);
+    }
+}
+
+}  // namespace
+
+int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cloud *scene, int max_iterations,
+                  float tolerance, float rejection_scale, int num_levels, double *poses16_host, size_t n_poses,
+                  double *residuals_host, uint64_t *iterations_host) {
+    if (n_poses == 0) return B200PPF_OK;
+    if (model->n == 0 || scene->n == 0) return fail_msg(ctx, B200PPF_ERR_INVALID, "icp: empty cloud");
+    if (max_iterations < 1 || num_levels < 1 || num_levels > 30 || !(tolerance >= 0.0f))
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "icp: bad parameters");
+    const size_t n = model->n, nd = scene->n, P = n_poses;
+    // one slab for all scratch
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_poses = take(P * 16 * sizeof(double)), o_res = take(P * sizeof(double)), o_it = take(sizeof(unsigned long long));
+    const size_t o_src = take(P * n * 6 * sizeof(float)), o_dst = take(P * nd * 6 * sizeof(float));
+    const size_t o_srct = take(P * n * 6 * sizeof(float)), o_moved = take(P * n * 3 * sizeof(float));
+    const size_t o_nn = take(P * n * sizeof(int)), o_d2 = take(P * n * sizeof(float));
+    const size_t o_win = take(P * nd * sizeof(unsigned long long));
+    const size_t o_cs = take(P * (ICP_CELLS_MAX + 1) * sizeof(uint32_t)), o_cf = take(P * ICP_CELLS_MAX * sizeof(uint32_t));
+    const size_t o_items = take(P * nd * sizeof(uint32_t));
+    unsigned char *slab = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&slab, off, ctx->stream));
+    IcpArgs a;
+    a.mpos = model->pos;
+    a.mnrm = model->nrm;
+    a.spos = scene->pos;
+    a.snrm = scene->nrm;
+    a.n_model = (uint32_t)n;
+    a.n_scene = (uint32_t)nd;
+    a.max_iterations = max_iterations;
+    a.num_levels = num_levels;
+    a.tolerance = tolerance;
+    a.rejection_scale = rejection_scale;
+    a.poses = reinterpret_cast<double *>(slab + o_poses);
+    a.residuals = reinterpret_cast<double *>(slab + o_res);
+    a.iterations = reinterpret_cast<unsigned long long *>(slab + o_it);
+    a.src_norm = reinterpret_cast<float *>(slab + o_src);
+    a.dst_norm = reinterpret_cast<float *>(slab + o_dst);
+    a.src_t = reinterpret_cast<float *>(slab + o_srct);
+    a.moved = reinterpret_cast<float *>(slab + o_moved);
+    a.nn = reinterpret_cast<int *>(slab + o_nn);
+    a.d2 = reinterpret_cast<float *>(slab + o_d2);
+    a.winner = reinterpret_cast<unsigned long long *>(slab + o_win);
+    a.cell_start = reinterpret_cast<uint32_t *>(slab + o_cs);
+    a.cell_fill = reinterpret_cast<uint32_t *>(slab + o_cf);
+    a.items = reinterpret_cast<uint32_t *>(slab + o_items);
+    PPF_CUDA(ctx, cudaMemcpyAsync(a.poses, poses16_host, P * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PPF_CUDA(ctx, cudaMemsetAsync(a.iterations, 0, sizeof(unsigned long long), ctx->stream));
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    PPF_LAUNCH(ctx, icp_refine_kernel, (unsigned)P, ICP_THREADS, 0, a);
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    PPF_CUDA(ctx, cudaMemcpyAsync(poses16_host, a.poses, P * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (residuals_host)
+        PPF_CUDA(ctx, cudaMemcpyAsync(residuals_host, a.residuals, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long it = 0;
+    PPF_CUDA(ctx, cudaMemcpyAsync(&it, a.iterations, sizeof(it), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timings.icp_ms, ctx->ev[0], ctx->ev[1]);
+    if (iterations_host) *iterations_host = it;
+    PPF_CUDA(ctx, cudaFreeAsync(slab, ctx->stream));
+    return B200PPF_OK;
+}
+
+}  // namespace b200ppf

@@ -125,6 +125,9 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n
                float *poses16, uint32_t *votes, size_t *n_out);
 int k5_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose16, float *out_host,
                  size_t out_stride_floats);
+int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cloud *scene, int max_iterations,
+                  float tolerance, float rejection_scale, int num_levels, double *poses16_host, size_t n_poses,
+                  double *residuals_host, uint64_t *iterations_host);
 
 // uniform grid over the scene (scene_grid.cu): cells of edge >= search radius, x fastest
 struct GridParams {
