@@ -9,9 +9,13 @@
 //   tolerance * (L+1)^2 and max_iterations / (L+1) iterations; pose <- PoseX * pose per level; the
 //   normalisation is undone at the end.  The tests' CPU restatement of the same source is the checker.
 //
-// One persistent CTA of 1024 threads per pose hypothesis runs the whole refinement — every pyramid level and
-// every iteration — in ONE launch: the reference refines its five best poses, and an iteration is far too small
-// (<= 20 k points) to be worth a kernel launch, let alone several.  Per iteration, inside the CTA:
+// One persistent thread-block CLUSTER (8 CTAs x 1024 threads, one SM each) per pose hypothesis runs the whole
+// refinement — every pyramid level and every iteration — in ONE launch: the reference refines its five best
+// poses, and an iteration is far too small (<= 20 k points) to be worth a kernel launch, let alone several.
+// The samples are strided over the cluster; sums and histograms are combined through distributed shared
+// memory (every CTA adds the eight partials in rank order, so all of them hold bit-identical state and take
+// the same branches); cluster.sync() is the only inter-SM synchronisation.  FP64 is scarce on this part
+// (measured: the double transforms dominate), which is what the eight SMs per pose are for.  Per iteration:
 //   nearest scene sample of every moved model sample   uniform grid over the level's scene samples, growing
 //                                                      shells, exact (ties: lowest index), float distances
 //   robust threshold  median + scale * 1.4826 * MAD    two exact radix selects (4 x 8-bit shared histograms)
@@ -21,16 +25,21 @@
 //   move the level's samples                           all threads
 // Arithmetic follows the original operation for operation (float where cv::Mat is CV_32F, double elsewhere,
 // -fmad=false), so the only differences are libm's double sin/cos and the order of the reductions.
+#include <cooperative_groups.h>
+
 #include "ppf_common.cuh"
 
 namespace b200ppf {
 
 namespace {
 
+namespace cg = cooperative_groups;
+
 constexpr int ICP_THREADS = 1024;
+constexpr int ICP_CLUSTER = 8;  // CTAs (SMs) per pose
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr uint32_t ICP_CELLS_MAX = 1u << 16;  // grid cells per level (scanned by the CTA)
-constexpr int NEQ = 28;                       // 21 (upper A) + 6 (b) + 1 (squared error)
+constexpr int NEQ = 29;                       // 21 (upper A) + 6 (b) + 1 (squared error) + 1 (matches)
 
 struct IcpArgs {
     const float4 *mpos, *mnrm;
@@ -50,11 +59,11 @@ struct IcpArgs {
     unsigned long long *winner;  // [n_scene]
     uint32_t *cell_start;        // [ICP_CELLS_MAX + 1]
     uint32_t *cell_fill;         // [ICP_CELLS_MAX]
-    uint32_t *items;             // [n_scene]
+    float4 *items;               // [n_scene]  cell-sorted level scene samples {x, y, z, sample index}
 };
 
-struct GridDev {
-    double lo[3], cell;
+struct GridDev {  // any exact nearest-neighbour structure gives the same matches: the grid itself is fp32
+    float lo[3], cell, inv_cell;
     int dim[3];
 };
 
@@ -81,6 +90,19 @@ __device__ void block_sum(const double *v, double *out, double (*scratch)[NEQ]) 
         }
     }
     __syncthreads();
+}
+
+// the same over the cluster: every CTA adds the partials of all ranks in rank order -> identical totals everywhere
+template <int K>
+__device__ void cluster_sum(cg::cluster_group &cluster, const double *v, double *part, double *out, double (*scratch)[NEQ]) {
+    block_sum<K>(v, part, scratch);
+    cluster.sync();
+    if (threadIdx.x < K) {
+        double s = 0.0;
+        for (unsigned r = 0; r < cluster.num_blocks(); ++r) s += cluster.map_shared_rank(part, r)[threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    cluster.sync();
 }
 
 __device__ __forceinline__ void transform_point(const double *P, const float *s, float *d, bool with_normal) {
@@ -163,9 +185,11 @@ __device__ void pose_from_euler(const double *rpy, const double *t, double *P) {
     }
 }
 
-// k-th smallest (0-based) of the non-negative floats f(i), i < m: 4 passes of 8-bit shared histograms
+// k-th smallest (0-based) of the non-negative floats f(i) over this cluster's samples i = first, first + stride, ...
+// 4 passes of 8-bit histograms: local shared histogram, summed over the cluster through distributed shared memory
 template <class F>
-__device__ float block_select(uint32_t m, uint32_t k, F f, uint32_t *hist, uint32_t *s_sel /*[2]: prefix, k*/) {
+__device__ float cluster_select(cg::cluster_group &cluster, uint32_t m, uint32_t first, uint32_t stride, uint32_t k, F f,
+                                uint32_t *hist, uint32_t *hist_tot, uint32_t *s_sel /*[2]: prefix, k*/) {
     if (threadIdx.x == 0) {
         s_sel[0] = 0;
         s_sel[1] = k;
@@ -174,14 +198,20 @@ __device__ float block_select(uint32_t m, uint32_t k, F f, uint32_t *hist, uint3
         for (uint32_t d = threadIdx.x; d < 256; d += ICP_THREADS) hist[d] = 0;
         __syncthreads();
         const uint32_t prefix = s_sel[0];
-        for (uint32_t i = threadIdx.x; i < m; i += ICP_THREADS) {
+        for (uint32_t i = first; i < m; i += stride) {
             const uint32_t bits = __float_as_uint(f(i));
             if (shift == 24 || (bits >> (shift + 8)) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
         }
-        __syncthreads();
+        cluster.sync();
+        if (threadIdx.x < 256) {
+            uint32_t t = 0;
+            for (unsigned r = 0; r < cluster.num_blocks(); ++r) t += cluster.map_shared_rank(hist, r)[threadIdx.x];
+            hist_tot[threadIdx.x] = t;
+        }
+        cluster.sync();
         if (threadIdx.x == 0) {
             uint32_t kk = s_sel[1], d = 0;
-            while (d < 255 && hist[d] <= kk) kk -= hist[d++];
+            while (d < 255 && hist_tot[d] <= kk) kk -= hist_tot[d++];
             s_sel[0] = (prefix << 8) | d;
             s_sel[1] = kk;
         }
@@ -190,24 +220,26 @@ __device__ float block_select(uint32_t m, uint32_t k, F f, uint32_t *hist, uint3
     return __uint_as_float(s_sel[0]);
 }
 
-__device__ __forceinline__ int grid_coord(const GridDev &g, double v, int c) {
-    const int k = (int)floor((v - g.lo[c]) / g.cell);
+__device__ __forceinline__ int grid_coord(const GridDev &g, float v, int c) {
+    const int k = (int)floorf((v - g.lo[c]) * g.inv_cell);
     return k < 0 ? 0 : (k >= g.dim[c] ? g.dim[c] - 1 : k);
 }
 
 __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArgs a) {
     __shared__ double s_red[ICP_WARPS][NEQ];
-    __shared__ double s_tot[NEQ];
+    __shared__ double s_part[NEQ], s_tot[NEQ];
     __shared__ double s_pose[16], s_posex[16], s_mean[3];
     __shared__ double s_scale, s_fold, s_fperc, s_fmin;
     __shared__ GridDev s_grid;
-    __shared__ uint32_t s_hist[256], s_sel[2], s_carry;
-    __shared__ float s_thr;
+    __shared__ uint32_t s_hist[256], s_hist_tot[256], s_sel[2], s_carry;
     __shared__ int s_flag, s_iter;
     __shared__ float s_bb[ICP_WARPS][6];
 
+    cg::cluster_group cluster = cg::this_cluster();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t p = blockIdx.x;
+    const uint32_t rank = cluster.block_rank(), csize = cluster.num_blocks();
+    const uint32_t first = rank * ICP_THREADS + tid, stride = csize * ICP_THREADS;  // this thread's samples
+    const uint32_t p = blockIdx.y;
     const uint32_t n = a.n_model, nd = a.n_scene;
     float *src = a.src_norm + (size_t)p * n * 6, *dst = a.dst_norm + (size_t)p * nd * 6;
     float *src_t = a.src_t + (size_t)p * n * 6, *moved = a.moved + (size_t)p * n * 3;
@@ -216,14 +248,14 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
     unsigned long long *winner = a.winner + (size_t)p * nd;
     uint32_t *cell_start = a.cell_start + (size_t)p * (ICP_CELLS_MAX + 1);
     uint32_t *cell_fill = a.cell_fill + (size_t)p * ICP_CELLS_MAX;
-    uint32_t *items = a.items + (size_t)p * nd;
+    float4 *items = a.items + (size_t)p * nd;
     double start_pose[16];
     for (int k = 0; k < 16; ++k) start_pose[k] = a.poses[(size_t)p * 16 + k];
 
     // ---- srcTemp = transformPCPose(model, start); centre both clouds, scale ------------------------------------
     double acc[NEQ];
     for (int k = 0; k < NEQ; ++k) acc[k] = 0.0;
-    for (uint32_t i = tid; i < n; i += ICP_THREADS) {
+    for (uint32_t i = first; i < n; i += stride) {
         const float4 q = a.mpos[i], r = a.mnrm[i];
         const float in[6] = {q.x, q.y, q.z, r.x, r.y, r.z};
         float out[6];
@@ -233,7 +265,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
         acc[1] += out[1];
         acc[2] += out[2];
     }
-    for (uint32_t i = tid; i < nd; i += ICP_THREADS) {
+    for (uint32_t i = first; i < nd; i += stride) {
         const float4 q = a.spos[i], r = a.snrm[i];
         dst[6 * (size_t)i] = q.x;
         dst[6 * (size_t)i + 1] = q.y;
@@ -245,22 +277,22 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
         acc[4] += q.y;
         acc[5] += q.z;
     }
-    block_sum<6>(acc, s_tot, s_red);
+    cluster_sum<6>(cluster, acc, s_part, s_tot, s_red);
     if (tid == 0)
         for (int c = 0; c < 3; ++c) s_mean[c] = 0.5 * (s_tot[c] / (double)n + s_tot[3 + c] / (double)nd);
     __syncthreads();
     acc[0] = acc[1] = 0.0;
-    for (uint32_t i = tid; i < n; i += ICP_THREADS) {
+    for (uint32_t i = first; i < n; i += stride) {
         float *q = src + 6 * (size_t)i;
         for (int c = 0; c < 3; ++c) q[c] = (float)((double)q[c] - s_mean[c]);
         acc[0] += sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]);
     }
-    for (uint32_t i = tid; i < nd; i += ICP_THREADS) {
+    for (uint32_t i = first; i < nd; i += stride) {
         float *q = dst + 6 * (size_t)i;
         for (int c = 0; c < 3; ++c) q[c] = (float)((double)q[c] - s_mean[c]);
         acc[1] += sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]);
     }
-    block_sum<2>(acc, s_tot, s_red);
+    cluster_sum<2>(cluster, acc, s_part, s_tot, s_red);
     if (tid == 0) {
         s_scale = (double)n / ((s_tot[0] + s_tot[1]) * 0.5);
         for (int k = 0; k < 16; ++k) s_pose[k] = (k % 5 == 0) ? 1.0 : 0.0;
@@ -268,11 +300,12 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
     }
     __syncthreads();
     const double scale = s_scale;
-    for (uint32_t i = tid; i < n; i += ICP_THREADS)
+    for (uint32_t i = first; i < n; i += stride)
         for (int c = 0; c < 3; ++c) src[6 * (size_t)i + c] = (float)((double)src[6 * (size_t)i + c] * scale);
-    for (uint32_t i = tid; i < nd; i += ICP_THREADS)
+    for (uint32_t i = first; i < nd; i += stride)
         for (int c = 0; c < 3; ++c) dst[6 * (size_t)i + c] = (float)((double)dst[6 * (size_t)i + c] * scale);
-    __syncthreads();
+    __threadfence();
+    cluster.sync();
 
     double residual = 0.0;
     unsigned long long iterations = 0;
@@ -287,14 +320,14 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
         if (m == 0 || md == 0) continue;
 
         // ---- level samples of the model under the pose so far; bounding box of the scene samples ---------------
-        float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-        for (uint32_t i = tid; i < m; i += ICP_THREADS) {
+        for (uint32_t i = first; i < m; i += stride) {
             float out[6];
             transform_point(s_pose, src + 6 * (size_t)i * step, out, true);
             for (int c = 0; c < 6; ++c) src_t[6 * (size_t)i + c] = out[c];
             for (int c = 0; c < 3; ++c) moved[3 * (size_t)i + c] = out[c];
         }
-        for (uint32_t j = tid; j < md; j += ICP_THREADS)
+        float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        for (uint32_t j = tid; j < md; j += ICP_THREADS)  // every CTA scans all scene samples: no exchange needed
             for (int c = 0; c < 3; ++c) {
                 const float v = dst[6 * (size_t)j * step + c];
                 lo[c] = fminf(lo[c], v);
@@ -317,19 +350,19 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
                     lo[c] = fminf(lo[c], s_bb[w][c]);
                     hi[c] = fmaxf(hi[c], s_bb[w][3 + c]);
                 }
-            // ~1 sample per cell, at most ICP_CELLS_MAX cells
-            const double ex = fmax((double)hi[0] - lo[0], 1e-9), ey = fmax((double)hi[1] - lo[1], 1e-9),
-                         ez = fmax((double)hi[2] - lo[2], 1e-9);
-            double cell = cbrt(ex * ey * ez / fmax(1.0, fmin((double)md, (double)ICP_CELLS_MAX / 8.0)));
-            cell = fmax(cell, fmax(ex, fmax(ey, ez)) / 256.0);
+            // ~2 samples per cell, at most ICP_CELLS_MAX cells
+            const float ex = fmaxf(hi[0] - lo[0], 1e-9f), ey = fmaxf(hi[1] - lo[1], 1e-9f), ez = fmaxf(hi[2] - lo[2], 1e-9f);
+            float cell = cbrtf(ex * ey * ez / fmaxf(1.0f, fminf(0.5f * (float)md, (float)ICP_CELLS_MAX / 8.0f)));
+            cell = fmaxf(cell, fmaxf(ex, fmaxf(ey, ez)) / 256.0f);
             for (;;) {
-                s_grid.dim[0] = (int)floor(ex / cell) + 1;
-                s_grid.dim[1] = (int)floor(ey / cell) + 1;
-                s_grid.dim[2] = (int)floor(ez / cell) + 1;
+                s_grid.dim[0] = (int)floorf(ex / cell) + 1;
+                s_grid.dim[1] = (int)floorf(ey / cell) + 1;
+                s_grid.dim[2] = (int)floorf(ez / cell) + 1;
                 if ((unsigned long long)s_grid.dim[0] * s_grid.dim[1] * s_grid.dim[2] <= ICP_CELLS_MAX) break;
-                cell *= 1.26;
+                cell *= 1.26f;
             }
             s_grid.cell = cell;
+            s_grid.inv_cell = 1.0f / cell;
             for (int c = 0; c < 3; ++c) s_grid.lo[c] = lo[c];
             for (int k = 0; k < 16; ++k) s_posex[k] = (k % 5 == 0) ? 1.0 : 0.0;
             s_fold = 9999999999.0;
@@ -341,54 +374,60 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
         __syncthreads();
         const GridDev g = s_grid;
         const uint32_t cells = (uint32_t)g.dim[0] * g.dim[1] * g.dim[2];
-        // ---- counting sort of the scene samples by cell ------------------------------------------------------------
-        for (uint32_t c = tid; c < cells; c += ICP_THREADS) cell_fill[c] = 0;
-        __syncthreads();
-        for (uint32_t j = tid; j < md; j += ICP_THREADS) {
+        // ---- counting sort of the scene samples by cell (counts and fill by the cluster, scan by rank 0) -----------
+        for (uint32_t c = first; c < cells; c += stride) cell_fill[c] = 0;
+        __threadfence();
+        cluster.sync();
+        for (uint32_t j = first; j < md; j += stride) {
             const float *q = dst + 6 * (size_t)j * step;
             const uint32_t c = ((uint32_t)grid_coord(g, q[2], 2) * g.dim[1] + grid_coord(g, q[1], 1)) * g.dim[0] +
                                grid_coord(g, q[0], 0);
             atomicAdd(&cell_fill[c], 1u);
         }
-        __syncthreads();
-        for (uint32_t base = 0; base < cells; base += ICP_THREADS) {  // exclusive scan, 1024 cells per round
-            const uint32_t c = base + tid;
-            const uint32_t v = c < cells ? cell_fill[c] : 0u;
-            uint32_t incl = v;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if ((int)lane >= o) incl += t;
-            }
-            if (lane == 31) s_hist[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t w = s_hist[lane], wi = w;
+        __threadfence();
+        cluster.sync();
+        if (rank == 0) {
+            for (uint32_t base = 0; base < cells; base += ICP_THREADS) {  // exclusive scan, 1024 cells per round
+                const uint32_t c = base + tid;
+                const uint32_t v = c < cells ? cell_fill[c] : 0u;
+                uint32_t incl = v;
                 for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-                    if ((int)lane >= o) wi += t;
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if ((int)lane >= o) incl += t;
                 }
-                s_hist[lane] = wi - w;
-                if (lane == 31) s_hist[32] = wi;
+                if (lane == 31) s_hist[warp] = incl;
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t w = s_hist[lane], wi = w;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                        if ((int)lane >= o) wi += t;
+                    }
+                    s_hist[lane] = wi - w;
+                    if (lane == 31) s_hist[32] = wi;
+                }
+                __syncthreads();
+                const uint32_t excl = s_carry + s_hist[warp] + incl - v;
+                if (c < cells) {
+                    cell_start[c] = excl;
+                    cell_fill[c] = excl;
+                }
+                __syncthreads();
+                if (tid == 0) s_carry += s_hist[32];
+                __syncthreads();
             }
-            __syncthreads();
-            const uint32_t excl = s_carry + s_hist[warp] + incl - v;
-            if (c < cells) {
-                cell_start[c] = excl;
-                cell_fill[c] = excl;
-            }
-            __syncthreads();
-            if (tid == 0) s_carry += s_hist[32];
-            __syncthreads();
+            if (tid == 0) cell_start[cells] = md;
         }
-        if (tid == 0) cell_start[cells] = md;
-        __syncthreads();
-        for (uint32_t j = tid; j < md; j += ICP_THREADS) {
+        __threadfence();
+        cluster.sync();
+        for (uint32_t j = first; j < md; j += stride) {
             const float *q = dst + 6 * (size_t)j * step;
             const uint32_t c = ((uint32_t)grid_coord(g, q[2], 2) * g.dim[1] + grid_coord(g, q[1], 1)) * g.dim[0] +
                                grid_coord(g, q[0], 0);
-            items[atomicAdd(&cell_fill[c], 1u)] = j;
+            items[atomicAdd(&cell_fill[c], 1u)] = make_float4(q[0], q[1], q[2], __uint_as_float(j));
         }
-        __syncthreads();
+        __threadfence();
+        cluster.sync();
 
         // ---- iterations --------------------------------------------------------------------------------------------
         for (;;) {
@@ -398,63 +437,75 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
             if (!s_flag) break;
             // nearest scene sample of every moved model sample
             const int max_r = max(g.dim[0], max(g.dim[1], g.dim[2]));
-            for (uint32_t i = tid; i < m; i += ICP_THREADS) {
+            for (uint32_t i = first; i < m; i += stride) {
                 const float qx = moved[3 * (size_t)i], qy = moved[3 * (size_t)i + 1], qz = moved[3 * (size_t)i + 2];
                 const int cx = grid_coord(g, qx, 0), cy = grid_coord(g, qy, 1), cz = grid_coord(g, qz, 2);
                 int best = -1;
                 float best_d2 = 3.402823466e38f;
-                for (int r = 0; r <= max_r; ++r) {
-                    if (best >= 0) {
-                        const double reach = (double)(r - 1) * g.cell;
-                        if (reach > 0 && reach * reach > (double)best_d2) break;
-                    }
-                    for (int z = cz - r; z <= cz + r; ++z) {
-                        if (z < 0 || z >= g.dim[2]) continue;
-                        for (int y = cy - r; y <= cy + r; ++y) {
-                            if (y < 0 || y >= g.dim[1]) continue;
-                            const bool shell_zy = (z == cz - r || z == cz + r || y == cy - r || y == cy + r);
-                            const int xs = shell_zy ? 1 : max(1, 2 * r);  // interior rows: only the two end cells
-                            for (int x = cx - r; x <= cx + r; x += xs) {
-                                if (x < 0 || x >= g.dim[0]) continue;
-                                const uint32_t c = ((uint32_t)z * g.dim[1] + y) * g.dim[0] + x;
-                                for (uint32_t s = cell_start[c]; s < cell_start[c + 1]; ++s) {
-                                    const uint32_t j = items[s];
-                                    const float *q = dst + 6 * (size_t)j * step;
-                                    const float dx = qx - q[0], dy = qy - q[1], dz = qz - q[2];
-                                    const float dd = dx * dx + dy * dy + dz * dz;
-                                    if (dd < best_d2 || (dd == best_d2 && (int)j < best)) {
-                                        best_d2 = dd;
-                                        best = (int)j;
-                                    }
-                                }
+                // Cubes of growing radius around the query's cell.  The cells x0..x1 of one (z, y) row are one
+                // contiguous run of the cell-sorted samples, so a cube is (2r+1)^2 plain loops — every lane of
+                // the warp walks the same loop nest (the shell-by-shell form left 2 of 32 lanes active).  A
+                // larger cube re-tests the inner one; with ~2 samples per cell almost every query ends at r = 1.
+                for (int r = 1; r <= max_r; ++r) {
+                    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dim[2] - 1);
+                    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dim[1] - 1);
+                    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dim[0] - 1);
+                    // one flat loop over the concatenated runs: an iteration either tests a sample or steps to
+                    // the next row, so lanes whose rows are empty do not idle while others walk theirs
+                    const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+                    int row = 0;
+                    uint32_t sidx = 0, e = 0;
+                    for (;;) {
+                        if (sidx < e) {
+                            const float4 q = items[sidx++];
+                            const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
+                            const float dd = dx * dx + dy * dy + dz * dz;
+                            const int j = (int)__float_as_uint(q.w);
+                            if (dd < best_d2 || (dd == best_d2 && j < best)) {
+                                best_d2 = dd;
+                                best = j;
                             }
+                        } else {
+                            if (row >= nrows) break;
+                            const int z = z0 + row / ny, y = y0 + row % ny;
+                            const uint32_t base = ((uint32_t)z * g.dim[1] + y) * g.dim[0];
+                            sidx = cell_start[base + x0];
+                            e = cell_start[base + x1 + 1];
+                            ++row;
                         }
                     }
+                    // every sample outside the cube is more than r cells away along one axis (slack: fp32 grid)
+                    const float reach = (float)r * g.cell * 0.999f;
+                    if (best >= 0 && best_d2 <= reach * reach) break;
                 }
                 nn[i] = best;
                 d2[i] = best_d2;
             }
-            for (uint32_t j = tid; j < md; j += ICP_THREADS) winner[j] = ~0ull;
-            __syncthreads();
-            // robust rejection threshold on the squared distances
+            for (uint32_t j = first; j < md; j += stride) winner[j] = ~0ull;
+            __threadfence();
+            // robust rejection threshold on the squared distances (the selects synchronise the cluster)
             float thr = 3.402823466e38f;
             if (a.rejection_scale > 0.0f) {
                 const uint32_t k = (m - 1) / 2;
-                const float med = block_select(m, k, [&](uint32_t i) { return d2[i]; }, s_hist, s_sel);
-                const float mad = block_select(
-                    m, k, [&](uint32_t i) { return (float)fabs((double)d2[i] - (double)med); }, s_hist, s_sel);
-                const float s = 1.48257968f * mad;
-                thr = a.rejection_scale * s + med;
+                const float med = cluster_select(cluster, m, first, stride, k, [&](uint32_t i) { return d2[i]; }, s_hist,
+                                                 s_hist_tot, s_sel);
+                const float mad = cluster_select(
+                    cluster, m, first, stride, k, [&](uint32_t i) { return (float)fabs((double)d2[i] - (double)med); },
+                    s_hist, s_hist_tot, s_sel);
+                const float sdev = 1.48257968f * mad;
+                thr = a.rejection_scale * sdev + med;
+            } else {
+                cluster.sync();
             }
             // of several model samples on one scene sample the closest survives (lowest index on ties)
-            for (uint32_t i = tid; i < m; i += ICP_THREADS)
+            for (uint32_t i = first; i < m; i += stride)
                 if (a.rejection_scale <= 0.0f || d2[i] < thr)
                     atomicMin(&winner[nn[i]], ((unsigned long long)__float_as_uint(d2[i]) << 32) | i);
-            __syncthreads();
+            __threadfence();
+            cluster.sync();
             // point-to-plane normal equations over the surviving pairs
             for (int k = 0; k < NEQ; ++k) acc[k] = 0.0;
-            uint32_t matches = 0;
-            for (uint32_t j = tid; j < md; j += ICP_THREADS) {
+            for (uint32_t j = first; j < md; j += stride) {
                 const unsigned long long wv = winner[j];
                 if (wv == ~0ull) continue;
                 const float *s = src_t + 6 * (size_t)(uint32_t)wv;
@@ -471,12 +522,11 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
                     const double e = (double)s[c] - (double)d[c];
                     acc[27] += e * e;
                 }
-                ++matches;
+                acc[28] += 1.0;
             }
-            block_sum<NEQ>(acc, s_tot, s_red);
-            const int any = __syncthreads_or(matches != 0);
+            cluster_sum<NEQ>(cluster, acc, s_part, s_tot, s_red);
             if (tid == 0) {
-                bool ok = any != 0;
+                bool ok = s_tot[28] > 0.0;
                 double x[6];
                 if (ok) {
                     double A[36], bb[6];
@@ -503,7 +553,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
             __syncthreads();
             if (!s_flag) break;
             ++iterations;
-            for (uint32_t i = tid; i < m; i += ICP_THREADS) {
+            for (uint32_t i = first; i < m; i += stride) {
                 float out[3];
                 transform_point(s_posex, src_t + 6 * (size_t)i, out, false);
                 for (int c = 0; c < 3; ++c) moved[3 * (size_t)i + c] = out[c];
@@ -516,9 +566,10 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
             for (int k = 0; k < 16; ++k) s_pose[k] = np[k];
         }
         residual = s_fmin;
-        __syncthreads();
+        __threadfence();
+        cluster.sync();
     }
-    if (tid == 0) {
+    if (tid == 0 && rank == 0) {
         // undo the normalisation, then Pose3D::appendPose: refined = delta * start
         double delta[16], out[16];
         for (int k = 0; k < 16; ++k) delta[k] = s_pose[k];
@@ -539,6 +590,7 @@ int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cl
                   float tolerance, float rejection_scale, int num_levels, double *poses16_host, size_t n_poses,
                   double *residuals_host, uint64_t *iterations_host) {
     if (n_poses == 0) return B200PPF_OK;
+    if (n_poses > 65535) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "icp: more than 65535 poses per call");
     if (model->n == 0 || scene->n == 0) return fail_msg(ctx, B200PPF_ERR_INVALID, "icp: empty cloud");
     if (max_iterations < 1 || num_levels < 1 || num_levels > 30 || !(tolerance >= 0.0f))
         return fail_msg(ctx, B200PPF_ERR_INVALID, "icp: bad parameters");
@@ -556,7 +608,7 @@ int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cl
     const size_t o_nn = take(P * n * sizeof(int)), o_d2 = take(P * n * sizeof(float));
     const size_t o_win = take(P * nd * sizeof(unsigned long long));
     const size_t o_cs = take(P * (ICP_CELLS_MAX + 1) * sizeof(uint32_t)), o_cf = take(P * ICP_CELLS_MAX * sizeof(uint32_t));
-    const size_t o_items = take(P * nd * sizeof(uint32_t));
+    const size_t o_items = take(P * nd * sizeof(float4));
     unsigned char *slab = nullptr;
     PPF_CUDA(ctx, cudaMallocAsync(&slab, off, ctx->stream));
     IcpArgs a;
@@ -582,11 +634,27 @@ int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cl
     a.winner = reinterpret_cast<unsigned long long *>(slab + o_win);
     a.cell_start = reinterpret_cast<uint32_t *>(slab + o_cs);
     a.cell_fill = reinterpret_cast<uint32_t *>(slab + o_cf);
-    a.items = reinterpret_cast<uint32_t *>(slab + o_items);
+    a.items = reinterpret_cast<float4 *>(slab + o_items);
     PPF_CUDA(ctx, cudaMemcpyAsync(a.poses, poses16_host, P * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PPF_CUDA(ctx, cudaMemsetAsync(a.iterations, 0, sizeof(unsigned long long), ctx->stream));
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    PPF_LAUNCH(ctx, icp_refine_kernel, (unsigned)P, ICP_THREADS, 0, a);
+    {
+        // one cluster of ICP_CLUSTER CTAs per pose: grid (ICP_CLUSTER, n_poses), cluster dimension (ICP_CLUSTER, 1, 1)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ICP_CLUSTER, (unsigned)P, 1);
+        cfg.blockDim = dim3(ICP_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ICP_CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PPF_CUDA(ctx, cudaLaunchKernelEx(&cfg, icp_refine_kernel, a));
+        ctx->launches++;
+    }
     cudaEventRecord(ctx->ev[1], ctx->stream);
     PPF_CUDA(ctx, cudaMemcpyAsync(poses16_host, a.poses, P * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (residuals_host)
