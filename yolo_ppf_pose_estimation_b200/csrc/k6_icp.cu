@@ -54,7 +54,8 @@ struct IcpArgs {
     float *src_norm, *dst_norm;  // [n_model][6], [n_scene][6]  normalised clouds
     float *src_t;                // [n_model][6]  level samples under the level's start pose
     float *moved;                // [n_model][3]
-    int *nn;                     // [n_model]
+    int *nn;                     // [n_model]  nearest scene sample of every level sample (kept between iterations)
+    int *nn_prev;                // [n_model]  the same at the end of the previous (coarser) level
     float *d2;                   // [n_model]
     unsigned long long *winner;  // [n_scene]
     uint32_t *cell_start;        // [ICP_CELLS_MAX + 1]
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
     float *src = a.src_norm + (size_t)p * n * 6, *dst = a.dst_norm + (size_t)p * nd * 6;
     float *src_t = a.src_t + (size_t)p * n * 6, *moved = a.moved + (size_t)p * n * 3;
     int *nn = a.nn + (size_t)p * n;
+    int *nn_prev = a.nn_prev + (size_t)p * n;
     float *d2 = a.d2 + (size_t)p * n;
     unsigned long long *winner = a.winner + (size_t)p * nd;
     uint32_t *cell_start = a.cell_start + (size_t)p * (ICP_CELLS_MAX + 1);
@@ -309,6 +311,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
 
     double residual = 0.0;
     unsigned long long iterations = 0;
+    int prev_step = 0;
+    uint32_t prev_m = 0;
     for (int level = a.num_levels - 1; level >= 0; --level) {
         const double div = pow(2.0, (double)level);
         const int num_samples = (int)nearbyint((double)n / div);
@@ -325,6 +329,18 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
             transform_point(s_pose, src + 6 * (size_t)i * step, out, true);
             for (int c = 0; c < 6; ++c) src_t[6 * (size_t)i + c] = out[c];
             for (int c = 0; c < 3; ++c) moved[3 * (size_t)i + c] = out[c];
+            // seed of the nearest-neighbour search: the match of the closest sample of the previous, coarser
+            // level (sample k there is sample k * prev_step / step here; likewise for the scene samples)
+            int seed = -1;
+            if (prev_step > 0) {
+                const uint32_t ratio = (uint32_t)prev_step / (uint32_t)step;
+                if (ratio >= 1 && (uint32_t)prev_step == ratio * (uint32_t)step) {
+                    const uint32_t k = min(i / ratio, prev_m - 1);
+                    const long long j = (long long)nn_prev[k] * ratio;
+                    if (nn_prev[k] >= 0 && j < (long long)md) seed = (int)j;
+                }
+            }
+            nn[i] = seed;
         }
         float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
         for (uint32_t j = tid; j < md; j += ICP_THREADS)  // every CTA scans all scene samples: no exchange needed
@@ -440,9 +456,54 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
             for (uint32_t i = first; i < m; i += stride) {
                 const float qx = moved[3 * (size_t)i], qy = moved[3 * (size_t)i + 1], qz = moved[3 * (size_t)i + 2];
                 const int cx = grid_coord(g, qx, 0), cy = grid_coord(g, qy, 1), cz = grid_coord(g, qz, 2);
-                int best = -1;
+                int best = nn[i];
                 float best_d2 = 3.402823466e38f;
-                // Cubes of growing radius around the query's cell.  The cells x0..x1 of one (z, y) row are one
+                if (best >= 0) {
+                    // Seeded search: the previous iteration's (or level's) match bounds the distance, and only the
+                    // cells that intersect the ball of that radius are visited — rows (z, y) and the x range inside
+                    // a row are pruned with the current best, which only shrinks.  A sample whose true neighbour
+                    // is 15 cells away costs ~700 mostly empty row steps instead of 30 000 distance tests.
+                    {
+                        const float *q = dst + 6 * (size_t)best * step;
+                        const float dx = qx - q[0], dy = qy - q[1], dz = qz - q[2];
+                        best_d2 = dx * dx + dy * dy + dz * dz;
+                    }
+                    const float slack = 1e-3f * g.cell;
+                    const float r0 = sqrtf(best_d2) * 1.001f + slack;
+                    const int z0 = grid_coord(g, qz - r0, 2), z1 = grid_coord(g, qz + r0, 2);
+                    const int y0 = grid_coord(g, qy - r0, 1), y1 = grid_coord(g, qy + r0, 1);
+                    const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+                    int row = 0;
+                    uint32_t sidx = 0, e = 0;
+                    for (;;) {
+                        if (sidx < e) {
+                            const float4 q = items[sidx++];
+                            const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
+                            const float dd = dx * dx + dy * dy + dz * dz;
+                            const int j = (int)__float_as_uint(q.w);
+                            if (dd < best_d2 || (dd == best_d2 && j < best)) {
+                                best_d2 = dd;
+                                best = j;
+                            }
+                        } else {
+                            if (row >= nrows) break;
+                            const int z = z0 + row / ny, y = y0 + row % ny;
+                            ++row;
+                            // lower bounds of the distance from the query to slab z / row y (a sliver of a cell
+                            // of slack: the cell of a sample comes from floor((v - lo) * inv_cell) in fp32)
+                            const float zl = g.lo[2] + (float)z * g.cell, yl = g.lo[1] + (float)y * g.cell;
+                            const float gz = fmaxf(0.0f, fmaxf(zl - qz, qz - (zl + g.cell)) - slack) * 0.999f;
+                            const float gy = fmaxf(0.0f, fmaxf(yl - qy, qy - (yl + g.cell)) - slack) * 0.999f;
+                            const float rem = best_d2 - gz * gz - gy * gy;
+                            if (rem < 0.0f) continue;
+                            const float reach = sqrtf(rem) * 1.001f + slack;
+                            const uint32_t base = ((uint32_t)z * g.dim[1] + y) * g.dim[0];
+                            sidx = cell_start[base + grid_coord(g, qx - reach, 0)];
+                            e = cell_start[base + grid_coord(g, qx + reach, 0) + 1];
+                        }
+                    }
+                } else
+                // Unseeded (the coarsest level): cubes of growing radius.  The cells x0..x1 of one (z, y) row are one
                 // contiguous run of the cell-sorted samples, so a cube is (2r+1)^2 plain loops — every lane of
                 // the warp walks the same loop nest (the shell-by-shell form left 2 of 32 lanes active).  A
                 // larger cube re-tests the inner one; with ~2 samples per cell almost every query ends at r = 1.
@@ -566,6 +627,9 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
             for (int k = 0; k < 16; ++k) s_pose[k] = np[k];
         }
         residual = s_fmin;
+        for (uint32_t i = first; i < m; i += stride) nn_prev[i] = nn[i];
+        prev_step = step;
+        prev_m = m;
         __threadfence();
         cluster.sync();
     }
@@ -605,7 +669,7 @@ int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cl
     const size_t o_poses = take(P * 16 * sizeof(double)), o_res = take(P * sizeof(double)), o_it = take(sizeof(unsigned long long));
     const size_t o_src = take(P * n * 6 * sizeof(float)), o_dst = take(P * nd * 6 * sizeof(float));
     const size_t o_srct = take(P * n * 6 * sizeof(float)), o_moved = take(P * n * 3 * sizeof(float));
-    const size_t o_nn = take(P * n * sizeof(int)), o_d2 = take(P * n * sizeof(float));
+    const size_t o_nn = take(P * n * sizeof(int)), o_nnp = take(P * n * sizeof(int)), o_d2 = take(P * n * sizeof(float));
     const size_t o_win = take(P * nd * sizeof(unsigned long long));
     const size_t o_cs = take(P * (ICP_CELLS_MAX + 1) * sizeof(uint32_t)), o_cf = take(P * ICP_CELLS_MAX * sizeof(uint32_t));
     const size_t o_items = take(P * nd * sizeof(float4));
@@ -630,6 +694,7 @@ int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cl
     a.src_t = reinterpret_cast<float *>(slab + o_srct);
     a.moved = reinterpret_cast<float *>(slab + o_moved);
     a.nn = reinterpret_cast<int *>(slab + o_nn);
+    a.nn_prev = reinterpret_cast<int *>(slab + o_nnp);
     a.d2 = reinterpret_cast<float *>(slab + o_d2);
     a.winner = reinterpret_cast<unsigned long long *>(slab + o_win);
     a.cell_start = reinterpret_cast<uint32_t *>(slab + o_cs);
