@@ -1,6 +1,6 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, bench lines (C2 default with the CPU leg, C1, C2-5mm, C3), ncu launch list and
-# one full capture of the voting kernel.  usage (repo root on the GPU box): bash tools/gpu_round.sh TAG
+# One gpurun call: GPU parity tests, bench lines (C3 default with the CPU leg and the reference arm, C2, C1, C2-5mm, C4),
+# ncu launch list of the default command, full captures of the voting kernel (C2 and quarter-scale C3), ICP timing.  usage (repo root on the GPU box): bash tools/gpu_round.sh TAG
 TAG=${1:-r1}
 O=gpurun_out
 mkdir -p $O
@@ -16,7 +16,10 @@ timeout 300 python bench.py --workload c4 --steps 2 --warmup 3 > $O/bench_c4_$TA
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_launches_$TAG.log 2>&1
 bash tools/gpu_prof.sh $TAG c2
-bash tools/gpu_prof.sh $TAG c3
+bash tools/gpu_prof.sh $TAG c3s
+timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:ppf_vote_kernel -s 3 -c 1 --csv \
+    --log-file $O/dram_c3_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_dram_c3_$TAG.log 2>&1
+python tools/icp_bench.py > $O/icp_bench_$TAG.json 2> $O/icp_bench_$TAG.err
 for f in c3 c3_ref c2 c2_ref c1 c2_5mm c4; do python - <<PY
 import json
 try:
