@@ -267,6 +267,7 @@ def run_b200(args, wl):
 
     # ---- offline stage: model upload + table build (reported, not part of the step) ---------------
     dms = [ctx.upload_cloud(library[k]) for k in my_models]
+    ctx.table_build_from_cloud(dms[0], wl.angle_step, wl.dist_step).free()  # untimed: first use loads the kernels
     t0 = time.perf_counter()
     tables = [ctx.table_build_from_cloud(dm, wl.angle_step, wl.dist_step) for dm in dms]
     table_build_ms = 1e3 * (time.perf_counter() - t0)
