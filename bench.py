@@ -277,17 +277,36 @@ def run_b200(args, wl):
     scene_pinned = torch.from_numpy(np.ascontiguousarray(wl.scene, np.float32)).pin_memory()
     n_s = wl.scene.shape[0]
 
+    # ---- several GPUs: the record exchange is fused into the vote epilogue (NVLink peer stores) -----------
+    p2p = world > 1 and not lib_mode and args.exchange == "p2p"
+    peer_sets, step_no = [], [0]
+    if p2p:
+        for _ in range(2):  # two buffer sets, alternating per step: a rank may be one step ahead of a peer that still clusters
+            own_ptr, handle = ctx.hyp_buffer_create(chunk * world)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            peer_sets.append([own_ptr if r == rank else ctx.hyp_buffer_open(handles[r]) for r in range(world)])
+
     def align(ds, collect=None):
         """vote (this rank's shard) -> all-gather -> cluster, once per model of this rank; returns the last (poses, votes)."""
         res = (np.zeros((0, 4, 4), np.float32), np.zeros(0, np.uint32))
         for dm, table in zip(dms, tables):
-            ctx.vote_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, local_buf.data_ptr())
+            if p2p:
+                peers = peer_sets[step_no[0] % 2]
+                step_no[0] += 1
+                ctx.vote_scatter_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, peers, rank, world)
+            else:
+                ctx.vote_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, local_buf.data_ptr())
             if collect is not None:  # untimed bookkeeping pass: work counters and kernel time of every model
                 st = ctx.vote_stats()
                 for k, v in st.items():
                     collect[k] = collect.get(k, 0) + v
                 collect["vote_ms"] = collect.get("vote_ms", 0.0) + ctx.timings()["vote_ms"]
-            if world > 1 and not lib_mode:
+            if p2p:
+                with torch.cuda.stream(stream):
+                    dist.barrier()  # every rank's records have landed in every buffer
+                res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=peers[rank], n=n_ref)
+            elif world > 1 and not lib_mode:
                 with torch.cuda.stream(stream):
                     ordered = sharding.all_gather_hypotheses(local_buf, n_ref, world, dist)
                 res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=ordered.data_ptr(), n=n_ref)
@@ -387,8 +406,9 @@ def run_b200(args, wl):
                        "n_ref": n_ref, "angle_step_deg": 12, "dist_step": float(wl.dist_step),
                        "table_entries": int(info.n_entries), "accumulator_slices": int(info.n_slices),
                        "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode
-                                    else f"reference points interleaved over {world} rank(s), table + scene replicated, "
-                                         f"all-gather of 64 B hypotheses" if world > 1 else "single GPU"),
+                                    else (f"reference points interleaved over {world} rank(s), table + scene replicated, 64 B "
+                                          f"hypotheses exchanged by " + ("the vote epilogue's NVLink peer stores" if p2p
+                                                                         else "an NCCL all-gather")) if world > 1 else "single GPU"),
                        "models_per_step": len(library),
                        "l2": "256 MiB memset between steps, outside the per-step CUDA-event brackets"},
             "ms_per_pose": ms_per_step / len(library),
@@ -442,6 +462,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="reference points in the CPU sample (0 = sized from a timing probe: ~15 s of CPU work per pass)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="several GPUs: records written into every peer's buffer by the vote epilogue (default) or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     from yolo_ppf_pose_estimation_b200 import workloads

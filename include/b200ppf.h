@@ -168,6 +168,26 @@ int b200ppf_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_tab
 int b200ppf_vote_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
                         const b200ppf_cloud *scene, size_t ref_first, size_t ref_step,
                         size_t ref_count, b200ppf_hypothesis *hyps_device);
+/* Several GPUs (one process / context per GPU): the exchange of the 64-byte records — the one collective on
+ * the path (north_star: "an NCCL allgather ... collects the pose hypotheses for clustering") — fused into the
+ * vote epilogue.  The pose kernel writes record k of this rank into slot slot_first + k*slot_step of EVERY
+ * buffer in peer_buffers (its own and the peers' buffers mapped through CUDA IPC, i.e. NVLink peer stores), so
+ * with slot_first = rank, slot_step = world every GPU ends up with the complete array in reference order.  A
+ * barrier across ranks (any: NCCL, MPI) must separate this call from the clustering that reads the buffer.
+ *   hyp_buffer_create   cudaMalloc'd buffer of n_records + its 64-byte IPC handle (send it to the peers)
+ *   hyp_buffer_open     map a peer's buffer from its handle (another process, same node)
+ *   hyp_buffer_download records first .. first+count-1 to the host (after the context stream has drained)
+ *   hyp_buffer_release  unmap (opened_from_handle = 1) or free (0) */
+int b200ppf_hyp_buffer_create(b200ppf_ctx *ctx, size_t n_records, b200ppf_hypothesis **buffer,
+                              unsigned char ipc_handle[64]);
+int b200ppf_hyp_buffer_open(b200ppf_ctx *ctx, const unsigned char ipc_handle[64], b200ppf_hypothesis **buffer);
+int b200ppf_hyp_buffer_download(b200ppf_ctx *ctx, const b200ppf_hypothesis *buffer, size_t first, size_t count,
+                                b200ppf_hypothesis *host);
+int b200ppf_hyp_buffer_release(b200ppf_ctx *ctx, b200ppf_hypothesis *buffer, int opened_from_handle);
+int b200ppf_vote_scatter_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
+                                const b200ppf_cloud *scene, size_t ref_first, size_t ref_step,
+                                size_t ref_count, b200ppf_hypothesis *const *peer_buffers, int n_peers,
+                                size_t slot_first, size_t slot_step);
 /* counters of the last vote on this context: pairs examined, pairs in radius (the metric's
  * "pairs voted"), non-empty bucket lookups, votes cast */
 int b200ppf_vote_stats(b200ppf_ctx *ctx, uint64_t *stats4);

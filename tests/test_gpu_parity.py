@@ -475,6 +475,24 @@ def test_k3_other_angle_steps(ctx, oracle, bottle, dev_crop, step_deg):
         assert np.array_equal(acc, ref), f"accumulator differs for reference {s_r}"
 
 
+def test_k3_peer_scatter_epilogue(ctx, dev_bottle, dev_crop, table_fused):
+    """The multi-GPU exchange fused into the vote epilogue: two "ranks" (here two calls on one GPU) write their
+    interleaved shares into BOTH record buffers; each buffer then equals the single-launch result."""
+    full = ctx.vote(dev_bottle, table_fused, dev_crop, 0, 1)
+    n = len(full)
+    bufs = [ctx.hyp_buffer_create(n)[0] for _ in range(2)]
+    for rank in range(2):
+        count = (n - rank + 1) // 2
+        ctx.vote_scatter_device(dev_bottle, table_fused, dev_crop, rank, 2, count, bufs, rank, 2)
+    for b in bufs:
+        got = ctx.download_hypotheses(b, n)
+        assert got.tobytes() == full.tobytes()
+        ctx.hyp_buffer_release(b, False)
+    from yolo_ppf_pose_estimation_b200 import capi
+    with pytest.raises(capi.B200PPFError):
+        ctx.vote_scatter_device(dev_bottle, table_fused, dev_crop, 0, 1, n, [], 0, 1)
+
+
 def test_k3_alpha_bins_on_device(ctx):
     from yolo_ppf_pose_estimation_b200 import capi
     rng = np.random.default_rng(5)

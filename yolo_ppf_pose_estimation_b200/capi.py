@@ -76,6 +76,11 @@ SYMBOLS = {
     "b200ppf_table_load": (_i, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "b200ppf_vote": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "b200ppf_vote_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
+    "b200ppf_vote_scatter_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp, _i, _sz, _sz]),
+    "b200ppf_hyp_buffer_create": (_i, [_vp, _sz, C.POINTER(_vp), _vp]),
+    "b200ppf_hyp_buffer_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "b200ppf_hyp_buffer_download": (_i, [_vp, _vp, _sz, _sz, _vp]),
+    "b200ppf_hyp_buffer_release": (_i, [_vp, _vp, _i]),
     "b200ppf_vote_stats": (_i, [_vp, _vp]),
     "b200ppf_vote_debug_pairs": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "b200ppf_vote_debug_accumulator": (_i, [_vp, _vp, _vp, _sz, _vp]),
@@ -252,6 +257,34 @@ class Context:
         """Asynchronous on the context stream; hyps_device_ptr is a device address (64 B per reference)."""
         self.check(lib().b200ppf_vote_device(self._h, model._h, table._h, scene._h, ref_first, ref_step,
                                              ref_count, _as_ptr(hyps_device_ptr)))
+
+    def hyp_buffer_create(self, n_records):
+        """-> (device address, 64-byte IPC handle) of a record buffer peers can map"""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self.check(lib().b200ppf_hyp_buffer_create(self._h, n_records, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def hyp_buffer_open(self, handle: bytes):
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self.check(lib().b200ppf_hyp_buffer_open(self._h, buf, C.byref(ptr)))
+        return ptr.value
+
+    def hyp_buffer_release(self, ptr, opened_from_handle):
+        self.check(lib().b200ppf_hyp_buffer_release(self._h, C.c_void_p(ptr), 1 if opened_from_handle else 0))
+
+    def vote_scatter_device(self, model, table, scene, ref_first, ref_step, ref_count, peer_ptrs, slot_first, slot_step):
+        """vote + pose; record k goes to slot slot_first + k*slot_step of every buffer in peer_ptrs (device addresses)"""
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        self.check(lib().b200ppf_vote_scatter_device(self._h, model._h, table._h, scene._h, ref_first, ref_step, ref_count,
+                                                     arr, len(peer_ptrs), slot_first, slot_step))
+
+    def download_hypotheses(self, ptr, n):
+        """records of a device buffer -> numpy (synchronises the context stream)"""
+        out = np.zeros(n, HYP_DTYPE)
+        self.check(lib().b200ppf_hyp_buffer_download(self._h, C.c_void_p(ptr), 0, n, _p(out)))
+        return out
 
     def vote_stats(self):
         s = np.zeros(4, np.uint64)

@@ -561,7 +561,78 @@ int b200ppf_vote_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200
                         b200ppf_hypothesis *hyps_device) {
     CHECK_CTX(ctx);
     if (ref_count && !hyps_device) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: null output pointer");
-    return k3_vote(ctx, model, t, scene, ref_first, ref_step, ref_count, hyps_device);
+    return k3_vote(ctx, model, t, scene, ref_first, ref_step, ref_count, &hyps_device, 1, 0, 1);
+}
+
+/* ---- multi-GPU exchange fused into the vote epilogue -------------------------------------------- */
+int b200ppf_vote_scatter_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,
+                                const b200ppf_cloud *scene, size_t ref_first, size_t ref_step, size_t ref_count,
+                                b200ppf_hypothesis *const *peer_buffers, int n_peers, size_t slot_first,
+                                size_t slot_step) {
+    CHECK_CTX(ctx);
+    if (!peer_buffers || n_peers < 1) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote scatter: no output buffers");
+    for (int g = 0; g < n_peers; ++g)
+        if (!peer_buffers[g]) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote scatter: null peer buffer");
+    if (slot_step == 0) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote scatter: slot step must be >= 1");
+    return k3_vote(ctx, model, t, scene, ref_first, ref_step, ref_count, peer_buffers, n_peers, slot_first, slot_step);
+}
+
+int b200ppf_hyp_buffer_create(b200ppf_ctx *ctx, size_t n_records, b200ppf_hypothesis **buffer,
+                              unsigned char ipc_handle[64]) {
+    CHECK_CTX(ctx);
+    if (!buffer) return fail_msg(ctx, B200PPF_ERR_INVALID, "hypothesis buffer: null argument");
+    *buffer = nullptr;
+    DeviceGuard guard(ctx->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle travels as 64 bytes");
+    b200ppf_hypothesis *p = nullptr;
+    PPF_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(1, n_records) * sizeof(b200ppf_hypothesis)));  // cudaMalloc: IPC-exportable
+    PPF_CUDA(ctx, cudaMemset(p, 0, std::max<size_t>(1, n_records) * sizeof(b200ppf_hypothesis)));
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) {
+            cudaFree(p);
+            return fail_msg(ctx, B200PPF_ERR_CUDA, cudaGetErrorString(e));
+        }
+        memcpy(ipc_handle, &h, 64);
+    }
+    *buffer = p;
+    return B200PPF_OK;
+}
+
+int b200ppf_hyp_buffer_open(b200ppf_ctx *ctx, const unsigned char ipc_handle[64], b200ppf_hypothesis **buffer) {
+    CHECK_CTX(ctx);
+    if (!ipc_handle || !buffer) return fail_msg(ctx, B200PPF_ERR_INVALID, "hypothesis buffer: null argument");
+    *buffer = nullptr;
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    void *p = nullptr;
+    PPF_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *buffer = static_cast<b200ppf_hypothesis *>(p);
+    return B200PPF_OK;
+}
+
+int b200ppf_hyp_buffer_download(b200ppf_ctx *ctx, const b200ppf_hypothesis *buffer, size_t first, size_t count,
+                                b200ppf_hypothesis *host) {
+    CHECK_CTX(ctx);
+    if (!buffer || (count && !host)) return fail_msg(ctx, B200PPF_ERR_INVALID, "hypothesis buffer: null argument");
+    DeviceGuard guard(ctx->device);
+    if (count)
+        PPF_CUDA(ctx, cudaMemcpyAsync(host, buffer + first, count * sizeof(b200ppf_hypothesis), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200PPF_OK;
+}
+
+int b200ppf_hyp_buffer_release(b200ppf_ctx *ctx, b200ppf_hypothesis *buffer, int opened_from_handle) {
+    CHECK_CTX(ctx);
+    if (!buffer) return B200PPF_OK;
+    DeviceGuard guard(ctx->device);
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (opened_from_handle) PPF_CUDA(ctx, cudaIpcCloseMemHandle(buffer));
+    else PPF_CUDA(ctx, cudaFree(buffer));
+    return B200PPF_OK;
 }
 
 int b200ppf_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
@@ -575,7 +646,8 @@ int b200ppf_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_tab
         PPF_CUDA(ctx, cudaMalloc(&ctx->d_hyps, ref_count * sizeof(b200ppf_hypothesis)));
         ctx->hyps_cap = ref_count;
     }
-    int rc = k3_vote(ctx, model, t, scene, ref_first, ref_step, ref_count, ctx->d_hyps);
+    b200ppf_hypothesis *const target = ctx->d_hyps;
+    int rc = k3_vote(ctx, model, t, scene, ref_first, ref_step, ref_count, &target, 1, 0, 1);
     if (rc) return rc;
     if (ref_count)
         PPF_CUDA(ctx, cudaMemcpyAsync(hyps_host, ctx->d_hyps, ref_count * sizeof(b200ppf_hypothesis),
@@ -699,7 +771,8 @@ int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf
         PPF_CUDA(ctx, cudaMalloc(&ctx->d_hyps, ref_count * sizeof(b200ppf_hypothesis)));
         ctx->hyps_cap = ref_count;
     }
-    int rc = k3_vote(ctx, model, t, scene, 0, ref_rate, ref_count, ctx->d_hyps);
+    b200ppf_hypothesis *const reg_target = ctx->d_hyps;
+    int rc = k3_vote(ctx, model, t, scene, 0, ref_rate, ref_count, &reg_target, 1, 0, 1);
     if (rc) return rc;
     rc = k4_cluster(ctx, ctx->d_hyps, ref_count, pos_thr, rot_thr, poses16, votes, n_out);
     if (rc) return rc;

@@ -459,12 +459,23 @@ ppf_vote_kernel(const VoteArgs a) {
     }
 }
 
+// Where the 64-byte records go.  Single GPU: one buffer, record r in slot r.  Several GPUs: the epilogue IS the
+// all-gather — every rank writes its record r straight into slot (slot_first + r * slot_step) of every peer's
+// buffer over NVLink (peer pointers from cudaIpcOpenMemHandle), so the gathered array is complete and already in
+// reference order on every GPU when the kernels have finished; no staging copy, no NCCL all-gather, no reorder.
+constexpr int MAX_PEERS = 16;
+struct PeerTargets {
+    b200ppf_hypothesis *base[MAX_PEERS];
+    int n;
+    uint32_t slot_first, slot_step;
+};
+
 // pose of every peak: one thread per reference point
 __global__ void ppf_peak_pose_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ snrm,
                                      const float4 *__restrict__ mpos, const float4 *__restrict__ mnrm,
                                      uint32_t ref_first, uint32_t ref_step, uint32_t ref_count,
                                      const unsigned long long *__restrict__ peaks, BinParams bp,
-                                     b200ppf_hypothesis *__restrict__ out) {
+                                     const PeerTargets out) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= ref_count) return;
     const uint32_t s_r = ref_first + r * ref_step;
@@ -481,7 +492,14 @@ __global__ void ppf_peak_pose_kernel(const float4 *__restrict__ spos, const floa
     h.model_index = i;
     h.alpha_bin = bin;
     h.scene_index = s_r;
-    out[r] = h;
+    const size_t slot = (size_t)out.slot_first + (size_t)r * out.slot_step;
+    const uint4 *src = reinterpret_cast<const uint4 *>(&h);
+    for (int g = 0; g < out.n; ++g) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out.base[g] + slot);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = src[q];  // 4 x 16 bytes: one full 64-byte record per peer
+    }
+    if (out.n > 1) __threadfence_system();
 }
 
 // parity hook: per-scene-point quantities of one reference point, exactly as phases A/B see them
@@ -715,7 +733,14 @@ size_t k3_accumulator_budget(const b200ppf_ctx *ctx) {
 }
 
 int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
-            size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *hyps_device) {
+            size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *const *targets, int n_targets,
+            size_t slot_first, size_t slot_step) {
+    if (n_targets < 1 || n_targets > MAX_PEERS) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: 1..16 output buffers");
+    PeerTargets out;
+    for (int g = 0; g < MAX_PEERS; ++g) out.base[g] = g < n_targets ? targets[g] : nullptr;
+    out.n = n_targets;
+    out.slot_first = (uint32_t)slot_first;
+    out.slot_step = (uint32_t)slot_step;
     int rc = check_vote_inputs(ctx, t, scene, ref_first, ref_step, ref_count);
     if (rc) return rc;
     if (!model || model->n != t->info.n_model)
@@ -729,8 +754,7 @@ int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t
     BinParams bp = t->bp;
     bp.mode = ctx->alpha_mode;
     PPF_LAUNCH(ctx, ppf_peak_pose_kernel, (unsigned)((ref_count + 127) / 128), 128, 0, scene->pos, scene->nrm,
-               model->pos, model->nrm, (uint32_t)ref_first, (uint32_t)ref_step, (uint32_t)ref_count, ctx->d_peaks, bp,
-               hyps_device);
+               model->pos, model->nrm, (uint32_t)ref_first, (uint32_t)ref_step, (uint32_t)ref_count, ctx->d_peaks, bp, out);
     cudaEventRecord(ctx->ev_vote[3], ctx->stream);
     ctx->vote_timed = true;
     return B200PPF_OK;

@@ -112,7 +112,8 @@ int k2_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int32_t *d4, ui
                  size_t *n_found);
 int k2_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host);
 int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
-            size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *hyps_device);
+            size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *const *targets, int n_targets,
+            size_t slot_first, size_t slot_step);
 int k3_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
                    uint8_t *in_radius, int32_t *d4, float *alpha_s);
 int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
