@@ -108,7 +108,8 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
                                                         const uint32_t *__restrict__ cell_start,
                                                         const uint32_t *__restrict__ cell_rank, HashParams hp,
                                                         uint32_t k, const float *a, float pos_thr, float rot_thr,
-                                                        const volatile uint32_t *state, F f) {
+                                                        const volatile uint32_t *state, const bool &leaders_only_now,
+                                                        F f) {
     const int cx = cell_of(a[3], hp.inv_cell), cy = cell_of(a[7], hp.inv_cell), cz = cell_of(a[11], hp.inv_cell);
     uint32_t seen[27];
     int n_seen = 0;
@@ -125,7 +126,45 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
                     const uint32_t j = cell_rank[s];
                     if (j >= k) break;  // ranks ascend inside a bucket (stable sort)
                     const uint32_t sj = state[j];
-                    if (ONLY_LEADERS ? sj != ST_LEADER : sj == ST_MEMBER) continue;
+                    // once the visitor knows it is blocked (leaders_only_now), an undecided neighbour can no longer
+                    // change its fate — only a LEADER can (it makes the pose a MEMBER): skip the rest untested
+                    if ((ONLY_LEADERS || leaders_only_now) ? sj != ST_LEADER : sj == ST_MEMBER) continue;
+                    const PoseRows pj = poses[j];
+                    const float ddx = a[3] - pj.r0.w, ddy = a[7] - pj.r1.w, ddz = a[11] - pj.r2.w;
+                    if (!(sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz) < pos_thr)) continue;
+                    float bb[12];
+                    rows_to_array(pj, bb);
+                    if (poses_within(a, bb, pos_thr, rot_thr) && f(j)) return;
+                }
+            }
+}
+
+// Leaders found so far are also kept in per-bucket lists (same slots as the bucket's poses, filled from its
+// start by atomic append): "is there an earlier leader within bounds" — the question that turns a pose into a
+// MEMBER, and the only one the assignment asks — then costs a scan of a few leaders per neighbouring bucket
+// instead of the bucket's whole population (10 000 poses on one object in config 3).  An entry whose store has
+// not landed yet reads as NONE and is simply not seen this round.  f(rank j) returns true to stop.
+template <class F>
+__device__ __forceinline__ void for_each_earlier_leader_within(const PoseRows *__restrict__ poses,
+                                                               const uint32_t *__restrict__ cell_start,
+                                                               const volatile uint32_t *leader_cnt,
+                                                               const volatile uint32_t *leader_list, HashParams hp,
+                                                               uint32_t k, const float *a, float pos_thr, float rot_thr, F f) {
+    const int cx = cell_of(a[3], hp.inv_cell), cy = cell_of(a[7], hp.inv_cell), cz = cell_of(a[11], hp.inv_cell);
+    uint32_t seen[27];
+    int n_seen = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const uint32_t h = cell_hash(cx + dx, cy + dy, cz + dz, hp.mask);
+                bool dup = false;
+                for (int q = 0; q < n_seen; ++q) dup |= (seen[q] == h);
+                if (dup) continue;
+                seen[n_seen++] = h;
+                const uint32_t b = cell_start[h], cnt = min(leader_cnt[h], cell_start[h + 1] - b);
+                for (uint32_t s = b; s < b + cnt; ++s) {
+                    const uint32_t j = leader_list[s];
+                    if (j >= k) continue;  // later leaders and not-yet-written slots (NONE)
                     const PoseRows pj = poses[j];
                     const float ddx = a[3] - pj.r0.w, ddy = a[7] - pj.r1.w, ddz = a[11] - pj.r2.w;
                     if (!(sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz) < pos_thr)) continue;
@@ -140,29 +179,46 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
 __global__ void __launch_bounds__(128)
 cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
                      const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
-                     volatile uint32_t *state, uint32_t *__restrict__ undecided, int first_round) {
+                     volatile uint32_t *state, uint32_t *__restrict__ undecided, uint32_t *leader_cnt,
+                     volatile uint32_t *leader_list) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n || state[k] != ST_UNDECIDED) return;
     float a[12];
     rows_to_array(poses[k], a);
     bool blocked = false, member = false;
-    for_each_earlier_within<false>(poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state, [&](uint32_t j) {
-        const uint32_t sj = state[j];
-        if (sj == ST_LEADER) {
-            member = true;
-            return true;
-        }
-        if (sj == ST_UNDECIDED) {
-            blocked = true;
-            // no leader exists before the first round ends: one undecided earlier neighbour settles "not a
-            // leader yet", and the rest of the O(cluster size) scan cannot make this pose a member
-            if (first_round) return true;
-        }
-        return false;
+    // fast path: an earlier leader within bounds, from the per-bucket leader lists
+    for_each_earlier_leader_within(poses, cell_start, leader_cnt, leader_list, hp, k, a, pos_thr, rot_thr, [&](uint32_t) {
+        member = true;
+        return true;
     });
-    if (member) state[k] = ST_MEMBER;
-    else if (!blocked) state[k] = ST_LEADER;
-    else atomicAdd(undecided, 1u);
+    if (!member) {
+        // otherwise the states decide: the first earlier pose within bounds that is a LEADER makes this one a MEMBER,
+        // the first that is still UNDECIDED blocks it for this round (MEMBERs are skipped unseen); a pose that finds
+        // neither — the only case that scans its whole neighbourhood — is a LEADER
+        const bool never = false;
+        for_each_earlier_within<false>(poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state, never, [&](uint32_t j) {
+            const uint32_t sj = state[j];
+            if (sj == ST_LEADER) {
+                member = true;
+                return true;
+            }
+            if (sj == ST_UNDECIDED) {
+                blocked = true;
+                return true;
+            }
+            return false;
+        });
+    }
+    if (member) {
+        state[k] = ST_MEMBER;
+    } else if (!blocked) {
+        const uint32_t h = cell_hash(cell_of(a[3], hp.inv_cell), cell_of(a[7], hp.inv_cell), cell_of(a[11], hp.inv_cell), hp.mask);
+        leader_list[cell_start[h] + atomicAdd(&leader_cnt[h], 1u)] = k;
+        __threadfence();
+        state[k] = ST_LEADER;
+    } else {
+        atomicAdd(undecided, 1u);
+    }
 }
 
 // exclusive prefix sum of the leader flags -> cluster creation index of every leader
@@ -233,7 +289,8 @@ leader_index_kernel(const uint32_t *__restrict__ state, uint32_t n, const uint32
 __global__ void __launch_bounds__(128)
 cluster_assign_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
                       const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
-                      const uint32_t *__restrict__ state, const uint32_t *__restrict__ leader_id,
+                      const uint32_t *__restrict__ state, const uint32_t *__restrict__ leader_cnt,
+                      const uint32_t *__restrict__ leader_list, const uint32_t *__restrict__ leader_id,
                       const uint32_t *__restrict__ votes, const uint32_t *__restrict__ order,
                       uint32_t *__restrict__ assign_sorted, uint32_t *__restrict__ assign_input,
                       uint32_t *__restrict__ cluster_votes, uint32_t *__restrict__ cluster_size) {
@@ -246,8 +303,8 @@ cluster_assign_kernel(const PoseRows *__restrict__ poses, const uint32_t *__rest
         float a[12];
         rows_to_array(poses[k], a);
         uint32_t best = NONE;
-        for_each_earlier_within<true>(poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state, [&](uint32_t j) {
-            if (state[j] == ST_LEADER) best = min(best, j);
+        for_each_earlier_leader_within(poses, cell_start, leader_cnt, leader_list, hp, k, a, pos_thr, rot_thr, [&](uint32_t j) {
+            best = min(best, j);
             return false;
         });
         c = best != NONE ? leader_id[best] : 0u;  // a MEMBER always has an earlier leader; guard only
@@ -369,7 +426,8 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     const size_t o_keys0 = take(n), o_keys1 = take(n), o_ord0 = take(n), o_ord1 = take(n), o_ck0 = take(n),
                  o_ck1 = take(n), o_cr0 = take(n), o_cr1 = take(n), o_votes = take(n), o_state = take(n),
                  o_lid = take(n), o_as = take(n), o_cv = take(n), o_cs = take(n), o_cell = take((size_t)n_cells + 1),
-                 o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12);
+                 o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12),
+                 o_lcnt = take(n_cells);
     uint32_t *pool = nullptr;
     PPF_CUDA(ctx, cudaMallocAsync(&pool, words * sizeof(uint32_t), st));
     keys[0] = pool + o_keys0; keys[1] = pool + o_keys1; order[0] = pool + o_ord0; order[1] = pool + o_ord1;
@@ -378,6 +436,8 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     cl_votes = pool + o_cv; cl_size = pool + o_cs; cell_start = pool + o_cell; block_sums = pool + o_bs;
     small = pool + o_small; d_out = reinterpret_cast<float *>(pool + o_out);
     poses = reinterpret_cast<PoseRows *>(pool + o_poses);
+    uint32_t *leader_cnt = pool + o_lcnt;
+    PPF_CUDA(ctx, cudaMemsetAsync(leader_cnt, 0, (size_t)n_cells * sizeof(uint32_t), st));
     // state .. cl_size are contiguous: one memset clears state (UNDECIDED), leader ids, assignments, cluster sums
     PPF_CUDA(ctx, cudaMemsetAsync(state, 0, (o_cell - o_state) * sizeof(uint32_t), st));
     PPF_CUDA(ctx, cudaMemsetAsync(small, 0, (16 + 48) * sizeof(uint32_t), st));
@@ -414,6 +474,9 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     PPF_LAUNCH(ctx, cluster_cell_offsets_kernel, (n_cells + 1 + 255) / 256, 256, 0, cell_keys_sorted, n, n_cells,
                cell_start);
 
+    // per-bucket leader lists live in the first sort's key buffer (free by now), slots unset = NONE
+    uint32_t *leader_list = keys[0];
+    PPF_CUDA(ctx, cudaMemsetAsync(leader_list, 0xFF, (size_t)n * sizeof(uint32_t), st));
     // ordered independent-set rounds until nothing is undecided
     const unsigned gr = (n + 127) / 128;
     for (int iter = 0;; ++iter) {
@@ -421,7 +484,7 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
         for (int r = 0; r < rounds; ++r) {
             PPF_CUDA(ctx, cudaMemsetAsync(small + 1, 0, sizeof(uint32_t), st));
             PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, cell_rank, hp, n, pos_thr, rot_thr,
-                       state, small + 1, (iter == 0 && r == 0) ? 1 : 0);
+                       state, small + 1, leader_cnt, leader_list);
         }
         PPF_CUDA(ctx, cudaMemcpyAsync(h_small + 1, small + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         PPF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -432,7 +495,7 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     PPF_LAUNCH(ctx, leader_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, n_scan_blocks, small + 2);
     PPF_LAUNCH(ctx, leader_index_kernel, n_scan_blocks, SCAN_BLOCK, 0, state, n, block_sums, leader_id);
     PPF_LAUNCH(ctx, cluster_assign_kernel, gr, 128, 0, poses, cell_start, cell_rank, hp, n, pos_thr, rot_thr, state,
-               leader_id, votes, ord, assign_sorted, ctx->d_assign, cl_votes, cl_size);
+               leader_cnt, leader_list, leader_id, votes, ord, assign_sorted, ctx->d_assign, cl_votes, cl_size);
     PPF_LAUNCH(ctx, cluster_top3_kernel, 1, 1024, 0, cl_votes, small + 2, small + 3);
     PPF_LAUNCH(ctx, cluster_average_kernel, 3, 256, 0, poses, assign_sorted, n, small + 3, cl_votes, cl_size, d_out,
                small + 6);
