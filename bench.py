@@ -440,7 +440,7 @@ def run_b200(args, wl):
         }
         if world == 1 and not args.no_cpu and not lib_mode:
             ob, hm = oracle_table(wl)
-            f0, st0, cnt = pick_cpu_sample(hm, wl, 1, 15.0, args.cpu_sample)
+            f0, st0, cnt = pick_cpu_sample(hm, wl, 1, 30.0, args.cpu_sample)
             t0 = time.perf_counter()
             _, cst = hm.vote(wl.model, wl.scene, f0, st0, cnt, n_threads=1)
             dt = time.perf_counter() - t0
@@ -460,7 +460,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", help="c1 | c2 | c2_5mm | c3 (default) | c3s | c4 | c4s (workloads.py)")
     ap.add_argument("--cpu-sample", type=int, default=0,
-                    help="reference points in the CPU sample (0 = sized from a timing probe: ~15 s of CPU work per pass)")
+                    help="reference points in the CPU sample (0 = sized from timed passes: ~30 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="several GPUs: records written into every peer's buffer by the vote epilogue (default) or NCCL all-gather")

@@ -87,6 +87,29 @@ def test_hot_loop_alpha_bin_equals_literal_form_and_oracle(oracle):
             assert exact[:-2].max() <= nal - 1
 
 
+def test_constant_shift_binning_over_many_angle_steps():
+    """The kernel's vote arithmetic (phase cells, hot words, wrap through the unsigned max — alpha_bin_phase, the
+    host build of the device functions) equals PCL's literal double-precision form for steps whose 2*pi/step is an
+    integer (8 ... 720 positions: the constant-shift path) and for arbitrary steps (per-entry path), on random
+    angles and on differences placed within a few ulps of every bin edge."""
+    from yolo_ppf_pose_estimation_b200 import capi
+    rng = np.random.default_rng(7)
+    steps = [np.float32(2 * np.pi / k) for k in (8, 12, 30, 36, 60, 90, 180, 360, 720)]
+    steps += [np.float32(x) for x in rng.uniform(0.02, 0.9, 6)]
+    for step in steps:
+        n = 60_000
+        am = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+        as_ = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+        T = 2 * np.pi / float(step)
+        k = rng.integers(0, int(T) + 1, n)
+        as2 = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+        am2 = ((k * np.float64(step) - np.pi + as2.astype(np.float64) + np.pi) % (2 * np.pi) - np.pi).astype(np.float32)
+        am2 = (am2.view(np.int32) + rng.integers(-3, 4, n).astype(np.int32)).view(np.float32)
+        ok = np.abs(am2) <= np.float32(3.14159274)
+        fast, exact = capi.debug_alpha_bins(np.concatenate([am, am2[ok]]), np.concatenate([as_, as2[ok]]), step, 0)
+        assert np.array_equal(fast, exact), float(step)
+
+
 def test_synthetic_clouds():
     from yolo_ppf_pose_estimation_b200 import synth
     m = synth.synth_model(5000, 1)
