@@ -92,7 +92,7 @@ typedef struct b200ppf_table_info {
 /* per-stage device times of the last call on this context, milliseconds (CUDA events) */
 typedef struct b200ppf_timings {
     float upload_ms, features_ms, keys_ms, sort_ms, csr_ms, grid_ms, vote_ms, pose_ms, cluster_ms,
-        transform_ms, icp_ms;
+        transform_ms, icp_ms, prep_ms;
 } b200ppf_timings;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -237,6 +237,59 @@ typedef struct b200ppf_icp_params {
 int b200ppf_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cloud *scene,
                        const b200ppf_icp_params *params, double *poses16, size_t n_poses,
                        double *residuals, uint64_t *iterations);
+
+/* ---- scene pre-processing ("next" row): the stages between the YOLO crop and the PPF engine -------------
+ * What the reference runs on every cropped object before matching (src/YOLO_cropping_ppf_test.cpp:96-103,
+ * :120-121), each a PCL operator on the host there and a device stage here, chained without leaving HBM:
+ *     Subsampling(leaf)            include/CloudProcessing.h:359-377  pcl::VoxelGrid<PointXYZ>
+ *     OutlierProcessing(50, thr)   include/CloudProcessing.h:340-358  pcl::StatisticalOutlierRemoval<PointXYZ>
+ *     NormalEstimation(30)         include/CloudProcessing.h:378-401  pcl::NormalEstimationOMP<PointXYZ, Normal>
+ *     EdgeExtraction(0.03)         include/CloudProcessing.h:402-427  curvature > threshold
+ *     PointCloudXYZNormalToMat     include/CloudProcessing.h:163-190  normals re-normalised, N x 6 rows
+ * A cloud made by upload_xyz has zero normals; normal_estimation fills normals and curvature in place.
+ * Results that PCL leaves unspecified are fixed as: a voxel's points are summed in input order; neighbours at
+ * equal distance are ordered by index. */
+int b200ppf_cloud_upload_xyz(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride_floats, b200ppf_cloud **out);
+/* rows of stride_floats floats: x y z at 0..2, the normal at normal_offset_floats and the curvature at
+ * curvature_offset_floats (each >= 3, or 0 to leave it out); every other float of a row is written as 0 */
+int b200ppf_cloud_download(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, float *host, size_t stride_floats,
+                           size_t normal_offset_floats, size_t curvature_offset_floats);
+/* [PCL] filters/impl/voxel_grid.hpp VoxelGrid::applyFilter: one centroid per occupied leaf, in ascending leaf
+ * index (x fastest).  A leaf so small that the index overflows an int returns a copy of the input, as PCL does
+ * (b200ppf_last_error then holds PCL's warning). */
+int b200ppf_voxel_grid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float leaf3[3], b200ppf_cloud **out);
+/* parity hook: the k nearest neighbours of every point (itself included), rows of k sorted by (squared
+ * distance, index); idx_host / d2_host are n*k, either may be NULL.  k <= min(n, 128). */
+int b200ppf_knn(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, int k, uint32_t *idx_host, float *d2_host);
+/* [PCL] filters/impl/statistical_outlier_removal.hpp applyFilterIndices (negative = false): drops the points
+ * whose mean distance to their mean_k nearest neighbours exceeds mean + stddev_mul * stddev over the cloud.
+ * Needs n > mean_k (PCL reads past its neighbour list otherwise) and mean_k <= 127.  Optional outputs: the kept
+ * indices (capacity n), the per-point mean distances (n) and the threshold. */
+int b200ppf_statistical_outlier_removal(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stddev_mul,
+                                        b200ppf_cloud **out, uint32_t *kept_indices_host, float *distances_host,
+                                        double *threshold);
+/* [PCL] features/impl/normal_3d_omp.hpp computeFeature with setKSearch(k): normal = eigenvector of the smallest
+ * eigenvalue of the neighbourhood covariance (pcl::eigen33), flipped towards viewpoint3 (NULL = the origin,
+ * PCL's default), curvature = lambda_0 / trace.  covariance_mode 0 = PCL >= 1.12 (sums shifted by the first
+ * neighbour), 1 = PCL 1.8-1.11 (raw sums).  k <= 128. */
+#define B200PPF_COVARIANCE_SHIFTED 0
+#define B200PPF_COVARIANCE_RAW 1
+int b200ppf_normal_estimation(b200ppf_ctx *ctx, b200ppf_cloud *cloud, int k, const float viewpoint3[3],
+                              int covariance_mode);
+/* EdgeExtraction: the points whose curvature exceeds the threshold, in order, with their normals */
+int b200ppf_curvature_edges(b200ppf_ctx *ctx, const b200ppf_cloud *in, float curvature_threshold, b200ppf_cloud **out);
+/* PointCloudXYZNormalToMat: n /= (float)sqrt(nx*nx + ny*ny + nz*nz) where that length exceeds 1e-5, in place */
+int b200ppf_normalize_normals(b200ppf_ctx *ctx, b200ppf_cloud *cloud);
+
+/* test hook (no context, no GPU): the neighbour query of the device kernels — the same __host__ __device__
+ * function — run on the CPU over a host-built grid of cell edge cell_edge (0 = the library's choice).
+ * mode 0: idx / d2 (n*k) as b200ppf_knn; 1: mean_dist (n) = mean distance to the k-1 nearest other points, as
+ * the outlier removal forms it; 2: normals4 (n*4) = nx ny nz curvature, as normal_estimation forms them.
+ * Like b200ppf_debug_alpha_bins with a NULL context this exists for the parity tests only; no product entry
+ * point routes through it. */
+int b200ppf_debug_knn_host(const float *xyz, size_t n, size_t stride_floats, int k, int mode, float cell_edge,
+                           const float viewpoint3[3], int covariance_mode, uint32_t *idx, float *d2, float *mean_dist,
+                           float *normals4);
 
 /* ---- PPFRegistration::align in one call: vote + cluster, final16 = results.front() -------- */
 int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t,

@@ -27,7 +27,7 @@ assert HYP_DTYPE.itemsize == 64
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (g++, no external dependencies)."""
-    src = [os.path.join(_HERE, f) for f in ("ppf_oracle.cpp", "icp_oracle.cpp", "ppf_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ppf_oracle.cpp", "icp_oracle.cpp", "prep_oracle.cpp", "ppf_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -96,6 +96,13 @@ def _declare(L):
                                   C.c_int, vp, vp, vp, vp]
     L.oracle_register.restype = sz
     L.oracle_max_threads.restype = C.c_int
+    L.oracle_voxel_grid.argtypes = [vp, sz, sz, vp, vp, C.POINTER(C.c_int)]
+    L.oracle_voxel_grid.restype = sz
+    L.oracle_knn.argtypes = [vp, sz, sz, C.c_int, vp, vp, C.c_int]
+    L.oracle_sor.argtypes = [vp, sz, sz, C.c_int, C.c_double, vp, vp, C.POINTER(C.c_double), C.c_int]
+    L.oracle_sor.restype = sz
+    L.oracle_normals.argtypes = [vp, sz, sz, C.c_int, vp, C.c_int, vp, C.c_int]
+    L.oracle_renormalize_normals.argtypes = [vp, sz, sz]
 
 
 def _f32(a):
@@ -313,3 +320,55 @@ def icp_refine(model, scene, poses, max_iterations=100, tolerance=0.005, rejecti
     if rc != 0:
         raise RuntimeError("oracle_icp_refine failed")
     return P, res, int(iters.value)
+
+
+# ---- scene pre-processing (prep_oracle.cpp): VoxelGrid, StatisticalOutlierRemoval, NormalEstimationOMP -----------
+COV_SHIFTED, COV_RAW = 0, 1  # computeMeanAndCovarianceMatrix of PCL >= 1.12 / PCL 1.8-1.11
+
+
+def voxel_grid(xyz, leaf):
+    """pcl::VoxelGrid<PointXYZ>: (N, >=3) -> (M, 3) centroids in ascending voxel order; (cloud, overflowed)."""
+    xyz = _f32(xyz)
+    leaf3 = _f32(np.broadcast_to(np.asarray(leaf, np.float32), (3,)))
+    out = np.zeros((xyz.shape[0], 3), np.float32)
+    status = C.c_int(0)
+    m = lib().oracle_voxel_grid(_p(xyz), xyz.shape[0], xyz.shape[1], _p(leaf3), _p(out), C.byref(status))
+    return out[:m].copy(), bool(status.value)
+
+
+def knn(xyz, k, n_threads=None):
+    """exact k nearest neighbours (self included), rows sorted by (d2, index): (idx (N,k) uint32, d2 (N,k) float32)"""
+    xyz = _f32(xyz)
+    k = min(int(k), xyz.shape[0])
+    idx = np.zeros((xyz.shape[0], k), np.uint32)
+    d2 = np.zeros((xyz.shape[0], k), np.float32)
+    lib().oracle_knn(_p(xyz), xyz.shape[0], xyz.shape[1], k, _p(idx), _p(d2), n_threads or max_threads())
+    return idx, d2
+
+
+def statistical_outlier_removal(xyz, mean_k=50, std_mul=1.0, n_threads=None):
+    """pcl::StatisticalOutlierRemoval<PointXYZ>: -> (keep mask (N,) bool, mean distances (N,), threshold)"""
+    xyz = _f32(xyz)
+    n = xyz.shape[0]
+    dist = np.zeros(n, np.float32)
+    keep = np.zeros(n, np.uint8)
+    thr = C.c_double(0.0)
+    lib().oracle_sor(_p(xyz), n, xyz.shape[1], mean_k, float(std_mul), _p(dist), _p(keep), C.byref(thr),
+                     n_threads or max_threads())
+    return keep.astype(bool), dist, thr.value
+
+
+def normals(xyz, k=30, viewpoint=(0.0, 0.0, 0.0), cov_mode=COV_SHIFTED, n_threads=None):
+    """pcl::NormalEstimationOMP<PointXYZ, Normal>::compute with setKSearch(k): -> (N, 4) [nx ny nz curvature]"""
+    xyz = _f32(xyz)
+    vp3 = _f32(viewpoint)
+    out = np.zeros((xyz.shape[0], 4), np.float32)
+    lib().oracle_normals(_p(xyz), xyz.shape[0], xyz.shape[1], k, _p(vp3), cov_mode, _p(out), n_threads or max_threads())
+    return out
+
+
+def renormalize_normals(nrm):
+    """CloudProcessor::PointCloudXYZNormalToMat's normal re-normalisation; returns a new (N, 3) array"""
+    out = _f32(nrm).copy()
+    lib().oracle_renormalize_normals(_p(out), out.shape[0], out.shape[1])
+    return out

@@ -138,6 +138,19 @@ int oracle_icp_refine(const float *model, size_t n_model, const float *scene, si
                       float tolerance, float rejection_scale, int num_levels, double *poses16, size_t n_poses,
                       double *residuals, uint64_t *iterations_run);
 
+/* "Next" row: the scene pre-processing between the YOLO crop and the PPF engine —
+ * reference include/CloudProcessing.h:359-377 (pcl::VoxelGrid), :340-358 (pcl::StatisticalOutlierRemoval),
+ * :378-401 (pcl::NormalEstimationOMP, k = 30), :402-427 (curvature edges), :163-190 (normals re-normalised).
+ * Restated in prep_oracle.cpp from the PCL files named there (parity unpinned).  xyz clouds are float32 rows
+ * of `stride` floats starting with x y z. */
+size_t oracle_voxel_grid(const float *xyz, size_t n, size_t stride, const float *leaf3, float *out_xyz, int *status);
+void oracle_knn(const float *xyz, size_t n, size_t stride, int k, uint32_t *idx, float *d2, int n_threads);
+size_t oracle_sor(const float *xyz, size_t n, size_t stride, int mean_k, double std_mul, float *distances, uint8_t *keep,
+                  double *threshold, int n_threads);
+void oracle_normals(const float *xyz, size_t n, size_t stride, int k, const float *viewpoint3, int cov_mode, float *out4,
+                    int n_threads);
+void oracle_renormalize_normals(float *nrm, size_t n, size_t stride);
+
 #ifdef __cplusplus
 }
 #endif

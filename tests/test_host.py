@@ -38,7 +38,7 @@ def test_struct_layouts_match_the_header():
     from yolo_ppf_pose_estimation_b200 import capi
     assert capi.HYP_DTYPE.itemsize == 64 and capi.SIG_DTYPE.itemsize == 20
     assert C.sizeof(capi.TableInfo) == 4 * 8 + 4 * 4 + 8 * 4 + 4 * 4
-    assert C.sizeof(capi.Timings) == 11 * 4
+    assert C.sizeof(capi.Timings) == 12 * 4
     assert capi.HYP_DTYPE.fields["votes"][1] == 48 and capi.HYP_DTYPE.fields["scene_index"][1] == 60
 
 

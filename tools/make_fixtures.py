@@ -14,7 +14,12 @@ it is frozen here as small float32 fixtures:
                                     include/CloudProcessing.h:279-332 around the surrogate YOLO box
                                     u in [536,631], v in [211,402]    (C1 scene)
 
-Usage: OPENCV_IO_ENABLE_OPENEXR=1 python tools/make_fixtures.py
+  scene_crop_raw.npz                the crop before any filtering: raw back-projected points inside the
+                                    frustum (xyz only) — the input of the pre-processing stages
+                                    Subsampling / OutlierProcessing / NormalEstimation
+                                    (include/CloudProcessing.h:340-401)        (`--raw-only` writes just this)
+
+Usage: OPENCV_IO_ENABLE_OPENEXR=1 python tools/make_fixtures.py [--raw-only]
 """
 import os
 import sys
@@ -107,6 +112,15 @@ def main():
     import cv2
 
     os.makedirs(OUT, exist_ok=True)
+    if "--raw-only" in sys.argv:
+        depth = cv2.imread(os.path.join(REF, "data", "1_depth.exr"), cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        if depth.ndim == 3:
+            depth = depth[:, :, 0]
+        xyz, _, _ = backproject(depth)
+        crop_raw = xyz[frustum_crop(xyz, depth, (536, 211, 631, 402))]
+        print("scene_crop_raw", crop_raw.shape)
+        np.savez_compressed(os.path.join(OUT, "scene_crop_raw.npz"), cloud=crop_raw.astype(np.float32))
+        return 0
     bottle = read_ply_ascii(os.path.join(REF, "data", "bottle_remesh_meter_normalized.ply"))
     print("bottle", bottle.shape)
     for leaf, name in ((0.01, "bottle_1cm"), (0.005, "bottle_5mm")):
@@ -132,6 +146,7 @@ def main():
     crop = np.concatenate([crop[:, :3], nrm], axis=1).astype(np.float32)
     print("scene_crop_1cm", crop_raw.shape, "->", crop.shape)
     np.savez_compressed(os.path.join(OUT, "scene_crop_1cm.npz"), cloud=crop)
+    np.savez_compressed(os.path.join(OUT, "scene_crop_raw.npz"), cloud=crop_raw.astype(np.float32))
 
 
 if __name__ == "__main__":

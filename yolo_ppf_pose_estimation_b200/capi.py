@@ -34,7 +34,7 @@ class TableInfo(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("upload_ms", "features_ms", "keys_ms", "sort_ms", "csr_ms", "grid_ms",
-                                         "vote_ms", "pose_ms", "cluster_ms", "transform_ms", "icp_ms")]
+                                         "vote_ms", "pose_ms", "cluster_ms", "transform_ms", "icp_ms", "prep_ms")]
 
 
 class IcpParams(C.Structure):
@@ -91,6 +91,16 @@ SYMBOLS = {
     "b200ppf_cluster_assignment": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "b200ppf_icp_refine": (_i, [_vp, _vp, _vp, C.POINTER(IcpParams), _vp, _sz, _vp, C.POINTER(C.c_uint64)]),
     "b200ppf_transform": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "b200ppf_cloud_upload_xyz": (_i, [_vp, _vp, _sz, _sz, C.POINTER(_vp)]),
+    "b200ppf_cloud_download": (_i, [_vp, _vp, _vp, _sz, _sz, _sz]),
+    "b200ppf_voxel_grid": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "b200ppf_knn": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "b200ppf_statistical_outlier_removal": (_i, [_vp, _vp, _i, C.c_double, C.POINTER(_vp), _vp, _vp,
+                                                 C.POINTER(C.c_double)]),
+    "b200ppf_normal_estimation": (_i, [_vp, _vp, _i, _vp, _i]),
+    "b200ppf_curvature_edges": (_i, [_vp, _vp, _f, C.POINTER(_vp)]),
+    "b200ppf_normalize_normals": (_i, [_vp, _vp]),
+    "b200ppf_debug_knn_host": (_i, [_vp, _sz, _sz, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "b200ppf_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
 }
 
@@ -202,6 +212,56 @@ class Context:
         h = C.c_void_p()
         self.check(lib().b200ppf_cloud_upload(self._h, ptr, n, stride, normal_offset, C.byref(h)))
         return Cloud(self, h)
+
+    # ---- scene pre-processing (reference CloudProcessing.h:340-427) --------------------------------
+    def upload_xyz(self, xyz):
+        """(N, >=3) float32 rows starting with x y z -> device cloud with zero normals"""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        h = C.c_void_p()
+        self.check(lib().b200ppf_cloud_upload_xyz(self._h, _p(xyz), xyz.shape[0], xyz.shape[1], C.byref(h)))
+        return Cloud(self, h)
+
+    def voxel_grid(self, cloud: "Cloud", leaf) -> "Cloud":
+        """pcl::VoxelGrid<PointXYZ>::filter (Subsampling)"""
+        leaf3 = np.ascontiguousarray(np.broadcast_to(np.asarray(leaf, np.float32), (3,)))
+        h = C.c_void_p()
+        self.check(lib().b200ppf_voxel_grid(self._h, cloud._h, _p(leaf3), C.byref(h)))
+        return Cloud(self, h)
+
+    def knn(self, cloud: "Cloud", k):
+        """parity hook: (idx (N,k) uint32, d2 (N,k) float32), rows sorted by (d2, index), self included"""
+        idx = np.zeros((cloud.size, k), np.uint32)
+        d2 = np.zeros((cloud.size, k), np.float32)
+        self.check(lib().b200ppf_knn(self._h, cloud._h, k, _p(idx), _p(d2)))
+        return idx, d2
+
+    def statistical_outlier_removal(self, cloud: "Cloud", mean_k=50, stddev_mul=1.0):
+        """pcl::StatisticalOutlierRemoval<PointXYZ>::filter (OutlierProcessing):
+        -> (filtered Cloud, kept indices, mean distances, threshold)"""
+        n = cloud.size
+        kept = np.zeros(n, np.uint32)
+        dist = np.zeros(n, np.float32)
+        thr = C.c_double(0.0)
+        h = C.c_void_p()
+        self.check(lib().b200ppf_statistical_outlier_removal(self._h, cloud._h, mean_k, float(stddev_mul), C.byref(h),
+                                                             _p(kept), _p(dist), C.byref(thr)))
+        out = Cloud(self, h)
+        return out, kept[:out.size].copy(), dist, thr.value
+
+    def normal_estimation(self, cloud: "Cloud", k=30, viewpoint=None, covariance_mode=0):
+        """pcl::NormalEstimationOMP::compute with setKSearch(k), in place (normals + curvature)"""
+        vp3 = None if viewpoint is None else np.ascontiguousarray(viewpoint, np.float32)
+        self.check(lib().b200ppf_normal_estimation(self._h, cloud._h, k, _p(vp3), covariance_mode))
+
+    def curvature_edges(self, cloud: "Cloud", threshold) -> "Cloud":
+        """CloudProcessor::EdgeExtraction: points with curvature > threshold"""
+        h = C.c_void_p()
+        self.check(lib().b200ppf_curvature_edges(self._h, cloud._h, np.float32(threshold), C.byref(h)))
+        return Cloud(self, h)
+
+    def normalize_normals(self, cloud: "Cloud"):
+        """CloudProcessor::PointCloudXYZNormalToMat's re-normalisation, in place"""
+        self.check(lib().b200ppf_normalize_normals(self._h, cloud._h))
 
     # ---- K1 / K2 -------------------------------------------------------------------------------
     def features_compute(self, model: "Cloud") -> "Features":
@@ -360,6 +420,23 @@ def debug_alpha_bins(alpha_m, alpha_s, angle_step, alpha_mode=ALPHA_MODE_A, ctx:
     return fast, exact
 
 
+def debug_knn_host(xyz, k, mode=0, cell_edge=0.0, viewpoint=None, covariance_mode=0):
+    """The device kernels' neighbour query (one __host__ __device__ function) run on the CPU: a test hook.
+    mode 0 -> (idx, d2); 1 -> mean distances to the k-1 nearest other points; 2 -> (N, 4) normals + curvature."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    n = xyz.shape[0]
+    idx = np.zeros((n, k), np.uint32) if mode == 0 else None
+    d2 = np.zeros((n, k), np.float32) if mode == 0 else None
+    dist = np.zeros(n, np.float32) if mode == 1 else None
+    nrm = np.zeros((n, 4), np.float32) if mode == 2 else None
+    vp3 = None if viewpoint is None else np.ascontiguousarray(viewpoint, np.float32)
+    rc = lib().b200ppf_debug_knn_host(_p(xyz), n, xyz.shape[1], k, mode, np.float32(cell_edge), _p(vp3), covariance_mode,
+                                      _p(idx), _p(d2), _p(dist), _p(nrm))
+    if rc != 0:
+        raise B200PPFError(rc, lib().b200ppf_last_error(None).decode())
+    return (idx, d2) if mode == 0 else (dist if mode == 1 else nrm)
+
+
 class _Handle:
     _free = None
 
@@ -384,6 +461,13 @@ class Cloud(_Handle):
     @property
     def size(self):
         return int(lib().b200ppf_cloud_size(self._h))
+
+    def download(self, curvature=False):
+        """-> (N, 6) [x y z nx ny nz] (the reference's cv::Mat layout), or (N, 7) with the curvature last"""
+        stride = 7 if curvature else 6
+        out = np.zeros((self.size, stride), np.float32)
+        self.ctx.check(lib().b200ppf_cloud_download(self.ctx._h, self._h, _p(out), stride, 3, 6 if curvature else 0))
+        return out
 
 
 class Features(_Handle):

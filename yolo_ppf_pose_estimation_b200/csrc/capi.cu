@@ -741,6 +741,87 @@ int b200ppf_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float 
     return k5_transform(ctx, cloud, pose16, out_host, out_stride_floats);
 }
 
+/* ---- scene pre-processing (prep.cu) ------------------------------------------------------ */
+
+int b200ppf_cloud_upload_xyz(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride, b200ppf_cloud **out) {
+    CHECK_CTX(ctx);
+    if (!out) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: null output pointer");
+    *out = nullptr;
+    if (n && !host) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: null host pointer");
+    if (stride < 3) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: rows must hold at least x y z");
+    if (n > 0xFFFFFFF0ull) return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "cloud upload: more than 2^32 points");
+    return prep_upload_xyz(ctx, host, n, stride, out);
+}
+
+int b200ppf_cloud_download(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, float *host, size_t stride, size_t noff,
+                           size_t coff) {
+    CHECK_CTX(ctx);
+    if (!cloud || (cloud->n && !host)) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud download: null argument");
+    if (stride < 3 || (noff && (noff < 3 || noff + 3 > stride)) || (coff && (coff < 3 || coff >= stride)) ||
+        (noff && coff && coff >= noff && coff < noff + 3))
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud download: stride / offsets do not describe [x y z .. nx ny nz .. curvature]");
+    return prep_download(ctx, cloud, host, stride, noff, coff);
+}
+
+int b200ppf_voxel_grid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *leaf3, b200ppf_cloud **out) {
+    CHECK_CTX(ctx);
+    if (!in || !leaf3 || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "voxel grid: null argument");
+    *out = nullptr;
+    for (int k = 0; k < 3; ++k)
+        if (!(leaf3[k] > 0.0f) || !std::isfinite(leaf3[k])) return fail_msg(ctx, B200PPF_ERR_INVALID, "voxel grid: leaf size must be positive");
+    ctx->error.clear();
+    return prep_voxel_grid(ctx, in, leaf3, out);
+}
+
+int b200ppf_knn(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, int k, uint32_t *idx_host, float *d2_host) {
+    CHECK_CTX(ctx);
+    if (!cloud) return fail_msg(ctx, B200PPF_ERR_INVALID, "knn: null cloud");
+    if (k < 1 || k > 128 || (size_t)k > std::max<size_t>(1, cloud->n))
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "knn: k must be in 1 .. min(n, 128)");
+    return prep_knn(ctx, cloud, k, idx_host, d2_host);
+}
+
+int b200ppf_statistical_outlier_removal(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stddev_mul,
+                                        b200ppf_cloud **out, uint32_t *kept_host, float *distances_host, double *threshold) {
+    CHECK_CTX(ctx);
+    if (!in || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "statistical outlier removal: null argument");
+    *out = nullptr;
+    if (mean_k < 1 || mean_k > 127) return fail_msg(ctx, B200PPF_ERR_INVALID, "statistical outlier removal: mean_k must be in 1 .. 127");
+    if (in->n < (size_t)mean_k + 1)
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "statistical outlier removal: the cloud needs more than mean_k points");
+    return prep_sor(ctx, in, mean_k, stddev_mul, out, kept_host, distances_host, threshold);
+}
+
+int b200ppf_normal_estimation(b200ppf_ctx *ctx, b200ppf_cloud *cloud, int k, const float *viewpoint3, int cov_mode) {
+    CHECK_CTX(ctx);
+    if (!cloud) return fail_msg(ctx, B200PPF_ERR_INVALID, "normal estimation: null cloud");
+    if (k < 1 || k > 128) return fail_msg(ctx, B200PPF_ERR_INVALID, "normal estimation: k must be in 1 .. 128");
+    if (cov_mode != B200PPF_COVARIANCE_SHIFTED && cov_mode != B200PPF_COVARIANCE_RAW)
+        return fail_msg(ctx, B200PPF_ERR_INVALID, "normal estimation: unknown covariance mode");
+    return prep_normals(ctx, cloud, k, viewpoint3, cov_mode);
+}
+
+int b200ppf_curvature_edges(b200ppf_ctx *ctx, const b200ppf_cloud *in, float threshold, b200ppf_cloud **out) {
+    CHECK_CTX(ctx);
+    if (!in || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "curvature edges: null argument");
+    *out = nullptr;
+    return prep_curvature_edges(ctx, in, threshold, out);
+}
+
+int b200ppf_normalize_normals(b200ppf_ctx *ctx, b200ppf_cloud *cloud) {
+    CHECK_CTX(ctx);
+    if (!cloud) return fail_msg(ctx, B200PPF_ERR_INVALID, "normalize normals: null cloud");
+    return prep_renormalize(ctx, cloud);
+}
+
+int b200ppf_debug_knn_host(const float *xyz, size_t n, size_t stride, int k, int mode, float cell_edge, const float *viewpoint3,
+                           int cov_mode, uint32_t *idx, float *d2, float *mean_dist, float *normals4) {
+    if ((n && !xyz) || stride < 3 || k < 1 || k > 128 || (size_t)k > std::max<size_t>(1, n) || mode < 0 || mode > 2 ||
+        (mode == 0 && (!idx || !d2)) || (mode == 1 && (!mean_dist || k < 2)) || (mode == 2 && !normals4))
+        return fail_msg(nullptr, B200PPF_ERR_INVALID, "debug knn: bad argument");
+    return prep_debug_knn_host(xyz, n, stride, k, mode, cell_edge, viewpoint3, cov_mode, idx, d2, mean_dist, normals4);
+}
+
 /* ---- align -------------------------------------------------------------------------------- */
 
 int b200ppf_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cloud *scene,

@@ -130,6 +130,19 @@ int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cl
                   float tolerance, float rejection_scale, int num_levels, double *poses16_host, size_t n_poses,
                   double *residuals_host, uint64_t *iterations_host);
 
+// scene pre-processing (prep.cu): voxel grid, k nearest neighbours, outlier removal, normals, curvature edges
+int prep_upload_xyz(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride, b200ppf_cloud **out);
+int prep_download(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, float *host, size_t stride, size_t noff, size_t coff);
+int prep_voxel_grid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *leaf3, b200ppf_cloud **out);
+int prep_knn(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, int k, uint32_t *idx_host, float *d2_host);
+int prep_sor(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stddev_mul, b200ppf_cloud **out, uint32_t *kept_host,
+             float *distances_host, double *threshold_out);
+int prep_normals(b200ppf_ctx *ctx, b200ppf_cloud *cloud, int k, const float *viewpoint3, int cov_mode);
+int prep_curvature_edges(b200ppf_ctx *ctx, const b200ppf_cloud *in, float threshold, b200ppf_cloud **out);
+int prep_renormalize(b200ppf_ctx *ctx, b200ppf_cloud *cloud);
+int prep_debug_knn_host(const float *xyz, size_t n, size_t stride, int k, int mode, float cell_edge, const float *viewpoint3,
+                        int cov_mode, uint32_t *idx, float *d2, float *mean_dist, float *normals4);
+
 // uniform grid over the scene (scene_grid.cu): cells of edge >= search radius, x fastest
 struct GridParams {
     float origin[3];
@@ -154,6 +167,8 @@ struct SceneGrid {
     uint32_t *orig = nullptr;        // cell-sorted position -> original scene index
 };
 
+// grid geometry for a bounding box and a search radius (host); returns the number of cells
+uint32_t scene_grid_params(const float *bbox_min, const float *bbox_max, float radius, GridParams *gp);
 int scene_grid_build(b200ppf_ctx *ctx, const b200ppf_cloud *scene, float radius, SceneGrid *out);
 void scene_grid_free(b200ppf_ctx *ctx, SceneGrid *g);
 

@@ -1,0 +1,961 @@
+// prep.cu — scene pre-processing on the device ("next" row): the stages the reference
+// runs between its YOLO crop and the PPF engine, so that a frame goes crop -> N x 6 scene cloud without
+// leaving HBM.
+//
+//   P1 voxel grid         reference include/CloudProcessing.h:359-377  pcl::VoxelGrid<PointXYZ>
+//                         [PCL] filters/include/pcl/filters/impl/voxel_grid.hpp applyFilter
+//   P2 k nearest          FLANN kd-tree behind StatisticalOutlierRemoval / NormalEstimationOMP
+//      neighbours         [PCL] kdtree/include/pcl/kdtree/impl/kdtree_flann.hpp nearestKSearch
+//   P3 outlier removal    reference :340-358  pcl::StatisticalOutlierRemoval<PointXYZ>(meanK = 50, thresh)
+//                         [PCL] filters/include/pcl/filters/impl/statistical_outlier_removal.hpp
+//   P4 normals+curvature  reference :378-401  pcl::NormalEstimationOMP<PointXYZ, Normal>, k = 30
+//                         [PCL] features/normal_3d.h, common/impl/centroid.hpp, common/impl/eigen.hpp
+//   P5 curvature edges    reference :402-427  EdgeExtraction (curvature > threshold)
+//   P6 renormalise        reference :163-190  PointCloudXYZNormalToMat
+//
+// Data layout: the same float4 SoA cloud the PPF kernels read (pos = x y z 1, nrm = nx ny nz curvature; the PPF
+// kernels never read nrm.w).  Neighbour search: the uniform cell-sorted grid of scene_grid.cu with a cell edge
+// chosen from the point density; one thread per query point, queries taken in cell order so that a warp's
+// candidates are the same few contiguous runs (L1-resident), rings of cells visited until the k-th distance is
+// inside the searched block.  The k best are a sorted list of 64-bit (distance bits, index) words, which is also
+// FLANN's output order (ties by index).  Everything order-dependent follows the CPU checker: voxel sums in
+// original point order, covariance sums in neighbour order, un-fused float arithmetic (-fmad=false).
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "ppf_common.cuh"
+
+namespace b200ppf {
+
+namespace {
+
+constexpr int SCAN_BLOCK = 1024;
+
+// ---- exclusive scan of 0/1 flags (three launches; same shape as K4's leader index) ----------------------------
+__global__ void __launch_bounds__(SCAN_BLOCK)
+flag_count_kernel(const uint32_t *__restrict__ flags, uint32_t n, uint32_t *__restrict__ block_sums) {
+    const uint32_t k = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const int c = __syncthreads_count(k < n && flags[k] != 0u);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = (uint32_t)c;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+flag_scan_blocks_kernel(uint32_t *__restrict__ block_sums, uint32_t n_blocks, uint32_t *__restrict__ total) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += SCAN_BLOCK) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((threadIdx.x & 31) >= (uint32_t)o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_tot[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (threadIdx.x >= (uint32_t)o) wi += t;
+            }
+            warp_tot[threadIdx.x] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+        if (i < n_blocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// rank[k] = number of set flags before k (written for every k)
+__global__ void __launch_bounds__(SCAN_BLOCK)
+flag_rank_kernel(const uint32_t *__restrict__ flags, uint32_t n, const uint32_t *__restrict__ block_sums,
+                 uint32_t *__restrict__ rank) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t k = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t v = (k < n && flags[k] != 0u) ? 1u : 0u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_tot[threadIdx.x], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (threadIdx.x >= (uint32_t)o) wi += t;
+        }
+        warp_tot[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    if (k < n) rank[k] = block_sums[blockIdx.x] + warp_tot[warp] + __popc(m & ((1u << lane) - 1u));
+}
+
+// flags -> rank (exclusive), *total on the host.  block_sums / d_total come from the stream-ordered pool.
+int flag_scan(b200ppf_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t *rank, uint32_t *total_host) {
+    *total_host = 0;
+    if (n == 0) return B200PPF_OK;
+    const uint32_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    uint32_t *block_sums = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&block_sums, ((size_t)nb + 1) * sizeof(uint32_t), ctx->stream));
+    uint32_t *d_total = block_sums + nb;
+    PPF_LAUNCH(ctx, flag_count_kernel, nb, SCAN_BLOCK, 0, flags, n, block_sums);
+    PPF_LAUNCH(ctx, flag_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, nb, d_total);
+    PPF_LAUNCH(ctx, flag_rank_kernel, nb, SCAN_BLOCK, 0, flags, n, block_sums, rank);
+    PPF_CUDA(ctx, cudaMemcpyAsync(total_host, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(block_sums, ctx->stream);
+    return B200PPF_OK;
+}
+
+// ---- bounding box of a device cloud (PCL getMinMax3D) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t float_order(float f) {  // order-preserving float -> uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+inline float float_unorder(uint32_t u) {
+    const uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float4 *__restrict__ pos, uint32_t n, uint32_t *__restrict__ mm) {
+    uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = pos[i];
+        const uint32_t c[3] = {float_order(p.x), float_order(p.y), float_order(p.z)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = min(lo[k], c[k]);
+            hi[k] = max(hi[k], c[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = __reduce_min_sync(0xFFFFFFFFu, lo[k]);
+        hi[k] = __reduce_max_sync(0xFFFFFFFFu, hi[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(mm + k, lo[k]);
+            atomicMax(mm + 3 + k, hi[k]);
+        }
+    }
+}
+
+int cloud_bbox_from_device(b200ppf_ctx *ctx, b200ppf_cloud *c) {
+    for (int k = 0; k < 3; ++k) c->bbox_min[k] = c->bbox_max[k] = 0.0f;
+    if (c->n == 0) return B200PPF_OK;
+    uint32_t *mm = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&mm, 6 * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMemsetAsync(mm, 0xFF, 3 * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMemsetAsync(mm + 3, 0x00, 3 * sizeof(uint32_t), ctx->stream));
+    const unsigned grid = (unsigned)std::min<size_t>((c->n + 255) / 256, (size_t)ctx->sm_count * 8);
+    PPF_LAUNCH(ctx, bbox_kernel, grid, 256, 0, c->pos, (uint32_t)c->n, mm);
+    uint32_t h[6];
+    PPF_CUDA(ctx, cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(mm, ctx->stream);
+    for (int k = 0; k < 3; ++k) {
+        c->bbox_min[k] = float_unorder(h[k]);
+        c->bbox_max[k] = float_unorder(h[3 + k]);
+    }
+    return B200PPF_OK;
+}
+
+// a cloud of n points whose arrays are allocated (pos | nrm in one allocation) but not filled
+int cloud_alloc(b200ppf_ctx *ctx, size_t n, b200ppf_cloud **out) {
+    b200ppf_cloud *c = new (std::nothrow) b200ppf_cloud();
+    if (!c) return fail_msg(ctx, B200PPF_ERR_NOMEM, "pre-processing: out of host memory");
+    c->ctx = ctx;
+    c->n = n;
+    cudaError_t e = cudaMallocAsync(&c->pos, std::max<size_t>(1, 2 * n) * sizeof(float4), ctx->stream);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail_msg(ctx, B200PPF_ERR_NOMEM, "pre-processing: device allocation of the output cloud failed");
+    }
+    c->nrm = c->pos + n;
+    *out = c;
+    return B200PPF_OK;
+}
+
+// ---- P1: voxel grid -------------------------------------------------------------------------------------------
+struct VoxelParams {
+    float inv[3];
+    int min_b[3];
+    int mul[3];
+};
+
+__global__ void __launch_bounds__(256)
+voxel_ids_kernel(const float4 *__restrict__ pos, uint32_t n, VoxelParams vp, uint32_t *__restrict__ ids) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    // ijk = static_cast<int>(std::floor(x * inverse_leaf_size_) - static_cast<float>(min_b_))
+    const int ijk0 = (int)(floorf(p.x * vp.inv[0]) - (float)vp.min_b[0]);
+    const int ijk1 = (int)(floorf(p.y * vp.inv[1]) - (float)vp.min_b[1]);
+    const int ijk2 = (int)(floorf(p.z * vp.inv[2]) - (float)vp.min_b[2]);
+    ids[i] = (uint32_t)(ijk0 * vp.mul[0] + ijk1 * vp.mul[1] + ijk2 * vp.mul[2]);
+}
+
+__global__ void __launch_bounds__(256)
+voxel_heads_kernel(const uint32_t *__restrict__ sorted_ids, uint32_t n, uint32_t *__restrict__ head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || sorted_ids[i] != sorted_ids[i - 1]) ? 1u : 0u;
+}
+
+// starts[v] = first sorted position of voxel v; starts[n_voxels] = n
+__global__ void __launch_bounds__(256)
+voxel_starts_kernel(const uint32_t *__restrict__ head, const uint32_t *__restrict__ rank, uint32_t n, uint32_t n_voxels,
+                    uint32_t *__restrict__ starts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) starts[n_voxels] = n;
+    if (i >= n) return;
+    if (head[i]) starts[rank[i]] = i;
+}
+
+// one thread per voxel: sequential float sum in original point order (the sort is stable), then / count
+__global__ void __launch_bounds__(128)
+voxel_centroid_kernel(const float4 *__restrict__ pos, const uint32_t *__restrict__ order, const uint32_t *__restrict__ starts,
+                      uint32_t n_voxels, float4 *__restrict__ out_pos, float4 *__restrict__ out_nrm) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_voxels) return;
+    const uint32_t first = starts[v], last = starts[v + 1];
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    for (uint32_t i = first; i < last; ++i) {
+        const float4 p = pos[order[i]];
+        cx += p.x;
+        cy += p.y;
+        cz += p.z;
+    }
+    const float cnt = (float)(last - first);
+    out_pos[v] = make_float4(cx / cnt, cy / cnt, cz / cnt, 1.0f);
+    out_nrm[v] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+__global__ void __launch_bounds__(256)
+copy_cloud_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, uint32_t n, float4 *__restrict__ out_pos,
+                  float4 *__restrict__ out_nrm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out_pos[i] = pos[i];
+    out_nrm[i] = nrm[i];
+}
+
+// ---- P2: k nearest neighbours ---------------------------------------------------------------------------------
+enum { KNN_EXPORT = 0, KNN_MEAN_DISTANCE = 1, KNN_NORMAL = 2 };
+
+struct KnnArgs {
+    const float4 *pos;    // cloud, original order
+    const float4 *gpos;   // cloud, cell-sorted
+    const uint32_t *cell_start;
+    const uint32_t *orig;  // cell-sorted position -> original index
+    GridParams gp;
+    float cell;  // cell edge
+    uint32_t n;
+    int k;  // neighbours wanted (self included), <= CAP, <= n
+    // outputs (by mode)
+    uint32_t *out_idx;  // [n*k]
+    float *out_d2;      // [n*k]
+    float *out_dist;    // [n] mean distance to the k-1 nearest other points
+    float4 *out_nrm;    // [n] nx ny nz curvature
+    float vp[3];        // viewpoint
+    int cov_mode;       // 0: sums shifted by the first neighbour (PCL >= 1.12), 1: raw sums
+};
+
+// the query below is __host__ __device__: b200ppf_debug_knn_host runs the very same code on the CPU (test hook,
+// like b200ppf_debug_alpha_bins), so the traversal and the epilogues can be checked without a GPU
+__host__ __device__ __forceinline__ uint32_t f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+__host__ __device__ __forceinline__ float bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+template <typename T>
+__host__ __device__ __forceinline__ T ld_ro(const T *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// [PCL] common/impl/eigen.hpp computeRoots2
+__host__ __device__ __forceinline__ void compute_roots2(float b, float c, float *roots) {
+    roots[0] = 0.0f;
+    float d = b * b - 4.0f * c;
+    if (d < 0.0f) d = 0.0f;
+    const float sd = sqrtf(d);
+    roots[2] = 0.5f * (b + sd);
+    roots[1] = 0.5f * (b - sd);
+}
+
+// [PCL] common/impl/eigen.hpp computeRoots (symmetric 3x3, eigenvalues ascending)
+__host__ __device__ inline void compute_roots(const float *m, float *roots) {
+    const float m00 = m[0], m01 = m[1], m02 = m[2], m11 = m[4], m12 = m[5], m22 = m[8];
+    const float c0 = m00 * m11 * m22 + 2.0f * m01 * m02 * m12 - m00 * m12 * m12 - m11 * m02 * m02 - m22 * m01 * m01;
+    const float c1 = m00 * m11 - m01 * m01 + m00 * m22 - m02 * m02 + m11 * m22 - m12 * m12;
+    const float c2 = m00 + m11 + m22;
+    if (fabsf(c0) < 1.1920929e-07f) {  // std::numeric_limits<float>::epsilon()
+        compute_roots2(c2, c1, roots);
+        return;
+    }
+    const float s_inv3 = (float)(1.0 / 3.0);
+    const float s_sqrt3 = 1.7320508075688772f;  // sqrtf(3.0f)
+    const float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+    const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0f) q = 0.0f;
+    const float rho = sqrtf(-a_over_3);
+    const float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+    const float cos_theta = cosf(theta);
+    const float sin_theta = sinf(theta);
+    roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    float t;
+    if (roots[0] >= roots[1]) t = roots[0], roots[0] = roots[1], roots[1] = t;
+    if (roots[1] >= roots[2]) {
+        t = roots[1], roots[1] = roots[2], roots[2] = t;
+        if (roots[0] >= roots[1]) t = roots[0], roots[0] = roots[1], roots[1] = t;
+    }
+    if (roots[0] <= 0.0f) compute_roots2(c2, c1, roots);
+}
+
+// [PCL] common/impl/eigen.hpp eigen33(mat, eigenvalue, eigenvector): the smallest eigenpair
+__host__ __device__ inline void eigen33_smallest(const float *cov, float *eigenvalue, float *evec) {
+    float scale = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) scale = fmaxf(scale, fabsf(cov[k]));
+    if (scale <= 1.17549435e-38f) scale = 1.0f;  // std::numeric_limits<float>::min()
+    float s[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = cov[k] / scale;
+    float roots[3];
+    compute_roots(s, roots);
+    *eigenvalue = roots[0] * scale;
+    s[0] -= roots[0];
+    s[4] -= roots[0];
+    s[8] -= roots[0];
+    float v[3][3];
+    // rows 0x1, 0x2, 1x2
+    v[0][0] = s[1] * s[5] - s[2] * s[4], v[0][1] = s[2] * s[3] - s[0] * s[5], v[0][2] = s[0] * s[4] - s[1] * s[3];
+    v[1][0] = s[1] * s[8] - s[2] * s[7], v[1][1] = s[2] * s[6] - s[0] * s[8], v[1][2] = s[0] * s[7] - s[1] * s[6];
+    v[2][0] = s[4] * s[8] - s[5] * s[7], v[2][1] = s[5] * s[6] - s[3] * s[8], v[2][2] = s[3] * s[7] - s[4] * s[6];
+    float len[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) len[k] = sqrtf(v[k][0] * v[k][0] + v[k][1] * v[k][1] + v[k][2] * v[k][2]);
+    int best = 0;
+    if (len[1] > len[best]) best = 1;
+    if (len[2] > len[best]) best = 2;
+    const float l = best == 0 ? len[0] : (best == 1 ? len[1] : len[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) evec[k] = (best == 0 ? v[0][k] : (best == 1 ? v[1][k] : v[2][k])) / l;
+}
+
+// one query point (q = its cell-sorted position): the k nearest, then the epilogue of MODE
+template <int CAP, int MODE>
+__host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q) {
+    const float4 pq = a.gpos[q];
+    const int cx = grid_cell_coord(a.gp, pq.x, 0), cy = grid_cell_coord(a.gp, pq.y, 1), cz = grid_cell_coord(a.gp, pq.z, 2);
+    const int dx = a.gp.dims[0], dy = a.gp.dims[1], dz = a.gp.dims[2];
+    const int k = a.k;
+    unsigned long long best[CAP];  // ascending (distance bits << 32 | original index); the first cnt are valid
+    int cnt = 0;
+
+    // candidates of the sorted positions [s0, s1)
+    auto scan_run = [&](uint32_t s0, uint32_t s1) {
+        for (uint32_t s = s0; s < s1; ++s) {
+            const float4 p = ld_ro(a.gpos + s);
+            // FLANN L2_Simple: result += diff * diff over x, y, z
+            const float ex = pq.x - p.x, ey = pq.y - p.y, ez = pq.z - p.z;
+            float d2 = ex * ex;
+            d2 += ey * ey;
+            d2 += ez * ez;
+            const unsigned long long key = ((unsigned long long)f32_bits(d2) << 32) | (unsigned long long)ld_ro(a.orig + s);
+            if (cnt == k && key >= best[k - 1]) continue;
+            int j = cnt < k ? cnt : k - 1;  // slot that opens up
+            while (j > 0 && best[j - 1] > key) {
+                best[j] = best[j - 1];
+                --j;
+            }
+            best[j] = key;
+            if (cnt < k) ++cnt;
+        }
+    };
+
+    int r_max = cx > dx - 1 - cx ? cx : dx - 1 - cx;
+    r_max = cy > r_max ? cy : r_max;
+    r_max = dy - 1 - cy > r_max ? dy - 1 - cy : r_max;
+    r_max = cz > r_max ? cz : r_max;
+    r_max = dz - 1 - cz > r_max ? dz - 1 - cz : r_max;
+    for (int r = 0; r <= r_max; ++r) {
+        // shell of cells at Chebyshev distance exactly r; rows along x are contiguous runs of sorted positions
+        for (int oz = -r; oz <= r; ++oz) {
+            const int z = cz + oz;
+            if (z < 0 || z >= dz) continue;
+            for (int oy = -r; oy <= r; ++oy) {
+                const int y = cy + oy;
+                if (y < 0 || y >= dy) continue;
+                const uint32_t row = ((uint32_t)z * (uint32_t)dy + (uint32_t)y) * (uint32_t)dx;
+                if (oz == -r || oz == r || oy == -r || oy == r) {
+                    const int x0 = cx - r > 0 ? cx - r : 0, x1 = cx + r < dx - 1 ? cx + r : dx - 1;
+                    scan_run(ld_ro(a.cell_start + row + x0), ld_ro(a.cell_start + row + x1 + 1));
+                } else {  // interior row of the shell: only its two end cells (r >= 1 here)
+                    if (cx - r >= 0) scan_run(ld_ro(a.cell_start + row + cx - r), ld_ro(a.cell_start + row + cx - r + 1));
+                    if (cx + r < dx) scan_run(ld_ro(a.cell_start + row + cx + r), ld_ro(a.cell_start + row + cx + r + 1));
+                }
+            }
+        }
+        // every unvisited point is more than (r - margin) cells away along some axis; the margin absorbs the
+        // float rounding of the cell coordinate
+        if (cnt == k && r >= 1) {
+            const float reach = ((float)r - 1e-3f) * a.cell;
+            if (bits_f32((uint32_t)(best[k - 1] >> 32)) <= reach * reach) break;
+        }
+    }
+
+    const uint32_t me = a.orig[q];
+    if (MODE == KNN_EXPORT) {
+        for (int j = 0; j < k; ++j) {
+            a.out_idx[(size_t)me * k + j] = j < cnt ? (uint32_t)best[j] : 0xFFFFFFFFu;
+            a.out_d2[(size_t)me * k + j] = j < cnt ? bits_f32((uint32_t)(best[j] >> 32)) : INFINITY;
+        }
+    } else if (MODE == KNN_MEAN_DISTANCE) {
+        // dist_sum += sqrt(nn_dists[k]) for k = 1 .. mean_k (0 is the query itself); (float)(dist_sum / mean_k)
+        double dist_sum = 0.0;
+        for (int j = 1; j < cnt; ++j) dist_sum += (double)sqrtf(bits_f32((uint32_t)(best[j] >> 32)));
+        a.out_dist[me] = (float)(dist_sum / (double)(k - 1));
+    } else {
+        if (cnt < 3) {
+            const float nan = bits_f32(0x7FC00000u);
+            a.out_nrm[me] = make_float4(nan, nan, nan, nan);
+            return;
+        }
+        // computeMeanAndCovarianceMatrix (float), neighbours in FLANN's order
+        float Kx = 0.0f, Ky = 0.0f, Kz = 0.0f;
+        if (a.cov_mode == 0) {
+            const float4 p0 = a.pos[(uint32_t)best[0]];
+            Kx = p0.x, Ky = p0.y, Kz = p0.z;
+        }
+        float accu[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        for (int j = 0; j < cnt; ++j) {
+            const float4 p = ld_ro(a.pos + (uint32_t)best[j]);
+            const float x = p.x - Kx, y = p.y - Ky, z = p.z - Kz;
+            accu[0] += x * x;
+            accu[1] += x * y;
+            accu[2] += x * z;
+            accu[3] += y * y;
+            accu[4] += y * z;
+            accu[5] += z * z;
+            accu[6] += x;
+            accu[7] += y;
+            accu[8] += z;
+        }
+        const float fcnt = (float)cnt;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) accu[t] /= fcnt;
+        float cov[9];
+        cov[0] = accu[0] - accu[6] * accu[6];
+        cov[1] = accu[1] - accu[6] * accu[7];
+        cov[2] = accu[2] - accu[6] * accu[8];
+        cov[4] = accu[3] - accu[7] * accu[7];
+        cov[5] = accu[4] - accu[7] * accu[8];
+        cov[8] = accu[5] - accu[8] * accu[8];
+        cov[3] = cov[1], cov[6] = cov[2], cov[7] = cov[5];
+        // solvePlaneParameters
+        float ev, nv[3];
+        eigen33_smallest(cov, &ev, nv);
+        const float eig_sum = cov[0] + cov[4] + cov[8];
+        float curvature = 0.0f;
+        if (eig_sum != 0.0f) curvature = fabsf(ev / eig_sum);
+        // flipNormalTowardsViewpoint
+        const float vx = a.vp[0] - pq.x, vy = a.vp[1] - pq.y, vz = a.vp[2] - pq.z;
+        const float cos_theta = vx * nv[0] + vy * nv[1] + vz * nv[2];
+        if (cos_theta < 0.0f) nv[0] *= -1.0f, nv[1] *= -1.0f, nv[2] *= -1.0f;
+        a.out_nrm[me] = make_float4(nv[0], nv[1], nv[2], curvature);
+    }
+}
+
+template <int CAP, int MODE>
+__global__ void __launch_bounds__(128) knn_kernel(const KnnArgs a) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;  // cell-sorted position of the query
+    if (q < a.n) knn_query<CAP, MODE>(a, q);
+}
+
+template <int MODE>
+int knn_launch(b200ppf_ctx *ctx, const KnnArgs &a) {
+    const unsigned grid = (a.n + 127) / 128;
+    void (*kern)(const KnnArgs) = a.k <= 32 ? knn_kernel<32, MODE> : (a.k <= 64 ? knn_kernel<64, MODE> : knn_kernel<128, MODE>);
+    PPF_LAUNCH(ctx, kern, grid, 128, 0, a);
+    return B200PPF_OK;
+}
+
+// cell edge for the neighbour grid: about k/2 points per cell if the cloud were one surface spanning the two
+// largest extents of its bounding box (a wrong guess costs time, not correctness)
+float knn_cell_edge(const b200ppf_cloud *c, int k) {
+    double e[3];
+    for (int t = 0; t < 3; ++t) e[t] = std::max(0.0, (double)c->bbox_max[t] - (double)c->bbox_min[t]);
+    std::sort(e, e + 3);
+    const double area = e[2] * e[1];
+    double h = area > 0.0 ? std::sqrt(0.5 * (double)k * area / (double)std::max<size_t>(1, c->n)) : 0.0;
+    h = std::max(h, e[2] / 1024.0);
+    if (!(h > 0.0)) h = 1e-3;
+    return (float)h;
+}
+
+// grid + neighbour kernel of one mode over `cloud`
+template <int MODE>
+int knn_run(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, KnnArgs a) {
+    SceneGrid grid;
+    int rc = scene_grid_build(ctx, cloud, knn_cell_edge(cloud, a.k), &grid);
+    if (rc == B200PPF_OK) {
+        a.pos = cloud->pos;
+        a.gpos = grid.pos;
+        a.cell_start = grid.cell_start;
+        a.orig = grid.orig;
+        a.gp = grid.gp;
+        a.cell = 1.0f / grid.gp.inv_cell;
+        a.n = (uint32_t)cloud->n;
+        rc = knn_launch<MODE>(ctx, a);
+    }
+    scene_grid_free(ctx, &grid);
+    return rc;
+}
+
+// ---- P3: statistical outlier removal --------------------------------------------------------------------------
+// per-block partial sums of d and d*d (float product, as PCL writes it) in double, fixed tree
+__global__ void __launch_bounds__(256)
+sor_partial_sums_kernel(const float *__restrict__ dist, uint32_t n, double *__restrict__ partial) {
+    __shared__ double sh[2][8];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0, ss = 0.0;
+    if (i < n) {
+        const float d = dist[i];
+        s = (double)d;
+        ss = (double)(d * d);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+        ss += __shfl_down_sync(0xFFFFFFFFu, ss, o);
+    }
+    if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s, sh[1][threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tss = 0.0;
+        for (int w = 0; w < 8; ++w) ts += sh[0][w], tss += sh[1][w];
+        partial[2 * blockIdx.x] = ts;
+        partial[2 * blockIdx.x + 1] = tss;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sor_flag_kernel(const float *__restrict__ dist, uint32_t n, double threshold, uint32_t *__restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = ((double)dist[i] > threshold) ? 0u : 1u;  // removed when distances[i] > distance_threshold
+}
+
+__global__ void __launch_bounds__(256)
+curvature_flag_kernel(const float4 *__restrict__ nrm, uint32_t n, float threshold, uint32_t *__restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (nrm[i].w > threshold) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+compact_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, const uint32_t *__restrict__ flags,
+               const uint32_t *__restrict__ rank, uint32_t n, float4 *__restrict__ out_pos, float4 *__restrict__ out_nrm,
+               uint32_t *__restrict__ out_index) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const uint32_t r = rank[i];
+    out_pos[r] = pos[i];
+    out_nrm[r] = nrm[i];
+    if (out_index) out_index[r] = i;
+}
+
+// keep the flagged points, in order -> new cloud (and, optionally, their indices on the host)
+int compact_cloud(b200ppf_ctx *ctx, const b200ppf_cloud *in, const uint32_t *flags, b200ppf_cloud **out, uint32_t *kept_host) {
+    const uint32_t n = (uint32_t)in->n;
+    uint32_t *rank = nullptr, *index = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&rank, std::max<size_t>(1, n) * sizeof(uint32_t), ctx->stream));
+    uint32_t m = 0;
+    int rc = flag_scan(ctx, flags, n, rank, &m);
+    b200ppf_cloud *c = nullptr;
+    if (rc == B200PPF_OK) rc = cloud_alloc(ctx, m, &c);
+    if (rc == B200PPF_OK && kept_host && m)
+        if (cudaMallocAsync(&index, (size_t)m * sizeof(uint32_t), ctx->stream) != cudaSuccess)
+            rc = fail_msg(ctx, B200PPF_ERR_NOMEM, "pre-processing: device allocation failed");
+    if (rc == B200PPF_OK && n) {
+        compact_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(in->pos, in->nrm, flags, rank, n, c->pos, c->nrm, index);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail_msg(ctx, B200PPF_ERR_CUDA, "pre-processing: compaction launch failed");
+    }
+    if (rc == B200PPF_OK && index)
+        if (cudaMemcpyAsync(kept_host, index, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            rc = fail_msg(ctx, B200PPF_ERR_CUDA, "pre-processing: index download failed");
+    if (rc == B200PPF_OK) rc = cloud_bbox_from_device(ctx, c);  // synchronises the stream
+    cudaFreeAsync(rank, ctx->stream);
+    if (index) cudaFreeAsync(index, ctx->stream);
+    if (rc != B200PPF_OK) {
+        if (c) b200ppf_cloud_free(c);
+        return rc;
+    }
+    *out = c;
+    return B200PPF_OK;
+}
+
+// ---- P6 ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) renormalize_kernel(float4 *__restrict__ nrm, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = nrm[i];
+    // double A = sqrt(nx*nx + ny*ny + nz*nz) with the sum in float; if (A > 0.00001) n /= static_cast<float>(A)
+    const double A = sqrt((double)(v.x * v.x + v.y * v.y + v.z * v.z));
+    if (A > 0.00001) {
+        const float fa = (float)A;
+        v.x /= fa;
+        v.y /= fa;
+        v.z /= fa;
+        nrm[i] = v;
+    }
+}
+
+// ---- download: SoA -> caller's AoS rows through a device staging buffer ----------------------------------------
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, uint32_t n, uint32_t stride, uint32_t noff,
+                 uint32_t coff, float *__restrict__ rows) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i], q = nrm[i];
+    float *r = rows + (size_t)i * stride;
+    for (uint32_t t = 0; t < stride; ++t) r[t] = 0.0f;
+    r[0] = p.x, r[1] = p.y, r[2] = p.z;
+    if (noff) r[noff] = q.x, r[noff + 1] = q.y, r[noff + 2] = q.z;
+    if (coff) r[coff] = q.w;
+}
+
+struct EventTimer {  // prep_ms of the timings block
+    b200ppf_ctx *ctx;
+    explicit EventTimer(b200ppf_ctx *c) : ctx(c) { cudaEventRecord(ctx->ev[0], ctx->stream); }
+    void stop() {
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->timings.prep_ms, ctx->ev[0], ctx->ev[1]);
+    }
+};
+
+}  // namespace
+
+// ================================================================================================================
+// host entry points (called from capi.cu)
+
+int prep_upload_xyz(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride, b200ppf_cloud **out) {
+    const size_t need = std::max<size_t>(1, n) * sizeof(float4);
+    if (ctx->stage_bytes < need) {
+        if (ctx->stage) cudaFreeHost(ctx->stage);
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        PPF_CUDA(ctx, cudaMallocHost(&ctx->stage, need));
+        ctx->stage_bytes = need;
+    }
+    float4 *sp = static_cast<float4 *>(ctx->stage);
+    size_t m = 0;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t i = 0; i < n; ++i) {
+        const float *p = host + i * stride;
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;  // PCL filters skip non-finite points
+        sp[m++] = make_float4(p[0], p[1], p[2], 1.0f);
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], p[k]);
+            hi[k] = std::max(hi[k], p[k]);
+        }
+    }
+    b200ppf_cloud *c = nullptr;
+    int rc = cloud_alloc(ctx, m, &c);
+    if (rc != B200PPF_OK) return rc;
+    for (int k = 0; k < 3; ++k) {
+        c->bbox_min[k] = m ? lo[k] : 0.0f;
+        c->bbox_max[k] = m ? hi[k] : 0.0f;
+    }
+    cudaError_t e = cudaSuccess;
+    if (m) e = cudaMemcpyAsync(c->pos, sp, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && m) e = cudaMemsetAsync(c->nrm, 0, m * sizeof(float4), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the staging buffer is reused by the next upload
+    if (e != cudaSuccess) {
+        b200ppf_cloud_free(c);
+        return fail_msg(ctx, B200PPF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = c;
+    return B200PPF_OK;
+}
+
+int prep_download(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, float *host, size_t stride, size_t noff, size_t coff) {
+    const size_t n = cloud->n;
+    if (n == 0) return B200PPF_OK;
+    float *rows = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&rows, n * stride * sizeof(float), ctx->stream));
+    PPF_LAUNCH(ctx, pack_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, cloud->pos, cloud->nrm, (uint32_t)n, (uint32_t)stride,
+               (uint32_t)noff, (uint32_t)coff, rows);
+    PPF_CUDA(ctx, cudaMemcpyAsync(host, rows, n * stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(rows, ctx->stream);
+    return B200PPF_OK;
+}
+
+int prep_voxel_grid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *leaf3, b200ppf_cloud **out) {
+    const uint32_t n = (uint32_t)in->n;
+    EventTimer timer(ctx);
+    if (n == 0) {
+        int rc = cloud_alloc(ctx, 0, out);
+        timer.stop();
+        return rc;
+    }
+    VoxelParams vp;
+    for (int k = 0; k < 3; ++k) vp.inv[k] = 1.0f / leaf3[k];  // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+    // "Leaf size is too small for the input dataset. Integer indices would overflow." -> PCL returns the input
+    int64_t d[3];
+    for (int k = 0; k < 3; ++k) d[k] = (int64_t)((in->bbox_max[k] - in->bbox_min[k]) * vp.inv[k]) + 1;
+    const bool overflow = d[0] * d[1] * d[2] > (int64_t)INT32_MAX;
+    if (overflow) {
+        b200ppf_cloud *c = nullptr;
+        int rc = cloud_alloc(ctx, n, &c);
+        if (rc != B200PPF_OK) return rc;
+        copy_cloud_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(in->pos, in->nrm, n, c->pos, c->nrm);
+        ctx->launches++;
+        for (int k = 0; k < 3; ++k) c->bbox_min[k] = in->bbox_min[k], c->bbox_max[k] = in->bbox_max[k];
+        timer.stop();
+        ctx->error = "voxel grid: leaf size is too small for the input dataset, integer indices would overflow; input returned unchanged";
+        *out = c;
+        return B200PPF_OK;
+    }
+    int div_b[3];
+    for (int k = 0; k < 3; ++k) {
+        vp.min_b[k] = (int)floorf(in->bbox_min[k] * vp.inv[k]);
+        const int max_b = (int)floorf(in->bbox_max[k] * vp.inv[k]);
+        div_b[k] = max_b - vp.min_b[k] + 1;
+    }
+    vp.mul[0] = 1, vp.mul[1] = div_b[0], vp.mul[2] = div_b[0] * div_b[1];
+    const uint64_t n_cells = (uint64_t)div_b[0] * (uint64_t)div_b[1] * (uint64_t)div_b[2];
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < n_cells) ++bits;
+
+    uint32_t *ids[2] = {nullptr, nullptr}, *ord[2] = {nullptr, nullptr}, *head = nullptr, *rank = nullptr, *starts = nullptr;
+    for (int b = 0; b < 2; ++b) {
+        PPF_CUDA(ctx, cudaMallocAsync(&ids[b], (size_t)n * sizeof(uint32_t), ctx->stream));
+        PPF_CUDA(ctx, cudaMallocAsync(&ord[b], (size_t)n * sizeof(uint32_t), ctx->stream));
+    }
+    PPF_CUDA(ctx, cudaMallocAsync(&head, (size_t)n * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&rank, (size_t)n * sizeof(uint32_t), ctx->stream));
+    const unsigned gb = (n + 255) / 256;
+    PPF_LAUNCH(ctx, voxel_ids_kernel, gb, 256, 0, in->pos, n, vp, ids[0]);
+    bool in_alt = false;
+    int rc = radix_sort_u32(ctx, ids[0], ids[1], ord[0], ord[1], nullptr, nullptr, n, bits, /*v0_iota=*/true, &in_alt);
+    if (rc != B200PPF_OK) return rc;
+    const int s = in_alt ? 1 : 0;
+    PPF_LAUNCH(ctx, voxel_heads_kernel, gb, 256, 0, ids[s], n, head);
+    uint32_t m = 0;
+    rc = flag_scan(ctx, head, n, rank, &m);
+    if (rc != B200PPF_OK) return rc;
+    PPF_CUDA(ctx, cudaMallocAsync(&starts, ((size_t)m + 1) * sizeof(uint32_t), ctx->stream));
+    b200ppf_cloud *c = nullptr;
+    rc = cloud_alloc(ctx, m, &c);
+    if (rc != B200PPF_OK) return rc;
+    PPF_LAUNCH(ctx, voxel_starts_kernel, gb, 256, 0, head, rank, n, m, starts);
+    PPF_LAUNCH(ctx, voxel_centroid_kernel, (m + 127) / 128, 128, 0, in->pos, ord[s], starts, m, c->pos, c->nrm);
+    rc = cloud_bbox_from_device(ctx, c);
+    for (int b = 0; b < 2; ++b) {
+        cudaFreeAsync(ids[b], ctx->stream);
+        cudaFreeAsync(ord[b], ctx->stream);
+    }
+    cudaFreeAsync(head, ctx->stream);
+    cudaFreeAsync(rank, ctx->stream);
+    cudaFreeAsync(starts, ctx->stream);
+    timer.stop();
+    if (rc != B200PPF_OK) {
+        b200ppf_cloud_free(c);
+        return rc;
+    }
+    *out = c;
+    return B200PPF_OK;
+}
+
+int prep_knn(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, int k, uint32_t *idx_host, float *d2_host) {
+    const size_t n = cloud->n;
+    if (n == 0) return B200PPF_OK;
+    KnnArgs a{};
+    a.k = k;
+    PPF_CUDA(ctx, cudaMallocAsync(&a.out_idx, n * (size_t)k * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&a.out_d2, n * (size_t)k * sizeof(float), ctx->stream));
+    EventTimer timer(ctx);
+    int rc = knn_run<KNN_EXPORT>(ctx, cloud, a);
+    timer.stop();
+    if (rc == B200PPF_OK && idx_host)
+        PPF_CUDA(ctx, cudaMemcpyAsync(idx_host, a.out_idx, n * (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (rc == B200PPF_OK && d2_host)
+        PPF_CUDA(ctx, cudaMemcpyAsync(d2_host, a.out_d2, n * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeAsync(a.out_idx, ctx->stream);
+    cudaFreeAsync(a.out_d2, ctx->stream);
+    return rc;
+}
+
+int prep_sor(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stddev_mul, b200ppf_cloud **out, uint32_t *kept_host,
+             float *distances_host, double *threshold_out) {
+    const uint32_t n = (uint32_t)in->n;
+    KnnArgs a{};
+    a.k = mean_k + 1;
+    float *dist = nullptr;
+    double *partial = nullptr;
+    uint32_t *flags = nullptr;
+    const uint32_t nb = (n + 255) / 256;
+    PPF_CUDA(ctx, cudaMallocAsync(&dist, (size_t)n * sizeof(float), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&partial, (size_t)nb * 2 * sizeof(double), ctx->stream));
+    PPF_CUDA(ctx, cudaMallocAsync(&flags, (size_t)n * sizeof(uint32_t), ctx->stream));
+    a.out_dist = dist;
+    EventTimer timer(ctx);
+    int rc = knn_run<KNN_MEAN_DISTANCE>(ctx, in, a);
+    if (rc != B200PPF_OK) return rc;
+    PPF_LAUNCH(ctx, sor_partial_sums_kernel, nb, 256, 0, dist, n, partial);
+    std::vector<double> hp((size_t)nb * 2);
+    PPF_CUDA(ctx, cudaMemcpyAsync(hp.data(), partial, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (distances_host)
+        PPF_CUDA(ctx, cudaMemcpyAsync(distances_host, dist, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0, sq_sum = 0.0;
+    for (uint32_t b = 0; b < nb; ++b) sum += hp[2 * b], sq_sum += hp[2 * b + 1];
+    // mean / variance / threshold exactly as PCL forms them (all points are valid here)
+    const double mean = sum / (double)n;
+    const double variance = (sq_sum - sum * sum / (double)n) / ((double)n - 1.0);
+    const double stddev = sqrt(variance);
+    const double thr = mean + stddev_mul * stddev;
+    if (threshold_out) *threshold_out = thr;
+    PPF_LAUNCH(ctx, sor_flag_kernel, nb, 256, 0, dist, n, thr, flags);
+    rc = compact_cloud(ctx, in, flags, out, kept_host);
+    timer.stop();
+    cudaFreeAsync(dist, ctx->stream);
+    cudaFreeAsync(partial, ctx->stream);
+    cudaFreeAsync(flags, ctx->stream);
+    return rc;
+}
+
+int prep_normals(b200ppf_ctx *ctx, b200ppf_cloud *cloud, int k, const float *viewpoint3, int cov_mode) {
+    if (cloud->n == 0) return B200PPF_OK;
+    KnnArgs a{};
+    a.k = (int)std::min<size_t>((size_t)k, cloud->n);
+    a.out_nrm = cloud->nrm;
+    for (int t = 0; t < 3; ++t) a.vp[t] = viewpoint3 ? viewpoint3[t] : 0.0f;
+    a.cov_mode = cov_mode;
+    EventTimer timer(ctx);
+    int rc = knn_run<KNN_NORMAL>(ctx, cloud, a);
+    timer.stop();
+    if (rc == B200PPF_OK) PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int prep_curvature_edges(b200ppf_ctx *ctx, const b200ppf_cloud *in, float threshold, b200ppf_cloud **out) {
+    const uint32_t n = (uint32_t)in->n;
+    uint32_t *flags = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&flags, std::max<size_t>(1, n) * sizeof(uint32_t), ctx->stream));
+    EventTimer timer(ctx);
+    if (n) PPF_LAUNCH(ctx, curvature_flag_kernel, (n + 255) / 256, 256, 0, in->nrm, n, threshold, flags);
+    int rc = compact_cloud(ctx, in, flags, out, nullptr);
+    timer.stop();
+    cudaFreeAsync(flags, ctx->stream);
+    return rc;
+}
+
+int prep_renormalize(b200ppf_ctx *ctx, b200ppf_cloud *cloud) {
+    const uint32_t n = (uint32_t)cloud->n;
+    if (n) PPF_LAUNCH(ctx, renormalize_kernel, (n + 255) / 256, 256, 0, cloud->nrm, n);
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200PPF_OK;
+}
+
+// Test hook: the neighbour query of the kernels (knn_query, __host__ __device__) run on the CPU over a grid built
+// on the host with the same geometry (scene_grid_params / grid_cell_coord).  Not a product path: nothing in the
+// library calls it; tests use it to check the traversal and the epilogues where there is no GPU.
+int prep_debug_knn_host(const float *xyz, size_t n, size_t stride, int k, int mode, float cell_edge, const float *viewpoint3,
+                        int cov_mode, uint32_t *idx, float *d2, float *mean_dist, float *normals4) {
+    if (n == 0) return B200PPF_OK;
+    std::vector<float4> pos(n), gpos(n), nrm(mode == KNN_NORMAL ? n : 0);
+    b200ppf_cloud c;
+    c.n = n;
+    for (int t = 0; t < 3; ++t) c.bbox_min[t] = INFINITY, c.bbox_max[t] = -INFINITY;
+    for (size_t i = 0; i < n; ++i) {
+        const float *p = xyz + i * stride;
+        pos[i] = make_float4(p[0], p[1], p[2], 1.0f);
+        for (int t = 0; t < 3; ++t) {
+            c.bbox_min[t] = std::min(c.bbox_min[t], p[t]);
+            c.bbox_max[t] = std::max(c.bbox_max[t], p[t]);
+        }
+    }
+    KnnArgs a{};
+    a.k = k;
+    const uint32_t n_cells = scene_grid_params(c.bbox_min, c.bbox_max, cell_edge > 0.0f ? cell_edge : knn_cell_edge(&c, k), &a.gp);
+    std::vector<uint32_t> cell(n), start((size_t)n_cells + 1, 0u), orig(n);
+    for (size_t i = 0; i < n; ++i) {
+        cell[i] = grid_cell_linear(a.gp, grid_cell_coord(a.gp, pos[i].x, 0), grid_cell_coord(a.gp, pos[i].y, 1),
+                                   grid_cell_coord(a.gp, pos[i].z, 2));
+        start[cell[i] + 1]++;
+    }
+    for (uint32_t t = 0; t < n_cells; ++t) start[t + 1] += start[t];
+    {
+        std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+        for (size_t i = 0; i < n; ++i) {  // stable: original order inside a cell, like the radix sort
+            const uint32_t s = fill[cell[i]]++;
+            orig[s] = (uint32_t)i;
+            gpos[s] = pos[i];
+        }
+    }
+    a.pos = pos.data();
+    a.gpos = gpos.data();
+    a.cell_start = start.data();
+    a.orig = orig.data();
+    a.cell = 1.0f / a.gp.inv_cell;
+    a.n = (uint32_t)n;
+    a.out_idx = idx;
+    a.out_d2 = d2;
+    a.out_dist = mean_dist;
+    a.out_nrm = nrm.data();
+    for (int t = 0; t < 3; ++t) a.vp[t] = viewpoint3 ? viewpoint3[t] : 0.0f;
+    a.cov_mode = cov_mode;
+    for (uint32_t q = 0; q < (uint32_t)n; ++q) {
+        if (mode == KNN_EXPORT) {
+            if (k <= 32) knn_query<32, KNN_EXPORT>(a, q); else if (k <= 64) knn_query<64, KNN_EXPORT>(a, q); else knn_query<128, KNN_EXPORT>(a, q);
+        } else if (mode == KNN_MEAN_DISTANCE) {
+            if (k <= 32) knn_query<32, KNN_MEAN_DISTANCE>(a, q); else if (k <= 64) knn_query<64, KNN_MEAN_DISTANCE>(a, q); else knn_query<128, KNN_MEAN_DISTANCE>(a, q);
+        } else {
+            if (k <= 32) knn_query<32, KNN_NORMAL>(a, q); else if (k <= 64) knn_query<64, KNN_NORMAL>(a, q); else knn_query<128, KNN_NORMAL>(a, q);
+        }
+    }
+    if (mode == KNN_NORMAL)
+        for (size_t i = 0; i < n; ++i) normals4[4 * i] = nrm[i].x, normals4[4 * i + 1] = nrm[i].y, normals4[4 * i + 2] = nrm[i].z, normals4[4 * i + 3] = nrm[i].w;
+    return B200PPF_OK;
+}
+
+}  // namespace b200ppf

@@ -63,14 +63,12 @@ void scene_grid_free(b200ppf_ctx *ctx, SceneGrid *g) {
     g->orig = nullptr;
 }
 
-int scene_grid_build(b200ppf_ctx *ctx, const b200ppf_cloud *scene, float radius, SceneGrid *out) {
-    *out = SceneGrid();
-    const uint32_t n = (uint32_t)scene->n;
-    GridParams &g = out->gp;
+uint32_t scene_grid_params(const float *bbox_min, const float *bbox_max, float radius, GridParams *gp) {
+    GridParams &g = *gp;
     // cell edge: the search radius plus a margin that absorbs the rounding of the cell coordinate
     double cell = (radius > 0.0f ? (double)radius : 1e-3) * 1.001;
     double ext[3];
-    for (int k = 0; k < 3; ++k) ext[k] = std::max(0.0, (double)scene->bbox_max[k] - (double)scene->bbox_min[k]);
+    for (int k = 0; k < 3; ++k) ext[k] = std::max(0.0, (double)bbox_max[k] - (double)bbox_min[k]);
     for (;;) {
         double cells = 1.0;
         for (int k = 0; k < 3; ++k) cells *= std::floor(ext[k] / cell) + 1.0;
@@ -78,11 +76,18 @@ int scene_grid_build(b200ppf_ctx *ctx, const b200ppf_cloud *scene, float radius,
         cell *= 1.26;  // coarser cells stay correct (a superset of candidates), just less selective
     }
     for (int k = 0; k < 3; ++k) {
-        g.origin[k] = scene->bbox_min[k];
+        g.origin[k] = bbox_min[k];
         g.dims[k] = (int)(std::floor(ext[k] / cell) + 1.0);
     }
     g.inv_cell = (float)(1.0 / cell);
-    out->n_cells = (uint32_t)g.dims[0] * (uint32_t)g.dims[1] * (uint32_t)g.dims[2];
+    return (uint32_t)g.dims[0] * (uint32_t)g.dims[1] * (uint32_t)g.dims[2];
+}
+
+int scene_grid_build(b200ppf_ctx *ctx, const b200ppf_cloud *scene, float radius, SceneGrid *out) {
+    *out = SceneGrid();
+    const uint32_t n = (uint32_t)scene->n;
+    GridParams &g = out->gp;
+    out->n_cells = scene_grid_params(scene->bbox_min, scene->bbox_max, radius, &g);
 
     uint32_t *ids[2] = {nullptr, nullptr}, *ord[2] = {nullptr, nullptr};
     for (int b = 0; b < 2; ++b) {
