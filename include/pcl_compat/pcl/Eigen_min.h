@@ -19,6 +19,16 @@ struct Vector3f {
     float z() const { return v[2]; }
 };
 
+struct Vector4f {
+    float v[4] = {0, 0, 0, 0};
+    Vector4f() = default;
+    Vector4f(float x, float y, float z, float w) : v{x, y, z, w} {}
+    float &operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+    float &operator[](int i) { return v[i]; }
+    float operator[](int i) const { return v[i]; }
+};
+
 struct Matrix4f {
     float m[16];  // column-major
     Matrix4f() { std::memset(m, 0, sizeof(m)); }

@@ -6,6 +6,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "../../b200ppf.h"
 #include "pcl_macros.h"
@@ -62,6 +63,27 @@ struct TableHandle {
         h = n;
     }
 };
+
+// device cloud -> PointCloud<PointT> (x y z of every point; the other fields keep their defaults)
+template <typename CloudT>
+inline bool downloadXYZ(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, CloudT &output) {
+    const std::size_t n = b200ppf_cloud_size(cloud);
+    std::vector<float> rows(n * 3);
+    if (b200ppf_cloud_download(ctx, cloud, rows.data(), 3, 0, 0) != B200PPF_OK) {
+        PCL_ERROR("[pcl::b200] %s\n", b200ppf_last_error(ctx));
+        return false;
+    }
+    output.points.resize(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        output.points[i].x = rows[3 * i];
+        output.points[i].y = rows[3 * i + 1];
+        output.points[i].z = rows[3 * i + 2];
+    }
+    output.width = static_cast<std::uint32_t>(n);
+    output.height = 1;
+    output.is_dense = true;
+    return true;
+}
 
 }  // namespace b200
 }  // namespace pcl

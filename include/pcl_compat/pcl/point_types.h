@@ -15,6 +15,21 @@ struct alignas(16) PointXYZ {
     PointXYZ(float x_, float y_, float z_) : data{x_, y_, z_, 1.f} {}
 };
 
+// pcl::Normal: 32 bytes, data_n[4] = {nx,ny,nz,0}, curvature, pad
+struct alignas(16) Normal {
+    union {
+        float data_n[4];
+        float normal[3];
+        struct { float normal_x, normal_y, normal_z; };
+    };
+    union {
+        struct { float curvature; };
+        float data_c[4];
+    };
+    Normal() : data_n{0.f, 0.f, 0.f, 0.f}, data_c{0.f, 0.f, 0.f, 0.f} {}
+};
+static_assert(sizeof(Normal) == 32, "pcl::Normal is 32 bytes");
+
 // 48 bytes, 16-byte aligned: data[4] = {x,y,z,1}, data_n[4] = {nx,ny,nz,0}, curvature, pad
 struct alignas(16) PointNormal {
     union {

@@ -333,12 +333,13 @@ void oracle_normals(const float *xyz, size_t n, size_t stride, int k, const floa
     }
 }
 
-/* reference include/CloudProcessing.h:181-186: A = sqrt(nx*nx + ny*ny + nz*nz) (float sum, double sqrt);
- * if A > 0.00001 the three components are divided by (float)A.  In place on n rows of `stride` floats. */
+/* reference include/CloudProcessing.h:181-186: double A = sqrt(nx*nx + ny*ny + nz*nz) — a float sum, and under the
+ * file's `using namespace std` the call resolves to the float overload, widened to double afterwards; if
+ * A > 0.00001 the three components are divided by (float)A.  In place on n rows of `stride` floats. */
 void oracle_renormalize_normals(float *nrm, size_t n, size_t stride) {
     for (size_t i = 0; i < n; ++i) {
         float *d = nrm + i * stride;
-        const double A = std::sqrt((double)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]));
+        const double A = (double)std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
         if (A > 0.00001) {
             d[0] /= (float)A;
             d[1] /= (float)A;

@@ -7,10 +7,13 @@ threshold is a double-precision sum over the cloud formed in a different (fixed)
 point may flip only inside that band; normals and curvature go through atan2f / cosf / sinf, whose device and
 glibc versions differ by ulps: 2e-4 per component / 2e-5 absolute.
 """
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
-from conftest import ANGLE_STEP, DIST_STEP, load_cloud
+from conftest import ANGLE_STEP, DIST_STEP, ROOT, load_cloud
 
 pytestmark = pytest.mark.gpu
 
@@ -181,3 +184,31 @@ def test_prep_chain_feeds_the_ppf_engine(ctx, oracle, crop_raw, bottle):
     dr = float(np.degrees(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1))))
     print(f"chain: {scene_gpu.shape[0]} scene points, votes {votes.tolist()} vs {rvotes.tolist()}, |dt| {dt:.2e} m, dR {dr:.3f} deg")
     assert dt < 1e-3 and dr < 0.5
+
+
+def test_cpp_pcl_prep_shim_end_to_end(tmp_path, ctx, crop_raw):
+    """tests/cpp/pcl_prep_example.cpp — VoxelGrid -> StatisticalOutlierRemoval -> NormalEstimationOMP ->
+    concatenateFields -> edges -> N x 6 through include/pcl_compat — gives the C-ABI chain's result."""
+    from yolo_ppf_pose_estimation_b200 import build
+    lib = build.build()
+    crop_raw.astype(np.float32).tofile(tmp_path / "scene_crop_raw.f32")
+    exe = tmp_path / "pcl_prep_example"
+    cmd = ["/usr/bin/g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include", "pcl_compat"), "-I",
+           os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "pcl_prep_example.cpp"), "-o", str(exe),
+           "-L", os.path.dirname(lib), "-lb200ppf", f"-Wl,-rpath,{os.path.dirname(lib)}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path / "scene_crop_raw.f32"), "0.005", "1.0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    d = ctx.voxel_grid(ctx.upload_xyz(crop_raw), 0.005)
+    n_voxel = d.size
+    d, _, _, _ = ctx.statistical_outlier_removal(d, 50, 1.0)
+    ctx.normal_estimation(d, 30)
+    n_edges = ctx.curvature_edges(d, 0.03).size
+    ctx.normalize_normals(d)
+    mat = d.download()
+    assert [int(x) for x in lines[0].split()[1:]] == [crop_raw.shape[0], n_voxel, mat.shape[0], mat.shape[0], n_edges]
+    for i in range(3):
+        assert np.array_equal(np.array([float(x) for x in lines[1 + i].split()[1:]], np.float32), mat[i])
+    assert float(lines[4].split()[1]) == float(np.sum(mat.astype(np.float64).reshape(-1).cumsum()[-1:]))

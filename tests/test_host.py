@@ -198,22 +198,24 @@ def test_two_rank_gloo_sharding(tmp_path):
 
 
 def test_cpp_shim_compiles_and_links(tmp_path):
-    """The PCL-shaped header shim is valid C++14 and links against libb200ppf.so."""
+    """The PCL-shaped header shim is valid C++14 and links against libb200ppf.so (PPF operators and the
+    pre-processing operators)."""
     from yolo_ppf_pose_estimation_b200 import build
     lib = build.build()
-    exe = tmp_path / "pcl_shim_example"
-    cmd = ["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
-           "-I", os.path.join(ROOT, "include", "pcl_compat"), "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "tests", "cpp", "pcl_shim_example.cpp"), "-o", str(exe),
-           "-L", os.path.dirname(lib), "-lb200ppf", f"-Wl,-rpath,{os.path.dirname(lib)}"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    # without a GPU the shim reports PCL-style errors and does not converge (no crash, no fallback)
     import torch
-    if not torch.cuda.is_available():
-        r = subprocess.run([str(exe), os.path.join(ROOT, "tests", "golden")], capture_output=True, text=True, timeout=120)
-        assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
-        assert "no CPU fallback" in r.stderr
+    for name, arg in (("pcl_shim_example", os.path.join(ROOT, "tests", "golden")), ("pcl_prep_example", "/nonexistent.f32")):
+        exe = tmp_path / name
+        cmd = ["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
+               "-I", os.path.join(ROOT, "include", "pcl_compat"), "-I", os.path.join(ROOT, "include"),
+               os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", str(exe),
+               "-L", os.path.dirname(lib), "-lb200ppf", f"-Wl,-rpath,{os.path.dirname(lib)}"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        # without a GPU the shim reports PCL-style errors and produces nothing (no crash, no fallback)
+        if not torch.cuda.is_available():
+            r = subprocess.run([str(exe), arg], capture_output=True, text=True, timeout=120)
+            assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+            assert "no CPU fallback" in r.stderr
 
 
 def test_bench_reference_arm_prints_the_contract_line():

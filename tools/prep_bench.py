@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Scene pre-processing timing (prep.cu): Subsampling -> OutlierProcessing(50, 1.0) -> NormalEstimation(30) ->
+EdgeExtraction(0.03) -> re-normalise, as src/YOLO_cropping_ppf_test.cpp:96-121 chains them, B200 vs the CPU
+restatement of the PCL operators on all host threads.  Two inputs: the reference's raw crop (29 450 points,
+tests/golden/scene_crop_raw.npz) and a synthetic 1 Mi-point scene (Azure Kinect WFOV size, config C4).
+Prints one JSON line per input.
+
+usage: python tools/prep_bench.py [--no-cpu] [--repeat 5] [--cpu-points 60000]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def gpu_chain(c, xyz, leaf, repeat):
+    stages = {"upload": [], "voxel_grid": [], "outlier_removal": [], "normals": [], "edges": [], "renormalise": [], "total_wall": []}
+    sizes = {}
+    for _ in range(repeat + 1):
+        t0 = time.perf_counter()
+        d = c.upload_xyz(xyz)
+        t1 = time.perf_counter()
+        v = c.voxel_grid(d, leaf)
+        stages["voxel_grid"].append(c.timings()["prep_ms"])
+        f, kept, _, _ = c.statistical_outlier_removal(v, 50, 1.0)
+        stages["outlier_removal"].append(c.timings()["prep_ms"])
+        c.normal_estimation(f, 30)
+        stages["normals"].append(c.timings()["prep_ms"])
+        e = c.curvature_edges(f, 0.03)
+        stages["edges"].append(c.timings()["prep_ms"])
+        t2 = time.perf_counter()
+        c.normalize_normals(f)
+        c.synchronize()
+        t3 = time.perf_counter()
+        stages["upload"].append(1e3 * (t1 - t0))
+        stages["renormalise"].append(1e3 * (t3 - t2))
+        stages["total_wall"].append(1e3 * (t3 - t0))
+        sizes = {"raw": int(xyz.shape[0]), "voxels": v.size, "kept": f.size, "edges": e.size}
+    return {k: float(np.median(v[1:])) for k, v in stages.items()}, sizes
+
+
+def cpu_chain(xyz, leaf):
+    from oracle import binding as ob
+    t = {}
+    t0 = time.perf_counter()
+    v = ob.voxel_grid(xyz, leaf)[0]
+    t["voxel_grid"] = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    keep, _, _ = ob.statistical_outlier_removal(v, 50, 1.0)
+    t["outlier_removal"] = 1e3 * (time.perf_counter() - t0)
+    v = v[keep]
+    t0 = time.perf_counter()
+    n = ob.normals(v, 30)
+    t["normals"] = 1e3 * (time.perf_counter() - t0)
+    t["threads"] = ob.max_threads()
+    t["points_after_voxel"] = int(keep.shape[0])
+    return t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--repeat", type=int, default=5)
+    ap.add_argument("--cpu-points", type=int, default=60000, help="the CPU leg (brute-force neighbours) takes a raw subset that voxelises to about this many points")
+    args = ap.parse_args()
+    from yolo_ppf_pose_estimation_b200 import capi, synth
+    c = capi.Context(0)
+    crop = np.load(os.path.join(ROOT, "tests", "golden", "scene_crop_raw.npz"))["cloud"].astype(np.float32)
+    big = np.ascontiguousarray(synth.synth_library_scene(1 << 20)[:, :3], np.float32)
+    for name, xyz, leaf in (("reference crop", crop, 0.005), ("synthetic 1Mi scene", big, 0.005)):
+        ms, sizes = gpu_chain(c, xyz, leaf, args.repeat)
+        rec = {"input": name, "leaf": leaf, "sizes": sizes, "b200_ms": ms,
+               "b200_points_per_s": sizes["raw"] / (1e-3 * (ms["voxel_grid"] + ms["outlier_removal"] + ms["normals"] + ms["edges"]))}
+        if not args.no_cpu:
+            sub = xyz
+            if sizes["voxels"] > args.cpu_points:  # the brute-force CPU neighbours are O(n^2): a spatial slab of the scene
+                order = np.argsort(xyz[:, 0], kind="stable")
+                sub = xyz[order[: int(xyz.shape[0] * args.cpu_points / sizes["voxels"])]]
+            rec["cpu_ms"] = cpu_chain(sub, leaf)
+            rec["cpu_sample_raw_points"] = int(sub.shape[0])
+        print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    main()

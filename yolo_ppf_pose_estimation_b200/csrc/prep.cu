@@ -635,8 +635,9 @@ __global__ void __launch_bounds__(256) renormalize_kernel(float4 *__restrict__ n
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 v = nrm[i];
-    // double A = sqrt(nx*nx + ny*ny + nz*nz) with the sum in float; if (A > 0.00001) n /= static_cast<float>(A)
-    const double A = sqrt((double)(v.x * v.x + v.y * v.y + v.z * v.z));
+    // double A = sqrt(nx*nx + ny*ny + nz*nz): float sum, float sqrt (the overload `using namespace std` selects),
+    // widened; if (A > 0.00001) n /= static_cast<float>(A)
+    const double A = (double)sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
     if (A > 0.00001) {
         const float fa = (float)A;
         v.x /= fa;
