@@ -62,10 +62,27 @@ def cpu_chain(xyz, leaf):
     return t
 
 
+def cpu_kdtree(c, xyz, leaf):
+    """the neighbour searches of the two stages with a kd-tree on all host threads (scipy cKDTree standing in for
+    the FLANN tree PCL builds), on the full-size voxelised cloud: the fair CPU figure for the search itself"""
+    from scipy.spatial import cKDTree
+    v = c.voxel_grid(c.upload_xyz(xyz), leaf).download()[:, :3].astype(np.float64)
+    t0 = time.perf_counter()
+    tree = cKDTree(v)
+    t1 = time.perf_counter()
+    tree.query(v, k=51, workers=-1)
+    t2 = time.perf_counter()
+    tree.query(v, k=30, workers=-1)
+    t3 = time.perf_counter()
+    return {"points": int(v.shape[0]), "build": 1e3 * (t1 - t0), "query_k51": 1e3 * (t2 - t1), "query_k30": 1e3 * (t3 - t2),
+            "threads": os.cpu_count()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--repeat", type=int, default=5)
+    ap.add_argument("--only", choices=["crop", "big"], default=None, help="run one of the two inputs")
     ap.add_argument("--cpu-points", type=int, default=60000, help="the CPU leg (brute-force neighbours) takes a raw subset that voxelises to about this many points")
     args = ap.parse_args()
     from yolo_ppf_pose_estimation_b200 import capi, synth
@@ -73,6 +90,8 @@ def main():
     crop = np.load(os.path.join(ROOT, "tests", "golden", "scene_crop_raw.npz"))["cloud"].astype(np.float32)
     big = np.ascontiguousarray(synth.synth_library_scene(1 << 20)[:, :3], np.float32)
     for name, xyz, leaf in (("reference crop", crop, 0.005), ("synthetic 1Mi scene", big, 0.005)):
+        if args.only and (args.only == "crop") != (name == "reference crop"):
+            continue
         ms, sizes = gpu_chain(c, xyz, leaf, args.repeat)
         rec = {"input": name, "leaf": leaf, "sizes": sizes, "b200_ms": ms,
                "b200_points_per_s": sizes["raw"] / (1e-3 * (ms["voxel_grid"] + ms["outlier_removal"] + ms["normals"] + ms["edges"]))}
@@ -83,6 +102,7 @@ def main():
                 sub = xyz[order[: int(xyz.shape[0] * args.cpu_points / sizes["voxels"])]]
             rec["cpu_ms"] = cpu_chain(sub, leaf)
             rec["cpu_sample_raw_points"] = int(sub.shape[0])
+            rec["cpu_kdtree_ms"] = cpu_kdtree(c, xyz, leaf)
         print(json.dumps(rec), flush=True)
 
 

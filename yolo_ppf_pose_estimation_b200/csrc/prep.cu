@@ -384,8 +384,22 @@ __host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q) {
     const int cx = grid_cell_coord(a.gp, pq.x, 0), cy = grid_cell_coord(a.gp, pq.y, 1), cz = grid_cell_coord(a.gp, pq.z, 2);
     const int dx = a.gp.dims[0], dy = a.gp.dims[1], dz = a.gp.dims[2];
     const int k = a.k;
-    unsigned long long best[CAP];  // ascending (distance bits << 32 | original index); the first cnt are valid
+    // the k best so far as (distance bits << 32 | original index) words: an unordered buffer while it fills, a
+    // max-heap (largest at [0]) once it holds k — a better candidate replaces the root in O(log k) — and an
+    // ascending array after the final heap sort
+    unsigned long long best[CAP];
     int cnt = 0;
+    auto sift_down = [&](int i, const int end, const unsigned long long v) {  // place v at or below i, heap = [0, end)
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= end) break;
+            if (c + 1 < end && best[c + 1] > best[c]) ++c;
+            if (best[c] <= v) break;
+            best[i] = best[c];
+            i = c;
+        }
+        best[i] = v;
+    };
 
     // candidates of the sorted positions [s0, s1)
     auto scan_run = [&](uint32_t s0, uint32_t s1) {
@@ -397,14 +411,13 @@ __host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q) {
             d2 += ey * ey;
             d2 += ez * ez;
             const unsigned long long key = ((unsigned long long)f32_bits(d2) << 32) | (unsigned long long)ld_ro(a.orig + s);
-            if (cnt == k && key >= best[k - 1]) continue;
-            int j = cnt < k ? cnt : k - 1;  // slot that opens up
-            while (j > 0 && best[j - 1] > key) {
-                best[j] = best[j - 1];
-                --j;
+            if (cnt < k) {
+                best[cnt++] = key;
+                if (cnt == k)
+                    for (int i = k / 2 - 1; i >= 0; --i) sift_down(i, k, best[i]);  // heapify
+            } else if (key < best[0]) {
+                sift_down(0, k, key);
             }
-            best[j] = key;
-            if (cnt < k) ++cnt;
         }
     };
 
@@ -435,8 +448,17 @@ __host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q) {
         // float rounding of the cell coordinate
         if (cnt == k && r >= 1) {
             const float reach = ((float)r - 1e-3f) * a.cell;
-            if (bits_f32((uint32_t)(best[k - 1] >> 32)) <= reach * reach) break;
+            if (bits_f32((uint32_t)(best[0] >> 32)) <= reach * reach) break;
         }
+    }
+
+    // ascending order = FLANN's (distance, then index): heap sort in place
+    if (cnt < k)
+        for (int i = cnt / 2 - 1; i >= 0; --i) sift_down(i, cnt, best[i]);
+    for (int end = cnt - 1; end > 0; --end) {
+        const unsigned long long v = best[end];
+        best[end] = best[0];
+        sift_down(0, end, v);
     }
 
     const uint32_t me = a.orig[q];
