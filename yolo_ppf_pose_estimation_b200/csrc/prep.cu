@@ -22,6 +22,7 @@
 // original point order, covariance sums in neighbour order, un-fused float arithmetic (-fmad=false).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -143,12 +144,17 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4 *__restrict__ po
         lo[k] = __reduce_min_sync(0xFFFFFFFFu, lo[k]);
         hi[k] = __reduce_max_sync(0xFFFFFFFFu, hi[k]);
     }
+    __shared__ uint32_t sh[6][8];
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicMin(mm + k, lo[k]);
-            atomicMax(mm + 3 + k, hi[k]);
-        }
+        for (int k = 0; k < 3; ++k) sh[k][threadIdx.x >> 5] = lo[k], sh[3 + k][threadIdx.x >> 5] = hi[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {  // one atomic per block and bound
+        uint32_t v = sh[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? min(v, sh[threadIdx.x][w]) : max(v, sh[threadIdx.x][w]);
+        if (threadIdx.x < 3) atomicMin(mm + threadIdx.x, v);
+        else atomicMax(mm + threadIdx.x, v);
     }
 }
 
@@ -377,9 +383,25 @@ __host__ __device__ inline void eigen33_smallest(const float *cov, float *eigenv
     for (int k = 0; k < 3; ++k) evec[k] = (best == 0 ? v[0][k] : (best == 1 ? v[1][k] : v[2][k])) / l;
 }
 
+// where a query keeps its k best: a per-thread array (local memory; the host build) or a column of the block's
+// shared memory — slot i of thread t at word i*128 + t, so a warp's accesses to whatever slots its lanes are at
+// fall into distinct bank pairs.  With 1 536 resident threads the local-memory arrays (k x 8 bytes each) overflow
+// L1 and ncu showed them travelling to DRAM (2.5 GB per launch on the 1 Mi-point scene); shared memory keeps them
+// on the SM at the price of occupancy.
+constexpr int KNN_THREADS = 128;
+template <int CAP>
+struct LocalKeys {
+    unsigned long long v[CAP];
+    __host__ __device__ __forceinline__ unsigned long long &operator[](int i) { return v[i]; }
+};
+struct SharedKeys {
+    unsigned long long *base;  // &smem[threadIdx.x]
+    __device__ __forceinline__ unsigned long long &operator[](int i) { return base[i * KNN_THREADS]; }
+};
+
 // one query point (q = its cell-sorted position): the k nearest, then the epilogue of MODE
-template <int CAP, int MODE>
-__host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q) {
+template <int MODE, typename Keys>
+__host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q, Keys &best) {
     const float4 pq = a.gpos[q];
     const int cx = grid_cell_coord(a.gp, pq.x, 0), cy = grid_cell_coord(a.gp, pq.y, 1), cz = grid_cell_coord(a.gp, pq.z, 2);
     const int dx = a.gp.dims[0], dy = a.gp.dims[1], dz = a.gp.dims[2];
@@ -387,7 +409,6 @@ __host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q) {
     // the k best so far as (distance bits << 32 | original index) words: an unordered buffer while it fills, a
     // max-heap (largest at [0]) once it holds k — a better candidate replaces the root in O(log k) — and an
     // ascending array after the final heap sort
-    unsigned long long best[CAP];
     int cnt = 0;
     auto sift_down = [&](int i, const int end, const unsigned long long v) {  // place v at or below i, heap = [0, end)
         for (;;) {
@@ -524,16 +545,34 @@ __host__ __device__ inline void knn_query(const KnnArgs &a, const uint32_t q) {
 }
 
 template <int CAP, int MODE>
-__global__ void __launch_bounds__(128) knn_kernel(const KnnArgs a) {
+__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const KnnArgs a) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;  // cell-sorted position of the query
-    if (q < a.n) knn_query<CAP, MODE>(a, q);
+    if (q >= a.n) return;
+    LocalKeys<CAP> best;
+    knn_query<MODE>(a, q, best);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(KNN_THREADS) knn_smem_kernel(const KnnArgs a) {
+    extern __shared__ unsigned long long knn_keys[];  // [k][KNN_THREADS]
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n) return;
+    SharedKeys best{knn_keys + threadIdx.x};
+    knn_query<MODE>(a, q, best);
 }
 
 template <int MODE>
 int knn_launch(b200ppf_ctx *ctx, const KnnArgs &a) {
-    const unsigned grid = (a.n + 127) / 128;
+    const unsigned grid = (a.n + KNN_THREADS - 1) / KNN_THREADS;
+    static const bool force_local = getenv("B200PPF_KNN_LOCAL") != nullptr;  // tuning switch: the local-memory variant
+    if (!force_local) {
+        const size_t smem = (size_t)a.k * KNN_THREADS * sizeof(unsigned long long);
+        PPF_CUDA(ctx, cudaFuncSetAttribute(knn_smem_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * KNN_THREADS * 8));
+        PPF_LAUNCH(ctx, knn_smem_kernel<MODE>, grid, KNN_THREADS, smem, a);
+        return B200PPF_OK;
+    }
     void (*kern)(const KnnArgs) = a.k <= 32 ? knn_kernel<32, MODE> : (a.k <= 64 ? knn_kernel<64, MODE> : knn_kernel<128, MODE>);
-    PPF_LAUNCH(ctx, kern, grid, 128, 0, a);
+    PPF_LAUNCH(ctx, kern, grid, KNN_THREADS, 0, a);
     return B200PPF_OK;
 }
 
@@ -967,13 +1006,14 @@ int prep_debug_knn_host(const float *xyz, size_t n, size_t stride, int k, int mo
     a.out_nrm = nrm.data();
     for (int t = 0; t < 3; ++t) a.vp[t] = viewpoint3 ? viewpoint3[t] : 0.0f;
     a.cov_mode = cov_mode;
+    LocalKeys<128> keys;
     for (uint32_t q = 0; q < (uint32_t)n; ++q) {
         if (mode == KNN_EXPORT) {
-            if (k <= 32) knn_query<32, KNN_EXPORT>(a, q); else if (k <= 64) knn_query<64, KNN_EXPORT>(a, q); else knn_query<128, KNN_EXPORT>(a, q);
+            knn_query<KNN_EXPORT>(a, q, keys);
         } else if (mode == KNN_MEAN_DISTANCE) {
-            if (k <= 32) knn_query<32, KNN_MEAN_DISTANCE>(a, q); else if (k <= 64) knn_query<64, KNN_MEAN_DISTANCE>(a, q); else knn_query<128, KNN_MEAN_DISTANCE>(a, q);
+            knn_query<KNN_MEAN_DISTANCE>(a, q, keys);
         } else {
-            if (k <= 32) knn_query<32, KNN_NORMAL>(a, q); else if (k <= 64) knn_query<64, KNN_NORMAL>(a, q); else knn_query<128, KNN_NORMAL>(a, q);
+            knn_query<KNN_NORMAL>(a, q, keys);
         }
     }
     if (mode == KNN_NORMAL)
