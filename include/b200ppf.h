@@ -241,6 +241,7 @@ int b200ppf_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200p
 /* ---- scene pre-processing ("next" row): the stages between the YOLO crop and the PPF engine -------------
  * What the reference runs on every cropped object before matching (src/YOLO_cropping_ppf_test.cpp:96-103,
  * :120-121), each a PCL operator on the host there and a device stage here, chained without leaving HBM:
+ *     SceneCropping(K)             include/CloudProcessing.h:263-339  pcl::ConvexHull + pcl::CropHull
  *     Subsampling(leaf)            include/CloudProcessing.h:359-377  pcl::VoxelGrid<PointXYZ>
  *     OutlierProcessing(50, thr)   include/CloudProcessing.h:340-358  pcl::StatisticalOutlierRemoval<PointXYZ>
  *     NormalEstimation(30)         include/CloudProcessing.h:378-401  pcl::NormalEstimationOMP<PointXYZ, Normal>
@@ -254,6 +255,19 @@ int b200ppf_cloud_upload_xyz(b200ppf_ctx *ctx, const float *host, size_t n, size
  * curvature_offset_floats (each >= 3, or 0 to leave it out); every other float of a row is written as 0 */
 int b200ppf_cloud_download(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, float *host, size_t stride_floats,
                            size_t normal_offset_floats, size_t curvature_offset_floats);
+/* SceneCropping, per YOLO box (include/CloudProcessing.h:263-339): the box grown by 30 pixels and clamped, the mean
+ * depth at its four corners, the four corner rays at that depth (include/Camera.h:50-61 back_projection_bbox) pushed
+ * 0.15 m further -> corners12 = left_top, left_bot, right_top, right_bot.  Host arithmetic on four pixels of the
+ * row-major float depth image (metres); no context needed. */
+int b200ppf_frustum_corners(const float *depth, int rows, int cols, int box_x, int box_y, int box_w, int box_h, double fx,
+                            double fy, double ppx, double ppy, float corners12[12]);
+/* The crop itself: the reference builds pcl::ConvexHull of {the four corners, the origin} and keeps what
+ * pcl::CropHull (dim 3) finds inside — the points of the pyramid, here five half-space tests per point in double
+ * (a point within rounding of a face may fall either way, as with PCL's ray casting).  The corners must be
+ * coplanar (the reference's share one z).  Kept points keep their order and normals; kept_indices_host (capacity
+ * n) is optional. */
+int b200ppf_crop_pyramid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float corners12[12], b200ppf_cloud **out,
+                         uint32_t *kept_indices_host);
 /* [PCL] filters/impl/voxel_grid.hpp VoxelGrid::applyFilter: one centroid per occupied leaf, in ascending leaf
  * index (x fastest).  A leaf so small that the index overflows an int returns a copy of the input, as PCL does
  * (b200ppf_last_error then holds PCL's warning). */

@@ -103,6 +103,10 @@ def _declare(L):
     L.oracle_sor.restype = sz
     L.oracle_normals.argtypes = [vp, sz, sz, C.c_int, vp, C.c_int, vp, C.c_int]
     L.oracle_renormalize_normals.argtypes = [vp, sz, sz]
+    L.oracle_frustum_corners.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                         C.c_double, C.c_double, vp]
+    L.oracle_crop_pyramid.argtypes = [vp, sz, sz, vp, vp]
+    L.oracle_crop_pyramid.restype = sz
 
 
 def _f32(a):
@@ -372,3 +376,23 @@ def renormalize_normals(nrm):
     out = _f32(nrm).copy()
     lib().oracle_renormalize_normals(_p(out), out.shape[0], out.shape[1])
     return out
+
+
+def frustum_corners(depth, box, intrinsics):
+    """SceneCropping's four far corners (left_top, left_bot, right_top, right_bot) for box = (x, y, w, h) and
+    intrinsics = (fx, fy, ppx, ppy): -> (4, 3) float32"""
+    depth = np.ascontiguousarray(depth, np.float32)
+    out = np.zeros((4, 3), np.float32)
+    fx, fy, ppx, ppy = (float(v) for v in intrinsics)
+    lib().oracle_frustum_corners(_p(depth), depth.shape[0], depth.shape[1], int(box[0]), int(box[1]), int(box[2]), int(box[3]),
+                                 fx, fy, ppx, ppy, _p(out))
+    return out
+
+
+def crop_pyramid(xyz, corners):
+    """ConvexHull{corners, origin} + CropHull: boolean mask of the points inside"""
+    xyz = _f32(xyz)
+    corners = _f32(corners).reshape(12)
+    keep = np.zeros(xyz.shape[0], np.uint8)
+    lib().oracle_crop_pyramid(_p(xyz), xyz.shape[0], xyz.shape[1], _p(corners), _p(keep))
+    return keep.astype(bool)

@@ -150,6 +150,10 @@ size_t oracle_sor(const float *xyz, size_t n, size_t stride, int mean_k, double 
 void oracle_normals(const float *xyz, size_t n, size_t stride, int k, const float *viewpoint3, int cov_mode, float *out4,
                     int n_threads);
 void oracle_renormalize_normals(float *nrm, size_t n, size_t stride);
+/* SceneCropping (reference include/CloudProcessing.h:263-339, include/Camera.h:50-61) */
+void oracle_frustum_corners(const float *depth, int rows, int cols, int bx, int by, int bw, int bh, double fx, double fy,
+                            double ppx, double ppy, float *corners12);
+size_t oracle_crop_pyramid(const float *xyz, size_t n, size_t stride, const float *corners12, uint8_t *keep);
 
 #ifdef __cplusplus
 }

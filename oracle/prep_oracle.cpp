@@ -333,6 +333,80 @@ void oracle_normals(const float *xyz, size_t n, size_t stride, int k, const floa
     }
 }
 
+/* reference include/CloudProcessing.h:270-300 (SceneCropping, per box) + include/Camera.h:50-61
+ * (back_projection_bbox): the box grown by 30 pixels and clamped, the mean of the depth image at its four
+ * corners, the four corner rays at that depth, pushed 0.15 m further.  corners12 = left_top, left_bot,
+ * right_top, right_bot (the order the reference pushes them into its hull cloud). */
+void oracle_frustum_corners(const float *depth, int rows, int cols, int bx, int by, int bw, int bh, double fx, double fy,
+                            double ppx, double ppy, float *corners12) {
+    double left = bx - 30;
+    if (left < 0) left = 0;
+    double top = by - 30;
+    if (top < 0) top = 0;
+    double right = bx + bw + 30;
+    if (right >= cols) right = cols - 1;
+    double bottom = by + bh + 30;
+    if (bottom >= rows) bottom = rows - 1;
+    const float depth_1 = depth[(size_t)(int)top * cols + (int)left];
+    const float depth_2 = depth[(size_t)(int)top * cols + (int)right];
+    const float depth_3 = depth[(size_t)(int)bottom * cols + (int)left];
+    const float depth_4 = depth[(size_t)(int)bottom * cols + (int)right];
+    const float depth_avg = (depth_1 + depth_2 + depth_3 + depth_4) / 4;
+    const int us[4] = {(int)left, (int)left, (int)right, (int)right};
+    const int vs[4] = {(int)top, (int)bottom, (int)top, (int)bottom};
+    for (int c = 0; c < 4; ++c) {
+        const float z = depth_avg;
+        float x = (float)((float)(us[c] - ppx) * z / fx);
+        float y = (float)((float)(vs[c] - ppy) * z / fy);
+        float zz = z;
+        zz += 0.15;  // float += double literal, as the reference writes it
+        corners12[3 * c + 0] = x, corners12[3 * c + 1] = y, corners12[3 * c + 2] = zz;
+    }
+}
+
+/* reference include/CloudProcessing.h:312-332: ConvexHull of {four corners, origin} + CropHull (dim 3) = the points
+ * inside that pyramid.  PCL decides by casting rays at the hull's triangles; here the same set is formed another
+ * way (the device uses five half-spaces): p is inside iff the ray from the apex through p meets the base plane at
+ * or beyond p, inside the base quadrilateral.  All in double; a point within rounding of a face may fall either
+ * way in any of the three formulations.  keep[n] = 1 inside; returns the count. */
+size_t oracle_crop_pyramid(const float *xyz, size_t n, size_t stride, const float *corners12, uint8_t *keep) {
+    double c[4][3];
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 3; ++k) c[i][k] = corners12[3 * i + k];
+    const int cyc[4] = {0, 1, 3, 2};  // left_top -> left_bot -> right_bot -> right_top
+    double e1[3], e2[3], nrm[3];
+    for (int k = 0; k < 3; ++k) e1[k] = c[1][k] - c[0][k], e2[k] = c[2][k] - c[0][k];
+    nrm[0] = e1[1] * e2[2] - e1[2] * e2[1];
+    nrm[1] = e1[2] * e2[0] - e1[0] * e2[2];
+    nrm[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    const double d = nrm[0] * c[0][0] + nrm[1] * c[0][1] + nrm[2] * c[0][2];
+    size_t kept = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const double p[3] = {xyz[i * stride], xyz[i * stride + 1], xyz[i * stride + 2]};
+        const double np_ = nrm[0] * p[0] + nrm[1] * p[1] + nrm[2] * p[2];
+        bool in = false;
+        if (p[0] == 0.0 && p[1] == 0.0 && p[2] == 0.0) {
+            in = true;  // the apex
+        } else if (np_ != 0.0 && d / np_ >= 1.0) {  // t * p lies in the base plane at t = d / (n.p) >= 1
+            const double t = d / np_;
+            const double h[3] = {t * p[0], t * p[1], t * p[2]};
+            int pos = 0, neg = 0;
+            for (int s = 0; s < 4; ++s) {  // h inside the convex quadrilateral: the same side of its four edges
+                const double *a = c[cyc[s]], *b = c[cyc[(s + 1) & 3]];
+                const double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ah[3] = {h[0] - a[0], h[1] - a[1], h[2] - a[2]};
+                const double cr[3] = {ab[1] * ah[2] - ab[2] * ah[1], ab[2] * ah[0] - ab[0] * ah[2], ab[0] * ah[1] - ab[1] * ah[0]};
+                const double sgn = cr[0] * nrm[0] + cr[1] * nrm[1] + cr[2] * nrm[2];
+                if (sgn > 0) ++pos;
+                if (sgn < 0) ++neg;
+            }
+            in = (pos == 0 || neg == 0);
+        }
+        keep[i] = in ? 1 : 0;
+        kept += in ? 1 : 0;
+    }
+    return kept;
+}
+
 /* reference include/CloudProcessing.h:181-186: double A = sqrt(nx*nx + ny*ny + nz*nz) — a float sum, and under the
  * file's `using namespace std` the call resolves to the float overload, widened to double afterwards; if
  * A > 0.00001 the three components are divided by (float)A.  In place on n rows of `stride` floats. */

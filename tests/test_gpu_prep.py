@@ -46,6 +46,37 @@ def test_upload_xyz_download_round_trip(ctx, crop_raw, dev_raw):
     assert ctx.upload_xyz(np.zeros((0, 3), np.float32)).size == 0
 
 
+def _crop_box():
+    b = np.load(os.path.join(ROOT, "tests", "golden", "crop_box.npz"))
+    depth = np.zeros(tuple(b["image"]), np.float32)
+    for (r, c), d in zip(b["pixels"], b["depths"]):
+        depth[r, c] = d
+    return depth, b["box"], b["intrinsics"]
+
+
+def test_p0_frustum_crop_vs_oracle(ctx, oracle, scene_full):
+    """SceneCropping for the surrogate YOLO box: corners on the host, ConvexHull + CropHull as five half-spaces"""
+    from yolo_ppf_pose_estimation_b200 import capi
+    depth, box, K = _crop_box()
+    cor = capi.frustum_corners(depth, box, K)
+    assert np.array_equal(cor, oracle.frustum_corners(depth, box, K))
+    rng = np.random.default_rng(5)
+    cloud = np.concatenate([scene_full, (rng.random((50000, 6)) * [1.0, 1.2, 2.0, 1, 1, 1] - [0.6, 0.7, 0.2, 0, 0, 0]).astype(np.float32)])
+    keep = oracle.crop_pyramid(cloud[:, :3], cor)
+    out, kept = ctx.crop_pyramid(ctx.upload_cloud(cloud), cor)
+    assert np.array_equal(kept, np.flatnonzero(keep))  # no point of these sits within rounding of a face
+    assert np.array_equal(out.download(), cloud[keep])  # order and normals kept
+    # nothing inside / everything inside / empty input
+    assert ctx.crop_pyramid(ctx.upload_xyz(cloud[:, :3] + np.float32(10.0)), cor)[0].size == 0
+    wide = cor * np.array([50, 50, 10], np.float32)
+    assert ctx.crop_pyramid(ctx.upload_xyz(cloud[keep][:, :3]), wide)[0].size == int(keep.sum())
+    assert ctx.crop_pyramid(ctx.upload_xyz(np.zeros((0, 3), np.float32)), cor)[0].size == 0
+    bent = cor.copy()
+    bent[3, 2] += 0.1  # the hull of a non-planar base is another solid
+    with pytest.raises(capi.B200PPFError):
+        ctx.crop_pyramid(ctx.upload_xyz(cloud[:, :3]), bent)
+
+
 @pytest.mark.parametrize("leaf", [0.01, 0.005, (0.02, 0.01, 0.005)])
 def test_p1_voxel_grid_vs_oracle(ctx, oracle, crop_raw, dev_raw, leaf):
     ref, overflow = oracle.voxel_grid(crop_raw, leaf)

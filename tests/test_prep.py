@@ -149,6 +149,63 @@ def test_renormalize_oracle(oracle):
     assert np.abs(np.linalg.norm(out[3]) - 1) < 1e-6
 
 
+def _crop_box():
+    import os
+    from conftest import GOLDEN
+    b = np.load(os.path.join(GOLDEN, "crop_box.npz"))
+    depth = np.zeros(tuple(b["image"]), np.float32)  # SceneCropping reads four pixels of the depth image, no more
+    for (r, c), d in zip(b["pixels"], b["depths"]):
+        depth[r, c] = d
+    return depth, b["box"], b["intrinsics"]
+
+
+def test_frustum_corners_oracle_and_library(oracle):
+    """SceneCropping's corner arithmetic (include/CloudProcessing.h:270-300, include/Camera.h:50-61): the oracle
+    against a float64 restatement, and the library's host routine against the oracle bit for bit"""
+    from yolo_ppf_pose_estimation_b200 import capi
+    depth, box, K = _crop_box()
+    cor = oracle.frustum_corners(depth, box, K)
+    fx, fy, ppx, ppy = K
+    l, t, r, b = box[0] - 30, box[1] - 30, box[0] + box[2] + 30, box[1] + box[3] + 30
+    zavg = np.mean([depth[t, l], depth[t, r], depth[b, l], depth[b, r]], dtype=np.float64)
+    ref = np.array([[(u - ppx) * zavg / fx, (v - ppy) * zavg / fy, zavg + 0.15] for u, v in ((l, t), (l, b), (r, t), (r, b))])
+    assert np.abs(cor - ref).max() < 1e-6
+    assert np.array_equal(capi.frustum_corners(depth, box, K), cor)
+    # boxes at the image border are clamped to [0, cols-1] x [0, rows-1]
+    for bx in ((1200, 650, 100, 100), (5, 3, 100, 100), (0, 0, 1280, 720)):
+        got = capi.frustum_corners(depth + 1.0, bx, K)
+        assert np.array_equal(got, oracle.frustum_corners(depth + 1.0, bx, K)) and np.all(got[:, 2] == np.float32(1.15))
+    with pytest.raises(capi.B200PPFError):
+        capi.frustum_corners(depth, (2000, 10, 5, 5), K)
+
+
+def test_crop_pyramid_oracle_vs_rectangle_rule(oracle, scene_full):
+    """inside {four coplanar corners, origin}: the oracle's ray/quad form and the device's five half-spaces (formed
+    here with numpy as prep.cu forms them) against the axis-aligned rule the reference's corners allow"""
+    depth, box, K = _crop_box()
+    cor = oracle.frustum_corners(depth, box, K)
+    rng = np.random.default_rng(5)
+    cloud = np.concatenate([scene_full[:, :3], (rng.random((50000, 3)) * [1.0, 1.2, 2.0] - [0.6, 0.7, 0.2]).astype(np.float32),
+                            np.zeros((1, 3), np.float32)])
+    keep = oracle.crop_pyramid(cloud, cor)
+    p, zf = cloud.astype(np.float64), float(cor[0, 2])
+    s = p[:, 2] / zf
+    ref = ((p[:, 2] >= 0) & (p[:, 2] <= zf) & (p[:, 0] >= cor[0, 0] * s) & (p[:, 0] <= cor[2, 0] * s) &
+           (p[:, 1] >= cor[0, 1] * s) & (p[:, 1] <= cor[1, 1] * s))
+    assert np.array_equal(keep, ref) and 500 < keep.sum() < cloud.shape[0] // 2
+    c = cor.astype(np.float64)
+    m, inside = c.mean(0), np.ones(cloud.shape[0], bool)
+    for a, b in ((0, 1), (1, 3), (3, 2), (2, 0)):
+        n = np.cross(c[a], c[b])
+        n = -n if n @ m > 0 else n
+        inside &= p @ n <= 0
+    n = np.cross(c[1] - c[0], c[2] - c[0])
+    d = n @ c[0]
+    n, d = (-n, -d) if d < 0 else (n, d)
+    inside &= p @ n <= d
+    assert np.array_equal(inside, keep)
+
+
 # ---- the kernels' neighbour query, host build, vs the oracle --------------------------------------------------
 
 def _capi():

@@ -17,7 +17,9 @@ it is frozen here as small float32 fixtures:
   scene_crop_raw.npz                the crop before any filtering: raw back-projected points inside the
                                     frustum (xyz only) — the input of the pre-processing stages
                                     Subsampling / OutlierProcessing / NormalEstimation
-                                    (include/CloudProcessing.h:340-401)        (`--raw-only` writes just this)
+                                    (include/CloudProcessing.h:340-401)
+  crop_box.npz                      the surrogate box, the four depth pixels SceneCropping reads at its expanded
+                                    corners and the intrinsics                 (`--raw-only` writes just these two)
 
 Usage: OPENCV_IO_ENABLE_OPENEXR=1 python tools/make_fixtures.py [--raw-only]
 """
@@ -108,6 +110,20 @@ def frustum_crop(xyz, depth, box, margin_px=30, margin_z=0.15):
     return (u >= u0) & (u <= u1) & (v >= v0) & (v <= v1) & (z <= zmax) & (z > 0)
 
 
+def save_crop_box(depth, box=(536, 211, 95, 191)):
+    """crop_box.npz: the surrogate YOLO box (x, y, width, height) and the four depth pixels SceneCropping reads at
+    its 30-pixel-expanded corners (include/CloudProcessing.h:279-288) — all the crop needs from the depth image"""
+    x, y, w, h = box
+    rows, cols = depth.shape
+    left, top = max(x - 30, 0), max(y - 30, 0)
+    right = x + w + 30 if x + w + 30 < cols else cols - 1
+    bottom = y + h + 30 if y + h + 30 < rows else rows - 1
+    px = np.array([[top, left], [top, right], [bottom, left], [bottom, right]], np.int32)  # (row, col) of depth_1..4
+    np.savez_compressed(os.path.join(OUT, "crop_box.npz"), box=np.array(box, np.int32), image=np.array([rows, cols], np.int32),
+                        pixels=px, depths=np.array([depth[r, c] for r, c in px], np.float32),
+                        intrinsics=np.array([FX, FY, CX, CY], np.float64))
+
+
 def main():
     import cv2
 
@@ -120,6 +136,7 @@ def main():
         crop_raw = xyz[frustum_crop(xyz, depth, (536, 211, 631, 402))]
         print("scene_crop_raw", crop_raw.shape)
         np.savez_compressed(os.path.join(OUT, "scene_crop_raw.npz"), cloud=crop_raw.astype(np.float32))
+        save_crop_box(depth)
         return 0
     bottle = read_ply_ascii(os.path.join(REF, "data", "bottle_remesh_meter_normalized.ply"))
     print("bottle", bottle.shape)
@@ -147,6 +164,7 @@ def main():
     print("scene_crop_1cm", crop_raw.shape, "->", crop.shape)
     np.savez_compressed(os.path.join(OUT, "scene_crop_1cm.npz"), cloud=crop)
     np.savez_compressed(os.path.join(OUT, "scene_crop_raw.npz"), cloud=crop_raw.astype(np.float32))
+    save_crop_box(depth)
 
 
 if __name__ == "__main__":

@@ -100,6 +100,8 @@ SYMBOLS = {
     "b200ppf_normal_estimation": (_i, [_vp, _vp, _i, _vp, _i]),
     "b200ppf_curvature_edges": (_i, [_vp, _vp, _f, C.POINTER(_vp)]),
     "b200ppf_normalize_normals": (_i, [_vp, _vp]),
+    "b200ppf_frustum_corners": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
+    "b200ppf_crop_pyramid": (_i, [_vp, _vp, _vp, C.POINTER(_vp), _vp]),
     "b200ppf_debug_knn_host": (_i, [_vp, _sz, _sz, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "b200ppf_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
 }
@@ -220,6 +222,15 @@ class Context:
         h = C.c_void_p()
         self.check(lib().b200ppf_cloud_upload_xyz(self._h, _p(xyz), xyz.shape[0], xyz.shape[1], C.byref(h)))
         return Cloud(self, h)
+
+    def crop_pyramid(self, cloud: "Cloud", corners):
+        """CloudProcessor::SceneCropping's ConvexHull + CropHull for one box: -> (cropped Cloud, kept indices)"""
+        c12 = np.ascontiguousarray(corners, np.float32).reshape(12)
+        kept = np.zeros(cloud.size, np.uint32)
+        h = C.c_void_p()
+        self.check(lib().b200ppf_crop_pyramid(self._h, cloud._h, _p(c12), C.byref(h), _p(kept)))
+        out = Cloud(self, h)
+        return out, kept[:out.size].copy()
 
     def voxel_grid(self, cloud: "Cloud", leaf) -> "Cloud":
         """pcl::VoxelGrid<PointXYZ>::filter (Subsampling)"""
@@ -418,6 +429,18 @@ def debug_alpha_bins(alpha_m, alpha_s, angle_step, alpha_mode=ALPHA_MODE_A, ctx:
     if rc != 0:
         raise B200PPFError(rc, lib().b200ppf_last_error(ctx._h if ctx else None).decode())
     return fast, exact
+
+
+def frustum_corners(depth, box, intrinsics):
+    """SceneCropping's four far corners for box = (x, y, w, h), intrinsics = (fx, fy, ppx, ppy): (4, 3) float32"""
+    depth = np.ascontiguousarray(depth, np.float32)
+    out = np.zeros((4, 3), np.float32)
+    fx, fy, ppx, ppy = (float(v) for v in intrinsics)
+    rc = lib().b200ppf_frustum_corners(_p(depth), depth.shape[0], depth.shape[1], int(box[0]), int(box[1]), int(box[2]),
+                                       int(box[3]), fx, fy, ppx, ppy, _p(out))
+    if rc != 0:
+        raise B200PPFError(rc, lib().b200ppf_last_error(None).decode())
+    return out
 
 
 def debug_knn_host(xyz, k, mode=0, cell_edge=0.0, viewpoint=None, covariance_mode=0):

@@ -814,6 +814,25 @@ int b200ppf_normalize_normals(b200ppf_ctx *ctx, b200ppf_cloud *cloud) {
     return prep_renormalize(ctx, cloud);
 }
 
+int b200ppf_frustum_corners(const float *depth, int rows, int cols, int box_x, int box_y, int box_w, int box_h, double fx,
+                            double fy, double ppx, double ppy, float *corners12) {
+    if (!depth || !corners12 || rows < 1 || cols < 1 || box_w < 0 || box_h < 0 || box_x >= cols || box_y >= rows ||
+        box_x + box_w + 30 < 0 || box_y + box_h + 30 < 0 || !(fx != 0.0) || !(fy != 0.0))
+        return fail_msg(nullptr, B200PPF_ERR_INVALID, "frustum corners: bad argument");
+    prep_frustum_corners(depth, rows, cols, box_x, box_y, box_w, box_h, fx, fy, ppx, ppy, corners12);
+    return B200PPF_OK;
+}
+
+int b200ppf_crop_pyramid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *corners12, b200ppf_cloud **out,
+                         uint32_t *kept_host) {
+    CHECK_CTX(ctx);
+    if (!in || !corners12 || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "crop: null argument");
+    *out = nullptr;
+    for (int k = 0; k < 12; ++k)
+        if (!std::isfinite(corners12[k])) return fail_msg(ctx, B200PPF_ERR_INVALID, "crop: non-finite corner");
+    return prep_crop_pyramid(ctx, in, corners12, out, kept_host);
+}
+
 int b200ppf_debug_knn_host(const float *xyz, size_t n, size_t stride, int k, int mode, float cell_edge, const float *viewpoint3,
                            int cov_mode, uint32_t *idx, float *d2, float *mean_dist, float *normals4) {
     if ((n && !xyz) || stride < 3 || k < 1 || k > 128 || (size_t)k > std::max<size_t>(1, n) || mode < 0 || mode > 2 ||

@@ -140,6 +140,9 @@ int prep_sor(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stdde
 int prep_normals(b200ppf_ctx *ctx, b200ppf_cloud *cloud, int k, const float *viewpoint3, int cov_mode);
 int prep_curvature_edges(b200ppf_ctx *ctx, const b200ppf_cloud *in, float threshold, b200ppf_cloud **out);
 int prep_renormalize(b200ppf_ctx *ctx, b200ppf_cloud *cloud);
+void prep_frustum_corners(const float *depth, int rows, int cols, int bx, int by, int bw, int bh, double fx, double fy,
+                          double ppx, double ppy, float *corners12);
+int prep_crop_pyramid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *corners12, b200ppf_cloud **out, uint32_t *kept_host);
 int prep_debug_knn_host(const float *xyz, size_t n, size_t stride, int k, int mode, float cell_edge, const float *viewpoint3,
                         int cov_mode, uint32_t *idx, float *d2, float *mean_dist, float *normals4);
 

@@ -1,7 +1,9 @@
-// prep.cu — scene pre-processing on the device ("next" row): the stages the reference
-// runs between its YOLO crop and the PPF engine, so that a frame goes crop -> N x 6 scene cloud without
-// leaving HBM.
+// prep.cu — scene pre-processing on the device ("next" rows, SURVEY.md §8f rank 2 and the crop of rank 4): the
+// stages the reference runs between its YOLO boxes and the PPF engine, so that a frame goes full scene cloud ->
+// N x 6 object cloud without leaving HBM.
 //
+//   P0 frustum crop       reference include/CloudProcessing.h:263-339  pcl::ConvexHull + pcl::CropHull (dim 3)
+//                         on {four corner rays, origin}; include/Camera.h:50-61 back_projection_bbox
 //   P1 voxel grid         reference include/CloudProcessing.h:359-377  pcl::VoxelGrid<PointXYZ>
 //                         [PCL] filters/include/pcl/filters/impl/voxel_grid.hpp applyFilter
 //   P2 k nearest          FLANN kd-tree behind StatisticalOutlierRemoval / NormalEstimationOMP
@@ -691,6 +693,25 @@ int compact_cloud(b200ppf_ctx *ctx, const b200ppf_cloud *in, const uint32_t *fla
     return B200PPF_OK;
 }
 
+// ---- P0: frustum crop ----------------------------------------------------------------------------------------
+// the pyramid {apex = camera origin, four far corners} as five half-spaces n.p <= d (double)
+struct PyramidPlanes {
+    double n[5][3];
+    double d[5];
+};
+
+__global__ void __launch_bounds__(256)
+pyramid_flag_kernel(const float4 *__restrict__ pos, uint32_t n, PyramidPlanes pl, uint32_t *__restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    const double x = p.x, y = p.y, z = p.z;
+    bool in = true;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) in = in && (pl.n[f][0] * x + pl.n[f][1] * y + pl.n[f][2] * z <= pl.d[f]);
+    flags[i] = in ? 1u : 0u;
+}
+
 // ---- P6 ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) renormalize_kernel(float4 *__restrict__ nrm, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -946,6 +967,73 @@ int prep_curvature_edges(b200ppf_ctx *ctx, const b200ppf_cloud *in, float thresh
     EventTimer timer(ctx);
     if (n) PPF_LAUNCH(ctx, curvature_flag_kernel, (n + 255) / 256, 256, 0, in->nrm, n, threshold, flags);
     int rc = compact_cloud(ctx, in, flags, out, nullptr);
+    timer.stop();
+    cudaFreeAsync(flags, ctx->stream);
+    return rc;
+}
+
+// reference include/CloudProcessing.h:270-300 + include/Camera.h:50-61, restated: host arithmetic on four pixels
+void prep_frustum_corners(const float *depth, int rows, int cols, int bx, int by, int bw, int bh, double fx, double fy,
+                          double ppx, double ppy, float *corners12) {
+    double left = bx - 30;  // the box grown by 30 pixels, clamped to the image
+    if (left < 0) left = 0;
+    double top = by - 30;
+    if (top < 0) top = 0;
+    double right = bx + bw + 30;
+    if (right >= cols) right = cols - 1;
+    double bottom = by + bh + 30;
+    if (bottom >= rows) bottom = rows - 1;
+    const int l = (int)left, t = (int)top, r = (int)right, b = (int)bottom;
+    const float depth_avg = (depth[(size_t)t * cols + l] + depth[(size_t)t * cols + r] + depth[(size_t)b * cols + l] +
+                             depth[(size_t)b * cols + r]) / 4;
+    const int us[4] = {l, l, r, r}, vs[4] = {t, b, t, b};  // left_top, left_bot, right_top, right_bot
+    for (int c = 0; c < 4; ++c) {
+        // back_projection_bbox: point.x = (float)(u - ppx) * z / fx  (float product, double quotient, float store)
+        corners12[3 * c + 0] = (float)((float)(us[c] - ppx) * depth_avg / fx);
+        corners12[3 * c + 1] = (float)((float)(vs[c] - ppy) * depth_avg / fy);
+        float z = depth_avg;
+        z += 0.15;  // "left_top.z += 0.15": float += double
+        corners12[3 * c + 2] = z;
+    }
+}
+
+int prep_crop_pyramid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *corners12, b200ppf_cloud **out, uint32_t *kept_host) {
+    double c[4][3], m[3] = {0, 0, 0};
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 3; ++k) c[i][k] = corners12[3 * i + k], m[k] += 0.25 * corners12[3 * i + k];
+    auto cross = [](const double *a, const double *b, double *o) {
+        o[0] = a[1] * b[2] - a[2] * b[1];
+        o[1] = a[2] * b[0] - a[0] * b[2];
+        o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto dot = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    PyramidPlanes pl;
+    const int cyc[4] = {0, 1, 3, 2};  // left_top -> left_bot -> right_bot -> right_top
+    for (int s = 0; s < 4; ++s) {  // side faces contain the apex (the origin): d = 0; the corners' centroid is inside
+        cross(c[cyc[s]], c[cyc[(s + 1) & 3]], pl.n[s]);
+        if (dot(pl.n[s], m) > 0)
+            for (int k = 0; k < 3; ++k) pl.n[s][k] = -pl.n[s][k];
+        pl.d[s] = 0.0;
+    }
+    double e1[3], e2[3];
+    for (int k = 0; k < 3; ++k) e1[k] = c[1][k] - c[0][k], e2[k] = c[2][k] - c[0][k];
+    cross(e1, e2, pl.n[4]);
+    pl.d[4] = dot(pl.n[4], c[0]);
+    if (pl.d[4] < 0) {  // the apex is inside
+        for (int k = 0; k < 3; ++k) pl.n[4][k] = -pl.n[4][k];
+        pl.d[4] = -pl.d[4];
+    }
+    const double nn = std::sqrt(dot(pl.n[4], pl.n[4]));
+    if (!(nn > 0.0) || !(pl.d[4] > 0.0)) return fail_msg(ctx, B200PPF_ERR_INVALID, "crop: the four corners do not span a base in front of the camera");
+    // the reference's corners share one z; a base that is not planar would make the hull a different solid
+    if (std::fabs(dot(pl.n[4], c[3]) - pl.d[4]) > 1e-6 * nn * (std::fabs(c[3][0]) + std::fabs(c[3][1]) + std::fabs(c[3][2]) + 1.0))
+        return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "crop: the four corners are not coplanar");
+    const uint32_t n = (uint32_t)in->n;
+    uint32_t *flags = nullptr;
+    PPF_CUDA(ctx, cudaMallocAsync(&flags, std::max<size_t>(1, n) * sizeof(uint32_t), ctx->stream));
+    EventTimer timer(ctx);
+    if (n) PPF_LAUNCH(ctx, pyramid_flag_kernel, (n + 255) / 256, 256, 0, in->pos, n, pl, flags);
+    int rc = compact_cloud(ctx, in, flags, out, kept_host);
     timer.stop();
     cudaFreeAsync(flags, ctx->stream);
     return rc;
