@@ -310,6 +310,40 @@ int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf
                      const b200ppf_cloud *scene, size_t ref_rate, float pos_thr, float rot_thr,
                      float *final16, float *poses16, uint32_t *votes, size_t *n_out);
 
+/* ---- one YOLO box, start to finish ------------------------------------------------------------------------
+ * What src/YOLO_cropping_ppf_test.cpp:91-122 does per detected object, as one call on device handles:
+ * SceneCropping -> Subsampling(leaf) -> OutlierProcessing(mean_k, stddev_mul) -> NormalEstimation(normal_k) ->
+ * EdgeExtraction(edge_curvature) -> PointCloudXYZNormalToMat -> match (PPFRegistration::align with the PCL
+ * thresholds below) -> ICP on the best poses (include/CloudProcessing.h:508-530: top N, ICP(100, 0.005, 2.5, 8),
+ * resultsSub[0] returned).  scene is the full frame (xyz; b200ppf_cloud_upload_xyz), corners12 comes from
+ * b200ppf_frustum_corners, model / table from the training calls above.  Nothing is copied to the host between
+ * the stages.  object_out (optional) receives the pre-processed object cloud, edges_out (optional) its curvature
+ * edges; free them with b200ppf_cloud_free. */
+typedef struct b200ppf_object_params {
+    float leaf;             /* Subsampling leaf size (CLI argument 4 of the reference) */
+    int sor_mean_k;         /* 50 */
+    double sor_stddev_mul;  /* CLI argument 5 */
+    int normal_k;           /* 30 */
+    float edge_curvature;   /* 0.03; <= 0 skips the edge extraction */
+    uint32_t ref_rate;      /* every ref_rate-th object point votes: 20 = the reference's 1 / 0.05 */
+    float pos_thr, rot_thr; /* pose clustering: PCL's 0.01 m, 20 degrees (radians here) */
+    int icp_poses;          /* best poses refined by ICP: 5 in the reference (the engine returns at most 3); 0 = none */
+    b200ppf_icp_params icp; /* (100, 0.005, 2.5, 8) */
+} b200ppf_object_params;
+typedef struct b200ppf_object_result {
+    double pose[16];  /* row-major 4x4, model -> scene: the best pose, after ICP when icp_poses > 0 */
+    double residual;  /* its ICP residual (0 without ICP) */
+    uint32_t votes;   /* votes of its pose cluster */
+    uint32_t n_poses; /* pose clusters the matching returned */
+    uint32_t n_cropped, n_sampled, n_filtered, n_edges; /* object size after the crop, voxel grid, outlier removal; edges */
+    /* device time per stage (CUDA events) and host wall time of the whole call, milliseconds */
+    float crop_ms, voxel_ms, outlier_ms, normals_ms, edges_ms, match_ms, icp_ms, total_wall_ms;
+} b200ppf_object_result;
+void b200ppf_object_params_default(b200ppf_object_params *params);
+int b200ppf_match_object(b200ppf_ctx *ctx, const b200ppf_cloud *scene, const float corners12[12],
+                         const b200ppf_cloud *model, const b200ppf_table *table, const b200ppf_object_params *params,
+                         b200ppf_object_result *result, b200ppf_cloud **object_out, b200ppf_cloud **edges_out);
+
 #ifdef __cplusplus
 }
 #endif

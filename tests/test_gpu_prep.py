@@ -243,3 +243,45 @@ def test_cpp_pcl_prep_shim_end_to_end(tmp_path, ctx, crop_raw):
     for i in range(3):
         assert np.array_equal(np.array([float(x) for x in lines[1 + i].split()[1:]], np.float32), mat[i])
     assert float(lines[4].split()[1]) == float(np.sum(mat.astype(np.float64).reshape(-1).cumsum()[-1:]))
+
+
+def test_match_object_equals_the_stepwise_chain(ctx, oracle, scene_full, bottle):
+    """b200ppf_match_object = SceneCropping -> Subsampling -> OutlierProcessing -> NormalEstimation -> EdgeExtraction ->
+    re-normalise -> align -> ICP in one call (src/YOLO_cropping_ppf_test.cpp:91-122): the same result as the stages
+    called one by one, and the pose the CPU chain finds on the device's own object cloud"""
+    from yolo_ppf_pose_estimation_b200 import capi
+    depth, box, K = _crop_box()
+    cor = capi.frustum_corners(depth, box, K)
+    scene = ctx.upload_xyz(scene_full[:, :3])
+    model = ctx.upload_cloud(bottle)
+    table = ctx.table_build_from_cloud(model, ANGLE_STEP, DIST_STEP)
+    res, obj, edges = ctx.match_object(scene, cor, model, table, leaf=0.01, ref_rate=5, icp_max_iterations=30, icp_num_levels=4)
+    # stage by stage
+    d, _ = ctx.crop_pyramid(scene, cor)
+    n_crop = d.size
+    d = ctx.voxel_grid(d, 0.01)
+    n_vox = d.size
+    d, _, _, _ = ctx.statistical_outlier_removal(d, 50, 1.0)
+    ctx.normal_estimation(d, 30)
+    e = ctx.curvature_edges(d, 0.03)
+    ctx.normalize_normals(d)
+    ctx.normalize_normals(e)
+    assert (res["n_cropped"], res["n_sampled"], res["n_filtered"], res["n_edges"]) == (n_crop, n_vox, d.size, e.size)
+    assert np.array_equal(obj.download(curvature=True), d.download(curvature=True))
+    assert np.array_equal(edges.download(curvature=True), e.download(curvature=True))
+    final, poses, votes = ctx.register(model, table, d, ref_rate=5)
+    P, resid, _ = ctx.icp_refine(model, d, poses.astype(np.float64), max_iterations=30, num_levels=4)
+    assert res["n_poses"] == len(poses) and res["votes"] == votes[0]
+    assert np.array_equal(res["pose"], P[0]) and res["residual"] == resid[0]
+    assert res["total_wall_ms"] > 0 and res["match_ms"] > 0 and res["icp_ms"] > 0
+    # the CPU chain on the same object cloud
+    obj_host = d.download()
+    hm = oracle.HashMap(ANGLE_STEP, DIST_STEP).set_input_feature_cloud(oracle.ppf_estimation(bottle))
+    _, rposes, rvotes, _ = hm.register(bottle, obj_host, ref_rate=5, n_threads=oracle.max_threads())
+    R, _, _ = oracle.icp_refine(bottle, obj_host, rposes[:1].astype(np.float64), max_iterations=30, num_levels=4)
+    dt = float(np.linalg.norm(res["pose"][:3, 3] - R[0][:3, 3]))
+    print(f"object: {n_crop} cropped -> {n_vox} -> {d.size} points, votes {res['votes']} vs {rvotes[0]}, |dt| vs CPU chain {dt:.2e} m, "
+          f"wall {res['total_wall_ms']:.2f} ms")
+    assert dt < 1e-3
+    with pytest.raises(capi.B200PPFError):  # nothing inside the frustum
+        ctx.match_object(ctx.upload_xyz(scene_full[:, :3] + np.float32(10)), cor, model, table)

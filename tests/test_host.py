@@ -39,6 +39,7 @@ def test_struct_layouts_match_the_header():
     assert capi.HYP_DTYPE.itemsize == 64 and capi.SIG_DTYPE.itemsize == 20
     assert C.sizeof(capi.TableInfo) == 4 * 8 + 4 * 4 + 8 * 4 + 4 * 4
     assert C.sizeof(capi.Timings) == 12 * 4
+    assert C.sizeof(capi.ObjectParams) == 56 and C.sizeof(capi.ObjectResult) == 16 * 8 + 8 + 6 * 4 + 8 * 4  # = the C sizeof
     assert capi.HYP_DTYPE.fields["votes"][1] == 48 and capi.HYP_DTYPE.fields["scene_index"][1] == 60
 
 

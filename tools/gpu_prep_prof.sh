@@ -10,12 +10,12 @@ if [ "$2" = "full" ]; then
 else
     python -m pytest tests/test_gpu_prep.py -x -q 2>&1 | tail -5 | tee $O/pytest_$TAG.log
 fi
-timeout 200 python tools/prep_bench.py > $O/prep_bench_$TAG.json 2> $O/prep_bench_$TAG.err; cat $O/prep_bench_$TAG.json; tail -3 $O/prep_bench_$TAG.err
+timeout 300 python tools/prep_bench.py > $O/prep_bench_$TAG.json 2> $O/prep_bench_$TAG.err; cat $O/prep_bench_$TAG.json; tail -3 $O/prep_bench_$TAG.err
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/prep_launches_$TAG.csv \
-    python tools/prep_bench.py --no-cpu --repeat 1 --only big > $O/ncu_prep_launches_$TAG.log 2>&1
+    python tools/prep_bench.py --no-cpu --repeat 1 --only big --no-frames > $O/ncu_prep_launches_$TAG.log 2>&1
 for which in sor:2 normals:3; do
     name=${which%%:*}; skip=${which##*:}
-    timeout 200 ncu --set full --clock-control none --import-source on -k regex:knn_kernel -s $skip -c 1 -f -o $O/prof_knn_${name}_$TAG \
-        python tools/prep_bench.py --no-cpu --repeat 1 --only big > $O/ncu_full_knn_${name}_$TAG.log 2>&1
+    timeout 200 ncu --set full --clock-control none --import-source on -k regex:knn_ -s $skip -c 1 -f -o $O/prof_knn_${name}_$TAG \
+        python tools/prep_bench.py --no-cpu --repeat 1 --only big --no-frames > $O/ncu_full_knn_${name}_$TAG.log 2>&1
     tail -2 $O/ncu_full_knn_${name}_$TAG.log | cut -c1-200
 done

@@ -78,11 +78,87 @@ def cpu_kdtree(c, xyz, leaf):
             "threads": os.cpu_count()}
 
 
+def frame_case(name):
+    """(scene xyz, corners, model N x 6, match_object overrides) for one detected object"""
+    from yolo_ppf_pose_estimation_b200 import capi, synth
+    gold = os.path.join(ROOT, "tests", "golden")
+    if name == "reference frame":  # the reference's own data: regenerated scene (1 cm), surrogate YOLO box, bottle model
+        b = np.load(os.path.join(gold, "crop_box.npz"))
+        depth = np.zeros(tuple(b["image"]), np.float32)
+        for (r, c), d in zip(b["pixels"], b["depths"]):
+            depth[r, c] = d
+        cor = capi.frustum_corners(depth, b["box"], b["intrinsics"])
+        scene = np.load(os.path.join(gold, "scene_full_1cm.npz"))["cloud"][:, :3]
+        model = np.load(os.path.join(gold, "bottle_1cm.npz"))["cloud"]
+        return np.ascontiguousarray(scene, np.float32), cor, model.astype(np.float32), dict(leaf=0.01, ref_rate=5)
+    # synthetic 1 Mi-point frame (config C4), library model 0: the box is the projection of its instance
+    k = 0
+    scene = np.ascontiguousarray(synth.synth_library_scene(1 << 20)[:, :3], np.float32)
+    model = synth.synth_model(2000, 10 + k, k).astype(np.float32)
+    T = synth.library_pose(k)
+    p = model[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    zf = np.float32(p[:, 2].max() + 0.15)
+    tx, ty = p[:, 0] / p[:, 2], p[:, 1] / p[:, 2]
+    xl, xr, yt, yb = (np.float32(v * zf) for v in (tx.min() - 0.03, tx.max() + 0.03, ty.min() - 0.03, ty.max() + 0.03))
+    cor = np.array([[xl, yt, zf], [xl, yb, zf], [xr, yt, zf], [xr, yb, zf]], np.float32)
+    return scene, cor, model, dict(leaf=0.005, ref_rate=20)  # 20 = the reference's 1 / 0.05
+
+
+def frame_bench(c, name, repeat, with_cpu):
+    """b200ppf_match_object (crop -> voxel -> outlier removal -> normals -> edges -> align -> ICP) per detected
+    object, scene resident in HBM as it would be for every box of a frame, vs the same chain on the CPU"""
+    from yolo_ppf_pose_estimation_b200 import capi
+    scene, cor, model, over = frame_case(name)
+    a = np.float32(12.0) / np.float32(180.0) * np.float32(np.pi)
+    dm = c.upload_cloud(model)
+    table = c.table_build_from_cloud(dm, a, np.float32(0.01))
+    t0 = time.perf_counter()
+    ds = c.upload_xyz(scene)
+    upload_ms = 1e3 * (time.perf_counter() - t0)
+    runs = [c.match_object(ds, cor, dm, table, **over)[0] for _ in range(repeat + 1)][1:]
+    med = {k: float(np.median([r[k] for r in runs])) for k in runs[0] if k.endswith("_ms")}
+    r = runs[-1]
+    rec = {"frame": name, "scene_points": int(scene.shape[0]), "model_points": int(model.shape[0]), "params": over,
+           "sizes": {k: int(r[k]) for k in ("n_cropped", "n_sampled", "n_filtered", "n_edges", "n_poses")}, "votes": int(r["votes"]),
+           "scene_upload_ms": upload_ms, "b200_ms": med}
+    if with_cpu:
+        from oracle import binding as ob
+        nt = ob.max_threads()
+        hm = ob.HashMap(a, np.float32(0.01)).set_input_feature_cloud(ob.ppf_estimation(model))  # training is offline
+        t = {}
+        t0 = time.perf_counter()
+        v = scene[ob.crop_pyramid(scene, cor)]
+        t["crop"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        v = ob.voxel_grid(v, over["leaf"])[0]
+        t["voxel"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        v = v[ob.statistical_outlier_removal(v, 50, 1.0)[0]]
+        t["outlier"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        n = ob.normals(v, 30)
+        obj = np.concatenate([v, ob.renormalize_normals(n[:, :3])], axis=1)
+        t["normals"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        _, poses, votes, _ = hm.register(model, obj, ref_rate=over["ref_rate"], n_threads=nt)
+        t["match"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        R, _, _ = ob.icp_refine(model, obj, poses.astype(np.float64))
+        t["icp"] = 1e3 * (time.perf_counter() - t0)
+        t["total"] = float(sum(t.values()))
+        rec["cpu_ms"] = t
+        rec["cpu_threads"] = nt
+        rec["cpu_note"] = "CPU restatement of the PCL / OpenCV operators, all host threads (ICP: one thread per pose, sequential); neighbour search by brute force"
+        rec["translation_diff_vs_cpu_m"] = float(np.linalg.norm(r["pose"][:3, 3] - R[0][:3, 3]))
+    print(json.dumps(rec), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--repeat", type=int, default=5)
-    ap.add_argument("--only", choices=["crop", "big"], default=None, help="run one of the two inputs")
+    ap.add_argument("--only", choices=["crop", "big", "frames"], default=None, help="run one of the inputs / only the per-object frames")
+    ap.add_argument("--no-frames", action="store_true", help="skip the per-object (b200ppf_match_object) lines")
     ap.add_argument("--cpu-points", type=int, default=60000, help="the CPU leg (brute-force neighbours) takes a raw subset that voxelises to about this many points")
     args = ap.parse_args()
     from yolo_ppf_pose_estimation_b200 import capi, synth
@@ -90,7 +166,7 @@ def main():
     crop = np.load(os.path.join(ROOT, "tests", "golden", "scene_crop_raw.npz"))["cloud"].astype(np.float32)
     big = np.ascontiguousarray(synth.synth_library_scene(1 << 20)[:, :3], np.float32)
     for name, xyz, leaf in (("reference crop", crop, 0.005), ("synthetic 1Mi scene", big, 0.005)):
-        if args.only and (args.only == "crop") != (name == "reference crop"):
+        if args.only and (args.only == "frames" or (args.only == "crop") != (name == "reference crop")):
             continue
         ms, sizes = gpu_chain(c, xyz, leaf, args.repeat)
         rec = {"input": name, "leaf": leaf, "sizes": sizes, "b200_ms": ms,
@@ -104,6 +180,9 @@ def main():
             rec["cpu_sample_raw_points"] = int(sub.shape[0])
             rec["cpu_kdtree_ms"] = cpu_kdtree(c, xyz, leaf)
         print(json.dumps(rec), flush=True)
+    if not args.no_frames and args.only in (None, "frames"):
+        for name in ("reference frame", "synthetic 1Mi frame"):
+            frame_bench(c, name, args.repeat, not args.no_cpu)
 
 
 if __name__ == "__main__":

@@ -42,6 +42,19 @@ class IcpParams(C.Structure):
                 ("num_levels", C.c_int)]
 
 
+class ObjectParams(C.Structure):
+    _fields_ = [("leaf", C.c_float), ("sor_mean_k", C.c_int), ("sor_stddev_mul", C.c_double), ("normal_k", C.c_int),
+                ("edge_curvature", C.c_float), ("ref_rate", C.c_uint32), ("pos_thr", C.c_float), ("rot_thr", C.c_float),
+                ("icp_poses", C.c_int), ("icp", IcpParams)]
+
+
+class ObjectResult(C.Structure):
+    _fields_ = [("pose", C.c_double * 16), ("residual", C.c_double), ("votes", C.c_uint32), ("n_poses", C.c_uint32),
+                ("n_cropped", C.c_uint32), ("n_sampled", C.c_uint32), ("n_filtered", C.c_uint32), ("n_edges", C.c_uint32)] + \
+               [(n, C.c_float) for n in ("crop_ms", "voxel_ms", "outlier_ms", "normals_ms", "edges_ms", "match_ms", "icp_ms",
+                                         "total_wall_ms")]
+
+
 # every symbol include/b200ppf.h declares: (name, restype, argtypes)
 _vp, _sz, _f, _i = C.c_void_p, C.c_size_t, C.c_float, C.c_int
 SYMBOLS = {
@@ -103,6 +116,9 @@ SYMBOLS = {
     "b200ppf_frustum_corners": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
     "b200ppf_crop_pyramid": (_i, [_vp, _vp, _vp, C.POINTER(_vp), _vp]),
     "b200ppf_debug_knn_host": (_i, [_vp, _sz, _sz, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
+    "b200ppf_object_params_default": (None, [C.POINTER(ObjectParams)]),
+    "b200ppf_match_object": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(ObjectParams), C.POINTER(ObjectResult), C.POINTER(_vp),
+                                  C.POINTER(_vp)]),
     "b200ppf_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
 }
 
@@ -273,6 +289,25 @@ class Context:
     def normalize_normals(self, cloud: "Cloud"):
         """CloudProcessor::PointCloudXYZNormalToMat's re-normalisation, in place"""
         self.check(lib().b200ppf_normalize_normals(self._h, cloud._h))
+
+    def match_object(self, scene: "Cloud", corners, model: "Cloud", table: "Table", **overrides):
+        """One YOLO box start to finish (src/YOLO_cropping_ppf_test.cpp:91-122) on device handles:
+        -> (result dict, object Cloud, edges Cloud or None).  overrides: fields of ObjectParams (icp_* for the ICP)."""
+        prm = ObjectParams()
+        lib().b200ppf_object_params_default(C.byref(prm))
+        for k, v in overrides.items():
+            if k.startswith("icp_") and k != "icp_poses":
+                setattr(prm.icp, k[4:], v)
+            else:
+                setattr(prm, k, v)
+        c12 = np.ascontiguousarray(corners, np.float32).reshape(12)
+        res = ObjectResult()
+        obj, edg = C.c_void_p(), C.c_void_p()
+        self.check(lib().b200ppf_match_object(self._h, scene._h, _p(c12), model._h, table._h, C.byref(prm), C.byref(res),
+                                              C.byref(obj), C.byref(edg)))
+        out = {n: getattr(res, n) for n, _ in ObjectResult._fields_ if n != "pose"}
+        out["pose"] = np.array(res.pose, np.float64).reshape(4, 4)
+        return out, Cloud(self, obj), (Cloud(self, edg) if edg.value else None)
 
     # ---- K1 / K2 -------------------------------------------------------------------------------
     def features_compute(self, model: "Cloud") -> "Features":

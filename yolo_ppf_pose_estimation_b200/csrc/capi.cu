@@ -1,5 +1,6 @@
 // capi.cu — the extern "C" surface declared in include/b200ppf.h.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -877,6 +878,85 @@ int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf
     rc = k4_cluster(ctx, ctx->d_hyps, ref_count, pos_thr, rot_thr, poses16, votes, n_out);
     if (rc) return rc;
     if (*n_out && final16) memcpy(final16, poses16, 16 * sizeof(float));
+    return B200PPF_OK;
+}
+
+void b200ppf_object_params_default(b200ppf_object_params *p) {
+    if (!p) return;
+    p->leaf = 0.01f;
+    p->sor_mean_k = 50;       // OutlierProcessing(50, thresh), src/YOLO_cropping_ppf_test.cpp:98
+    p->sor_stddev_mul = 1.0;
+    p->normal_k = 30;         // NormalEstimation(30), :101
+    p->edge_curvature = 0.03f;  // EdgeExtraction(0.03), :103
+    p->ref_rate = 20;         // relSceneSampleStep = 0.05, include/CloudProcessing.h:481
+    p->pos_thr = 0.01f;       // PCL defaults of PPFRegistration
+    p->rot_thr = 20.0f / 180.0f * 3.14159265358979f;
+    p->icp_poses = 5;         // N = 5, include/CloudProcessing.h:508
+    p->icp = b200ppf_icp_params{100, 0.005f, 2.5f, 8};
+}
+
+int b200ppf_match_object(b200ppf_ctx *ctx, const b200ppf_cloud *scene, const float *corners12, const b200ppf_cloud *model,
+                         const b200ppf_table *table, const b200ppf_object_params *params, b200ppf_object_result *res,
+                         b200ppf_cloud **object_out, b200ppf_cloud **edges_out) {
+    if (!ctx) return fail_msg(nullptr, B200PPF_ERR_INVALID, "null context");
+    if (object_out) *object_out = nullptr;
+    if (edges_out) *edges_out = nullptr;
+    if (!scene || !corners12 || !model || !table || !res) return fail_msg(ctx, B200PPF_ERR_INVALID, "match object: null argument");
+    b200ppf_object_params p;
+    b200ppf_object_params_default(&p);
+    if (params) p = *params;
+    memset(res, 0, sizeof(*res));
+    const auto t0 = std::chrono::steady_clock::now();
+    struct Owned {  // intermediate clouds live until the call returns
+        b200ppf_cloud *c = nullptr;
+        ~Owned() { if (c) b200ppf_cloud_free(c); }
+        b200ppf_cloud *release() { b200ppf_cloud *r = c; c = nullptr; return r; }
+    } cropped, sampled, object, edges;
+    int rc = b200ppf_crop_pyramid(ctx, scene, corners12, &cropped.c, nullptr);
+    if (rc) return rc;
+    res->crop_ms = ctx->timings.prep_ms;
+    res->n_cropped = (uint32_t)cropped.c->n;
+    if (cropped.c->n == 0) return fail_msg(ctx, B200PPF_ERR_STATE, "match object: no scene point inside the box's frustum");
+    const float leaf3[3] = {p.leaf, p.leaf, p.leaf};
+    if ((rc = b200ppf_voxel_grid(ctx, cropped.c, leaf3, &sampled.c))) return rc;
+    res->voxel_ms = ctx->timings.prep_ms;
+    res->n_sampled = (uint32_t)sampled.c->n;
+    if ((rc = b200ppf_statistical_outlier_removal(ctx, sampled.c, p.sor_mean_k, p.sor_stddev_mul, &object.c, nullptr, nullptr, nullptr)))
+        return rc;
+    res->outlier_ms = ctx->timings.prep_ms;
+    res->n_filtered = (uint32_t)object.c->n;
+    if ((rc = b200ppf_normal_estimation(ctx, object.c, p.normal_k, nullptr, B200PPF_COVARIANCE_SHIFTED))) return rc;
+    res->normals_ms = ctx->timings.prep_ms;
+    if (p.edge_curvature > 0.0f) {
+        if ((rc = b200ppf_curvature_edges(ctx, object.c, p.edge_curvature, &edges.c))) return rc;
+        res->edges_ms = ctx->timings.prep_ms;
+        res->n_edges = (uint32_t)edges.c->n;
+    }
+    if ((rc = b200ppf_normalize_normals(ctx, object.c))) return rc;
+    if (edges.c && (rc = b200ppf_normalize_normals(ctx, edges.c))) return rc;
+    float final16[16], poses16[3 * 16];
+    uint32_t votes[3] = {0, 0, 0};
+    size_t n_poses = 0;
+    if ((rc = b200ppf_register(ctx, model, table, object.c, p.ref_rate, p.pos_thr, p.rot_thr, final16, poses16, votes, &n_poses)))
+        return rc;
+    b200ppf_timings tm;
+    b200ppf_get_timings(ctx, &tm);
+    res->match_ms = tm.grid_ms + tm.vote_ms + tm.pose_ms + tm.cluster_ms;
+    res->n_poses = (uint32_t)n_poses;
+    if (n_poses == 0) return fail_msg(ctx, B200PPF_ERR_STATE, "match object: the matching returned no pose");  // reference: exit(0), :502-507
+    double refined[3 * 16], residuals[3] = {0, 0, 0};
+    for (size_t k = 0; k < n_poses * 16; ++k) refined[k] = (double)poses16[k];
+    const size_t n_icp = std::min<size_t>(n_poses, p.icp_poses > 0 ? (size_t)p.icp_poses : 0);
+    if (n_icp) {
+        if ((rc = b200ppf_icp_refine(ctx, model, object.c, &p.icp, refined, n_icp, residuals, nullptr))) return rc;
+        res->icp_ms = ctx->timings.icp_ms;
+    }
+    memcpy(res->pose, refined, 16 * sizeof(double));  // resultsSub[0]
+    res->residual = residuals[0];
+    res->votes = votes[0];
+    res->total_wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (object_out) *object_out = object.release();
+    if (edges_out) *edges_out = edges.release();
     return B200PPF_OK;
 }
 
