@@ -36,6 +36,37 @@ namespace {
 
 constexpr int SCAN_BLOCK = 1024;
 
+// stream-ordered scratch buffer, returned to the pool when it leaves scope — also on the early error returns
+template <typename T>
+struct StreamBuf {
+    b200ppf_ctx *ctx;
+    T *p = nullptr;
+    explicit StreamBuf(b200ppf_ctx *c) : ctx(c) {}
+    StreamBuf(const StreamBuf &) = delete;
+    StreamBuf &operator=(const StreamBuf &) = delete;
+    ~StreamBuf() {
+        if (p) cudaFreeAsync(p, ctx->stream);
+    }
+    cudaError_t alloc(size_t count) { return cudaMallocAsync(&p, std::max<size_t>(1, count) * sizeof(T), ctx->stream); }
+    operator T *() const { return p; }
+};
+
+// an output cloud under construction: freed unless released to the caller
+struct CloudOwner {
+    b200ppf_cloud *c = nullptr;
+    CloudOwner() = default;
+    CloudOwner(const CloudOwner &) = delete;
+    CloudOwner &operator=(const CloudOwner &) = delete;
+    ~CloudOwner() {
+        if (c) b200ppf_cloud_free(c);
+    }
+    b200ppf_cloud *release() {
+        b200ppf_cloud *r = c;
+        c = nullptr;
+        return r;
+    }
+};
+
 // ---- exclusive scan of 0/1 flags (three launches; same shape as K4's leader index) ----------------------------
 __global__ void __launch_bounds__(SCAN_BLOCK)
 flag_count_kernel(const uint32_t *__restrict__ flags, uint32_t n, uint32_t *__restrict__ block_sums) {
@@ -106,15 +137,14 @@ int flag_scan(b200ppf_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t *ran
     *total_host = 0;
     if (n == 0) return B200PPF_OK;
     const uint32_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    uint32_t *block_sums = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&block_sums, ((size_t)nb + 1) * sizeof(uint32_t), ctx->stream));
+    StreamBuf<uint32_t> block_sums(ctx);
+    PPF_CUDA(ctx, block_sums.alloc((size_t)nb + 1));
     uint32_t *d_total = block_sums + nb;
     PPF_LAUNCH(ctx, flag_count_kernel, nb, SCAN_BLOCK, 0, flags, n, block_sums);
     PPF_LAUNCH(ctx, flag_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, nb, d_total);
     PPF_LAUNCH(ctx, flag_rank_kernel, nb, SCAN_BLOCK, 0, flags, n, block_sums, rank);
     PPF_CUDA(ctx, cudaMemcpyAsync(total_host, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(block_sums, ctx->stream);
     return B200PPF_OK;
 }
 
@@ -163,8 +193,8 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4 *__restrict__ po
 int cloud_bbox_from_device(b200ppf_ctx *ctx, b200ppf_cloud *c) {
     for (int k = 0; k < 3; ++k) c->bbox_min[k] = c->bbox_max[k] = 0.0f;
     if (c->n == 0) return B200PPF_OK;
-    uint32_t *mm = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&mm, 6 * sizeof(uint32_t), ctx->stream));
+    StreamBuf<uint32_t> mm(ctx);
+    PPF_CUDA(ctx, mm.alloc(6));
     PPF_CUDA(ctx, cudaMemsetAsync(mm, 0xFF, 3 * sizeof(uint32_t), ctx->stream));
     PPF_CUDA(ctx, cudaMemsetAsync(mm + 3, 0x00, 3 * sizeof(uint32_t), ctx->stream));
     const unsigned grid = (unsigned)std::min<size_t>((c->n + 255) / 256, (size_t)ctx->sm_count * 8);
@@ -172,7 +202,6 @@ int cloud_bbox_from_device(b200ppf_ctx *ctx, b200ppf_cloud *c) {
     uint32_t h[6];
     PPF_CUDA(ctx, cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(mm, ctx->stream);
     for (int k = 0; k < 3; ++k) {
         c->bbox_min[k] = float_unorder(h[k]);
         c->bbox_max[k] = float_unorder(h[3 + k]);
@@ -665,31 +694,18 @@ compact_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, c
 // keep the flagged points, in order -> new cloud (and, optionally, their indices on the host)
 int compact_cloud(b200ppf_ctx *ctx, const b200ppf_cloud *in, const uint32_t *flags, b200ppf_cloud **out, uint32_t *kept_host) {
     const uint32_t n = (uint32_t)in->n;
-    uint32_t *rank = nullptr, *index = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&rank, std::max<size_t>(1, n) * sizeof(uint32_t), ctx->stream));
+    StreamBuf<uint32_t> rank(ctx), index(ctx);
+    PPF_CUDA(ctx, rank.alloc(n));
     uint32_t m = 0;
     int rc = flag_scan(ctx, flags, n, rank, &m);
-    b200ppf_cloud *c = nullptr;
-    if (rc == B200PPF_OK) rc = cloud_alloc(ctx, m, &c);
-    if (rc == B200PPF_OK && kept_host && m)
-        if (cudaMallocAsync(&index, (size_t)m * sizeof(uint32_t), ctx->stream) != cudaSuccess)
-            rc = fail_msg(ctx, B200PPF_ERR_NOMEM, "pre-processing: device allocation failed");
-    if (rc == B200PPF_OK && n) {
-        compact_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(in->pos, in->nrm, flags, rank, n, c->pos, c->nrm, index);
-        ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess) rc = fail_msg(ctx, B200PPF_ERR_CUDA, "pre-processing: compaction launch failed");
-    }
-    if (rc == B200PPF_OK && index)
-        if (cudaMemcpyAsync(kept_host, index, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-            rc = fail_msg(ctx, B200PPF_ERR_CUDA, "pre-processing: index download failed");
-    if (rc == B200PPF_OK) rc = cloud_bbox_from_device(ctx, c);  // synchronises the stream
-    cudaFreeAsync(rank, ctx->stream);
-    if (index) cudaFreeAsync(index, ctx->stream);
-    if (rc != B200PPF_OK) {
-        if (c) b200ppf_cloud_free(c);
-        return rc;
-    }
-    *out = c;
+    if (rc != B200PPF_OK) return rc;
+    CloudOwner c;
+    if ((rc = cloud_alloc(ctx, m, &c.c)) != B200PPF_OK) return rc;
+    if (kept_host && m) PPF_CUDA(ctx, index.alloc(m));
+    if (n) PPF_LAUNCH(ctx, compact_kernel, (n + 255) / 256, 256, 0, in->pos, in->nrm, flags, rank, n, c.c->pos, c.c->nrm, index);
+    if (index) PPF_CUDA(ctx, cudaMemcpyAsync(kept_host, index, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = cloud_bbox_from_device(ctx, c.c)) != B200PPF_OK) return rc;  // synchronises the stream
+    *out = c.release();
     return B200PPF_OK;
 }
 
@@ -778,35 +794,29 @@ int prep_upload_xyz(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride
             hi[k] = std::max(hi[k], p[k]);
         }
     }
-    b200ppf_cloud *c = nullptr;
-    int rc = cloud_alloc(ctx, m, &c);
+    CloudOwner c;
+    int rc = cloud_alloc(ctx, m, &c.c);
     if (rc != B200PPF_OK) return rc;
     for (int k = 0; k < 3; ++k) {
-        c->bbox_min[k] = m ? lo[k] : 0.0f;
-        c->bbox_max[k] = m ? hi[k] : 0.0f;
+        c.c->bbox_min[k] = m ? lo[k] : 0.0f;
+        c.c->bbox_max[k] = m ? hi[k] : 0.0f;
     }
-    cudaError_t e = cudaSuccess;
-    if (m) e = cudaMemcpyAsync(c->pos, sp, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && m) e = cudaMemsetAsync(c->nrm, 0, m * sizeof(float4), ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the staging buffer is reused by the next upload
-    if (e != cudaSuccess) {
-        b200ppf_cloud_free(c);
-        return fail_msg(ctx, B200PPF_ERR_CUDA, cudaGetErrorString(e));
-    }
-    *out = c;
+    if (m) PPF_CUDA(ctx, cudaMemcpyAsync(c.c->pos, sp, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    if (m) PPF_CUDA(ctx, cudaMemsetAsync(c.c->nrm, 0, m * sizeof(float4), ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next upload
+    *out = c.release();
     return B200PPF_OK;
 }
 
 int prep_download(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, float *host, size_t stride, size_t noff, size_t coff) {
     const size_t n = cloud->n;
     if (n == 0) return B200PPF_OK;
-    float *rows = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&rows, n * stride * sizeof(float), ctx->stream));
+    StreamBuf<float> rows(ctx);
+    PPF_CUDA(ctx, rows.alloc(n * stride));
     PPF_LAUNCH(ctx, pack_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, cloud->pos, cloud->nrm, (uint32_t)n, (uint32_t)stride,
                (uint32_t)noff, (uint32_t)coff, rows);
     PPF_CUDA(ctx, cudaMemcpyAsync(host, rows, n * stride * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(rows, ctx->stream);
     return B200PPF_OK;
 }
 
@@ -825,15 +835,14 @@ int prep_voxel_grid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *leaf
     for (int k = 0; k < 3; ++k) d[k] = (int64_t)((in->bbox_max[k] - in->bbox_min[k]) * vp.inv[k]) + 1;
     const bool overflow = d[0] * d[1] * d[2] > (int64_t)INT32_MAX;
     if (overflow) {
-        b200ppf_cloud *c = nullptr;
-        int rc = cloud_alloc(ctx, n, &c);
+        CloudOwner c;
+        int rc = cloud_alloc(ctx, n, &c.c);
         if (rc != B200PPF_OK) return rc;
-        copy_cloud_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(in->pos, in->nrm, n, c->pos, c->nrm);
-        ctx->launches++;
-        for (int k = 0; k < 3; ++k) c->bbox_min[k] = in->bbox_min[k], c->bbox_max[k] = in->bbox_max[k];
+        PPF_LAUNCH(ctx, copy_cloud_kernel, (n + 255) / 256, 256, 0, in->pos, in->nrm, n, c.c->pos, c.c->nrm);
+        for (int k = 0; k < 3; ++k) c.c->bbox_min[k] = in->bbox_min[k], c.c->bbox_max[k] = in->bbox_max[k];
         timer.stop();
         ctx->error = "voxel grid: leaf size is too small for the input dataset, integer indices would overflow; input returned unchanged";
-        *out = c;
+        *out = c.release();
         return B200PPF_OK;
     }
     int div_b[3];
@@ -847,43 +856,30 @@ int prep_voxel_grid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *leaf
     int bits = 1;
     while (bits < 32 && (1ull << bits) < n_cells) ++bits;
 
-    uint32_t *ids[2] = {nullptr, nullptr}, *ord[2] = {nullptr, nullptr}, *head = nullptr, *rank = nullptr, *starts = nullptr;
-    for (int b = 0; b < 2; ++b) {
-        PPF_CUDA(ctx, cudaMallocAsync(&ids[b], (size_t)n * sizeof(uint32_t), ctx->stream));
-        PPF_CUDA(ctx, cudaMallocAsync(&ord[b], (size_t)n * sizeof(uint32_t), ctx->stream));
-    }
-    PPF_CUDA(ctx, cudaMallocAsync(&head, (size_t)n * sizeof(uint32_t), ctx->stream));
-    PPF_CUDA(ctx, cudaMallocAsync(&rank, (size_t)n * sizeof(uint32_t), ctx->stream));
+    StreamBuf<uint32_t> ids0(ctx), ids1(ctx), ord0(ctx), ord1(ctx), head(ctx), rank(ctx), starts(ctx);
+    PPF_CUDA(ctx, ids0.alloc(n));
+    PPF_CUDA(ctx, ids1.alloc(n));
+    PPF_CUDA(ctx, ord0.alloc(n));
+    PPF_CUDA(ctx, ord1.alloc(n));
+    PPF_CUDA(ctx, head.alloc(n));
+    PPF_CUDA(ctx, rank.alloc(n));
     const unsigned gb = (n + 255) / 256;
-    PPF_LAUNCH(ctx, voxel_ids_kernel, gb, 256, 0, in->pos, n, vp, ids[0]);
+    PPF_LAUNCH(ctx, voxel_ids_kernel, gb, 256, 0, in->pos, n, vp, ids0);
     bool in_alt = false;
-    int rc = radix_sort_u32(ctx, ids[0], ids[1], ord[0], ord[1], nullptr, nullptr, n, bits, /*v0_iota=*/true, &in_alt);
+    int rc = radix_sort_u32(ctx, ids0, ids1, ord0, ord1, nullptr, nullptr, n, bits, /*v0_iota=*/true, &in_alt);
     if (rc != B200PPF_OK) return rc;
-    const int s = in_alt ? 1 : 0;
-    PPF_LAUNCH(ctx, voxel_heads_kernel, gb, 256, 0, ids[s], n, head);
+    const uint32_t *sorted_ids = in_alt ? ids1 : ids0, *order = in_alt ? ord1 : ord0;
+    PPF_LAUNCH(ctx, voxel_heads_kernel, gb, 256, 0, sorted_ids, n, head);
     uint32_t m = 0;
-    rc = flag_scan(ctx, head, n, rank, &m);
-    if (rc != B200PPF_OK) return rc;
-    PPF_CUDA(ctx, cudaMallocAsync(&starts, ((size_t)m + 1) * sizeof(uint32_t), ctx->stream));
-    b200ppf_cloud *c = nullptr;
-    rc = cloud_alloc(ctx, m, &c);
-    if (rc != B200PPF_OK) return rc;
+    if ((rc = flag_scan(ctx, head, n, rank, &m)) != B200PPF_OK) return rc;
+    PPF_CUDA(ctx, starts.alloc((size_t)m + 1));
+    CloudOwner c;
+    if ((rc = cloud_alloc(ctx, m, &c.c)) != B200PPF_OK) return rc;
     PPF_LAUNCH(ctx, voxel_starts_kernel, gb, 256, 0, head, rank, n, m, starts);
-    PPF_LAUNCH(ctx, voxel_centroid_kernel, (m + 127) / 128, 128, 0, in->pos, ord[s], starts, m, c->pos, c->nrm);
-    rc = cloud_bbox_from_device(ctx, c);
-    for (int b = 0; b < 2; ++b) {
-        cudaFreeAsync(ids[b], ctx->stream);
-        cudaFreeAsync(ord[b], ctx->stream);
-    }
-    cudaFreeAsync(head, ctx->stream);
-    cudaFreeAsync(rank, ctx->stream);
-    cudaFreeAsync(starts, ctx->stream);
+    PPF_LAUNCH(ctx, voxel_centroid_kernel, (m + 127) / 128, 128, 0, in->pos, order, starts, m, c.c->pos, c.c->nrm);
+    if ((rc = cloud_bbox_from_device(ctx, c.c)) != B200PPF_OK) return rc;
     timer.stop();
-    if (rc != B200PPF_OK) {
-        b200ppf_cloud_free(c);
-        return rc;
-    }
-    *out = c;
+    *out = c.release();
     return B200PPF_OK;
 }
 
@@ -892,19 +888,20 @@ int prep_knn(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, int k, uint32_t *idx_
     if (n == 0) return B200PPF_OK;
     KnnArgs a{};
     a.k = k;
-    PPF_CUDA(ctx, cudaMallocAsync(&a.out_idx, n * (size_t)k * sizeof(uint32_t), ctx->stream));
-    PPF_CUDA(ctx, cudaMallocAsync(&a.out_d2, n * (size_t)k * sizeof(float), ctx->stream));
+    StreamBuf<uint32_t> out_idx(ctx);
+    StreamBuf<float> out_d2(ctx);
+    PPF_CUDA(ctx, out_idx.alloc(n * (size_t)k));
+    PPF_CUDA(ctx, out_d2.alloc(n * (size_t)k));
+    a.out_idx = out_idx;
+    a.out_d2 = out_d2;
     EventTimer timer(ctx);
     int rc = knn_run<KNN_EXPORT>(ctx, cloud, a);
     timer.stop();
-    if (rc == B200PPF_OK && idx_host)
-        PPF_CUDA(ctx, cudaMemcpyAsync(idx_host, a.out_idx, n * (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (rc == B200PPF_OK && d2_host)
-        PPF_CUDA(ctx, cudaMemcpyAsync(d2_host, a.out_d2, n * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (rc != B200PPF_OK) return rc;
+    if (idx_host) PPF_CUDA(ctx, cudaMemcpyAsync(idx_host, out_idx, n * (size_t)k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d2_host) PPF_CUDA(ctx, cudaMemcpyAsync(d2_host, out_d2, n * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(a.out_idx, ctx->stream);
-    cudaFreeAsync(a.out_d2, ctx->stream);
-    return rc;
+    return B200PPF_OK;
 }
 
 int prep_sor(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stddev_mul, b200ppf_cloud **out, uint32_t *kept_host,
@@ -912,13 +909,13 @@ int prep_sor(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stdde
     const uint32_t n = (uint32_t)in->n;
     KnnArgs a{};
     a.k = mean_k + 1;
-    float *dist = nullptr;
-    double *partial = nullptr;
-    uint32_t *flags = nullptr;
+    StreamBuf<float> dist(ctx);
+    StreamBuf<double> partial(ctx);
+    StreamBuf<uint32_t> flags(ctx);
     const uint32_t nb = (n + 255) / 256;
-    PPF_CUDA(ctx, cudaMallocAsync(&dist, (size_t)n * sizeof(float), ctx->stream));
-    PPF_CUDA(ctx, cudaMallocAsync(&partial, (size_t)nb * 2 * sizeof(double), ctx->stream));
-    PPF_CUDA(ctx, cudaMallocAsync(&flags, (size_t)n * sizeof(uint32_t), ctx->stream));
+    PPF_CUDA(ctx, dist.alloc(n));
+    PPF_CUDA(ctx, partial.alloc((size_t)nb * 2));
+    PPF_CUDA(ctx, flags.alloc(n));
     a.out_dist = dist;
     EventTimer timer(ctx);
     int rc = knn_run<KNN_MEAN_DISTANCE>(ctx, in, a);
@@ -940,9 +937,6 @@ int prep_sor(b200ppf_ctx *ctx, const b200ppf_cloud *in, int mean_k, double stdde
     PPF_LAUNCH(ctx, sor_flag_kernel, nb, 256, 0, dist, n, thr, flags);
     rc = compact_cloud(ctx, in, flags, out, kept_host);
     timer.stop();
-    cudaFreeAsync(dist, ctx->stream);
-    cudaFreeAsync(partial, ctx->stream);
-    cudaFreeAsync(flags, ctx->stream);
     return rc;
 }
 
@@ -962,13 +956,12 @@ int prep_normals(b200ppf_ctx *ctx, b200ppf_cloud *cloud, int k, const float *vie
 
 int prep_curvature_edges(b200ppf_ctx *ctx, const b200ppf_cloud *in, float threshold, b200ppf_cloud **out) {
     const uint32_t n = (uint32_t)in->n;
-    uint32_t *flags = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&flags, std::max<size_t>(1, n) * sizeof(uint32_t), ctx->stream));
+    StreamBuf<uint32_t> flags(ctx);
+    PPF_CUDA(ctx, flags.alloc(n));
     EventTimer timer(ctx);
     if (n) PPF_LAUNCH(ctx, curvature_flag_kernel, (n + 255) / 256, 256, 0, in->nrm, n, threshold, flags);
     int rc = compact_cloud(ctx, in, flags, out, nullptr);
     timer.stop();
-    cudaFreeAsync(flags, ctx->stream);
     return rc;
 }
 
@@ -1029,13 +1022,12 @@ int prep_crop_pyramid(b200ppf_ctx *ctx, const b200ppf_cloud *in, const float *co
     if (std::fabs(dot(pl.n[4], c[3]) - pl.d[4]) > 1e-6 * nn * (std::fabs(c[3][0]) + std::fabs(c[3][1]) + std::fabs(c[3][2]) + 1.0))
         return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "crop: the four corners are not coplanar");
     const uint32_t n = (uint32_t)in->n;
-    uint32_t *flags = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&flags, std::max<size_t>(1, n) * sizeof(uint32_t), ctx->stream));
+    StreamBuf<uint32_t> flags(ctx);
+    PPF_CUDA(ctx, flags.alloc(n));
     EventTimer timer(ctx);
     if (n) PPF_LAUNCH(ctx, pyramid_flag_kernel, (n + 255) / 256, 256, 0, in->pos, n, pl, flags);
     int rc = compact_cloud(ctx, in, flags, out, kept_host);
     timer.stop();
-    cudaFreeAsync(flags, ctx->stream);
     return rc;
 }
 
