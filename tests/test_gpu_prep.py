@@ -285,3 +285,32 @@ def test_match_object_equals_the_stepwise_chain(ctx, oracle, scene_full, bottle)
     assert dt < 1e-3
     with pytest.raises(capi.B200PPFError):  # nothing inside the frustum
         ctx.match_object(ctx.upload_xyz(scene_full[:, :3] + np.float32(10)), cor, model, table)
+
+
+def test_full_size_1Mi_scene_equals_the_host_build_of_the_kernels(ctx, oracle):
+    """BASELINE config 4's frame (1 Mi points -> 684 438 after the 5 mm voxel grid): every stage against the checker
+    (voxel grid) or against the kernels' own query code run on the CPU (b200ppf_debug_knn_host) — which tests/test_prep.py
+    ties to the checker at small sizes and to a kd-tree at this size.  Index and float work bit-exact, normals within the
+    libm band."""
+    from yolo_ppf_pose_estimation_b200 import capi, synth
+    scene = np.ascontiguousarray(synth.synth_library_scene(1 << 20)[:, :3], np.float32)
+    v = ctx.voxel_grid(ctx.upload_xyz(scene), 0.005)
+    vh = v.download()[:, :3]
+    assert np.array_equal(vh, oracle.voxel_grid(scene, 0.005)[0]) and v.size == 684438
+    gi, gd = ctx.knn(v, 51)
+    hi, hd = capi.debug_knn_host(vh, 51, 0)
+    assert np.array_equal(gd, hd) and np.array_equal(gi, hi)
+    out, kept, gdist, thr = ctx.statistical_outlier_removal(v, 50, 1.0)
+    # the epilogue of the same search: sqrtf of the 50 other neighbours summed in double, in order
+    mean = (np.sqrt(hd[:, 1:]).astype(np.float64).cumsum(axis=1)[:, -1] / 50).astype(np.float32)
+    assert np.array_equal(gdist, mean)
+    m64 = mean.astype(np.float64)
+    assert abs(thr - (m64.mean() + m64.std(ddof=1))) <= 1e-9 * thr
+    assert np.array_equal(kept, np.flatnonzero(~(m64 > thr))) and out.size == 540433
+    ctx.normal_estimation(out, 30)
+    gn = out.download(curvature=True)
+    hn = capi.debug_knn_host(gn[:, :3], 30, 2)
+    dn, dc = np.abs(gn[:, 3:6] - hn[:, :3]).max(1), np.abs(gn[:, 6] - hn[:, 3])
+    print(f"1 Mi scene normals: max curvature diff {dc.max():.3g}, normal component diff p99.9 {np.quantile(dn, 0.999):.3g}, max {dn.max():.3g}")
+    assert dc.max() < 2e-5 and (dn > 2e-4).mean() < 1e-3  # nearly isotropic neighbourhoods have no stable normal
+    assert ctx.curvature_edges(out, 0.03).size in range(126399 - 20, 126399 + 21)

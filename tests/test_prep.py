@@ -252,3 +252,20 @@ def test_kernel_epilogues_equal_oracle(oracle, crop_5mm):
         assert np.array_equal(ref, got)
     vp = (0.3, -0.1, 2.0)
     assert np.array_equal(oracle.normals(crop_5mm, 12, viewpoint=vp), capi.debug_knn_host(crop_5mm, 12, 2, viewpoint=vp))
+
+
+def test_kernel_query_at_full_size_vs_kdtree(oracle):
+    """the kernels' query code (host build) on BASELINE config 4's frame after the 5 mm voxel grid (684 438 points, a
+    2.3-million-cell search grid) against an independent kd-tree: same distances, same neighbours up to ties"""
+    from yolo_ppf_pose_estimation_b200 import synth
+    scene = np.ascontiguousarray(synth.synth_library_scene(1 << 20)[:, :3], np.float32)
+    v = oracle.voxel_grid(scene, 0.005)[0]
+    assert v.shape[0] == 684438
+    gi, gd = _capi().debug_knn_host(v, 31, 0)
+    dist, nn = cKDTree(v.astype(np.float64)).query(v.astype(np.float64), k=31, workers=-1)
+    d2 = dist ** 2
+    assert (np.abs(gd - d2) / np.maximum(d2, 1e-12))[:, 1:].max() < 1e-5
+    assert (gi == nn).mean() > 0.9999
+    # the outlier-removal epilogue on the same cloud: the count the B200 run of tools/prep_bench.py reports
+    mean = _capi().debug_knn_host(v, 51, 1).astype(np.float64)
+    assert int((~(mean > mean.mean() + mean.std(ddof=1))).sum()) == 540433
