@@ -405,52 +405,40 @@ struct Grid {
     }
 };
 
-/* one reference point of the A.4 voting loop; acc must be zero on entry and is zero on exit */
-void vote_one_reference(const oracle_hashmap *hm, int feature_mode, int alpha_mode,
-                        const float *model, size_t n_m, const float *scene, size_t n_s,
-                        const Grid *grid, size_t s_r, uint32_t n_alpha, uint32_t *acc,
-                        oracle_hypothesis *hyp, uint64_t *stats) {
-    const float *pr = scene + 6 * s_r;
-    V3 p_r = ld3(pr), n_r = ld3(pr + 3);
-    Frame sg = ref_frame(p_r, n_r);
-    const float radius = hm->max_dist * 0.5f;
-    std::vector<std::pair<size_t, size_t>> bucket;
-    uint64_t examined = 0, in_radius = 0, nonempty = 0, votes = 0;
-
-    auto visit = [&](size_t s_i) {
-        if (s_i == s_r) return;
-        ++examined;
-        const float *pi = scene + 6 * s_i;
-        V3 p_i = ld3(pi), n_i = ld3(pi + 3);
-        /* radius predicate on f4 itself (SURVEY.md A.8 rule 7) */
-        V3 d{p_i.x - p_r.x, p_i.y - p_r.y, p_i.z - p_r.z};
-        float dist = norm3(d);
-        if (!(dist < radius)) return;
-        float f[4];
-        if (!pair_features(feature_mode, p_r, n_r, p_i, n_i, f)) return;
-        ++in_radius;
-        Key k = quantise(hm, f);
-        auto range = hm->map.equal_range(k);
-        bucket.clear();
-        for (auto it = range.first; it != range.second; ++it) bucket.push_back(it->second);
-        if (bucket.empty()) return;
-        ++nonempty;
-        float alpha_s = planar_alpha(sg, p_i);
-        for (const auto &ij : bucket) {
-            uint32_t bin = alpha_bin(alpha_mode, hm->angle_step, n_alpha,
-                                     hm->alpha_m[ij.first][ij.second], alpha_s);
-            if (bin == UINT32_MAX) continue;
-            acc[ij.first * n_alpha + bin]++;
-            ++votes;
-        }
-    };
-    if (grid) {
-        grid->for_each_candidate(pr, visit);
-    } else {
-        for (size_t s_i = 0; s_i < n_s; ++s_i) visit(s_i);
+/* one scene point paired with the reference point: the body of PCL's inner loop.  counters = examined, in radius,
+ * non-empty lookups, votes */
+inline void vote_one_pair(const oracle_hashmap *hm, int feature_mode, int alpha_mode, const float *scene, size_t s_r,
+                          size_t s_i, const V3 &p_r, const V3 &n_r, const Frame &sg, float radius, uint32_t n_alpha,
+                          uint32_t *acc, std::vector<std::pair<size_t, size_t>> &bucket, uint64_t *counters) {
+    if (s_i == s_r) return;
+    ++counters[0];
+    const float *pi = scene + 6 * s_i;
+    V3 p_i = ld3(pi), n_i = ld3(pi + 3);
+    /* radius predicate on f4 itself (SURVEY.md A.8 rule 7) */
+    V3 d{p_i.x - p_r.x, p_i.y - p_r.y, p_i.z - p_r.z};
+    float dist = norm3(d);
+    if (!(dist < radius)) return;
+    float f[4];
+    if (!pair_features(feature_mode, p_r, n_r, p_i, n_i, f)) return;
+    ++counters[1];
+    Key k = quantise(hm, f);
+    auto range = hm->map.equal_range(k);
+    bucket.clear();
+    for (auto it = range.first; it != range.second; ++it) bucket.push_back(it->second);
+    if (bucket.empty()) return;
+    ++counters[2];
+    float alpha_s = planar_alpha(sg, p_i);
+    for (const auto &ij : bucket) {
+        uint32_t bin = alpha_bin(alpha_mode, hm->angle_step, n_alpha, hm->alpha_m[ij.first][ij.second], alpha_s);
+        if (bin == UINT32_MAX) continue;
+        acc[ij.first * n_alpha + bin]++;
+        ++counters[3];
     }
+}
 
-    /* first maximum, i-major / bin-minor, strict '>' ; reset */
+/* first maximum, i-major / bin-minor, strict '>' ; reset ; pose of the peak */
+inline void peak_and_reset(const oracle_hashmap *hm, int alpha_mode, const float *model, size_t n_m, const Frame &sg,
+                           size_t s_r, uint32_t n_alpha, uint32_t *acc, oracle_hypothesis *hyp) {
     uint32_t max_v = 0;
     size_t max_i = 0, max_j = 0;
     for (size_t i = 0; i < n_m; ++i)
@@ -465,19 +453,84 @@ void vote_one_reference(const oracle_hashmap *hm, int feature_mode, int alpha_mo
         }
     const float *pm = model + 6 * max_i;
     Frame mg = ref_frame(ld3(pm), ld3(pm + 3));
-    compose_pose(sg, peak_theta(alpha_mode, hm->angle_step, static_cast<uint32_t>(max_j)), mg,
-                 hyp->pose);
+    compose_pose(sg, peak_theta(alpha_mode, hm->angle_step, static_cast<uint32_t>(max_j)), mg, hyp->pose);
     hyp->votes = max_v;
     hyp->model_index = static_cast<uint32_t>(max_i);
     hyp->alpha_bin = static_cast<uint32_t>(max_j);
     hyp->scene_index = static_cast<uint32_t>(s_r);
-    if (stats) {
-        stats[0] += examined;
-        stats[1] += in_radius;
-        stats[2] += nonempty;
-        stats[3] += votes;
-    }
 }
+
+/* one reference point of the A.4 voting loop; acc must be zero on entry and is zero on exit */
+void vote_one_reference(const oracle_hashmap *hm, int feature_mode, int alpha_mode,
+                        const float *model, size_t n_m, const float *scene, size_t n_s,
+                        const Grid *grid, size_t s_r, uint32_t n_alpha, uint32_t *acc,
+                        oracle_hypothesis *hyp, uint64_t *stats) {
+    const float *pr = scene + 6 * s_r;
+    V3 p_r = ld3(pr), n_r = ld3(pr + 3);
+    Frame sg = ref_frame(p_r, n_r);
+    const float radius = hm->max_dist * 0.5f;
+    std::vector<std::pair<size_t, size_t>> bucket;
+    uint64_t counters[4] = {0, 0, 0, 0};
+    auto visit = [&](size_t s_i) {
+        vote_one_pair(hm, feature_mode, alpha_mode, scene, s_r, s_i, p_r, n_r, sg, radius, n_alpha, acc, bucket, counters);
+    };
+    if (grid) {
+        grid->for_each_candidate(pr, visit);
+    } else {
+        for (size_t s_i = 0; s_i < n_s; ++s_i) visit(s_i);
+    }
+    peak_and_reset(hm, alpha_mode, model, n_m, sg, s_r, n_alpha, acc, hyp);
+    if (stats)
+        for (int k = 0; k < 4; ++k) stats[k] += counters[k];
+}
+
+#ifdef _OPENMP
+/* the same reference point with its scene pairs spread over the threads (thread-private accumulators summed before
+ * the peak scan): what keeps every core busy when a pass holds fewer reference points than threads, or a few very
+ * expensive ones.  Counters are integers and accumulator adds commute: the hypothesis is the serial one. */
+void vote_one_reference_parallel(const oracle_hashmap *hm, int feature_mode, int alpha_mode, const float *model, size_t n_m,
+                                 const float *scene, size_t n_s, const Grid *grid, size_t s_r, uint32_t n_alpha,
+                                 std::vector<std::vector<uint32_t>> &accs, oracle_hypothesis *hyp, uint64_t *stats) {
+    const float *pr = scene + 6 * s_r;
+    V3 p_r = ld3(pr), n_r = ld3(pr + 3);
+    Frame sg = ref_frame(p_r, n_r);
+    const float radius = hm->max_dist * 0.5f;
+    std::vector<size_t> cand;
+    if (grid) {
+        grid->for_each_candidate(pr, [&](size_t s_i) { cand.push_back(s_i); });
+    } else {
+        cand.resize(n_s);
+        for (size_t s_i = 0; s_i < n_s; ++s_i) cand[s_i] = s_i;
+    }
+    const int n_threads = static_cast<int>(accs.size());
+    uint64_t tot[4] = {0, 0, 0, 0};
+#pragma omp parallel num_threads(n_threads)
+    {
+        uint32_t *acc = accs[omp_get_thread_num()].data();
+        std::vector<std::pair<size_t, size_t>> bucket;
+        uint64_t counters[4] = {0, 0, 0, 0};
+#pragma omp for schedule(dynamic, 16)
+        for (long long c = 0; c < static_cast<long long>(cand.size()); ++c)
+            vote_one_pair(hm, feature_mode, alpha_mode, scene, s_r, cand[c], p_r, n_r, sg, radius, n_alpha, acc, bucket, counters);
+#pragma omp critical
+        for (int k = 0; k < 4; ++k) tot[k] += counters[k];
+#pragma omp barrier
+        /* sum the private accumulators into the first one, rows split over the threads; clear the others */
+#pragma omp for schedule(static)
+        for (long long i = 0; i < static_cast<long long>(n_m); ++i)
+            for (int t = 1; t < n_threads; ++t) {
+                uint32_t *src = accs[t].data() + static_cast<size_t>(i) * n_alpha, *dst = accs[0].data() + static_cast<size_t>(i) * n_alpha;
+                for (uint32_t j = 0; j < n_alpha; ++j) {
+                    dst[j] += src[j];
+                    src[j] = 0;
+                }
+            }
+    }
+    peak_and_reset(hm, alpha_mode, model, n_m, sg, s_r, n_alpha, accs[0].data(), hyp);
+    if (stats)
+        for (int k = 0; k < 4; ++k) stats[k] += tot[k];
+}
+#endif
 
 }  // namespace
 
@@ -693,6 +746,18 @@ int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, cons
     if (use_grid) grid.build(scene, n_s, radius);
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
 #ifdef _OPENMP
+    if (n_threads > 1 && ref_count < 4 * static_cast<size_t>(n_threads)) {
+        /* few reference points: threads share each one's scene pairs (a 10 000-point model makes single reference
+         * points cost minutes, so a pass over a handful of them would leave most cores idle otherwise) */
+        std::vector<std::vector<uint32_t>> accs(static_cast<size_t>(n_threads), std::vector<uint32_t>(n_m * n_alpha, 0u));
+        for (size_t r = 0; r < ref_count; ++r) {
+            size_t s_r = ref_first + r * ref_step;
+            if (s_r >= n_s) continue;
+            vote_one_reference_parallel(hm, feature_mode, alpha_mode, model, n_m, scene, n_s, use_grid ? &grid : nullptr, s_r,
+                                        n_alpha, accs, &hyps[r], stats);
+        }
+        return 0;
+    }
     if (n_threads > 1) {
         uint64_t tot[4] = {0, 0, 0, 0};
 #pragma omp parallel num_threads(n_threads)

@@ -201,6 +201,19 @@ def test_threads_and_grid_do_not_change_results(oracle, oracle_bottle, bottle, s
         assert h["votes"] == acc.max()
 
 
+def test_few_reference_points_share_their_pairs_across_threads(oracle, oracle_bottle, bottle, scene_full):
+    """with fewer reference points than 4 x threads the CPU arm spreads each point's scene pairs over the threads
+    (bench.py --impl reference on the 10 000-point model): hypotheses and counters are the serial ones"""
+    _, hm = oracle_bottle
+    for count, step in ((1, 1), (5, 7001), (31, 1300)):
+        h1, s1 = hm.vote(bottle, scene_full, 11, step, count, n_threads=1)
+        h8, s8 = hm.vote(bottle, scene_full, 11, step, count, n_threads=8)
+        assert h1.tobytes() == h8.tobytes() and s1 == s8
+    h1, s1 = hm.vote(bottle, scene_full, 0, 100, 400, n_threads=1)  # many points: one thread per point
+    h8, s8 = hm.vote(bottle, scene_full, 0, 100, 400, n_threads=8)
+    assert h1.tobytes() == h8.tobytes() and s1 == s8
+
+
 def test_self_match_recovers_pose(oracle, oracle_bottle, bottle):
     from scipy.spatial.transform import Rotation as Rot
     _, hm = oracle_bottle
