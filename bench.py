@@ -202,18 +202,19 @@ def run_reference(args, wl):
     threads = ob.max_threads()
     # the whole --steps K --warmup W run should end within a few minutes: ~150 s of voting in total
     first, step, count = pick_cpu_sample(hm, wl, threads, 150.0 / (args.warmup + args.steps) / len(library), args.cpu_sample)
-    times, pairs = [], 0
+    times, pairs, votes = [], 0, 0
     for k in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        step_pairs = 0
+        step_pairs = step_votes = 0
         for m, (_, hm_k) in zip(library, tables):
             hyps, st = hm_k.vote(m, wl.scene, first, step, count, n_threads=threads)
             ob.cluster(hyps, wl.pos_thr, wl.rot_thr)
             step_pairs += st["pairs_in_radius"]
+            step_votes += st["votes"]
         dt = time.perf_counter() - t0
         if k >= args.warmup:
             times.append(dt)
-            pairs = step_pairs
+            pairs, votes = step_pairs, step_votes
     ms = 1e3 * float(np.mean(times))
     value = pairs / (ms * 1e-3)
     sample = (f"{count} of {wl.n_ref} reference points per step (every {step // wl.ref_rate}-th), full scene, vote + cluster"
@@ -225,6 +226,7 @@ def run_reference(args, wl):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_pose_extrapolated": ms * wl.n_ref / count,
+        "votes_per_sec": votes / (ms * 1e-3),  # the sample-independent rate (pairs differ in cost by orders of magnitude)
     }
     print(json.dumps(line), flush=True)
 

@@ -746,9 +746,10 @@ int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, cons
     if (use_grid) grid.build(scene, n_s, radius);
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
 #ifdef _OPENMP
-    if (n_threads > 1 && ref_count < 4 * static_cast<size_t>(n_threads)) {
-        /* few reference points: threads share each one's scene pairs (a 10 000-point model makes single reference
-         * points cost minutes, so a pass over a handful of them would leave most cores idle otherwise) */
+    if (n_threads > 1 && (ref_count < 4 * static_cast<size_t>(n_threads) || n_m >= 4096)) {
+        /* few reference points, or a large model: threads share each point's scene pairs (a 10 000-point model makes
+         * single reference points cost from a second to minutes, so one thread per point would leave most cores
+         * idle behind the expensive ones) */
         std::vector<std::vector<uint32_t>> accs(static_cast<size_t>(n_threads), std::vector<uint32_t>(n_m * n_alpha, 0u));
         for (size_t r = 0; r < ref_count; ++r) {
             size_t s_r = ref_first + r * ref_step;
