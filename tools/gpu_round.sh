@@ -20,6 +20,14 @@ bash tools/gpu_prof.sh $TAG c3s
 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:ppf_vote_kernel -s 3 -c 1 --csv \
     --log-file $O/dram_c3_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_dram_c3_$TAG.log 2>&1
 python tools/icp_bench.py > $O/icp_bench_$TAG.json 2> $O/icp_bench_$TAG.err
+# pre-processing row: stage and per-object timings vs the CPU chain, launch list, full captures of the neighbour kernel
+timeout 300 python tools/prep_bench.py > $O/prep_bench_$TAG.jsonl 2> $O/prep_bench_$TAG.err; tail -c 400 $O/prep_bench_$TAG.err
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/prep_launches_$TAG.csv \
+    python tools/prep_bench.py --no-cpu --repeat 1 --only big --no-frames > $O/ncu_prep_launches_$TAG.log 2>&1
+for which in sor:2 normals:3; do
+    timeout 200 ncu --set full --clock-control none --import-source on -k regex:knn_ -s ${which##*:} -c 1 -f -o $O/prof_knn_${which%%:*}_$TAG \
+        python tools/prep_bench.py --no-cpu --repeat 1 --only big --no-frames > $O/ncu_full_knn_${which%%:*}_$TAG.log 2>&1
+done
 for f in c3 c3_ref c2 c2_ref c1 c2_5mm c4; do python - <<PY
 import json
 try:
