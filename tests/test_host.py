@@ -219,6 +219,21 @@ def test_cpp_shim_compiles_and_links(tmp_path):
             assert "no CPU fallback" in r.stderr
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/b200ppf.h is the drop-in boundary: plain C types only — the INTEGRATION.md frame example compiles as
+    strict C99 and the header as C++11"""
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c",
+                        os.path.join(ROOT, "tests", "cpp", "c_abi_frame_example.c"), "-o", str(tmp_path / "a.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "hdr.cpp"
+    src.write_text('#include "b200ppf.h"\nint (*probe)(void) = &b200ppf_version;\n')
+    r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c", str(src), "-o",
+                        str(tmp_path / "b.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
                         "--steps", "1", "--warmup", "0", "--cpu-sample", "8"], capture_output=True, text=True, timeout=600)
