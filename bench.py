@@ -185,7 +185,7 @@ def pick_cpu_sample(hm, wl, threads, budget_s, requested):
         dt = max(time.perf_counter() - t0, 1e-4)
         if dt >= 0.25 * budget_s or n >= cap:
             break
-        n = min(cap, max(2 * n, int(0.6 * budget_s / dt * n)))
+        n = min(cap, max(2 * n, int(0.4 * budget_s / dt * n)))  # headroom: a larger sample meets costlier points
     if dt > budget_s:  # even the smallest sample overshoots: shrink proportionally
         n = max(1, int(n * budget_s / dt))
     return cpu_sample_refs(wl, n)
@@ -200,8 +200,9 @@ def run_reference(args, wl):
     tables = [oracle_table(wl, m) for m in library]
     ob, hm = tables[0]
     threads = ob.max_threads()
-    # the whole --steps K --warmup W run should end within a few minutes: ~150 s of voting in total
-    first, step, count = pick_cpu_sample(hm, wl, threads, 150.0 / (args.warmup + args.steps) / len(library), args.cpu_sample)
+    # the whole --steps K --warmup W run should end within a few minutes: ~100 s of voting in total (the CPU build of
+    # the 10 000-point model's table adds two to three minutes before that)
+    first, step, count = pick_cpu_sample(hm, wl, threads, 100.0 / (args.warmup + args.steps) / len(library), args.cpu_sample)
     times, pairs, votes = [], 0, 0
     for k in range(args.warmup + args.steps):
         t0 = time.perf_counter()
