@@ -199,15 +199,17 @@ def test_two_rank_gloo_sharding(tmp_path):
 
 
 def test_cpp_shim_compiles_and_links(tmp_path):
-    """The PCL-shaped header shim is valid C++14 and links against libb200ppf.so (PPF operators and the
-    pre-processing operators)."""
+    """The PCL-shaped header shim (PPF operators, pre-processing operators) and the OpenCV-shaped ICP shim are valid
+    C++14 and link against libb200ppf.so."""
     from yolo_ppf_pose_estimation_b200 import build
     lib = build.build()
     import torch
-    for name, arg in (("pcl_shim_example", os.path.join(ROOT, "tests", "golden")), ("pcl_prep_example", "/nonexistent.f32")):
+    for name, arg in (("pcl_shim_example", os.path.join(ROOT, "tests", "golden")), ("pcl_prep_example", "/nonexistent.f32"),
+                      ("cv_icp_shim_example", "/nonexistent")):
         exe = tmp_path / name
         cmd = ["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
-               "-I", os.path.join(ROOT, "include", "pcl_compat"), "-I", os.path.join(ROOT, "include"),
+               "-I", os.path.join(ROOT, "include", "pcl_compat"), "-I", os.path.join(ROOT, "include", "opencv_compat"),
+               "-I", os.path.join(ROOT, "include"),
                os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", str(exe),
                "-L", os.path.dirname(lib), "-lb200ppf", f"-Wl,-rpath,{os.path.dirname(lib)}"]
         r = subprocess.run(cmd, capture_output=True, text=True)
