@@ -183,7 +183,9 @@ def pick_cpu_sample(hm, wl, threads, budget_s, requested):
         t0 = time.perf_counter()
         hm.vote(wl.model, wl.scene, f0, st0, cnt, n_threads=threads)
         dt = max(time.perf_counter() - t0, 1e-4)
-        if dt >= 0.25 * budget_s or n >= cap:
+        # one thread: stop growing early — a single reference point on the object of the 10 000-point model costs
+        # minutes there, and a larger spread sample is likelier to meet one
+        if dt >= (0.25 if threads > 1 else 0.1) * budget_s or n >= cap:
             break
         n = min(cap, max(2 * n, int(0.4 * budget_s / dt * n)))  # headroom: a larger sample meets costlier points
     if dt > budget_s:  # even the smallest sample overshoots: shrink proportionally
