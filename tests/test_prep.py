@@ -269,3 +269,40 @@ def test_kernel_query_at_full_size_vs_kdtree(oracle):
     # the outlier-removal epilogue on the same cloud: the count the B200 run of tools/prep_bench.py reports
     mean = _capi().debug_knn_host(v, 51, 1).astype(np.float64)
     assert int((~(mean > mean.mean() + mean.std(ddof=1))).sum()) == 540433
+
+
+def test_kernel_query_fuzz_against_the_checker(oracle):
+    """seeded sweep over cloud shapes that stress the traversal (needles, lattices full of ties and duplicates, a cloud
+    whose extent is a few float ulps, two density scales, planes, negative coordinates) x any k <= 128 x cell edges from
+    far too small to one cell for everything: neighbour lists, mean distances and normals of the kernels' host build
+    equal the checker's bit for bit"""
+    capi = _capi()
+    rng = np.random.default_rng(20261018)
+    for case in range(48):
+        n = int(rng.integers(1, 1500))
+        kind = case % 7
+        if kind == 0:
+            x = rng.normal(size=(n, 3))
+        elif kind == 1:
+            x = rng.random((n, 3)) * [1, 1e-3, 1e-6]
+        elif kind == 2:
+            x = np.round(rng.random((n, 3)) * 8) / 8
+        elif kind == 3:
+            x = rng.random((n, 3)) * 1e-4 + 1000.0
+        elif kind == 4:
+            x = np.concatenate([rng.normal(size=(n // 2, 3)) * 1e-3, rng.normal(size=(n - n // 2, 3)) * 10])
+        elif kind == 5:
+            x = rng.random((n, 3)) * [1, 1, 0]
+        else:
+            x = -rng.random((n, 3)) * 5
+        x = x.astype(np.float32)
+        k = int(rng.integers(1, min(n, 128) + 1))
+        cell = float(rng.choice([0.0, 1e-3, 0.05, 0.7, 30.0])) * float(rng.choice([1.0, np.ptp(x) + 1e-9]))
+        oi, od = oracle.knn(x, k)
+        gi, gd = capi.debug_knn_host(x, k, 0, cell)
+        assert np.array_equal(oi, gi) and np.array_equal(od, gd), (case, n, k, cell)
+        if k >= 2 and n > k:
+            mean = (np.sqrt(od[:, 1:]).astype(np.float64).cumsum(axis=1)[:, -1] / (k - 1)).astype(np.float32)
+            assert np.array_equal(capi.debug_knn_host(x, k, 1, cell), mean), (case, n, k, cell)
+        if k >= 3:
+            assert np.array_equal(oracle.normals(x, k), capi.debug_knn_host(x, k, 2, cell), equal_nan=True), (case, n, k, cell)
