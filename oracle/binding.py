@@ -27,7 +27,7 @@ assert HYP_DTYPE.itemsize == 64
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (g++, no external dependencies)."""
-    src = [os.path.join(_HERE, f) for f in ("ppf_oracle.cpp", "icp_oracle.cpp", "prep_oracle.cpp", "ppf_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ppf_oracle.cpp", "icp_oracle.cpp", "prep_oracle.cpp", "cvppf_oracle.cpp", "ppf_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -107,6 +107,22 @@ def _declare(L):
                                          C.c_double, C.c_double, vp]
     L.oracle_crop_pyramid.argtypes = [vp, sz, sz, vp, vp]
     L.oracle_crop_pyramid.restype = sz
+    L.oracle_cv_create.argtypes = [C.c_double, C.c_double, C.c_double]
+    L.oracle_cv_create.restype = vp
+    L.oracle_cv_destroy.argtypes = [vp]
+    L.oracle_cv_set_search_params.argtypes = [vp, C.c_double, C.c_double]
+    L.oracle_cv_sample.argtypes = [vp, sz, C.c_float, vp]
+    L.oracle_cv_sample.restype = sz
+    L.oracle_cv_murmur.argtypes = [C.c_char_p, C.c_int, C.c_uint32]
+    L.oracle_cv_murmur.restype = C.c_uint32
+    L.oracle_cv_pair.argtypes = [vp, vp, C.c_double, C.c_double, vp]
+    L.oracle_cv_pair.restype = C.c_uint32
+    L.oracle_cv_train.argtypes = [vp, vp, sz]
+    L.oracle_cv_train.restype = sz
+    L.oracle_cv_model_points.argtypes = [vp, vp]
+    L.oracle_cv_model_points.restype = sz
+    L.oracle_cv_match.argtypes = [vp, vp, sz, C.c_double, C.c_double, vp, vp, sz, vp, C.POINTER(sz), C.c_int]
+    L.oracle_cv_match.restype = sz
 
 
 def _f32(a):
@@ -396,3 +412,63 @@ def crop_pyramid(xyz, corners):
     keep = np.zeros(xyz.shape[0], np.uint8)
     lib().oracle_crop_pyramid(_p(xyz), xyz.shape[0], xyz.shape[1], _p(corners), _p(keep))
     return keep.astype(bool)
+
+
+# ---- the engine the reference actually calls: cv::ppf_match_3d::PPF3DDetector (cvppf_oracle.cpp) --------------------
+def cv_sample(pc, sample_step):
+    """samplePCByQuantization over the cloud's own bounding box: (N, 6) -> (M, 6)"""
+    pc = _f32(pc)
+    out = np.zeros_like(pc)
+    m = lib().oracle_cv_sample(_p(pc), pc.shape[0], np.float32(sample_step), _p(out))
+    return out[:m].copy()
+
+
+def cv_murmur(data: bytes, seed: int) -> int:
+    """MurmurHash3_x86_32"""
+    return int(lib().oracle_cv_murmur(data, len(data), seed))
+
+
+def cv_pair(p1n1, p2n2, angle_step, distance_step):
+    """(computePPFFeatures (4,), hashPPF) of one pair"""
+    a, b = _f32(p1n1), _f32(p2n2)
+    f = np.zeros(4, np.float64)
+    h = lib().oracle_cv_pair(_p(a), _p(b), float(angle_step), float(distance_step), _p(f))
+    return f, int(h)
+
+
+class CvDetector:
+    """PPF3DDetector(relativeSamplingStep, relativeDistanceStep = 0.05, numAngles = 30)"""
+
+    def __init__(self, relative_sampling_step, relative_distance_step=0.05, num_angles=30):
+        self._h = lib().oracle_cv_create(float(relative_sampling_step), float(relative_distance_step), float(num_angles))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_cv_destroy(self._h)
+            self._h = None
+
+    def set_search_params(self, position_threshold=-1.0, rotation_threshold=-1.0):
+        lib().oracle_cv_set_search_params(self._h, float(position_threshold), float(rotation_threshold))
+
+    def train_model(self, model):
+        model = _f32(model)
+        self.n_model = int(lib().oracle_cv_train(self._h, _p(model), model.shape[0]))
+        return self
+
+    def model_points(self):
+        out = np.zeros((self.n_model, 6), np.float32)
+        lib().oracle_cv_model_points(self._h, _p(out))
+        return out
+
+    def match(self, scene, relative_scene_sample_step=1.0 / 5.0, relative_scene_distance=0.03, max_poses=16, n_threads=None):
+        """-> (poses (P, 4, 4) float64, cluster votes (P,), raw per-reference (votes, model index, alpha index), #clusters)"""
+        scene = _f32(scene)
+        poses = np.zeros((max_poses, 16), np.float64)
+        votes = np.zeros(max_poses, np.uint32)
+        raw = np.zeros((scene.shape[0], 3), np.uint32)
+        n_refs = C.c_size_t(0)
+        ncl = lib().oracle_cv_match(self._h, _p(scene), scene.shape[0], float(relative_scene_sample_step),
+                                    float(relative_scene_distance), _p(poses), _p(votes), max_poses, _p(raw), C.byref(n_refs),
+                                    n_threads or max_threads())
+        k = min(int(ncl), max_poses)
+        return poses[:k].reshape(-1, 4, 4), votes[:k], raw[:n_refs.value].copy(), int(ncl)

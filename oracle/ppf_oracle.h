@@ -155,6 +155,23 @@ void oracle_frustum_corners(const float *depth, int rows, int cols, int bx, int 
                             double ppx, double ppy, float *corners12);
 size_t oracle_crop_pyramid(const float *xyz, size_t n, size_t stride, const float *corners12, uint8_t *keep);
 
+/* The engine the reference actually calls — cv::ppf_match_3d::PPF3DDetector (opencv_contrib surface_matching),
+ * reference include/CloudProcessing.h:205-236 (construction, trainModel), :442 (match) — restated in cvppf_oracle.cpp
+ * as the checker of a row that is not built on the device yet.  Parity unpinned; see the
+ * header of that file for what is known to be soft.  Clouds are N x 6 float32 [x y z nx ny nz]. */
+typedef struct oracle_cv_detector oracle_cv_detector;
+oracle_cv_detector *oracle_cv_create(double relative_sampling_step, double relative_distance_step, double num_angles);
+void oracle_cv_destroy(oracle_cv_detector *d);
+void oracle_cv_set_search_params(oracle_cv_detector *d, double position_threshold, double rotation_threshold);
+size_t oracle_cv_sample(const float *pc, size_t n, float sample_step, float *out);
+uint32_t oracle_cv_murmur(const void *key, int len, uint32_t seed);
+uint32_t oracle_cv_pair(const float *p1n1, const float *p2n2, double angle_step, double distance_step, double *f);
+size_t oracle_cv_train(oracle_cv_detector *d, const float *model, size_t n);
+size_t oracle_cv_model_points(const oracle_cv_detector *d, float *out6);
+size_t oracle_cv_match(const oracle_cv_detector *d, const float *scene, size_t n, double relative_scene_sample_step,
+                       double relative_scene_distance, double *out_poses, uint32_t *out_votes, size_t cap, uint32_t *raw3,
+                       size_t *n_refs, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif
