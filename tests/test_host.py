@@ -221,6 +221,41 @@ def test_cpp_shim_compiles_and_links(tmp_path):
             assert "no CPU fallback" in r.stderr
 
 
+def test_opencv_icp_shim_marshalling_against_the_cpu_checker(tmp_path, oracle):
+    """include/opencv_compat's ICP / Pose3D: the reference's call (include/CloudProcessing.h:518-523) built against a
+    test double of the five C-ABI entry points it uses, backed by the CPU restatement of opencv_contrib's ICP — what the
+    example writes equals oracle.icp_refine on the same clouds and poses (the GPU run of the same example is
+    tests/test_gpu_zz_opencv_icp_shim.py)"""
+    from yolo_ppf_pose_estimation_b200 import synth
+    odir = os.path.join(ROOT, "oracle", "_build")
+    model = synth.synth_model(3000, 1).astype(np.float32)
+    G = synth.gt_pose(2)
+    scene = np.concatenate([model[:, :3] @ G[:3, :3].T + G[:3, 3], model[:, 3:] @ G[:3, :3].T], axis=1).astype(np.float32)[::2]
+    starts = []
+    for k in range(3):
+        D = np.eye(4)
+        D[:3, 3] = (0.004 * (k + 1), -0.003, 0.002 * k)
+        starts.append(D @ G)
+    starts = np.ascontiguousarray(starts, np.float64)
+    model.tofile(tmp_path / "model.f32")
+    scene.tofile(tmp_path / "scene.f32")
+    starts.tofile(tmp_path / "poses.f64")
+    exe = tmp_path / "cv_icp_shim_mock"
+    cmd = ["/usr/bin/g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include", "opencv_compat"), "-I",
+           os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "cv_icp_shim_example.cpp"),
+           os.path.join(ROOT, "tests", "cpp", "mock_b200ppf_icp.cpp"), "-o", str(exe), "-L", odir, "-lppf_oracle",
+           f"-Wl,-rpath,{odir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(tmp_path / "refined.f64", np.float64).reshape(-1, 17)
+    P, res, _ = oracle.icp_refine(model, scene, starts)
+    assert out.shape[0] == 3
+    assert np.array_equal(out[:, :16].reshape(-1, 4, 4), P) and np.array_equal(out[:, 16], res)
+    assert np.linalg.norm(P[0][:3, 3] - G[:3, 3]) < 1e-3 and "Pose to Model Index" in r.stdout
+
+
 def test_header_is_plain_c(tmp_path):
     """include/b200ppf.h is the drop-in boundary: plain C types only — the INTEGRATION.md frame example compiles as
     strict C99 and the header as C++11"""
