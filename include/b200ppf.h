@@ -52,6 +52,19 @@ extern "C" {
 /* alpha binning of the voting loop: A = PCL >= 1.12, B = PCL 1.8-1.11 legacy */
 #define B200PPF_ALPHA_MODE_A 0
 #define B200PPF_ALPHA_MODE_B 1
+/* How many alpha columns the accumulator of the voting loop has, and what becomes of a vote whose bin lies past
+ * the last one.  PCL sizes the rows with 2*pi / angle_step; for its float 12 degrees that quotient is
+ * 30 - 1.3e-6, so the choice of rounding decides whether the 30th bin exists:
+ *   CEIL        ceil(2*pi/step) columns — current PCL; every bin the binning formula can produce has a column
+ *               (default; in the one-in-a-billion case of a quotient that is an exact integer the bin equal to the
+ *               column count is clamped rather than written out of bounds);
+ *   FLOOR_DROP  floor(2*pi/step) columns — PCL 1.8 .. 1.11; a vote for bin 29 increments the word behind the
+ *               row's std::vector storage (inside glibc's 120-byte chunk for a 116-byte row) and is never read: lost;
+ *   FLOOR_CLAMP floor columns, the vote joins the last column — what round 1 of this library did; kept as a switch.
+ * The rule is read when a table is built and travels with the table (and its file). */
+#define B200PPF_NALPHA_CEIL 0
+#define B200PPF_NALPHA_FLOOR_DROP 1
+#define B200PPF_NALPHA_FLOOR_CLAMP 2
 
 typedef struct b200ppf_ctx b200ppf_ctx;
 typedef struct b200ppf_cloud b200ppf_cloud;       /* device point+normal cloud (float4 SoA) */
@@ -80,13 +93,15 @@ typedef struct b200ppf_table_info {
     uint64_t key_space;   /* dense packed-key range per slice */
     uint32_t n_slices;    /* model-row slices (accumulator tiles), 1 for small models */
     uint32_t slice_rows;  /* model rows per slice */
-    uint32_t n_alpha;     /* accumulator columns = floor(2*pi/angle_step) */
+    uint32_t n_alpha;     /* accumulator columns: ceil or floor of 2*pi/angle_step (nalpha_rule) */
     uint32_t key_bits;    /* bits sorted */
     int32_t lo[4];        /* lower bound of each quantised component */
     int32_t size[4];      /* extent of each quantised component */
     float angle_step, dist_step;
     float max_dist;       /* getModelDiameter() */
     uint32_t phase_cells; /* alpha_m phase cells per bucket (1: buckets are not subdivided) */
+    uint32_t nalpha_rule; /* B200PPF_NALPHA_* the table was built under */
+    uint32_t reserved;
 } b200ppf_table_info;
 
 /* per-stage device times of the last call on this context, milliseconds (CUDA events) */
@@ -102,6 +117,7 @@ const char *b200ppf_last_error(const b200ppf_ctx *ctx); /* ctx may be NULL: glob
 int b200ppf_version(void);
 int b200ppf_set_feature_mode(b200ppf_ctx *ctx, int feature_mode);
 int b200ppf_set_alpha_mode(b200ppf_ctx *ctx, int alpha_mode);
+int b200ppf_set_nalpha_rule(b200ppf_ctx *ctx, int nalpha_rule); /* B200PPF_NALPHA_*; default CEIL */
 int b200ppf_get_device(const b200ppf_ctx *ctx);
 void *b200ppf_get_stream(const b200ppf_ctx *ctx); /* cudaStream_t */
 int b200ppf_synchronize(b200ppf_ctx *ctx);
@@ -155,7 +171,10 @@ void b200ppf_table_free(b200ppf_table *t);
  * the device table — parameters, bucket and phase-cell offsets, entry arrays — to one little-endian
  * binary file with a magic, a format version and a 64-bit checksum; load rebuilds it on ctx's device
  * without re-running K1/K2 and fails with B200PPF_ERR_IO on a missing, truncated, corrupt or
- * other-version file and with B200PPF_ERR_STATE when the file's feature / alpha mode differs from ctx's. */
+ * other-version file and with B200PPF_ERR_STATE when the file's feature / alpha mode differs from ctx's.
+ * Beyond the checksum, load re-derives everything the voting kernel takes on trust (monotone offsets that stay
+ * inside their buckets, key space = product of the key ranges, binning parameters as a function of the angle
+ * step, every entry's pair index, slice, fixed-point alpha_m and hot word) and refuses a file that disagrees. */
 int b200ppf_table_save(b200ppf_ctx *ctx, const b200ppf_table *t, const char *path);
 int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out);
 
@@ -200,11 +219,14 @@ int b200ppf_vote_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t,
 /* parity hook for the voting loop's alpha binning: evaluates the hot-loop form (fast) and the
  * literal PCL form (exact) for n (alpha_m, alpha_s) pairs — on the device when ctx is given, with
  * the host build of the same inline functions when ctx is NULL. */
-int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, int nalpha_rule, const float *alpha_m,
                              const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact);
 
 /* roofline denominator the HBM/tensor peaks do not cover: measured rate of shared-memory reductions
- * (one per vote).  pattern 0 = conflict-free, 1 = random words (the voting kernel's), 2 = one word. */
+ * (one per vote).  pattern 0 = conflict-free, 1 = random words (address from an LCG), 2 = one word,
+ * 3 / 4 = exactly 2 / 4 lanes per bank; 5 / 6 / 7 = the voting loop's own shape (one coalesced 4-byte gather
+ * from an L2-resident table per reduction, eight in flight per lane) with conflict-free / random / 2-per-bank
+ * addresses.  +8 selects the 1024-thread x 1 CTA per SM shape instead of 512 x 2. */
 int b200ppf_microbench_atoms(b200ppf_ctx *ctx, int pattern, double *atoms_per_sec);
 
 /* ---- K4: [PCL] ppf_registration.hpp clusterPoses / posesWithinErrorBounds ---------------- */
@@ -318,7 +340,12 @@ int b200ppf_register(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf
  * resultsSub[0] returned).  scene is the full frame (xyz; b200ppf_cloud_upload_xyz), corners12 comes from
  * b200ppf_frustum_corners, model / table from the training calls above.  Nothing is copied to the host between
  * the stages.  object_out (optional) receives the pre-processed object cloud, edges_out (optional) its curvature
- * edges; free them with b200ppf_cloud_free. */
+ * edges; free them with b200ppf_cloud_free.
+ * What this is NOT: the reference's Matching_S2B feeds the edge cloud to its detector's match_S2B; the PCL
+ * matching here votes on the object cloud only, so the edges are extracted only when edges_out asks for them.
+ * The pose is PPFRegistration::align's (PCL arithmetic), not cv::ppf_match_3d::PPF3DDetector's — that engine is
+ * the b200cv_* interface.  PCL's clusterPoses returns at most three poses, so at most three are refined
+ * (icp_poses > 3 is clamped); sor_stddev_mul has no default in the reference (argv[5]): 1.0 is this library's. */
 typedef struct b200ppf_object_params {
     float leaf;             /* Subsampling leaf size (CLI argument 4 of the reference) */
     int sor_mean_k;         /* 50 */
@@ -327,7 +354,7 @@ typedef struct b200ppf_object_params {
     float edge_curvature;   /* 0.03; <= 0 skips the edge extraction */
     uint32_t ref_rate;      /* every ref_rate-th object point votes: 20 = the reference's 1 / 0.05 */
     float pos_thr, rot_thr; /* pose clustering: PCL's 0.01 m, 20 degrees (radians here) */
-    int icp_poses;          /* best poses refined by ICP: 5 in the reference (the engine returns at most 3); 0 = none */
+    int icp_poses;          /* best poses refined by ICP: 5 in the reference; clamped to the 3 that PCL's clustering returns; 0 = none */
     b200ppf_icp_params icp; /* (100, 0.005, 2.5, 8) */
 } b200ppf_object_params;
 typedef struct b200ppf_object_result {

@@ -17,6 +17,8 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libppf_oracle.so")
 
 FEATURE_PCL_PFH, FEATURE_DROST_COS, FEATURE_DROST_ANGLE = 0, 1, 2
 ALPHA_MODE_A, ALPHA_MODE_B = 0, 1
+NALPHA_CEIL, NALPHA_FLOOR_DROP, NALPHA_FLOOR_CLAMP = 0, 1, 2
+BIN_NAN, BIN_DROPPED = 0xFFFFFFFF, 0xFFFFFFFE
 
 HYP_DTYPE = np.dtype(
     [("pose", np.float32, (12,)), ("votes", np.uint32), ("model_index", np.uint32),
@@ -74,9 +76,10 @@ def _declare(L):
     L.oracle_hashmap_query_key.argtypes = [vp, vp, vp, sz]
     L.oracle_hashmap_query_key.restype = sz
     L.oracle_hashmap_dump_keys.argtypes = [vp, vp, vp]
-    L.oracle_num_alpha_bins.argtypes = [C.c_float]
+    L.oracle_hashmap_set_nalpha_rule.argtypes = [vp, C.c_int]
+    L.oracle_num_alpha_bins.argtypes = [C.c_float, C.c_int]
     L.oracle_num_alpha_bins.restype = C.c_uint32
-    L.oracle_alpha_bin.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+    L.oracle_alpha_bin.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
     L.oracle_alpha_bin.restype = C.c_uint32
     L.oracle_scene_pairs.argtypes = [vp, C.c_int, vp, sz, sz, vp, vp, vp]
     L.oracle_scene_pairs.restype = sz
@@ -162,23 +165,31 @@ def ppf_estimation(cloud, mode=FEATURE_PCL_PFH):
     return out
 
 
-def num_alpha_bins(angle_step):
-    return int(lib().oracle_num_alpha_bins(np.float32(angle_step)))
+def num_alpha_bins(angle_step, nalpha_rule=NALPHA_CEIL):
+    return int(lib().oracle_num_alpha_bins(np.float32(angle_step), nalpha_rule))
 
 
-def alpha_bin(alpha_m, alpha_s, angle_step, mode=ALPHA_MODE_A):
-    return int(lib().oracle_alpha_bin(mode, np.float32(angle_step), np.float32(alpha_m),
+def alpha_bin(alpha_m, alpha_s, angle_step, mode=ALPHA_MODE_A, nalpha_rule=NALPHA_CEIL):
+    """bin of one vote; BIN_NAN for a NaN angle, BIN_DROPPED for a vote the FLOOR_DROP rule loses"""
+    return int(lib().oracle_alpha_bin(mode, nalpha_rule, np.float32(angle_step), np.float32(alpha_m),
                                       np.float32(alpha_s)))
 
 
 class HashMap:
     """pcl::PPFHashMapSearch restated (unordered_multimap + alpha_m matrix)."""
 
-    def __init__(self, angle_step=np.float32(12.0 / 180.0 * np.pi), dist_step=np.float32(0.01)):
+    def __init__(self, angle_step=np.float32(12.0 / 180.0 * np.pi), dist_step=np.float32(0.01), nalpha_rule=NALPHA_CEIL):
         self.angle_step = np.float32(angle_step)
         self.dist_step = np.float32(dist_step)
         self._h = lib().oracle_hashmap_create(self.angle_step, self.dist_step)
         self.n = 0
+        self.set_nalpha_rule(nalpha_rule)
+
+    def set_nalpha_rule(self, rule):
+        """columns of the voting accumulator: NALPHA_CEIL (default) | NALPHA_FLOOR_DROP | NALPHA_FLOOR_CLAMP"""
+        self.nalpha_rule = int(rule)
+        lib().oracle_hashmap_set_nalpha_rule(self._h, self.nalpha_rule)
+        return self
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -246,7 +257,7 @@ class HashMap:
 
     def vote_accumulate(self, n_m, scene, s_r, mode=FEATURE_PCL_PFH, alpha_mode=ALPHA_MODE_A):
         scene = _f32(scene)
-        acc = np.zeros((n_m, num_alpha_bins(self.angle_step)), np.uint32)
+        acc = np.zeros((n_m, num_alpha_bins(self.angle_step, self.nalpha_rule)), np.uint32)
         votes = lib().oracle_vote_accumulate(self._h, mode, alpha_mode, n_m, _p(scene),
                                              scene.shape[0], s_r, _p(acc))
         return acc, int(votes)
@@ -254,7 +265,7 @@ class HashMap:
     def vote_accumulate_from_pairs(self, n_m, d, alpha_s, alpha_mode=ALPHA_MODE_A):
         d = np.ascontiguousarray(d, np.int32).reshape(-1, 4)
         alpha_s = _f32(alpha_s)
-        acc = np.zeros((n_m, num_alpha_bins(self.angle_step)), np.uint32)
+        acc = np.zeros((n_m, num_alpha_bins(self.angle_step, self.nalpha_rule)), np.uint32)
         votes = lib().oracle_vote_accumulate_from_pairs(self._h, alpha_mode, n_m, d.shape[0], _p(d),
                                                         _p(alpha_s), _p(acc))
         return acc, int(votes)

@@ -222,6 +222,7 @@ struct oracle_hashmap {
     float angle_step;
     float dist_step;
     float max_dist;
+    int nalpha_rule = ORACLE_NALPHA_CEIL;
     size_t n;
     std::unordered_multimap<Key, std::pair<size_t, size_t>, KeyHash> map;
     std::vector<std::vector<float>> alpha_m;
@@ -239,11 +240,27 @@ inline Key quantise(const oracle_hashmap *hm, const float *f) {
     return k;
 }
 
-inline uint32_t num_alpha_bins(float angle_step) {
-    return static_cast<uint32_t>(std::floor(2 * M_PI / angle_step)); /* double */
+/* Columns of the accumulator (ppf_registration.hpp, `aux_size`).  PCL 1.8 .. 1.11 take the floor of
+ * 2*pi / step, current PCL the ceiling; for PCL's float 12 degrees the quotient is 30 - 1.3e-6, i.e. 29 or 30
+ * columns while the binning formula below produces bins 0 .. 29.  ppf_oracle.h ORACLE_NALPHA_*. */
+inline uint32_t num_alpha_bins(float angle_step, int rule) {
+    const double t = 2 * M_PI / angle_step; /* double */
+    return static_cast<uint32_t>(rule == ORACLE_NALPHA_CEIL ? std::ceil(t) : std::floor(t));
 }
 
-inline uint32_t alpha_bin(int mode, float angle_step, uint32_t n_alpha, float alpha_m,
+constexpr uint32_t BIN_DROPPED = UINT32_MAX - 1;
+
+/* what becomes of a bin past the last column */
+inline uint32_t place_bin(int rule, uint32_t n_alpha, uint32_t bin) {
+    if (bin < n_alpha) return bin;
+    /* FLOOR_DROP: PCL <= 1.11 executes accumulator_array[i][29]++ on a 29-element std::vector<unsigned int>: the word
+     * behind the row's 116 bytes, inside the 120 usable bytes of its glibc chunk — never read again, the vote is lost.
+     * CEIL reaches this line only when 2*pi/step is an integer to the last bit (then PCL writes out of bounds too);
+     * the oracle clamps there, as it does under FLOOR_CLAMP, the rule of this repository's round 1. */
+    return rule == ORACLE_NALPHA_FLOOR_DROP ? BIN_DROPPED : n_alpha - 1;
+}
+
+inline uint32_t alpha_bin(int mode, float angle_step, uint32_t n_alpha, int rule, float alpha_m,
                           float alpha_s) {
     float alpha = alpha_m - alpha_s;
     if (std::isnan(alpha)) return UINT32_MAX;
@@ -260,8 +277,7 @@ inline uint32_t alpha_bin(int mode, float angle_step, uint32_t n_alpha, float al
         double b = std::floor((alpha + M_PI) / angle_step);
         bin = b < 0 ? 0u : static_cast<uint32_t>(b);
     }
-    if (bin >= n_alpha) bin = n_alpha - 1; /* PCL writes out of bounds here; we clamp */
-    return bin;
+    return place_bin(rule, n_alpha, bin);
 }
 
 /* pose = T_sg^-1 * Rx(theta) * T_mg  as 3x4 row-major */
@@ -429,10 +445,10 @@ inline void vote_one_pair(const oracle_hashmap *hm, int feature_mode, int alpha_
     ++counters[2];
     float alpha_s = planar_alpha(sg, p_i);
     for (const auto &ij : bucket) {
-        uint32_t bin = alpha_bin(alpha_mode, hm->angle_step, n_alpha, hm->alpha_m[ij.first][ij.second], alpha_s);
+        uint32_t bin = alpha_bin(alpha_mode, hm->angle_step, n_alpha, hm->nalpha_rule, hm->alpha_m[ij.first][ij.second], alpha_s);
         if (bin == UINT32_MAX) continue;
-        acc[ij.first * n_alpha + bin]++;
-        ++counters[3];
+        if (bin != BIN_DROPPED) acc[ij.first * n_alpha + bin]++;
+        ++counters[3]; /* a dropped vote is still an increment PCL executes */
     }
 }
 
@@ -665,10 +681,12 @@ void oracle_hashmap_dump_keys(const oracle_hashmap *hm, int32_t *keys, uint32_t 
     }
 }
 
-uint32_t oracle_num_alpha_bins(float angle_step) { return num_alpha_bins(angle_step); }
+void oracle_hashmap_set_nalpha_rule(oracle_hashmap *hm, int rule) { hm->nalpha_rule = rule; }
 
-uint32_t oracle_alpha_bin(int alpha_mode, float angle_step, float alpha_m, float alpha_s) {
-    return alpha_bin(alpha_mode, angle_step, num_alpha_bins(angle_step), alpha_m, alpha_s);
+uint32_t oracle_num_alpha_bins(float angle_step, int nalpha_rule) { return num_alpha_bins(angle_step, nalpha_rule); }
+
+uint32_t oracle_alpha_bin(int alpha_mode, int nalpha_rule, float angle_step, float alpha_m, float alpha_s) {
+    return alpha_bin(alpha_mode, angle_step, num_alpha_bins(angle_step, nalpha_rule), nalpha_rule, alpha_m, alpha_s);
 }
 
 size_t oracle_scene_pairs(const oracle_hashmap *hm, int feature_mode, const float *scene,
@@ -700,7 +718,7 @@ size_t oracle_scene_pairs(const oracle_hashmap *hm, int feature_mode, const floa
 uint64_t oracle_vote_accumulate_from_pairs(const oracle_hashmap *hm, int alpha_mode, size_t n_m,
                                            size_t n_pairs, const int32_t *d, const float *alpha_s,
                                            uint32_t *acc) {
-    const uint32_t n_alpha = num_alpha_bins(hm->angle_step);
+    const uint32_t n_alpha = num_alpha_bins(hm->angle_step, hm->nalpha_rule);
     std::memset(acc, 0, n_m * n_alpha * sizeof(uint32_t));
     uint64_t votes = 0;
     for (size_t p = 0; p < n_pairs; ++p) {
@@ -708,10 +726,10 @@ uint64_t oracle_vote_accumulate_from_pairs(const oracle_hashmap *hm, int alpha_m
         std::memcpy(k.d, d + 4 * p, sizeof(k.d));
         auto range = hm->map.equal_range(k);
         for (auto it = range.first; it != range.second; ++it) {
-            uint32_t bin = alpha_bin(alpha_mode, hm->angle_step, n_alpha,
+            uint32_t bin = alpha_bin(alpha_mode, hm->angle_step, n_alpha, hm->nalpha_rule,
                                      hm->alpha_m[it->second.first][it->second.second], alpha_s[p]);
             if (bin == UINT32_MAX) continue;
-            acc[it->second.first * n_alpha + bin]++;
+            if (bin != BIN_DROPPED) acc[it->second.first * n_alpha + bin]++;
             ++votes;
         }
     }
@@ -739,7 +757,7 @@ int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, cons
                 size_t n_m, const float *scene, size_t n_s, size_t ref_first, size_t ref_step,
                 size_t ref_count, int n_threads, oracle_hypothesis *hyps, uint64_t *stats) {
     if (!hm || hm->n != n_m || ref_step == 0) return -1;
-    const uint32_t n_alpha = num_alpha_bins(hm->angle_step);
+    const uint32_t n_alpha = num_alpha_bins(hm->angle_step, hm->nalpha_rule);
     Grid grid;
     const float radius = hm->max_dist * 0.5f;
     const bool use_grid = radius > 0.0f && n_s > 2048;

@@ -28,6 +28,10 @@ extern "C" {
 enum { ORACLE_FEATURE_PCL_PFH = 0, ORACLE_FEATURE_DROST_COS = 1, ORACLE_FEATURE_DROST_ANGLE = 2 };
 /* alpha binning: mode A = PCL >= 1.12 (canonical), mode B = PCL 1.8-1.11 */
 enum { ORACLE_ALPHA_MODE_A = 0, ORACLE_ALPHA_MODE_B = 1 };
+/* columns of the voting accumulator (SURVEY.md A.4 `aux_size`): CEIL = ceil(2*pi/step), current PCL and the
+ * default; FLOOR_DROP = floor(2*pi/step) with the votes for the missing last bin lost, PCL 1.8 .. 1.11;
+ * FLOOR_CLAMP = floor with those votes added to the last column (round 1 of this repository). */
+enum { ORACLE_NALPHA_CEIL = 0, ORACLE_NALPHA_FLOOR_DROP = 1, ORACLE_NALPHA_FLOOR_CLAMP = 2 };
 
 /* A.1 / A.1' : one pair feature.  Returns 1 when the pair is valid. */
 int oracle_pair_feature(int feature_mode, const float *p1, const float *n1, const float *p2,
@@ -64,10 +68,12 @@ size_t oracle_hashmap_query_key(const oracle_hashmap *hm, const int32_t *d, uint
 /* dump every distinct key (4 ints each) and its bucket length; arrays sized num_keys */
 void oracle_hashmap_dump_keys(const oracle_hashmap *hm, int32_t *keys, uint32_t *lengths);
 
+/* the column rule of every voting call on this map (default ORACLE_NALPHA_CEIL) */
+void oracle_hashmap_set_nalpha_rule(oracle_hashmap *hm, int nalpha_rule);
 /* A.4 : number of alpha bins */
-uint32_t oracle_num_alpha_bins(float angle_step);
-/* A.4 : bin of one (alpha_m, alpha_s) pair. Returns UINT32_MAX for NaN. */
-uint32_t oracle_alpha_bin(int alpha_mode, float angle_step, float alpha_m, float alpha_s);
+uint32_t oracle_num_alpha_bins(float angle_step, int nalpha_rule);
+/* A.4 : bin of one (alpha_m, alpha_s) pair. Returns UINT32_MAX for NaN, UINT32_MAX - 1 for a vote the rule drops. */
+uint32_t oracle_alpha_bin(int alpha_mode, int nalpha_rule, float angle_step, float alpha_m, float alpha_s);
 
 /* A.4 : per-scene-pair quantities of one reference point (debug / parity):
  * for every scene point s writes in_radius[s] (0/1; 0 for s==s_r and for failed pairs),

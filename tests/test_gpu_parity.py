@@ -85,7 +85,7 @@ def test_k2_buckets_bit_exact(oracle_bottle, table_from_oracle_features):
     assert ti.n_entries == hm.num_entries == 294306
     assert ti.n_keys == hm.num_keys == 10448
     assert np.float32(ti.max_dist) == np.float32(hm.model_diameter)
-    assert ti.n_alpha == 29 and ti.n_slices == 1
+    assert ti.n_alpha == 30 and ti.nalpha_rule == 0 and ti.n_slices == 1   # ceil(2*pi / float(12 deg)): the default column rule
     buckets = parity.table_buckets(t)
     keys, lengths = hm.dump_keys()
     assert len(buckets) == len(keys)
@@ -225,6 +225,120 @@ def test_k2_table_save_load(tmp_path, ctx, dev_bottle, dev_crop, table_fused):
     with pytest.raises(capi.B200PPFError) as e:
         cb.table_load(path)
     assert "mode differs" in str(e.value)
+
+
+def _mix_bytes(h, data):
+    """the table file's 64-bit multiplicative checksum (csrc/capi.cu mix_bytes)"""
+    M = (1 << 64) - 1
+    data = bytes(data)
+    data += b"\0" * (-len(data) % 8)
+    for w in np.frombuffer(data, "<u8").tolist():
+        h = ((h ^ w) * 0x9E3779B97F4A7C15) & M
+        h ^= h >> 29
+    return h
+
+
+def test_k2_table_load_refuses_consistent_looking_but_invalid_files(tmp_path, ctx, dev_bottle):
+    """A file whose checksum is RIGHT but whose contents would send the voting kernel out of bounds (rewritten or
+    crafted): decreasing offsets, a hot word pointing outside the accumulator slice, a pair index beyond n*n, key
+    ranges whose product is not the key space, binning parameters that do not follow from the angle step."""
+    import ctypes as C
+    from yolo_ppf_pose_estimation_b200 import capi
+    small = ctx.upload_cloud(dev_bottle.download()[::6].copy())
+    t = ctx.table_build_from_cloud(small, ANGLE_STEP, DIST_STEP)
+    path = str(tmp_path / "t.b200ppf")
+    t.save(path)
+    raw = bytearray(open(path, "rb").read())
+    hdr = int(np.frombuffer(raw[12:16], "<u4")[0])
+    n_off, n_sub, n_ent = (int(x) for x in np.frombuffer(raw[24:48], "<u8"))
+    info_off, info_len = 56, C.sizeof(capi.TableInfo)
+    a_off = hdr                      # arrays: offsets, sub_offsets, entry_w, entry_am, entry_alpha, entry_idx
+    starts = np.cumsum([0, n_off, n_sub, n_ent, n_ent, n_ent]) * 4 + a_off
+
+    def resign(blob):
+        h = _mix_bytes(0x42323030, blob[info_off:hdr])      # info, key and binning parameters
+        for k, cnt in enumerate((n_off, n_sub, n_ent, n_ent, n_ent, n_ent)):
+            h = _mix_bytes(h, blob[starts[k]:starts[k] + 4 * cnt])
+        blob[48:56] = np.array([h], "<u8").tobytes()
+        return blob
+
+    good = tmp_path / "good.b200ppf"
+    good.write_bytes(resign(bytearray(raw)))
+    assert bytes(resign(bytearray(raw))) == bytes(raw)      # the test's checksum is the library's
+    ctx.table_load(str(good))
+
+    def word(blob, array, index):
+        o = int(starts[array]) + 4 * index
+        return o, int(np.frombuffer(blob[o:o + 4], "<u4")[0])
+
+    cases = []
+    b = bytearray(raw)                                     # offsets decrease in the middle
+    o, v = word(b, 0, n_off // 2)
+    b[o:o + 4] = np.array([v + 7], "<u4").tobytes()
+    cases.append(("offsets", b))
+    b = bytearray(raw)                                     # a hot word far outside the accumulator slice
+    o, v = word(b, 2, n_ent // 3)
+    b[o:o + 4] = np.array([(v & 0xFF000000) | 0x00FFFFF0], "<u4").tobytes()
+    cases.append(("hot word", b))
+    b = bytearray(raw)                                     # pair index beyond n*n
+    o, v = word(b, 5, 5)
+    b[o:o + 4] = np.array([0x7FFFFFFF], "<u4").tobytes()
+    cases.append(("pair index", b))
+    b = bytearray(raw)                                     # key ranges: size[0] + 1 (both copies), key_space unchanged
+    ti = capi.TableInfo.from_buffer_copy(bytes(raw[info_off:info_off + info_len]))
+    ti.size[0] += 1
+    b[info_off:info_off + info_len] = bytes(ti)
+    kp_size0 = info_off + info_len + 8 + 16                # KeyParams: two float steps, lo[4], size[4], ...
+    assert np.frombuffer(b[kp_size0:kp_size0 + 4], "<i4")[0] == ti.size[0] - 1
+    b[kp_size0:kp_size0 + 4] = np.array([ti.size[0]], "<i4").tobytes()
+    cases.append(("key space", b))
+    b = bytearray(raw)                                     # binning: another fixed-point multiplier (the last header word holding it)
+    fm = np.frombuffer(bytes(raw[info_off + info_len:hdr]), "<u4")
+    ix = int(np.flatnonzero(fm == fm[fm > (1 << 24)].max())[-1])
+    o = info_off + info_len + 4 * ix
+    b[o:o + 4] = np.array([int(fm[ix]) + 12345], "<u4").tobytes()
+    cases.append(("binning parameters", b))
+    for what, blob in cases:
+        bad = tmp_path / "bad.b200ppf"
+        bad.write_bytes(resign(blob))
+        with pytest.raises(capi.B200PPFError) as e:
+            ctx.table_load(str(bad))
+        assert "invalid table" in str(e.value) and what in str(e.value), (what, str(e.value))
+
+
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_k3_alpha_column_rules(bottle, scene_crop, oracle, oracle_bottle, rule):
+    """The three rules for the accumulator's alpha columns (include/b200ppf.h B200PPF_NALPHA_*): ceil = 30 columns for
+    PCL's 12 degrees (default), floor + drop and floor + clamp = 29.  Accumulators bit-exact against the oracle under the
+    same rule, hypotheses equal to the oracle's on the same accumulators, the rule survives save / load."""
+    from yolo_ppf_pose_estimation_b200 import capi
+    feats, _ = oracle_bottle
+    hm = oracle.HashMap(ANGLE_STEP, DIST_STEP, nalpha_rule=rule).set_input_feature_cloud(feats)
+    c = capi.Context(0, nalpha_rule=rule)
+    t = c.table_build(c.features_upload(feats), ANGLE_STEP, DIST_STEP)
+    assert t.info.n_alpha == (30 if rule == 0 else 29) == oracle.num_alpha_bins(ANGLE_STEP, rule) and t.info.nalpha_rule == rule
+    dm, ds = c.upload_cloud(bottle), c.upload_cloud(scene_crop)
+    cast = {}
+    for s_r in REFS:
+        inr, d, a = c.vote_debug_pairs(t, ds, s_r)
+        acc = c.vote_debug_accumulator(t, ds, s_r)
+        ref, votes = hm.vote_accumulate_from_pairs(bottle.shape[0], d[inr > 0], a[inr > 0])
+        assert acc.shape == ref.shape and np.array_equal(acc, ref), (rule, s_r)
+        assert int(acc.sum()) == votes if rule != 1 else int(acc.sum()) < votes    # dropped votes are cast but not stored
+        assert c.vote_stats()["votes"] == votes
+    hy = c.vote(dm, t, ds, 0, 5)
+    for h in hy[::9]:
+        acc = c.vote_debug_accumulator(t, ds, int(h["scene_index"]))
+        flat = int(np.argmax(acc))
+        assert h["votes"] == acc.reshape(-1)[flat]
+        if h["votes"]:
+            assert (int(h["model_index"]), int(h["alpha_bin"])) == divmod(flat, acc.shape[1])
+    import tempfile
+    with tempfile.TemporaryDirectory() as d_:
+        path = os.path.join(d_, "t.b200ppf")
+        t.save(path)
+        t2 = capi.Context(0).table_load(path)          # the rule travels with the file, whatever the loading context's is
+        assert t2.info.nalpha_rule == rule and t2.info.n_alpha == t.info.n_alpha
 
 
 # ---- K3 ------------------------------------------------------------------------------------------

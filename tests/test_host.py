@@ -37,10 +37,23 @@ def test_struct_layouts_match_the_header():
     import ctypes as C
     from yolo_ppf_pose_estimation_b200 import capi
     assert capi.HYP_DTYPE.itemsize == 64 and capi.SIG_DTYPE.itemsize == 20
-    assert C.sizeof(capi.TableInfo) == 4 * 8 + 4 * 4 + 8 * 4 + 4 * 4
-    assert C.sizeof(capi.Timings) == 12 * 4
-    assert C.sizeof(capi.ObjectParams) == 56 and C.sizeof(capi.ObjectResult) == 16 * 8 + 8 + 6 * 4 + 8 * 4  # = the C sizeof
     assert capi.HYP_DTYPE.fields["votes"][1] == 48 and capi.HYP_DTYPE.fields["scene_index"][1] == 60
+    # sizes and the offset of every struct's last member as the C compiler lays them out
+    import subprocess
+    import tempfile
+    structs = {"b200ppf_table_info": (capi.TableInfo, "reserved"), "b200ppf_timings": (capi.Timings, "prep_ms"),
+               "b200ppf_icp_params": (capi.IcpParams, "num_levels"), "b200ppf_object_params": (capi.ObjectParams, "icp"),
+               "b200ppf_object_result": (capi.ObjectResult, "total_wall_ms")}
+    body = "".join(f'printf("{n} %zu %zu\\n", sizeof({n}), offsetof({n}, {last}));' for n, (_, last) in structs.items())
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "layout.c")
+        open(src, "w").write(f'#include <stdio.h>\n#include <stddef.h>\n#include "b200ppf.h"\nint main(void){{{body}return 0;}}\n')
+        subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(d, "layout")], check=True)
+        out = subprocess.run([os.path.join(d, "layout")], capture_output=True, text=True, check=True).stdout
+    for line in out.strip().splitlines():
+        name, size, off = line.split()
+        cls, last = structs[name]
+        assert C.sizeof(cls) == int(size) and getattr(cls, last).offset == int(off), line
 
 
 def test_no_cpu_fallback_without_a_gpu():
@@ -78,14 +91,16 @@ def test_hot_loop_alpha_bin_equals_literal_form_and_oracle(oracle):
         am2 = (edge + as2.astype(np.float64)).astype(np.float32)
         am2 = (am2.view(np.int32) + rng.integers(-4, 5, n).astype(np.int32)).view(np.float32)
         AM, AS = np.concatenate([am, am2, [np.nan, 0.0]]).astype(np.float32), np.concatenate([as_, as2, [0.0, np.nan]]).astype(np.float32)
-        for mode in (0, 1):
-            fast, exact = capi.debug_alpha_bins(AM, AS, step, mode)
+        for mode, rule in ((0, 0), (0, 1), (0, 2), (1, 0), (1, 2)):
+            nal = oracle.num_alpha_bins(step, rule)
+            fast, exact = capi.debug_alpha_bins(AM, AS, step, mode, nalpha_rule=rule)
             assert np.array_equal(fast, exact)
             sel = rng.choice(len(AM), 3000, replace=False)
-            ref = np.array([L.oracle_alpha_bin(mode, step, AM[i], AS[i]) for i in sel], np.uint32)
+            ref = np.array([L.oracle_alpha_bin(mode, rule, step, AM[i], AS[i]) for i in sel], np.uint32)
+            ref[ref == oracle.BIN_DROPPED] = nal  # the device files a dropped vote in the row's spare cell
             assert np.array_equal(exact[sel], ref)
             assert exact[-1] == exact[-2] == 0xFFFFFFFF
-            assert exact[:-2].max() <= nal - 1
+            assert exact[:-2].max() <= (nal if rule == 1 else nal - 1)
 
 
 def test_constant_shift_binning_over_many_angle_steps():
@@ -107,8 +122,9 @@ def test_constant_shift_binning_over_many_angle_steps():
         am2 = ((k * np.float64(step) - np.pi + as2.astype(np.float64) + np.pi) % (2 * np.pi) - np.pi).astype(np.float32)
         am2 = (am2.view(np.int32) + rng.integers(-3, 4, n).astype(np.int32)).view(np.float32)
         ok = np.abs(am2) <= np.float32(3.14159274)
-        fast, exact = capi.debug_alpha_bins(np.concatenate([am, am2[ok]]), np.concatenate([as_, as2[ok]]), step, 0)
-        assert np.array_equal(fast, exact), float(step)
+        for rule in (0, 1, 2):
+            fast, exact = capi.debug_alpha_bins(np.concatenate([am, am2[ok]]), np.concatenate([as_, as2[ok]]), step, 0, nalpha_rule=rule)
+            assert np.array_equal(fast, exact), (float(step), rule)
 
 
 def test_synthetic_clouds():

@@ -129,28 +129,82 @@ def test_hashmap_query_and_quantisation(oracle_bottle):
 
 
 def test_num_alpha_bins_and_binning(oracle):
-    assert oracle.num_alpha_bins(ANGLE_STEP) == 29          # float(12 deg) > 2*pi/30: floor gives 29
-    assert oracle.num_alpha_bins(np.float32(0.25)) == 25
+    # float(12 deg) > 2*pi/30, so 2*pi/step = 30 - 1.3e-6: the ceiling (current PCL, the default) gives 30 columns,
+    # the floor (PCL <= 1.11) 29 while the binning formula still produces bin 29
+    assert oracle.num_alpha_bins(ANGLE_STEP) == oracle.num_alpha_bins(ANGLE_STEP, oracle.NALPHA_CEIL) == 30
+    assert oracle.num_alpha_bins(ANGLE_STEP, oracle.NALPHA_FLOOR_DROP) == oracle.num_alpha_bins(ANGLE_STEP, oracle.NALPHA_FLOOR_CLAMP) == 29
+    assert oracle.num_alpha_bins(np.float32(0.25)) == 26 and oracle.num_alpha_bins(np.float32(0.25), oracle.NALPHA_FLOOR_DROP) == 25
     rng = np.random.default_rng(2)
-    for _ in range(2000):
+    seen29 = 0
+    for _ in range(4000):
         am, as_ = rng.uniform(-np.pi, np.pi, 2).astype(np.float32)
-        b = oracle.alpha_bin(am, as_, ANGLE_STEP)
         a = float(np.float32(am - as_))
         if a < -np.pi:
             a = float(np.float32(a + 2 * np.pi))
         elif a > np.pi:
             a = float(np.float32(a - 2 * np.pi))
-        assert b == min(int(np.floor((a + np.pi) / float(ANGLE_STEP))), 28)
+        literal = int(np.floor((a + np.pi) / float(ANGLE_STEP)))
+        assert 0 <= literal <= 29
+        seen29 += literal == 29
+        assert oracle.alpha_bin(am, as_, ANGLE_STEP) == literal                                   # ceil: every bin has a column
+        assert oracle.alpha_bin(am, as_, ANGLE_STEP, nalpha_rule=oracle.NALPHA_FLOOR_CLAMP) == min(literal, 28)
+        assert oracle.alpha_bin(am, as_, ANGLE_STEP, nalpha_rule=oracle.NALPHA_FLOOR_DROP) == (literal if literal < 29 else oracle.BIN_DROPPED)
         bb = oracle.alpha_bin(am, as_, ANGLE_STEP, mode=oracle.ALPHA_MODE_B)
         assert bb == int(np.floor(np.float32(am - as_)) + np.floor(np.pi / float(ANGLE_STEP)))
-    assert oracle.alpha_bin(np.float32("nan"), 0.0, ANGLE_STEP) == 0xFFFFFFFF
+    assert seen29 > 50
+    assert oracle.alpha_bin(np.float32("nan"), 0.0, ANGLE_STEP) == oracle.BIN_NAN
+
+
+def test_column_rules_differ_only_in_the_last_bin(oracle, oracle_bottle, bottle, scene_crop):
+    """ceil: 30 columns; floor+drop: the first 29 of them; floor+clamp: column 28 also holds column 29's votes.
+    The votes cast (increments PCL executes) are the same under all three."""
+    _, hm = oracle_bottle
+    try:
+        accs, cast = {}, {}
+        for rule in (oracle.NALPHA_CEIL, oracle.NALPHA_FLOOR_DROP, oracle.NALPHA_FLOOR_CLAMP):
+            hm.set_nalpha_rule(rule)
+            accs[rule], cast[rule] = hm.vote_accumulate(543, scene_crop, 250)
+        ceil, drop, clamp = (accs[r].astype(np.int64) for r in (0, 1, 2))
+        assert ceil.shape == (543, 30) and drop.shape == clamp.shape == (543, 29)
+        assert ceil[:, 29].sum() > 0
+        assert np.array_equal(drop, ceil[:, :29])
+        assert np.array_equal(clamp[:, :28], ceil[:, :28]) and np.array_equal(clamp[:, 28], ceil[:, 28] + ceil[:, 29])
+        assert cast[0] == cast[1] == cast[2] == ceil.sum()
+    finally:
+        hm.set_nalpha_rule(oracle.NALPHA_CEIL)
 
 
 # ---- voting ---------------------------------------------------------------------------------------
 
-def test_golden_vectors(oracle, oracle_bottle, bottle, scene_crop):
+def test_golden_vectors_of_the_other_column_rules(oracle, oracle_bottle, bottle, scene_crop):
+    """tests/golden/oracle_golden_rules.npz (tools/make_golden.py): hypotheses, clusters and one accumulator under the
+    ceil (default) and floor+drop rules."""
+    g = np.load(os.path.join(GOLDEN, "oracle_golden_rules.npz"))
+    _, hm = oracle_bottle
+    try:
+        for name, rule in (("ceil", oracle.NALPHA_CEIL), ("drop", oracle.NALPHA_FLOOR_DROP)):
+            hm.set_nalpha_rule(rule)
+            hyps, stats = hm.vote(bottle, scene_crop, 0, 5, n_threads=1)
+            assert np.array_equal(hyps["votes"], g[f"{name}_hyp_votes"]) and np.array_equal(hyps["model_index"], g[f"{name}_hyp_model_index"])
+            assert np.array_equal(hyps["alpha_bin"], g[f"{name}_hyp_alpha_bin"]) and np.allclose(hyps["pose"], g[f"{name}_hyp_pose"], atol=1e-6)
+            assert stats["votes"] == int(g[f"{name}_votes_cast"])
+            poses, votes, assign, ncl = oracle.cluster(hyps)
+            assert ncl == int(g[f"{name}_n_clusters"]) and np.array_equal(votes, g[f"{name}_cluster_votes"])
+            assert np.allclose(poses, g[f"{name}_cluster_poses"], atol=1e-6)
+            acc, _ = hm.vote_accumulate(543, scene_crop, 250)
+            assert acc.shape[1] == int(g[f"{name}_n_alpha"])
+            flat = acc.reshape(-1)
+            assert np.array_equal(np.flatnonzero(flat), g[f"{name}_acc250_nonzero_index"])
+            assert np.array_equal(flat[flat > 0], g[f"{name}_acc250_nonzero_value"])
+    finally:
+        hm.set_nalpha_rule(oracle.NALPHA_CEIL)
+
+
+def test_golden_vectors(oracle, bottle, scene_crop):
+    """round 1's frozen vectors: the floor+clamp column rule"""
     g = np.load(os.path.join(GOLDEN, "oracle_golden.npz"))
-    feats, hm = oracle_bottle
+    feats = oracle.ppf_estimation(bottle)
+    hm = oracle.HashMap(ANGLE_STEP, DIST_STEP, nalpha_rule=oracle.NALPHA_FLOOR_CLAMP).set_input_feature_cloud(feats)
     assert np.allclose(feats[g["pair_index"]], g["pair_features"], atol=1e-6, equal_nan=True)
     keys, lengths = hm.dump_keys()
     order = np.lexsort(keys.T[::-1])

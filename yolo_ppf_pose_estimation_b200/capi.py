@@ -14,6 +14,7 @@ from . import build as _build
 
 FEATURE_PCL_PFH, FEATURE_DROST_COS, FEATURE_DROST_ANGLE = 0, 1, 2
 ALPHA_MODE_A, ALPHA_MODE_B = 0, 1
+NALPHA_CEIL, NALPHA_FLOOR_DROP, NALPHA_FLOOR_CLAMP = 0, 1, 2
 
 HYP_DTYPE = np.dtype(
     [("pose", np.float32, (12,)), ("votes", np.uint32), ("model_index", np.uint32),
@@ -29,7 +30,7 @@ class TableInfo(C.Structure):
                 ("key_space", C.c_uint64), ("n_slices", C.c_uint32), ("slice_rows", C.c_uint32),
                 ("n_alpha", C.c_uint32), ("key_bits", C.c_uint32), ("lo", C.c_int32 * 4),
                 ("size", C.c_int32 * 4), ("angle_step", C.c_float), ("dist_step", C.c_float),
-                ("max_dist", C.c_float), ("phase_cells", C.c_uint32)]
+                ("max_dist", C.c_float), ("phase_cells", C.c_uint32), ("nalpha_rule", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Timings(C.Structure):
@@ -64,6 +65,7 @@ SYMBOLS = {
     "b200ppf_version": (_i, []),
     "b200ppf_set_feature_mode": (_i, [_vp, _i]),
     "b200ppf_set_alpha_mode": (_i, [_vp, _i]),
+    "b200ppf_set_nalpha_rule": (_i, [_vp, _i]),
     "b200ppf_get_device": (_i, [_vp]),
     "b200ppf_get_stream": (_vp, [_vp]),
     "b200ppf_synchronize": (_i, [_vp]),
@@ -97,7 +99,7 @@ SYMBOLS = {
     "b200ppf_vote_stats": (_i, [_vp, _vp]),
     "b200ppf_vote_debug_pairs": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "b200ppf_vote_debug_accumulator": (_i, [_vp, _vp, _vp, _sz, _vp]),
-    "b200ppf_debug_alpha_bins": (_i, [_vp, _f, _i, _vp, _vp, _sz, _vp, _vp]),
+    "b200ppf_debug_alpha_bins": (_i, [_vp, _f, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "b200ppf_microbench_atoms": (_i, [_vp, _i, C.POINTER(C.c_double)]),
     "b200ppf_cluster": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_cluster_device": (_i, [_vp, _vp, _sz, _f, _f, _vp, _vp, C.POINTER(_sz)]),
@@ -165,13 +167,15 @@ def _as_ptr(x):
 class Context:
     """One GPU, one stream.  One context per process/rank."""
 
-    def __init__(self, device: int = 0, feature_mode: int = FEATURE_PCL_PFH, alpha_mode: int = ALPHA_MODE_A):
+    def __init__(self, device: int = 0, feature_mode: int = FEATURE_PCL_PFH, alpha_mode: int = ALPHA_MODE_A,
+                 nalpha_rule: int = NALPHA_CEIL):
         self._h = C.c_void_p()
         rc = lib().b200ppf_create(device, C.byref(self._h))
         if rc != 0:
             raise B200PPFError(rc, lib().b200ppf_last_error(None).decode())
         self.check(lib().b200ppf_set_feature_mode(self._h, feature_mode))
         self.check(lib().b200ppf_set_alpha_mode(self._h, alpha_mode))
+        self.check(lib().b200ppf_set_nalpha_rule(self._h, nalpha_rule))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -202,6 +206,10 @@ class Context:
 
     def set_alpha_mode(self, mode):
         self.check(lib().b200ppf_set_alpha_mode(self._h, mode))
+
+    def set_nalpha_rule(self, rule):
+        """alpha columns of the accumulator: NALPHA_CEIL (default) | NALPHA_FLOOR_DROP | NALPHA_FLOOR_CLAMP; read at table build"""
+        self.check(lib().b200ppf_set_nalpha_rule(self._h, rule))
 
     def set_feature_mode(self, mode):
         self.check(lib().b200ppf_set_feature_mode(self._h, mode))
@@ -453,14 +461,15 @@ class Context:
         return final.reshape(4, 4), poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
 
 
-def debug_alpha_bins(alpha_m, alpha_s, angle_step, alpha_mode=ALPHA_MODE_A, ctx: "Context | None" = None):
+def debug_alpha_bins(alpha_m, alpha_s, angle_step, alpha_mode=ALPHA_MODE_A, ctx: "Context | None" = None,
+                     nalpha_rule=NALPHA_CEIL):
     """(fast, exact) alpha bins; host build of the inline functions when ctx is None, device otherwise."""
     am = np.ascontiguousarray(alpha_m, np.float32)
     as_ = np.ascontiguousarray(alpha_s, np.float32)
     fast = np.zeros(am.shape[0], np.uint32)
     exact = np.zeros(am.shape[0], np.uint32)
-    rc = lib().b200ppf_debug_alpha_bins(ctx._h if ctx else None, np.float32(angle_step), alpha_mode, _p(am), _p(as_),
-                                        am.shape[0], _p(fast), _p(exact))
+    rc = lib().b200ppf_debug_alpha_bins(ctx._h if ctx else None, np.float32(angle_step), alpha_mode, nalpha_rule, _p(am),
+                                        _p(as_), am.shape[0], _p(fast), _p(exact))
     if rc != 0:
         raise B200PPFError(rc, lib().b200ppf_last_error(ctx._h if ctx else None).decode())
     return fast, exact

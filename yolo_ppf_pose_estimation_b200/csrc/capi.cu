@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -119,6 +120,13 @@ int b200ppf_set_alpha_mode(b200ppf_ctx *ctx, int mode) {
     return B200PPF_OK;
 }
 
+int b200ppf_set_nalpha_rule(b200ppf_ctx *ctx, int rule) {
+    if (!ctx) return fail_msg(nullptr, B200PPF_ERR_INVALID, "null context");
+    if (rule < 0 || rule > 2) return fail_msg(ctx, B200PPF_ERR_INVALID, "unknown alpha-column rule");
+    ctx->nalpha_rule = rule;
+    return B200PPF_OK;
+}
+
 int b200ppf_get_device(const b200ppf_ctx *ctx) { return ctx ? ctx->device : -1; }
 void *b200ppf_get_stream(const b200ppf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t b200ppf_launch_count(const b200ppf_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -153,8 +161,7 @@ int b200ppf_cloud_upload(b200ppf_ctx *ctx, const float *host, size_t n, size_t s
     if (n && !host) return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: null host pointer");
     if (stride < 6 || noff < 3 || noff + 3 > stride)
         return fail_msg(ctx, B200PPF_ERR_INVALID, "cloud upload: stride/normal offset do not describe [x y z .. nx ny nz]");
-    // AoS -> float4 SoA staging in the context's grow-only pinned buffer, dropping NaN points
-    // (SURVEY.md A.8 rule 5)
+    // AoS -> float4 SoA staging in the context's grow-only pinned buffer, dropping non-finite points
     const size_t need = std::max<size_t>(1, 2 * n) * sizeof(float4);
     if (ctx->stage_bytes < need) {
         if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -172,8 +179,10 @@ int b200ppf_cloud_upload(b200ppf_ctx *ctx, const float *host, size_t n, size_t s
     float4 *sp = stage, *sn = stage + n;
     for (size_t i = 0; i < n; ++i) {
         const float *p = host + i * stride, *q = p + noff;
-        if (std::isnan(p[0]) || std::isnan(p[1]) || std::isnan(p[2]) || std::isnan(q[0]) || std::isnan(q[1]) ||
-            std::isnan(q[2]))
+        // non-finite rows are dropped: NaN (SURVEY.md A.8 rule 5) and +-Inf alike (depth-derived clouds carry both;
+        // an infinite coordinate would make the bounding box, and every grid sized from it, meaningless)
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2]) || !std::isfinite(q[0]) ||
+            !std::isfinite(q[1]) || !std::isfinite(q[2]))
             continue;
         sp[m] = make_float4(p[0], p[1], p[2], 1.0f);
         sn[m] = make_float4(q[0], q[1], q[2], 0.0f);
@@ -390,7 +399,7 @@ int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *off
 namespace {
 
 constexpr uint64_t TABLE_MAGIC = 0x4C42543030325042ull;  // "BP200TBL" little-endian
-constexpr uint32_t TABLE_FORMAT = 2;                      // 2: phase-sorted buckets, hot words
+constexpr uint32_t TABLE_FORMAT = 3;                      // 3: + alpha-column rule (2: phase-sorted buckets, hot words)
 
 struct TableFileHeader {
     uint64_t magic;
@@ -429,6 +438,66 @@ struct FileCloser {
     }
 };
 
+// Everything the voting kernel takes on trust from a table, re-derived from the file's own parameters and entries:
+// a file that passes cannot make the kernel read outside its arrays or add outside its accumulator slice, whoever
+// wrote it (the checksum only catches accidents).  Returns nullptr or what is wrong.
+const char *validate_table_file(const TableFileHeader &h, const std::vector<std::vector<uint32_t>> &a) {
+    const b200ppf_table_info &info = h.info;
+    const b200ppf::KeyParams &kp = h.kp;
+    if (info.n_model < 1) return "no model points";
+    if (!(info.angle_step > 0.0f) || !(info.dist_step > 0.0f) || kp.angle_step != info.angle_step || kp.dist_step != info.dist_step)
+        return "discretisation steps";
+    if (h.feature_mode > 2 || h.alpha_mode > 1 || info.nalpha_rule > 2) return "unknown mode";
+    unsigned __int128 ks = 1;
+    for (int k = 0; k < 4; ++k) {
+        if (kp.size[k] < 1 || kp.size[k] != info.size[k] || kp.lo[k] != info.lo[k]) return "key ranges";
+        ks *= (unsigned __int128)(uint32_t)kp.size[k];
+    }
+    if (ks != (unsigned __int128)info.key_space || kp.key_space != info.key_space) return "key space is not the product of the key ranges";
+    if (info.n_slices < 1 || info.slice_rows < 1 || (uint64_t)info.n_slices * info.slice_rows < info.n_model ||
+        (uint64_t)(info.n_slices - 1) * info.slice_rows >= info.n_model)
+        return "accumulator slices do not tile the model rows";
+    // the binning parameters are a function of (angle step, alpha mode, column rule); only the number of phase
+    // cells may be lower than that function's choice (large key spaces halve it)
+    b200ppf::BinParams ref = b200ppf::make_bin_params(info.angle_step, (int)h.alpha_mode, (int)info.nalpha_rule);
+    if (h.bp.cells_log2 > ref.cells_log2) return "phase cells";
+    ref.cells_log2 = h.bp.cells_log2;
+    if (ref.cells_log2 == 0) ref.bulk = 0;
+    if (memcmp(&ref, &h.bp, sizeof(ref)) != 0) return "binning parameters do not follow from the angle step";
+    if (info.n_alpha != ref.n_alpha || info.phase_cells != (1u << ref.cells_log2)) return "alpha columns";
+    const std::vector<uint32_t> &off = a[0], &sub = a[1], &ew = a[2], &eam = a[3], &ealpha = a[4], &eidx = a[5];
+    const uint64_t ne = h.n_entries, total_keys = (uint64_t)info.key_space * info.n_slices;
+    if (off.empty() || off[0] != 0 || off.back() != ne) return "bucket offsets do not cover the entries";
+    for (size_t k = 0; k + 1 < off.size(); ++k)
+        if (off[k] > off[k + 1]) return "bucket offsets decrease";
+    if (!sub.empty()) {
+        if (sub.back() != ne) return "phase-cell offsets do not cover the entries";
+        for (size_t k = 0; k + 1 < sub.size(); ++k)
+            if (sub[k] > sub[k + 1]) return "phase-cell offsets decrease";
+        for (uint64_t k = 0; k <= total_keys; ++k)
+            if (sub[k << ref.cells_log2] != off[k]) return "phase-cell offsets leave their bucket";
+    }
+    const uint64_t n = info.n_model, nn = n * n;
+    const uint32_t stride_bytes = ref.row_stride * 4u;
+    for (uint32_t slice = 0; slice < info.n_slices; ++slice) {
+        const uint64_t p0 = off[(uint64_t)slice * info.key_space], p1 = off[(uint64_t)(slice + 1) * info.key_space];
+        const uint64_t row0 = (uint64_t)slice * info.slice_rows, rows = std::min<uint64_t>(info.slice_rows, n - row0);
+        for (uint64_t p = p0; p < p1; ++p) {
+            if (eidx[p] >= nn) return "entry pair index out of range";
+            const uint64_t i = eidx[p] / n;
+            if (i < row0 || i >= row0 + rows) return "entry filed under another accumulator slice";
+            float alpha;
+            memcpy(&alpha, &ealpha[p], sizeof(float));
+            if (!(alpha >= -3.14159274f && alpha <= 3.14159274f)) return "entry alpha_m outside [-pi, pi]";
+            const uint32_t a_fix = b200ppf::alpha_to_fix(alpha), row_bytes = (uint32_t)(i - row0) * stride_bytes;
+            if (eam[p] != a_fix) return "entry fixed-point alpha_m does not match its float";
+            if (ew[p] != (ref.bulk ? b200ppf::hot_word(ref, row_bytes, b200ppf::phase_of_fix(ref, a_fix)) : row_bytes))
+                return "entry hot word does not match its pair";
+        }
+    }
+    return nullptr;
+}
+
 }  // namespace
 
 int b200ppf_table_save(b200ppf_ctx *ctx, const b200ppf_table *t, const char *path) {
@@ -460,9 +529,9 @@ int b200ppf_table_save(b200ppf_ctx *ctx, const b200ppf_table *t, const char *pat
                                           ctx->stream));
     }
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    uint64_t sum = mix_bytes(0x42323030u, &h.info, sizeof(h.info));
-    sum = mix_bytes(sum, &h.kp, sizeof(h.kp));
-    sum = mix_bytes(sum, &h.bp, sizeof(h.bp));
+    // the parameter block (info, kp, bp: everything behind the checksum field) and then the six arrays
+    uint64_t sum = mix_bytes(0x42323030u, reinterpret_cast<const char *>(&h) + offsetof(TableFileHeader, info),
+                             sizeof(h) - offsetof(TableFileHeader, info));
     for (int a = 0; a < 6; ++a) sum = mix_bytes(sum, host[a].data(), host[a].size() * sizeof(uint32_t));
     h.checksum = sum;
     FileCloser fc{fopen(path, "wb")};
@@ -491,16 +560,18 @@ int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out) 
         return fail_msg(ctx, B200PPF_ERR_STATE, "table load: the file's feature / alpha mode differs from the context's");
     const uint64_t total_keys = (uint64_t)h.info.key_space * h.info.n_slices;
     const bool sane = h.n_offsets == total_keys + 1 && total_keys < (1ull << 31) && h.bp.cells_log2 <= 8 &&
+                      (total_keys << h.bp.cells_log2) < (1ull << 31) &&
                       h.n_sub_offsets == (h.bp.cells_log2 ? (total_keys << h.bp.cells_log2) + 1 : 0) &&
-                      h.n_entries == h.info.n_entries && h.n_entries <= 0xFFFFFFFFull && h.info.n_model <= 65535 &&
+                      h.n_entries == h.info.n_entries && h.n_entries <= 0xFFFFFFFFull && h.info.n_model >= 1 &&
+                      h.info.n_model <= 65535 && h.n_entries <= h.info.n_model * h.info.n_model &&
                       h.info.n_alpha >= 1 && h.bp.n_alpha == h.info.n_alpha && h.bp.row_stride == h.info.n_alpha + 1 &&
                       h.kp.slice_rows == h.info.slice_rows && h.kp.n_slices == h.info.n_slices;
     if (!sane) return fail_msg(ctx, B200PPF_ERR_IO, "table load: inconsistent header");
     const uint64_t lengths[6] = {h.n_offsets, h.n_sub_offsets, h.n_entries, h.n_entries, h.n_entries, h.n_entries};
     std::vector<std::vector<uint32_t>> host(6);
-    uint64_t sum = mix_bytes(0x42323030u, &h.info, sizeof(h.info));
-    sum = mix_bytes(sum, &h.kp, sizeof(h.kp));
-    sum = mix_bytes(sum, &h.bp, sizeof(h.bp));
+    // the parameter block (info, kp, bp: everything behind the checksum field) and then the six arrays
+    uint64_t sum = mix_bytes(0x42323030u, reinterpret_cast<const char *>(&h) + offsetof(TableFileHeader, info),
+                             sizeof(h) - offsetof(TableFileHeader, info));
     for (int a = 0; a < 6; ++a) {
         host[a].resize(lengths[a]);
         if (lengths[a] && fread(host[a].data(), sizeof(uint32_t), lengths[a], fc.f) != lengths[a])
@@ -509,9 +580,11 @@ int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out) 
     }
     if (fgetc(fc.f) != EOF) return fail_msg(ctx, B200PPF_ERR_IO, "table load: trailing bytes");
     if (sum != h.checksum) return fail_msg(ctx, B200PPF_ERR_IO, "table load: checksum mismatch (corrupt file)");
-    // offsets must be monotone and end at n_entries: the voting kernel trusts them
-    if (host[0].back() != h.n_entries || (h.n_sub_offsets && host[1].back() != h.n_entries))
-        return fail_msg(ctx, B200PPF_ERR_IO, "table load: offsets do not cover the entries");
+    if (const char *why = validate_table_file(h, host)) {
+        char msg[200];
+        snprintf(msg, sizeof(msg), "table load: invalid table (%s)", why);
+        return fail_msg(ctx, B200PPF_ERR_IO, msg);
+    }
 
     b200ppf_table *t = new (std::nothrow) b200ppf_table();
     if (!t) return fail_msg(ctx, B200PPF_ERR_NOMEM, "table load: out of host memory");
@@ -683,19 +756,20 @@ int b200ppf_vote_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, con
     return k3_debug_accumulator(ctx, t, scene, s_r, acc);
 }
 
-int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+int b200ppf_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, int nalpha_rule, const float *alpha_m,
                              const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact) {
-    if (!(angle_step > 0.0f) || alpha_mode < 0 || alpha_mode > 1 || (n && (!alpha_m || !alpha_s || !fast || !exact)))
+    if (!(angle_step > 0.0f) || alpha_mode < 0 || alpha_mode > 1 || nalpha_rule < 0 || nalpha_rule > 2 ||
+        (n && (!alpha_m || !alpha_s || !fast || !exact)))
         return fail_msg(ctx, B200PPF_ERR_INVALID, "debug alpha bins: bad argument");
     if (n == 0) return B200PPF_OK;
-    if (!ctx) return k3_debug_alpha_bins(nullptr, angle_step, alpha_mode, alpha_m, alpha_s, n, fast, exact);
+    if (!ctx) return k3_debug_alpha_bins(nullptr, angle_step, alpha_mode, nalpha_rule, alpha_m, alpha_s, n, fast, exact);
     DeviceGuard guard(ctx->device);
-    return k3_debug_alpha_bins(ctx, angle_step, alpha_mode, alpha_m, alpha_s, n, fast, exact);
+    return k3_debug_alpha_bins(ctx, angle_step, alpha_mode, nalpha_rule, alpha_m, alpha_s, n, fast, exact);
 }
 
 int b200ppf_microbench_atoms(b200ppf_ctx *ctx, int pattern, double *atoms_per_sec) {
     CHECK_CTX(ctx);
-    if (!atoms_per_sec || pattern < 0 || pattern > 2) return fail_msg(ctx, B200PPF_ERR_INVALID, "microbench: bad argument");
+    if (!atoms_per_sec || pattern < 0 || pattern > 15) return fail_msg(ctx, B200PPF_ERR_INVALID, "microbench: bad argument");
     return microbench_atoms(ctx, pattern, atoms_per_sec);
 }
 
@@ -714,12 +788,10 @@ int b200ppf_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_host, size_
     if (!poses16 || !votes || !n_out || (n && !hyps_host)) return fail_msg(ctx, B200PPF_ERR_INVALID, "cluster: null argument");
     *n_out = 0;
     if (n == 0) return B200PPF_OK;
-    b200ppf_hypothesis *d = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&d, n * sizeof(b200ppf_hypothesis), ctx->stream));
+    StreamBuf<b200ppf_hypothesis> d(ctx);
+    PPF_CUDA(ctx, d.alloc(n));
     PPF_CUDA(ctx, cudaMemcpyAsync(d, hyps_host, n * sizeof(b200ppf_hypothesis), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = k4_cluster(ctx, d, n, pos_thr, rot_thr, poses16, votes, n_out);
-    cudaFreeAsync(d, ctx->stream);
-    return rc;
+    return k4_cluster(ctx, d, n, pos_thr, rot_thr, poses16, votes, n_out);
 }
 
 int b200ppf_cluster_assignment(b200ppf_ctx *ctx, uint32_t *assignment, size_t n, size_t *n_clusters) {
@@ -927,7 +999,7 @@ int b200ppf_match_object(b200ppf_ctx *ctx, const b200ppf_cloud *scene, const flo
     res->n_filtered = (uint32_t)object.c->n;
     if ((rc = b200ppf_normal_estimation(ctx, object.c, p.normal_k, nullptr, B200PPF_COVARIANCE_SHIFTED))) return rc;
     res->normals_ms = ctx->timings.prep_ms;
-    if (p.edge_curvature > 0.0f) {
+    if (p.edge_curvature > 0.0f && edges_out) {  // the edge cloud does not enter the PCL matching: extracted on request only
         if ((rc = b200ppf_curvature_edges(ctx, object.c, p.edge_curvature, &edges.c))) return rc;
         res->edges_ms = ctx->timings.prep_ms;
         res->n_edges = (uint32_t)edges.c->n;

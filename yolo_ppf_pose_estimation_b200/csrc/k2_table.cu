@@ -344,7 +344,8 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     info.n_model = n;
     info.angle_step = angle_step;
     info.dist_step = dist_step;
-    info.n_alpha = (uint32_t)std::floor(2.0 * M_PI / (double)angle_step);
+    info.n_alpha = num_alpha_bins(angle_step, ctx->nalpha_rule);
+    info.nalpha_rule = (uint32_t)ctx->nalpha_rule;
     if (info.n_alpha == 0) {
         delete t;
         return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: angle step larger than 2*pi");
@@ -352,7 +353,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     // accumulator slices: rows per slice bounded by the shared-memory budget of the voting kernel
     {
         size_t budget = k3_accumulator_budget(ctx);
-        // rows are n_alpha + 1 words wide (PCL's out-of-range bin gets its own cell)
+        // rows are n_alpha + 1 words wide (the spare cell takes bins past the last column)
         size_t rows_max = budget / (((size_t)info.n_alpha + 1) * sizeof(uint32_t));
         if (rows_max == 0) {
             delete t;
@@ -422,7 +423,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         kp.lo[3] = 0;
         kp.size[3] = (int)std::floor(diag / dist_step) + 2;
     }
-    t->bp = make_bin_params(angle_step, ctx->alpha_mode);
+    t->bp = make_bin_params(angle_step, ctx->alpha_mode, ctx->nalpha_rule);
     {
         unsigned __int128 ks = 1;
         for (int k = 0; k < 4; ++k) ks *= (unsigned __int128)(uint32_t)kp.size[k];
@@ -454,7 +455,10 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
 
     // ---- keys ---------------------------------------------------------------------------------
     uint32_t *keys[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr}, *alp[2] = {nullptr, nullptr};
+    unsigned long long *d_cnt = nullptr;
     auto cleanup = [&]() {
+        if (d_cnt) cudaFreeAsync(d_cnt, ctx->stream);
+        d_cnt = nullptr;
         for (int b = 0; b < 2; ++b) {
             if (keys[b]) cudaFreeAsync(keys[b], ctx->stream);
             if (idx[b]) cudaFreeAsync(idx[b], ctx->stream);
@@ -550,7 +554,6 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     K2_CUDA(cudaMemsetAsync(t->entry_am + n_entries, 0, ENTRY_PAD * sizeof(uint32_t), ctx->stream));
     K2_CUDA(cudaMalloc(&t->entry_idx, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
     K2_CUDA(cudaMalloc(&t->entry_alpha, std::max<size_t>(1, n_entries) * sizeof(float)));
-    unsigned long long *d_cnt = nullptr;
     K2_CUDA(cudaMallocAsync(&d_cnt, sizeof(unsigned long long), ctx->stream));
     K2_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
     {
@@ -584,7 +587,6 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     K2_CUDA(cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ctx->ev[3], ctx->stream);
     K2_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_cnt, ctx->stream);
     if (h_range[10] != 0) {
         cleanup();
         b200ppf_table_free(t);

@@ -135,7 +135,7 @@ __device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_add
                                            float alpha_s, uint32_t &skipped) {
     const uint32_t bin = MODE == ALPHA_MODE_B
                              ? alpha_bin_fast(bp, alpha_m, alpha_s)
-                             : alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
+                             : alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
     if (bin == 0xFFFFFFFFu) ++skipped;  // NaN alpha: no vote
     else red_shared_inc(acc_addr + ((rowoff + bin) << 2));
 }
@@ -407,12 +407,13 @@ ppf_vote_kernel(const VoteArgs a) {
     flush();
 
     // ---- peak: first maximum in (i, bin) order == max of (votes, ~flat) ---------------------------
-    // one thread per model row: fold PCL's out-of-range bin n_alpha into n_alpha - 1, then scan the row
+    // one thread per model row: the spare cell n_alpha (bins past the last column) joins column n_alpha - 1 under
+    // the FLOOR_CLAMP rule and is ignored otherwise (FLOOR_DROP: the vote is lost; CEIL: it stays empty)
     const uint32_t n_alpha = a.bp.n_alpha;
     unsigned long long best = 0;
     for (uint32_t r = tid; r < rows; r += THREADS) {
         uint32_t *row = acc + r * stride;
-        row[n_alpha - 1] += row[n_alpha];
+        if (a.bp.fold) row[n_alpha - 1] += row[n_alpha];
         uint32_t bv = 0, bc = 0;
         for (uint32_t c = 0; c < n_alpha; ++c) {
             const uint32_t v = row[c];
@@ -536,7 +537,7 @@ __global__ void debug_alpha_bins_kernel(BinParams bp, const float *__restrict__ 
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     fast[p] = alpha_bin_phase(bp, am[p], as[p]);
-    exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, am[p], as[p]);
+    exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, bp.overflow_bin, am[p], as[p]);
 }
 
 size_t accumulator_bytes(const b200ppf_table *t) {
@@ -561,12 +562,14 @@ float radius_sq_bound(float r) {
 int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_first,
                 size_t ref_step, size_t ref_count, uint32_t *acc_dump) {
     const float radius = t->info.max_dist * 0.5f;
-    SceneGrid grid;
+    struct GridOwner {  // the grid goes back to the pool on every return path, the launch macros' error returns included
+        b200ppf_ctx *ctx;
+        SceneGrid g;
+        ~GridOwner() { scene_grid_free(ctx, &g); }
+    } owner{ctx, SceneGrid()};
+    SceneGrid &grid = owner.g;
     int rc = scene_grid_build(ctx, scene, radius, &grid);
-    if (rc) {
-        scene_grid_free(ctx, &grid);
-        return rc;
-    }
+    if (rc) return rc;
     VoteArgs a;
     a.pos = scene->pos;
     a.nrm = scene->nrm;
@@ -615,7 +618,6 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
 #undef LAUNCH_VOTE_T
 #undef LAUNCH_VOTE
     cudaEventRecord(ctx->ev_vote[2], ctx->stream);
-    scene_grid_free(ctx, &grid);
     return B200PPF_OK;
 }
 
@@ -647,11 +649,19 @@ int check_vote_inputs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cl
 
 }  // namespace
 
-BinParams make_bin_params(float angle_step, int alpha_mode) {
+uint32_t num_alpha_bins(float angle_step, int nalpha_rule) {
+    const double t = 2.0 * M_PI / (double)angle_step;
+    return (uint32_t)(nalpha_rule == NALPHA_CEIL ? ceil(t) : floor(t));
+}
+
+BinParams make_bin_params(float angle_step, int alpha_mode, int nalpha_rule) {
     BinParams bp;
     bp.angle_step = angle_step;
     bp.inv_step = 1.0f / angle_step;
-    bp.n_alpha = (uint32_t)floor(2.0 * M_PI / (double)angle_step);
+    bp.n_alpha = num_alpha_bins(angle_step, nalpha_rule);
+    bp.nalpha_rule = nalpha_rule;
+    bp.overflow_bin = nalpha_rule == NALPHA_FLOOR_DROP ? bp.n_alpha : bp.n_alpha - 1;
+    bp.fold = nalpha_rule == NALPHA_FLOOR_CLAMP ? 1u : 0u;
     bp.mode = alpha_mode;
     bp.mode_b_offset = (int)floor(M_PI / (double)angle_step);
     bp.guard = std::max(2e-4f, 1e-5f * bp.inv_step);
@@ -698,13 +708,13 @@ BinParams make_bin_params(float angle_step, int alpha_mode) {
     return bp;
 }
 
-int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, int nalpha_rule, const float *alpha_m,
                         const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact) {
-    const BinParams bp = make_bin_params(angle_step, alpha_mode);
+    const BinParams bp = make_bin_params(angle_step, alpha_mode, nalpha_rule);
     if (!ctx) {  // host build of the same inline functions
         for (size_t p = 0; p < n; ++p) {
             fast[p] = alpha_bin_phase(bp, alpha_m[p], alpha_s[p]);
-            exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, alpha_m[p], alpha_s[p]);
+            exact[p] = alpha_bin_exact(bp.mode, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m[p], alpha_s[p]);
         }
         return B200PPF_OK;
     }
@@ -789,14 +799,13 @@ int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf
     rc = ensure_vote_scratch(ctx, 1);
     if (rc) return rc;
     const size_t len = (size_t)t->info.n_model * t->info.n_alpha;
-    uint32_t *d_acc = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&d_acc, len * sizeof(uint32_t), ctx->stream));
+    StreamBuf<uint32_t> d_acc(ctx);
+    PPF_CUDA(ctx, d_acc.alloc(len));
     PPF_CUDA(ctx, cudaMemsetAsync(d_acc, 0, len * sizeof(uint32_t), ctx->stream));
     rc = launch_vote(ctx, t, scene, s_r, 1, 1, d_acc);
     if (rc) return rc;
     PPF_CUDA(ctx, cudaMemcpyAsync(acc, d_acc, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_acc, ctx->stream);
     return B200PPF_OK;
 }
 

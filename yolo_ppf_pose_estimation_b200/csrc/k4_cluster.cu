@@ -428,8 +428,9 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
                  o_lid = take(n), o_as = take(n), o_cv = take(n), o_cs = take(n), o_cell = take((size_t)n_cells + 1),
                  o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12),
                  o_lcnt = take(n_cells);
-    uint32_t *pool = nullptr;
-    PPF_CUDA(ctx, cudaMallocAsync(&pool, words * sizeof(uint32_t), st));
+    StreamBuf<uint32_t> pool_owner(ctx);  // returned to the pool on every path out of this function
+    PPF_CUDA(ctx, pool_owner.alloc(words));
+    uint32_t *pool = pool_owner.p;
     keys[0] = pool + o_keys0; keys[1] = pool + o_keys1; order[0] = pool + o_ord0; order[1] = pool + o_ord1;
     ckeys[0] = pool + o_ck0; ckeys[1] = pool + o_ck1; crank[0] = pool + o_cr0; crank[1] = pool + o_cr1;
     votes = pool + o_votes; state = pool + o_state; leader_id = pool + o_lid; assign_sorted = pool + o_as;
@@ -441,11 +442,12 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     // state .. cl_size are contiguous: one memset clears state (UNDECIDED), leader ids, assignments, cluster sums
     PPF_CUDA(ctx, cudaMemsetAsync(state, 0, (o_cell - o_state) * sizeof(uint32_t), st));
     PPF_CUDA(ctx, cudaMemsetAsync(small, 0, (16 + 48) * sizeof(uint32_t), st));
-    if (ctx->assign_n < n) {
+    if (ctx->assign_cap < n) {
         if (ctx->d_assign) cudaFree(ctx->d_assign);
         ctx->d_assign = nullptr;
-        ctx->assign_n = 0;
+        ctx->assign_cap = ctx->assign_n = 0;
         PPF_CUDA(ctx, cudaMalloc(&ctx->d_assign, n * sizeof(uint32_t)));
+        ctx->assign_cap = n;
     }
     ctx->assign_n = n;
 
@@ -514,7 +516,6 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
         ++k;
     }
     *n_out = k;
-    cudaFreeAsync(pool, st);
     return B200PPF_OK;
 }
 

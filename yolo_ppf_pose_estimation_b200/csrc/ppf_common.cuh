@@ -28,6 +28,7 @@ struct b200ppf_ctx {
     cudaStream_t stream = nullptr;
     int feature_mode = B200PPF_FEATURE_PCL_PFH;
     int alpha_mode = B200PPF_ALPHA_MODE_A;
+    int nalpha_rule = B200PPF_NALPHA_CEIL;
     int sm_count = 148;
     size_t smem_optin = 0;
     std::string error;
@@ -44,7 +45,8 @@ struct b200ppf_ctx {
     size_t hyps_cap = 0;
     // cluster scratch of the last cluster call
     uint32_t *d_assign = nullptr;  // cluster creation index per hypothesis (input order)
-    size_t assign_n = 0;
+    size_t assign_n = 0;    // hypotheses of the last cluster call
+    size_t assign_cap = 0;  // capacity of d_assign
     uint32_t n_clusters = 0;
     // grow-only pinned staging buffer of cloud uploads
     void *stage = nullptr;
@@ -104,6 +106,26 @@ int fail_msg(b200ppf_ctx *ctx, int code, const char *msg);
         PPF_CUDA(ctx, cudaGetLastError());                                         \
     } while (0)
 
+// stream-ordered scratch buffer, returned to the pool when it leaves scope — also on the early error returns
+template <typename T>
+struct StreamBuf {
+    b200ppf_ctx *ctx;
+    T *p = nullptr;
+    explicit StreamBuf(b200ppf_ctx *c) : ctx(c) {}
+    StreamBuf(const StreamBuf &) = delete;
+    StreamBuf &operator=(const StreamBuf &) = delete;
+    ~StreamBuf() {
+        if (p) cudaFreeAsync(p, ctx->stream);
+    }
+    cudaError_t alloc(size_t count) { return cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), ctx->stream); }
+    T *release() {
+        T *r = p;
+        p = nullptr;
+        return r;
+    }
+    operator T *() const { return p; }
+};
+
 // ---- stage entry points implemented in the k*.cu files (host functions) ----------------------
 int k1_features_compute(b200ppf_ctx *ctx, const b200ppf_cloud *model, b200ppf_signature *out);
 int k2_build(b200ppf_ctx *ctx, const b200ppf_features *f, const b200ppf_cloud *model, float angle_step,
@@ -118,9 +140,10 @@ int k3_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud
                    uint8_t *in_radius, int32_t *d4, float *alpha_s);
 int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
                          uint32_t *acc);
-int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, const float *alpha_m,
+int k3_debug_alpha_bins(b200ppf_ctx *ctx, float angle_step, int alpha_mode, int nalpha_rule, const float *alpha_m,
                          const float *alpha_s, size_t n, uint32_t *fast, uint32_t *exact);
-BinParams make_bin_params(float angle_step, int alpha_mode);
+BinParams make_bin_params(float angle_step, int alpha_mode, int nalpha_rule);
+uint32_t num_alpha_bins(float angle_step, int nalpha_rule);
 int microbench_atoms(b200ppf_ctx *ctx, int pattern, double *atoms_per_sec);
 int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps_device, size_t n, float pos_thr, float rot_thr,
                float *poses16, uint32_t *votes, size_t *n_out);

@@ -30,6 +30,11 @@ __host__ __device__ __forceinline__ float norm3(V3 a) { return sqrtf(dot3(a, a))
 
 enum { FEATURE_PCL_PFH = 0, FEATURE_DROST_COS = 1, FEATURE_DROST_ANGLE = 2 };
 enum { ALPHA_MODE_A = 0, ALPHA_MODE_B = 1 };
+// How many alpha columns the accumulator has and what becomes of a vote whose bin is past the last one
+// (include/b200ppf.h B200PPF_NALPHA_*): CEIL = ceil(2*pi/step) columns (no such vote exists for PCL's 12
+// degrees), FLOOR_DROP = floor(2*pi/step) columns, the vote is lost (PCL <= 1.11 increments one word past the
+// row's heap block), FLOOR_CLAMP = floor columns, the vote joins the last column (this library's round 1).
+enum { NALPHA_CEIL = 0, NALPHA_FLOOR_DROP = 1, NALPHA_FLOOR_CLAMP = 2 };
 
 // computePairFeatures ([PCL] features/src/pfh.cpp).  f = {f1,f2,f3,f4}.
 __host__ __device__ __forceinline__ bool pair_features_pfh(V3 p1, V3 n1, V3 p2, V3 n2, float *f) {
@@ -156,9 +161,10 @@ __host__ __device__ __forceinline__ float planar_alpha(const Frame &F, V3 m) {
 
 // ---- alpha binning ([PCL] impl/ppf_registration.hpp, voting loop) ---------------------------
 
-// literal form: float subtract, double wrap / divide / floor.  Returns 0xFFFFFFFF for NaN.
+// literal form: float subtract, double wrap / divide / floor.  Returns 0xFFFFFFFF for NaN.  A bin past the last
+// column becomes overflow_bin: n_alpha - 1 (clamp) or n_alpha (the spare cell every accumulator row carries).
 __host__ __device__ __forceinline__ uint32_t alpha_bin_exact(int mode, float angle_step, uint32_t n_alpha,
-                                                             float alpha_m, float alpha_s) {
+                                                             uint32_t overflow_bin, float alpha_m, float alpha_s) {
     const double PI_D = 3.14159265358979323846;
     float alpha = alpha_m - alpha_s;
     if (alpha != alpha) return 0xFFFFFFFFu;
@@ -175,7 +181,7 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_exact(int mode, float ang
         double b = floor(((double)alpha + PI_D) / (double)angle_step);
         bin = b < 0.0 ? 0u : (uint32_t)b;
     }
-    if (bin >= n_alpha) bin = n_alpha - 1;
+    if (bin >= n_alpha) bin = overflow_bin;
     return bin;
 }
 
@@ -188,11 +194,14 @@ struct BinParams {
     float angle_step;
     float inv_step;
     uint32_t n_alpha;
+    uint32_t overflow_bin;  // where a bin >= n_alpha goes: n_alpha - 1 (CEIL, FLOOR_CLAMP) or the spare cell n_alpha (FLOOR_DROP)
+    uint32_t fold;          // FLOOR_CLAMP: the spare cell is added to column n_alpha - 1 before the peak scan
+    int nalpha_rule;
     int mode;
     int mode_b_offset;  // floor(pi / angle_step)
     float guard;        // max(2e-4, 1e-5 / angle_step): > 20x the fp32 estimate's error bound
     // fixed-point form of the hot loop (alpha_bin_fixed below)
-    uint32_t row_stride;   // accumulator row stride = n_alpha + 1 (PCL's out-of-range bin n_alpha gets a cell, merged later)
+    uint32_t row_stride;   // accumulator row stride = n_alpha + 1: the spare cell n_alpha takes the bins past the last column
     uint32_t fix_mul;      // round(T * 2^fix_shift), T = 2*pi/angle_step bins per turn
     uint32_t fix_shift;    // fractional bits of fix_mul: high word of X*fix_mul = bin . (fix_shift-bit position inside the bin)
     uint32_t frac_mul;     // 2^(32 - fix_shift): a second multiply splits that word into (bin, position << (32-fix_shift))
@@ -285,7 +294,7 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_fast(const BinParams &bp,
         if (d != d) return 0xFFFFFFFFu;
         int b = (int)floorf(d) + bp.mode_b_offset;
         uint32_t bin = b < 0 ? 0u : (uint32_t)b;
-        return bin >= bp.n_alpha ? bp.n_alpha - 1 : bin;
+        return bin >= bp.n_alpha ? bp.overflow_bin : bin;
     }
     float w = d;
     // (double)d < -pi  <=>  d <= -3.14159274f (= float(pi), just beyond pi); same on the + side
@@ -295,10 +304,10 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_fast(const BinParams &bp,
     float fl = floorf(q);
     float fr = q - fl;
     if (!(fr > bp.guard && fr < 1.0f - bp.guard))  // also catches NaN
-        return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
+        return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
     if (fl < 0.0f) return 0u;  // only reachable for |alpha_m - alpha_s| > 3*pi; same as the literal form
     uint32_t bin = (uint32_t)(int)fl;
-    return bin >= bp.n_alpha ? bp.n_alpha - 1 : bin;
+    return bin >= bp.n_alpha ? bp.overflow_bin : bin;
 }
 
 // what the voting kernel computes for one vote (mode A: fixed-point estimate, literal form inside
@@ -310,10 +319,10 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_hot(const BinParams &bp, 
     // the fixed-point form holds one turn: both angles must be atan2f results (|a| <= float(pi)), which
     // is what the table and the scene frames produce; anything else takes the literal form
     if (!(fabsf(alpha_m) <= 3.14159274f && fabsf(alpha_s) <= 3.14159274f))
-        return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
+        return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
     const uint32_t b = alpha_bin_fixed(bp, alpha_to_fix(alpha_m), alpha_to_fix(alpha_s) - 0x80000000u);
-    if (b == 0xFFFFFFFFu) return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, alpha_m, alpha_s);
-    return b >= bp.n_alpha ? bp.n_alpha - 1 : b;
+    if (b == 0xFFFFFFFFu) return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
+    return b >= bp.n_alpha ? bp.overflow_bin : b;
 }
 
 // what the voting kernel computes for one (entry, scene pair) of a phase-sorted table: the
@@ -335,7 +344,7 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_phase(const BinParams &bp
     const uint32_t t = w - cst, t2 = t + bp.wrap_add;
     const uint32_t addr = (t > t2 ? t : t2) & ((1u << bp.low_bits) - 1u);
     const uint32_t b = (addr - base) >> 2;
-    return b >= bp.n_alpha ? bp.n_alpha - 1 : b;
+    return b >= bp.n_alpha ? bp.overflow_bin : b;
 }
 
 __host__ __device__ __forceinline__ float peak_theta(int mode, float angle_step, uint32_t bin) {

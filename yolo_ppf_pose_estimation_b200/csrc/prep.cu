@@ -36,21 +36,6 @@ namespace {
 
 constexpr int SCAN_BLOCK = 1024;
 
-// stream-ordered scratch buffer, returned to the pool when it leaves scope — also on the early error returns
-template <typename T>
-struct StreamBuf {
-    b200ppf_ctx *ctx;
-    T *p = nullptr;
-    explicit StreamBuf(b200ppf_ctx *c) : ctx(c) {}
-    StreamBuf(const StreamBuf &) = delete;
-    StreamBuf &operator=(const StreamBuf &) = delete;
-    ~StreamBuf() {
-        if (p) cudaFreeAsync(p, ctx->stream);
-    }
-    cudaError_t alloc(size_t count) { return cudaMallocAsync(&p, std::max<size_t>(1, count) * sizeof(T), ctx->stream); }
-    operator T *() const { return p; }
-};
-
 // an output cloud under construction: freed unless released to the caller
 struct CloudOwner {
     b200ppf_cloud *c = nullptr;

@@ -68,11 +68,16 @@ uint32_t scene_grid_params(const float *bbox_min, const float *bbox_max, float r
     // cell edge: the search radius plus a margin that absorbs the rounding of the cell coordinate
     double cell = (radius > 0.0f ? (double)radius : 1e-3) * 1.001;
     double ext[3];
-    for (int k = 0; k < 3; ++k) ext[k] = std::max(0.0, (double)bbox_max[k] - (double)bbox_min[k]);
-    for (;;) {
+    for (int k = 0; k < 3; ++k) {
+        ext[k] = std::max(0.0, (double)bbox_max[k] - (double)bbox_min[k]);
+        if (!std::isfinite(ext[k]) || !std::isfinite((double)bbox_min[k])) return 0;  // no grid over a non-finite box
+    }
+    if (!std::isfinite(cell)) return 0;
+    for (int guard = 0;; ++guard) {
         double cells = 1.0;
         for (int k = 0; k < 3; ++k) cells *= std::floor(ext[k] / cell) + 1.0;
         if (cells <= (double)MAX_CELLS) break;
+        if (guard > 400) return 0;  // 1.26^400 exceeds any finite extent: unreachable for finite input
         cell *= 1.26;  // coarser cells stay correct (a superset of candidates), just less selective
     }
     for (int k = 0; k < 3; ++k) {
@@ -88,31 +93,32 @@ int scene_grid_build(b200ppf_ctx *ctx, const b200ppf_cloud *scene, float radius,
     const uint32_t n = (uint32_t)scene->n;
     GridParams &g = out->gp;
     out->n_cells = scene_grid_params(scene->bbox_min, scene->bbox_max, radius, &g);
+    if (out->n_cells == 0) return fail_msg(ctx, B200PPF_ERR_INVALID, "scene grid: the cloud's bounding box or the search radius is not finite");
 
-    uint32_t *ids[2] = {nullptr, nullptr}, *ord[2] = {nullptr, nullptr};
-    for (int b = 0; b < 2; ++b) {
-        PPF_CUDA(ctx, cudaMallocAsync(&ids[b], std::max(1u, n) * sizeof(uint32_t), ctx->stream));
-        PPF_CUDA(ctx, cudaMallocAsync(&ord[b], std::max(1u, n) * sizeof(uint32_t), ctx->stream));
-    }
+    // scratch leaves with the scope on every path; the grid's own arrays are the caller's to free (scene_grid_free,
+    // also after a failure)
+    StreamBuf<uint32_t> ids0(ctx), ids1(ctx), ord0(ctx), ord1(ctx);
+    PPF_CUDA(ctx, ids0.alloc(n));
+    PPF_CUDA(ctx, ids1.alloc(n));
+    PPF_CUDA(ctx, ord0.alloc(n));
+    PPF_CUDA(ctx, ord1.alloc(n));
     PPF_CUDA(ctx, cudaMallocAsync(&out->cell_start, ((size_t)out->n_cells + 1) * sizeof(uint32_t), ctx->stream));
     PPF_CUDA(ctx, cudaMallocAsync(&out->pos, std::max(1u, n) * sizeof(float4), ctx->stream));
     PPF_CUDA(ctx, cudaMallocAsync(&out->nrm, std::max(1u, n) * sizeof(float4), ctx->stream));
     const unsigned gb = (n + 255) / 256;
     bool in_alt = false;
     if (n) {
-        PPF_LAUNCH(ctx, grid_cell_ids_kernel, gb, 256, 0, scene->pos, n, g, ids[0]);
+        PPF_LAUNCH(ctx, grid_cell_ids_kernel, gb, 256, 0, scene->pos, n, g, ids0.p);
         int bits = 1;
         while ((1u << bits) < out->n_cells) ++bits;
-        int rc = radix_sort_u32(ctx, ids[0], ids[1], ord[0], ord[1], nullptr, nullptr, n, bits, /*v0_iota=*/true, &in_alt);
+        int rc = radix_sort_u32(ctx, ids0, ids1, ord0, ord1, nullptr, nullptr, n, bits, /*v0_iota=*/true, &in_alt);
         if (rc) return rc;
     }
-    const int s = in_alt ? 1 : 0;
-    PPF_LAUNCH(ctx, grid_offsets_kernel, (out->n_cells + 1 + 255) / 256, 256, 0, ids[s], n, out->n_cells, out->cell_start);
-    if (n) PPF_LAUNCH(ctx, grid_gather_kernel, gb, 256, 0, scene->pos, scene->nrm, ord[s], n, out->pos, out->nrm);
-    out->orig = ord[s];  // sorted position -> original scene index
-    cudaFreeAsync(ord[1 - s], ctx->stream);
-    cudaFreeAsync(ids[0], ctx->stream);
-    cudaFreeAsync(ids[1], ctx->stream);
+    const uint32_t *ids_sorted = in_alt ? ids1.p : ids0.p;
+    const uint32_t *ord_sorted = in_alt ? ord1.p : ord0.p;
+    PPF_LAUNCH(ctx, grid_offsets_kernel, (out->n_cells + 1 + 255) / 256, 256, 0, ids_sorted, n, out->n_cells, out->cell_start);
+    if (n) PPF_LAUNCH(ctx, grid_gather_kernel, gb, 256, 0, scene->pos, scene->nrm, ord_sorted, n, out->pos, out->nrm);
+    out->orig = in_alt ? ord1.release() : ord0.release();  // sorted position -> original scene index
     return B200PPF_OK;
 }
 
