@@ -18,11 +18,15 @@ separately (table_build_ms), not inside the step.
             scene + table resident in HBM, per-step CUDA events on the context stream, max over ranks
   e2e       the same through the host-buffer C ABI: every step uploads the scene from pinned host
             memory, runs align and reads the poses back
-  roofline  the voting kernel: algorithmic bytes / its CUDA-event duration vs measured HBM
-  cpu_baseline  the CPU oracle (port of PCL's loop, 1 thread = PCL as shipped) on a bounded sample
+  roofline  the voting kernel against what binds it — the SM's L1 data pipe: one shared-memory reduction per vote.
+            achieved = votes / s inside the kernel (CUDA events on the context stream), peak = the rate of the same
+            loop shape (one coalesced 4-byte gather + one red.shared per vote) with conflict-free addresses, measured
+            live by csrc/microbench.cu; HBM bytes per launch (ncu) are reported as `traffic`, L2 bandwidth beside it
+  cpu_baseline  the CPU oracle (port of PCL's loop) on a fixed, bounded sample of reference points, all host cores
 
---impl reference times the CPU oracle with every host thread on the same workload (bounded sample
-of reference points per step).  The oracle is test infrastructure: it is only ever the baseline here.
+--impl reference times the CPU oracle with every host core on the same workload: each step votes on the next few
+entries of a FIXED list of 64 evenly spread reference points (the same points on every box and at every --gpus)
+and clusters them.  The oracle is test infrastructure: it is only ever the baseline here.
 """
 from __future__ import annotations
 
@@ -163,73 +167,99 @@ def oracle_table(wl, model=None):
     return ob, hm
 
 
-def cpu_sample_refs(wl, n_sample):
-    """Evenly spread sample of reference slots (same refs every run)."""
-    n_sample = max(1, min(n_sample, wl.n_ref))
-    step = max(1, wl.n_ref // n_sample)
-    return 0, step * wl.ref_rate, n_sample
+def host_threads():
+    """Cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
-def pick_cpu_sample(hm, wl, threads, budget_s, requested):
-    """Bounded sample of reference points whose pass takes about budget_s seconds on `threads` threads.
-    The per-reference cost spans 10 ms (bottle) to tens of seconds (10 000-point model, dense spots), so
-    the size is calibrated by timed passes over geometrically growing spread samples."""
+SAMPLE_SLOTS = 64
+
+
+def sample_list(wl):
+    """The fixed CPU sample of a workload: 64 reference slots spread evenly over the scene (slot k sits in the middle
+    of the k-th 64th), listed in bit-reversed order so that every prefix — and every run of consecutive entries — is
+    itself evenly spread.  Scene arrays are grouped by surface (object, ground, walls, clutter), so an even spread is
+    a stratified sample.  Returns reference-point indices into the scene."""
+    n = min(SAMPLE_SLOTS, wl.n_ref)
+    bits = max(1, (n - 1).bit_length())
+    order = [int(format(k, f"0{bits}b")[::-1], 2) for k in range(1 << bits)]
+    order = [k for k in order if k < n]
+    return [int((k + 0.5) * wl.n_ref / n) * wl.ref_rate for k in order]
+
+
+# votes one reference point costs on average (measured on the B200 arm; only used to size a CPU step)
+VOTES_PER_REF = {"c1": 1.0e5, "c2": 1.7e5, "c2_5mm": 2.2e6, "c3": 8.1e7, "c3s": 1.3e6, "c4": 8.1e6, "c4s": 8.1e6}
+
+
+def refs_per_cpu_step(wl, threads, requested, models=1, seconds=4.0):
+    """reference points one CPU step votes on: about `seconds` of work at ~1.1e6 votes/s per thread, 1 .. 64"""
     if requested:
-        return cpu_sample_refs(wl, requested)
-    cap = min(4096, wl.n_ref)
-    n = min(cap, max(4, threads))
-    while True:
-        f0, st0, cnt = cpu_sample_refs(wl, n)
-        t0 = time.perf_counter()
-        hm.vote(wl.model, wl.scene, f0, st0, cnt, n_threads=threads)
-        dt = max(time.perf_counter() - t0, 1e-4)
-        # one thread: stop growing early — a single reference point on the object of the 10 000-point model costs
-        # minutes there, and a larger spread sample is likelier to meet one
-        if dt >= (0.25 if threads > 1 else 0.1) * budget_s or n >= cap:
-            break
-        n = min(cap, max(2 * n, int(0.4 * budget_s / dt * n)))  # headroom: a larger sample meets costlier points
-    if dt > budget_s:  # even the smallest sample overshoots: shrink proportionally
-        n = max(1, int(n * budget_s / dt))
-    return cpu_sample_refs(wl, n)
+        return max(1, min(requested, SAMPLE_SLOTS, wl.n_ref))
+    per_ref = VOTES_PER_REF.get(wl.name, 1e6) * models / (1.1e6 * threads)
+    return int(max(1, min(SAMPLE_SLOTS, wl.n_ref, round(seconds / per_ref))))
+
+
+def vote_refs(hm, wl, model, refs, threads):
+    """the oracle's voting loop on an explicit list of reference points -> (hypotheses, counters)"""
+    return hm.vote_refs(model, wl.scene, refs, n_threads=threads)
+
+
+def workload_config(wl, gpus):
+    """`config` of the JSON line: the workload only — identical in the B200 arm and the reference arm"""
+    m = wl.library()[0]
+    return {"workload": f"{wl.name}: {wl.description}", "n_model": int(m.shape[0]), "models": len(wl.library()),
+            "n_scene": int(wl.scene.shape[0]), "n_ref": int(wl.n_ref), "ref_rate": int(wl.ref_rate), "angle_step_deg": 12,
+            "dist_step": float(wl.dist_step), "alpha_columns": "ceil(2*pi/step) = 30 (current PCL)", "gpus": int(gpus),
+            "l2": "B200 arm: 256 MiB memset between steps, outside the per-step CUDA-event brackets; CPU arm: n/a"}
 
 
 def run_reference(args, wl):
-    """The reference arm: CPU oracle, all host threads, bounded sample of reference points per step."""
+    """The reference arm: CPU oracle, all host cores, a fixed rotating sample of reference points."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     library = wl.library()
     tables = [oracle_table(wl, m) for m in library]
-    ob, hm = tables[0]
-    threads = ob.max_threads()
-    # the whole --steps K --warmup W run should end within a few minutes: ~100 s of voting in total (the CPU build of
-    # the 10 000-point model's table adds two to three minutes before that)
-    first, step, count = pick_cpu_sample(hm, wl, threads, 100.0 / (args.warmup + args.steps) / len(library), args.cpu_sample)
-    times, pairs, votes = [], 0, 0
+    ob = tables[0][0]
+    threads = host_threads()
+    refs_all = sample_list(wl)
+    per_step = refs_per_cpu_step(wl, threads, args.cpu_sample, len(library))
+    times, pairs, votes, used = [], 0, 0, []
     for k in range(args.warmup + args.steps):
+        refs = [refs_all[(k * per_step + j) % len(refs_all)] for j in range(per_step)]
         t0 = time.perf_counter()
         step_pairs = step_votes = 0
         for m, (_, hm_k) in zip(library, tables):
-            hyps, st = hm_k.vote(m, wl.scene, first, step, count, n_threads=threads)
+            hyps, st = vote_refs(hm_k, wl, m, refs, threads)
             ob.cluster(hyps, wl.pos_thr, wl.rot_thr)
             step_pairs += st["pairs_in_radius"]
             step_votes += st["votes"]
         dt = time.perf_counter() - t0
         if k >= args.warmup:
             times.append(dt)
-            pairs, votes = step_pairs, step_votes
-    ms = 1e3 * float(np.mean(times))
-    value = pairs / (ms * 1e-3)
-    sample = (f"{count} of {wl.n_ref} reference points per step (every {step // wl.ref_rate}-th), full scene, vote + cluster"
+            pairs += step_pairs
+            votes += step_votes
+            used += refs
+    total_s = float(np.sum(times))
+    ms = 1e3 * total_s / args.steps
+    value = pairs / total_s
+    n_used = len(set(used))
+    sample = (f"{per_step} reference point(s) per step from a fixed list of {len(refs_all)} evenly spread ones (bit-reversed order, "
+              f"{n_used} distinct points over the {args.steps} timed steps), full scene, vote + cluster"
               + (f", for each of the {len(library)} models" if len(library) > 1 else ""))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": wl.data, "config": {"workload": f"{wl.name}: {wl.description}", "sample": sample},
+        "dtype": "f32", "data": wl.data, "config": workload_config(wl, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "ms_per_pose_extrapolated": ms * wl.n_ref / count,
-        "votes_per_sec": votes / (ms * 1e-3),  # the sample-independent rate (pairs differ in cost by orders of magnitude)
+        "sample_refs": sorted(set(used)),
+        "sample_work": {"pairs_in_radius": pairs, "votes": votes, "votes_per_pair": votes / max(1, pairs)},
+        "ms_per_pose_extrapolated": 1e3 * total_s / max(1, len(used)) * wl.n_ref,
+        "votes_per_sec": votes / total_s,  # the sample-independent rate (pairs differ in cost by orders of magnitude)
     }
     print(json.dumps(line), flush=True)
 
@@ -382,9 +412,9 @@ def run_b200(args, wl):
         ms_per_step = total_ms / args.steps
         value = pairs / (ms_per_step * 1e-3)
         e2e_ms = e2e_total_ms / args.steps
-        peak, peak_src = measured_peaks()
+        hbm_peak, hbm_src = measured_peaks()
         # algorithmic bytes of one voting launch on one rank (DESIGN.md "K3 roofline"):
-        #   4 B gathered per vote (the hot word; the 1/16 of votes on the per-entry path gather 8 B: 4.25 B mean);
+        #   4 B gathered per vote (the hot word; the 1/16 of votes in the scene phase's own cell gather 8 B: 4.25 B mean);
         #   per in-radius pair and slice 16 B of CSR offsets + 32 B of point/normal;
         #   16 B per scene point per resident wave of CTAs for the position sweep
         my_pairs, my_votes = stats["pairs_in_radius"], stats["votes"]
@@ -393,11 +423,14 @@ def run_b200(args, wl):
         per_vote = 4.0 + 4.0 / max(1, info.phase_cells) if info.phase_cells > 1 else 8.0
         alg_bytes = per_vote * my_votes + 48.0 * my_pairs * info.n_slices + 16.0 * n_s * waves
         k3_ms = float(np.mean(vote_ms))
-        achieved = alg_bytes / (k3_ms * 1e-3) / 1e9
-        # the denominator HBM peaks do not cover: shared-memory reductions per second, measured here
-        # (csrc/microbench.cu: 2 x 512-thread CTAs per SM, 64 KB accumulators; random words = the voting pattern)
-        atoms_peak_random = ctx.microbench_atoms(1)
-        atoms_peak_spread = ctx.microbench_atoms(0)
+        votes_per_s = my_votes / (k3_ms * 1e-3)
+        # The roof: the SM's L1 data pipe.  Measured live (csrc/microbench.cu) in the voting loop's own shape — one
+        # coalesced 4-byte gather from an L2-resident table + one red.shared.add per vote, eight gathers in flight per
+        # lane — with conflict-free addresses; +8 = the 1024-thread x 1 CTA/SM launch shape of sliced tables.
+        shape = 8 if info.n_slices > 1 else 0
+        peak_cf = max(ctx.microbench_atoms(5 + shape) for _ in range(2))
+        peak_2way = max(ctx.microbench_atoms(7 + shape) for _ in range(2))
+        peak_random = max(ctx.microbench_atoms(6 + shape) for _ in range(2))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k3_dram_traffic.json")
         if os.path.exists(tpath):
@@ -407,15 +440,13 @@ def run_b200(args, wl):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": wl.data,
-            "config": {"workload": f"{wl.name}: {wl.description}", "n_model": int(info.n_model), "n_scene": n_s,
-                       "n_ref": n_ref, "angle_step_deg": 12, "dist_step": float(wl.dist_step),
-                       "table_entries": int(info.n_entries), "accumulator_slices": int(info.n_slices),
-                       "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode
-                                    else (f"reference points interleaved over {world} rank(s), table + scene replicated, 64 B "
-                                          f"hypotheses exchanged by " + ("the vote epilogue's NVLink peer stores" if p2p
-                                                                         else "an NCCL all-gather")) if world > 1 else "single GPU"),
-                       "models_per_step": len(library),
-                       "l2": "256 MiB memset between steps, outside the per-step CUDA-event brackets"},
+            "config": workload_config(wl, world),
+            "run": {"table_entries": int(info.n_entries), "accumulator_slices": int(info.n_slices),
+                    "alpha_columns": int(info.n_alpha), "phase_cells": int(info.phase_cells),
+                    "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode
+                                 else (f"reference points interleaved over {world} rank(s), table + scene replicated, 64 B "
+                                       f"hypotheses exchanged by " + ("the vote epilogue's NVLink peer stores" if p2p
+                                                                      else "an NCCL all-gather")) if world > 1 else "single GPU")},
             "ms_per_pose": ms_per_step / len(library),
             "votes_per_sec": nvotes / (ms_per_step * 1e-3),
             "pairs_examined_per_sec": examined / (ms_per_step * 1e-3),
@@ -427,31 +458,36 @@ def run_b200(args, wl):
                     "h2d_bytes_per_step": int(2 * 16 * n_s), "d2h_bytes_per_step": int(3 * 16 * 4 + 8 * 4 + 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "ppf_vote_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
+            "roofline": {"kernel": "ppf_vote_kernel", "bound": "shared_atomic", "achieved": votes_per_s, "peak": peak_cf,
+                         "unit": "shared-memory reductions/s", "frac": votes_per_s / peak_cf,
+                         "peak_source": "measured in this run: b200ppf_microbench_atoms, the voting loop's shape (coalesced 4-byte "
+                                        "gather + red.shared per vote, 8 in flight per lane), conflict-free addresses",
+                         "peak_two_lanes_per_bank": peak_2way, "peak_random_words": peak_random,
+                         "frac_of_random_words_peak": votes_per_s / peak_random,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                          "traffic_source": traffic["source"] if traffic else None,
-                         "peak_source": peak_src,
                          "kernel_ms": k3_ms, "kernel_ms_max_over_ranks": vote_kernel_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "votes_per_sec_in_kernel": my_votes / (k3_ms * 1e-3),
-                         "atomic": {"achieved": my_votes / (k3_ms * 1e-3), "unit": "shared-memory reductions/s",
-                                    "peak": atoms_peak_random, "frac": my_votes / (k3_ms * 1e-3) / atoms_peak_random,
-                                    "peak_conflict_free": atoms_peak_spread,
-                                    "peak_source": "measured in this run (b200ppf_microbench_atoms, random words in a 64 KB accumulator)"},
-                         "note": "the gathered table bytes are served by L2 (DRAM traffic is the table + scene once), so "
-                                 "'achieved' can exceed the HBM copy peak; what binds is the L1 data pipe: one "
-                                 "shared-memory reduction per vote — see 'atomic'"},
+                         "kernel_share_of_step": k3_ms / ms_per_step,
+                         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "algorithmic_gbs": alg_bytes / (k3_ms * 1e-3) / 1e9,
+                                 "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                                 "note": "the gathered table words are served by L2/L1, not HBM (DRAM traffic = table + scene "
+                                         "once per launch): an HBM fraction of the algorithmic bytes is not a bound"},
+                         "l2": {"gathered_gbs": per_vote * my_votes / (k3_ms * 1e-3) / 1e9,
+                                "note": "hot words gathered per second, an upper bound on the L2 -> L1 traffic (part hits L1)"}},
         }
         if world == 1 and not args.no_cpu and not lib_mode:
             ob, hm = oracle_table(wl)
-            f0, st0, cnt = pick_cpu_sample(hm, wl, 1, 30.0, args.cpu_sample)
+            threads = host_threads()
+            refs = sample_list(wl)[:refs_per_cpu_step(wl, threads, args.cpu_sample, 1, seconds=20.0)]
             t0 = time.perf_counter()
-            _, cst = hm.vote(wl.model, wl.scene, f0, st0, cnt, n_threads=1)
+            _, cst = vote_refs(hm, wl, wl.model, refs, threads)
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": cst["pairs_in_radius"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{cnt} of {n_ref} reference points (every {st0 // wl.ref_rate}-th), full scene, "
-                                              f"voting loop only, {dt:.1f} s", "votes_per_sec": cst["votes"] / dt}
+            line["cpu_baseline"] = {"value": cst["pairs_in_radius"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"the first {len(refs)} of the fixed list of {SAMPLE_SLOTS} evenly spread reference "
+                                              f"points (bench.py sample_list), full scene, voting loop only, {dt:.1f} s",
+                                    "votes_per_sec": cst["votes"] / dt,
+                                    "sample_votes_per_pair": cst["votes"] / max(1, cst["pairs_in_radius"]),
+                                    "workload_votes_per_pair": nvotes / max(1.0, pairs)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -465,7 +501,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", help="c1 | c2 | c2_5mm | c3 (default) | c3s | c4 | c4s (workloads.py)")
     ap.add_argument("--cpu-sample", type=int, default=0,
-                    help="reference points in the CPU sample (0 = sized from timed passes: ~30 s of CPU work)")
+                    help="reference points per CPU step, taken in order from the fixed 64-point list (0 = sized for ~4 s per step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="several GPUs: records written into every peer's buffer by the vote epilogue (default) or NCCL all-gather")

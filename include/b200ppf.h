@@ -102,6 +102,7 @@ typedef struct b200ppf_table_info {
     uint32_t phase_cells; /* alpha_m phase cells per bucket (1: buckets are not subdivided) */
     uint32_t nalpha_rule; /* B200PPF_NALPHA_* the table was built under */
     uint32_t reserved;
+    uint64_t n_merged;    /* words of the merged-vote array the voting kernel walks (<= n_entries; 0: no phase cells) */
 } b200ppf_table_info;
 
 /* per-stage device times of the last call on this context, milliseconds (CUDA events) */

@@ -89,6 +89,8 @@ def _declare(L):
     L.oracle_vote_accumulate_from_pairs.restype = C.c_uint64
     L.oracle_vote.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, sz, sz, sz, sz, C.c_int, vp, vp]
     L.oracle_vote.restype = C.c_int
+    L.oracle_vote_refs.argtypes = [vp, C.c_int, C.c_int, vp, sz, vp, sz, vp, sz, C.c_int, vp, vp]
+    L.oracle_vote_refs.restype = C.c_int
     L.oracle_peak_pose.argtypes = [C.c_int, C.c_float, vp, sz, C.c_uint32, vp, sz, vp]
     L.oracle_cluster.argtypes = [vp, sz, C.c_float, C.c_float, vp, vp, vp, vp]
     L.oracle_cluster.restype = sz
@@ -282,6 +284,19 @@ class HashMap:
                                _p(hyps), _p(stats))
         if rc != 0:
             raise RuntimeError("oracle_vote failed (model/table size mismatch?)")
+        return hyps, dict(zip(("pairs_examined", "pairs_in_radius", "nonempty_lookups", "votes"),
+                              (int(x) for x in stats)))
+
+    def vote_refs(self, model, scene, refs, n_threads=1, mode=FEATURE_PCL_PFH, alpha_mode=ALPHA_MODE_A):
+        """the voting loop over an explicit list of reference points -> (hypotheses, counters)"""
+        model, scene = _f32(model), _f32(scene)
+        refs = np.ascontiguousarray(refs, np.uint64)
+        hyps = np.zeros(len(refs), HYP_DTYPE)
+        stats = np.zeros(4, np.uint64)
+        rc = lib().oracle_vote_refs(self._h, mode, alpha_mode, _p(model), model.shape[0], _p(scene), scene.shape[0],
+                                    _p(refs), len(refs), n_threads, _p(hyps), _p(stats))
+        if rc != 0:
+            raise RuntimeError("oracle_vote_refs failed (model/table size mismatch?)")
         return hyps, dict(zip(("pairs_examined", "pairs_in_radius", "nonempty_lookups", "votes"),
                               (int(x) for x in stats)))
 

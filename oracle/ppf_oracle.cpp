@@ -756,7 +756,16 @@ uint64_t oracle_vote_accumulate(const oracle_hashmap *hm, int feature_mode, int 
 int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, const float *model,
                 size_t n_m, const float *scene, size_t n_s, size_t ref_first, size_t ref_step,
                 size_t ref_count, int n_threads, oracle_hypothesis *hyps, uint64_t *stats) {
-    if (!hm || hm->n != n_m || ref_step == 0) return -1;
+    if (ref_step == 0) return -1;
+    std::vector<size_t> refs(ref_count);
+    for (size_t r = 0; r < ref_count; ++r) refs[r] = ref_first + r * ref_step;
+    return oracle_vote_refs(hm, feature_mode, alpha_mode, model, n_m, scene, n_s, refs.data(), ref_count, n_threads, hyps, stats);
+}
+
+int oracle_vote_refs(const oracle_hashmap *hm, int feature_mode, int alpha_mode, const float *model, size_t n_m,
+                     const float *scene, size_t n_s, const size_t *refs, size_t ref_count, int n_threads,
+                     oracle_hypothesis *hyps, uint64_t *stats) {
+    if (!hm || hm->n != n_m || (ref_count && !refs)) return -1;
     const uint32_t n_alpha = num_alpha_bins(hm->angle_step, hm->nalpha_rule);
     Grid grid;
     const float radius = hm->max_dist * 0.5f;
@@ -770,7 +779,7 @@ int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, cons
          * idle behind the expensive ones) */
         std::vector<std::vector<uint32_t>> accs(static_cast<size_t>(n_threads), std::vector<uint32_t>(n_m * n_alpha, 0u));
         for (size_t r = 0; r < ref_count; ++r) {
-            size_t s_r = ref_first + r * ref_step;
+            size_t s_r = refs[r];
             if (s_r >= n_s) continue;
             vote_one_reference_parallel(hm, feature_mode, alpha_mode, model, n_m, scene, n_s, use_grid ? &grid : nullptr, s_r,
                                         n_alpha, accs, &hyps[r], stats);
@@ -785,7 +794,7 @@ int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, cons
             uint64_t local[4] = {0, 0, 0, 0};
 #pragma omp for schedule(dynamic, 4)
             for (long long r = 0; r < static_cast<long long>(ref_count); ++r) {
-                size_t s_r = ref_first + static_cast<size_t>(r) * ref_step;
+                size_t s_r = refs[static_cast<size_t>(r)];
                 if (s_r >= n_s) continue;
                 vote_one_reference(hm, feature_mode, alpha_mode, model, n_m, scene, n_s,
                                    use_grid ? &grid : nullptr, s_r, n_alpha, acc.data(), &hyps[r], local);
@@ -802,7 +811,7 @@ int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, cons
 #endif
     std::vector<uint32_t> acc(n_m * n_alpha, 0u);
     for (size_t r = 0; r < ref_count; ++r) {
-        size_t s_r = ref_first + r * ref_step;
+        size_t s_r = refs[r];
         if (s_r >= n_s) continue;
         vote_one_reference(hm, feature_mode, alpha_mode, model, n_m, scene, n_s,
                            use_grid ? &grid : nullptr, s_r, n_alpha, acc.data(), &hyps[r], stats);

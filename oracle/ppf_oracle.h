@@ -110,6 +110,11 @@ int oracle_vote(const oracle_hashmap *hm, int feature_mode, int alpha_mode, cons
                 size_t n_m, const float *scene, size_t n_s, size_t ref_first, size_t ref_step,
                 size_t ref_count, int n_threads, oracle_hypothesis *hyps, uint64_t *stats);
 
+/* the same loop over an explicit list of reference points (bench.py's fixed CPU sample) */
+int oracle_vote_refs(const oracle_hashmap *hm, int feature_mode, int alpha_mode, const float *model, size_t n_m,
+                     const float *scene, size_t n_s, const size_t *refs, size_t ref_count, int n_threads,
+                     oracle_hypothesis *hyps, uint64_t *stats);
+
 /* A.4 : pose of one peak (model_index, alpha_bin) for scene reference s_r */
 void oracle_peak_pose(int alpha_mode, float angle_step, const float *model, size_t model_index,
                       uint32_t alpha_bin, const float *scene, size_t s_r, float *pose12);

@@ -250,16 +250,18 @@ def test_k2_table_load_refuses_consistent_looking_but_invalid_files(tmp_path, ct
     t.save(path)
     raw = bytearray(open(path, "rb").read())
     hdr = int(np.frombuffer(raw[12:16], "<u4")[0])
-    n_off, n_sub, n_ent = (int(x) for x in np.frombuffer(raw[24:48], "<u8"))
-    info_off, info_len = 56, C.sizeof(capi.TableInfo)
-    a_off = hdr                      # arrays: offsets, sub_offsets, entry_w, entry_am, entry_alpha, entry_idx
-    starts = np.cumsum([0, n_off, n_sub, n_ent, n_ent, n_ent]) * 4 + a_off
+    n_off, n_sub, n_ent, n_mrg = (int(x) for x in np.frombuffer(raw[24:56], "<u8"))
+    info_off, info_len = 64, C.sizeof(capi.TableInfo)
+    a_off = hdr     # arrays: offsets, sub_offsets, entry_w, entry_am, entry_alpha, entry_idx, merged_w, merged cell offsets
+    counts = (n_off, n_sub, n_ent, n_ent, n_ent, n_ent, n_mrg, n_sub if n_mrg else 0)
+    starts = np.cumsum((0,) + counts[:-1]) * 4 + a_off
+    assert starts[-1] + 4 * counts[-1] == len(raw) and n_mrg and n_mrg < n_ent
 
     def resign(blob):
         h = _mix_bytes(0x42323030, blob[info_off:hdr])      # info, key and binning parameters
-        for k, cnt in enumerate((n_off, n_sub, n_ent, n_ent, n_ent, n_ent)):
+        for k, cnt in enumerate(counts):
             h = _mix_bytes(h, blob[starts[k]:starts[k] + 4 * cnt])
-        blob[48:56] = np.array([h], "<u8").tobytes()
+        blob[56:64] = np.array([h], "<u8").tobytes()
         return blob
 
     good = tmp_path / "good.b200ppf"
@@ -280,6 +282,14 @@ def test_k2_table_load_refuses_consistent_looking_but_invalid_files(tmp_path, ct
     o, v = word(b, 2, n_ent // 3)
     b[o:o + 4] = np.array([(v & 0xFF000000) | 0x00FFFFF0], "<u4").tobytes()
     cases.append(("hot word", b))
+    b = bytearray(raw)                                     # a merged vote word far outside the accumulator slice
+    o, v = word(b, 6, n_mrg // 2)
+    b[o:o + 4] = np.array([(v & 0xFF000000) | 0x00FFFFF0], "<u4").tobytes()
+    cases.append(("merged vote word", b))
+    b = bytearray(raw)                                     # a merged count that no longer matches the cell's entries
+    o, v = word(b, 6, n_mrg // 3)
+    b[o:o + 4] = np.array([v + (1 << 24)], "<u4").tobytes()
+    cases.append(("merged vote counts", b))
     b = bytearray(raw)                                     # pair index beyond n*n
     o, v = word(b, 5, 5)
     b[o:o + 4] = np.array([0x7FFFFFFF], "<u4").tobytes()
@@ -292,11 +302,12 @@ def test_k2_table_load_refuses_consistent_looking_but_invalid_files(tmp_path, ct
     assert np.frombuffer(b[kp_size0:kp_size0 + 4], "<i4")[0] == ti.size[0] - 1
     b[kp_size0:kp_size0 + 4] = np.array([ti.size[0]], "<i4").tobytes()
     cases.append(("key space", b))
-    b = bytearray(raw)                                     # binning: another fixed-point multiplier (the last header word holding it)
-    fm = np.frombuffer(bytes(raw[info_off + info_len:hdr]), "<u4")
-    ix = int(np.flatnonzero(fm == fm[fm > (1 << 24)].max())[-1])
-    o = info_off + info_len + 4 * ix
-    b[o:o + 4] = np.array([int(fm[ix]) + 12345], "<u4").tobytes()
+    b = bytearray(raw)                                     # binning: another fixed-point multiplier
+    o = info_off + info_len + 4 * 15 + 4 * 10              # KeyParams is 15 words; fix_mul is word 10 of BinParams
+    fix_mul = int(np.frombuffer(bytes(raw[o:o + 4]), "<u4")[0])
+    T = 2 * np.pi / float(ANGLE_STEP)
+    assert any(fix_mul == int(np.rint(T * 2 ** sh)) for sh in range(20, 31)), "header layout changed: update this test"
+    b[o:o + 4] = np.array([fix_mul ^ 0x3039], "<u4").tobytes()
     cases.append(("binning parameters", b))
     for what, blob in cases:
         bad = tmp_path / "bad.b200ppf"

@@ -41,7 +41,7 @@ def test_struct_layouts_match_the_header():
     # sizes and the offset of every struct's last member as the C compiler lays them out
     import subprocess
     import tempfile
-    structs = {"b200ppf_table_info": (capi.TableInfo, "reserved"), "b200ppf_timings": (capi.Timings, "prep_ms"),
+    structs = {"b200ppf_table_info": (capi.TableInfo, "n_merged"), "b200ppf_timings": (capi.Timings, "prep_ms"),
                "b200ppf_icp_params": (capi.IcpParams, "num_levels"), "b200ppf_object_params": (capi.ObjectParams, "icp"),
                "b200ppf_object_result": (capi.ObjectResult, "total_wall_ms")}
     body = "".join(f'printf("{n} %zu %zu\\n", sizeof({n}), offsetof({n}, {last}));' for n, (_, last) in structs.items())

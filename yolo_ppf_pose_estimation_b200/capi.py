@@ -30,7 +30,8 @@ class TableInfo(C.Structure):
                 ("key_space", C.c_uint64), ("n_slices", C.c_uint32), ("slice_rows", C.c_uint32),
                 ("n_alpha", C.c_uint32), ("key_bits", C.c_uint32), ("lo", C.c_int32 * 4),
                 ("size", C.c_int32 * 4), ("angle_step", C.c_float), ("dist_step", C.c_float),
-                ("max_dist", C.c_float), ("phase_cells", C.c_uint32), ("nalpha_rule", C.c_uint32), ("reserved", C.c_uint32)]
+                ("max_dist", C.c_float), ("phase_cells", C.c_uint32), ("nalpha_rule", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_merged", C.c_uint64)]
 
 
 class Timings(C.Structure):

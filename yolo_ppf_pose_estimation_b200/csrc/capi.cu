@@ -399,13 +399,14 @@ int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *off
 namespace {
 
 constexpr uint64_t TABLE_MAGIC = 0x4C42543030325042ull;  // "BP200TBL" little-endian
-constexpr uint32_t TABLE_FORMAT = 3;                      // 3: + alpha-column rule (2: phase-sorted buckets, hot words)
+constexpr uint32_t TABLE_FORMAT = 3;                      // 3: alpha-column rule, bin-major hot words (2: phase-sorted buckets)
 
 struct TableFileHeader {
     uint64_t magic;
     uint32_t format, header_bytes;
     uint32_t feature_mode, alpha_mode;
     uint64_t n_offsets, n_sub_offsets, n_entries;  // array lengths in 32-bit words (entries: without the padding)
+    uint64_t n_merged;                              // merged-vote words (its cell bounds have n_sub_offsets words)
     uint64_t checksum;                              // over info, kp, bp and the six arrays, in file order
     b200ppf_table_info info;
     b200ppf::KeyParams kp;
@@ -478,7 +479,8 @@ const char *validate_table_file(const TableFileHeader &h, const std::vector<std:
             if (sub[k << ref.cells_log2] != off[k]) return "phase-cell offsets leave their bucket";
     }
     const uint64_t n = info.n_model, nn = n * n;
-    const uint32_t stride_bytes = ref.row_stride * 4u;
+    if (kp.slice_rows != info.slice_rows || kp.n_slices != info.n_slices || kp.row_pitch != (info.slice_rows + 31u) / 32u * 32u)
+        return "slice geometry";
     for (uint32_t slice = 0; slice < info.n_slices; ++slice) {
         const uint64_t p0 = off[(uint64_t)slice * info.key_space], p1 = off[(uint64_t)(slice + 1) * info.key_space];
         const uint64_t row0 = (uint64_t)slice * info.slice_rows, rows = std::min<uint64_t>(info.slice_rows, n - row0);
@@ -489,10 +491,27 @@ const char *validate_table_file(const TableFileHeader &h, const std::vector<std:
             float alpha;
             memcpy(&alpha, &ealpha[p], sizeof(float));
             if (!(alpha >= -3.14159274f && alpha <= 3.14159274f)) return "entry alpha_m outside [-pi, pi]";
-            const uint32_t a_fix = b200ppf::alpha_to_fix(alpha), row_bytes = (uint32_t)(i - row0) * stride_bytes;
+            const uint32_t a_fix = b200ppf::alpha_to_fix(alpha), local = (uint32_t)(i - row0);
             if (eam[p] != a_fix) return "entry fixed-point alpha_m does not match its float";
-            if (ew[p] != (ref.bulk ? b200ppf::hot_word(ref, row_bytes, b200ppf::phase_of_fix(ref, a_fix)) : row_bytes))
+            if (ew[p] != (ref.bulk ? b200ppf::hot_word(ref, kp.row_pitch, local, b200ppf::phase_of_fix(ref, a_fix)) : 4u * local))
                 return "entry hot word does not match its pair";
+        }
+    }
+    // merged votes: cell bounds monotone inside the array; every word a 4-aligned offset inside the accumulator slice
+    // with a count >= 1; the counts of a cell add up to the cell's entries (the votes cast are those of the entries)
+    const std::vector<uint32_t> &mw = a[6], &msub = a[7];
+    if (!mw.empty() || !msub.empty()) {
+        if (msub.size() != sub.size() || msub.empty() || msub[0] != 0 || msub.back() != mw.size()) return "merged cell offsets";
+        const uint32_t acc_bytes = ref.acc_cols * kp.row_pitch * 4u;
+        for (size_t c = 0; c + 1 < msub.size(); ++c) {
+            if (msub[c] > msub[c + 1]) return "merged cell offsets decrease";
+            uint64_t votes = 0;
+            for (uint64_t p = msub[c]; p < msub[c + 1]; ++p) {
+                const uint32_t off = mw[p] & 0xFFFFFFu, cnt = mw[p] >> 24;
+                if (cnt == 0 || (off & 3u) || off >= acc_bytes) return "merged vote word outside the accumulator slice";
+                votes += cnt;
+            }
+            if (votes != (uint64_t)sub[c + 1] - sub[c]) return "merged vote counts do not add up to the cell's entries";
         }
     }
     return nullptr;
@@ -518,11 +537,14 @@ int b200ppf_table_save(b200ppf_ctx *ctx, const b200ppf_table *t, const char *pat
     h.n_offsets = total_keys + 1;
     h.n_sub_offsets = t->sub_offsets ? (total_keys << t->bp.cells_log2) + 1 : 0;
     h.n_entries = t->info.n_entries;
-    const uint32_t *arrays[6] = {t->offsets, t->sub_offsets, t->entry_w, t->entry_am,
-                                 reinterpret_cast<const uint32_t *>(t->entry_alpha), t->entry_idx};
-    const uint64_t lengths[6] = {h.n_offsets, h.n_sub_offsets, h.n_entries, h.n_entries, h.n_entries, h.n_entries};
-    std::vector<std::vector<uint32_t>> host(6);
-    for (int a = 0; a < 6; ++a) {
+    h.n_merged = t->merged_w ? t->n_merged : 0;
+    constexpr int NA = 8;
+    const uint32_t *arrays[NA] = {t->offsets, t->sub_offsets, t->entry_w, t->entry_am,
+                                  reinterpret_cast<const uint32_t *>(t->entry_alpha), t->entry_idx, t->merged_w, t->msub_offsets};
+    const uint64_t lengths[NA] = {h.n_offsets, h.n_sub_offsets, h.n_entries, h.n_entries, h.n_entries, h.n_entries, h.n_merged,
+                                  t->msub_offsets ? h.n_sub_offsets : 0};
+    std::vector<std::vector<uint32_t>> host(NA);
+    for (int a = 0; a < NA; ++a) {
         host[a].resize(lengths[a]);
         if (lengths[a])
             PPF_CUDA(ctx, cudaMemcpyAsync(host[a].data(), arrays[a], lengths[a] * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -532,12 +554,12 @@ int b200ppf_table_save(b200ppf_ctx *ctx, const b200ppf_table *t, const char *pat
     // the parameter block (info, kp, bp: everything behind the checksum field) and then the six arrays
     uint64_t sum = mix_bytes(0x42323030u, reinterpret_cast<const char *>(&h) + offsetof(TableFileHeader, info),
                              sizeof(h) - offsetof(TableFileHeader, info));
-    for (int a = 0; a < 6; ++a) sum = mix_bytes(sum, host[a].data(), host[a].size() * sizeof(uint32_t));
+    for (int a = 0; a < NA; ++a) sum = mix_bytes(sum, host[a].data(), host[a].size() * sizeof(uint32_t));
     h.checksum = sum;
     FileCloser fc{fopen(path, "wb")};
     if (!fc.f) return fail_msg(ctx, B200PPF_ERR_IO, "table save: cannot open the file for writing");
     bool ok = fwrite(&h, sizeof(h), 1, fc.f) == 1;
-    for (int a = 0; a < 6 && ok; ++a)
+    for (int a = 0; a < NA && ok; ++a)
         if (!host[a].empty()) ok = fwrite(host[a].data(), sizeof(uint32_t), host[a].size(), fc.f) == host[a].size();
     ok = ok && fflush(fc.f) == 0;
     if (!ok) return fail_msg(ctx, B200PPF_ERR_IO, "table save: short write");
@@ -564,15 +586,20 @@ int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out) 
                       h.n_sub_offsets == (h.bp.cells_log2 ? (total_keys << h.bp.cells_log2) + 1 : 0) &&
                       h.n_entries == h.info.n_entries && h.n_entries <= 0xFFFFFFFFull && h.info.n_model >= 1 &&
                       h.info.n_model <= 65535 && h.n_entries <= h.info.n_model * h.info.n_model &&
-                      h.info.n_alpha >= 1 && h.bp.n_alpha == h.info.n_alpha && h.bp.row_stride == h.info.n_alpha + 1 &&
+                      h.info.n_alpha >= 1 && h.bp.n_alpha == h.info.n_alpha &&
                       h.kp.slice_rows == h.info.slice_rows && h.kp.n_slices == h.info.n_slices;
     if (!sane) return fail_msg(ctx, B200PPF_ERR_IO, "table load: inconsistent header");
-    const uint64_t lengths[6] = {h.n_offsets, h.n_sub_offsets, h.n_entries, h.n_entries, h.n_entries, h.n_entries};
-    std::vector<std::vector<uint32_t>> host(6);
+    constexpr int NA = 8;
+    const bool has_merged = h.bp.cells_log2 != 0 && h.n_entries != 0;
+    if (h.n_merged > h.n_entries || (has_merged ? h.n_merged == 0 : h.n_merged != 0) || h.info.n_merged != h.n_merged)
+        return fail_msg(ctx, B200PPF_ERR_IO, "table load: inconsistent header");
+    const uint64_t lengths[NA] = {h.n_offsets, h.n_sub_offsets, h.n_entries, h.n_entries, h.n_entries, h.n_entries, h.n_merged,
+                                  has_merged ? h.n_sub_offsets : 0};
+    std::vector<std::vector<uint32_t>> host(NA);
     // the parameter block (info, kp, bp: everything behind the checksum field) and then the six arrays
     uint64_t sum = mix_bytes(0x42323030u, reinterpret_cast<const char *>(&h) + offsetof(TableFileHeader, info),
                              sizeof(h) - offsetof(TableFileHeader, info));
-    for (int a = 0; a < 6; ++a) {
+    for (int a = 0; a < NA; ++a) {
         host[a].resize(lengths[a]);
         if (lengths[a] && fread(host[a].data(), sizeof(uint32_t), lengths[a], fc.f) != lengths[a])
             return fail_msg(ctx, B200PPF_ERR_IO, "table load: truncated file");
@@ -593,11 +620,13 @@ int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out) 
     t->kp = h.kp;
     t->bp = h.bp;
     t->feature_mode = (int)h.feature_mode;
-    uint32_t **dev[6] = {&t->offsets, &t->sub_offsets, &t->entry_w, &t->entry_am,
-                         reinterpret_cast<uint32_t **>(&t->entry_alpha), &t->entry_idx};
-    for (int a = 0; a < 6; ++a) {
+    t->n_merged = h.n_merged;
+    uint32_t **dev[NA] = {&t->offsets, &t->sub_offsets, &t->entry_w, &t->entry_am,
+                          reinterpret_cast<uint32_t **>(&t->entry_alpha), &t->entry_idx, &t->merged_w, &t->msub_offsets};
+    for (int a = 0; a < NA; ++a) {
         if (a == 1 && !h.n_sub_offsets) continue;
-        const size_t pad = (a == 2 || a == 3) ? b200ppf::ENTRY_PAD : 0;
+        if (a >= 6 && !has_merged) continue;
+        const size_t pad = (a == 2 || a == 3 || a == 6) ? b200ppf::ENTRY_PAD : 0;
         const size_t words = std::max<size_t>(1, lengths[a] + pad);
         cudaError_t e = cudaMalloc(dev[a], words * sizeof(uint32_t));
         if (e == cudaSuccess && pad) e = cudaMemsetAsync(*dev[a] + lengths[a], 0, pad * sizeof(uint32_t), ctx->stream);
@@ -625,6 +654,8 @@ void b200ppf_table_free(b200ppf_table *t) {
     if (t->entry_am) cudaFree(t->entry_am);
     if (t->entry_idx) cudaFree(t->entry_idx);
     if (t->entry_alpha) cudaFree(t->entry_alpha);
+    if (t->merged_w) cudaFree(t->merged_w);
+    if (t->msub_offsets) cudaFree(t->msub_offsets);
     delete t;
 }
 

@@ -52,6 +52,10 @@ __device__ __forceinline__ uint32_t sort_key(const KeyParams &kp, const BinParam
             else cell = min((uint32_t)(fr * (float)(1u << bp.cells_log2)), (1u << bp.cells_log2) - 1u);
         }
         key = (key << bp.cells_log2) | cell;
+        // merged votes: the bin of alpha_m (from the fixed-point phase the hot word is made of) follows the cell, so
+        // that the entries of one (cell, bin, model row) — identical votes for every scene pair outside the cell —
+        // end up adjacent after the stable sort
+        if (kp.merge_bits) key = (key << kp.merge_bits) | (alpha == alpha ? phase_bin(bp, phase_of_fix(bp, alpha_to_fix(alpha))) : 0u);
     }
     return key;
 }
@@ -187,20 +191,59 @@ __global__ void csr_offsets_kernel(const uint32_t *__restrict__ sorted_keys, uin
     offsets[k] = lo;
 }
 
-// sub_offsets[k'] for k' = key << shift | cell: the search is confined to the key's own bucket
+// sub_offsets[k'] for k' = key << shift | cell: the search is confined to the key's own bucket; the sort keys carry
+// low_bits more bits below the cell (the bin of alpha_m of tables with merged votes)
 __global__ void csr_sub_offsets_kernel(const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ offsets,
-                                       uint32_t total_sub, uint32_t shift, uint32_t *__restrict__ sub_offsets) {
+                                       uint32_t total_sub, uint32_t shift, uint32_t low_bits,
+                                       uint32_t *__restrict__ sub_offsets) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > total_sub) return;
     uint32_t lo = offsets[k >> shift];
     if (k < total_sub) {
         uint32_t hi = offsets[(k >> shift) + 1];
+        const uint32_t want = k << low_bits;
         while (lo < hi) {
             uint32_t mid = lo + ((hi - lo) >> 1);
-            if (sorted_keys[mid] < k) lo = mid + 1; else hi = mid;
+            if (sorted_keys[mid] < want) lo = mid + 1; else hi = mid;
         }
     }
     sub_offsets[k] = lo;
+}
+
+// ---- merged votes ------------------------------------------------------------------------------------------------
+// After the sort the entries of one (slice, key, cell, bin of alpha_m) are adjacent and ordered by (i, j): a run of
+// entries with the same model row i casts the same vote — same accumulator word, same shift — for every scene pair
+// whose phase lies in another cell.  The run becomes ONE word of the merged array, (count << 24) | hot word, and the
+// voting kernel adds `count` with one reduction (config 3: 1.74 entries per word).  Runs are cut every 255 entries.
+__global__ void merge_heads_kernel(const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ sorted_idx,
+                                   uint32_t n_entries, uint32_t n, uint32_t *__restrict__ head) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_entries) return;
+    head[p] = (p == 0 || p % 255u == 0u || sorted_keys[p] != sorted_keys[p - 1] || sorted_idx[p] / n != sorted_idx[p - 1] / n) ? 1u : 0u;
+}
+
+__global__ void merge_words_kernel(const uint32_t *__restrict__ head, const uint32_t *__restrict__ rank,
+                                   const uint32_t *__restrict__ entry_w, uint32_t n_entries,
+                                   uint32_t *__restrict__ merged_w) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_entries || !head[p]) return;
+    uint32_t q = p + 1;
+    while (q < n_entries && !head[q]) ++q;  // <= 255 steps
+    merged_w[rank[p]] = ((q - p) << 24) | entry_w[p];
+}
+
+__global__ void merge_identity_kernel(const uint32_t *__restrict__ entry_w, uint32_t n_entries, uint32_t *__restrict__ merged_w) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_entries) merged_w[p] = (1u << 24) | entry_w[p];
+}
+
+// merged position of every cell bound (cell starts are run heads)
+__global__ void merge_offsets_kernel(const uint32_t *__restrict__ sub_offsets, uint32_t total_sub, const uint32_t *__restrict__ rank,
+                                     uint32_t n_entries, uint32_t n_merged, uint32_t *__restrict__ msub_offsets) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > total_sub) return;
+    const uint32_t o = sub_offsets[c];
+    msub_offsets[c] = o < n_entries ? rank[o] : n_merged;
 }
 
 __global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint32_t total_keys,
@@ -211,11 +254,11 @@ __global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
 }
 
-// per entry: the hot word (accumulator byte offset of model row i inside its slice, plus — phase-sorted
-// tables — the bin of alpha_m and the wrap field), alpha_m in fixed point for the per-entry path, and
+// per entry: the hot word (byte offset, inside the bin-major accumulator slice, of model row i's cell in the column of
+// alpha_m's own bin — column 0 for tables without phase cells), alpha_m in fixed point for the per-entry paths, and
 // the float alpha_m for the literal form of the guard-band votes and for the API exports.
 __global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const uint32_t *__restrict__ sorted_alpha,
-                               uint32_t n_entries, uint32_t n, uint32_t slice_rows, BinParams bp,
+                               uint32_t n_entries, uint32_t n, uint32_t slice_rows, uint32_t pitch, BinParams bp,
                                uint32_t *__restrict__ entry_w, uint32_t *__restrict__ entry_am,
                                float *__restrict__ entry_alpha, int *__restrict__ bad_alpha) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,28 +268,32 @@ __global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const ui
     const float alpha = __uint_as_float(sorted_alpha[p]);
     // atan2f range; anything else cannot come from PPFEstimation and would not wrap like PCL's floats
     if (!(alpha >= -3.14159274f && alpha <= 3.14159274f)) *bad_alpha = 1;
-    const uint32_t a_fix = alpha_to_fix(alpha), row_bytes = local * bp.row_stride * 4u;
-    entry_w[p] = bp.bulk ? hot_word(bp, row_bytes, phase_of_fix(bp, a_fix)) : row_bytes;
+    const uint32_t a_fix = alpha_to_fix(alpha);
+    entry_w[p] = bp.bulk ? hot_word(bp, pitch, local, phase_of_fix(bp, a_fix)) : 4u * local;
     entry_am[p] = a_fix;
     entry_alpha[p] = alpha;
 }
 
-// Bank spreading.  Every vote of a shift range lands at (hot word - one constant), so the shared-memory
-// bank of a vote is the bank of the hot word's own address up to a rotation common to the whole
-// range.  Inside each phase cell the entries are therefore re-ordered by (rank within their bank
-// class, bank): any 32 consecutive entries then hold each bank at most twice where random order
-// holds the fullest bank ~3.5 times — the voting kernel's ATOMS wavefronts drop accordingly.  The
-// order inside a cell is free: exports re-sort to (i, j), vote counts do not depend on it.
-// One warp per non-empty cell; ranks follow the (i, j) order, so the result is deterministic.
+// Bank ordering.  The accumulator is bin-major with a pitch that is a multiple of 32, so the shared-memory bank of a
+// vote is (model row mod 32) for every scene pair.  A warp votes for 32 consecutive entries per instruction, and the
+// instruction costs as many passes of the SM's data pipe as its fullest bank holds entries.  Inside each phase cell
+// (where the order is free: exports re-sort to (i, j), vote counts do not depend on it) the entries are therefore laid
+// out as
+//   core   m = the rarest bank's count rounds of 32 entries, one per bank in bank order: ANY 32 consecutive
+//          entries of this part hit 32 different banks, however the voting loop's batches are aligned;
+//   tail   what the fuller banks have left, T entries sorted by bank and dealt round-robin into ceil(T / 32)
+//          groups: a bank with e entries left puts ceil(e / groups) of them into each group,
+// which meets the lower bound max(entries / 32, fullest bank) on the passes of a cell up to rounding.
+// Only the merged words (the shift ranges' input) are ordered; the per-entry arrays of the scene phase's own cell
+// (1/16 of the votes) stay in sorted order.  One warp per non-empty cell; ranks inside a bank follow the sorted
+// order, so the result is deterministic.
 constexpr int SPREAD_WARPS = 8;
 __global__ void __launch_bounds__(SPREAD_WARPS * 32)
-bank_spread_kernel(const uint32_t *__restrict__ sub_offsets, uint32_t total_sub, const uint32_t *__restrict__ w_in,
-                   const uint32_t *__restrict__ am_in, const uint32_t *__restrict__ alpha_in,
-                   const uint32_t *__restrict__ idx_in, uint32_t *__restrict__ w_out, uint32_t *__restrict__ am_out,
-                   float *__restrict__ alpha_out, uint32_t *__restrict__ idx_out) {
-    __shared__ uint32_t s_count[SPREAD_WARPS][32], s_run[SPREAD_WARPS][32];
+bank_order_kernel(const uint32_t *__restrict__ sub_offsets, uint32_t total_sub, const uint32_t *__restrict__ w_in,
+                  uint32_t *__restrict__ w_out) {
+    __shared__ uint32_t s_count[SPREAD_WARPS][32], s_run[SPREAD_WARPS][32], s_prefix[SPREAD_WARPS][32];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t *count = s_count[wib], *run = s_run[wib];
+    uint32_t *count = s_count[wib], *run = s_run[wib], *prefix = s_prefix[wib];
     const uint32_t n_warps = gridDim.x * SPREAD_WARPS;
     for (uint32_t c0 = (blockIdx.x * SPREAD_WARPS + wib) * 32; c0 < total_sub; c0 += n_warps * 32) {
         const uint32_t c = c0 + lane;
@@ -265,6 +312,21 @@ bank_spread_kernel(const uint32_t *__restrict__ sub_offsets, uint32_t total_sub,
             __syncwarp();
             for (uint32_t k = cb + lane; k < ce; k += 32) atomicAdd(&count[(w_in[k] >> 2) & 31u], 1u);
             __syncwarp();
+            // m = the rarest bank's count; prefix = exclusive scan of what each bank has beyond m
+            const uint32_t cnt = count[lane];
+            uint32_t m = cnt;
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+            const uint32_t extra = cnt - m;
+            uint32_t incl = extra;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            prefix[lane] = incl - extra;
+            const uint32_t tail = __shfl_sync(0xFFFFFFFFu, incl, 31);  // T
+            const uint32_t groups = (tail + 31u) / 32u;                  // K
+            const uint32_t gq = groups ? tail / groups : 0u, gr = groups ? tail % groups : 0u;
+            __syncwarp();
             for (uint32_t k0 = cb; k0 < ce; k0 += 32) {
                 const uint32_t k = k0 + lane;
                 const bool valid = k < ce;
@@ -277,19 +339,15 @@ bank_spread_kernel(const uint32_t *__restrict__ sub_offsets, uint32_t total_sub,
                 if (valid && lane == (uint32_t)(31 - __clz(same))) run[bank] = r + 1;  // highest lane of the class
                 __syncwarp();
                 if (valid) {
-                    // entries ordered before (r, bank): every class contributes min(count, r), plus the lower
-                    // banks that still have an entry of rank r
-                    uint32_t dest = 0;
-#pragma unroll 8
-                    for (uint32_t bb = 0; bb < 32; ++bb) {
-                        const uint32_t cnt = count[bb];
-                        dest += min(cnt, r) + ((bb < bank && cnt > r) ? 1u : 0u);
+                    uint32_t dest;
+                    if (r < m) {
+                        dest = r * 32u + bank;
+                    } else {
+                        const uint32_t t = prefix[bank] + (r - m);
+                        const uint32_t j = t % groups, pos = t / groups;
+                        dest = 32u * m + j * gq + min(j, gr) + pos;
                     }
-                    const uint32_t o = cb + dest;
-                    w_out[o] = w;
-                    am_out[o] = am_in[k];
-                    alpha_out[o] = __uint_as_float(alpha_in[k]);
-                    idx_out[o] = idx_in[k];
+                    w_out[cb + dest] = w;
                 }
             }
             __syncwarp();
@@ -350,14 +408,15 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         delete t;
         return fail_msg(ctx, B200PPF_ERR_INVALID, "table build: angle step larger than 2*pi");
     }
-    // accumulator slices: rows per slice bounded by the shared-memory budget of the voting kernel
+    // accumulator slices: rows per slice bounded by the shared-memory budget of the voting kernel.  The slice is held
+    // bin-major with a pitch of 32-row multiples (k3_vote.cu), acc_cols columns (the FLOOR rules carry a spare one).
+    t->bp = make_bin_params(angle_step, ctx->alpha_mode, ctx->nalpha_rule);
     {
         size_t budget = k3_accumulator_budget(ctx);
-        // rows are n_alpha + 1 words wide (the spare cell takes bins past the last column)
-        size_t rows_max = budget / (((size_t)info.n_alpha + 1) * sizeof(uint32_t));
+        size_t rows_max = budget / ((size_t)t->bp.acc_cols * sizeof(uint32_t)) / 32 * 32;
         if (rows_max == 0) {
             delete t;
-            return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "table build: angle step too fine for one accumulator row in shared memory");
+            return fail_msg(ctx, B200PPF_ERR_UNSUPPORTED, "table build: angle step too fine for 32 accumulator rows in shared memory");
         }
         if (const char *e = getenv("B200PPF_SLICE_ROWS")) {
             size_t v = (size_t)atoll(e);
@@ -373,6 +432,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     kp.dist_step = dist_step;
     kp.slice_rows = info.slice_rows;
     kp.n_slices = info.n_slices;
+    kp.row_pitch = (info.slice_rows + 31u) / 32u * 32u;
 
     int *d_range = nullptr;  // lo[4], hi[4], max_f4_bits, out_of_range, bad_alpha, pad
     PPF_CUDA(ctx, cudaMallocAsync(&d_range, 12 * sizeof(int), ctx->stream));
@@ -423,7 +483,6 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         kp.lo[3] = 0;
         kp.size[3] = (int)std::floor(diag / dist_step) + 2;
     }
-    t->bp = make_bin_params(angle_step, ctx->alpha_mode, ctx->nalpha_rule);
     {
         unsigned __int128 ks = 1;
         for (int k = 0; k < 4; ++k) ks *= (unsigned __int128)(uint32_t)kp.size[k];
@@ -450,7 +509,14 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     const uint32_t total_keys = kp.key_space * info.n_slices;
     const uint32_t cells_log2 = t->bp.cells_log2;
     const uint32_t total_sub = total_keys << cells_log2;
-    info.key_bits = (uint32_t)ceil_log2((uint64_t)total_sub + 1);
+    // merged votes: the bin of alpha_m joins the sort key when the key still fits 32 bits
+    kp.merge_bits = 0;
+    if (t->bp.bulk && !getenv("B200PPF_NO_MERGE")) {
+        const uint32_t mb = (uint32_t)ceil_log2((uint64_t)t->bp.n_turn);
+        if (ceil_log2((uint64_t)total_sub + 1) + (int)mb <= 32) kp.merge_bits = mb;
+    }
+    const uint32_t merge_bits = kp.merge_bits;
+    info.key_bits = (uint32_t)ceil_log2((uint64_t)total_sub + 1) + merge_bits;
     info.phase_cells = 1u << cells_log2;
 
     // ---- keys ---------------------------------------------------------------------------------
@@ -523,10 +589,10 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     {
         auto launch = [&]() -> int {
             PPF_LAUNCH(ctx, csr_offsets_kernel, (total_keys + 1 + 255) / 256, 256, 0, keys[s], (uint32_t)count,
-                       total_keys, cells_log2, t->offsets);
+                       total_keys, cells_log2 + merge_bits, t->offsets);
             if (cells_log2)
                 PPF_LAUNCH(ctx, csr_sub_offsets_kernel, (total_sub + 1 + 255) / 256, 256, 0, keys[s], t->offsets, total_sub,
-                           cells_log2, t->sub_offsets);
+                           cells_log2, merge_bits, t->sub_offsets);
             return B200PPF_OK;
         };
         K2_TRY(launch());
@@ -559,29 +625,64 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     {
         auto launch = [&]() -> int {
             if (n_entries) {
-                if (cells_log2 && !getenv("B200PPF_NO_BANK_SPREAD")) {
-                    // entries in (key, cell, i, j) order into the free halves of the sort buffers, then the
-                    // bank-spreading permutation inside every phase cell writes the table's arrays
-                    uint32_t *w_tmp = keys[1 - s], *am_tmp = idx[1 - s], *alpha_tmp = alp[1 - s];
-                    PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
-                               info.slice_rows, t->bp, w_tmp, am_tmp, reinterpret_cast<float *>(alpha_tmp), d_range + 10);
-                    const unsigned blocks = (unsigned)std::min<size_t>(((size_t)total_sub + 32 * SPREAD_WARPS - 1) /
-                                                                           (32 * SPREAD_WARPS),
-                                                                       (size_t)ctx->sm_count * 16);
-                    PPF_LAUNCH(ctx, bank_spread_kernel, blocks, SPREAD_WARPS * 32, 0, t->sub_offsets, total_sub, w_tmp, am_tmp,
-                               alpha_tmp, idx[s], t->entry_w, t->entry_am, t->entry_alpha, t->entry_idx);
-                } else {
-                    PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
-                               info.slice_rows, t->bp, t->entry_w, t->entry_am, t->entry_alpha, d_range + 10);
-                    PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
-                                                  cudaMemcpyDeviceToDevice, ctx->stream));
-                }
+                // per-entry arrays in sorted order: (key, cell, [bin of alpha_m,] i, j)
+                PPF_LAUNCH(ctx, entries_kernel, (n_entries + 255) / 256, 256, 0, idx[s], alp[s], n_entries, (uint32_t)n,
+                           info.slice_rows, kp.row_pitch, t->bp, t->entry_w, t->entry_am, t->entry_alpha, d_range + 10);
+                PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
             }
             PPF_LAUNCH(ctx, count_nonempty_kernel, (total_keys + 255) / 256, 256, 0, t->offsets, total_keys, d_cnt);
             return B200PPF_OK;
         };
         K2_TRY(launch());
     }
+    // ---- merged votes + bank order (phase-sorted tables) ---------------------------------------------
+    t->n_merged = 0;
+    if (cells_log2 && n_entries) {
+        // the free halves of the sort buffers hold the run heads, their ranks and the unordered merged words
+        uint32_t *head = keys[1 - s], *rank = idx[1 - s], *mw_tmp = alp[1 - s];
+        uint32_t n_merged = n_entries;
+        {
+            auto launch = [&]() -> int {
+                if (merge_bits)
+                    PPF_LAUNCH(ctx, merge_heads_kernel, (n_entries + 255) / 256, 256, 0, keys[s], idx[s], n_entries, (uint32_t)n, head);
+                return B200PPF_OK;
+            };
+            K2_TRY(launch());
+        }
+        if (merge_bits) {
+            K2_TRY(flag_scan_u32(ctx, head, n_entries, rank, &n_merged));
+        }
+        K2_CUDA(cudaMalloc(&t->merged_w, ((size_t)n_merged + ENTRY_PAD) * sizeof(uint32_t)));
+        K2_CUDA(cudaMemsetAsync(t->merged_w + n_merged, 0, ENTRY_PAD * sizeof(uint32_t), ctx->stream));
+        K2_CUDA(cudaMalloc(&t->msub_offsets, ((size_t)total_sub + 1) * sizeof(uint32_t)));
+        {
+            auto launch = [&]() -> int {
+                if (merge_bits) {
+                    PPF_LAUNCH(ctx, merge_words_kernel, (n_entries + 255) / 256, 256, 0, head, rank, t->entry_w, n_entries, mw_tmp);
+                    PPF_LAUNCH(ctx, merge_offsets_kernel, (total_sub + 1 + 255) / 256, 256, 0, t->sub_offsets, total_sub, rank,
+                               n_entries, n_merged, t->msub_offsets);
+                } else {  // no room for the bin in the sort key: one word per entry, count 1
+                    PPF_LAUNCH(ctx, merge_identity_kernel, (n_entries + 255) / 256, 256, 0, t->entry_w, n_entries, mw_tmp);
+                    PPF_CUDA(ctx, cudaMemcpyAsync(t->msub_offsets, t->sub_offsets, ((size_t)total_sub + 1) * sizeof(uint32_t),
+                                                  cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+                if (!getenv("B200PPF_NO_BANK_SPREAD")) {
+                    const unsigned blocks = (unsigned)std::min<size_t>(((size_t)total_sub + 32 * SPREAD_WARPS - 1) /
+                                                                           (32 * SPREAD_WARPS),
+                                                                       (size_t)ctx->sm_count * 16);
+                    PPF_LAUNCH(ctx, bank_order_kernel, blocks, SPREAD_WARPS * 32, 0, t->msub_offsets, total_sub, mw_tmp, t->merged_w);
+                } else {
+                    PPF_CUDA(ctx, cudaMemcpyAsync(t->merged_w, mw_tmp, (size_t)n_merged * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                                  ctx->stream));
+                }
+                return B200PPF_OK;
+            };
+            K2_TRY(launch());
+        }
+        t->n_merged = n_merged;
+    }
+    info.n_merged = t->n_merged;
     unsigned long long h_cnt = 0;
     K2_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
     K2_CUDA(cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));

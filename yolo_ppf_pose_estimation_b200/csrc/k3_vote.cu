@@ -18,12 +18,16 @@
 //             Buckets are ordered by the phase cell of alpha_m (k2_table.cu): the cells below the
 //             scene pair's phase and the cells above it are two "shift" items whose every vote lands
 //             at (entry's hot word - one constant); the scene phase's own cell is a "per-entry" item;
-//   C  vote   warps pull work items.  Shift items: 4 x 32 hot words in flight per lane, a vote is
-//             load / subtract / add / max / mask / red.shared (ppf_math.cuh "constant-shift voting").
-//             Per-entry items: fixed-point alpha binning with guard bands, the literal
-//             double-precision form inside the bands.
-// Roofline: 4 B (shift) or 8 B (per-entry) gathered + 1 shared atomic per vote,
-// 16 B of CSR offsets per in-radius pair; shared-atomic / L1 throughput binds, not HBM.
+//   C  vote   warps pull work items.  Shift items: 8 x 32 hot words in flight per lane, a vote is
+//             load / subtract / add-min / red.shared (ppf_math.cuh "constant-shift voting").
+//             The scene phase's own cell compares phases per entry; tables whose 2*pi/step is not an
+//             integer bin every entry in fixed point with guard bands, the literal double-precision
+//             form inside the bands.
+// The accumulator slice is bin-major (word = bin * pitch + row, pitch a multiple of 32): the bank of a vote
+// is (row mod 32) whatever the scene pair, and the table build orders every phase cell so that 32
+// consecutive entries hit 32 different banks.
+// Roofline (profiles/): the SM's L1 data pipe — one wavefront per 32 gathered hot words plus one per
+// distinct bank conflict degree of the 32 reductions; HBM sees the table and the scene once.
 #include <algorithm>
 #include <cmath>
 
@@ -50,16 +54,20 @@ constexpr int CAND_CAP = B200PPF_CAND_CAP;  // in-radius candidates buffered bet
 constexpr int VOTE_UNROLL = B200PPF_VOTE_UNROLL;
 static_assert(CAND_CAP >= 2 * VOTE_THREADS_LARGE, "flush threshold must leave one sweep iteration of room");
 
-// One in-radius scene pair with a non-empty bucket [off, off + len): the entries below k_below lie under
-// the scene pair's phase (shift constant c_below), those from k_above on over it (c_below minus one
-// bin), the ones in between — the scene phase's own cell, or the whole bucket — take the per-entry path.
+// One in-radius scene pair with a non-empty bucket.  Phase-sorted tables: the bucket's merged words are
+// [off, off + len); those below k_below lie under the scene pair's phase (shift constant c_below), those from
+// k_above on over it (c_below minus one bin); the scene phase's own cell — or the whole bucket when the phase sits
+// on a cell edge, then k_below = k_above = len — takes the per-entry path over the unmerged entries
+// [e_off, e_off + e_len).  Other tables: off = len = 0, every entry is in [e_off, e_off + e_len).
 struct __align__(16) WorkItem {
     uint32_t off, len;
-    uint32_t k_below, k_above;  // the scene phase's own cell is [k_below, k_above); the whole bucket when it does not split
-    uint32_t c_below;           // constant subtracted from the hot words below the scene phase (shift q + 1)
+    uint32_t k_below, k_above;
+    uint32_t e_off, e_len;      // per-entry range in the unmerged entry arrays
+    uint32_t pad0, pad1;
+    uint32_t c_below;           // constant subtracted from the hot words below the scene phase: 4 * pitch * (q + 1)
     uint32_t c_s;               // per-entry path: alpha_to_fix(alpha_s) - 2^31
     float alpha_s;              // per-entry path: PCL's float (literal form of the guard-band votes)
-    uint32_t pad;
+    uint32_t phi;               // the scene pair's phase inside its bin (fix_shift bits); 0xFFFFFFFF: every entry takes the literal form
 };
 
 // candidate queue + one work item per thread (phase B turns THREADS candidates into items per round)
@@ -76,6 +84,8 @@ struct VoteArgs {
     uint32_t n_s;
     uint32_t ref_first, ref_step, ref_count;
     const uint32_t *sub_offsets;  // phase-cell bounds (bucket bounds when the table has no phase cells)
+    const uint32_t *msub_offsets; // the same bounds in the merged-vote array (phase-sorted tables)
+    const uint32_t *merged_w;     // (count << 24) | hot word
     const uint32_t *entry_w;
     const uint32_t *entry_am;
     const float *entry_alpha;
@@ -98,46 +108,49 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 __device__ __forceinline__ void red_shared_inc(uint32_t addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
+// shared-memory add of a merged vote's count (ATOMS.ADD without a return value)
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_add_if_lt(uint32_t addr, uint32_t v, uint32_t k, uint32_t len) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(k),
+                 "r"(len)
+                 : "memory");
+}
 // the same, predicated on k < len (the partial last step of a shift item)
 __device__ __forceinline__ void red_shared_inc_if_lt(uint32_t addr, uint32_t k, uint32_t len) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"(k), "r"(len)
                  : "memory");
 }
 
-// One vote of a shift item (ppf_math.cuh "constant-shift voting"): c0 = item constant, c1 = c0 - wrap_add
-__device__ __forceinline__ uint32_t shift_address(uint32_t w, uint32_t c0, uint32_t c1, uint32_t lowmask) {
-    const uint32_t t = w - c0, t2 = w - c1;
-    return max(t, t2) & lowmask;
-}
-
-// One vote of the per-entry path (alpha mode A), in fixed point (ppf_math.cuh, alpha_bin_fixed):
-//   X = A_m - C_s  (wraps like the angle),  hi = mulhi(X, T_fix) = bin.position,  (bin, frac) = hi * 2^(32-s).
-// The increment is unconditional — a select is cheaper than a divergent branch — but when frac lies
-// in the guard band around a bin edge (or X in the band around the +-pi seam), or the lane is past
-// the end of the bucket, it is steered to a scratch word; a guard-band hit returns true and the
-// caller settles that entry with the literal double-precision form.
+// One vote of the per-entry path of tables without phase cells (alpha mode A), in fixed point (ppf_math.cuh,
+// alpha_bin_fixed):  X = A_m - C_s  (wraps like the angle),  hi = mulhi(X, T_fix) = bin.position,
+// (bin, frac) = hi * 2^(32-s).  The increment is unconditional — a select is cheaper than a divergent branch —
+// but when frac lies in the guard band around a bin edge (or X in the band around the +-pi seam), or the lane
+// is past the end of the bucket, it is steered to a scratch word; a guard-band hit returns true and the
+// caller settles that entry with the literal double-precision form.  en.x = byte offset of the row.
 template <bool SEAM>
-__device__ __forceinline__ bool vote_fixed(const BinParams &bp, uint32_t acc_addr, uint32_t scratch_addr, uint2 en,
-                                           uint32_t c_s, bool valid) {
+__device__ __forceinline__ bool vote_fixed(const BinParams &bp, uint32_t acc_addr, uint32_t unit, uint32_t scratch_addr,
+                                           uint2 en, uint32_t c_s, bool valid) {
     const uint32_t x = en.y - c_s;
     const uint32_t hi = __umulhi(x, bp.fix_mul);
     const unsigned long long p2 = (unsigned long long)hi * bp.frac_mul;  // runtime multiplier: stays an IMAD (FMA pipe)
     const uint32_t bin = (uint32_t)(p2 >> 32), frac = (uint32_t)p2;
     bool sure = (frac - bp.fix_guard) < (0u - 2u * bp.fix_guard);
     if (SEAM) sure = sure && ((x + bp.seam_guard) >= 2u * bp.seam_guard);
-    red_shared_inc((sure && valid) ? acc_addr + ((en.x + bin) << 2) : scratch_addr);
+    red_shared_inc((sure && valid) ? acc_addr + en.x + unit * bin : scratch_addr);
     return valid && !sure;
 }
 
-// the rare path, and every vote of alpha mode B: literal form on PCL's floats
+// the rare path, and every vote of alpha mode B: literal form on PCL's floats.  row_bytes = 4 * row.
 template <int MODE>
-__device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_addr, uint32_t rowoff, float alpha_m,
-                                           float alpha_s, uint32_t &skipped) {
+__device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_addr, uint32_t unit, uint32_t row_bytes,
+                                           float alpha_m, float alpha_s, uint32_t &skipped) {
     const uint32_t bin = MODE == ALPHA_MODE_B
                              ? alpha_bin_fast(bp, alpha_m, alpha_s)
                              : alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
     if (bin == 0xFFFFFFFFu) ++skipped;  // NaN alpha: no vote
-    else red_shared_inc(acc_addr + ((rowoff + bin) << 2));
+    else red_shared_inc(acc_addr + row_bytes + unit * bin);
 }
 
 template <int MODE, bool SEAM, bool BULK, int THREADS>
@@ -155,9 +168,11 @@ ppf_vote_kernel(const VoteArgs a) {
     const uint32_t slice = blockIdx.y;
     const uint32_t slice_base = slice * a.kp.slice_rows;
     const uint32_t rows = min(a.kp.slice_rows, a.n_model - slice_base);
-    const uint32_t stride = a.bp.row_stride;             // n_alpha + 1 words per model row
-    const uint32_t acc_len = rows * stride;
-    // queues first: the accumulator's shared address must be >= 4 * N_T (shift items subtract up to that)
+    const uint32_t pitch = a.kp.row_pitch;               // words between two alpha columns (multiple of 32)
+    const uint32_t unit = 4u * pitch;                    // bytes per alpha position
+    const uint32_t wrap_bytes = unit * a.bp.n_turn;      // one turn
+    const uint32_t acc_len = a.bp.acc_cols * pitch;
+    // queues first; the accumulator starts on a 128-byte boundary, so a vote's bank is its row mod 32
     uint32_t *cand = reinterpret_cast<uint32_t *>(smem_raw);
     WorkItem *items = reinterpret_cast<WorkItem *>(cand + CAND_CAP);
     uint32_t *acc = reinterpret_cast<uint32_t *>(items + THREADS);
@@ -195,7 +210,8 @@ ppf_vote_kernel(const VoteArgs a) {
 
     const uint32_t lf = a.bp.cells_log2;
     const uint32_t *slice_offsets = a.sub_offsets + (((size_t)slice * a.kp.key_space) << lf);
-    const uint32_t lowmask = (1u << a.bp.low_bits) - 1u;
+    const uint32_t *slice_moffsets = BULK ? a.msub_offsets + (((size_t)slice * a.kp.key_space) << lf) : nullptr;
+    const uint32_t fmask = (1u << a.bp.fix_shift) - 1u;
     uint32_t st_examined = 0, st_in_radius = 0, st_nonempty = 0, st_votes = 0, st_skipped = 0;
 
     // phases B + C over the buffered candidates
@@ -204,8 +220,10 @@ ppf_vote_kernel(const VoteArgs a) {
         for (uint32_t c0 = 0; c0 < ncand; c0 += THREADS) {
             // ---- B: pair features -> work items -------------------------------------------------
             const uint32_t c = c0 + tid;
-            // the bucket [o0, oF) splits at the scene phase's cell [oa, ob): below it, inside it, above it
-            uint32_t o0 = 0, oa = 0, ob = 0, oF = 0, q = 0, c_s = 0;
+            // the bucket [o0, oF) of unmerged entries; phase-sorted tables: its merged words [m0, mF) split at the scene
+            // phase's cell [ma, mb) into below / above, and the cell's own unmerged entries are [oa, ob)
+            uint32_t o0 = 0, oa = 0, ob = 0, oF = 0, q = 0, c_s = 0, phi = 0;
+            uint32_t m0 = 0, ma = 0, mb = 0, mF = 0;
             float alpha_s = 0.0f;
             if (tid < THREADS && c < ncand) {
                 const uint32_t s = cand[c];
@@ -220,18 +238,28 @@ ppf_vote_kernel(const VoteArgs a) {
                         const uint32_t *so = slice_offsets + ((size_t)key << lf);
                         o0 = __ldg(so);
                         oF = __ldg(so + (1u << lf));
-                        oa = ob = oF;  // empty bucket: no item
+                        oa = o0;
+                        ob = oF;  // the whole bucket takes the per-entry path unless it splits below
                         if (oF > o0) {
                             alpha_s = planar_alpha(s_sg, v3_of(p4));
                             c_s = alpha_to_fix(alpha_s) - 0x80000000u;
                             ++st_nonempty;
-                            uint32_t cell;
-                            if (BULK && phase_split(a.bp, c_s, q, cell)) {
-                                oa = __ldg(so + cell);
-                                ob = __ldg(so + cell + 1);
-                            } else {  // the whole bucket takes the per-entry path
-                                oa = o0;
-                                ob = oF;
+                            st_votes += oF - o0;
+                            if (BULK) {
+                                uint32_t cell;
+                                const bool split = phase_split(a.bp, c_s, q, cell);
+                                // per-entry phase comparison needs the scene pair's own position; in the sliver
+                                // between N_T and T (q == N_T) every entry takes the literal form
+                                phi = q < a.bp.n_turn ? (phase_of_fix(a.bp, c_s) & fmask) : 0xFFFFFFFFu;
+                                if (split) {
+                                    const uint32_t *mo = slice_moffsets + ((size_t)key << lf);
+                                    m0 = __ldg(mo);
+                                    mF = __ldg(mo + (1u << lf));
+                                    ma = __ldg(mo + cell);
+                                    mb = __ldg(mo + cell + 1);
+                                    oa = __ldg(so + cell);
+                                    ob = __ldg(so + cell + 1);
+                                }
                             }
                         }
                     }
@@ -240,7 +268,8 @@ ppf_vote_kernel(const VoteArgs a) {
             // Items enter the queue longest class first (classes = powers of two of the bucket length): the
             // warps then finish on short items and the CTA's barrier is not held up by one long bucket.
             const bool push = oF > o0;
-            const uint32_t cls = push ? (uint32_t)min(7, max(0, 23 - (int)__clz(oF - o0))) : 8u + (lane & 7u);
+            const uint32_t work = (mF - m0) + (ob - oa);  // words this item walks
+            const uint32_t cls = push ? (uint32_t)min(7, max(0, 23 - (int)__clz(work))) : 8u + (lane & 7u);
             uint32_t rank = 0;
             {
                 const uint32_t same = __match_any_sync(0xFFFFFFFFu, cls);
@@ -256,14 +285,17 @@ ppf_vote_kernel(const VoteArgs a) {
 #pragma unroll
                 for (uint32_t k = 7; k > 0; --k) slot += (k > cls) ? s_cls[k] : 0u;
                 WorkItem it;
-                it.off = o0;
-                it.len = oF - o0;
-                it.k_below = oa - o0;
-                it.k_above = ob - o0;
-                it.c_below = ((q + 1u) << a.bp.low_bits) + 4u * (q + 1u) - acc_addr;
+                it.off = m0;
+                it.len = mF - m0;
+                it.k_below = ma - m0;
+                it.k_above = mb - m0;
+                it.e_off = oa;
+                it.e_len = ob - oa;
+                it.pad0 = it.pad1 = 0;
+                it.c_below = unit * (q + 1u);
                 it.c_s = c_s;
                 it.alpha_s = alpha_s;
-                it.pad = 0;
+                it.phi = phi;
                 items[slot] = it;
             }
             if (tid == 0) {
@@ -282,48 +314,95 @@ ppf_vote_kernel(const VoteArgs a) {
                 if (w >= nitems) break;
                 const WorkItem wi = items[w];
                 const uint32_t len = wi.len;
-                const uint32_t *wp = a.entry_w + wi.off;
-                if (lane == 0) st_votes += len;
-                // shift range [kb, ke): every vote is hot word - constant (wrapped through the max).  The entry
+                const uint32_t *mp = a.merged_w + wi.off;
+                // shift range [kb, ke) of merged words: count votes at umin(hot word - c, hot word - c + one turn).  The
                 // arrays carry ENTRY_PAD readable words past the end, so the partial batch loads unclamped.
                 auto shift_range = [&](uint32_t kb, uint32_t ke, uint32_t c0v) {
-                    const uint32_t c1v = c0v - a.bp.wrap_add;
+                    const uint32_t c1v = c0v - wrap_bytes;
                     uint32_t k0 = kb + lane;
-                    // long ranges: 8 x 32 hot words in flight per lane (the gathers are latency-bound)
+                    auto vote = [&](uint32_t w) {
+                        const uint32_t off = w & 0xFFFFFFu;
+                        red_shared_add(acc_addr + min(off - c0v, off - c1v), w >> 24);
+                    };
+                    // long ranges: 8 x 32 words in flight per lane (the gathers are latency-bound)
                     for (; k0 - lane + 64 * VOTE_UNROLL <= ke; k0 += 64 * VOTE_UNROLL) {  // warp-uniform: a double batch
                         uint32_t hw[2 * VOTE_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < 2 * VOTE_UNROLL; ++u) hw[u] = __ldg(wp + k0 + u * 32);
+                        for (int u = 0; u < 2 * VOTE_UNROLL; ++u) hw[u] = __ldg(mp + k0 + u * 32);
 #pragma unroll
-                        for (int u = 0; u < 2 * VOTE_UNROLL; ++u) red_shared_inc(shift_address(hw[u], c0v, c1v, lowmask));
+                        for (int u = 0; u < 2 * VOTE_UNROLL; ++u) vote(hw[u]);
                     }
                     if (k0 - lane + 32 * VOTE_UNROLL <= ke) {  // warp-uniform: one more full batch
                         uint32_t hw[VOTE_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(wp + k0 + u * 32);
+                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(mp + k0 + u * 32);
 #pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u) red_shared_inc(shift_address(hw[u], c0v, c1v, lowmask));
+                        for (int u = 0; u < VOTE_UNROLL; ++u) vote(hw[u]);
                         k0 += 32 * VOTE_UNROLL;
                     }
                     if (k0 - lane < ke) {  // warp-uniform: a partial batch remains; votes are predicated
                         uint32_t hw[VOTE_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(wp + k0 + u * 32);
+                        for (int u = 0; u < VOTE_UNROLL; ++u) hw[u] = __ldg(mp + k0 + u * 32);
 #pragma unroll
-                        for (int u = 0; u < VOTE_UNROLL; ++u)
-                            red_shared_inc_if_lt(shift_address(hw[u], c0v, c1v, lowmask), k0 + u * 32, ke);
+                        for (int u = 0; u < VOTE_UNROLL; ++u) {
+                            const uint32_t off = hw[u] & 0xFFFFFFu;
+                            red_shared_add_if_lt(acc_addr + min(off - c0v, off - c1v), hw[u] >> 24, k0 + u * 32, ke);
+                        }
                     }
                 };
                 if (BULK) {
                     if (wi.k_below) shift_range(0u, wi.k_below, wi.c_below);
-                    if (wi.k_above < len) shift_range(wi.k_above, len, wi.c_below - ((1u << a.bp.low_bits) + 4u));
+                    if (wi.k_above < len) shift_range(wi.k_above, len, wi.c_below - unit);
                 }
-                if (wi.k_below < wi.k_above) {
-                    if (MODE == ALPHA_MODE_A) {
-                        // per-entry range: branch-free fixed-point votes, 32 entries per step (two steps in
+                if (wi.e_len) {
+                    // per-entry range [0, e_end) of the unmerged entry arrays
+                    const uint32_t *wp = a.entry_w + wi.e_off;
+                    const uint32_t *ap = a.entry_am + wi.e_off;
+                    const float *fp = a.entry_alpha + wi.e_off;
+                    const uint32_t e_end = wi.e_len;
+                    if (BULK && wi.phi != 0xFFFFFFFFu) {
+                        // the scene phase's own cell (or the whole bucket when the phase sits on a cell edge): an entry
+                        // whose phase is below the scene's shifts by q + 1, the others by q; within the guard band of
+                        // the scene phase the literal form decides.  32 entries per step, two steps in flight.
+                        const uint32_t guard = a.bp.phase_guard;
+                        for (uint32_t k0 = lane; k0 - lane < e_end; k0 += 64) {  // warp-uniform
+                            uint2 en[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) en[u] = make_uint2(__ldg(wp + k0 + u * 32), __ldg(ap + k0 + u * 32));
+                            bool risky[2];
+                            uint32_t pu[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                risky[u] = false;
+                                if (k0 - lane + u * 32 < e_end) {  // warp-uniform
+                                    pu[u] = __umulhi(en[u].y, a.bp.fix_mul);
+                                    const int d = (int)(pu[u] & fmask) - (int)wi.phi;
+                                    const bool valid = k0 + u * 32 < e_end;
+                                    const bool sure = (uint32_t)(d + (int)guard) >= 2u * guard;
+                                    const uint32_t c = wi.c_below - (d >= 0 ? unit : 0u);
+                                    red_shared_inc((sure && valid) ? acc_addr + min(en[u].x - c, en[u].x - c + wrap_bytes)
+                                                                   : scratch_addr);
+                                    risky[u] = valid && !sure;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 2; ++u)
+                                if (risky[u])
+                                    vote_exact<MODE>(a.bp, acc_addr, unit, en[u].x - unit * phase_bin(a.bp, pu[u]),
+                                                     __ldg(fp + k0 + u * 32), wi.alpha_s, st_skipped);
+                        }
+                    } else if (BULK) {
+                        // the sliver between N_T and T: literal form for every entry (one scene pair in ~10^7)
+                        for (uint32_t k = lane; k < e_end; k += 32) {
+                            const uint32_t w = __ldg(wp + k);
+                            vote_exact<MODE>(a.bp, acc_addr, unit, w - unit * phase_bin(a.bp, __umulhi(__ldg(ap + k), a.bp.fix_mul)),
+                                             __ldg(fp + k), wi.alpha_s, st_skipped);
+                        }
+                    } else if (MODE == ALPHA_MODE_A) {
+                        // tables without phase cells: branch-free fixed-point votes, 32 entries per step (two steps in
                         // flight); lanes past the end read the padding and vote into the scratch word
-                        const uint32_t *ap = a.entry_am + wi.off;
-                        for (uint32_t k0 = wi.k_below + lane; k0 - lane < wi.k_above; k0 += 64) {  // warp-uniform
+                        for (uint32_t k0 = lane; k0 - lane < e_end; k0 += 64) {  // warp-uniform
                             uint2 en[2];
 #pragma unroll
                             for (int u = 0; u < 2; ++u) en[u] = make_uint2(__ldg(wp + k0 + u * 32), __ldg(ap + k0 + u * 32));
@@ -331,22 +410,20 @@ ppf_vote_kernel(const VoteArgs a) {
 #pragma unroll
                             for (int u = 0; u < 2; ++u) {
                                 risky[u] = false;
-                                if (k0 - lane + u * 32 < wi.k_above) {  // warp-uniform
-                                    en[u].x = hot_word_row_words(a.bp, en[u].x);
-                                    risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, scratch_addr, en[u], wi.c_s,
-                                                                k0 + u * 32 < wi.k_above);
-                                }
+                                if (k0 - lane + u * 32 < e_end)  // warp-uniform
+                                    risky[u] = vote_fixed<SEAM>(a.bp, acc_addr, unit, scratch_addr, en[u], wi.c_s,
+                                                                k0 + u * 32 < e_end);
                             }
 #pragma unroll
                             for (int u = 0; u < 2; ++u)
                                 if (risky[u])
-                                    vote_exact<MODE>(a.bp, acc_addr, en[u].x, __ldg(a.entry_alpha + wi.off + k0 + u * 32),
+                                    vote_exact<MODE>(a.bp, acc_addr, unit, en[u].x, __ldg(fp + k0 + u * 32),
                                                      wi.alpha_s, st_skipped);
                         }
                     } else {
-                        for (uint32_t k = wi.k_below + lane; k < wi.k_above; k += 32)
-                            vote_exact<MODE>(a.bp, acc_addr, hot_word_row_words(a.bp, __ldg(wp + k)),
-                                             __ldg(a.entry_alpha + wi.off + k), wi.alpha_s, st_skipped);
+                        for (uint32_t k = lane; k < e_end; k += 32)
+                            vote_exact<MODE>(a.bp, acc_addr, unit, __ldg(wp + k), __ldg(fp + k), wi.alpha_s,
+                                             st_skipped);
                     }
                 }
             }
@@ -407,16 +484,16 @@ ppf_vote_kernel(const VoteArgs a) {
     flush();
 
     // ---- peak: first maximum in (i, bin) order == max of (votes, ~flat) ---------------------------
-    // one thread per model row: the spare cell n_alpha (bins past the last column) joins column n_alpha - 1 under
-    // the FLOOR_CLAMP rule and is ignored otherwise (FLOOR_DROP: the vote is lost; CEIL: it stays empty)
+    // one thread per model row (consecutive threads read consecutive words of a column): the spare column n_alpha
+    // (bins past the last column) joins column n_alpha - 1 under the FLOOR_CLAMP rule and is ignored otherwise
+    // (FLOOR_DROP: the vote is lost; CEIL: there is no such column)
     const uint32_t n_alpha = a.bp.n_alpha;
     unsigned long long best = 0;
     for (uint32_t r = tid; r < rows; r += THREADS) {
-        uint32_t *row = acc + r * stride;
-        if (a.bp.fold) row[n_alpha - 1] += row[n_alpha];
         uint32_t bv = 0, bc = 0;
         for (uint32_t c = 0; c < n_alpha; ++c) {
-            const uint32_t v = row[c];
+            uint32_t v = acc[c * pitch + r];
+            if (a.bp.fold && c == n_alpha - 1) v += acc[n_alpha * pitch + r];
             if (v > bv) {  // strict: the first maximum of the row
                 bv = v;
                 bc = c;
@@ -444,7 +521,8 @@ ppf_vote_kernel(const VoteArgs a) {
         atomicAdd(&s_stat[0], (unsigned long long)st_examined);
         atomicAdd(&s_stat[1], (unsigned long long)st_in_radius);
         atomicAdd(&s_stat[2], (unsigned long long)st_nonempty);
-        atomicAdd(&s_stat[3], (unsigned long long)(st_votes - st_skipped));
+        atomicAdd(&s_stat[3], (unsigned long long)st_votes);
+        atomicAdd(&s_stat[3], 0ull - (unsigned long long)st_skipped);  // NaN alphas cast no vote
     }
     __syncthreads();
     if (tid == 0) {
@@ -541,7 +619,7 @@ __global__ void debug_alpha_bins_kernel(BinParams bp, const float *__restrict__ 
 }
 
 size_t accumulator_bytes(const b200ppf_table *t) {
-    return (size_t)t->info.slice_rows * (t->info.n_alpha + 1) * sizeof(uint32_t);
+    return (size_t)t->kp.row_pitch * t->bp.acc_cols * sizeof(uint32_t);
 }
 // launch shape of a table: 512 x 2 CTAs/SM when the slice is small enough, else 1024 x 1
 int vote_threads(const b200ppf_table *t) {
@@ -583,6 +661,8 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     a.ref_step = (uint32_t)ref_step;
     a.ref_count = (uint32_t)ref_count;
     a.sub_offsets = t->sub_offsets ? t->sub_offsets : t->offsets;
+    a.msub_offsets = t->msub_offsets;
+    a.merged_w = t->merged_w;
     a.entry_w = t->entry_w;
     a.entry_am = t->entry_am;
     a.entry_alpha = t->entry_alpha;
@@ -665,7 +745,7 @@ BinParams make_bin_params(float angle_step, int alpha_mode, int nalpha_rule) {
     bp.mode = alpha_mode;
     bp.mode_b_offset = (int)floor(M_PI / (double)angle_step);
     bp.guard = std::max(2e-4f, 1e-5f * bp.inv_step);
-    bp.row_stride = bp.n_alpha + 1;
+    bp.acc_cols = nalpha_rule == NALPHA_CEIL ? bp.n_alpha : bp.n_alpha + 1;
     // fixed-point hot loop: T bins per turn, multiplier with as many fractional bits as fit 32 bits
     const double T = 2.0 * M_PI / (double)angle_step;
     int kbits = 1;
@@ -686,20 +766,13 @@ BinParams make_bin_params(float angle_step, int alpha_mode, int nalpha_rule) {
     bp.bulk = 0;
     bp.n_turn = (uint32_t)llrint(T);
     bp.cells_log2 = 0;
-    bp.low_bits = 31;
-    bp.field_bias = 0;
-    bp.wrap_add = 0;
     bp.phase_guard = 0;
     const double off_int = fabs(T - (double)bp.n_turn);
-    int fbits = 1;
-    while ((1u << fbits) < 2u * bp.n_turn) ++fbits;
-    if (alpha_mode == ALPHA_MODE_A && bp.n_turn >= 2 && fbits <= 13 && off_int < 0.25 * guard_bins) {
+    // the spare column must be able to hold position N_T - 1 and the column count must cover one turn
+    if (alpha_mode == ALPHA_MODE_A && bp.n_turn >= 2 && bp.n_turn <= bp.acc_cols && off_int < 0.25 * guard_bins) {
         const double unit = (double)(1u << bp.fix_shift);
         bp.bulk = 1;
         bp.cells_log2 = 4;
-        bp.low_bits = 32u - (uint32_t)fbits;
-        bp.field_bias = (1u << fbits) - bp.n_turn;
-        bp.wrap_add = (bp.n_turn << bp.low_bits) + 4u * bp.n_turn;
         bp.phase_guard = (uint32_t)ceil(guard_bins * unit) + (uint32_t)ceil(off_int * unit) + 16u;
         // the guard must stay a small part of a phase cell
         while (bp.cells_log2 > 0 && 8ull * bp.phase_guard > (1ull << (bp.fix_shift - bp.cells_log2))) --bp.cells_log2;

@@ -78,6 +78,11 @@ struct b200ppf_table {
     uint32_t *entry_am = nullptr;     // alpha_m as fixed-point turns (per-entry path)
     float *entry_alpha = nullptr;  // alpha_m as PCL's float (guard-band votes, alpha_m_ export)
     uint32_t *entry_idx = nullptr;  // i*n + j per entry (API queries, alpha_m_ export)
+    // phase-sorted tables: the entries of a cell that share (model row, bin of alpha_m) cast the same vote for every
+    // scene pair whose phase lies in another cell — they are merged into one word with a count
+    uint32_t *merged_w = nullptr;      // (count << 24) | hot word, bank-ordered inside each cell
+    uint32_t *msub_offsets = nullptr;  // phase-cell bounds in merged_w, same indexing as sub_offsets
+    size_t n_merged = 0;
     int feature_mode = 0;
 };
 
@@ -152,6 +157,9 @@ int k5_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float *pose
 int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cloud *scene, int max_iterations,
                   float tolerance, float rejection_scale, int num_levels, double *poses16_host, size_t n_poses,
                   double *residuals_host, uint64_t *iterations_host);
+
+// exclusive scan of 0/1 flags on the context stream (prep.cu): rank[k] = set flags before k; total on the host
+int flag_scan_u32(b200ppf_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t *rank, uint32_t *total_host);
 
 // scene pre-processing (prep.cu): voxel grid, k nearest neighbours, outlier removal, normals, curvature edges
 int prep_upload_xyz(b200ppf_ctx *ctx, const float *host, size_t n, size_t stride, b200ppf_cloud **out);

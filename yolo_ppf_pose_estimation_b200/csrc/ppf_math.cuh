@@ -201,7 +201,7 @@ struct BinParams {
     int mode_b_offset;  // floor(pi / angle_step)
     float guard;        // max(2e-4, 1e-5 / angle_step): > 20x the fp32 estimate's error bound
     // fixed-point form of the hot loop (alpha_bin_fixed below)
-    uint32_t row_stride;   // accumulator row stride = n_alpha + 1: the spare cell n_alpha takes the bins past the last column
+    uint32_t acc_cols;     // accumulator columns held in shared memory: n_alpha, plus the spare column n_alpha under the FLOOR rules
     uint32_t fix_mul;      // round(T * 2^fix_shift), T = 2*pi/angle_step bins per turn
     uint32_t fix_shift;    // fractional bits of fix_mul: high word of X*fix_mul = bin . (fix_shift-bit position inside the bin)
     uint32_t frac_mul;     // 2^(32 - fix_shift): a second multiply splits that word into (bin, position << (32-fix_shift))
@@ -211,9 +211,6 @@ struct BinParams {
     uint32_t bulk;         // 1 when the table carries phase cells and hot words
     uint32_t n_turn;       // N_T = round(T): alpha positions per turn
     uint32_t cells_log2;   // log2 of the phase cells per bucket (0: buckets are not subdivided)
-    uint32_t low_bits;     // a hot word = wrap field (32 - low_bits bits) | byte offset of (row, B_e) (low_bits bits)
-    uint32_t field_bias;   // 2^field_bits - N_T: the field holds B_e + field_bias
-    uint32_t wrap_add;     // (N_T << low_bits) + 4 * N_T
     uint32_t phase_guard;  // guard band around the scene phase, in 2^-fix_shift bins
 };
 
@@ -222,28 +219,36 @@ struct BinParams {
 // c = (alpha_s / step) mod T = q + phi, PCL's bin is floor((u_e - c) mod T).  When T is an integer
 // N_T (up to the guard band) this is (B_e - q - [f_e < phi]) mod N_T: inside a bucket whose entries
 // are ordered by phase cell, every entry of the cells below phi's cell shifts by q + 1, every entry
-// of the cells above it by q, and only phi's own cell needs the per-entry arithmetic.  A hot word
-// packs the wrap test and the accumulator address into one 32-bit value so that a vote of those two
-// ranges is: load, subtract the per-range constant, add, max, mask, shared-memory reduction.
-//   word  = (B_e + 2^b - N_T) << low_bits | (row byte offset + 4 * B_e)
-//   const = q' << low_bits | (4 * q' - accumulator base)          (q' = q or q + 1)
-//   t = word - const ; address = max(t, t + wrap_add) & (2^low_bits - 1)
-// 2^b = smallest power of two >= 2 * N_T: the field of t is >= 2^b - N_T exactly when B_e >= q'
-// (no wrap), and adding N_T overflows the field exactly then, so the unsigned max picks the wrapped
-// sum only when B_e < q'.
+// of the cells above it by q, and phi's own cell decides per entry by comparing the phases.
+//
+// The accumulator slice is held BIN-MAJOR: word(bin, row) = bin * pitch + row, pitch = the slice's rows
+// rounded up to a multiple of 32.  A hot word is the byte offset of the entry's own cell,
+//   word = 4 * (B_e * pitch + row),
+// and a vote with shift q' is
+//   t = word - 4 * pitch * q' ;  offset = umin(t, t + 4 * pitch * N_T)
+// (t is "negative", i.e. huge as an unsigned number, exactly when B_e < q', and adding one turn then wraps
+// it back into range).  Because pitch is a multiple of 32, neither the shift nor the wrap changes the
+// shared-memory bank of the vote: it is (row mod 32) for every scene pair, which is what lets the table
+// build order each phase cell so that 32 consecutive entries hit 32 different banks (k2_table.cu).
 __host__ __device__ __forceinline__ uint32_t phase_of_fix(const BinParams &bp, uint32_t a_fix) {
     return (uint32_t)(((unsigned long long)a_fix * bp.fix_mul) >> 32);  // B . f with fix_shift fractional bits
 }
 __host__ __device__ __forceinline__ uint32_t phase_cell(const BinParams &bp, uint32_t u) {
     return (u & ((1u << bp.fix_shift) - 1u)) >> (bp.fix_shift - bp.cells_log2);
 }
-__host__ __device__ __forceinline__ uint32_t hot_word(const BinParams &bp, uint32_t row_bytes, uint32_t u) {
+// integer position B_e of a phase word (T a hair above N_T: the sliver is the start of the turn)
+__host__ __device__ __forceinline__ uint32_t phase_bin(const BinParams &bp, uint32_t u) {
     uint32_t B = u >> bp.fix_shift;
-    if (B >= bp.n_turn) B -= bp.n_turn;  // T a hair above N_T: the sliver is the start of the turn
-    return ((B + bp.field_bias) << bp.low_bits) | (row_bytes + 4u * B);
+    if (B >= bp.n_turn) B -= bp.n_turn;
+    return B;
 }
-__host__ __device__ __forceinline__ uint32_t hot_word_row_words(const BinParams &bp, uint32_t w) {
-    return ((w & ((1u << bp.low_bits) - 1u)) >> 2) - ((w >> bp.low_bits) - bp.field_bias);
+__host__ __device__ __forceinline__ uint32_t hot_word(const BinParams &bp, uint32_t pitch, uint32_t row, uint32_t u) {
+    return 4u * (phase_bin(bp, u) * pitch + row);
+}
+// byte offset of a vote: the hot word shifted by q' alpha positions (c = 4 * pitch * q'), wrapped
+__host__ __device__ __forceinline__ uint32_t shifted_offset(uint32_t w, uint32_t c, uint32_t wrap_bytes) {
+    const uint32_t t = w - c, t2 = t + wrap_bytes;
+    return t < t2 ? t : t2;
 }
 // scene side: returns false when the whole bucket must take the per-entry path
 __host__ __device__ __forceinline__ bool phase_split(const BinParams &bp, uint32_t c_s, uint32_t &q, uint32_t &cell) {
@@ -325,25 +330,35 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_hot(const BinParams &bp, 
     return b >= bp.n_alpha ? bp.overflow_bin : b;
 }
 
-// what the voting kernel computes for one (entry, scene pair) of a phase-sorted table: the
-// constant-shift form outside the scene phase's cell, the per-entry form inside it
+// what the voting kernel computes for one (entry, scene pair) of a phase-sorted table: the constant-shift form
+// outside the scene phase's cell, the phase comparison inside it (the literal form within the guard band)
 __host__ __device__ __forceinline__ uint32_t alpha_bin_phase(const BinParams &bp, float alpha_m, float alpha_s) {
     if (!bp.bulk || bp.mode == ALPHA_MODE_B) return alpha_bin_hot(bp, alpha_m, alpha_s);
     if (alpha_m != alpha_m || alpha_s != alpha_s) return 0xFFFFFFFFu;
     if (!(fabsf(alpha_m) <= 3.14159274f && fabsf(alpha_s) <= 3.14159274f)) return alpha_bin_hot(bp, alpha_m, alpha_s);
     const uint32_t u = phase_of_fix(bp, alpha_to_fix(alpha_m));
+    const uint32_t c_s = alpha_to_fix(alpha_s) - 0x80000000u;
     uint32_t q, cell;
-    if (!phase_split(bp, alpha_to_fix(alpha_s) - 0x80000000u, q, cell)) return alpha_bin_hot(bp, alpha_m, alpha_s);
+    const bool split = phase_split(bp, c_s, q, cell);
+    if (q >= bp.n_turn)  // the scene pair sits in the sliver between N_T and T: the literal form for every entry
+        return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
     const uint32_t ce = phase_cell(bp, u);
-    if (ce == cell) return alpha_bin_hot(bp, alpha_m, alpha_s);
-    // the kernel's own integer path, address arithmetic included (accumulator base 4 * N_T, row 0)
-    const uint32_t w = hot_word(bp, 0u, u);
-    const uint32_t qp = q + (ce < cell ? 1u : 0u);
-    const uint32_t base = 4u * bp.n_turn;
-    const uint32_t cst = (qp << bp.low_bits) + 4u * qp - base;
-    const uint32_t t = w - cst, t2 = t + bp.wrap_add;
-    const uint32_t addr = (t > t2 ? t : t2) & ((1u << bp.low_bits) - 1u);
-    const uint32_t b = (addr - base) >> 2;
+    uint32_t qp;
+    if (split && ce != cell) {
+        qp = q + (ce < cell ? 1u : 0u);
+    } else {
+        // the scene phase's own cell — or the whole bucket when the scene phase is close to a cell edge
+        const uint32_t fmask = (1u << bp.fix_shift) - 1u;
+        const uint32_t phi = phase_of_fix(bp, c_s) & fmask;
+        const int d = (int)(u & fmask) - (int)phi;
+        if ((uint32_t)(d + (int)bp.phase_guard) < 2u * bp.phase_guard)
+            return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
+        qp = q + (d < 0 ? 1u : 0u);
+    }
+    // the kernel's own integer path, address arithmetic included (pitch 32, row 5)
+    const uint32_t pitch = 32u, unit = 4u * pitch;
+    const uint32_t off = shifted_offset(hot_word(bp, pitch, 5u, u), unit * qp, unit * bp.n_turn);
+    const uint32_t b = off / unit;
     return b >= bp.n_alpha ? bp.overflow_bin : b;
 }
 
@@ -471,6 +486,8 @@ struct KeyParams {
     uint32_t key_space;   // size[0]*size[1]*size[2]*size[3]
     uint32_t slice_rows;  // model rows per accumulator slice
     uint32_t n_slices;
+    uint32_t row_pitch;   // slice_rows rounded up to a multiple of 32: words between two alpha columns of the accumulator
+    uint32_t merge_bits;  // bits of alpha_m's bin appended to the sort key (phase-sorted tables with merged votes), else 0
 };
 
 __host__ __device__ __forceinline__ void quantise(const KeyParams &kp, const float *f, int *d) {

@@ -755,6 +755,10 @@ struct EventTimer {  // prep_ms of the timings block
 
 }  // namespace
 
+int flag_scan_u32(b200ppf_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t *rank, uint32_t *total_host) {
+    return flag_scan(ctx, flags, n, rank, total_host);
+}
+
 // ================================================================================================================
 // host entry points (called from capi.cu)
 
