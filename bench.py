@@ -162,8 +162,9 @@ class ClockSampler:
 def oracle_table(wl, model=None):
     from oracle import binding as ob
     ob.build()
-    feats = ob.ppf_estimation(wl.model if model is None else model)
-    hm = ob.HashMap(wl.angle_step, wl.dist_step).set_input_feature_cloud(feats)
+    th = host_threads()  # the container is built sharded by key over the host cores: same buckets, seconds instead of minutes
+    feats = ob.ppf_estimation(wl.model if model is None else model, n_threads=th)
+    hm = ob.HashMap(wl.angle_step, wl.dist_step).set_input_feature_cloud(feats, n_threads=th)
     return ob, hm
 
 
@@ -181,8 +182,9 @@ SAMPLE_SLOTS = 64
 def sample_list(wl):
     """The fixed CPU sample of a workload: 64 reference slots spread evenly over the scene (slot k sits in the middle
     of the k-th 64th), listed in bit-reversed order so that every prefix — and every run of consecutive entries — is
-    itself evenly spread.  Scene arrays are grouped by surface (object, ground, walls, clutter), so an even spread is
-    a stratified sample.  Returns reference-point indices into the scene."""
+    itself evenly spread.  The synthetic scenes are stored in a fixed pseudo-random order, so an even spread is a uniform
+    random sample of the surfaces (object, ground, walls, clutter), the same on every box.  Returns reference-point
+    indices into the scene."""
     n = min(SAMPLE_SLOTS, wl.n_ref)
     bits = max(1, (n - 1).bit_length())
     order = [int(format(k, f"0{bits}b")[::-1], 2) for k in range(1 << bits)]
@@ -312,24 +314,22 @@ def run_b200(args, wl):
     scene_pinned = torch.from_numpy(np.ascontiguousarray(wl.scene, np.float32)).pin_memory()
     n_s = wl.scene.shape[0]
 
-    # ---- several GPUs: the record exchange is fused into the vote epilogue (NVLink peer stores) -----------
+    # ---- several GPUs: b200ppf_group_* — the record exchange is fused into the vote epilogue (NVLink peer stores), the
+    # per-step barrier is a flag the peers' kernels raise and a one-thread kernel awaits: no torch.distributed call in a step
     p2p = world > 1 and not lib_mode and args.exchange == "p2p"
-    peer_sets, step_no = [], [0]
+    group = None
     if p2p:
-        for _ in range(2):  # two buffer sets, alternating per step: a rank may be one step ahead of a peer that still clusters
-            own_ptr, handle = ctx.hyp_buffer_create(chunk * world)
-            handles = [None] * world
-            dist.all_gather_object(handles, handle)
-            peer_sets.append([own_ptr if r == rank else ctx.hyp_buffer_open(handles[r]) for r in range(world)])
+        group = capi.Group(ctx, rank, world, chunk * world)
+        handles = [None] * world
+        dist.all_gather_object(handles, group.handles.tobytes())   # bootstrap only: 192 bytes per rank, once
+        group.connect([np.frombuffer(h, np.uint8) for h in handles])
 
     def align(ds, collect=None):
-        """vote (this rank's shard) -> all-gather -> cluster, once per model of this rank; returns the last (poses, votes)."""
+        """vote (this rank's shard) -> exchange -> cluster, once per model of this rank; returns the last (poses, votes)."""
         res = (np.zeros((0, 4, 4), np.float32), np.zeros(0, np.uint32))
         for dm, table in zip(dms, tables):
             if p2p:
-                peers = peer_sets[step_no[0] % 2]
-                step_no[0] += 1
-                ctx.vote_scatter_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, peers, rank, world)
+                group.vote(dm, table, ds, wl.ref_rate)
             else:
                 ctx.vote_device(dm, table, ds, first * wl.ref_rate, step * wl.ref_rate, count, local_buf.data_ptr())
             if collect is not None:  # untimed bookkeeping pass: work counters and kernel time of every model
@@ -338,9 +338,7 @@ def run_b200(args, wl):
                     collect[k] = collect.get(k, 0) + v
                 collect["vote_ms"] = collect.get("vote_ms", 0.0) + ctx.timings()["vote_ms"]
             if p2p:
-                with torch.cuda.stream(stream):
-                    dist.barrier()  # every rank's records have landed in every buffer
-                res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=peers[rank], n=n_ref)
+                res = group.cluster(n_ref, wl.pos_thr, wl.rot_thr)
             elif world > 1 and not lib_mode:
                 with torch.cuda.stream(stream):
                     ordered = sharding.all_gather_hypotheses(local_buf, n_ref, world, dist)
@@ -445,8 +443,8 @@ def run_b200(args, wl):
                     "alpha_columns": int(info.n_alpha), "phase_cells": int(info.phase_cells),
                     "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode
                                  else (f"reference points interleaved over {world} rank(s), table + scene replicated, 64 B "
-                                       f"hypotheses exchanged by " + ("the vote epilogue's NVLink peer stores" if p2p
-                                                                      else "an NCCL all-gather")) if world > 1 else "single GPU")},
+                                       f"hypotheses exchanged by " + ("b200ppf_group: the vote epilogue's NVLink peer stores + device-side flags"
+                                                                      if p2p else "an NCCL all-gather")) if world > 1 else "single GPU")},
             "ms_per_pose": ms_per_step / len(library),
             "votes_per_sec": nvotes / (ms_per_step * 1e-3),
             "pairs_examined_per_sec": examined / (ms_per_step * 1e-3),

@@ -89,7 +89,7 @@ typedef struct b200ppf_hypothesis {
 typedef struct b200ppf_table_info {
     uint64_t n_model;     /* model points */
     uint64_t n_entries;   /* valid ordered pairs stored */
-    uint64_t n_keys;      /* non-empty buckets */
+    uint64_t n_keys;      /* distinct keys (non-empty buckets of the multimap) */
     uint64_t key_space;   /* dense packed-key range per slice */
     uint32_t n_slices;    /* model-row slices (accumulator tiles), 1 for small models */
     uint32_t slice_rows;  /* model rows per slice */
@@ -164,6 +164,8 @@ int b200ppf_table_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host)
  * Any pointer may be NULL. */
 int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *offsets,
                          uint32_t *entry_i, uint32_t *entry_j, float *entry_alpha_m);
+/* a copy of a table on another context's device (device-to-device; NVLink between peers) */
+int b200ppf_table_clone(b200ppf_ctx *dst, const b200ppf_table *src, b200ppf_table **out);
 void b200ppf_table_free(b200ppf_table *t);
 
 /* Trained-model persistence.  The reference never trains at run time: it deserialises a detector it
@@ -208,6 +210,52 @@ int b200ppf_vote_scatter_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, co
                                 const b200ppf_cloud *scene, size_t ref_first, size_t ref_step,
                                 size_t ref_count, b200ppf_hypothesis *const *peer_buffers, int n_peers,
                                 size_t slot_first, size_t slot_step);
+/* ---- several GPUs behind the ABI --------------------------------------------------------------------------------
+ * PPFRegistration::align with the scene reference points interleaved over G GPUs.  Every rank votes on
+ * its share against its own replica of the table and the scene; the hypothesis records are exchanged by the vote
+ * epilogue itself (peer stores into every rank's buffer over NVLink) and a per-step flag, raised by each rank's last
+ * block and awaited by a one-thread kernel on every rank's stream, separates voting from clustering: no host
+ * synchronisation and no collective call on the path.
+ *   b200ppf_group_*   one process per GPU (torchrun / MPI): create -> exchange the B200PPF_GROUP_HANDLE_BYTES blobs of
+ *                     all ranks by any means (rank order) -> connect -> register per frame.  Every rank returns the
+ *                     same poses (clustering is deterministic and runs on every rank's own complete copy).
+ *   b200ppf_multi_*   one process driving G GPUs (what the PCL-shaped shim uses when B200PPF_DEVICES lists several):
+ *                     train / load and scene upload replicate, register runs the G ranks from the calling thread. */
+typedef struct b200ppf_group b200ppf_group;
+typedef struct b200ppf_multi b200ppf_multi;
+#define B200PPF_GROUP_HANDLE_BYTES 192
+int b200ppf_group_create(b200ppf_ctx *ctx, int rank, int world, size_t n_records, b200ppf_group **out,
+                         unsigned char handles[B200PPF_GROUP_HANDLE_BYTES]);
+int b200ppf_group_connect(b200ppf_group *group, const unsigned char *all_handles /* world * B200PPF_GROUP_HANDLE_BYTES */);
+void b200ppf_group_destroy(b200ppf_group *group);
+/* vote: asynchronous; cluster: waits on the device for all ranks' records, returns this rank's poses */
+int b200ppf_group_vote(b200ppf_group *group, const b200ppf_cloud *model, const b200ppf_table *table,
+                       const b200ppf_cloud *scene, size_t ref_rate);
+int b200ppf_group_cluster(b200ppf_group *group, size_t n_ref, float pos_thr, float rot_thr, float *final16,
+                          float *poses16, uint32_t *votes, size_t *n_out);
+int b200ppf_group_register(b200ppf_group *group, const b200ppf_cloud *model, const b200ppf_table *table,
+                           const b200ppf_cloud *scene, size_t ref_rate, float pos_thr, float rot_thr, float *final16,
+                           float *poses16, uint32_t *votes, size_t *n_out);
+/* device pointer to the complete record set of the last step (reference order) */
+const b200ppf_hypothesis *b200ppf_group_records(const b200ppf_group *group);
+
+int b200ppf_multi_create(const int *devices, int n_devices, b200ppf_multi **out);
+void b200ppf_multi_destroy(b200ppf_multi *multi);
+int b200ppf_multi_size(const b200ppf_multi *multi);
+b200ppf_ctx *b200ppf_multi_context(b200ppf_multi *multi, int g);
+const b200ppf_table *b200ppf_multi_table(const b200ppf_multi *multi, int g);
+const char *b200ppf_multi_last_error(const b200ppf_multi *multi);
+int b200ppf_multi_train(b200ppf_multi *multi, const float *model_host, size_t n, size_t stride_floats,
+                        size_t normal_offset_floats, float angle_step, float dist_step);
+int b200ppf_multi_adopt(b200ppf_multi *multi, const float *model_host, size_t n, size_t stride_floats,
+                        size_t normal_offset_floats, const b200ppf_table *table);
+int b200ppf_multi_load(b200ppf_multi *multi, const float *model_host, size_t n, size_t stride_floats,
+                       size_t normal_offset_floats, const char *table_path);
+int b200ppf_multi_scene(b200ppf_multi *multi, const float *scene_host, size_t n, size_t stride_floats,
+                        size_t normal_offset_floats);
+int b200ppf_multi_register(b200ppf_multi *multi, size_t ref_rate, float pos_thr, float rot_thr, float *final16,
+                           float *poses16, uint32_t *votes, size_t *n_out);
+
 /* counters of the last vote on this context: pairs examined, pairs in radius (the metric's
  * "pairs voted"), non-empty bucket lookups, votes cast */
 int b200ppf_vote_stats(b200ppf_ctx *ctx, uint64_t *stats4);

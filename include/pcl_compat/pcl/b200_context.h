@@ -29,6 +29,31 @@ inline b200ppf_ctx *defaultContext() {
     return ctx;
 }
 
+// Several GPUs: B200PPF_DEVICES=0,1,2,3 makes PPFRegistration::align shard the scene reference points over those
+// devices of this process (b200ppf_multi_*; the first one should be the default context's device).  nullptr = one GPU.
+inline b200ppf_multi *defaultMulti() {
+    static b200ppf_multi *multi = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *e = std::getenv("B200PPF_DEVICES");
+        if (!e) return;
+        std::vector<int> dev;
+        for (const char *p = e; *p;) {
+            char *end = nullptr;
+            long v = std::strtol(p, &end, 10);
+            if (end == p) break;
+            dev.push_back(static_cast<int>(v));
+            p = (*end == ',') ? end + 1 : end;
+        }
+        if (dev.size() < 2) return;
+        if (b200ppf_multi_create(dev.data(), static_cast<int>(dev.size()), &multi) != B200PPF_OK) {
+            PCL_ERROR("[pcl::b200] B200PPF_DEVICES: %s\n", b200ppf_last_error(nullptr));
+            multi = nullptr;
+        }
+    });
+    return multi;
+}
+
 // RAII owners of the opaque handles
 struct CloudHandle {
     b200ppf_cloud *h = nullptr;

@@ -193,12 +193,14 @@ public:
     void setInputSource(const PointCloudSourceConstPtr &cloud) {
         input_ = cloud;
         source_dev_.reset();
+        multi_source_ = nullptr;
     }
     void setInputCloud(const PointCloudSourceConstPtr &cloud) { setInputSource(cloud); }  // PCL < 1.7 name
     // scene (PCL also builds its kd-tree here; the device grid is built inside align)
     void setInputTarget(const PointCloudTargetConstPtr &cloud) {
         target_ = cloud;
         target_dev_.reset();
+        multi_target_ = nullptr;
     }
     PointCloudSourceConstPtr getInputSource() const { return input_; }
     PointCloudTargetConstPtr getInputTarget() const { return target_; }
@@ -239,11 +241,38 @@ public:
         float final16[16], poses[3 * 16];
         uint32_t votes[3];
         std::size_t n_out = 0;
-        if (b200ppf_register(ctx, source_dev_.h, search_method_->deviceTable(), target_dev_.h,
-                             scene_reference_point_sampling_rate_ ? scene_reference_point_sampling_rate_ : 1,
-                             clustering_position_diff_threshold_, clustering_rotation_diff_threshold_, final16, poses,
-                             votes, &n_out) != B200PPF_OK ||
-            n_out == 0) {
+        const unsigned int rate = scene_reference_point_sampling_rate_ ? scene_reference_point_sampling_rate_ : 1;
+        if (b200ppf_multi *multi = b200::defaultMulti()) {
+            // B200PPF_DEVICES lists several GPUs: the scene reference points are interleaved over them
+            // (model + table replicated once per (source, table) pair, the scene once per target)
+            if (multi_table_ != search_method_->deviceTable() || multi_source_ != input_.get()) {
+                if (b200ppf_multi_adopt(multi, reinterpret_cast<const float *>(input_->points.data()), input_->size(),
+                                        sizeof(PointSource) / sizeof(float), 4, search_method_->deviceTable()) != B200PPF_OK) {
+                    PCL_ERROR("[pcl::PPFRegistration::align] %s\n", b200ppf_multi_last_error(multi));
+                    return;
+                }
+                multi_table_ = search_method_->deviceTable();
+                multi_source_ = input_.get();
+                multi_target_ = nullptr;
+            }
+            if (multi_target_ != target_.get()) {
+                if (b200ppf_multi_scene(multi, reinterpret_cast<const float *>(target_->points.data()), target_->size(),
+                                        sizeof(PointTarget) / sizeof(float), 4) != B200PPF_OK) {
+                    PCL_ERROR("[pcl::PPFRegistration::align] %s\n", b200ppf_multi_last_error(multi));
+                    return;
+                }
+                multi_target_ = target_.get();
+            }
+            if (b200ppf_multi_register(multi, rate, clustering_position_diff_threshold_, clustering_rotation_diff_threshold_,
+                                       final16, poses, votes, &n_out) != B200PPF_OK ||
+                n_out == 0) {
+                PCL_ERROR("[pcl::PPFRegistration::computeTransformation] %s\n", b200ppf_multi_last_error(multi));
+                return;
+            }
+        } else if (b200ppf_register(ctx, source_dev_.h, search_method_->deviceTable(), target_dev_.h, rate,
+                                    clustering_position_diff_threshold_, clustering_rotation_diff_threshold_, final16, poses,
+                                    votes, &n_out) != B200PPF_OK ||
+                   n_out == 0) {
             PCL_ERROR("[pcl::PPFRegistration::computeTransformation] %s\n", b200ppf_last_error(ctx));
             return;
         }
@@ -283,6 +312,9 @@ private:
     PointCloudSourceConstPtr input_;
     PointCloudTargetConstPtr target_;
     b200::CloudHandle source_dev_, target_dev_;
+    // what the multi-GPU handle currently holds (B200PPF_DEVICES)
+    const b200ppf_table *multi_table_ = nullptr;
+    const void *multi_source_ = nullptr, *multi_target_ = nullptr;
     Matrix4 final_transformation_ = Matrix4::Identity(), transformation_ = Matrix4::Identity(),
             previous_transformation_ = Matrix4::Identity();
     bool converged_ = false;

@@ -60,10 +60,15 @@ def _declare(L):
     L.oracle_ref_frame.argtypes = [vp, vp, vp, vp]
     L.oracle_ppf_estimation.argtypes = [C.c_int, vp, sz, vp]
     L.oracle_ppf_estimation.restype = sz
+    L.oracle_ppf_estimation_mt.argtypes = [C.c_int, vp, sz, vp, C.c_int]
+    L.oracle_ppf_estimation_mt.restype = sz
     L.oracle_hashmap_create.argtypes = [C.c_float, C.c_float]
     L.oracle_hashmap_create.restype = vp
     L.oracle_hashmap_destroy.argtypes = [vp]
     L.oracle_hashmap_set_features.argtypes = [vp, vp, sz]
+    L.oracle_hashmap_set_features_mt.argtypes = [vp, vp, sz, C.c_int]
+    L.oracle_vote_accumulate_from_pairs_mt.argtypes = [vp, C.c_int, sz, sz, vp, vp, vp, C.c_int]
+    L.oracle_vote_accumulate_from_pairs_mt.restype = C.c_uint64
     L.oracle_hashmap_model_diameter.argtypes = [vp]
     L.oracle_hashmap_model_diameter.restype = C.c_float
     L.oracle_hashmap_num_entries.argtypes = [vp]
@@ -158,13 +163,21 @@ def ref_frame(p_r, n_r):
     return R.reshape(3, 3), t
 
 
-def ppf_estimation(cloud, mode=FEATURE_PCL_PFH):
-    """PPFEstimation::compute -> (N*N, 5) float32, NaN rows for invalid pairs."""
+def ppf_estimation(cloud, mode=FEATURE_PCL_PFH, n_threads=1):
+    """PPFEstimation::compute -> (N*N, 5) float32, NaN rows for invalid pairs (rows in parallel when n_threads > 1)."""
     cloud = _f32(cloud)
     n = cloud.shape[0]
     out = np.empty((n * n, 5), np.float32)
-    lib().oracle_ppf_estimation(mode, _p(cloud), n, _p(out))
+    lib().oracle_ppf_estimation_mt(mode, _p(cloud), n, _p(out), int(n_threads))
     return out
+
+
+def host_threads():
+    """cores this process may run on (OMP_NUM_THREADS is ignored: torchrun sets it to 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def num_alpha_bins(angle_step, nalpha_rule=NALPHA_CEIL):
@@ -198,9 +211,10 @@ class HashMap:
             lib().oracle_hashmap_destroy(self._h)
             self._h = None
 
-    def set_input_feature_cloud(self, feats):
+    def set_input_feature_cloud(self, feats, n_threads=1):
+        """n_threads > 1 builds the container sharded by key (same bucket contents, minutes -> seconds at 10^8 pairs)"""
         feats = _f32(feats).reshape(-1, 5)
-        lib().oracle_hashmap_set_features(self._h, _p(feats), feats.shape[0])
+        lib().oracle_hashmap_set_features_mt(self._h, _p(feats), feats.shape[0], int(n_threads))
         self.n = int(np.sqrt(np.float32(feats.shape[0])))
         return self
 
@@ -264,12 +278,12 @@ class HashMap:
                                              scene.shape[0], s_r, _p(acc))
         return acc, int(votes)
 
-    def vote_accumulate_from_pairs(self, n_m, d, alpha_s, alpha_mode=ALPHA_MODE_A):
+    def vote_accumulate_from_pairs(self, n_m, d, alpha_s, alpha_mode=ALPHA_MODE_A, n_threads=1):
         d = np.ascontiguousarray(d, np.int32).reshape(-1, 4)
         alpha_s = _f32(alpha_s)
         acc = np.zeros((n_m, num_alpha_bins(self.angle_step, self.nalpha_rule)), np.uint32)
-        votes = lib().oracle_vote_accumulate_from_pairs(self._h, alpha_mode, n_m, d.shape[0], _p(d),
-                                                        _p(alpha_s), _p(acc))
+        votes = lib().oracle_vote_accumulate_from_pairs_mt(self._h, alpha_mode, n_m, d.shape[0], _p(d),
+                                                           _p(alpha_s), _p(acc), int(n_threads))
         return acc, int(votes)
 
     def vote(self, model, scene, ref_first=0, ref_step=1, ref_count=None, n_threads=1,

@@ -224,9 +224,26 @@ struct oracle_hashmap {
     float max_dist;
     int nalpha_rule = ORACLE_NALPHA_CEIL;
     size_t n;
-    std::unordered_multimap<Key, std::pair<size_t, size_t>, KeyHash> map;
+    /* PCL's one unordered_multimap; built by several threads it is split into shards by key (every key lives in
+     * exactly one shard, so equal_range on its shard returns what the single container would) */
+    typedef std::unordered_multimap<Key, std::pair<size_t, size_t>, KeyHash> Map;
+    std::vector<Map> maps;
     std::vector<std::vector<float>> alpha_m;
     size_t n_keys;
+    size_t shard_of(const Key &k) const {
+        if (maps.size() <= 1) return 0;
+        KeyHash h;
+        h.mixed = true;
+        return (h(k) >> 7) % maps.size();
+    }
+    std::pair<Map::const_iterator, Map::const_iterator> equal_range(const Key &k) const {
+        return maps[shard_of(k)].equal_range(k);
+    }
+    size_t size() const {
+        size_t t = 0;
+        for (const Map &m : maps) t += m.size();
+        return t;
+    }
 };
 
 namespace {
@@ -379,6 +396,9 @@ float rotation_angle(const float *R) {
 bool poses_within(const float *a, const float *b, float pos_thr, float rot_thr) {
     V3 dt{a[3] - b[3], a[7] - b[7], a[11] - b[11]};
     float position_diff = norm3(dt);
+    /* PCL evaluates both differences and ANDs them; a pose too far away fails whatever its rotation, so the
+     * rotation is only worked out for the others (same result, and the greedy loop over 10^5 poses stays in seconds) */
+    if (!(position_diff < pos_thr)) return false;
     /* R_a^-1 * R_b, inverse as transpose */
     float M[9];
     for (int r = 0; r < 3; ++r)
@@ -438,7 +458,7 @@ inline void vote_one_pair(const oracle_hashmap *hm, int feature_mode, int alpha_
     if (!pair_features(feature_mode, p_r, n_r, p_i, n_i, f)) return;
     ++counters[1];
     Key k = quantise(hm, f);
-    auto range = hm->map.equal_range(k);
+    auto range = hm->equal_range(k);
     bucket.clear();
     for (auto it = range.first; it != range.second; ++it) bucket.push_back(it->second);
     if (bucket.empty()) return;
@@ -569,9 +589,20 @@ void oracle_ref_frame(const float *p_r, const float *n_r, float *R, float *t) {
 }
 
 size_t oracle_ppf_estimation(int feature_mode, const float *cloud, size_t n, float *out) {
+    return oracle_ppf_estimation_mt(feature_mode, cloud, n, out, 1);
+}
+
+/* rows of the N x N feature cloud are independent: n_threads > 1 computes them in parallel (same values) */
+size_t oracle_ppf_estimation_mt(int feature_mode, const float *cloud, size_t n, float *out, int n_threads) {
     const float nan = std::numeric_limits<float>::quiet_NaN();
     size_t valid = 0;
-    for (size_t i = 0; i < n; ++i) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(n_threads > 1 ? n_threads : 1) schedule(static) reduction(+ : valid)
+#else
+    (void)n_threads;
+#endif
+    for (long long ii = 0; ii < static_cast<long long>(n); ++ii) {
+        const size_t i = static_cast<size_t>(ii);
         V3 p_i = ld3(cloud + 6 * i), n_i = ld3(cloud + 6 * i + 3);
         for (size_t j = 0; j < n; ++j) {
             float *o = out + (i * n + j) * 5;
@@ -607,13 +638,16 @@ oracle_hashmap *oracle_hashmap_create(float angle_step, float dist_step) {
 void oracle_hashmap_destroy(oracle_hashmap *hm) { delete hm; }
 
 void oracle_hashmap_set_features(oracle_hashmap *hm, const float *feats, size_t count) {
+    oracle_hashmap_set_features_mt(hm, feats, count, 1);
+}
+
+void oracle_hashmap_set_features_mt(oracle_hashmap *hm, const float *feats, size_t count, int n_threads) {
     unsigned int n = static_cast<unsigned int>(std::sqrt(static_cast<float>(count)));
-    {
-        KeyHash kh;
-        kh.mixed = n > ORACLE_PCL_HASH_MAX_POINTS && !std::getenv("ORACLE_FORCE_PCL_HASH");
-        hm->map = decltype(hm->map)(0, kh);
-        if (kh.mixed) hm->map.reserve(count);
-    }
+    KeyHash kh;
+    kh.mixed = n > ORACLE_PCL_HASH_MAX_POINTS && !std::getenv("ORACLE_FORCE_PCL_HASH");
+    const size_t shards = n_threads > 1 ? static_cast<size_t>(n_threads) : 1;
+    hm->maps.clear();
+    for (size_t t = 0; t < shards; ++t) hm->maps.emplace_back(0, kh);
     hm->n = n;
     hm->max_dist = -1.0f;
     hm->alpha_m.assign(n, std::vector<float>());
@@ -622,25 +656,47 @@ void oracle_hashmap_set_features(oracle_hashmap *hm, const float *feats, size_t 
         for (size_t j = 0; j < n; ++j) {
             const float *s = feats + (i * n + j) * 5;
             row[j] = s[4];
-            /* PCL inserts the NaN diagonal too (key = (int)NaN, UB); no finite query can reach
-             * those nodes, so skipping them is observationally identical. */
             if (std::isnan(s[0]) || std::isnan(s[1]) || std::isnan(s[2]) || std::isnan(s[3])) continue;
-            Key k = quantise(hm, s);
-            hm->map.insert(std::make_pair(k, std::make_pair(i, j)));
             if (hm->max_dist < s[3]) hm->max_dist = s[3];
         }
         hm->alpha_m[i] = std::move(row);
     }
-    size_t keys = 0;
-    for (auto it = hm->map.begin(); it != hm->map.end();) {
-        ++keys;
-        it = hm->map.equal_range(it->first).second;
+    /* the inserts, in PCL's order (i ascending, j ascending) inside every shard */
+    auto fill = [&](size_t shard) {
+        oracle_hashmap::Map &map = hm->maps[shard];
+        if (kh.mixed) map.reserve(count / shards + count / (8 * shards) + 16);
+        for (size_t i = 0; i < n; ++i)
+            for (size_t j = 0; j < n; ++j) {
+                const float *s = feats + (i * n + j) * 5;
+                /* PCL inserts the NaN diagonal too (key = (int)NaN, UB); no finite query can reach
+                 * those nodes, so skipping them is observationally identical. */
+                if (std::isnan(s[0]) || std::isnan(s[1]) || std::isnan(s[2]) || std::isnan(s[3])) continue;
+                Key k = quantise(hm, s);
+                if (shards > 1 && hm->shard_of(k) != shard) continue;
+                map.insert(std::make_pair(k, std::make_pair(i, j)));
+            }
+    };
+#ifdef _OPENMP
+    if (shards > 1) {
+#pragma omp parallel for num_threads(static_cast<int>(shards)) schedule(static, 1)
+        for (long long t = 0; t < static_cast<long long>(shards); ++t) fill(static_cast<size_t>(t));
+    } else {
+        fill(0);
     }
+#else
+    for (size_t t = 0; t < shards; ++t) fill(t);
+#endif
+    size_t keys = 0;
+    for (const oracle_hashmap::Map &map : hm->maps)
+        for (auto it = map.begin(); it != map.end();) {
+            ++keys;
+            it = map.equal_range(it->first).second;
+        }
     hm->n_keys = keys;
 }
 
 float oracle_hashmap_model_diameter(const oracle_hashmap *hm) { return hm->max_dist; }
-size_t oracle_hashmap_num_entries(const oracle_hashmap *hm) { return hm->map.size(); }
+size_t oracle_hashmap_num_entries(const oracle_hashmap *hm) { return hm->size(); }
 size_t oracle_hashmap_num_keys(const oracle_hashmap *hm) { return hm->n_keys; }
 
 void oracle_hashmap_quantise(const oracle_hashmap *hm, const float *f, int32_t *d) {
@@ -652,7 +708,7 @@ size_t oracle_hashmap_query_key(const oracle_hashmap *hm, const int32_t *d, uint
                                 size_t cap) {
     Key k;
     std::memcpy(k.d, d, sizeof(k.d));
-    auto range = hm->map.equal_range(k);
+    auto range = hm->equal_range(k);
     std::vector<std::pair<size_t, size_t>> v;
     for (auto it = range.first; it != range.second; ++it) v.push_back(it->second);
     std::sort(v.begin(), v.end());
@@ -672,13 +728,14 @@ size_t oracle_hashmap_query(const oracle_hashmap *hm, float f1, float f2, float 
 
 void oracle_hashmap_dump_keys(const oracle_hashmap *hm, int32_t *keys, uint32_t *lengths) {
     size_t idx = 0;
-    for (auto it = hm->map.begin(); it != hm->map.end();) {
-        auto range = hm->map.equal_range(it->first);
-        std::memcpy(keys + 4 * idx, it->first.d, 4 * sizeof(int32_t));
-        lengths[idx] = static_cast<uint32_t>(std::distance(range.first, range.second));
-        ++idx;
-        it = range.second;
-    }
+    for (const oracle_hashmap::Map &map : hm->maps)
+        for (auto it = map.begin(); it != map.end();) {
+            auto range = map.equal_range(it->first);
+            std::memcpy(keys + 4 * idx, it->first.d, 4 * sizeof(int32_t));
+            lengths[idx] = static_cast<uint32_t>(std::distance(range.first, range.second));
+            ++idx;
+            it = range.second;
+        }
 }
 
 void oracle_hashmap_set_nalpha_rule(oracle_hashmap *hm, int rule) { hm->nalpha_rule = rule; }
@@ -718,21 +775,49 @@ size_t oracle_scene_pairs(const oracle_hashmap *hm, int feature_mode, const floa
 uint64_t oracle_vote_accumulate_from_pairs(const oracle_hashmap *hm, int alpha_mode, size_t n_m,
                                            size_t n_pairs, const int32_t *d, const float *alpha_s,
                                            uint32_t *acc) {
+    return oracle_vote_accumulate_from_pairs_mt(hm, alpha_mode, n_m, n_pairs, d, alpha_s, acc, 1);
+}
+
+/* n_threads > 1: the pairs are spread over threads with private accumulators that are summed at the end (integer
+ * adds commute: the result is the serial one) */
+uint64_t oracle_vote_accumulate_from_pairs_mt(const oracle_hashmap *hm, int alpha_mode, size_t n_m, size_t n_pairs,
+                                              const int32_t *d, const float *alpha_s, uint32_t *acc, int n_threads) {
     const uint32_t n_alpha = num_alpha_bins(hm->angle_step, hm->nalpha_rule);
-    std::memset(acc, 0, n_m * n_alpha * sizeof(uint32_t));
+    const size_t len = n_m * n_alpha;
+    std::memset(acc, 0, len * sizeof(uint32_t));
     uint64_t votes = 0;
-    for (size_t p = 0; p < n_pairs; ++p) {
+    auto walk = [&](size_t p, uint32_t *a, uint64_t &v) {
         Key k;
         std::memcpy(k.d, d + 4 * p, sizeof(k.d));
-        auto range = hm->map.equal_range(k);
+        auto range = hm->equal_range(k);
         for (auto it = range.first; it != range.second; ++it) {
             uint32_t bin = alpha_bin(alpha_mode, hm->angle_step, n_alpha, hm->nalpha_rule,
                                      hm->alpha_m[it->second.first][it->second.second], alpha_s[p]);
             if (bin == UINT32_MAX) continue;
-            if (bin != BIN_DROPPED) acc[it->second.first * n_alpha + bin]++;
-            ++votes;
+            if (bin != BIN_DROPPED) a[it->second.first * n_alpha + bin]++;
+            ++v;
         }
+    };
+#ifdef _OPENMP
+    if (n_threads > 1) {
+#pragma omp parallel num_threads(n_threads)
+        {
+            std::vector<uint32_t> priv(len, 0u);
+            uint64_t v = 0;
+#pragma omp for schedule(dynamic, 8)
+            for (long long p = 0; p < static_cast<long long>(n_pairs); ++p) walk(static_cast<size_t>(p), priv.data(), v);
+#pragma omp critical
+            {
+                for (size_t e = 0; e < len; ++e) acc[e] += priv[e];
+                votes += v;
+            }
+        }
+        return votes;
     }
+#else
+    (void)n_threads;
+#endif
+    for (size_t p = 0; p < n_pairs; ++p) walk(p, acc, votes);
     return votes;
 }
 

@@ -47,6 +47,7 @@ void oracle_ref_frame(const float *p_r, const float *n_r, float *R, float *t);
  * {f1,f2,f3,f4,alpha_m}, row-major [i*N+j]; invalid pairs (i==j or failure) are all-NaN.
  * Returns the number of valid pairs. */
 size_t oracle_ppf_estimation(int feature_mode, const float *cloud, size_t n, float *out);
+size_t oracle_ppf_estimation_mt(int feature_mode, const float *cloud, size_t n, float *out, int n_threads);
 
 /* A.3 : PPFHashMapSearch */
 typedef struct oracle_hashmap oracle_hashmap;
@@ -54,6 +55,9 @@ oracle_hashmap *oracle_hashmap_create(float angle_step, float dist_step);
 void oracle_hashmap_destroy(oracle_hashmap *hm);
 /* setInputFeatureCloud: feats = count*5 floats, count = n*n. NaN pairs are skipped. */
 void oracle_hashmap_set_features(oracle_hashmap *hm, const float *feats, size_t count);
+/* the same container built by n_threads threads (sharded by key; identical bucket contents) — keeps the CPU side of
+ * the full-size parity tests and of bench.py within minutes; n_threads <= 1 is the single container */
+void oracle_hashmap_set_features_mt(oracle_hashmap *hm, const float *feats, size_t count, int n_threads);
 float oracle_hashmap_model_diameter(const oracle_hashmap *hm);
 size_t oracle_hashmap_num_entries(const oracle_hashmap *hm);
 size_t oracle_hashmap_num_keys(const oracle_hashmap *hm);
@@ -92,6 +96,9 @@ uint64_t oracle_vote_accumulate(const oracle_hashmap *hm, int feature_mode, int 
 uint64_t oracle_vote_accumulate_from_pairs(const oracle_hashmap *hm, int alpha_mode, size_t n_m,
                                            size_t n_pairs, const int32_t *d /*[n][4]*/,
                                            const float *alpha_s, uint32_t *acc);
+
+uint64_t oracle_vote_accumulate_from_pairs_mt(const oracle_hashmap *hm, int alpha_mode, size_t n_m, size_t n_pairs,
+                                              const int32_t *d, const float *alpha_s, uint32_t *acc, int n_threads);
 
 /* one hypothesis per reference point (64 bytes, same record the device emits) */
 typedef struct oracle_hypothesis {

@@ -562,24 +562,141 @@ def axis_pose_error(P, G):
     return dt, float(np.degrees(np.arccos(c)))
 
 
-def test_c3_full_size_properties(ctx):
-    """BASELINE config 3 at full size (10 000 x 100 000, 8.1e12 votes per pass) — properties only, no oracle:
-    the pose is the scene's ground truth, its cluster votes are the frozen values of the first verified run,
-    and reference shards reproduce the single-launch records byte for byte."""
-    from yolo_ppf_pose_estimation_b200 import workloads, synth
+@pytest.fixture(scope="module")
+def c3_full(ctx, oracle):
+    """BASELINE config 3 at full size on both sides: the oracle's container for the 10 000-point model (10^8 pairs,
+    built sharded over the host cores) and the device table made from the oracle's own signatures (identical floats
+    in), seven accumulator slices, the 1024-thread launch shape."""
+    from yolo_ppf_pose_estimation_b200 import workloads
     wl = workloads.load("c3")
+    th = oracle.host_threads()
+    feats = oracle.ppf_estimation(wl.model, n_threads=th)
+    hm = oracle.HashMap(wl.angle_step, wl.dist_step).set_input_feature_cloud(feats, n_threads=th)
     dm, ds = ctx.upload_cloud(wl.model), ctx.upload_cloud(wl.scene)
-    t = ctx.table_build_from_cloud(dm, wl.angle_step, wl.dist_step)
-    assert t.info.n_entries == 99990000 and t.info.phase_cells == 16
-    hy = ctx.vote(dm, t, ds, 0, 1)
+    tf = ctx.table_build(ctx.features_upload(feats), wl.angle_step, wl.dist_step)
+    del feats
+    hy = ctx.vote(dm, tf, ds, 0, 1)
     st = ctx.vote_stats()
-    assert st["votes"] == 8106143691736 and st["pairs_in_radius"] == 99513110
+    return wl, hm, dm, ds, tf, hy, st, th
+
+
+def _c3_sample_refs(wl):
+    """one reference point on the object, one on the ground plane, one on a wall, one in a clutter blob"""
+    from yolo_ppf_pose_estimation_b200 import synth
+    s = wl.scene.astype(np.float64)
+    G = synth.gt_pose(2)
+    centre = G[:3, 3] + G[:3, :3] @ np.array([0.0, 0.0, 0.09])
+    on_object = int(np.argmin(np.linalg.norm(s[:, :3] - centre, axis=1)))
+    ground = int(np.flatnonzero((np.abs(s[:, 1] - 0.45) < 0.002) & (s[:, 4] < -0.95) & (np.abs(s[:, 0]) < 0.5))[0])
+    wall = int(np.flatnonzero((np.abs(s[:, 2] - 2.5) < 0.002) & (s[:, 5] < -0.95) & (np.abs(s[:, 0]) < 0.5))[0])
+    planes = (np.abs(s[:, 1] - 0.45) < 0.01) | (np.abs(s[:, 2] - 2.5) < 0.01) | (np.abs(s[:, 0] + 1.0) < 0.01)
+    far = np.linalg.norm(s[:, :3] - centre, axis=1) > 0.3
+    clutter = int(np.flatnonzero(~planes & far)[0])
+    return {"object": on_object, "ground": ground, "wall": wall, "clutter": clutter}
+
+
+def test_c3_full_size_vs_oracle(ctx, oracle, c3_full):
+    """The headline configuration against the oracle, not against itself: accumulators of reference points on the
+    object, on the two kinds of plane and in the clutter bit-exact at seven slices, each hypothesis the first maximum
+    of its accumulator with the oracle's pose, the table's bucket statistics those of the oracle's container."""
+    wl, hm, dm, ds, tf, hy, st, th = c3_full
+    ti = tf.info
+    assert ti.n_slices == 7 and ti.phase_cells == 16 and ti.n_alpha == 30
+    assert ti.n_entries == hm.num_entries == 99990000 and ti.n_keys == hm.num_keys
+    assert 0 < ti.n_merged < ti.n_entries
+    assert np.float32(ti.max_dist) == np.float32(hm.model_diameter)
+    n = wl.model.shape[0]
+    seen = {}
+    for what, s_r in _c3_sample_refs(wl).items():
+        inr, d, a = ctx.vote_debug_pairs(tf, ds, s_r)
+        acc = ctx.vote_debug_accumulator(tf, ds, s_r)
+        ref, votes = hm.vote_accumulate_from_pairs(n, d[inr > 0], a[inr > 0], n_threads=th)
+        assert votes == int(acc.sum()) == ctx.vote_stats()["votes"], (what, s_r)
+        assert np.array_equal(acc, ref), f"accumulator differs for the {what} reference point {s_r}"
+        flat = int(np.argmax(acc))
+        h = hy[s_r]
+        assert h["scene_index"] == s_r and h["votes"] == acc.reshape(-1)[flat]
+        assert (int(h["model_index"]), int(h["alpha_bin"])) == divmod(flat, acc.shape[1])
+        P = oracle.peak_pose(wl.model, int(h["model_index"]), int(h["alpha_bin"]), wl.scene, s_r, wl.angle_step)
+        assert np.abs(P.reshape(-1) - h["pose"]).max() < 2e-5
+        seen[what] = (int(inr.sum()), votes)
+    print("C3 full size, (in-radius pairs, votes) per sampled reference point:", seen)
+    assert seen["object"][1] > 1e8 and seen["ground"][1] > 1e7    # the sample does hit the expensive points
+
+
+def test_c3_full_size_clustering_vs_oracle(ctx, oracle, c3_full):
+    """K4 on all 100 000 hypotheses of config 3 (one cluster of thousands of members on the object: the leader-list
+    path): assignments, cluster votes and the three averaged poses against the oracle's greedy loop."""
+    wl, hm, dm, ds, tf, hy, st, th = c3_full
     poses, votes = ctx.cluster(hy, wl.pos_thr, wl.rot_thr)
-    assert votes.tolist() == [400444760, 100356427, 79863461]
+    assign, ncl = ctx.cluster_assignment(len(hy))
+    rposes, rvotes, rassign, rncl = oracle.cluster(hy, wl.pos_thr, wl.rot_thr)
+    assert ncl == rncl and np.array_equal(assign, rassign)
+    assert np.array_equal(votes, rvotes)
+    assert np.abs(poses - rposes).max() < 1e-5
+    assert np.bincount(rassign).max() > 2000
+
+
+def test_c3_full_size_properties(ctx, c3_full):
+    """Size-independent properties at full size (8.1e12 votes per pass): work counters, the ground-truth pose, and
+    reference shards reproducing the single-launch records byte for byte."""
+    from yolo_ppf_pose_estimation_b200 import synth
+    wl, hm, dm, ds, tf, hy, st, th = c3_full
+    # counters of the table made from the oracle's signatures; the table made from the device's own differs by edge pairs
+    assert abs(st["votes"] - 8106143691736) < 1e-6 * 8106143691736 and st["pairs_in_radius"] == 99513110
+    poses, votes = ctx.cluster(hy, wl.pos_thr, wl.rot_thr)
     dt, da = axis_pose_error(poses[0], synth.gt_pose(2))
     assert dt < 2e-3 and da < 3.0, (dt, da)
-    part = ctx.vote(dm, t, ds, 5, 997)
+    part = ctx.vote(dm, tf, ds, 5, 997)
     assert part.tobytes() == hy[5::997].tobytes()
+    # the table built straight from the model cloud (device floats) differs from the oracle's by edge pairs only
+    t = ctx.table_build_from_cloud(dm, wl.angle_step, wl.dist_step)
+    assert abs(int(t.info.n_entries) - 99990000) <= 64 and t.info.phase_cells == 16
+    ctx.vote(dm, t, ds, 0, 997)
+    tf_votes = ctx.vote_stats()["votes"]
+    ctx.vote(dm, tf, ds, 0, 997)
+    assert abs(tf_votes - ctx.vote_stats()["votes"]) < 1e-5 * tf_votes
+
+
+def test_c4s_library_both_partitionings(ctx, oracle):
+    """BASELINE config 4 (eighth-scale scene): the 8-model library against one scene.  Accumulators of sampled
+    reference points bit-exact per model; and the two ways of spreading the work over G GPUs — one model per GPU
+    (every reference point), or every table on every GPU with the reference points interleaved — give the same
+    hypothesis records byte for byte, hence the same poses."""
+    from yolo_ppf_pose_estimation_b200 import workloads, synth
+    wl = workloads.load("c4s")
+    th = oracle.host_threads()
+    ds = ctx.upload_cloud(wl.scene)
+    rate, n_ref = wl.ref_rate, wl.n_ref
+    for k in (0, 3, 7):
+        model = wl.models[k]
+        feats = oracle.ppf_estimation(model, n_threads=th)
+        hm = oracle.HashMap(wl.angle_step, wl.dist_step).set_input_feature_cloud(feats, n_threads=th)
+        dm = ctx.upload_cloud(model)
+        tf = ctx.table_build(ctx.features_upload(feats), wl.angle_step, wl.dist_step)
+        assert tf.info.n_entries == hm.num_entries
+        G = synth.library_pose(k, 3)
+        centre = G[:3, 3] + G[:3, :3] @ np.array([0.0, 0.0, 0.09])
+        near = np.argsort(np.linalg.norm(wl.scene[:, :3].astype(np.float64) - centre, axis=1))[:400]
+        on_object = int(near[near % rate == 0][0])      # a reference point of the workload on model k's instance
+        for s_r in (on_object, rate * 1234):
+            inr, d, a = ctx.vote_debug_pairs(tf, ds, s_r)
+            acc = ctx.vote_debug_accumulator(tf, ds, s_r)
+            ref, votes = hm.vote_accumulate_from_pairs(model.shape[0], d[inr > 0], a[inr > 0], n_threads=th)
+            assert votes == int(acc.sum()) and np.array_equal(acc, ref), (k, s_r)
+        # partitioning 1: this model on one GPU, every reference point
+        full = ctx.vote(dm, tf, ds, 0, rate, n_ref)
+        # partitioning 2: reference points interleaved over 4 ranks, every rank holding this model's table
+        merged = np.empty_like(full)
+        for r in range(4):
+            cnt = (n_ref - r + 3) // 4
+            merged[r::4] = ctx.vote(dm, tf, ds, r * rate, 4 * rate, cnt)
+        assert merged.tobytes() == full.tobytes()
+        poses, votes = ctx.cluster(full, wl.pos_thr, wl.rot_thr)
+        rposes, rvotes, _, _ = oracle.cluster(full, wl.pos_thr, wl.rot_thr)
+        assert np.array_equal(votes, rvotes) and np.abs(poses - rposes).max() < 1e-5
+        dt, da = axis_pose_error(poses[0], G)
+        assert dt < 5e-3 and da < 3.0, (k, dt, da)
 
 
 @pytest.mark.parametrize("step_deg", [6.0, 14.3239448782706, 25.0])
@@ -616,6 +733,72 @@ def test_k3_peer_scatter_epilogue(ctx, dev_bottle, dev_crop, table_fused):
     from yolo_ppf_pose_estimation_b200 import capi
     with pytest.raises(capi.B200PPFError):
         ctx.vote_scatter_device(dev_bottle, table_fused, dev_crop, 0, 1, n, [], 0, 1)
+
+
+def test_multi_gpu_group_in_one_process(ctx, bottle, scene_crop, dev_bottle, dev_crop, table_fused):
+    """b200ppf_multi_*: the group machinery (interleaved shares, records stored into every rank's buffer by the vote
+    epilogue, device-side flags, the waiting kernel) with three 'ranks' that are three contexts on this one GPU:
+    the poses are those of the single-context align, step after step (the two buffer sets alternate)."""
+    from yolo_ppf_pose_estimation_b200 import capi
+    final, poses, votes = ctx.register(dev_bottle, table_fused, dev_crop, ref_rate=5)
+    m = capi.Multi([0, 0, 0])
+    assert m.size == 3
+    m.train(bottle, ANGLE_STEP, DIST_STEP)
+    m.scene(scene_crop)
+    for _ in range(3):
+        f2, p2, v2 = m.register(ref_rate=5)
+        assert np.array_equal(v2, votes) and np.array_equal(p2, poses) and np.array_equal(f2, final)
+    # another scene size on the same handle (buffers are re-made when they are too small), every point a reference
+    f1, p1, v1 = ctx.register(dev_bottle, table_fused, dev_crop, ref_rate=1)
+    f3, p3, v3 = m.register(ref_rate=1)
+    assert np.array_equal(v3, v1) and np.array_equal(p3, p1)
+    with pytest.raises(capi.B200PPFError):
+        capi.Multi([0, 99])
+    m.close()
+
+
+def test_multi_gpu_group_across_processes(tmp_path, ctx, dev_bottle, dev_crop, table_fused):
+    """b200ppf_group_*: two processes (both on this GPU), buffers mapped into one another through the CUDA IPC handle
+    blobs, exchanged here through files: both ranks return the single-context poses."""
+    final, poses, votes = ctx.register(dev_bottle, table_fused, dev_crop, ref_rate=5)
+    code = f"""
+import sys, os, time, numpy as np
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+from yolo_ppf_pose_estimation_b200 import capi
+from conftest import ANGLE_STEP, DIST_STEP, load_cloud
+rank, world, d = int(sys.argv[1]), 2, sys.argv[2]
+m, s = load_cloud('bottle_1cm'), load_cloud('scene_crop_1cm')
+c = capi.Context(0)
+dm, ds = c.upload_cloud(m), c.upload_cloud(s)
+t = c.table_build_from_cloud(dm, ANGLE_STEP, DIST_STEP)
+g = capi.Group(c, rank, world, (s.shape[0] + 4) // 5 + 8)
+np.save(os.path.join(d, f'h{{rank}}.tmp.npy'), g.handles); os.replace(os.path.join(d, f'h{{rank}}.tmp.npy'), os.path.join(d, f'h{{rank}}.npy'))
+hs = []
+for r in range(world):
+    p = os.path.join(d, f'h{{r}}.npy')
+    for _ in range(600):
+        if os.path.exists(p): break
+        time.sleep(0.05)
+    hs.append(np.load(p))
+g.connect(hs)
+for step in range(3):
+    poses, votes = g.register(dm, t, ds, 5)
+np.savez(os.path.join(d, f'out{{rank}}.npz'), poses=poses, votes=votes)
+open(os.path.join(d, f'done{{rank}}'), 'w').close()
+for r in range(world):          # keep the buffers mapped until the peer is done with them
+    for _ in range(600):
+        if os.path.exists(os.path.join(d, f'done{{r}}')): break
+        time.sleep(0.05)
+g.close()
+print('RANK_OK')
+"""
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r), str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, o in enumerate(outs):
+        assert "RANK_OK" in o, o
+        z = np.load(tmp_path / f"out{r}.npz")
+        assert np.array_equal(z["votes"], votes) and np.array_equal(z["poses"], poses)
 
 
 def test_k3_alpha_bins_on_device(ctx):
@@ -832,3 +1015,9 @@ def test_cpp_pcl_shim_end_to_end(tmp_path, ctx, bottle, scene_crop, dev_bottle, 
     bucket = lines[5].split()
     assert int(bucket[1]) >= 1 and (int(bucket[3]), int(bucket[4])) <= (0, 1)
     assert lines[7].split() == ["reloaded_table_same_pose", "1"]
+    # the same binary with B200PPF_DEVICES=0,0: PPFRegistration::align goes through b200ppf_multi_* (two contexts on
+    # this GPU stand in for two GPUs) — same table copied device to device, same poses, same output
+    r2 = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300,
+                        env=dict(os.environ, B200PPF_DEVICES="0,0"))
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    assert r2.stdout.strip().splitlines()[:8] == lines[:8]

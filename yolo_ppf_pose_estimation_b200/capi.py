@@ -87,6 +87,7 @@ SYMBOLS = {
     "b200ppf_table_query_key": (_i, [_vp, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "b200ppf_table_alpha_m": (_i, [_vp, _vp, _vp]),
     "b200ppf_table_export": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200ppf_table_clone": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b200ppf_table_free": (None, [_vp]),
     "b200ppf_table_save": (_i, [_vp, _vp, C.c_char_p]),
     "b200ppf_table_load": (_i, [_vp, C.c_char_p, C.POINTER(_vp)]),
@@ -97,6 +98,24 @@ SYMBOLS = {
     "b200ppf_hyp_buffer_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b200ppf_hyp_buffer_download": (_i, [_vp, _vp, _sz, _sz, _vp]),
     "b200ppf_hyp_buffer_release": (_i, [_vp, _vp, _i]),
+    "b200ppf_group_create": (_i, [_vp, _i, _i, _sz, C.POINTER(_vp), _vp]),
+    "b200ppf_group_connect": (_i, [_vp, _vp]),
+    "b200ppf_group_destroy": (None, [_vp]),
+    "b200ppf_group_vote": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "b200ppf_group_cluster": (_i, [_vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
+    "b200ppf_group_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
+    "b200ppf_group_records": (_vp, [_vp]),
+    "b200ppf_multi_create": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "b200ppf_multi_destroy": (None, [_vp]),
+    "b200ppf_multi_size": (_i, [_vp]),
+    "b200ppf_multi_context": (_vp, [_vp, _i]),
+    "b200ppf_multi_table": (_vp, [_vp, _i]),
+    "b200ppf_multi_last_error": (C.c_char_p, [_vp]),
+    "b200ppf_multi_train": (_i, [_vp, _vp, _sz, _sz, _sz, _f, _f]),
+    "b200ppf_multi_adopt": (_i, [_vp, _vp, _sz, _sz, _sz, _vp]),
+    "b200ppf_multi_load": (_i, [_vp, _vp, _sz, _sz, _sz, C.c_char_p]),
+    "b200ppf_multi_scene": (_i, [_vp, _vp, _sz, _sz, _sz]),
+    "b200ppf_multi_register": (_i, [_vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_vote_stats": (_i, [_vp, _vp]),
     "b200ppf_vote_debug_pairs": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "b200ppf_vote_debug_accumulator": (_i, [_vp, _vp, _vp, _sz, _vp]),
@@ -460,6 +479,103 @@ class Context:
         self.check(lib().b200ppf_register(self._h, model._h, table._h, scene._h, ref_rate, np.float32(pos_thr),
                                           np.float32(rot_thr), _p(final), _p(poses), _p(votes), C.byref(k)))
         return final.reshape(4, 4), poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
+
+
+GROUP_HANDLE_BYTES = 192
+
+
+class Group:
+    """One rank of a multi-process group (one process / context per GPU): b200ppf_group_*."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, n_records: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        self.handles = np.zeros(GROUP_HANDLE_BYTES, np.uint8)
+        ctx.check(lib().b200ppf_group_create(ctx._h, rank, world, n_records, C.byref(self._h), _p(self.handles)))
+
+    def connect(self, all_handles):
+        """all_handles: the `handles` blobs of every rank, in rank order (world x 192 bytes)"""
+        blob = np.ascontiguousarray(np.concatenate([np.asarray(h, np.uint8).reshape(-1) for h in all_handles]))
+        assert blob.size == self.world * GROUP_HANDLE_BYTES
+        self.ctx.check(lib().b200ppf_group_connect(self._h, _p(blob)))
+
+    def vote(self, model, table, scene, ref_rate=1):
+        self.ctx.check(lib().b200ppf_group_vote(self._h, model._h, table._h, scene._h, ref_rate))
+
+    def cluster(self, n_ref, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
+        final = np.zeros(16, np.float32)
+        poses = np.zeros((3, 16), np.float32)
+        votes = np.zeros(3, np.uint32)
+        k = C.c_size_t(0)
+        self.ctx.check(lib().b200ppf_group_cluster(self._h, n_ref, np.float32(pos_thr), np.float32(rot_thr), _p(final),
+                                                   _p(poses), _p(votes), C.byref(k)))
+        return poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
+
+    def register(self, model, table, scene, ref_rate=1, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
+        self.vote(model, table, scene, ref_rate)
+        return self.cluster((scene.size + ref_rate - 1) // ref_rate, pos_thr, rot_thr)
+
+    def records(self, n):
+        """the complete hypothesis set of the last step (synchronises)"""
+        return self.ctx.download_hypotheses(lib().b200ppf_group_records(self._h), n)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().b200ppf_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Multi:
+    """Several GPUs driven by this process: b200ppf_multi_* (what the PCL-shaped shim uses for B200PPF_DEVICES=0,1,..)."""
+
+    def __init__(self, devices):
+        dev = np.ascontiguousarray(devices, np.int32)
+        self._h = C.c_void_p()
+        rc = lib().b200ppf_multi_create(_p(dev), len(dev), C.byref(self._h))
+        if rc != 0:
+            raise B200PPFError(rc, lib().b200ppf_last_error(None).decode())
+
+    def check(self, rc):
+        if rc != 0:
+            raise B200PPFError(rc, lib().b200ppf_multi_last_error(self._h).decode())
+
+    @property
+    def size(self):
+        return lib().b200ppf_multi_size(self._h)
+
+    def train(self, model, angle_step, dist_step):
+        m = np.ascontiguousarray(model, np.float32)
+        self.check(lib().b200ppf_multi_train(self._h, _p(m), m.shape[0], m.shape[1], 3, np.float32(angle_step), np.float32(dist_step)))
+
+    def scene(self, scene):
+        s = np.ascontiguousarray(scene, np.float32)
+        self.check(lib().b200ppf_multi_scene(self._h, _p(s), s.shape[0], s.shape[1], 3))
+
+    def register(self, ref_rate=5, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
+        final = np.zeros(16, np.float32)
+        poses = np.zeros((3, 16), np.float32)
+        votes = np.zeros(3, np.uint32)
+        k = C.c_size_t(0)
+        self.check(lib().b200ppf_multi_register(self._h, ref_rate, np.float32(pos_thr), np.float32(rot_thr), _p(final), _p(poses),
+                                                _p(votes), C.byref(k)))
+        return final.reshape(4, 4), poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().b200ppf_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def debug_alpha_bins(alpha_m, alpha_s, angle_step, alpha_mode=ALPHA_MODE_A, ctx: "Context | None" = None,

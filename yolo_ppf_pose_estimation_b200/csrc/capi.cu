@@ -645,6 +645,53 @@ int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out) 
     return B200PPF_OK;
 }
 
+int b200ppf_table_clone(b200ppf_ctx *dst, const b200ppf_table *src, b200ppf_table **out) {
+    CHECK_CTX(dst);
+    if (!src || !out) return fail_msg(dst, B200PPF_ERR_INVALID, "table clone: null argument");
+    *out = nullptr;
+    if (src->ctx) cudaStreamSynchronize(src->ctx->stream);  // the source table's build has finished (device guard is dst's)
+    b200ppf_table *t = new (std::nothrow) b200ppf_table();
+    if (!t) return fail_msg(dst, B200PPF_ERR_NOMEM, "table clone: out of host memory");
+    t->ctx = dst;
+    t->info = src->info;
+    t->kp = src->kp;
+    t->bp = src->bp;
+    t->feature_mode = src->feature_mode;
+    t->n_merged = src->n_merged;
+    const uint64_t total_keys = (uint64_t)src->info.key_space * src->info.n_slices;
+    const size_t n_sub = src->sub_offsets ? (size_t)(total_keys << src->bp.cells_log2) + 1 : 0, ne = src->info.n_entries;
+    const int src_dev = src->ctx ? src->ctx->device : dst->device;
+    struct Arr {
+        uint32_t *const *from;
+        uint32_t **to;
+        size_t words, pad;
+    } arrs[8] = {{&src->offsets, &t->offsets, (size_t)total_keys + 1, 0},
+                 {&src->sub_offsets, &t->sub_offsets, n_sub, 0},
+                 {&src->entry_w, &t->entry_w, ne, b200ppf::ENTRY_PAD},
+                 {&src->entry_am, &t->entry_am, ne, b200ppf::ENTRY_PAD},
+                 {reinterpret_cast<uint32_t *const *>(&src->entry_alpha), reinterpret_cast<uint32_t **>(&t->entry_alpha), std::max<size_t>(1, ne), 0},
+                 {&src->entry_idx, &t->entry_idx, std::max<size_t>(1, ne), 0},
+                 {&src->merged_w, &t->merged_w, src->merged_w ? src->n_merged : 0, b200ppf::ENTRY_PAD},
+                 {&src->msub_offsets, &t->msub_offsets, src->msub_offsets ? n_sub : 0, 0}};
+    for (const Arr &a : arrs) {
+        if (!*a.from) continue;
+        cudaError_t e = cudaMalloc(a.to, (a.words + a.pad) * sizeof(uint32_t));
+        if (e == cudaSuccess && a.pad) e = cudaMemsetAsync(*a.to + a.words, 0, a.pad * sizeof(uint32_t), dst->stream);
+        if (e == cudaSuccess && a.words)
+            e = cudaMemcpyPeerAsync(*a.to, dst->device, *a.from, src_dev, a.words * sizeof(uint32_t), dst->stream);
+        if (e != cudaSuccess) {
+            b200ppf_table_free(t);
+            return fail_msg(dst, e == cudaErrorMemoryAllocation ? B200PPF_ERR_NOMEM : B200PPF_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    if (cudaStreamSynchronize(dst->stream) != cudaSuccess) {
+        b200ppf_table_free(t);
+        return fail_msg(dst, B200PPF_ERR_CUDA, "table clone: copy failed");
+    }
+    *out = t;
+    return B200PPF_OK;
+}
+
 void b200ppf_table_free(b200ppf_table *t) {
     if (!t) return;
     DeviceGuard guard(t->ctx ? t->ctx->device : 0);

@@ -246,10 +246,16 @@ __global__ void merge_offsets_kernel(const uint32_t *__restrict__ sub_offsets, u
     msub_offsets[c] = o < n_entries ? rank[o] : n_merged;
 }
 
-__global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint32_t total_keys,
+// distinct keys of the table: a key counts once however many accumulator slices hold entries of it
+__global__ void count_nonempty_kernel(const uint32_t *__restrict__ offsets, uint32_t key_space, uint32_t n_slices,
                                       unsigned long long *__restrict__ count) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    bool ne = k < total_keys && offsets[k + 1] > offsets[k];
+    bool ne = false;
+    if (k < key_space)
+        for (uint32_t s = 0; s < n_slices && !ne; ++s) {
+            const size_t b = (size_t)s * key_space + k;
+            ne = offsets[b + 1] > offsets[b];
+        }
     uint32_t m = __ballot_sync(0xFFFFFFFFu, ne);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
 }
@@ -631,7 +637,7 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
                 PPF_CUDA(ctx, cudaMemcpyAsync(t->entry_idx, idx[s], (size_t)n_entries * sizeof(uint32_t),
                                               cudaMemcpyDeviceToDevice, ctx->stream));
             }
-            PPF_LAUNCH(ctx, count_nonempty_kernel, (total_keys + 255) / 256, 256, 0, t->offsets, total_keys, d_cnt);
+            PPF_LAUNCH(ctx, count_nonempty_kernel, (kp.key_space + 255) / 256, 256, 0, t->offsets, kp.key_space, info.n_slices, d_cnt);
             return B200PPF_OK;
         };
         K2_TRY(launch());

@@ -542,11 +542,15 @@ ppf_vote_kernel(const VoteArgs a) {
 // all-gather — every rank writes its record r straight into slot (slot_first + r * slot_step) of every peer's
 // buffer over NVLink (peer pointers from cudaIpcOpenMemHandle), so the gathered array is complete and already in
 // reference order on every GPU when the kernels have finished; no staging copy, no NCCL all-gather, no reorder.
-constexpr int MAX_PEERS = 16;
 struct PeerTargets {
     b200ppf_hypothesis *base[MAX_PEERS];
     int n;
     uint32_t slot_first, slot_step;
+    // optional completion signal (b200ppf_group): when the last block of the pose kernel has written its records,
+    // flag word `signal_slot` of every peer's flag array is set to signal_value (system-scope, after a fence)
+    uint32_t *flags[MAX_PEERS];
+    uint32_t signal_slot, signal_value;
+    uint32_t *done_counter;  // blocks finished so far (this device)
 };
 
 // pose of every peak: one thread per reference point
@@ -556,7 +560,7 @@ __global__ void ppf_peak_pose_kernel(const float4 *__restrict__ spos, const floa
                                      const unsigned long long *__restrict__ peaks, BinParams bp,
                                      const PeerTargets out) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= ref_count) return;
+    if (r < ref_count) {
     const uint32_t s_r = ref_first + r * ref_step;
     const unsigned long long pk = peaks[r];
     const uint32_t votes = (uint32_t)(pk >> 32);
@@ -579,6 +583,30 @@ __global__ void ppf_peak_pose_kernel(const float4 *__restrict__ spos, const floa
         for (int q = 0; q < 4; ++q) dst[q] = src[q];  // 4 x 16 bytes: one full 64-byte record per peer
     }
     if (out.n > 1) __threadfence_system();
+    }
+    if (out.done_counter) {
+        // the last block to finish tells every peer that this rank's records have landed
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(out.done_counter, 1u) == gridDim.x - 1) {
+                *out.done_counter = 0;
+                __threadfence_system();
+                for (int g = 0; g < out.n; ++g)
+                    *reinterpret_cast<volatile uint32_t *>(out.flags[g] + out.signal_slot) = out.signal_value;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+// spin until every rank's flag has reached `value` (one thread; the flags are written by the peers' pose kernels)
+__global__ void group_wait_kernel(const uint32_t *flags, int world, uint32_t value) {
+    for (int g = 0; g < world; ++g) {
+        const volatile uint32_t *f = flags + g;
+        while ((int32_t)(*f - value) < 0) __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 // parity hook: per-scene-point quantities of one reference point, exactly as phases A/B see them
@@ -815,12 +843,23 @@ size_t k3_accumulator_budget(const b200ppf_ctx *ctx) {
     return total - queue_bytes(VOTE_THREADS_LARGE) - STATIC_RESERVE;
 }
 
+int k3_group_wait(b200ppf_ctx *ctx, const uint32_t *flags, int world, uint32_t value) {
+    PPF_LAUNCH(ctx, group_wait_kernel, 1, 1, 0, flags, world, value);
+    return B200PPF_OK;
+}
+
 int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
             size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *const *targets, int n_targets,
-            size_t slot_first, size_t slot_step) {
+            size_t slot_first, size_t slot_step, const VoteSignal *signal) {
     if (n_targets < 1 || n_targets > MAX_PEERS) return fail_msg(ctx, B200PPF_ERR_INVALID, "vote: 1..16 output buffers");
     PeerTargets out;
-    for (int g = 0; g < MAX_PEERS; ++g) out.base[g] = g < n_targets ? targets[g] : nullptr;
+    for (int g = 0; g < MAX_PEERS; ++g) {
+        out.base[g] = g < n_targets ? targets[g] : nullptr;
+        out.flags[g] = signal && g < n_targets ? signal->flags[g] : nullptr;
+    }
+    out.signal_slot = signal ? signal->slot : 0u;
+    out.signal_value = signal ? signal->value : 0u;
+    out.done_counter = signal ? signal->done_counter : nullptr;
     out.n = n_targets;
     out.slot_first = (uint32_t)slot_first;
     out.slot_step = (uint32_t)slot_step;
@@ -828,15 +867,20 @@ int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t
     if (rc) return rc;
     if (!model || model->n != t->info.n_model)
         return fail_msg(ctx, B200PPF_ERR_STATE, "vote: model cloud does not match the table (setInputSource vs setSearchMethod)");
-    if (ref_count == 0) return B200PPF_OK;
-    rc = ensure_vote_scratch(ctx, ref_count);
+    if (ref_count == 0 && !signal) return B200PPF_OK;
+    rc = ensure_vote_scratch(ctx, std::max<size_t>(1, ref_count));
     if (rc) return rc;
     cudaEventRecord(ctx->ev_vote[0], ctx->stream);
-    rc = launch_vote(ctx, t, scene, ref_first, ref_step, ref_count, nullptr);  // records ev_vote[1], [2]
-    if (rc) return rc;
+    if (ref_count) {
+        rc = launch_vote(ctx, t, scene, ref_first, ref_step, ref_count, nullptr);  // records ev_vote[1], [2]
+        if (rc) return rc;
+    } else {  // a rank without reference points still signals its peers
+        cudaEventRecord(ctx->ev_vote[1], ctx->stream);
+        cudaEventRecord(ctx->ev_vote[2], ctx->stream);
+    }
     BinParams bp = t->bp;
     bp.mode = ctx->alpha_mode;
-    PPF_LAUNCH(ctx, ppf_peak_pose_kernel, (unsigned)((ref_count + 127) / 128), 128, 0, scene->pos, scene->nrm,
+    PPF_LAUNCH(ctx, ppf_peak_pose_kernel, (unsigned)((std::max<size_t>(1, ref_count) + 127) / 128), 128, 0, scene->pos, scene->nrm,
                model->pos, model->nrm, (uint32_t)ref_first, (uint32_t)ref_step, (uint32_t)ref_count, ctx->d_peaks, bp, out);
     cudaEventRecord(ctx->ev_vote[3], ctx->stream);
     ctx->vote_timed = true;

@@ -17,8 +17,12 @@
 //   * within-bounds needs |dt| < pos_thr, so poses are hashed by translation cell (edge >=
 //     pos_thr) and only the 27 neighbouring cells are searched: O(P) tests for realistic inputs
 //     instead of P^2/2.  Hash collisions only add candidates that the exact test rejects.
-//   * a MEMBER's cluster is the lowest-ranked LEADER within bounds; cluster creation indices are
-//     the exclusive prefix sum of the leader flags.
+//   * the poses that are not MEMBERs yet are kept as one list per translation cell, in rank order, and the
+//     list is compacted after every round: a pose walks only the few earlier leaders and undecided poses of
+//     its 27 cells, not the thousands of members that pile up on one object (config 3: 10 000 of them);
+//   * a MEMBER's cluster is the lowest-ranked LEADER within bounds — the first hit of a walk over the
+//     leaders-only lists, which are in rank order too; cluster creation indices are the exclusive prefix
+//     sum of the leader flags.
 #include <algorithm>
 #include <cmath>
 
@@ -99,17 +103,15 @@ __global__ void cluster_cell_offsets_kernel(const uint32_t *__restrict__ sorted_
     cell_start[c] = lo;
 }
 
-// visit every earlier (rank < k) pose that is within bounds of pose k; f(rank j) returns true to stop.
-// ONLY_LEADERS / !ONLY_LEADERS: poses whose state is not LEADER / is MEMBER are skipped before their 48 bytes
-// are loaded and the rotation test is run — a MEMBER neither blocks nor adopts anybody, and once the dense
-// clusters have resolved almost every earlier pose is one (C3: 82 -> ~10 ms for the 15 rounds).
-template <bool ONLY_LEADERS, class F>
+// Walk the earlier (rank < k) entries of the per-cell lists around pose k, in rank order inside every cell, and call
+// f(rank j) for those within bounds of k; f returns true to stop.  The lists hold what is still of interest — every
+// pose at first, then the non-members, finally the leaders only — and `keep(state)` skips entries untested.
+template <class Keep, class F>
 __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restrict__ poses,
                                                         const uint32_t *__restrict__ cell_start,
-                                                        const uint32_t *__restrict__ cell_rank, HashParams hp,
-                                                        uint32_t k, const float *a, float pos_thr, float rot_thr,
-                                                        const volatile uint32_t *state, const bool &leaders_only_now,
-                                                        F f) {
+                                                        const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t k,
+                                                        const float *a, float pos_thr, float rot_thr,
+                                                        const volatile uint32_t *state, Keep keep, F f) {
     const int cx = cell_of(a[3], hp.inv_cell), cy = cell_of(a[7], hp.inv_cell), cz = cell_of(a[11], hp.inv_cell);
     uint32_t seen[27];
     int n_seen = 0;
@@ -124,11 +126,8 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
                 const uint32_t b = cell_start[h], e = cell_start[h + 1];
                 for (uint32_t s = b; s < e; ++s) {
                     const uint32_t j = cell_rank[s];
-                    if (j >= k) break;  // ranks ascend inside a bucket (stable sort)
-                    const uint32_t sj = state[j];
-                    // once the visitor knows it is blocked (leaders_only_now), an undecided neighbour can no longer
-                    // change its fate — only a LEADER can (it makes the pose a MEMBER): skip the rest untested
-                    if ((ONLY_LEADERS || leaders_only_now) ? sj != ST_LEADER : sj == ST_MEMBER) continue;
+                    if (j >= k) break;  // ranks ascend inside a bucket (stable sort, order-preserving compaction)
+                    if (!keep(state[j])) continue;
                     const PoseRows pj = poses[j];
                     const float ddx = a[3] - pj.r0.w, ddy = a[7] - pj.r1.w, ddz = a[11] - pj.r2.w;
                     if (!(sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz) < pos_thr)) continue;
@@ -139,86 +138,97 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
             }
 }
 
-// Leaders found so far are also kept in per-bucket lists (same slots as the bucket's poses, filled from its
-// start by atomic append): "is there an earlier leader within bounds" — the question that turns a pose into a
-// MEMBER, and the only one the assignment asks — then costs a scan of a few leaders per neighbouring bucket
-// instead of the bucket's whole population (10 000 poses on one object in config 3).  An entry whose store has
-// not landed yet reads as NONE and is simply not seen this round.  f(rank j) returns true to stop.
-template <class F>
-__device__ __forceinline__ void for_each_earlier_leader_within(const PoseRows *__restrict__ poses,
-                                                               const uint32_t *__restrict__ cell_start,
-                                                               const volatile uint32_t *leader_cnt,
-                                                               const volatile uint32_t *leader_list, HashParams hp,
-                                                               uint32_t k, const float *a, float pos_thr, float rot_thr, F f) {
-    const int cx = cell_of(a[3], hp.inv_cell), cy = cell_of(a[7], hp.inv_cell), cz = cell_of(a[11], hp.inv_cell);
-    uint32_t seen[27];
-    int n_seen = 0;
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const uint32_t h = cell_hash(cx + dx, cy + dy, cz + dz, hp.mask);
-                bool dup = false;
-                for (int q = 0; q < n_seen; ++q) dup |= (seen[q] == h);
-                if (dup) continue;
-                seen[n_seen++] = h;
-                const uint32_t b = cell_start[h], cnt = min(leader_cnt[h], cell_start[h + 1] - b);
-                for (uint32_t s = b; s < b + cnt; ++s) {
-                    const uint32_t j = leader_list[s];
-                    if (j >= k) continue;  // later leaders and not-yet-written slots (NONE)
-                    const PoseRows pj = poses[j];
-                    const float ddx = a[3] - pj.r0.w, ddy = a[7] - pj.r1.w, ddz = a[11] - pj.r2.w;
-                    if (!(sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz) < pos_thr)) continue;
-                    float bb[12];
-                    rows_to_array(pj, bb);
-                    if (poses_within(a, bb, pos_thr, rot_thr) && f(j)) return;
-                }
-            }
-}
-
-// one round of the ordered independent-set resolution
+// one round of the ordered independent-set resolution over the non-member lists: the first earlier LEADER within
+// bounds makes the pose a MEMBER; failing that, an earlier UNDECIDED pose within bounds blocks it for this round
+// (from then on only leaders are still tested); a pose that meets neither is a LEADER
 __global__ void __launch_bounds__(128)
 cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
                      const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
-                     volatile uint32_t *state, uint32_t *__restrict__ undecided, uint32_t *leader_cnt,
-                     volatile uint32_t *leader_list) {
+                     volatile uint32_t *state, uint32_t *__restrict__ undecided) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n || state[k] != ST_UNDECIDED) return;
     float a[12];
     rows_to_array(poses[k], a);
     bool blocked = false, member = false;
-    // fast path: an earlier leader within bounds, from the per-bucket leader lists
-    for_each_earlier_leader_within(poses, cell_start, leader_cnt, leader_list, hp, k, a, pos_thr, rot_thr, [&](uint32_t) {
-        member = true;
-        return true;
-    });
-    if (!member) {
-        // otherwise the states decide: the first earlier pose within bounds that is a LEADER makes this one a MEMBER,
-        // the first that is still UNDECIDED blocks it for this round (MEMBERs are skipped unseen); a pose that finds
-        // neither — the only case that scans its whole neighbourhood — is a LEADER
-        const bool never = false;
-        for_each_earlier_within<false>(poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state, never, [&](uint32_t j) {
+    for_each_earlier_within(
+        poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state,
+        [&](uint32_t sj) { return sj == ST_LEADER || (sj == ST_UNDECIDED && !blocked); },
+        [&](uint32_t j) {
+            // decisions use final states only (LEADER / MEMBER never change), so a stale read costs a round, not correctness
             const uint32_t sj = state[j];
             if (sj == ST_LEADER) {
                 member = true;
                 return true;
             }
-            if (sj == ST_UNDECIDED) {
-                blocked = true;
-                return true;
-            }
+            if (sj == ST_UNDECIDED) blocked = true;
             return false;
         });
+    if (member) state[k] = ST_MEMBER;
+    else if (!blocked) state[k] = ST_LEADER;
+    else atomicAdd(undecided, 1u);
+}
+
+// list compaction: keep[s] = the entry's pose is (still) of interest; the scan that follows preserves the order
+__global__ void cluster_keep_flags_kernel(const uint32_t *__restrict__ cell_rank, const uint32_t *__restrict__ n_list,
+                                          const uint32_t *__restrict__ state, uint32_t leaders_only,
+                                          uint32_t *__restrict__ keep) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_list) return;
+    const uint32_t st = state[cell_rank[s]];
+    keep[s] = leaders_only ? (st == ST_LEADER) : (st != ST_MEMBER);
+}
+
+__global__ void cluster_compact_kernel(const uint32_t *__restrict__ cell_rank, const uint32_t *__restrict__ cell_keys,
+                                       const uint32_t *__restrict__ n_list, const uint32_t *__restrict__ keep,
+                                       const uint32_t *__restrict__ pos, uint32_t *__restrict__ rank_out,
+                                       uint32_t *__restrict__ keys_out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_list || !keep[s]) return;
+    rank_out[pos[s]] = cell_rank[s];
+    keys_out[pos[s]] = cell_keys[s];
+}
+
+// cell bounds of a (compacted) list whose length lives on the device
+__global__ void cluster_cell_offsets_dev_kernel(const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ n_list,
+                                                uint32_t n_cells, uint32_t *__restrict__ cell_start) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    uint32_t lo = 0, hi = *n_list;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (sorted_keys[mid] < c) lo = mid + 1; else hi = mid;
     }
-    if (member) {
-        state[k] = ST_MEMBER;
-    } else if (!blocked) {
-        const uint32_t h = cell_hash(cell_of(a[3], hp.inv_cell), cell_of(a[7], hp.inv_cell), cell_of(a[11], hp.inv_cell), hp.mask);
-        leader_list[cell_start[h] + atomicAdd(&leader_cnt[h], 1u)] = k;
-        __threadfence();
-        state[k] = ST_LEADER;
-    } else {
-        atomicAdd(undecided, 1u);
+    cell_start[c] = lo;
+}
+
+// order-preserving positions of the kept list entries (the list length lives on the device)
+__global__ void __launch_bounds__(SCAN_BLOCK)
+keep_count_kernel(const uint32_t *__restrict__ keep, const uint32_t *__restrict__ n_list, uint32_t *__restrict__ block_sums) {
+    const uint32_t k = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const int c = __syncthreads_count(k < *n_list && keep[k] != 0u);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = (uint32_t)c;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+keep_index_kernel(const uint32_t *__restrict__ keep, const uint32_t *__restrict__ n_list,
+                  const uint32_t *__restrict__ block_sums, uint32_t *__restrict__ pos) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t k = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t v = (k < *n_list && keep[k] != 0u) ? 1u : 0u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_tot[threadIdx.x], wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (threadIdx.x >= (uint32_t)o) wi += t;
+        }
+        warp_tot[threadIdx.x] = wi - w;
     }
+    __syncthreads();
+    if (k < *n_list) pos[k] = block_sums[blockIdx.x] + warp_tot[warp] + __popc(m & ((1u << lane) - 1u));
 }
 
 // exclusive prefix sum of the leader flags -> cluster creation index of every leader
@@ -285,12 +295,12 @@ leader_index_kernel(const uint32_t *__restrict__ state, uint32_t n, const uint32
     if (k < n) leader_id[k] = v ? block_sums[blockIdx.x] + warp_tot[warp] + __popc(m & ((1u << lane) - 1u)) : NONE;
 }
 
-// every pose -> its cluster (leaders: their own; members: the lowest-ranked leader within bounds)
+// every pose -> its cluster (leaders: their own; members: the lowest-ranked leader within bounds).  The lists hold
+// leaders only by now; inside a cell they are in rank order, so the walk of a cell stops at its first hit.
 __global__ void __launch_bounds__(128)
 cluster_assign_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
                       const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
-                      const uint32_t *__restrict__ state, const uint32_t *__restrict__ leader_cnt,
-                      const uint32_t *__restrict__ leader_list, const uint32_t *__restrict__ leader_id,
+                      const uint32_t *__restrict__ state, const uint32_t *__restrict__ leader_id,
                       const uint32_t *__restrict__ votes, const uint32_t *__restrict__ order,
                       uint32_t *__restrict__ assign_sorted, uint32_t *__restrict__ assign_input,
                       uint32_t *__restrict__ cluster_votes, uint32_t *__restrict__ cluster_size) {
@@ -303,10 +313,32 @@ cluster_assign_kernel(const PoseRows *__restrict__ poses, const uint32_t *__rest
         float a[12];
         rows_to_array(poses[k], a);
         uint32_t best = NONE;
-        for_each_earlier_leader_within(poses, cell_start, leader_cnt, leader_list, hp, k, a, pos_thr, rot_thr, [&](uint32_t j) {
-            best = min(best, j);
-            return false;
-        });
+        const int cx = cell_of(a[3], hp.inv_cell), cy = cell_of(a[7], hp.inv_cell), cz = cell_of(a[11], hp.inv_cell);
+        uint32_t seen[27];
+        int n_seen = 0;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const uint32_t h = cell_hash(cx + dx, cy + dy, cz + dz, hp.mask);
+                    bool dup = false;
+                    for (int q = 0; q < n_seen; ++q) dup |= (seen[q] == h);
+                    if (dup) continue;
+                    seen[n_seen++] = h;
+                    const uint32_t b = cell_start[h], e = cell_start[h + 1];
+                    for (uint32_t s = b; s < e; ++s) {
+                        const uint32_t j = cell_rank[s];
+                        if (j >= k || j >= best) break;  // ranks ascend: nothing better further on in this cell
+                        const PoseRows pj = poses[j];
+                        const float ddx = a[3] - pj.r0.w, ddy = a[7] - pj.r1.w, ddz = a[11] - pj.r2.w;
+                        if (!(sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz) < pos_thr)) continue;
+                        float bb[12];
+                        rows_to_array(pj, bb);
+                        if (poses_within(a, bb, pos_thr, rot_thr)) {
+                            best = j;
+                            break;
+                        }
+                    }
+                }
         c = best != NONE ? leader_id[best] : 0u;  // a MEMBER always has an earlier leader; guard only
     }
     assign_sorted[k] = c;
@@ -426,8 +458,7 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     const size_t o_keys0 = take(n), o_keys1 = take(n), o_ord0 = take(n), o_ord1 = take(n), o_ck0 = take(n),
                  o_ck1 = take(n), o_cr0 = take(n), o_cr1 = take(n), o_votes = take(n), o_state = take(n),
                  o_lid = take(n), o_as = take(n), o_cv = take(n), o_cs = take(n), o_cell = take((size_t)n_cells + 1),
-                 o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12),
-                 o_lcnt = take(n_cells);
+                 o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12);
     StreamBuf<uint32_t> pool_owner(ctx);  // returned to the pool on every path out of this function
     PPF_CUDA(ctx, pool_owner.alloc(words));
     uint32_t *pool = pool_owner.p;
@@ -437,8 +468,6 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     cl_votes = pool + o_cv; cl_size = pool + o_cs; cell_start = pool + o_cell; block_sums = pool + o_bs;
     small = pool + o_small; d_out = reinterpret_cast<float *>(pool + o_out);
     poses = reinterpret_cast<PoseRows *>(pool + o_poses);
-    uint32_t *leader_cnt = pool + o_lcnt;
-    PPF_CUDA(ctx, cudaMemsetAsync(leader_cnt, 0, (size_t)n_cells * sizeof(uint32_t), st));
     // state .. cl_size are contiguous: one memset clears state (UNDECIDED), leader ids, assignments, cluster sums
     PPF_CUDA(ctx, cudaMemsetAsync(state, 0, (o_cell - o_state) * sizeof(uint32_t), st));
     PPF_CUDA(ctx, cudaMemsetAsync(small, 0, (16 + 48) * sizeof(uint32_t), st));
@@ -476,28 +505,45 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     PPF_LAUNCH(ctx, cluster_cell_offsets_kernel, (n_cells + 1 + 255) / 256, 256, 0, cell_keys_sorted, n, n_cells,
                cell_start);
 
-    // per-bucket leader lists live in the first sort's key buffer (free by now), slots unset = NONE
-    uint32_t *leader_list = keys[0];
-    PPF_CUDA(ctx, cudaMemsetAsync(leader_list, 0xFF, (size_t)n * sizeof(uint32_t), st));
+    // The per-cell lists (cell_rank / cell keys, sorted by cell then rank) start with every pose and are compacted to
+    // the non-members after each round, to the leaders at the end.  keep flags and positions live in the first
+    // sort's buffers (free by now); small[9] = current list length.
+    uint32_t *keep = keys[0], *pos = keys[1];
+    int cur = in_alt ? 1 : 0;  // which crank / ckeys buffer holds the current lists
+    uint32_t n_list = n;
+    PPF_CUDA(ctx, cudaMemcpyAsync(small + 9, &n_list, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    auto compact = [&](uint32_t leaders_only) -> int {
+        const unsigned gl = (n_list + 255) / 256, gs = (n_list + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        if (n_list == 0) return B200PPF_OK;
+        PPF_LAUNCH(ctx, cluster_keep_flags_kernel, gl, 256, 0, crank[cur], small + 9, state, leaders_only, keep);
+        PPF_LAUNCH(ctx, keep_count_kernel, gs, SCAN_BLOCK, 0, keep, small + 9, block_sums);
+        PPF_LAUNCH(ctx, leader_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, gs, small + 10);
+        PPF_LAUNCH(ctx, keep_index_kernel, gs, SCAN_BLOCK, 0, keep, small + 9, block_sums, pos);
+        PPF_LAUNCH(ctx, cluster_compact_kernel, gl, 256, 0, crank[cur], ckeys[cur], small + 9, keep, pos, crank[1 - cur], ckeys[1 - cur]);
+        PPF_CUDA(ctx, cudaMemcpyAsync(small + 9, small + 10, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        cur = 1 - cur;
+        PPF_LAUNCH(ctx, cluster_cell_offsets_dev_kernel, (n_cells + 1 + 255) / 256, 256, 0, ckeys[cur], small + 9, n_cells, cell_start);
+        return B200PPF_OK;
+    };
     // ordered independent-set rounds until nothing is undecided
     const unsigned gr = (n + 127) / 128;
     for (int iter = 0;; ++iter) {
-        const int rounds = iter == 0 ? 3 : 4;
-        for (int r = 0; r < rounds; ++r) {
-            PPF_CUDA(ctx, cudaMemsetAsync(small + 1, 0, sizeof(uint32_t), st));
-            PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, cell_rank, hp, n, pos_thr, rot_thr,
-                       state, small + 1, leader_cnt, leader_list);
-        }
-        PPF_CUDA(ctx, cudaMemcpyAsync(h_small + 1, small + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PPF_CUDA(ctx, cudaMemsetAsync(small + 1, 0, sizeof(uint32_t), st));
+        PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, crank[cur], hp, n, pos_thr, rot_thr, state, small + 1);
+        // lists worth compacting: the walk of a pose is as long as the non-members of its 27 cells
+        if (n_list > 2048 && (rc = compact(0u))) return rc;
+        PPF_CUDA(ctx, cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
         PPF_CUDA(ctx, cudaStreamSynchronize(st));
+        n_list = h_small[9];
         if (h_small[1] == 0) break;
         if (iter > (int)n) return fail_msg(ctx, B200PPF_ERR_CUDA, "cluster: leader resolution did not converge");
     }
+    if ((rc = compact(1u))) return rc;  // leaders only, rank order inside every cell
     PPF_LAUNCH(ctx, leader_count_kernel, n_scan_blocks, SCAN_BLOCK, 0, state, n, block_sums);
     PPF_LAUNCH(ctx, leader_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, n_scan_blocks, small + 2);
     PPF_LAUNCH(ctx, leader_index_kernel, n_scan_blocks, SCAN_BLOCK, 0, state, n, block_sums, leader_id);
-    PPF_LAUNCH(ctx, cluster_assign_kernel, gr, 128, 0, poses, cell_start, cell_rank, hp, n, pos_thr, rot_thr, state,
-               leader_cnt, leader_list, leader_id, votes, ord, assign_sorted, ctx->d_assign, cl_votes, cl_size);
+    PPF_LAUNCH(ctx, cluster_assign_kernel, gr, 128, 0, poses, cell_start, crank[cur], hp, n, pos_thr, rot_thr, state,
+               leader_id, votes, ord, assign_sorted, ctx->d_assign, cl_votes, cl_size);
     PPF_LAUNCH(ctx, cluster_top3_kernel, 1, 1024, 0, cl_votes, small + 2, small + 3);
     PPF_LAUNCH(ctx, cluster_average_kernel, 3, 256, 0, poses, assign_sorted, n, small + 3, cl_votes, cl_size, d_out,
                small + 6);

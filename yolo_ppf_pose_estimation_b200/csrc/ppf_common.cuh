@@ -138,9 +138,17 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *f, const b200ppf_cloud *m
 int k2_query_key(b200ppf_ctx *ctx, const b200ppf_table *t, const int32_t *d4, uint64_t *pairs, size_t cap,
                  size_t *n_found);
 int k2_alpha_m(b200ppf_ctx *ctx, const b200ppf_table *t, float *host);
+constexpr int MAX_PEERS = 16;
+// completion signal of a vote (b200ppf_group): flag word `slot` of every target's flag array := value
+struct VoteSignal {
+    uint32_t *flags[MAX_PEERS];
+    uint32_t slot, value;
+    uint32_t *done_counter;
+};
 int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene,
             size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *const *targets, int n_targets,
-            size_t slot_first, size_t slot_step);
+            size_t slot_first, size_t slot_step, const VoteSignal *signal = nullptr);
+int k3_group_wait(b200ppf_ctx *ctx, const uint32_t *flags, int world, uint32_t value);
 int k3_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
                    uint8_t *in_radius, int32_t *d4, float *alpha_s);
 int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
