@@ -420,6 +420,62 @@ int b200ppf_match_object(b200ppf_ctx *ctx, const b200ppf_cloud *scene, const flo
                          const b200ppf_cloud *model, const b200ppf_table *table, const b200ppf_object_params *params,
                          b200ppf_object_result *result, b200ppf_cloud **object_out, b200ppf_cloud **edges_out);
 
+/* ---- the engine the reference actually calls: cv::ppf_match_3d::PPF3DDetector ---------------------------------------
+ * include/CloudProcessing.h:205,217,234 construct PPF3DDetector(relativeSamplingStep, relativeDistanceStep), :236 trains it
+ * (trainModel), :442 matches (match(scene, results, relativeSceneSampleStep, relativeSceneDistance)) and :495 calls the
+ * fork-only match_S2B(scene, edge, results, ...).  opencv_contrib surface_matching (ppf_match_3d.cpp, ppf_helpers.cpp,
+ * c_utils.hpp, hash_murmur86.hpp, t_hash_int.cpp, pose_3d.cpp) restated for the device in csrc/k7_cvppf.cu; the
+ * OpenCV-shaped class over these entry points is include/opencv_compat/opencv2/surface_matching/ppf_match_3d.hpp.
+ * Clouds are host rows of stride_floats >= 6 floats [x y z nx ny nz] (the reference's N x 6 CV_32F cv::Mat).
+ * match_S2B: the fork's source is not available; by its name (surface-to-boundary pairs, Choi et al.) and its inputs (the
+ * object cloud and the curvature-edge cloud EdgeExtraction makes of it) it is taken to be match() with the reference
+ * points drawn from the sampled surface cloud and paired with the sampled EDGE cloud instead of the surface cloud. */
+typedef struct b200cv_detector b200cv_detector;
+/* cv::ppf_match_3d::Pose3D: pose, alpha, residual, modelIndex, numVotes, angle, t, q (w x y z) + the peak it came from */
+typedef struct b200cv_pose {
+    double pose[16]; /* row-major 4x4, model -> scene */
+    double alpha, residual, angle;
+    double t[3];
+    double q[4];
+    uint32_t model_index, num_votes;
+    uint32_t alpha_index, reference_index;
+} b200cv_pose;
+typedef struct b200cv_info {
+    uint64_t n_sampled;  /* model points after samplePCByQuantization */
+    uint64_t table_size; /* buckets of the hash table: the power of two >= n_sampled^2 (>= 16) */
+    uint64_t n_nodes;    /* n_sampled * (n_sampled - 1) */
+    uint64_t n_scene_sampled, n_second_sampled; /* last match: sampled scene points, points they were paired with */
+    double angle_step, distance_step;
+    double position_threshold, rotation_threshold;
+    int32_t num_angles;
+    int32_t reserved;
+} b200cv_info;
+int b200cv_detector_create(b200ppf_ctx *ctx, double relative_sampling_step, double relative_distance_step,
+                           double num_angles, b200cv_detector **out);
+void b200cv_detector_free(b200cv_detector *d);
+/* setSearchParams(positionThreshold, rotationThreshold): a negative value keeps the default */
+int b200cv_detector_set_search_params(b200cv_detector *d, double position_threshold, double rotation_threshold);
+int b200cv_detector_train(b200cv_detector *d, const float *model, size_t n, size_t stride_floats);
+int b200cv_detector_get_info(const b200cv_detector *d, b200cv_info *info);
+int b200cv_detector_model_points(const b200cv_detector *d, float *out6);  /* n_sampled x 6 */
+int b200cv_detector_scene_points(const b200cv_detector *d, float *out6);  /* last match: n_scene_sampled x 6 */
+/* results: the pose clusters, best first (at most cap are written, *n_results receives the number of clusters) */
+int b200cv_detector_match(b200cv_detector *d, const float *scene, size_t n, size_t stride_floats,
+                          double relative_scene_sample_step, double relative_scene_distance, b200cv_pose *results,
+                          size_t cap, size_t *n_results);
+int b200cv_detector_match_s2b(b200cv_detector *d, const float *scene, size_t n, size_t stride_floats, const float *edge,
+                              size_t n_edge, size_t edge_stride_floats, double relative_scene_sample_step,
+                              double relative_scene_distance, b200cv_pose *results, size_t cap, size_t *n_results);
+/* parity hooks: one bucket of the table (ppfInd = i * n_sampled + j, ascending), the whole table, the per-reference poses
+ * of the last match before clustering, the accumulator (n_sampled * num_angles words) of one reference point */
+int b200cv_detector_bucket(b200cv_detector *d, size_t bucket, uint32_t *ppf_ind, size_t cap, size_t *n_found);
+int b200cv_detector_table_export(b200cv_detector *d, uint32_t *offsets, uint32_t *nodes, float *alpha_m);
+int b200cv_detector_raw_poses(const b200cv_detector *d, b200cv_pose *raw, size_t cap, size_t *n);
+int b200cv_detector_debug_accumulator(b200cv_detector *d, const float *scene, size_t n, size_t stride_floats,
+                                      const float *edge, size_t n_edge, size_t edge_stride_floats,
+                                      double relative_scene_sample_step, double relative_scene_distance, size_t reference,
+                                      uint32_t *acc);
+
 #ifdef __cplusplus
 }
 #endif

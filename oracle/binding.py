@@ -133,6 +133,14 @@ def _declare(L):
     L.oracle_cv_model_points.restype = sz
     L.oracle_cv_match.argtypes = [vp, vp, sz, C.c_double, C.c_double, vp, vp, sz, vp, C.POINTER(sz), C.c_int]
     L.oracle_cv_match.restype = sz
+    L.oracle_cv_match_s2b.argtypes = [vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, vp, sz, vp, C.POINTER(sz), C.c_int]
+    L.oracle_cv_match_s2b.restype = sz
+    L.oracle_cv_table_size.argtypes = [vp]
+    L.oracle_cv_table_size.restype = sz
+    L.oracle_cv_bucket.argtypes = [vp, sz, vp, sz]
+    L.oracle_cv_bucket.restype = sz
+    L.oracle_cv_accumulator.argtypes = [vp, vp, sz, vp, sz, C.c_double, sz, vp]
+    L.oracle_cv_accumulator.restype = sz
 
 
 def _f32(a):
@@ -512,3 +520,36 @@ class CvDetector:
                                     n_threads or max_threads())
         k = min(int(ncl), max_poses)
         return poses[:k].reshape(-1, 4, 4), votes[:k], raw[:n_refs.value].copy(), int(ncl)
+
+    def match_s2b(self, scene, edge, relative_scene_sample_step=1.0 / 5.0, relative_scene_distance=0.03, max_poses=16, n_threads=None):
+        """the fork's match_S2B as inferred: reference points from the scene, paired with the edge cloud; returns as match()"""
+        scene, edge = _f32(scene), _f32(edge)
+        poses = np.zeros((max_poses, 16), np.float64)
+        votes = np.zeros(max_poses, np.uint32)
+        raw = np.zeros((scene.shape[0], 3), np.uint32)
+        n_refs = C.c_size_t(0)
+        ncl = lib().oracle_cv_match_s2b(self._h, _p(scene), scene.shape[0], _p(edge), edge.shape[0], float(relative_scene_sample_step),
+                                        float(relative_scene_distance), _p(poses), _p(votes), max_poses, _p(raw), C.byref(n_refs),
+                                        n_threads or max_threads())
+        k = min(int(ncl), max_poses)
+        return poses[:k].reshape(-1, 4, 4), votes[:k], raw[:n_refs.value].copy(), int(ncl)
+
+    @property
+    def table_size(self):
+        return int(lib().oracle_cv_table_size(self._h))
+
+    def bucket(self, b):
+        """ppfInd = i * M + j of the nodes chained in bucket b, ascending"""
+        n = int(lib().oracle_cv_bucket(self._h, int(b), None, 0))
+        out = np.zeros(n, np.uint32)
+        if n:
+            lib().oracle_cv_bucket(self._h, int(b), _p(out), n)
+        return out
+
+    def accumulator(self, scene, sampled_index, relative_scene_distance, num_angles=30, edge=None):
+        scene = _f32(scene)
+        edge = None if edge is None else _f32(edge)
+        acc = np.zeros((self.n_model, num_angles), np.uint32)
+        lib().oracle_cv_accumulator(self._h, _p(scene), scene.shape[0], _p(edge) if edge is not None else None,
+                                    0 if edge is None else edge.shape[0], float(relative_scene_distance), int(sampled_index), _p(acc))
+        return acc

@@ -365,6 +365,18 @@ size_t oracle_cv_model_points(const oracle_cv_detector *d, float *out6) {
 size_t oracle_cv_match(const oracle_cv_detector *d, const float *scene, size_t n, double relative_scene_sample_step,
                        double relative_scene_distance, double *out_poses, uint32_t *out_votes, size_t cap, uint32_t *raw3,
                        size_t *n_refs, int n_threads) {
+    return oracle_cv_match_s2b(d, scene, n, nullptr, 0, relative_scene_sample_step, relative_scene_distance, out_poses, out_votes,
+                               cap, raw3, n_refs, n_threads);
+}
+
+/* match_S2B(scene, edge, ...) of the reference's private fork (include/CloudProcessing.h:495) — source unavailable.
+ * INFERRED from the name (Choi et al., surface-to-boundary pairs) and from its inputs (the object cloud and the
+ * curvature-edge cloud EdgeExtraction makes of it): reference points are taken from the sampled surface cloud exactly
+ * as in match(); the points they are paired with are the sampled EDGE cloud (sampled over its own bounding box with
+ * the same relative distance) instead of the surface cloud itself.  edge == nullptr is match(). */
+size_t oracle_cv_match_s2b(const oracle_cv_detector *d, const float *scene, size_t n, const float *edge, size_t n_edge,
+                           double relative_scene_sample_step, double relative_scene_distance, double *out_poses,
+                           uint32_t *out_votes, size_t cap, uint32_t *raw3, size_t *n_refs, int n_threads) {
     const size_t m = d->m();
     const int num_angles = (int)std::floor(2 * PI / d->angle_step);
     const int step = (int)(1.0 / relative_scene_sample_step);
@@ -372,6 +384,14 @@ size_t oracle_cv_match(const oracle_cv_detector *d, const float *scene, size_t n
     bbox6(scene, n, r);
     const std::vector<float> sampled = sample_by_quantization(scene, n, r, (float)relative_scene_distance);
     const size_t ns = sampled.size() / 6;
+    std::vector<float> sampled_edge;
+    if (edge) {
+        float re[6];
+        bbox6(edge, n_edge, re);
+        sampled_edge = sample_by_quantization(edge, n_edge, re, (float)relative_scene_distance);
+    }
+    const std::vector<float> &second = edge ? sampled_edge : sampled;  // the points a reference point is paired with
+    const size_t n2 = second.size() / 6;
     const size_t refs = step > 0 ? (ns + step - 1) / step : 0;
     if (n_refs) *n_refs = refs;
     std::vector<Pose> poses(refs);
@@ -384,11 +404,11 @@ size_t oracle_cv_match(const oracle_cv_detector *d, const float *scene, size_t n
         M33 Rsg;
         V3 tsg;
         compute_transform_rt(p1, n1, Rsg, tsg);
-        for (size_t j = 0; j < ns; ++j) {
-            if (i == j) continue;
-            const V3 p2 = ld(&sampled[6 * j]), n2 = ld(&sampled[6 * j + 3]);
+        for (size_t j = 0; j < n2; ++j) {
+            if (!edge && i == j) continue;
+            const V3 p2 = ld(&second[6 * j]), nrm2 = ld(&second[6 * j + 3]);
             double f[4];
-            ppf_features(p1, n1, p2, n2, f);
+            ppf_features(p1, n1, p2, nrm2, f);
             const uint32_t h = hash_ppf(f, d->angle_step, (float)d->distance_step);
             bool is_nan;
             const double alpha_scene = planar_alpha(Rsg, tsg, p2, &is_nan);
@@ -479,6 +499,59 @@ size_t oracle_cv_match(const oracle_cv_detector *d, const float *scene, size_t n
         out_votes[o] = (uint32_t)std::min<uint64_t>(cluster_votes[corder[o]], 0xFFFFFFFFull);
     }
     return clusters.size();
+}
+
+size_t oracle_cv_table_size(const oracle_cv_detector *d) { return d->table_size; }
+
+size_t oracle_cv_bucket(const oracle_cv_detector *d, size_t bucket, uint32_t *ppf_ind, size_t cap) {
+    if (bucket >= d->buckets.size()) return 0;
+    std::vector<uint32_t> v;
+    for (const auto &node : d->buckets[bucket]) v.push_back(node.second);
+    std::sort(v.begin(), v.end());
+    for (size_t k = 0; k < v.size() && k < cap; ++k) ppf_ind[k] = v[k];
+    return v.size();
+}
+
+/* the voting loop of one reference point (index into the SAMPLED scene), accumulator only */
+size_t oracle_cv_accumulator(const oracle_cv_detector *d, const float *scene, size_t n, const float *edge, size_t n_edge,
+                             double relative_scene_distance, size_t i, uint32_t *acc) {
+    const size_t m = d->m();
+    const int num_angles = (int)std::floor(2 * PI / d->angle_step);
+    float r[6];
+    bbox6(scene, n, r);
+    const std::vector<float> sampled = sample_by_quantization(scene, n, r, (float)relative_scene_distance);
+    std::vector<float> sampled_edge;
+    if (edge) {
+        float re[6];
+        bbox6(edge, n_edge, re);
+        sampled_edge = sample_by_quantization(edge, n_edge, re, (float)relative_scene_distance);
+    }
+    const std::vector<float> &second = edge ? sampled_edge : sampled;
+    const size_t ns = sampled.size() / 6, n2 = second.size() / 6;
+    std::memset(acc, 0, m * (size_t)num_angles * sizeof(uint32_t));
+    if (i >= ns) return 0;
+    const V3 p1 = ld(&sampled[6 * i]), n1 = ld(&sampled[6 * i + 3]);
+    M33 Rsg;
+    V3 tsg;
+    compute_transform_rt(p1, n1, Rsg, tsg);
+    size_t votes = 0;
+    for (size_t j = 0; j < n2; ++j) {
+        if (!edge && i == j) continue;
+        const V3 p2 = ld(&second[6 * j]), nrm2 = ld(&second[6 * j + 3]);
+        double f[4];
+        ppf_features(p1, n1, p2, nrm2, f);
+        const uint32_t h = hash_ppf(f, d->angle_step, (float)d->distance_step);
+        bool is_nan;
+        const double alpha_scene = planar_alpha(Rsg, tsg, p2, &is_nan);
+        if (is_nan) continue;
+        for (const auto &node : d->buckets[h & (d->table_size - 1)]) {
+            const double alpha = (double)d->alpha_m[node.second] - alpha_scene;
+            const int alpha_index = (int)(num_angles * (alpha + 2 * PI) / (4 * PI));
+            const size_t a = (size_t)node.first * num_angles + (size_t)alpha_index;
+            if (a < m * (size_t)num_angles) acc[a]++, ++votes;
+        }
+    }
+    return votes;
 }
 
 }  // extern "C"

@@ -190,6 +190,17 @@ size_t oracle_cv_match(const oracle_cv_detector *d, const float *scene, size_t n
                        double relative_scene_distance, double *out_poses, uint32_t *out_votes, size_t cap, uint32_t *raw3,
                        size_t *n_refs, int n_threads);
 
+/* the fork-only match_S2B as inferred (see cvppf_oracle.cpp): reference points from the scene, paired with the edge cloud */
+size_t oracle_cv_match_s2b(const oracle_cv_detector *d, const float *scene, size_t n, const float *edge, size_t n_edge,
+                           double relative_scene_sample_step, double relative_scene_distance, double *out_poses,
+                           uint32_t *out_votes, size_t cap, uint32_t *raw3, size_t *n_refs, int n_threads);
+/* parity hooks for the device engine: one bucket of the chained table as (i, ppfInd) pairs sorted by ppfInd (returns its
+ * length), the table size, and the accumulator of one reference point of match / match_S2B (m * num_angles words) */
+size_t oracle_cv_table_size(const oracle_cv_detector *d);
+size_t oracle_cv_bucket(const oracle_cv_detector *d, size_t bucket, uint32_t *ppf_ind, size_t cap);
+size_t oracle_cv_accumulator(const oracle_cv_detector *d, const float *scene, size_t n, const float *edge, size_t n_edge,
+                             double relative_scene_distance, size_t sampled_index, uint32_t *acc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,12 +24,16 @@ def main():
     ap.add_argument("--sizes", default="5000,10000,20000,35000,50000")
     ap.add_argument("--features", action="store_true", help="also time K1 with the materialised N*N*20 B feature cloud")
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--cpu-max", type=int, default=10000,
+                    help="largest model for which the CPU side (PPFEstimation + PPFHashMapSearch::setInputFeatureCloud, one thread = PCL "
+                         "as shipped) is measured; larger ones are extrapolated in proportion to the pairs and flagged")
     args = ap.parse_args()
     peak = 6549.4
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peak = float(json.load(open(p))["hbm_gbs"])
     ctx = capi.Context(0)
+    cpu_ref = None  # (pairs, estimation seconds, container seconds) of the largest measured CPU build
     for n in [int(x) for x in args.sizes.split(",")]:
         model = synth.synth_model(n, 1)
         dm = ctx.upload_cloud(model)
@@ -58,6 +62,27 @@ def main():
             best["k1_write_gbs"] = 20.0 * n * n / (best["k1_features_ms"] * 1e-3) / 1e9
             best["k1_hbm_frac"] = best["k1_write_gbs"] / peak
             F.free()
+        # the CPU side of BASELINE config 5: the oracle's literal restatement on one thread
+        if args.cpu_max and n <= args.cpu_max:
+            from oracle import binding as ob
+            t0 = time.perf_counter()
+            feats = ob.ppf_estimation(model, n_threads=1)
+            t1 = time.perf_counter()
+            hm = ob.HashMap(workloads.ANGLE_STEP, workloads.DIST_STEP).set_input_feature_cloud(feats, n_threads=1)
+            t2 = time.perf_counter()
+            assert hm.num_entries == best["entries"] or abs(hm.num_entries - best["entries"]) <= 64
+            cpu_ref = (n * (n - 1), t1 - t0, t2 - t1)
+            best["cpu"] = {"estimation_s": t1 - t0, "hashmap_s": t2 - t1, "threads": 1, "extrapolated": False,
+                           "note": "oracle port; above 1024 model points its container mixes the key hash (PCL's own hash makes the "
+                                   "build quadratic: 41 min for 2 009 points), i.e. this CPU side is faster than PCL as shipped"}
+            del hm, feats
+        elif cpu_ref is not None:
+            k = n * (n - 1) / cpu_ref[0]
+            best["cpu"] = {"estimation_s": cpu_ref[1] * k, "hashmap_s": cpu_ref[2] * k, "threads": 1, "extrapolated": True,
+                           "note": "scaled with the pairs from the largest measured build (SURVEY.md §8d: the multimap of 50 000 points "
+                                   "would need ~150 GB)"}
+        if "cpu" in best:
+            best["speedup_vs_cpu"] = (best["cpu"]["estimation_s"] + best["cpu"]["hashmap_s"]) / (best["device_ms"] * 1e-3)
         print(json.dumps(best), flush=True)
         dm.free()
 

@@ -17,7 +17,7 @@ BUILD_DIR = os.path.join(_HERE, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "libb200ppf.so")
 
 SOURCES = ["capi.cu", "radix_sort.cu", "k1_features.cu", "k2_table.cu", "k3_vote.cu", "scene_grid.cu", "k4_cluster.cu",
-           "k5_transform.cu", "k6_icp.cu", "prep.cu", "microbench.cu", "group.cu"]
+           "k5_transform.cu", "k6_icp.cu", "prep.cu", "microbench.cu", "group.cu", "k7_cvppf.cu"]
 HEADERS = ["ppf_common.cuh", "ppf_math.cuh", os.path.join("..", "..", "include", "b200ppf.h")]
 
 NVCC_FLAGS = [

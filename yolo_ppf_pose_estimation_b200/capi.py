@@ -57,6 +57,19 @@ class ObjectResult(C.Structure):
                                          "total_wall_ms")]
 
 
+CV_POSE_DTYPE = np.dtype([("pose", np.float64, (16,)), ("alpha", np.float64), ("residual", np.float64), ("angle", np.float64),
+                          ("t", np.float64, (3,)), ("q", np.float64, (4,)), ("model_index", np.uint32), ("num_votes", np.uint32),
+                          ("alpha_index", np.uint32), ("reference_index", np.uint32)])
+assert CV_POSE_DTYPE.itemsize == 224
+
+
+class CvInfo(C.Structure):
+    _fields_ = [("n_sampled", C.c_uint64), ("table_size", C.c_uint64), ("n_nodes", C.c_uint64), ("n_scene_sampled", C.c_uint64),
+                ("n_second_sampled", C.c_uint64), ("angle_step", C.c_double), ("distance_step", C.c_double),
+                ("position_threshold", C.c_double), ("rotation_threshold", C.c_double), ("num_angles", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 # every symbol include/b200ppf.h declares: (name, restype, argtypes)
 _vp, _sz, _f, _i = C.c_void_p, C.c_size_t, C.c_float, C.c_int
 SYMBOLS = {
@@ -142,6 +155,19 @@ SYMBOLS = {
     "b200ppf_match_object": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(ObjectParams), C.POINTER(ObjectResult), C.POINTER(_vp),
                                   C.POINTER(_vp)]),
     "b200ppf_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
+    "b200cv_detector_create": (_i, [_vp, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "b200cv_detector_free": (None, [_vp]),
+    "b200cv_detector_set_search_params": (_i, [_vp, C.c_double, C.c_double]),
+    "b200cv_detector_train": (_i, [_vp, _vp, _sz, _sz]),
+    "b200cv_detector_get_info": (_i, [_vp, C.POINTER(CvInfo)]),
+    "b200cv_detector_model_points": (_i, [_vp, _vp]),
+    "b200cv_detector_scene_points": (_i, [_vp, _vp]),
+    "b200cv_detector_match": (_i, [_vp, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _sz, C.POINTER(_sz)]),
+    "b200cv_detector_match_s2b": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, C.c_double, C.c_double, _vp, _sz, C.POINTER(_sz)]),
+    "b200cv_detector_bucket": (_i, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "b200cv_detector_table_export": (_i, [_vp, _vp, _vp, _vp]),
+    "b200cv_detector_raw_poses": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "b200cv_detector_debug_accumulator": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, C.c_double, C.c_double, _sz, _vp]),
 }
 
 _lib = None
@@ -479,6 +505,107 @@ class Context:
         self.check(lib().b200ppf_register(self._h, model._h, table._h, scene._h, ref_rate, np.float32(pos_thr),
                                           np.float32(rot_thr), _p(final), _p(poses), _p(votes), C.byref(k)))
         return final.reshape(4, 4), poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
+
+
+class CvDetector:
+    """cv::ppf_match_3d::PPF3DDetector(relativeSamplingStep, relativeDistanceStep = 0.05, numAngles = 30) on the device
+    (b200cv_*; reference include/CloudProcessing.h:205-236, :442, :495)."""
+
+    def __init__(self, ctx: "Context", relative_sampling_step, relative_distance_step=0.05, num_angles=30):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx.check(lib().b200cv_detector_create(ctx._h, float(relative_sampling_step), float(relative_distance_step),
+                                               float(num_angles), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().b200cv_detector_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_search_params(self, position_threshold=-1.0, rotation_threshold=-1.0):
+        self.ctx.check(lib().b200cv_detector_set_search_params(self._h, float(position_threshold), float(rotation_threshold)))
+
+    def train_model(self, model):
+        m = np.ascontiguousarray(model, np.float32)
+        self.ctx.check(lib().b200cv_detector_train(self._h, _p(m), m.shape[0], m.shape[1]))
+        return self
+
+    @property
+    def info(self) -> CvInfo:
+        ci = CvInfo()
+        self.ctx.check(lib().b200cv_detector_get_info(self._h, C.byref(ci)))
+        return ci
+
+    def model_points(self):
+        out = np.zeros((self.info.n_sampled, 6), np.float32)
+        self.ctx.check(lib().b200cv_detector_model_points(self._h, _p(out)))
+        return out
+
+    def scene_points(self):
+        out = np.zeros((self.info.n_scene_sampled, 6), np.float32)
+        self.ctx.check(lib().b200cv_detector_scene_points(self._h, _p(out)))
+        return out
+
+    def _match(self, scene, edge, sample_step, distance, max_poses):
+        s = np.ascontiguousarray(scene, np.float32)
+        res = np.zeros(max_poses, CV_POSE_DTYPE)
+        k = C.c_size_t(0)
+        if edge is None:
+            self.ctx.check(lib().b200cv_detector_match(self._h, _p(s), s.shape[0], s.shape[1], float(sample_step), float(distance),
+                                                       _p(res), max_poses, C.byref(k)))
+        else:
+            e = np.ascontiguousarray(edge, np.float32)
+            self.ctx.check(lib().b200cv_detector_match_s2b(self._h, _p(s), s.shape[0], s.shape[1], _p(e), e.shape[0], e.shape[1],
+                                                           float(sample_step), float(distance), _p(res), max_poses, C.byref(k)))
+        return res[:min(k.value, max_poses)], int(k.value)
+
+    def match(self, scene, relative_scene_sample_step=1.0 / 5.0, relative_scene_distance=0.03, max_poses=16):
+        """-> (pose clusters best first as CV_POSE_DTYPE records, number of clusters)"""
+        return self._match(scene, None, relative_scene_sample_step, relative_scene_distance, max_poses)
+
+    def match_s2b(self, scene, edge, relative_scene_sample_step=1.0 / 5.0, relative_scene_distance=0.03, max_poses=16):
+        return self._match(scene, edge, relative_scene_sample_step, relative_scene_distance, max_poses)
+
+    def raw_poses(self):
+        """the per-reference poses of the last match, before clustering"""
+        k = C.c_size_t(0)
+        self.ctx.check(lib().b200cv_detector_raw_poses(self._h, None, 0, C.byref(k)))
+        out = np.zeros(k.value, CV_POSE_DTYPE)
+        self.ctx.check(lib().b200cv_detector_raw_poses(self._h, _p(out), k.value, C.byref(k)))
+        return out
+
+    def bucket(self, b):
+        k = C.c_size_t(0)
+        self.ctx.check(lib().b200cv_detector_bucket(self._h, int(b), None, 0, C.byref(k)))
+        out = np.zeros(k.value, np.uint32)
+        if k.value:
+            self.ctx.check(lib().b200cv_detector_bucket(self._h, int(b), _p(out), k.value, C.byref(k)))
+        return out
+
+    def table_export(self):
+        ci = self.info
+        off = np.zeros(ci.table_size + 1, np.uint32)
+        nodes = np.zeros(ci.n_nodes, np.uint32)
+        alpha = np.zeros(ci.n_sampled * ci.n_sampled, np.float32)
+        self.ctx.check(lib().b200cv_detector_table_export(self._h, _p(off), _p(nodes), _p(alpha)))
+        return off, nodes, alpha
+
+    def accumulator(self, scene, reference, relative_scene_sample_step, relative_scene_distance, edge=None):
+        """accumulator (M, numAngles) of reference point number `reference` (the reference-th of the sampled references)"""
+        s = np.ascontiguousarray(scene, np.float32)
+        ci = self.info
+        acc = np.zeros((ci.n_sampled, ci.num_angles), np.uint32)
+        e = None if edge is None else np.ascontiguousarray(edge, np.float32)
+        self.ctx.check(lib().b200cv_detector_debug_accumulator(self._h, _p(s), s.shape[0], s.shape[1], _p(e), 0 if e is None else e.shape[0],
+                                                               0 if e is None else e.shape[1], float(relative_scene_sample_step),
+                                                               float(relative_scene_distance), int(reference), _p(acc)))
+        return acc
 
 
 GROUP_HANDLE_BYTES = 192

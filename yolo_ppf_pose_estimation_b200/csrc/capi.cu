@@ -77,6 +77,14 @@ int b200ppf_create(int device, b200ppf_ctx **out) {
     }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     for (auto &ev : ctx->ev_vote) cudaEventCreate(&ev);
+    {   // keep freed scratch and table arrays in the device's stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return B200PPF_OK;
 }
@@ -628,7 +636,7 @@ int b200ppf_table_load(b200ppf_ctx *ctx, const char *path, b200ppf_table **out) 
         if (a >= 6 && !has_merged) continue;
         const size_t pad = (a == 2 || a == 3 || a == 6) ? b200ppf::ENTRY_PAD : 0;
         const size_t words = std::max<size_t>(1, lengths[a] + pad);
-        cudaError_t e = cudaMalloc(dev[a], words * sizeof(uint32_t));
+        cudaError_t e = cudaMallocAsync(dev[a], words * sizeof(uint32_t), ctx->stream);
         if (e == cudaSuccess && pad) e = cudaMemsetAsync(*dev[a] + lengths[a], 0, pad * sizeof(uint32_t), ctx->stream);
         if (e == cudaSuccess && lengths[a])
             e = cudaMemcpyAsync(*dev[a], host[a].data(), lengths[a] * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
@@ -675,7 +683,7 @@ int b200ppf_table_clone(b200ppf_ctx *dst, const b200ppf_table *src, b200ppf_tabl
                  {&src->msub_offsets, &t->msub_offsets, src->msub_offsets ? n_sub : 0, 0}};
     for (const Arr &a : arrs) {
         if (!*a.from) continue;
-        cudaError_t e = cudaMalloc(a.to, (a.words + a.pad) * sizeof(uint32_t));
+        cudaError_t e = cudaMallocAsync(a.to, (a.words + a.pad) * sizeof(uint32_t), dst->stream);
         if (e == cudaSuccess && a.pad) e = cudaMemsetAsync(*a.to + a.words, 0, a.pad * sizeof(uint32_t), dst->stream);
         if (e == cudaSuccess && a.words)
             e = cudaMemcpyPeerAsync(*a.to, dst->device, *a.from, src_dev, a.words * sizeof(uint32_t), dst->stream);
@@ -695,14 +703,14 @@ int b200ppf_table_clone(b200ppf_ctx *dst, const b200ppf_table *src, b200ppf_tabl
 void b200ppf_table_free(b200ppf_table *t) {
     if (!t) return;
     DeviceGuard guard(t->ctx ? t->ctx->device : 0);
-    if (t->offsets) cudaFree(t->offsets);
-    if (t->sub_offsets) cudaFree(t->sub_offsets);
-    if (t->entry_w) cudaFree(t->entry_w);
-    if (t->entry_am) cudaFree(t->entry_am);
-    if (t->entry_idx) cudaFree(t->entry_idx);
-    if (t->entry_alpha) cudaFree(t->entry_alpha);
-    if (t->merged_w) cudaFree(t->merged_w);
-    if (t->msub_offsets) cudaFree(t->msub_offsets);
+    // the arrays come from the device's stream-ordered pool (k2_build, load, clone): they go back to it, so that the
+    // next build re-uses the memory instead of asking the driver for gigabytes again
+    void *arrays[8] = {t->offsets, t->sub_offsets, t->entry_w, t->entry_am, t->entry_idx, t->entry_alpha, t->merged_w, t->msub_offsets};
+    for (void *p : arrays) {
+        if (!p) continue;
+        if (t->ctx) cudaFreeAsync(p, t->ctx->stream);
+        else cudaFree(p);
+    }
     delete t;
 }
 

@@ -590,8 +590,8 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
     cudaEventRecord(ctx->ev[2], ctx->stream);
 
     // ---- CSR ------------------------------------------------------------------------------------
-    K2_CUDA(cudaMalloc(&t->offsets, ((size_t)total_keys + 1) * sizeof(uint32_t)));
-    if (cells_log2) K2_CUDA(cudaMalloc(&t->sub_offsets, ((size_t)total_sub + 1) * sizeof(uint32_t)));
+    K2_CUDA(cudaMallocAsync(&t->offsets, ((size_t)total_keys + 1) * sizeof(uint32_t), ctx->stream));
+    if (cells_log2) K2_CUDA(cudaMallocAsync(&t->sub_offsets, ((size_t)total_sub + 1) * sizeof(uint32_t), ctx->stream));
     {
         auto launch = [&]() -> int {
             PPF_LAUNCH(ctx, csr_offsets_kernel, (total_keys + 1 + 255) / 256, 256, 0, keys[s], (uint32_t)count,
@@ -620,12 +620,12 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         info.max_dist = bits < 0 ? -1.0f : mx;  // PCL: max_dist_ starts at -1
     }
     // the voting kernel reads whole batches: ENTRY_PAD readable (zero) words follow the last entry
-    K2_CUDA(cudaMalloc(&t->entry_w, ((size_t)n_entries + ENTRY_PAD) * sizeof(uint32_t)));
-    K2_CUDA(cudaMalloc(&t->entry_am, ((size_t)n_entries + ENTRY_PAD) * sizeof(uint32_t)));
+    K2_CUDA(cudaMallocAsync(&t->entry_w, ((size_t)n_entries + ENTRY_PAD) * sizeof(uint32_t), ctx->stream));
+    K2_CUDA(cudaMallocAsync(&t->entry_am, ((size_t)n_entries + ENTRY_PAD) * sizeof(uint32_t), ctx->stream));
     K2_CUDA(cudaMemsetAsync(t->entry_w + n_entries, 0, ENTRY_PAD * sizeof(uint32_t), ctx->stream));
     K2_CUDA(cudaMemsetAsync(t->entry_am + n_entries, 0, ENTRY_PAD * sizeof(uint32_t), ctx->stream));
-    K2_CUDA(cudaMalloc(&t->entry_idx, std::max<size_t>(1, n_entries) * sizeof(uint32_t)));
-    K2_CUDA(cudaMalloc(&t->entry_alpha, std::max<size_t>(1, n_entries) * sizeof(float)));
+    K2_CUDA(cudaMallocAsync(&t->entry_idx, std::max<size_t>(1, n_entries) * sizeof(uint32_t), ctx->stream));
+    K2_CUDA(cudaMallocAsync(&t->entry_alpha, std::max<size_t>(1, n_entries) * sizeof(float), ctx->stream));
     K2_CUDA(cudaMallocAsync(&d_cnt, sizeof(unsigned long long), ctx->stream));
     K2_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
     {
@@ -659,9 +659,9 @@ int k2_build(b200ppf_ctx *ctx, const b200ppf_features *feat, const b200ppf_cloud
         if (merge_bits) {
             K2_TRY(flag_scan_u32(ctx, head, n_entries, rank, &n_merged));
         }
-        K2_CUDA(cudaMalloc(&t->merged_w, ((size_t)n_merged + ENTRY_PAD) * sizeof(uint32_t)));
+        K2_CUDA(cudaMallocAsync(&t->merged_w, ((size_t)n_merged + ENTRY_PAD) * sizeof(uint32_t), ctx->stream));
         K2_CUDA(cudaMemsetAsync(t->merged_w + n_merged, 0, ENTRY_PAD * sizeof(uint32_t), ctx->stream));
-        K2_CUDA(cudaMalloc(&t->msub_offsets, ((size_t)total_sub + 1) * sizeof(uint32_t)));
+        K2_CUDA(cudaMallocAsync(&t->msub_offsets, ((size_t)total_sub + 1) * sizeof(uint32_t), ctx->stream));
         {
             auto launch = [&]() -> int {
                 if (merge_bits) {

@@ -150,9 +150,23 @@ cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restr
     float a[12];
     rows_to_array(poses[k], a);
     bool blocked = false, member = false;
+    // A pose that has compared itself with UNDECIDED_TESTS earlier undecided poses without finding one within bounds gives
+    // up for this round (it stays undecided: always safe).  Before any leader exists, the poses of a crowded cell that
+    // resemble nobody would otherwise compare themselves with thousands of poses each.  The lowest-ranked undecided pose
+    // has no undecided pose before it, so it never gives up and every round decides at least one pose.
+    constexpr int UNDECIDED_TESTS = 48;
+    int tested = 0;
     for_each_earlier_within(
         poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state,
-        [&](uint32_t sj) { return sj == ST_LEADER || (sj == ST_UNDECIDED && !blocked); },
+        [&](uint32_t sj) {
+            if (sj == ST_LEADER) return true;
+            if (sj != ST_UNDECIDED || blocked) return false;
+            if (++tested > UNDECIDED_TESTS) {
+                blocked = true;
+                return false;
+            }
+            return true;
+        },
         [&](uint32_t j) {
             // decisions use final states only (LEADER / MEMBER never change), so a stale read costs a round, not correctness
             const uint32_t sj = state[j];
