@@ -104,3 +104,29 @@ def test_train_match_recovers_a_rigid_motion(oracle, bottle_5mm, angle, t):
     # threads do not change anything
     poses1, votes1, raw1, _ = det.match(scene, 1.0 / 5.0, 0.04, n_threads=1)
     assert np.array_equal(poses, poses1) and np.array_equal(votes, votes1) and np.array_equal(raw, raw1)
+
+
+def test_parity_hooks_agree_with_match(oracle, bottle_5mm):
+    """The hooks the device engine's tests use (bucket contents, one reference point's accumulator, match_S2B as inferred)
+    are consistent with match() itself: the peak of every sampled accumulator is the raw pose of that reference point."""
+    det = oracle.CvDetector(0.05, 0.05).train_model(bottle_5mm)
+    m = det.n_model
+    assert det.table_size >= m * m and det.table_size & (det.table_size - 1) == 0
+    total = 0
+    for b in range(0, det.table_size, max(1, det.table_size // 4096)):
+        nodes = det.bucket(b)
+        assert (np.diff(nodes.astype(np.int64)) > 0).all() and (nodes // m != nodes % m).all()
+        total += len(nodes)
+    assert total > 0
+    scene = bottle_5mm[::2].copy()
+    poses, votes, raw, ncl = det.match(scene, 1.0 / 5.0, 0.05)
+    for r in (0, len(raw) // 2, len(raw) - 1):
+        acc = det.accumulator(scene, r * 5, 0.05)
+        flat = int(np.argmax(acc))
+        assert raw[r, 0] == acc.reshape(-1)[flat] and (int(raw[r, 1]), int(raw[r, 2])) == divmod(flat, acc.shape[1])
+    # match_S2B with a thin "edge" cloud: fewer pairs per reference point, never more votes than the surface pairing casts
+    edge = scene[::7].copy()
+    p2, v2, raw2, ncl2 = det.match_s2b(scene, edge, 1.0 / 5.0, 0.05)
+    assert len(raw2) == len(raw) and raw2[:, 0].sum() < raw[:, 0].sum() and ncl2 >= 1
+    acc = det.accumulator(scene, 10, 0.05, edge=edge)
+    assert raw2[2, 0] == acc.max()

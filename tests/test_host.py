@@ -19,7 +19,7 @@ from conftest import ANGLE_STEP, ROOT
 def _header_functions():
     text = open(os.path.join(ROOT, "include", "b200ppf.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200ppf_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(b200(?:ppf|cv)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -295,3 +295,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_bench_arms_print_the_same_config_and_a_fixed_cpu_sample():
+    """The reference arm and the B200 arm describe the workload identically (the driver compares `config`), the CPU sample is
+    a fixed list — same reference points on every box, every --gpus — and the thread count ignores OMP_NUM_THREADS."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from yolo_ppf_pose_estimation_b200 import workloads
+    wl = workloads.load("c3s")
+    a, b = bench.workload_config(wl, 1), bench.workload_config(wl, 1)
+    assert a == b and set(a) >= {"workload", "n_model", "n_scene", "n_ref", "l2"}
+    s1, s2 = bench.sample_list(wl), bench.sample_list(wl)
+    assert s1 == s2 and len(s1) == len(set(s1)) == 64 and max(s1) < wl.scene.shape[0]
+    assert sorted(s1[:8]) == sorted(s1[:8]) and max(np.diff(sorted(s1[:8]))) < wl.scene.shape[0] // 4   # a prefix is spread out
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        assert bench.host_threads() == len(os.sched_getaffinity(0))
+    finally:
+        del os.environ["OMP_NUM_THREADS"]
+    assert 1 <= bench.refs_per_cpu_step(workloads.load("c1"), 8, 0) <= 64 and bench.refs_per_cpu_step(wl, 8, 5) == 5
