@@ -338,7 +338,7 @@ def run_b200(args, wl):
                     collect[k] = collect.get(k, 0) + v
                 collect["vote_ms"] = collect.get("vote_ms", 0.0) + ctx.timings()["vote_ms"]
             if p2p:
-                res = group.cluster(n_ref, wl.pos_thr, wl.rot_thr)
+                res = group.cluster(dm, table, ds, wl.ref_rate, wl.pos_thr, wl.rot_thr)
             elif world > 1 and not lib_mode:
                 with torch.cuda.stream(stream):
                     ordered = sharding.all_gather_hypotheses(local_buf, n_ref, world, dist)
@@ -442,9 +442,11 @@ def run_b200(args, wl):
             "run": {"table_entries": int(info.n_entries), "accumulator_slices": int(info.n_slices),
                     "alpha_columns": int(info.n_alpha), "phase_cells": int(info.phase_cells),
                     "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode
-                                 else (f"reference points interleaved over {world} rank(s), table + scene replicated, 64 B "
-                                       f"hypotheses exchanged by " + ("b200ppf_group: the vote epilogue's NVLink peer stores + device-side flags"
-                                                                      if p2p else "an NCCL all-gather")) if world > 1 else "single GPU")},
+                                 else ((f"b200ppf_group: {world} ranks draw (reference point, slice) tasks from one queue over NVLink, "
+                                        f"table + scene replicated, 8-byte peaks merged into every rank's array by system-scope atomicMax, "
+                                        f"device-side flags" if p2p else
+                                        f"reference points interleaved over {world} rank(s), table + scene replicated, 64 B hypotheses "
+                                        f"exchanged by an NCCL all-gather")) if world > 1 else "single GPU")},
             "ms_per_pose": ms_per_step / len(library),
             "votes_per_sec": nvotes / (ms_per_step * 1e-3),
             "pairs_examined_per_sec": examined / (ms_per_step * 1e-3),

@@ -211,11 +211,12 @@ int b200ppf_vote_scatter_device(b200ppf_ctx *ctx, const b200ppf_cloud *model, co
                                 size_t ref_count, b200ppf_hypothesis *const *peer_buffers, int n_peers,
                                 size_t slot_first, size_t slot_step);
 /* ---- several GPUs behind the ABI --------------------------------------------------------------------------------
- * PPFRegistration::align with the scene reference points interleaved over G GPUs.  Every rank votes on
- * its share against its own replica of the table and the scene; the hypothesis records are exchanged by the vote
- * epilogue itself (peer stores into every rank's buffer over NVLink) and a per-step flag, raised by each rank's last
- * block and awaited by a one-thread kernel on every rank's stream, separates voting from clustering: no host
- * synchronisation and no collective call on the path.
+ * PPFRegistration::align with the scene reference points spread over G GPUs.  Every rank holds a replica
+ * of the table and the scene; the persistent CTAs of all ranks draw (reference point, slice) tasks from ONE queue — a
+ * counter in rank 0's memory, system-scope atomics over NVLink — so the ranks finish together whatever the scene's cost
+ * distribution; every task's 8-byte peak is merged into every rank's peak array by a system-scope atomicMax, and a
+ * per-step flag, raised by each rank's last CTA and awaited by a one-thread kernel on every rank's stream, separates
+ * voting from pose assembly and clustering: no host synchronisation and no collective call on the path.
  *   b200ppf_group_*   one process per GPU (torchrun / MPI): create -> exchange the B200PPF_GROUP_HANDLE_BYTES blobs of
  *                     all ranks by any means (rank order) -> connect -> register per frame.  Every rank returns the
  *                     same poses (clustering is deterministic and runs on every rank's own complete copy).
@@ -228,10 +229,12 @@ int b200ppf_group_create(b200ppf_ctx *ctx, int rank, int world, size_t n_records
                          unsigned char handles[B200PPF_GROUP_HANDLE_BYTES]);
 int b200ppf_group_connect(b200ppf_group *group, const unsigned char *all_handles /* world * B200PPF_GROUP_HANDLE_BYTES */);
 void b200ppf_group_destroy(b200ppf_group *group);
-/* vote: asynchronous; cluster: waits on the device for all ranks' records, returns this rank's poses */
+/* vote: asynchronous; cluster: waits on the device for all ranks' flags, assembles the poses of all reference points
+ * from this rank's complete peak array, returns this rank's clustered poses (model / table / scene as given to vote) */
 int b200ppf_group_vote(b200ppf_group *group, const b200ppf_cloud *model, const b200ppf_table *table,
                        const b200ppf_cloud *scene, size_t ref_rate);
-int b200ppf_group_cluster(b200ppf_group *group, size_t n_ref, float pos_thr, float rot_thr, float *final16,
+int b200ppf_group_cluster(b200ppf_group *group, const b200ppf_cloud *model, const b200ppf_table *table,
+                          const b200ppf_cloud *scene, size_t ref_rate, float pos_thr, float rot_thr, float *final16,
                           float *poses16, uint32_t *votes, size_t *n_out);
 int b200ppf_group_register(b200ppf_group *group, const b200ppf_cloud *model, const b200ppf_table *table,
                            const b200ppf_cloud *scene, size_t ref_rate, float pos_thr, float rot_thr, float *final16,

@@ -115,7 +115,7 @@ SYMBOLS = {
     "b200ppf_group_connect": (_i, [_vp, _vp]),
     "b200ppf_group_destroy": (None, [_vp]),
     "b200ppf_group_vote": (_i, [_vp, _vp, _vp, _vp, _sz]),
-    "b200ppf_group_cluster": (_i, [_vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
+    "b200ppf_group_cluster": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_group_register": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _vp, _vp, _vp, C.POINTER(_sz)]),
     "b200ppf_group_records": (_vp, [_vp]),
     "b200ppf_multi_create": (_i, [_vp, _i, C.POINTER(_vp)]),
@@ -629,18 +629,18 @@ class Group:
     def vote(self, model, table, scene, ref_rate=1):
         self.ctx.check(lib().b200ppf_group_vote(self._h, model._h, table._h, scene._h, ref_rate))
 
-    def cluster(self, n_ref, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
+    def cluster(self, model, table, scene, ref_rate=1, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
         final = np.zeros(16, np.float32)
         poses = np.zeros((3, 16), np.float32)
         votes = np.zeros(3, np.uint32)
         k = C.c_size_t(0)
-        self.ctx.check(lib().b200ppf_group_cluster(self._h, n_ref, np.float32(pos_thr), np.float32(rot_thr), _p(final),
-                                                   _p(poses), _p(votes), C.byref(k)))
+        self.ctx.check(lib().b200ppf_group_cluster(self._h, model._h, table._h, scene._h, ref_rate, np.float32(pos_thr),
+                                                   np.float32(rot_thr), _p(final), _p(poses), _p(votes), C.byref(k)))
         return poses[:k.value].reshape(-1, 4, 4), votes[:k.value]
 
     def register(self, model, table, scene, ref_rate=1, pos_thr=0.01, rot_thr=20.0 / 180.0 * np.pi):
         self.vote(model, table, scene, ref_rate)
-        return self.cluster((scene.size + ref_rate - 1) // ref_rate, pos_thr, rot_thr)
+        return self.cluster(model, table, scene, ref_rate, pos_thr, rot_thr)
 
     def records(self, n):
         """the complete hypothesis set of the last step (synchronises)"""

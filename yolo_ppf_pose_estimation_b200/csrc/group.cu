@@ -1,11 +1,15 @@
 // group.cu — PPFRegistration::align over several GPUs behind the C ABI.
 //
-// Scene reference points are independent units: rank g of G votes on reference slots g, g + G, ...
-// against its own replica of the model table and the scene; the ONE exchange on the path — the 64-byte hypothesis
-// records that clustering needs in full — is fused into the vote epilogue: the pose kernel stores every record
-// straight into slot (g + k * G) of every rank's buffer (NVLink peer stores), its last block then raises this rank's
-// flag in every rank's flag array, and a one-thread kernel on each rank's stream waits for all G flags before that
-// rank clusters.  No host synchronisation, no NCCL call and no staging copy sit between voting and clustering.
+// Scene reference points are independent units; every rank holds its own replica of the model table
+// and the scene.  The ranks share ONE work queue: a counter in rank 0's memory from which the persistent CTAs of every
+// GPU draw (reference point, accumulator slice) tasks with system-scope atomics over NVLink — whichever GPU is free
+// takes the next task, so the ranks finish together whatever the cost distribution of the scene (a static interleaving
+// left 6 % imbalance at 8 GPUs).  The ONE exchange on the path is fused into the vote kernel: a task's peak — 8 bytes,
+// (votes, ~flat index) — is merged into EVERY rank's peak array by a system-scope 64-bit atomicMax (the same merge that
+// combines the slices of one reference point on one GPU).  When a rank's CTAs find the queue empty, its last CTA raises
+// the rank's flag in every rank's flag array; a one-thread kernel on each rank's stream waits for all G flags, then the
+// rank assembles all poses from its complete peak array and clusters.  No host synchronisation, no NCCL call, no
+// staging copy between voting and clustering.
 //
 // Two ways to form a group, same code underneath:
 //   * one process per GPU (torchrun, MPI): b200ppf_group_create -> exchange the 192-byte handle blobs by any means
@@ -13,7 +17,8 @@
 //   * one process driving several GPUs: b200ppf_multi_create makes G contexts + groups and connects them with
 //     plain peer pointers; b200ppf_multi_register runs the G ranks from one host thread (every call is asynchronous
 //     until the final read-back of rank 0's poses).
-// Two buffer sets alternate between steps, so a rank may be one step ahead of a peer that still clusters.
+// Two sets of peak arrays, flags and queue counters alternate between steps, so a rank may be one step ahead of a peer that
+// still clusters; a set is cleared by its owner one step before it is used (see b200ppf_group_vote).
 #include <algorithm>
 #include <cstring>
 #include <new>
@@ -25,9 +30,11 @@ struct b200ppf_group {
     b200ppf_ctx *ctx = nullptr;
     int rank = 0, world = 1;
     size_t n_records = 0;                      // capacity of every buffer (reference slots)
-    b200ppf_hypothesis *own[2] = {nullptr, nullptr};
-    uint32_t *own_flags = nullptr;             // [2][MAX_PEERS] step counters written by the peers, + done counter at [32]
-    b200ppf_hypothesis *peer[2][b200ppf::MAX_PEERS] = {};
+    unsigned long long *own[2] = {nullptr, nullptr};  // peak arrays, written by every rank's vote kernel
+    uint32_t *own_flags = nullptr;             // [2][MAX_PEERS] step counters written by the peers, done counter at [32],
+                                               // queue counters at [40], [41] (rank 0's are the ones in use)
+    b200ppf_hypothesis *records = nullptr;     // this rank's hypothesis records of the last step (local)
+    unsigned long long *peer[2][b200ppf::MAX_PEERS] = {};
     uint32_t *peer_flags[b200ppf::MAX_PEERS] = {};
     bool opened[b200ppf::MAX_PEERS] = {};      // mapped through an IPC handle (to be closed), not a local pointer
     bool connected = false;
@@ -58,7 +65,8 @@ struct DevGuard {
     }
 };
 
-constexpr size_t FLAG_WORDS = 2 * MAX_PEERS + 8;  // two flag sets + the done counter
+constexpr size_t FLAG_WORDS = 2 * MAX_PEERS + 16;  // two flag sets, the done counter, two queue counters
+constexpr size_t DONE_WORD = 2 * MAX_PEERS, QUEUE_WORD = 2 * MAX_PEERS + 8;
 
 int group_alloc(b200ppf_ctx *ctx, int rank, int world, size_t n_records, b200ppf_group **out) {
     if (!ctx || !out) return fail_msg(ctx, B200PPF_ERR_INVALID, "group: null argument");
@@ -73,9 +81,10 @@ int group_alloc(b200ppf_ctx *ctx, int rank, int world, size_t n_records, b200ppf
     DevGuard guard(ctx->device);
     cudaError_t e = cudaSuccess;
     for (int s = 0; s < 2 && e == cudaSuccess; ++s) {  // cudaMalloc: exportable through CUDA IPC
-        e = cudaMalloc(&g->own[s], g->n_records * sizeof(b200ppf_hypothesis));
-        if (e == cudaSuccess) e = cudaMemset(g->own[s], 0, g->n_records * sizeof(b200ppf_hypothesis));
+        e = cudaMalloc(&g->own[s], g->n_records * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(g->own[s], 0, g->n_records * sizeof(unsigned long long));
     }
+    if (e == cudaSuccess) e = cudaMalloc(&g->records, g->n_records * sizeof(b200ppf_hypothesis));
     if (e == cudaSuccess) e = cudaMalloc(&g->own_flags, FLAG_WORDS * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(g->own_flags, 0, FLAG_WORDS * sizeof(uint32_t));
     if (e != cudaSuccess) {
@@ -130,8 +139,8 @@ int b200ppf_group_connect(b200ppf_group *g, const unsigned char *all_handles) {
                 return fail_msg(g->ctx, B200PPF_ERR_CUDA, "group connect: cudaIpcOpenMemHandle failed (ranks must share one node with peer access)");
             }
         }
-        g->peer[0][r] = static_cast<b200ppf_hypothesis *>(p[0]);
-        g->peer[1][r] = static_cast<b200ppf_hypothesis *>(p[1]);
+        g->peer[0][r] = static_cast<unsigned long long *>(p[0]);
+        g->peer[1][r] = static_cast<unsigned long long *>(p[1]);
         g->peer_flags[r] = static_cast<uint32_t *>(p[2]);
         g->opened[r] = true;
     }
@@ -152,13 +161,15 @@ void b200ppf_group_destroy(b200ppf_group *g) {
     for (int s = 0; s < 2; ++s)
         if (g->own[s]) cudaFree(g->own[s]);
     if (g->own_flags) cudaFree(g->own_flags);
+    if (g->records) cudaFree(g->records);
     delete g;
 }
 
-/* the asynchronous half: this rank's shard of the vote, its records stored into every rank's buffer, its flag raised */
+/* the asynchronous half: this rank's persistent CTAs on the shared queue; peaks merged into every rank's array; flag raised */
 int b200ppf_group_vote(b200ppf_group *g, const b200ppf_cloud *model, const b200ppf_table *table, const b200ppf_cloud *scene,
                        size_t ref_rate) {
-    if (!g || !scene) return fail_msg(g ? g->ctx : nullptr, B200PPF_ERR_INVALID, "group vote: null argument");
+    if (!g || !scene || !table) return fail_msg(g ? g->ctx : nullptr, B200PPF_ERR_INVALID, "group vote: null argument");
+    (void)model;
     b200ppf_ctx *ctx = g->ctx;
     if (!g->connected) return fail_msg(ctx, B200PPF_ERR_STATE, "group vote: the group is not connected yet");
     if (ref_rate == 0) ref_rate = 1;
@@ -168,27 +179,42 @@ int b200ppf_group_vote(b200ppf_group *g, const b200ppf_cloud *model, const b200p
     DevGuard guard(ctx->device);
     const int set = (int)(g->step & 1u);
     g->step += 1;
-    const size_t count = (size_t)g->rank < n_ref ? (n_ref - g->rank + g->world - 1) / g->world : 0;
-    VoteSignal sig;
-    for (int r = 0; r < MAX_PEERS; ++r) sig.flags[r] = r < g->world ? g->peer_flags[r] + set * MAX_PEERS : nullptr;
-    sig.slot = (uint32_t)g->rank;
-    sig.value = g->step;
-    sig.done_counter = g->own_flags + 2 * MAX_PEERS;
-    return k3_vote(ctx, model, table, scene, (size_t)g->rank * ref_rate, (size_t)g->world * ref_rate, count, g->peer[set], g->world,
-                   (size_t)g->rank, (size_t)g->world, &sig);
+    // Clear the OTHER set for the next step now: its last users finished before they raised the flags this rank waited for
+    // at the end of the previous step, and its next users cannot start before this rank raises the flag of THIS step, which
+    // the kernel launched below does when it ends (stream order).  The very first step finds both sets cleared by create.
+    PPF_CUDA(ctx, cudaMemsetAsync(g->own[1 - set], 0, g->n_records * sizeof(unsigned long long), ctx->stream));
+    PPF_CUDA(ctx, cudaMemsetAsync(g->own_flags + QUEUE_WORD + (1 - set), 0, sizeof(uint32_t), ctx->stream));
+    VoteQueue q;
+    q.counter = g->peer_flags[0] + QUEUE_WORD + set;  // rank 0 owns the queue
+    q.n_peers = g->world;
+    for (int r = 0; r < MAX_PEERS; ++r) {
+        q.peer_peaks[r] = r < g->world ? g->peer[set][r] : nullptr;
+        q.flags[r] = r < g->world ? g->peer_flags[r] + set * MAX_PEERS : nullptr;
+    }
+    q.slot = (uint32_t)g->rank;
+    q.value = g->step;
+    q.done_counter = g->own_flags + DONE_WORD;
+    return k3_vote_shared(ctx, table, scene, ref_rate, n_ref, &q);
 }
 
-/* the second half: wait (on the device) for every rank's records, then cluster this rank's complete copy */
-int b200ppf_group_cluster(b200ppf_group *g, size_t n_ref, float pos_thr, float rot_thr, float *final16, float *poses16,
-                          uint32_t *votes, size_t *n_out) {
-    if (!g || !poses16 || !votes || !n_out) return fail_msg(g ? g->ctx : nullptr, B200PPF_ERR_INVALID, "group cluster: null argument");
+/* the second half: wait (on the device) for every rank's flag, assemble all poses from this rank's complete peak array,
+ * cluster */
+int b200ppf_group_cluster(b200ppf_group *g, const b200ppf_cloud *model, const b200ppf_table *table, const b200ppf_cloud *scene,
+                          size_t ref_rate, float pos_thr, float rot_thr, float *final16, float *poses16, uint32_t *votes,
+                          size_t *n_out) {
+    if (!g || !poses16 || !votes || !n_out || !model || !table || !scene)
+        return fail_msg(g ? g->ctx : nullptr, B200PPF_ERR_INVALID, "group cluster: null argument");
     b200ppf_ctx *ctx = g->ctx;
     if (g->step == 0) return fail_msg(ctx, B200PPF_ERR_STATE, "group cluster: no vote has been issued");
+    if (ref_rate == 0) ref_rate = 1;
+    const size_t n_ref = (scene->n + ref_rate - 1) / ref_rate;
     DevGuard guard(ctx->device);
     const int set = (int)((g->step - 1) & 1u);
     int rc = k3_group_wait(ctx, g->own_flags + set * MAX_PEERS, g->world, g->step);
     if (rc) return rc;
-    rc = k4_cluster(ctx, g->own[set], n_ref, pos_thr, rot_thr, poses16, votes, n_out);
+    rc = k3_poses(ctx, model, table, scene, ref_rate, n_ref, g->own[set], g->records);
+    if (rc) return rc;
+    rc = k4_cluster(ctx, g->records, n_ref, pos_thr, rot_thr, poses16, votes, n_out);
     if (rc) return rc;
     if (*n_out && final16) memcpy(final16, poses16, 16 * sizeof(float));
     return B200PPF_OK;
@@ -199,13 +225,10 @@ int b200ppf_group_register(b200ppf_group *g, const b200ppf_cloud *model, const b
                            size_t *n_out) {
     int rc = b200ppf_group_vote(g, model, table, scene, ref_rate);
     if (rc) return rc;
-    if (ref_rate == 0) ref_rate = 1;
-    return b200ppf_group_cluster(g, (scene->n + ref_rate - 1) / ref_rate, pos_thr, rot_thr, final16, poses16, votes, n_out);
+    return b200ppf_group_cluster(g, model, table, scene, ref_rate, pos_thr, rot_thr, final16, poses16, votes, n_out);
 }
 
-const b200ppf_hypothesis *b200ppf_group_records(const b200ppf_group *g) {
-    return g && g->step ? g->own[(g->step - 1) & 1u] : nullptr;
-}
+const b200ppf_hypothesis *b200ppf_group_records(const b200ppf_group *g) { return g && g->step ? g->records : nullptr; }
 
 /* ---- one process, several GPUs ------------------------------------------------------------------------------------ */
 
@@ -373,7 +396,8 @@ int b200ppf_multi_register(b200ppf_multi *m, size_t ref_rate, float pos_thr, flo
         int rc = b200ppf_group_vote(m->group[g], m->model[g], m->table[g], m->scene[g], ref_rate);
         if (rc) return multi_fail(m, g, rc);
     }
-    int rc = b200ppf_group_cluster(m->group[0], n_ref, pos_thr, rot_thr, final16, poses16, votes, n_out);
+    int rc = b200ppf_group_cluster(m->group[0], m->model[0], m->table[0], m->scene[0], ref_rate, pos_thr, rot_thr, final16, poses16,
+                                   votes, n_out);
     if (rc) return multi_fail(m, 0, rc);
     // the other devices only have to drain before their buffers are reused two steps from now; keep the steps aligned
     for (int g = 1; g < G; ++g) {

@@ -98,6 +98,17 @@ struct VoteArgs {
     unsigned long long *peaks;
     unsigned long long *stats;
     uint32_t *acc_dump;  // debug: full accumulator of reference 0 (n_model * n_alpha)
+    // Several GPUs sharing ONE work queue (b200ppf_group): persistent CTAs draw (reference, slice) tasks from a counter in
+    // rank 0's memory with system-scope atomics over NVLink — whichever GPU is free takes the next task, so the ranks
+    // finish together whatever the scene's cost distribution — and merge each task's peak into EVERY rank's peak array
+    // with a system-scope 64-bit atomicMax.  When its queue is exhausted, the last CTA of a rank raises that rank's flag
+    // in every rank's flag array.
+    uint32_t *queue;  // nullptr: the grid is (reference, slice) and peaks are local
+    unsigned long long *peer_peaks[MAX_PEERS];
+    uint32_t *peer_flags[MAX_PEERS];
+    int n_peers;
+    uint32_t signal_slot, signal_value;
+    uint32_t *done_counter;
 };
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
@@ -153,9 +164,9 @@ __device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_add
     else red_shared_inc(acc_addr + row_bytes + unit * bin);
 }
 
+// one (reference point, accumulator slice) task; ref_i = reference slot of this launch
 template <int MODE, bool SEAM, bool BULK, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : B200PPF_VOTE_MINBLOCKS)
-ppf_vote_kernel(const VoteArgs a) {
+__device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_i, const uint32_t slice) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Frame s_sg;
     __shared__ uint32_t s_ncand, s_nitems, s_next, s_scratch;
@@ -165,7 +176,6 @@ ppf_vote_kernel(const VoteArgs a) {
     __shared__ unsigned long long s_stat[4];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t slice = blockIdx.y;
     const uint32_t slice_base = slice * a.kp.slice_rows;
     const uint32_t rows = min(a.kp.slice_rows, a.n_model - slice_base);
     const uint32_t pitch = a.kp.row_pitch;               // words between two alpha columns (multiple of 32)
@@ -179,7 +189,7 @@ ppf_vote_kernel(const VoteArgs a) {
     const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
     const uint32_t scratch_addr = (uint32_t)__cvta_generic_to_shared(&s_scratch);
 
-    const uint32_t s_r = a.ref_first + blockIdx.x * a.ref_step;
+    const uint32_t s_r = a.ref_first + ref_i * a.ref_step;
     const float4 pr4 = a.pos[s_r], nr4 = a.nrm[s_r];
     const V3 p_r = v3_of(pr4), n_r = v3_of(nr4);
     if (tid == 0) {
@@ -528,13 +538,52 @@ ppf_vote_kernel(const VoteArgs a) {
     if (tid == 0) {
 #pragma unroll
         for (int w = 1; w < (THREADS / 32); ++w) best = max(best, s_best[w]);
-        if (best) atomicMax(a.peaks + blockIdx.x, best);
+        if (best) {
+            if (a.queue) {
+                for (int g = 0; g < a.n_peers; ++g) atomicMax_system(a.peer_peaks[g] + ref_i, best);
+            } else {
+                atomicMax(a.peaks + ref_i, best);
+            }
+        }
         if (slice == 0) {
             atomicAdd(a.stats + 0, s_stat[0]);
             atomicAdd(a.stats + 1, s_stat[1]);
         }
         atomicAdd(a.stats + 2, s_stat[2]);
         atomicAdd(a.stats + 3, s_stat[3]);
+    }
+}
+
+template <int MODE, bool SEAM, bool BULK, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : B200PPF_VOTE_MINBLOCKS)
+ppf_vote_kernel(const VoteArgs a) {
+    if (!a.queue) {  // one CTA per (reference point, slice)
+        vote_task<MODE, SEAM, BULK, THREADS>(a, blockIdx.x, blockIdx.y);
+        return;
+    }
+    // persistent CTAs on a queue shared by all ranks; the next task is drawn while the current one runs
+    __shared__ uint32_t s_task;
+    const uint32_t n_slices = a.kp.n_slices, total = a.ref_count * n_slices;
+    uint32_t next = 0;
+    if (threadIdx.x == 0) next = atomicAdd_system(a.queue, 1u);
+    for (;;) {
+        if (threadIdx.x == 0) s_task = next;
+        __syncthreads();
+        const uint32_t task = s_task;
+        if (task >= total) break;
+        if (threadIdx.x == 0) next = atomicAdd_system(a.queue, 1u);
+        vote_task<MODE, SEAM, BULK, THREADS>(a, task / n_slices, task % n_slices);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && a.done_counter) {
+        __threadfence_system();  // this CTA's peaks are visible everywhere before it counts as done
+        if (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) {
+            *a.done_counter = 0;
+            __threadfence_system();
+            for (int g = 0; g < a.n_peers; ++g)
+                *reinterpret_cast<volatile uint32_t *>(a.peer_flags[g] + a.signal_slot) = a.signal_value;
+            __threadfence_system();
+        }
     }
 }
 
@@ -666,7 +715,7 @@ float radius_sq_bound(float r) {
 }
 
 int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_first,
-                size_t ref_step, size_t ref_count, uint32_t *acc_dump) {
+                size_t ref_step, size_t ref_count, uint32_t *acc_dump, const VoteQueue *queue = nullptr) {
     const float radius = t->info.max_dist * 0.5f;
     struct GridOwner {  // the grid goes back to the pool on every return path, the launch macros' error returns included
         b200ppf_ctx *ctx;
@@ -704,8 +753,29 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     a.peaks = ctx->d_peaks;
     a.stats = ctx->d_stats;
     a.acc_dump = acc_dump;
+    a.queue = nullptr;
+    a.n_peers = 0;
+    a.signal_slot = a.signal_value = 0;
+    a.done_counter = nullptr;
+    for (int g = 0; g < MAX_PEERS; ++g) {
+        a.peer_peaks[g] = nullptr;
+        a.peer_flags[g] = nullptr;
+    }
     const size_t smem = vote_smem_bytes(t);
     dim3 grid_dim((unsigned)ref_count, t->info.n_slices);
+    if (queue) {
+        a.queue = queue->counter;
+        a.n_peers = queue->n_peers;
+        a.signal_slot = queue->slot;
+        a.signal_value = queue->value;
+        a.done_counter = queue->done_counter;
+        for (int g = 0; g < queue->n_peers; ++g) {
+            a.peer_peaks[g] = queue->peer_peaks[g];
+            a.peer_flags[g] = queue->flags[g];
+        }
+        // persistent: as many CTAs as the device holds at once
+        grid_dim = dim3((unsigned)(ctx->sm_count * (vote_threads(t) == VOTE_THREADS_SMALL ? B200PPF_VOTE_MINBLOCKS : 1)), 1);
+    }
     cudaEventRecord(ctx->ev_vote[1], ctx->stream);  // grid build ends, voting starts
 #define LAUNCH_VOTE_T(M, S, B, T)                                                                                  \
     do {                                                                                                            \
@@ -884,6 +954,43 @@ int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t
                model->pos, model->nrm, (uint32_t)ref_first, (uint32_t)ref_step, (uint32_t)ref_count, ctx->d_peaks, bp, out);
     cudaEventRecord(ctx->ev_vote[3], ctx->stream);
     ctx->vote_timed = true;
+    return B200PPF_OK;
+}
+
+// group mode, first half: this rank's persistent CTAs on the shared queue over ALL reference points of the scene
+int k3_vote_shared(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_rate, size_t n_ref,
+                   const VoteQueue *queue) {
+    int rc = check_vote_inputs(ctx, t, scene, 0, ref_rate, n_ref);
+    if (rc) return rc;
+    if (!ctx->d_stats) PPF_CUDA(ctx, cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)));
+    PPF_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    cudaEventRecord(ctx->ev_vote[0], ctx->stream);
+    rc = launch_vote(ctx, t, scene, 0, ref_rate, n_ref, nullptr, queue);  // records ev_vote[1], [2]
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev_vote[3], ctx->stream);
+    ctx->vote_timed = true;
+    return B200PPF_OK;
+}
+
+// group mode, second half: the poses of all reference points from the complete peak array
+int k3_poses(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_rate,
+             size_t n_ref, const unsigned long long *peaks, b200ppf_hypothesis *out_records) {
+    if (!model || model->n != t->info.n_model)
+        return fail_msg(ctx, B200PPF_ERR_STATE, "vote: model cloud does not match the table (setInputSource vs setSearchMethod)");
+    PeerTargets out;
+    for (int g = 0; g < MAX_PEERS; ++g) {
+        out.base[g] = g == 0 ? out_records : nullptr;
+        out.flags[g] = nullptr;
+    }
+    out.n = 1;
+    out.slot_first = 0;
+    out.slot_step = 1;
+    out.signal_slot = out.signal_value = 0;
+    out.done_counter = nullptr;
+    BinParams bp = t->bp;
+    bp.mode = ctx->alpha_mode;
+    PPF_LAUNCH(ctx, ppf_peak_pose_kernel, (unsigned)((n_ref + 127) / 128), 128, 0, scene->pos, scene->nrm, model->pos, model->nrm, 0u,
+               (uint32_t)ref_rate, (uint32_t)n_ref, peaks, bp, out);
     return B200PPF_OK;
 }
 

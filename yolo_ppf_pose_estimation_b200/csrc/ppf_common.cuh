@@ -149,6 +149,19 @@ int k3_vote(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t
             size_t ref_first, size_t ref_step, size_t ref_count, b200ppf_hypothesis *const *targets, int n_targets,
             size_t slot_first, size_t slot_step, const VoteSignal *signal = nullptr);
 int k3_group_wait(b200ppf_ctx *ctx, const uint32_t *flags, int world, uint32_t value);
+// one work queue shared by the ranks of a group (k3_vote.cu): counter in rank 0's memory, peaks merged into every rank's array
+struct VoteQueue {
+    uint32_t *counter;
+    unsigned long long *peer_peaks[MAX_PEERS];
+    uint32_t *flags[MAX_PEERS];
+    int n_peers;
+    uint32_t slot, value;
+    uint32_t *done_counter;
+};
+int k3_vote_shared(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_rate, size_t n_ref,
+                   const VoteQueue *queue);
+int k3_poses(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_table *t, const b200ppf_cloud *scene, size_t ref_rate,
+             size_t n_ref, const unsigned long long *peaks, b200ppf_hypothesis *out_records);
 int k3_debug_pairs(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
                    uint8_t *in_radius, int32_t *d4, float *alpha_s);
 int k3_debug_accumulator(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *scene, size_t s_r,
