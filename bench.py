@@ -279,6 +279,7 @@ def run_b200(args, wl):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")              # no "NCCL version ..." banner
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -372,16 +373,17 @@ def run_b200(args, wl):
         return total, vote_ms, launches, poses, votes
 
     # ---- resident-input measurement ---------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0 and os.environ.get("BENCH_CLOCKS", "1") != "0":
+        sampler.start()  # NVML is initialised here, outside the timed region; only the samples of the timed region are kept
     barrier()
     timed_steps(lambda: ds_resident, args.warmup)
     stats = {}
     align(ds_resident, collect=stats)
     for k in ("pairs_in_radius", "votes", "pairs_examined", "nonempty_lookups", "vote_ms"):
         stats.setdefault(k, 0)
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0 and os.environ.get("BENCH_CLOCKS", "1") != "0":
-        sampler.start()
+    sampler.samples.clear()
     total_ms, vote_ms, launches, poses, votes = timed_steps(lambda: ds_resident, args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

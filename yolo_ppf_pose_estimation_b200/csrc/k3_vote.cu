@@ -572,7 +572,8 @@ ppf_vote_kernel(const VoteArgs a) {
         const uint32_t task = s_task;
         if (task >= total) break;
         if (threadIdx.x == 0) next = atomicAdd_system(a.queue, 1u);
-        vote_task<MODE, SEAM, BULK, THREADS>(a, task / n_slices, task % n_slices);
+        // slice-major order, as the (reference, slice) grid runs: the CTAs in flight share one slice of the table in L2
+        vote_task<MODE, SEAM, BULK, THREADS>(a, task % a.ref_count, task / a.ref_count);
         __syncthreads();
     }
     if (threadIdx.x == 0 && a.done_counter) {

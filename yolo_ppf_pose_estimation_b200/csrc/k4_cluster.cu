@@ -127,7 +127,9 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
                 for (uint32_t s = b; s < e; ++s) {
                     const uint32_t j = cell_rank[s];
                     if (j >= k) break;  // ranks ascend inside a bucket (stable sort, order-preserving compaction)
-                    if (!keep(state[j])) continue;
+                    const int kk = keep(state[j]);  // 0: skip untested, 1: test, 2: stop the walk
+                    if (kk == 2) return;
+                    if (!kk) continue;
                     const PoseRows pj = poses[j];
                     const float ddx = a[3] - pj.r0.w, ddy = a[7] - pj.r1.w, ddz = a[11] - pj.r2.w;
                     if (!(sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz) < pos_thr)) continue;
@@ -144,7 +146,7 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
 __global__ void __launch_bounds__(128)
 cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
                      const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
-                     volatile uint32_t *state, uint32_t *__restrict__ undecided) {
+                     volatile uint32_t *state, uint32_t *__restrict__ undecided, uint32_t first_round) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n || state[k] != ST_UNDECIDED) return;
     float a[12];
@@ -158,14 +160,14 @@ cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restr
     int tested = 0;
     for_each_earlier_within(
         poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state,
-        [&](uint32_t sj) {
-            if (sj == ST_LEADER) return true;
-            if (sj != ST_UNDECIDED || blocked) return false;
+        [&](uint32_t sj) -> int {
+            if (sj == ST_LEADER) return 1;
+            if (sj != ST_UNDECIDED || blocked) return 0;
             if (++tested > UNDECIDED_TESTS) {
                 blocked = true;
-                return false;
+                return first_round ? 2 : 0;  // no leader exists in the first round: nothing further on can change the outcome
             }
-            return true;
+            return 1;
         },
         [&](uint32_t j) {
             // decisions use final states only (LEADER / MEMBER never change), so a stale read costs a round, not correctness
@@ -174,7 +176,10 @@ cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restr
                 member = true;
                 return true;
             }
-            if (sj == ST_UNDECIDED) blocked = true;
+            if (sj == ST_UNDECIDED) {
+                blocked = true;
+                if (first_round) return true;  // blocked, and no leader to be found yet
+            }
             return false;
         });
     if (member) state[k] = ST_MEMBER;
@@ -543,7 +548,8 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     const unsigned gr = (n + 127) / 128;
     for (int iter = 0;; ++iter) {
         PPF_CUDA(ctx, cudaMemsetAsync(small + 1, 0, sizeof(uint32_t), st));
-        PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, crank[cur], hp, n, pos_thr, rot_thr, state, small + 1);
+        PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, crank[cur], hp, n, pos_thr, rot_thr, state, small + 1,
+                   iter == 0 ? 1u : 0u);
         // lists worth compacting: the walk of a pose is as long as the non-members of its 27 cells
         if (n_list > 2048 && (rc = compact(0u))) return rc;
         PPF_CUDA(ctx, cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
