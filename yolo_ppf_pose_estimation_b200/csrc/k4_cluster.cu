@@ -140,48 +140,58 @@ __device__ __forceinline__ void for_each_earlier_within(const PoseRows *__restri
             }
 }
 
-// one round of the ordered independent-set resolution over the non-member lists: the first earlier LEADER within
-// bounds makes the pose a MEMBER; failing that, an earlier UNDECIDED pose within bounds blocks it for this round
-// (from then on only leaders are still tested); a pose that meets neither is a LEADER
+// one round of the ordered independent-set resolution.  Two sets of per-cell lists, both in rank order: the leaders found
+// so far (short) and the poses that are not members yet.  An earlier LEADER within bounds makes the pose a MEMBER; failing
+// that, an earlier UNDECIDED pose within bounds blocks it for this round; a pose that meets neither is a LEADER.
 __global__ void __launch_bounds__(128)
 cluster_round_kernel(const PoseRows *__restrict__ poses, const uint32_t *__restrict__ cell_start,
-                     const uint32_t *__restrict__ cell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
-                     volatile uint32_t *state, uint32_t *__restrict__ undecided, uint32_t first_round) {
+                     const uint32_t *__restrict__ cell_rank, const uint32_t *__restrict__ lcell_start,
+                     const uint32_t *__restrict__ lcell_rank, HashParams hp, uint32_t n, float pos_thr, float rot_thr,
+                     volatile uint32_t *state, uint32_t *__restrict__ undecided) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n || state[k] != ST_UNDECIDED) return;
     float a[12];
     rows_to_array(poses[k], a);
     bool blocked = false, member = false;
-    // A pose that has compared itself with UNDECIDED_TESTS earlier undecided poses without finding one within bounds gives
-    // up for this round (it stays undecided: always safe).  Before any leader exists, the poses of a crowded cell that
-    // resemble nobody would otherwise compare themselves with thousands of poses each.  The lowest-ranked undecided pose
-    // has no undecided pose before it, so it never gives up and every round decides at least one pose.
-    constexpr int UNDECIDED_TESTS = 48;
-    int tested = 0;
+    // every leader the lists know of (those made in this very round are met next round: a stale view costs a round, not
+    // correctness — decisions only ever use final states)
     for_each_earlier_within(
-        poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state,
-        [&](uint32_t sj) -> int {
-            if (sj == ST_LEADER) return 1;
-            if (sj != ST_UNDECIDED || blocked) return 0;
-            if (++tested > UNDECIDED_TESTS) {
-                blocked = true;
-                return first_round ? 2 : 0;  // no leader exists in the first round: nothing further on can change the outcome
-            }
-            return 1;
-        },
-        [&](uint32_t j) {
-            // decisions use final states only (LEADER / MEMBER never change), so a stale read costs a round, not correctness
-            const uint32_t sj = state[j];
-            if (sj == ST_LEADER) {
-                member = true;
-                return true;
-            }
-            if (sj == ST_UNDECIDED) {
-                blocked = true;
-                if (first_round) return true;  // blocked, and no leader to be found yet
-            }
-            return false;
+        poses, lcell_start, lcell_rank, hp, k, a, pos_thr, rot_thr, state, [&](uint32_t) -> int { return 1; },
+        [&](uint32_t) {
+            member = true;
+            return true;
         });
+    if (!member) {
+        // A pose that has compared itself with UNDECIDED_TESTS earlier undecided poses without finding one within bounds
+        // gives up for this round (it stays undecided: always safe) — the poses of a crowded cell that resemble nobody would
+        // otherwise compare themselves with thousands of poses each.  The lowest-ranked undecided pose has no undecided pose
+        // before it, so it never gives up and every round decides at least one pose.
+        constexpr int UNDECIDED_TESTS = 48;
+        int tested = 0;
+        for_each_earlier_within(
+            poses, cell_start, cell_rank, hp, k, a, pos_thr, rot_thr, state,
+            [&](uint32_t sj) -> int {
+                if (sj == ST_LEADER) return 1;  // possibly one made in this very round, which the leaders' lists do not hold yet
+                if (sj != ST_UNDECIDED) return 0;
+                if (++tested > UNDECIDED_TESTS) {
+                    blocked = true;
+                    return 2;
+                }
+                return 1;
+            },
+            [&](uint32_t j) {
+                const uint32_t sj = state[j];
+                if (sj == ST_LEADER) {
+                    member = true;
+                    return true;
+                }
+                if (sj == ST_UNDECIDED) {
+                    blocked = true;
+                    return true;
+                }
+                return false;
+            });
+    }
     if (member) state[k] = ST_MEMBER;
     else if (!blocked) state[k] = ST_LEADER;
     else atomicAdd(undecided, 1u);
@@ -477,7 +487,8 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     const size_t o_keys0 = take(n), o_keys1 = take(n), o_ord0 = take(n), o_ord1 = take(n), o_ck0 = take(n),
                  o_ck1 = take(n), o_cr0 = take(n), o_cr1 = take(n), o_votes = take(n), o_state = take(n),
                  o_lid = take(n), o_as = take(n), o_cv = take(n), o_cs = take(n), o_cell = take((size_t)n_cells + 1),
-                 o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12);
+                 o_bs = take(n_scan_blocks), o_small = take(16), o_out = take(48), o_poses = take((size_t)n * 12),
+                 o_lr = take(n), o_lk = take(n), o_lcell = take((size_t)n_cells + 1);
     StreamBuf<uint32_t> pool_owner(ctx);  // returned to the pool on every path out of this function
     PPF_CUDA(ctx, pool_owner.alloc(words));
     uint32_t *pool = pool_owner.p;
@@ -487,6 +498,7 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     cl_votes = pool + o_cv; cl_size = pool + o_cs; cell_start = pool + o_cell; block_sums = pool + o_bs;
     small = pool + o_small; d_out = reinterpret_cast<float *>(pool + o_out);
     poses = reinterpret_cast<PoseRows *>(pool + o_poses);
+    uint32_t *lrank = pool + o_lr, *lkeys = pool + o_lk, *lcell_start = pool + o_lcell;
     // state .. cl_size are contiguous: one memset clears state (UNDECIDED), leader ids, assignments, cluster sums
     PPF_CUDA(ctx, cudaMemsetAsync(state, 0, (o_cell - o_state) * sizeof(uint32_t), st));
     PPF_CUDA(ctx, cudaMemsetAsync(small, 0, (16 + 48) * sizeof(uint32_t), st));
@@ -531,38 +543,53 @@ int k4_cluster(b200ppf_ctx *ctx, const b200ppf_hypothesis *hyps, size_t n_, floa
     int cur = in_alt ? 1 : 0;  // which crank / ckeys buffer holds the current lists
     uint32_t n_list = n;
     PPF_CUDA(ctx, cudaMemcpyAsync(small + 9, &n_list, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // compaction of the current non-member lists: into themselves without the members (mode 0: small[9] <- new length), or
+    // into the leaders-only lists (mode 1: small[11] <- their length); n_list bounds the source length on the host
     auto compact = [&](uint32_t leaders_only) -> int {
         const unsigned gl = (n_list + 255) / 256, gs = (n_list + SCAN_BLOCK - 1) / SCAN_BLOCK;
-        if (n_list == 0) return B200PPF_OK;
-        PPF_LAUNCH(ctx, cluster_keep_flags_kernel, gl, 256, 0, crank[cur], small + 9, state, leaders_only, keep);
-        PPF_LAUNCH(ctx, keep_count_kernel, gs, SCAN_BLOCK, 0, keep, small + 9, block_sums);
-        PPF_LAUNCH(ctx, leader_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, gs, small + 10);
-        PPF_LAUNCH(ctx, keep_index_kernel, gs, SCAN_BLOCK, 0, keep, small + 9, block_sums, pos);
-        PPF_LAUNCH(ctx, cluster_compact_kernel, gl, 256, 0, crank[cur], ckeys[cur], small + 9, keep, pos, crank[1 - cur], ckeys[1 - cur]);
-        PPF_CUDA(ctx, cudaMemcpyAsync(small + 9, small + 10, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-        cur = 1 - cur;
-        PPF_LAUNCH(ctx, cluster_cell_offsets_dev_kernel, (n_cells + 1 + 255) / 256, 256, 0, ckeys[cur], small + 9, n_cells, cell_start);
+        uint32_t *dst_rank = leaders_only ? lrank : crank[1 - cur], *dst_keys = leaders_only ? lkeys : ckeys[1 - cur];
+        uint32_t *dst_n = small + (leaders_only ? 11 : 10);
+        if (n_list == 0) {
+            PPF_CUDA(ctx, cudaMemsetAsync(dst_n, 0, sizeof(uint32_t), st));
+        } else {
+            PPF_LAUNCH(ctx, cluster_keep_flags_kernel, gl, 256, 0, crank[cur], small + 9, state, leaders_only, keep);
+            PPF_LAUNCH(ctx, keep_count_kernel, gs, SCAN_BLOCK, 0, keep, small + 9, block_sums);
+            PPF_LAUNCH(ctx, leader_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, gs, dst_n);
+            PPF_LAUNCH(ctx, keep_index_kernel, gs, SCAN_BLOCK, 0, keep, small + 9, block_sums, pos);
+            PPF_LAUNCH(ctx, cluster_compact_kernel, gl, 256, 0, crank[cur], ckeys[cur], small + 9, keep, pos, dst_rank, dst_keys);
+        }
+        if (leaders_only) {
+            PPF_LAUNCH(ctx, cluster_cell_offsets_dev_kernel, (n_cells + 1 + 255) / 256, 256, 0, lkeys, small + 11, n_cells, lcell_start);
+        } else {
+            PPF_CUDA(ctx, cudaMemcpyAsync(small + 9, small + 10, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            cur = 1 - cur;
+            PPF_LAUNCH(ctx, cluster_cell_offsets_dev_kernel, (n_cells + 1 + 255) / 256, 256, 0, ckeys[cur], small + 9, n_cells, cell_start);
+        }
         return B200PPF_OK;
     };
+    // no leader yet: empty leaders-only lists
+    PPF_CUDA(ctx, cudaMemsetAsync(lcell_start, 0, ((size_t)n_cells + 1) * sizeof(uint32_t), st));
     // ordered independent-set rounds until nothing is undecided
     const unsigned gr = (n + 127) / 128;
     for (int iter = 0;; ++iter) {
         PPF_CUDA(ctx, cudaMemsetAsync(small + 1, 0, sizeof(uint32_t), st));
-        PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, crank[cur], hp, n, pos_thr, rot_thr, state, small + 1,
-                   iter == 0 ? 1u : 0u);
-        // lists worth compacting: the walk of a pose is as long as the non-members of its 27 cells
-        if (n_list > 2048 && (rc = compact(0u))) return rc;
+        PPF_LAUNCH(ctx, cluster_round_kernel, gr, 128, 0, poses, cell_start, crank[cur], lcell_start, lrank, hp, n, pos_thr, rot_thr,
+                   state, small + 1);
+        // the members leave the lists (worth it while the lists are long: a pose's walk is as long as the non-members of its
+        // 27 cells), then the leaders-only lists are drawn from what is left
+        if (n_list > 2048 && iter > 0 && (rc = compact(0u))) return rc;
+        if ((rc = compact(1u))) return rc;
         PPF_CUDA(ctx, cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
         PPF_CUDA(ctx, cudaStreamSynchronize(st));
         n_list = h_small[9];
         if (h_small[1] == 0) break;
         if (iter > (int)n) return fail_msg(ctx, B200PPF_ERR_CUDA, "cluster: leader resolution did not converge");
     }
-    if ((rc = compact(1u))) return rc;  // leaders only, rank order inside every cell
+    // lcell_start / lrank now hold every leader, in rank order inside every cell
     PPF_LAUNCH(ctx, leader_count_kernel, n_scan_blocks, SCAN_BLOCK, 0, state, n, block_sums);
     PPF_LAUNCH(ctx, leader_scan_blocks_kernel, 1, SCAN_BLOCK, 0, block_sums, n_scan_blocks, small + 2);
     PPF_LAUNCH(ctx, leader_index_kernel, n_scan_blocks, SCAN_BLOCK, 0, state, n, block_sums, leader_id);
-    PPF_LAUNCH(ctx, cluster_assign_kernel, gr, 128, 0, poses, cell_start, crank[cur], hp, n, pos_thr, rot_thr, state,
+    PPF_LAUNCH(ctx, cluster_assign_kernel, gr, 128, 0, poses, lcell_start, lrank, hp, n, pos_thr, rot_thr, state,
                leader_id, votes, ord, assign_sorted, ctx->d_assign, cl_votes, cl_size);
     PPF_LAUNCH(ctx, cluster_top3_kernel, 1, 1024, 0, cl_votes, small + 2, small + 3);
     PPF_LAUNCH(ctx, cluster_average_kernel, 3, 256, 0, poses, assign_sorted, n, small + 3, cl_votes, cl_size, d_out,
