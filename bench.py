@@ -289,7 +289,14 @@ def run_b200(args, wl):
     n_ref = wl.n_ref
     library = wl.library()
     lib_mode = len(library) > 1
-    if lib_mode:
+    lib_sharded = lib_mode and args.c4_mode == "refs" and world > 1
+    if lib_sharded:
+        # model library (c4), second partitioning: every rank holds all tables, the reference points of every model's
+        # align are shared by all ranks (the group's queue) — one align per model, each over all GPUs
+        my_models = list(range(len(library)))
+        first, step, count = sharding.shard(n_ref, rank, world)
+        chunk = sharding.chunk_size(n_ref, world)
+    elif lib_mode:
         # model library (c4): model-parallel — rank r aligns models r, r + world, ... against the replicated scene,
         # every reference point each; no hypothesis exchange, only the final poses are gathered
         my_models = [k for k in range(len(library)) if k % world == rank]
@@ -317,7 +324,7 @@ def run_b200(args, wl):
 
     # ---- several GPUs: b200ppf_group_* — the record exchange is fused into the vote epilogue (NVLink peer stores), the
     # per-step barrier is a flag the peers' kernels raise and a one-thread kernel awaits: no torch.distributed call in a step
-    p2p = world > 1 and not lib_mode and args.exchange == "p2p"
+    p2p = world > 1 and (not lib_mode or lib_sharded) and args.exchange == "p2p"
     group = None
     if p2p:
         group = capi.Group(ctx, rank, world, chunk * world)
@@ -340,7 +347,7 @@ def run_b200(args, wl):
                 collect["vote_ms"] = collect.get("vote_ms", 0.0) + ctx.timings()["vote_ms"]
             if p2p:
                 res = group.cluster(dm, table, ds, wl.ref_rate, wl.pos_thr, wl.rot_thr)
-            elif world > 1 and not lib_mode:
+            elif world > 1 and (not lib_mode or lib_sharded):
                 with torch.cuda.stream(stream):
                     ordered = sharding.all_gather_hypotheses(local_buf, n_ref, world, dist)
                 res = ctx.cluster(None, wl.pos_thr, wl.rot_thr, device_ptr=ordered.data_ptr(), n=n_ref)
@@ -443,7 +450,7 @@ def run_b200(args, wl):
             "config": workload_config(wl, world),
             "run": {"table_entries": int(info.n_entries), "accumulator_slices": int(info.n_slices),
                     "alpha_columns": int(info.n_alpha), "phase_cells": int(info.phase_cells),
-                    "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode
+                    "sharding": (f"model-parallel: {len(library)} models over {world} rank(s), scene replicated" if lib_mode and not lib_sharded
                                  else ((f"b200ppf_group: {world} ranks draw (reference point, slice) tasks from one queue over NVLink, "
                                         f"table + scene replicated, 8-byte peaks merged into every rank's array by system-scope atomicMax, "
                                         f"device-side flags" if p2p else
@@ -505,6 +512,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="reference points per CPU step, taken in order from the fixed 64-point list (0 = sized for ~4 s per step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--c4-mode", default="models", choices=["models", "refs"],
+                    help="model library on several GPUs: one model per GPU (default) or every table on every GPU with the "
+                         "reference points of each align shared by all GPUs")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="several GPUs: records written into every peer's buffer by the vote epilogue (default) or NCCL all-gather")
     args = ap.parse_args()
