@@ -43,6 +43,10 @@ namespace {
 // Two launch shapes: 512 threads with two CTAs per SM when the accumulator slice leaves room for both,
 // 1024 threads with one CTA per SM (the same 32 warps) for the large slices of sliced tables.
 constexpr int VOTE_THREADS_SMALL = 512;
+#ifndef B200PPF_OWN_UNROLL
+#define B200PPF_OWN_UNROLL 2
+#endif
+constexpr int OWN_UNROLL = B200PPF_OWN_UNROLL;  // steps of 32 entries in flight in the scene phase's own cell
 constexpr int VOTE_THREADS_LARGE = 1024;
 #ifndef B200PPF_CAND_CAP
 #define B200PPF_CAND_CAP 2048
@@ -83,6 +87,7 @@ struct VoteArgs {
     GridParams gp;
     uint32_t n_s;
     uint32_t ref_first, ref_step, ref_count;
+    const uint32_t *ref_order;    // task position -> reference slot, heaviest neighbourhood first (nullptr: identity)
     const uint32_t *sub_offsets;  // phase-cell bounds (bucket bounds when the table has no phase cells)
     const uint32_t *msub_offsets; // the same bounds in the merged-vote array (phase-sorted tables)
     const uint32_t *merged_w;     // (count << 24) | hot word
@@ -128,6 +133,13 @@ __device__ __forceinline__ void red_shared_add_if_lt(uint32_t addr, uint32_t v, 
                  "r"(len)
                  : "memory");
 }
+// increment predicated on x >= lo && k < len (the scene phase's own cell: outside the guard band, inside the bucket)
+__device__ __forceinline__ void red_shared_inc_if_ge_lt(uint32_t addr, uint32_t x, uint32_t lo, uint32_t k, uint32_t len) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ge.u32 p, %1, %2;\n\tsetp.lt.and.u32 q, %3, %4, p;\n\t@q red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr),
+        "r"(x), "r"(lo), "r"(k), "r"(len)
+        : "memory");
+}
 // the same, predicated on k < len (the partial last step of a shift item)
 __device__ __forceinline__ void red_shared_inc_if_lt(uint32_t addr, uint32_t k, uint32_t len) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"(k), "r"(len)
@@ -166,7 +178,8 @@ __device__ __forceinline__ void vote_exact(const BinParams &bp, uint32_t acc_add
 
 // one (reference point, accumulator slice) task; ref_i = reference slot of this launch
 template <int MODE, bool SEAM, bool BULK, int THREADS>
-__device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_i, const uint32_t slice) {
+__device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_i, const uint32_t slice,
+                                          uint32_t *next_task) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Frame s_sg;
     __shared__ uint32_t s_ncand, s_nitems, s_next, s_scratch;
@@ -189,6 +202,11 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
     const uint32_t acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
     const uint32_t scratch_addr = (uint32_t)__cvta_generic_to_shared(&s_scratch);
 
+    // shared queue: one thread draws the NEXT task now and parks it in shared memory once the accumulator is clear —
+    // the round trip (over NVLink on the other ranks) overlaps the prologue and costs no register in the vote loops
+    const bool draws = next_task != nullptr && tid == THREADS - 1;
+    uint32_t drawn = 0;
+    if (draws) drawn = atomicAdd_system(a.queue, 1u);
     const uint32_t s_r = a.ref_first + ref_i * a.ref_step;
     const float4 pr4 = a.pos[s_r], nr4 = a.nrm[s_r];
     const V3 p_r = v3_of(pr4), n_r = v3_of(nr4);
@@ -217,6 +235,7 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
     }
     for (uint32_t k = tid; k < acc_len; k += THREADS) acc[k] = 0;
     __syncthreads();
+    if (draws) *next_task = drawn;  // everyone has read the current task before the barrier above
 
     const uint32_t lf = a.bp.cells_log2;
     const uint32_t *slice_offsets = a.sub_offsets + (((size_t)slice * a.kp.key_space) << lf);
@@ -375,32 +394,33 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                         // the scene phase's own cell (or the whole bucket when the phase sits on a cell edge): an entry
                         // whose phase is below the scene's shifts by q + 1, the others by q; within the guard band of
                         // the scene phase the literal form decides.  32 entries per step, two steps in flight.
-                        const uint32_t guard = a.bp.phase_guard;
-                        for (uint32_t k0 = lane; k0 - lane < e_end; k0 += 64) {  // warp-uniform
-                            uint2 en[2];
+                        // dg = (entry phase in its cell) - (scene phase) + guard.  Outside [0, 2 guard) the comparison is
+                        // safe: dg negative as a signed number = the entry lies below the scene phase and shifts one more.
+                        const uint32_t guard2 = 2u * a.bp.phase_guard, phi_g = wi.phi - a.bp.phase_guard;
+                        const uint32_t c_lo = wi.c_below, c_hi = wi.c_below - unit;
+                        for (uint32_t k0 = lane; k0 - lane < e_end; k0 += 32 * OWN_UNROLL) {  // warp-uniform
+                            uint32_t w[OWN_UNROLL], pu[OWN_UNROLL];
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) en[u] = make_uint2(__ldg(wp + k0 + u * 32), __ldg(ap + k0 + u * 32));
-                            bool risky[2];
-                            uint32_t pu[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                risky[u] = false;
-                                if (k0 - lane + u * 32 < e_end) {  // warp-uniform
-                                    pu[u] = __umulhi(en[u].y, a.bp.fix_mul);
-                                    const int d = (int)(pu[u] & fmask) - (int)wi.phi;
-                                    const bool valid = k0 + u * 32 < e_end;
-                                    const bool sure = (uint32_t)(d + (int)guard) >= 2u * guard;
-                                    const uint32_t c = wi.c_below - (d >= 0 ? unit : 0u);
-                                    red_shared_inc((sure && valid) ? acc_addr + min(en[u].x - c, en[u].x - c + wrap_bytes)
-                                                                   : scratch_addr);
-                                    risky[u] = valid && !sure;
-                                }
+                            for (int u = 0; u < OWN_UNROLL; ++u) {
+                                w[u] = __ldg(wp + k0 + u * 32);
+                                pu[u] = __ldg(ap + k0 + u * 32);
                             }
+                            bool risky = false;
 #pragma unroll
-                            for (int u = 0; u < 2; ++u)
-                                if (risky[u])
-                                    vote_exact<MODE>(a.bp, acc_addr, unit, en[u].x - unit * phase_bin(a.bp, pu[u]),
-                                                     __ldg(fp + k0 + u * 32), wi.alpha_s, st_skipped);
+                            for (int u = 0; u < OWN_UNROLL; ++u) {
+                                pu[u] = __umulhi(pu[u], a.bp.fix_mul);
+                                const uint32_t dg = (pu[u] & fmask) - phi_g;
+                                const uint32_t t = w[u] - ((int)dg >= 0 ? c_hi : c_lo);
+                                red_shared_inc_if_ge_lt(acc_addr + min(t, t + wrap_bytes), dg, guard2, k0 + u * 32, e_end);
+                                risky |= dg < guard2 && k0 + u * 32 < e_end;
+                            }
+                            if (__any_sync(0xFFFFFFFFu, risky)) {  // one entry in ~10^3 sits within the guard band
+#pragma unroll
+                                for (int u = 0; u < OWN_UNROLL; ++u)
+                                    if ((pu[u] & fmask) - phi_g < guard2 && k0 + u * 32 < e_end)
+                                        vote_exact<MODE>(a.bp, acc_addr, unit, w[u] - unit * phase_bin(a.bp, pu[u]),
+                                                         __ldg(fp + k0 + u * 32), wi.alpha_s, st_skipped);
+                            }
                         }
                     } else if (BULK) {
                         // the sliver between N_T and T: literal form for every entry (one scene pair in ~10^7)
@@ -554,27 +574,43 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
     }
 }
 
+// Task order.  A task's cost follows the number of scene points around its reference point (C3: 81 % of the tasks take
+// ~0.1 ms, 9 % take 4-9 ms, profiles/r2_queue_task_histogram.txt), and a heavy task drawn last leaves every other CTA
+// idle while it runs — 13 ms per launch on C3, the same on one GPU or eight.  So each slice hands out its reference
+// points heaviest neighbourhood first (the 27 grid cells the task will sweep), and the launch ends on the 0.1 ms tasks.
+__global__ void ref_cost_kernel(const float4 *__restrict__ pos, const uint32_t *__restrict__ cell_start, GridParams gp,
+                                uint32_t ref_first, uint32_t ref_step, uint32_t ref_count, uint32_t n_s,
+                                uint32_t *__restrict__ inv_cost) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ref_count) return;
+    const float4 p = pos[ref_first + r * ref_step];
+    const int cx = grid_cell_coord(gp, p.x, 0), cy = grid_cell_coord(gp, p.y, 1), cz = grid_cell_coord(gp, p.z, 2);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gp.dims[0] - 1);
+    uint32_t n = 0;
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, gp.dims[2] - 1); ++z)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, gp.dims[1] - 1); ++y)
+            n += cell_start[grid_cell_linear(gp, x1, y, z) + 1] - cell_start[grid_cell_linear(gp, x0, y, z)];
+    inv_cost[r] = n_s - n;  // ascending sort = heaviest first; equal costs keep reference order (stable sort)
+}
+
 template <int MODE, bool SEAM, bool BULK, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : B200PPF_VOTE_MINBLOCKS)
 ppf_vote_kernel(const VoteArgs a) {
-    if (!a.queue) {  // one CTA per (reference point, slice)
-        vote_task<MODE, SEAM, BULK, THREADS>(a, blockIdx.x, blockIdx.y);
-        return;
-    }
-    // persistent CTAs on a queue shared by all ranks; the next task is drawn while the current one runs
+    // Either one CTA per (reference point, slice) — the grid is (positions, slices) — or persistent CTAs on a queue
+    // shared by all ranks.  One call site serves both, so the two modes run the same machine code.  Slice-major order
+    // either way: the CTAs in flight share one slice of the table in L2.
     __shared__ uint32_t s_task;
-    const uint32_t n_slices = a.kp.n_slices, total = a.ref_count * n_slices;
-    uint32_t next = 0;
-    if (threadIdx.x == 0) next = atomicAdd_system(a.queue, 1u);
+    const bool persistent = a.queue != nullptr;
+    const uint32_t total = a.ref_count * a.kp.n_slices;
+    if (threadIdx.x == 0) s_task = persistent ? atomicAdd_system(a.queue, 1u) : blockIdx.y * a.ref_count + blockIdx.x;
     for (;;) {
-        if (threadIdx.x == 0) s_task = next;
         __syncthreads();
         const uint32_t task = s_task;
         if (task >= total) break;
-        if (threadIdx.x == 0) next = atomicAdd_system(a.queue, 1u);
-        // slice-major order, as the (reference, slice) grid runs: the CTAs in flight share one slice of the table in L2
-        vote_task<MODE, SEAM, BULK, THREADS>(a, task % a.ref_count, task / a.ref_count);
-        __syncthreads();
+        const uint32_t pos = task % a.ref_count;
+        vote_task<MODE, SEAM, BULK, THREADS>(a, a.ref_order ? a.ref_order[pos] : pos, task / a.ref_count,
+                                             persistent ? &s_task : nullptr);
+        if (!persistent) break;
     }
     if (threadIdx.x == 0 && a.done_counter) {
         __threadfence_system();  // this CTA's peaks are visible everywhere before it counts as done
@@ -778,6 +814,24 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
         grid_dim = dim3((unsigned)(ctx->sm_count * (vote_threads(t) == VOTE_THREADS_SMALL ? B200PPF_VOTE_MINBLOCKS : 1)), 1);
     }
     cudaEventRecord(ctx->ev_vote[1], ctx->stream);  // grid build ends, voting starts
+    // heaviest neighbourhood first once the launch is several waves deep (see ref_cost_kernel)
+    StreamBuf<uint32_t> cost(ctx), cost_alt(ctx), order(ctx), order_alt(ctx);
+    a.ref_order = nullptr;
+    if (ref_count * t->info.n_slices >= 8 * (size_t)ctx->sm_count && !getenv("B200PPF_NO_TASK_ORDER")) {
+        PPF_CUDA(ctx, cost.alloc(ref_count));
+        PPF_CUDA(ctx, cost_alt.alloc(ref_count));
+        PPF_CUDA(ctx, order.alloc(ref_count));
+        PPF_CUDA(ctx, order_alt.alloc(ref_count));
+        PPF_LAUNCH(ctx, ref_cost_kernel, (unsigned)((ref_count + 255) / 256), 256, 0, scene->pos, grid.cell_start, grid.gp,
+                   (uint32_t)ref_first, (uint32_t)ref_step, (uint32_t)ref_count, (uint32_t)scene->n, cost.p);
+        int bits = 1;
+        while ((scene->n >> bits) != 0) ++bits;  // costs are counts of scene points
+        bool in_alt = false;
+        rc = radix_sort_u32(ctx, cost.p, cost_alt.p, order.p, order_alt.p, nullptr, nullptr, ref_count, bits, /*v0_iota=*/true,
+                            &in_alt);
+        if (rc) return rc;
+        a.ref_order = in_alt ? order_alt.p : order.p;
+    }
 #define LAUNCH_VOTE_T(M, S, B, T)                                                                                  \
     do {                                                                                                            \
         PPF_CUDA(ctx, cudaFuncSetAttribute(ppf_vote_kernel<M, S, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
