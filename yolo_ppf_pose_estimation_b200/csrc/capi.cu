@@ -407,7 +407,7 @@ int b200ppf_table_export(b200ppf_ctx *ctx, const b200ppf_table *t, uint32_t *off
 namespace {
 
 constexpr uint64_t TABLE_MAGIC = 0x4C42543030325042ull;  // "BP200TBL" little-endian
-constexpr uint32_t TABLE_FORMAT = 3;                      // 3: alpha-column rule, bin-major hot words (2: phase-sorted buckets)
+constexpr uint32_t TABLE_FORMAT = 4;                      // 4: sub-phase byte above the hot word (3: alpha-column rule, bin-major hot words)
 
 struct TableFileHeader {
     uint64_t magic;
@@ -501,7 +501,7 @@ const char *validate_table_file(const TableFileHeader &h, const std::vector<std:
             if (!(alpha >= -3.14159274f && alpha <= 3.14159274f)) return "entry alpha_m outside [-pi, pi]";
             const uint32_t a_fix = b200ppf::alpha_to_fix(alpha), local = (uint32_t)(i - row0);
             if (eam[p] != a_fix) return "entry fixed-point alpha_m does not match its float";
-            if (ew[p] != (ref.bulk ? b200ppf::hot_word(ref, kp.row_pitch, local, b200ppf::phase_of_fix(ref, a_fix)) : 4u * local))
+            if (ew[p] != (ref.bulk ? b200ppf::entry_word(ref, kp.row_pitch, local, alpha) : 4u * local))
                 return "entry hot word does not match its pair";
         }
     }

@@ -35,22 +35,7 @@ __device__ __forceinline__ uint32_t slice_of(uint32_t i, uint32_t slice_rows) { 
 __device__ __forceinline__ uint32_t sort_key(const KeyParams &kp, const BinParams &bp, uint32_t i, uint32_t k, float alpha) {
     uint32_t key = slice_of(i, kp.slice_rows) * kp.key_space + k;
     if (bp.cells_log2) {
-        // Phase cell of alpha_m in fp32: frac((alpha + pi) / step) * cells.  The estimate is within 1e-6 rad of
-        // the fixed-point phase the voting kernel reasons with; an entry that lands on the other side of a
-        // cell edge because of it is harmless, since the kernel sends the whole bucket down the per-entry
-        // path whenever the scene phase is within phase_guard (>= 4e-6 rad) of a cell edge — otherwise such
-        // an entry compares with the scene phase exactly like the edge itself does.  (alpha outside
-        // atan2f's range is rejected later, entries_kernel; any cell will do for it.)
-        // The one edge that must be exact is the circular one (phase 0 == phase 1: an entry moved across it
-        // would sit below every scene phase instead of above): close to it the fixed-point phase decides.
-        uint32_t cell = 0;
-        if (alpha == alpha) {
-            const float u = (alpha + 3.14159274f) * bp.inv_step;
-            const float fr = u - floorf(u);
-            const float thr = fmaxf(1e-4f, 2e-6f * (float)bp.n_turn);  // >> the fp32 error of u (a few ulps of T)
-            if (fr < thr || fr > 1.0f - thr) cell = phase_cell(bp, phase_of_fix(bp, alpha_to_fix(alpha)));
-            else cell = min((uint32_t)(fr * (float)(1u << bp.cells_log2)), (1u << bp.cells_log2) - 1u);
-        }
+        const uint32_t cell = filed_phase_cell(bp, alpha);  // fp32 estimate, exact at the circular edge (ppf_math.cuh)
         key = (key << bp.cells_log2) | cell;
         // merged votes: the bin of alpha_m (from the fixed-point phase the hot word is made of) follows the cell, so
         // that the entries of one (cell, bin, model row) — identical votes for every scene pair outside the cell —
@@ -229,12 +214,12 @@ __global__ void merge_words_kernel(const uint32_t *__restrict__ head, const uint
     if (p >= n_entries || !head[p]) return;
     uint32_t q = p + 1;
     while (q < n_entries && !head[q]) ++q;  // <= 255 steps
-    merged_w[rank[p]] = ((q - p) << 24) | entry_w[p];
+    merged_w[rank[p]] = ((q - p) << 24) | (entry_w[p] & HOT_MASK);
 }
 
 __global__ void merge_identity_kernel(const uint32_t *__restrict__ entry_w, uint32_t n_entries, uint32_t *__restrict__ merged_w) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n_entries) merged_w[p] = (1u << 24) | entry_w[p];
+    if (p < n_entries) merged_w[p] = (1u << 24) | (entry_w[p] & HOT_MASK);
 }
 
 // merged position of every cell bound (cell starts are run heads)
@@ -275,7 +260,7 @@ __global__ void entries_kernel(const uint32_t *__restrict__ sorted_idx, const ui
     // atan2f range; anything else cannot come from PPFEstimation and would not wrap like PCL's floats
     if (!(alpha >= -3.14159274f && alpha <= 3.14159274f)) *bad_alpha = 1;
     const uint32_t a_fix = alpha_to_fix(alpha);
-    entry_w[p] = bp.bulk ? hot_word(bp, pitch, local, phase_of_fix(bp, a_fix)) : 4u * local;
+    entry_w[p] = bp.bulk ? entry_word(bp, pitch, local, alpha) : 4u * local;
     entry_am[p] = a_fix;
     entry_alpha[p] = alpha;
 }

@@ -43,11 +43,11 @@ namespace {
 // Two launch shapes: 512 threads with two CTAs per SM when the accumulator slice leaves room for both,
 // 1024 threads with one CTA per SM (the same 32 warps) for the large slices of sliced tables.
 constexpr int VOTE_THREADS_SMALL = 512;
+constexpr int VOTE_THREADS_LARGE = 1024;
 #ifndef B200PPF_OWN_UNROLL
-#define B200PPF_OWN_UNROLL 2
+#define B200PPF_OWN_UNROLL 4
 #endif
 constexpr int OWN_UNROLL = B200PPF_OWN_UNROLL;  // steps of 32 entries in flight in the scene phase's own cell
-constexpr int VOTE_THREADS_LARGE = 1024;
 #ifndef B200PPF_CAND_CAP
 #define B200PPF_CAND_CAP 2048
 #endif
@@ -67,7 +67,8 @@ struct __align__(16) WorkItem {
     uint32_t off, len;
     uint32_t k_below, k_above;
     uint32_t e_off, e_len;      // per-entry range in the unmerged entry arrays
-    uint32_t pad0, pad1;
+    uint32_t sub_range;         // own cell: sub_lo | sub_hi << 8 | 1 << 16 (ppf_math.cuh, sub_phase); 0: compare every entry in full
+    uint32_t pad1;
     uint32_t c_below;           // constant subtracted from the hot words below the scene phase: 4 * pitch * (q + 1)
     uint32_t c_s;               // per-entry path: alpha_to_fix(alpha_s) - 2^31
     float alpha_s;              // per-entry path: PCL's float (literal form of the guard-band votes)
@@ -114,6 +115,7 @@ struct VoteArgs {
     int n_peers;
     uint32_t signal_slot, signal_value;
     uint32_t *done_counter;
+    int no_sub_phase;  // debug (B200PPF_NO_SUB_PHASE): compare every own-cell entry in full
 };
 
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o) {
@@ -251,7 +253,7 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
             const uint32_t c = c0 + tid;
             // the bucket [o0, oF) of unmerged entries; phase-sorted tables: its merged words [m0, mF) split at the scene
             // phase's cell [ma, mb) into below / above, and the cell's own unmerged entries are [oa, ob)
-            uint32_t o0 = 0, oa = 0, ob = 0, oF = 0, q = 0, c_s = 0, phi = 0;
+            uint32_t o0 = 0, oa = 0, ob = 0, oF = 0, q = 0, c_s = 0, phi = 0, sub_range = 0;
             uint32_t m0 = 0, ma = 0, mb = 0, mF = 0;
             float alpha_s = 0.0f;
             if (tid < THREADS && c < ncand) {
@@ -281,6 +283,8 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                                 // between N_T and T (q == N_T) every entry takes the literal form
                                 phi = q < a.bp.n_turn ? (phase_of_fix(a.bp, c_s) & fmask) : 0xFFFFFFFFu;
                                 if (split) {
+                                    const uint32_t in = phi & ((1u << (a.bp.fix_shift - lf)) - 1u), sh = sub_phase_shift(a.bp);
+                                    sub_range = ((in - a.bp.phase_guard) >> sh) | (((in + a.bp.phase_guard - 1u) >> sh) << 8) | 0x10000u;
                                     const uint32_t *mo = slice_moffsets + ((size_t)key << lf);
                                     m0 = __ldg(mo);
                                     mF = __ldg(mo + (1u << lf));
@@ -320,7 +324,8 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                 it.k_above = mb - m0;
                 it.e_off = oa;
                 it.e_len = ob - oa;
-                it.pad0 = it.pad1 = 0;
+                it.sub_range = a.no_sub_phase ? 0u : sub_range;
+                it.pad1 = 0;
                 it.c_below = unit * (q + 1u);
                 it.c_s = c_s;
                 it.alpha_s = alpha_s;
@@ -394,15 +399,57 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                         // the scene phase's own cell (or the whole bucket when the phase sits on a cell edge): an entry
                         // whose phase is below the scene's shifts by q + 1, the others by q; within the guard band of
                         // the scene phase the literal form decides.  32 entries per step, two steps in flight.
-                        // dg = (entry phase in its cell) - (scene phase) + guard.  Outside [0, 2 guard) the comparison is
-                        // safe: dg negative as a signed number = the entry lies below the scene phase and shifts one more.
                         const uint32_t guard2 = 2u * a.bp.phase_guard, phi_g = wi.phi - a.bp.phase_guard;
                         const uint32_t c_lo = wi.c_below, c_hi = wi.c_below - unit;
+                        if (wi.sub_range) {
+                            // the scene phase's own cell by sub-phase: rel = (entry's sub-phase) - sub_lo.  rel > span
+                            // (unsigned) = outside the scene's own sub-phases, and then the sign of rel tells the side.
+                            const uint32_t sub_lo = wi.sub_range & 0xFFu, span = ((wi.sub_range >> 8) & 0xFFu) - sub_lo;
+                            // The increment is unconditional with the decision as its value (adding 0 is free of side
+                            // effects and cheaper than a branch around the reduction); lanes past the end read the
+                            // next bucket or the padding, whose words address the accumulator like any other.
+                            auto own_step = [&](const uint32_t k0, const bool tail) {
+                                uint32_t w[OWN_UNROLL], v[OWN_UNROLL], settled = 0;
+#pragma unroll
+                                for (int u = 0; u < OWN_UNROLL; ++u) w[u] = __ldg(wp + k0 + u * 32);
+#pragma unroll
+                                for (int u = 0; u < OWN_UNROLL; ++u) {
+                                    const uint32_t rel = (w[u] >> 24) - sub_lo;
+                                    const bool past = tail && k0 + u * 32 >= e_end;
+                                    v[u] = (rel > span && !past) ? 1u : 0u;
+                                    const uint32_t t = (w[u] & HOT_MASK) - ((int)rel > (int)span ? c_hi : c_lo);
+                                    if (!tail || k0 - lane + u * 32 < e_end)  // warp-uniform: no reduction for an empty step
+                                        red_shared_add(acc_addr + min(t, t + wrap_bytes), v[u]);
+                                    settled += past ? 1u : v[u];
+                                }
+                                if (__any_sync(0xFFFFFFFFu, settled != OWN_UNROLL)) {  // ~1 entry in 256: the full comparison
+#pragma unroll
+                                    for (int u = 0; u < OWN_UNROLL; ++u)
+                                        if (!v[u] && !(tail && k0 + u * 32 >= e_end)) {
+                                            const uint32_t pu = __umulhi(__ldg(ap + k0 + u * 32), a.bp.fix_mul);
+                                            const uint32_t dg = (pu & fmask) - phi_g;
+                                            if (dg >= guard2) {
+                                                const uint32_t t = (w[u] & HOT_MASK) - ((int)dg >= 0 ? c_hi : c_lo);
+                                                red_shared_inc(acc_addr + min(t, t + wrap_bytes));
+                                            } else {
+                                                vote_exact<MODE>(a.bp, acc_addr, unit, (w[u] & HOT_MASK) - unit * phase_bin(a.bp, pu),
+                                                                 __ldg(fp + k0 + u * 32), wi.alpha_s, st_skipped);
+                                            }
+                                        }
+                                }
+                            };
+                            uint32_t k0 = lane;
+                            for (; k0 - lane + 32 * OWN_UNROLL <= e_end; k0 += 32 * OWN_UNROLL) own_step(k0, false);  // warp-uniform
+                            if (k0 - lane < e_end) own_step(k0, true);
+                        } else
+                        // the scene phase sits on a cell edge and the whole bucket is compared in full:
+                        // dg = (entry phase in its cell) - (scene phase) + guard.  Outside [0, 2 guard) the comparison is
+                        // safe: dg negative as a signed number = the entry lies below the scene phase and shifts one more.
                         for (uint32_t k0 = lane; k0 - lane < e_end; k0 += 32 * OWN_UNROLL) {  // warp-uniform
                             uint32_t w[OWN_UNROLL], pu[OWN_UNROLL];
 #pragma unroll
                             for (int u = 0; u < OWN_UNROLL; ++u) {
-                                w[u] = __ldg(wp + k0 + u * 32);
+                                w[u] = __ldg(wp + k0 + u * 32) & HOT_MASK;
                                 pu[u] = __ldg(ap + k0 + u * 32);
                             }
                             bool risky = false;
@@ -425,7 +472,7 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                     } else if (BULK) {
                         // the sliver between N_T and T: literal form for every entry (one scene pair in ~10^7)
                         for (uint32_t k = lane; k < e_end; k += 32) {
-                            const uint32_t w = __ldg(wp + k);
+                            const uint32_t w = __ldg(wp + k) & HOT_MASK;
                             vote_exact<MODE>(a.bp, acc_addr, unit, w - unit * phase_bin(a.bp, __umulhi(__ldg(ap + k), a.bp.fix_mul)),
                                              __ldg(fp + k), wi.alpha_s, st_skipped);
                         }
@@ -794,6 +841,7 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
     a.n_peers = 0;
     a.signal_slot = a.signal_value = 0;
     a.done_counter = nullptr;
+    a.no_sub_phase = getenv("B200PPF_NO_SUB_PHASE") ? 1 : 0;
     for (int g = 0; g < MAX_PEERS; ++g) {
         a.peer_peaks[g] = nullptr;
         a.peer_flags[g] = nullptr;
@@ -928,7 +976,8 @@ BinParams make_bin_params(float angle_step, int alpha_mode, int nalpha_rule) {
         bp.cells_log2 = 4;
         bp.phase_guard = (uint32_t)ceil(guard_bins * unit) + (uint32_t)ceil(off_int * unit) + 16u;
         // the guard must stay a small part of a phase cell
-        while (bp.cells_log2 > 0 && 8ull * bp.phase_guard > (1ull << (bp.fix_shift - bp.cells_log2))) --bp.cells_log2;
+        while (bp.cells_log2 > 0 && (8ull * bp.phase_guard > (1ull << (bp.fix_shift - bp.cells_log2)) || bp.fix_shift < bp.cells_log2 + 8u))
+            --bp.cells_log2;  // ... and hold the 8-bit sub-phase of the entry words
         if (bp.cells_log2 == 0) bp.bulk = 0;
     }
     return bp;

@@ -245,6 +245,12 @@ __host__ __device__ __forceinline__ uint32_t phase_bin(const BinParams &bp, uint
 __host__ __device__ __forceinline__ uint32_t hot_word(const BinParams &bp, uint32_t pitch, uint32_t row, uint32_t u) {
     return 4u * (phase_bin(bp, u) * pitch + row);
 }
+// The unmerged entry arrays carry, above the 24-bit hot word, the top 8 bits of the entry's position INSIDE its phase
+// cell ("sub-phase").  For a scene pair whose phase lies in the same cell, an entry with a smaller sub-phase is below
+// the scene phase and one with a larger sub-phase above it — one load and one byte compare per entry; only the entries
+// whose sub-phase is the scene's own (up to the guard band: sub_lo..sub_hi) need the full-precision comparison.
+constexpr uint32_t HOT_MASK = 0xFFFFFFu;
+__host__ __device__ __forceinline__ uint32_t sub_phase_shift(const BinParams &bp) { return bp.fix_shift - bp.cells_log2 - 8u; }
 // byte offset of a vote: the hot word shifted by q' alpha positions (c = 4 * pitch * q'), wrapped
 __host__ __device__ __forceinline__ uint32_t shifted_offset(uint32_t w, uint32_t c, uint32_t wrap_bytes) {
     const uint32_t t = w - c, t2 = t + wrap_bytes;
@@ -277,6 +283,38 @@ __host__ __device__ __forceinline__ uint32_t alpha_to_fix(float a) {
 #else
     return (uint32_t)(unsigned long long)llrint(v);
 #endif
+}
+
+// sub-phase of phase word u relative to phase cell `cell` (the table files an entry under the cell its fp32 phase
+// estimate names — filed_phase_cell, within 1e-6 rad of the fixed-point phase — so an entry next to a cell edge may lie
+// just outside its cell: it gets the cell's first or last sub-phase, which orders it against every scene phase the
+// constant-shift path admits, those being at least phase_guard away from the cell edges)
+__host__ __device__ __forceinline__ uint32_t sub_phase(const BinParams &bp, uint32_t u, uint32_t cell) {
+    const uint32_t wbits = bp.fix_shift - bp.cells_log2;
+    const int rel = (int)(u & ((1u << bp.fix_shift) - 1u)) - (int)(cell << wbits);
+    if (rel < 0) return 0u;
+    if (rel >= (int)(1u << wbits)) return 0xFFu;
+    return (uint32_t)rel >> sub_phase_shift(bp);
+}
+// Phase cell an entry is filed under, from alpha_m in fp32: frac((alpha + pi) / step) * cells.  The estimate is within
+// 1e-6 rad of the fixed-point phase the voting kernel reasons with; an entry that lands on the other side of a cell
+// edge because of it is harmless, since the kernel compares every entry of the bucket in full whenever the scene phase
+// is within phase_guard (>= 4e-6 rad) of a cell edge — otherwise such an entry compares with the scene phase exactly
+// like the edge itself does.  The one edge that must be exact is the circular one (phase 0 == phase 1: an entry moved
+// across it would sit below every scene phase instead of above): close to it the fixed-point phase decides.
+__host__ __device__ __forceinline__ uint32_t filed_phase_cell(const BinParams &bp, float alpha) {
+    if (!(alpha == alpha)) return 0u;
+    const float u = (alpha + 3.14159274f) * bp.inv_step;
+    const float fr = u - floorf(u);
+    const float thr = fmaxf(1e-4f, 2e-6f * (float)bp.n_turn);  // >> the fp32 error of u (a few ulps of T)
+    if (fr < thr || fr > 1.0f - thr) return phase_cell(bp, phase_of_fix(bp, alpha_to_fix(alpha)));
+    const uint32_t c = (uint32_t)(fr * (float)(1u << bp.cells_log2)), last = (1u << bp.cells_log2) - 1u;
+    return c < last ? c : last;
+}
+// word of the unmerged entry arrays of a phase-sorted table
+__host__ __device__ __forceinline__ uint32_t entry_word(const BinParams &bp, uint32_t pitch, uint32_t row, float alpha) {
+    const uint32_t u = phase_of_fix(bp, alpha_to_fix(alpha));
+    return (sub_phase(bp, u, filed_phase_cell(bp, alpha)) << 24) | hot_word(bp, pitch, row, u);
 }
 
 // returns the bin in [0, n_alpha] (n_alpha = PCL's out-of-range bin) or 0xFFFFFFFF when the guard
@@ -342,7 +380,7 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_phase(const BinParams &bp
     const bool split = phase_split(bp, c_s, q, cell);
     if (q >= bp.n_turn)  // the scene pair sits in the sliver between N_T and T: the literal form for every entry
         return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
-    const uint32_t ce = phase_cell(bp, u);
+    const uint32_t ce = filed_phase_cell(bp, alpha_m);  // the cell the table files the entry under
     uint32_t qp;
     if (split && ce != cell) {
         qp = q + (ce < cell ? 1u : 0u);
@@ -351,9 +389,21 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_phase(const BinParams &bp
         const uint32_t fmask = (1u << bp.fix_shift) - 1u;
         const uint32_t phi = phase_of_fix(bp, c_s) & fmask;
         const int d = (int)(u & fmask) - (int)phi;
-        if ((uint32_t)(d + (int)bp.phase_guard) < 2u * bp.phase_guard)
-            return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
-        qp = q + (d < 0 ? 1u : 0u);
+        bool settled = false;
+        if (split) {  // the kernel's first look: the entry word's sub-phase byte against the scene's own sub-phases
+            const uint32_t in = phi & ((1u << (bp.fix_shift - bp.cells_log2)) - 1u), sh = sub_phase_shift(bp);
+            const uint32_t sub_lo = (in - bp.phase_guard) >> sh, span = ((in + bp.phase_guard - 1u) >> sh) - sub_lo;
+            const uint32_t rel = sub_phase(bp, u, ce) - sub_lo;
+            if (rel > span) {
+                qp = q + ((int)rel > (int)span ? 0u : 1u);
+                settled = true;
+            }
+        }
+        if (!settled) {
+            if ((uint32_t)(d + (int)bp.phase_guard) < 2u * bp.phase_guard)
+                return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
+            qp = q + (d < 0 ? 1u : 0u);
+        }
     }
     // the kernel's own integer path, address arithmetic included (pitch 32, row 5)
     const uint32_t pitch = 32u, unit = 4u * pitch;
