@@ -30,6 +30,7 @@
 // distinct bank conflict degree of the 32 reductions; HBM sees the table and the scene once.
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 #include "ppf_common.cuh"
 
@@ -48,6 +49,11 @@ constexpr int VOTE_THREADS_LARGE = 1024;
 #define B200PPF_OWN_UNROLL 4
 #endif
 constexpr int OWN_UNROLL = B200PPF_OWN_UNROLL;  // steps of 32 entries in flight in the scene phase's own cell
+#ifndef B200PPF_OWN_SUB_MIN
+#define B200PPF_OWN_SUB_MIN 96
+#endif
+constexpr uint32_t OWN_SUB_MIN = B200PPF_OWN_SUB_MIN;  // shorter own cells are compared in full (config 2: ~10 entries per cell)
+constexpr int FULL_UNROLL = 2;  // steps in flight of the full comparison
 #ifndef B200PPF_CAND_CAP
 #define B200PPF_CAND_CAP 2048
 #endif
@@ -401,19 +407,20 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                         // the scene phase the literal form decides.  32 entries per step, two steps in flight.
                         const uint32_t guard2 = 2u * a.bp.phase_guard, phi_g = wi.phi - a.bp.phase_guard;
                         const uint32_t c_lo = wi.c_below, c_hi = wi.c_below - unit;
-                        if (wi.sub_range) {
+                        if (wi.sub_range && e_end >= OWN_SUB_MIN) {
                             // the scene phase's own cell by sub-phase: rel = (entry's sub-phase) - sub_lo.  rel > span
                             // (unsigned) = outside the scene's own sub-phases, and then the sign of rel tells the side.
                             const uint32_t sub_lo = wi.sub_range & 0xFFu, span = ((wi.sub_range >> 8) & 0xFFu) - sub_lo;
                             // The increment stays the +1 form (ATOMS.POPC.INC): the entries of one model row are adjacent
                             // in the cell, and lanes of one instruction that hit the same word are counted in one pass —
                             // adding the decision as a value (ATOMS.ADD) serialises them and measured 2 % slower.
-                            auto own_step = [&](const uint32_t k0, const bool tail) {
-                                uint32_t w[OWN_UNROLL], v[OWN_UNROLL], settled = 0;
+                            auto own_step = [&](auto steps, const uint32_t k0, const bool tail) {
+                                constexpr int U = decltype(steps)::value;
+                                uint32_t w[U], v[U], settled = 0;
 #pragma unroll
-                                for (int u = 0; u < OWN_UNROLL; ++u) w[u] = __ldg(wp + k0 + u * 32);
+                                for (int u = 0; u < U; ++u) w[u] = __ldg(wp + k0 + u * 32);
 #pragma unroll
-                                for (int u = 0; u < OWN_UNROLL; ++u) {
+                                for (int u = 0; u < U; ++u) {
                                     const uint32_t rel = (w[u] >> 24) - sub_lo;
                                     const bool past = tail && k0 + u * 32 >= e_end;
                                     v[u] = (rel > span && !past) ? 1u : 0u;
@@ -421,9 +428,9 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                                     if (v[u]) red_shared_inc(acc_addr + min(t, t + wrap_bytes));
                                     settled += past ? 1u : v[u];
                                 }
-                                if (__any_sync(0xFFFFFFFFu, settled != OWN_UNROLL)) {  // ~1 entry in 256: the full comparison
+                                if (__any_sync(0xFFFFFFFFu, settled != U)) {  // ~1 entry in 256: the full comparison
 #pragma unroll
-                                    for (int u = 0; u < OWN_UNROLL; ++u)
+                                    for (int u = 0; u < U; ++u)
                                         if (!v[u] && !(tail && k0 + u * 32 >= e_end)) {
                                             const uint32_t pu = __umulhi(__ldg(ap + k0 + u * 32), a.bp.fix_mul);
                                             const uint32_t dg = (pu & fmask) - phi_g;
@@ -438,22 +445,23 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                                 }
                             };
                             uint32_t k0 = lane;
-                            for (; k0 - lane + 32 * OWN_UNROLL <= e_end; k0 += 32 * OWN_UNROLL) own_step(k0, false);  // warp-uniform
-                            if (k0 - lane < e_end) own_step(k0, true);
+                            for (; k0 - lane + 32 * OWN_UNROLL <= e_end; k0 += 32 * OWN_UNROLL)  // warp-uniform
+                                own_step(std::integral_constant<int, OWN_UNROLL>(), k0, false);
+                            for (; k0 - lane < e_end; k0 += 32) own_step(std::integral_constant<int, 1>(), k0, true);
                         } else
                         // the scene phase sits on a cell edge and the whole bucket is compared in full:
                         // dg = (entry phase in its cell) - (scene phase) + guard.  Outside [0, 2 guard) the comparison is
                         // safe: dg negative as a signed number = the entry lies below the scene phase and shifts one more.
-                        for (uint32_t k0 = lane; k0 - lane < e_end; k0 += 32 * OWN_UNROLL) {  // warp-uniform
-                            uint32_t w[OWN_UNROLL], pu[OWN_UNROLL];
+                        for (uint32_t k0 = lane; k0 - lane < e_end; k0 += 32 * FULL_UNROLL) {  // warp-uniform
+                            uint32_t w[FULL_UNROLL], pu[FULL_UNROLL];
 #pragma unroll
-                            for (int u = 0; u < OWN_UNROLL; ++u) {
+                            for (int u = 0; u < FULL_UNROLL; ++u) {
                                 w[u] = __ldg(wp + k0 + u * 32) & HOT_MASK;
                                 pu[u] = __ldg(ap + k0 + u * 32);
                             }
                             bool risky = false;
 #pragma unroll
-                            for (int u = 0; u < OWN_UNROLL; ++u) {
+                            for (int u = 0; u < FULL_UNROLL; ++u) {
                                 pu[u] = __umulhi(pu[u], a.bp.fix_mul);
                                 const uint32_t dg = (pu[u] & fmask) - phi_g;
                                 const uint32_t t = w[u] - ((int)dg >= 0 ? c_hi : c_lo);
@@ -462,7 +470,7 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                             }
                             if (__any_sync(0xFFFFFFFFu, risky)) {  // one entry in ~10^3 sits within the guard band
 #pragma unroll
-                                for (int u = 0; u < OWN_UNROLL; ++u)
+                                for (int u = 0; u < FULL_UNROLL; ++u)
                                     if ((pu[u] & fmask) - phi_g < guard2 && k0 + u * 32 < e_end)
                                         vote_exact<MODE>(a.bp, acc_addr, unit, w[u] - unit * phase_bin(a.bp, pu[u]),
                                                          __ldg(fp + k0 + u * 32), wi.alpha_s, st_skipped);
@@ -861,10 +869,11 @@ int launch_vote(b200ppf_ctx *ctx, const b200ppf_table *t, const b200ppf_cloud *s
         grid_dim = dim3((unsigned)(ctx->sm_count * (vote_threads(t) == VOTE_THREADS_SMALL ? B200PPF_VOTE_MINBLOCKS : 1)), 1);
     }
     cudaEventRecord(ctx->ev_vote[1], ctx->stream);  // grid build ends, voting starts
-    // heaviest neighbourhood first once the launch is several waves deep (see ref_cost_kernel)
+    // heaviest neighbourhood first once the launch is several waves deep and the buckets long enough for a task to take
+    // longer than the ordering does (see ref_cost_kernel; config 2's 295 k-entry table gains nothing from it)
     StreamBuf<uint32_t> cost(ctx), cost_alt(ctx), order(ctx), order_alt(ctx);
     a.ref_order = nullptr;
-    if (ref_count * t->info.n_slices >= 8 * (size_t)ctx->sm_count && !getenv("B200PPF_NO_TASK_ORDER")) {
+    if (ref_count * t->info.n_slices >= 8 * (size_t)ctx->sm_count && t->info.n_entries >= (1u << 21) && !getenv("B200PPF_NO_TASK_ORDER")) {
         PPF_CUDA(ctx, cost.alloc(ref_count));
         PPF_CUDA(ctx, cost_alt.alloc(ref_count));
         PPF_CUDA(ctx, order.alloc(ref_count));
