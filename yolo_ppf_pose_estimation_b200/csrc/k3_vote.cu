@@ -128,6 +128,12 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return __shfl_xor_sync(0xFFFFFFFFu, v, o);
 }
 
+// keeps a loop-invariant value in a register (an opaque move the compiler cannot rematerialise)
+__device__ __forceinline__ uint32_t pin_register(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
 // shared-memory increment without a return value (ATOMS.POPC.INC on the CTA's shared window)
 __device__ __forceinline__ void red_shared_inc(uint32_t addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
@@ -408,6 +414,9 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                         const uint32_t guard2 = 2u * a.bp.phase_guard, phi_g = wi.phi - a.bp.phase_guard;
                         const uint32_t c_lo = wi.c_below, c_hi = wi.c_below - unit;
                         if (wi.sub_range && e_end >= OWN_SUB_MIN) {
+                            // pinned in registers: left to itself the compiler re-derives the accumulator base (S2UR of
+                            // the CTA id + three uniform ops) and c_hi inside every predicated increment
+                            const uint32_t acc_own = pin_register(acc_addr), c_hi_own = pin_register(c_hi);
                             // the scene phase's own cell by sub-phase: rel = (entry's sub-phase) - sub_lo.  rel > span
                             // (unsigned) = outside the scene's own sub-phases, and then the sign of rel tells the side.
                             const uint32_t sub_lo = wi.sub_range & 0xFFu, span = ((wi.sub_range >> 8) & 0xFFu) - sub_lo;
@@ -424,8 +433,8 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                                     const uint32_t rel = (w[u] >> 24) - sub_lo;
                                     const bool past = tail && k0 + u * 32 >= e_end;
                                     v[u] = (rel > span && !past) ? 1u : 0u;
-                                    const uint32_t t = (w[u] & HOT_MASK) - ((int)rel > (int)span ? c_hi : c_lo);
-                                    if (v[u]) red_shared_inc(acc_addr + min(t, t + wrap_bytes));
+                                    const uint32_t t = (w[u] & HOT_MASK) - ((int)rel > (int)span ? c_hi_own : c_lo);
+                                    if (v[u]) red_shared_inc(acc_own + min(t, t + wrap_bytes));
                                     settled += past ? 1u : v[u];
                                 }
                                 if (__any_sync(0xFFFFFFFFu, settled != U)) {  // ~1 entry in 256: the full comparison
