@@ -127,6 +127,40 @@ def test_constant_shift_binning_over_many_angle_steps():
             assert np.array_equal(fast, exact), (float(step), rule)
 
 
+def test_constant_shift_binning_at_phase_cell_edges():
+    """Entries whose alpha_m sits within a few ulps of a phase-cell edge are filed by an fp32 estimate that may name the
+    neighbouring cell; their sub-phase byte then saturates at that cell's first / last value.  Scene phases just outside
+    the guard band of the same edge, deeper inside the two cells, and in the entry's own sub-phase must all bin like PCL's
+    literal form (the first version of the sub-phase byte moved one vote in a million by one bin here; and the guard band
+    has to be circular: an entry at the very start of a bin and a scene phase at the very end of one are neighbours)."""
+    from yolo_ppf_pose_estimation_b200 import capi
+    rng = np.random.default_rng(23)
+    for k in (12, 30, 36, 90, 360):
+        step = np.float32(2 * np.pi / k)
+        st = float(step)
+        n = 120_000
+        B = rng.integers(0, k, n)
+        c = rng.integers(0, 17, n)  # 16 cells per bin: edges 0 ... 16
+        am = (-np.pi + st * (B + c / 16.0)).astype(np.float32)
+        am = (am.view(np.int32) + rng.integers(-6, 7, n).astype(np.int32)).view(np.float32)
+        q = rng.integers(0, k, n)
+        side = rng.choice([-1.0, 1.0], n)
+        eps = np.concatenate([np.full(n // 4, 4.3e-6), np.full(n // 4, 1.2e-5), rng.uniform(0, 5e-6, n // 4),
+                              rng.uniform(0, st / 16, n - 3 * (n // 4))])
+        rng.shuffle(eps)
+        a_s = st * (q + c / 16.0) + side * eps
+        a_s = ((a_s + np.pi) % (2 * np.pi) - np.pi).astype(np.float32)
+        ok = (np.abs(am) <= np.float32(3.14159274)) & (np.abs(a_s) <= np.float32(3.14159274))
+        # and scene phases in the entry's own sub-phase: a few 2^-12 bins around the entry's position
+        a_s2 = (st * (q + (B - B) + ((am.astype(np.float64) + np.pi) / st) % 1.0) + rng.uniform(-1, 1, n) * st * 2.0 ** -12)
+        a_s2 = ((a_s2 + np.pi) % (2 * np.pi) - np.pi).astype(np.float32)
+        AM = np.concatenate([am[ok], am[ok]])
+        AS = np.concatenate([a_s[ok], a_s2[ok]])
+        for rule in (0, 1, 2):
+            fast, exact = capi.debug_alpha_bins(AM, AS, step, 0, nalpha_rule=rule)
+            assert np.array_equal(fast, exact), (k, rule, int((fast != exact).sum()))
+
+
 def test_synthetic_clouds():
     from yolo_ppf_pose_estimation_b200 import synth
     m = synth.synth_model(5000, 1)

@@ -474,13 +474,15 @@ __device__ __forceinline__ void vote_task(const VoteArgs &a, const uint32_t ref_
                                 pu[u] = __umulhi(pu[u], a.bp.fix_mul);
                                 const uint32_t dg = (pu[u] & fmask) - phi_g;
                                 const uint32_t t = w[u] - ((int)dg >= 0 ? c_hi : c_lo);
-                                red_shared_inc_if_ge_lt(acc_addr + min(t, t + wrap_bytes), dg, guard2, k0 + u * 32, e_end);
-                                risky |= dg < guard2 && k0 + u * 32 < e_end;
+                                // the guard band is circular: with the scene phase within the guard of a bin edge (the
+                                // whole bucket is here then) an entry just across that edge is as close as one beside it
+                                red_shared_inc_if_ge_lt(acc_addr + min(t, t + wrap_bytes), dg & fmask, guard2, k0 + u * 32, e_end);
+                                risky |= (dg & fmask) < guard2 && k0 + u * 32 < e_end;
                             }
                             if (__any_sync(0xFFFFFFFFu, risky)) {  // one entry in ~10^3 sits within the guard band
 #pragma unroll
                                 for (int u = 0; u < FULL_UNROLL; ++u)
-                                    if ((pu[u] & fmask) - phi_g < guard2 && k0 + u * 32 < e_end)
+                                    if ((((pu[u] & fmask) - phi_g) & fmask) < guard2 && k0 + u * 32 < e_end)
                                         vote_exact<MODE>(a.bp, acc_addr, unit, w[u] - unit * phase_bin(a.bp, pu[u]),
                                                          __ldg(fp + k0 + u * 32), wi.alpha_s, st_skipped);
                             }

@@ -400,7 +400,7 @@ __host__ __device__ __forceinline__ uint32_t alpha_bin_phase(const BinParams &bp
             }
         }
         if (!settled) {
-            if ((uint32_t)(d + (int)bp.phase_guard) < 2u * bp.phase_guard)
+            if (((uint32_t)(d + (int)bp.phase_guard) & fmask) < 2u * bp.phase_guard)  // circular: across a bin edge too
                 return alpha_bin_exact(ALPHA_MODE_A, bp.angle_step, bp.n_alpha, bp.overflow_bin, alpha_m, alpha_s);
             qp = q + (d < 0 ? 1u : 0u);
         }
