@@ -390,6 +390,19 @@ def icp_refine(model, scene, poses, max_iterations=100, tolerance=0.005, rejecti
     return P, res, int(iters.value)
 
 
+def solve6(N, g):
+    """the ICP's minimum-norm solve of the 6 x 6 Gram system (icp_oracle.cpp solve6)"""
+    N = np.ascontiguousarray(np.asarray(N, np.float64).reshape(6, 6)).copy()
+    g = np.ascontiguousarray(np.asarray(g, np.float64).reshape(6)).copy()
+    x = np.zeros(6, np.float64)
+    L = lib()
+    L.oracle_icp_solve6.restype = C.c_int
+    L.oracle_icp_solve6.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    if L.oracle_icp_solve6(_p(N), _p(g), _p(x)) != 0:
+        raise RuntimeError("oracle_icp_solve6 failed")
+    return x
+
+
 # ---- scene pre-processing (prep_oracle.cpp): VoxelGrid, StatisticalOutlierRemoval, NormalEstimationOMP -----------
 COV_SHIFTED, COV_RAW = 0, 1  # computeMeanAndCovarianceMatrix of PCL >= 1.12 / PCL 1.8-1.11
 

@@ -12,8 +12,9 @@
  *     tolerance * (L+1)^2 and max_iterations / (L+1) iterations;
  *   - one iteration: nearest scene sample of every (moved) model sample (squared distances, as FLANN
  *     reports them); robust rejection at median + scale * 1.48257968 * MAD; of several model samples that
- *     chose the same scene sample the closest survives; point-to-plane least squares, linearised about
- *     the level's un-moved samples, gives (roll, pitch, yaw, t) -> PoseX = [Rx*Ry*Rz | t];
+ *     chose the same scene sample the closest survives; point-to-plane least squares (minimum-norm solution, as
+ *     cv::solve(DECOMP_SVD) gives it), linearised about the level's un-moved samples, gives (roll, pitch, yaw, t)
+ *     -> PoseX = [Rx*Ry*Rz | t];
  *     error = || [Src_Match - Dst_Match] ||_F over all six columns / samples; stop when its ratio to the
  *     previous error is within 1 +- tolerance;
  *   - pose <- PoseX * pose per level; the normalisation is undone at the end.
@@ -185,26 +186,120 @@ float rejection_threshold(const std::vector<float> &r, float scale) {
     return scale * s + med;
 }
 
-/* solve the 6x6 normal equations (the original solves A x = b with cv::solve(DECOMP_SVD): same minimiser) */
-bool solve6(double A[36], double b[6], double x[6]) {
-    int perm[6] = {0, 1, 2, 3, 4, 5};
-    for (int c = 0; c < 6; ++c) {
-        int piv = c;
-        for (int r = c + 1; r < 6; ++r)
-            if (std::fabs(A[perm[r] * 6 + c]) > std::fabs(A[perm[piv] * 6 + c])) piv = r;
-        std::swap(perm[c], perm[piv]);
-        const double d = A[perm[c] * 6 + c];
-        if (!(std::fabs(d) > 1e-300)) return false;
-        for (int r = c + 1; r < 6; ++r) {
-            const double f = A[perm[r] * 6 + c] / d;
-            for (int k = c; k < 6; ++k) A[perm[r] * 6 + k] -= f * A[perm[c] * 6 + k];
-            b[perm[r]] -= f * b[perm[c]];
+/* The original solves the n x 6 system A x = b with cv::solve(DECOMP_SVD): the least-squares solution of MINIMUM NORM, which
+ * is what keeps the coarsest pyramid levels of a small cloud sane — with fewer than six surviving correspondences (the
+ * reference's own 681-point object has 4-5 samples at level 7) the system is rank-deficient, and an elimination of the
+ * normal equations divides by rounding noise and sends the pose metres away.  The same solution from the 6 x 6 Gram matrix
+ * N = A^T A, g = A^T b:  N = V diag(l) V^T by cyclic Jacobi rotations,  x = sum over l_i > cut of v_i (v_i . g) / l_i.
+ * cut = 1e-12 * l_max: singular values below 1e-6 of the largest count as zero (the SVD of A itself would resolve them
+ * down to ~1e-15; a Gram matrix cannot, and a direction that weak is unobservable in float32 point data anyway). */
+/* the 15 index pairs of a sweep as 5 rounds of 3 disjoint pairs: the three rotations of a round touch different rows and
+ * columns, so the device evaluates their (long, dependent) divide / square-root chains side by side.  Columns of all three
+ * first, then rows of all three — in that order here too, so that both sides round alike. */
+static const int JACOBI_ROUNDS[5][3][2] = {{{0, 5}, {1, 4}, {2, 3}}, {{1, 5}, {0, 2}, {3, 4}}, {{2, 5}, {1, 3}, {0, 4}},
+                                           {{3, 5}, {2, 4}, {0, 1}}, {{4, 5}, {0, 3}, {1, 2}}};
+
+bool solve6_min_norm(double A[36], double b[6], double x[6]) {
+    double V[36];
+    for (int k = 0; k < 36; ++k) V[k] = 0.0;
+    for (int k = 0; k < 6; ++k) V[k * 6 + k] = 1.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < 6; ++p) {
+            diag += std::fabs(A[p * 6 + p]);
+            for (int q = p + 1; q < 6; ++q) off += std::fabs(A[p * 6 + q]);
+        }
+        if (!(off > 1e-300) || off <= 1e-18 * diag) break;
+        for (int round = 0; round < 5; ++round) {
+            double c[3], sn[3];
+            for (int u = 0; u < 3; ++u) {  // the three rotations, from the matrix as the round finds it
+                const int p = JACOBI_ROUNDS[round][u][0], q = JACOBI_ROUNDS[round][u][1];
+                const double apq = A[p * 6 + q];
+                if (apq == 0.0) {
+                    c[u] = 1.0;
+                    sn[u] = 0.0;
+                    continue;
+                }
+                const double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                c[u] = 1.0 / std::sqrt(t * t + 1.0);
+                sn[u] = t * c[u];
+            }
+            for (int u = 0; u < 3; ++u) {  // columns p, q of A and V
+                const int p = JACOBI_ROUNDS[round][u][0], q = JACOBI_ROUNDS[round][u][1];
+                for (int k = 0; k < 6; ++k) {
+                    const double akp = A[k * 6 + p], akq = A[k * 6 + q];
+                    A[k * 6 + p] = c[u] * akp - sn[u] * akq;
+                    A[k * 6 + q] = sn[u] * akp + c[u] * akq;
+                    const double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
+                    V[k * 6 + p] = c[u] * vkp - sn[u] * vkq;
+                    V[k * 6 + q] = sn[u] * vkp + c[u] * vkq;
+                }
+            }
+            for (int u = 0; u < 3; ++u) {  // rows p, q of A
+                const int p = JACOBI_ROUNDS[round][u][0], q = JACOBI_ROUNDS[round][u][1];
+                for (int k = 0; k < 6; ++k) {
+                    const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+                    A[p * 6 + k] = c[u] * apk - sn[u] * aqk;
+                    A[q * 6 + k] = sn[u] * apk + c[u] * aqk;
+                }
+            }
         }
     }
+    double lmax = 0.0;
+    for (int k = 0; k < 6; ++k) lmax = std::fmax(lmax, A[k * 6 + k]);
+    if (!(lmax > 0.0)) return false;
+    const double cut = 1e-12 * lmax;
+    for (int r = 0; r < 6; ++r) x[r] = 0.0;
+    for (int k = 0; k < 6; ++k) {
+        const double l = A[k * 6 + k];
+        if (!(l > cut)) continue;
+        double proj = 0.0;
+        for (int r = 0; r < 6; ++r) proj += V[r * 6 + k] * b[r];
+        proj /= l;
+        for (int r = 0; r < 6; ++r) x[r] += V[r * 6 + k] * proj;
+    }
+    for (int c = 0; c < 6; ++c)
+        if (!std::isfinite(x[c])) return false;
+    return true;
+}
+
+/* Fast path: the elimination of round 1 (partial pivoting) while every pivot is at least 1e-9 of the largest diagonal
+ * entry — then the system has full rank and the least-squares solution is the minimum-norm one; otherwise (fewer than
+ * six independent correspondences) the Jacobi form above.  Both implementations take the same branch on the same numbers. */
+bool solve6(double A[36], double b[6], double x[6]) {
+    double E[36], g[6], dmax = 0.0;
+    for (int k = 0; k < 36; ++k) E[k] = A[k];
+    for (int k = 0; k < 6; ++k) {
+        g[k] = b[k];
+        dmax = std::fmax(dmax, std::fabs(A[k * 6 + k]));
+    }
+    const double floor_pivot = 1e-9 * dmax;
+    int perm[6] = {0, 1, 2, 3, 4, 5};
+    bool full_rank = dmax > 0.0;
+    for (int c = 0; c < 6 && full_rank; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (std::fabs(E[perm[r] * 6 + c]) > std::fabs(E[perm[piv] * 6 + c])) piv = r;
+        const int t = perm[c];
+        perm[c] = perm[piv];
+        perm[piv] = t;
+        const double d = E[perm[c] * 6 + c];
+        if (!(std::fabs(d) > floor_pivot)) {
+            full_rank = false;
+            break;
+        }
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = E[perm[r] * 6 + c] / d;
+            for (int k = c; k < 6; ++k) E[perm[r] * 6 + k] -= f * E[perm[c] * 6 + k];
+            g[perm[r]] -= f * g[perm[c]];
+        }
+    }
+    if (!full_rank) return solve6_min_norm(A, b, x);
     for (int c = 5; c >= 0; --c) {
-        double s = b[perm[c]];
-        for (int k = c + 1; k < 6; ++k) s -= A[perm[c] * 6 + k] * x[k];
-        x[c] = s / A[perm[c] * 6 + c];
+        double s = g[perm[c]];
+        for (int k = c + 1; k < 6; ++k) s -= E[perm[c] * 6 + k] * x[k];
+        x[c] = s / E[perm[c] * 6 + c];
     }
     for (int c = 0; c < 6; ++c)
         if (!std::isfinite(x[c])) return false;
@@ -364,3 +459,6 @@ extern "C" int oracle_icp_refine(const float *model, size_t n_model, const float
     }
     return 0;
 }
+
+/* the minimum-norm solve alone (tests): N 6x6 row-major (destroyed), g[6] -> x[6]; 0 on success */
+extern "C" int oracle_icp_solve6(double *N, double *g, double *x) { return solve6(N, g, x) ? 0 : -1; }

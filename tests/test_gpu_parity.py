@@ -985,6 +985,23 @@ def test_k6_icp_vs_oracle(ctx, oracle):
         assert dt < 1e-4 and dr < 0.02, (k, dt, dr)
 
 
+def test_k6_icp_on_the_reference_object(ctx, oracle, oracle_bottle, bottle, scene_crop, dev_bottle, dev_crop):
+    """The reference's own sizes (543-point model, 934-point crop, 8 levels: 4 samples at the coarsest, fewer correspondences
+    than unknowns): the minimum-norm solve keeps both sides on the same trajectory where the elimination of round 1 let
+    them fly apart (metres) — device and oracle end at the same pose, near the PPF pose they started from."""
+    _, hm = oracle_bottle
+    _, poses, votes, _ = hm.register(bottle, scene_crop, ref_rate=5, n_threads=4)
+    starts = poses[:3].astype(np.float64)
+    P, res, it = ctx.icp_refine(dev_bottle, dev_crop, starts)
+    R, rres, rit = oracle.icp_refine(bottle, scene_crop, starts)
+    c = np.append(bottle[:, :3].mean(axis=0).astype(np.float64), 1.0)
+    assert (res < 1.0).all() and (rres < 1.0).all()                      # no 1e10 sentinel on either side
+    assert np.linalg.norm((R[0] @ c - starts[0] @ c)[:3]) < 0.02        # the best pose stays on the object
+    for k in range(len(starts)):
+        moved = np.linalg.norm((P[k] @ c - R[k] @ c)[:3])
+        assert moved < 1e-3 and abs(res[k] - rres[k]) <= 1e-3 * max(1.0, rres[k]), (k, moved, res[k], rres[k])
+
+
 def test_cpp_pcl_shim_end_to_end(tmp_path, ctx, bottle, scene_crop, dev_bottle, dev_crop, oracle_bottle):
     """tests/cpp/pcl_shim_example.cpp — PPFEstimation::compute -> PPFHashMapSearch::setInputFeatureCloud
     -> PPFRegistration::align through include/pcl_compat — gives the C-ABI result."""

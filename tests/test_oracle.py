@@ -368,3 +368,30 @@ def test_icp_oracle_recovers_ground_truth(oracle):
         dt = np.linalg.norm(P[k][:3, 3] - G[:3, 3])
         da = np.degrees(np.arccos(np.clip(P[k][:3, 2] @ G[:3, 2], -1, 1)))   # surface of revolution: axis only
         assert dt < 5e-4 and da < 0.3, (k, dt, da)
+
+
+def test_icp_on_the_reference_object_stays_put_at_the_coarse_levels(oracle, oracle_bottle, bottle, scene_crop):
+    """The reference's own numbers: ICP(100, 0.005, 2.5, 8) on the 543-point bottle and the 934-point YOLO crop leaves 4 model
+    samples at the coarsest level — fewer correspondences than unknowns.  cv::solve(DECOMP_SVD) answers with the minimum-norm
+    update there; an elimination of the normal equations divides by rounding noise (round 1 of this repository: residual
+    sentinel 1e10 or a pose metres away, depending on the number of levels).  No depth may end in the sentinel, the
+    reference's own depth (8) and the full-rank depths must end within 2 cm of the PPF pose they started from."""
+    _, hm = oracle_bottle
+    _, poses, votes, _ = hm.register(bottle, scene_crop, ref_rate=5, n_threads=4)
+    start = poses[:1].astype(np.float64)
+    for levels in range(1, 9):
+        P, res, it = oracle.icp_refine(bottle, scene_crop, start, num_levels=levels)
+        assert res[0] < 0.2 and it > 0, (levels, res)
+        c = np.append(bottle[:, :3].mean(axis=0).astype(np.float64), 1.0)  # where the object ends up (the bottle is a
+        moved = np.linalg.norm((P[0] @ c - start[0] @ c)[:3])                 # surface of revolution: t alone says little)
+        assert moved < (0.02 if levels in (1, 2, 3, 4, 5, 8) else 0.5), (levels, moved)  # 6, 7: 16 / 8 samples still wander
+    # full-rank systems: the minimum-norm solution IS the least-squares solution (synthetic case of the test above unchanged)
+    A = np.random.default_rng(3).normal(size=(40, 6))
+    b = A @ np.arange(1.0, 7.0)
+    x = oracle.solve6(A.T @ A, A.T @ b)
+    assert np.allclose(x, np.arange(1.0, 7.0), rtol=1e-10)
+    # rank 3 (three correspondences): the pseudo-inverse solution, not noise / noise
+    A3 = A[:3]
+    x3 = oracle.solve6(A3.T @ A3, A3.T @ b[:3])
+    assert np.allclose(x3, np.linalg.pinv(A3) @ b[:3], rtol=1e-8, atol=1e-10)
+

@@ -21,7 +21,8 @@
 //   robust threshold  median + scale * 1.4826 * MAD    two exact radix selects (4 x 8-bit shared histograms)
 //   one model sample per scene sample                  64-bit atomicMin on (distance bits, model sample)
 //   point-to-plane normal equations                    27 doubles reduced by shuffles + shared memory
-//   6 x 6 solve, Euler -> pose, error, stop test       thread 0, double precision
+//   6 x 6 minimum-norm solve                           first warp (elimination on lane 0 when the rank is full)
+//   Euler -> pose, error, stop test                    thread 0, double precision
 //   move the level's samples                           all threads
 // Arithmetic follows the original operation for operation (float where cv::Mat is CV_32F, double elsewhere,
 // -fmad=false), so the only differences are libm's double sin/cos and the order of the reductions.
@@ -36,7 +37,8 @@ namespace {
 namespace cg = cooperative_groups;
 
 constexpr int ICP_THREADS = 1024;
-constexpr int ICP_CLUSTER = 8;  // CTAs (SMs) per pose
+constexpr int ICP_CLUSTER = 8;  // CTAs (SMs) per pose, at most
+constexpr uint32_t ICP_BRUTE_MAX = 1024;  // levels with at most this many scene samples search them all from shared memory
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr uint32_t ICP_CELLS_MAX = 1u << 16;  // grid cells per level (scanned by the CTA)
 constexpr int NEQ = 29;                       // 21 (upper A) + 6 (b) + 1 (squared error) + 1 (matches)
@@ -139,31 +141,132 @@ __device__ __forceinline__ void mat4_mul(const double *a, const double *b, doubl
         }
 }
 
-__device__ bool solve6(double *A, double *b, double *x) {
-    int perm[6] = {0, 1, 2, 3, 4, 5};
-    for (int c = 0; c < 6; ++c) {
-        int piv = c;
-        for (int r = c + 1; r < 6; ++r)
-            if (fabs(A[perm[r] * 6 + c]) > fabs(A[perm[piv] * 6 + c])) piv = r;
-        const int t = perm[c];
-        perm[c] = perm[piv];
-        perm[piv] = t;
-        const double d = A[perm[c] * 6 + c];
-        if (!(fabs(d) > 1e-300)) return false;
-        for (int r = c + 1; r < 6; ++r) {
-            const double f = A[perm[r] * 6 + c] / d;
-            for (int k = c; k < 6; ++k) A[perm[r] * 6 + k] -= f * A[perm[c] * 6 + k];
-            b[perm[r]] -= f * b[perm[c]];
+// Minimum-norm least squares from the 6 x 6 Gram matrix (what cv::solve(DECOMP_SVD) returns for the n x 6 system): cyclic
+// Jacobi rotations, eigenvalues below 1e-12 of the largest dropped.  With fewer than six surviving correspondences (the
+// coarsest levels of a small cloud) an elimination would divide by rounding noise; this stays put in the directions the
+// data do not constrain.  Operation for operation the solve the tests' CPU checker performs, run by one warp on shared
+// memory.  The 15 index pairs of a sweep are taken as 5 rounds of 3 disjoint pairs (the same table as the checker's):
+// lanes 0-5, 6-11 and 12-17 evaluate the three rotations of a round side by side — the divide / square-root chain of a
+// rotation is five dependent double-precision operations, ~0.4 us, and a sweep is five of them instead of fifteen — and
+// lane 6 u + k takes index k of rotation u's column updates and then of its row updates; the convergence sums are
+// evaluated redundantly by every lane in the checker's order.
+__constant__ int JACOBI_ROUNDS[5][3][2] = {{{0, 5}, {1, 4}, {2, 3}}, {{1, 5}, {0, 2}, {3, 4}}, {{2, 5}, {1, 3}, {0, 4}},
+                                           {{3, 5}, {2, 4}, {0, 1}}, {{4, 5}, {0, 3}, {1, 2}}};
+
+__device__ bool solve6_min_norm_warp(double *A, double *V, const double *b, double *x, int lane) {
+    if (lane < 6)
+        for (int k = 0; k < 6; ++k) V[lane * 6 + k] = k == lane ? 1.0 : 0.0;
+    __syncwarp();
+    const int u = lane < 18 ? lane / 6 : 0, k = lane % 6;  // lanes 18-31 shadow pair 0 and write nothing
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < 6; ++p) {
+            diag += fabs(A[p * 6 + p]);
+            for (int q = p + 1; q < 6; ++q) off += fabs(A[p * 6 + q]);
+        }
+        if (!(off > 1e-300) || off <= 1e-18 * diag) break;  // warp-uniform
+        for (int round = 0; round < 5; ++round) {
+            const int p = JACOBI_ROUNDS[round][u][0], q = JACOBI_ROUNDS[round][u][1];
+            const double apq = A[p * 6 + q];
+            double c = 1.0, sn = 0.0;
+            if (apq != 0.0) {
+                const double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                c = 1.0 / sqrt(t * t + 1.0);
+                sn = t * c;
+            }
+            __syncwarp();  // every lane has read its rotation's inputs
+            if (lane < 18) {  // columns p, q of A and V, row k
+                const double akp = A[k * 6 + p], akq = A[k * 6 + q];
+                A[k * 6 + p] = c * akp - sn * akq;
+                A[k * 6 + q] = sn * akp + c * akq;
+                const double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
+                V[k * 6 + p] = c * vkp - sn * vkq;
+                V[k * 6 + q] = sn * vkp + c * vkq;
+            }
+            __syncwarp();
+            if (lane < 18) {  // rows p, q of A, column k
+                const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+                A[p * 6 + k] = c * apk - sn * aqk;
+                A[q * 6 + k] = sn * apk + c * aqk;
+            }
+            __syncwarp();
         }
     }
-    for (int c = 5; c >= 0; --c) {
-        double s = b[perm[c]];
-        for (int k = c + 1; k < 6; ++k) s -= A[perm[c] * 6 + k] * x[k];
-        x[c] = s / A[perm[c] * 6 + c];
+    bool ok = true;
+    if (lane == 0) {
+        double lmax = 0.0;
+        for (int k = 0; k < 6; ++k) lmax = fmax(lmax, A[k * 6 + k]);
+        ok = lmax > 0.0;
+        if (ok) {
+            const double cut = 1e-12 * lmax;
+            for (int r = 0; r < 6; ++r) x[r] = 0.0;
+            for (int k = 0; k < 6; ++k) {
+                const double l = A[k * 6 + k];
+                if (!(l > cut)) continue;
+                double proj = 0.0;
+                for (int r = 0; r < 6; ++r) proj += V[r * 6 + k] * b[r];
+                proj /= l;
+                for (int r = 0; r < 6; ++r) x[r] += V[r * 6 + k] * proj;
+            }
+            for (int c = 0; c < 6; ++c)
+                if (!isfinite(x[c])) ok = false;
+        }
     }
-    for (int c = 0; c < 6; ++c)
-        if (!isfinite(x[c])) return false;
-    return true;
+    return __shfl_sync(0xFFFFFFFFu, ok ? 1 : 0, 0) != 0;
+}
+
+// Fast path (lane 0): the elimination of round 1 (partial pivoting) while every pivot is at least 1e-9 of the largest
+// diagonal entry — then the system has full rank and the least-squares solution is the minimum-norm one; otherwise (fewer
+// than six independent correspondences) the Jacobi form above.  Both implementations take the same branch on the same
+// numbers.  Called by the whole first warp; A, V, b, x live in shared memory.
+__device__ bool solve6_warp(double *A, double *V, const double *b, double *x, int lane) {
+    int state = 0;  // 0: rank-deficient, 1: solved, 2: failed
+    if (lane == 0) {
+        double E[36], g[6], dmax = 0.0;
+        for (int k = 0; k < 36; ++k) E[k] = A[k];
+        for (int k = 0; k < 6; ++k) {
+            g[k] = b[k];
+            dmax = fmax(dmax, fabs(A[k * 6 + k]));
+        }
+        const double floor_pivot = 1e-9 * dmax;
+        int perm[6] = {0, 1, 2, 3, 4, 5};
+        bool full_rank = dmax > 0.0;
+        for (int c = 0; c < 6 && full_rank; ++c) {
+            int piv = c;
+            for (int r = c + 1; r < 6; ++r)
+                if (fabs(E[perm[r] * 6 + c]) > fabs(E[perm[piv] * 6 + c])) piv = r;
+            const int t = perm[c];
+            perm[c] = perm[piv];
+            perm[piv] = t;
+            const double d = E[perm[c] * 6 + c];
+            if (!(fabs(d) > floor_pivot)) {
+                full_rank = false;
+                break;
+            }
+            for (int r = c + 1; r < 6; ++r) {
+                const double f = E[perm[r] * 6 + c] / d;
+                for (int k = c; k < 6; ++k) E[perm[r] * 6 + k] -= f * E[perm[c] * 6 + k];
+                g[perm[r]] -= f * g[perm[c]];
+            }
+        }
+        if (full_rank) {
+            double xs[6];
+            for (int c = 5; c >= 0; --c) {
+                double sacc = g[perm[c]];
+                for (int k = c + 1; k < 6; ++k) sacc -= E[perm[c] * 6 + k] * xs[k];
+                xs[c] = sacc / E[perm[c] * 6 + c];
+            }
+            state = 1;
+            for (int c = 0; c < 6; ++c) {
+                x[c] = xs[c];
+                if (!isfinite(xs[c])) state = 2;
+            }
+        }
+    }
+    state = __shfl_sync(0xFFFFFFFFu, state, 0);
+    if (state == 0) return solve6_min_norm_warp(A, V, b, x, lane);
+    return state == 1;
 }
 
 __device__ void pose_from_euler(const double *rpy, const double *t, double *P) {
@@ -230,6 +333,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
     __shared__ double s_red[ICP_WARPS][NEQ];
     __shared__ double s_part[NEQ], s_tot[NEQ];
     __shared__ double s_pose[16], s_posex[16], s_mean[3];
+    __shared__ double s_A[36], s_V[36], s_b6[6], s_x6[6];  // the 6 x 6 solve of the first warp
+    __shared__ float4 s_items[ICP_BRUTE_MAX];              // a small level's scene samples (x, y, z, index)
     __shared__ double s_scale, s_fold, s_fperc, s_fmin;
     __shared__ GridDev s_grid;
     __shared__ uint32_t s_hist[256], s_hist_tot[256], s_sel[2], s_carry;
@@ -390,6 +495,18 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
         __syncthreads();
         const GridDev g = s_grid;
         const uint32_t cells = (uint32_t)g.dim[0] * g.dim[1] * g.dim[2];
+        // A small level (the coarse levels of every cloud, every level of the reference's 681-point object) keeps its scene
+        // samples in shared memory and tests them all: a few microseconds per iteration, where walking the grid rows around
+        // a far-away previous match is a chain of ~700 dependent global loads (~0.2 ms per iteration, whatever the size).
+        // The nearest sample, lowest index on ties, is the same either way.
+        const bool brute = md <= ICP_BRUTE_MAX;
+        if (brute) {
+            for (uint32_t j = tid; j < md; j += ICP_THREADS) {
+                const float *q = dst + 6 * (size_t)j * step;
+                s_items[j] = make_float4(q[0], q[1], q[2], __uint_as_float(j));
+            }
+            __syncthreads();
+        } else {
         // ---- counting sort of the scene samples by cell (counts and fill by the cluster, scan by rank 0) -----------
         for (uint32_t c = first; c < cells; c += stride) cell_fill[c] = 0;
         __threadfence();
@@ -444,6 +561,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
         }
         __threadfence();
         cluster.sync();
+        }
 
         // ---- iterations --------------------------------------------------------------------------------------------
         for (;;) {
@@ -458,7 +576,19 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
                 const int cx = grid_coord(g, qx, 0), cy = grid_coord(g, qy, 1), cz = grid_coord(g, qz, 2);
                 int best = nn[i];
                 float best_d2 = 3.402823466e38f;
-                if (best >= 0) {
+                if (brute) {
+                    best = -1;
+                    for (uint32_t sidx = 0; sidx < md; ++sidx) {
+                        const float4 q = s_items[sidx];
+                        const float dx = qx - q.x, dy = qy - q.y, dz = qz - q.z;
+                        const float dd = dx * dx + dy * dy + dz * dz;
+                        const int j = (int)__float_as_uint(q.w);
+                        if (dd < best_d2 || (dd == best_d2 && j < best)) {
+                            best_d2 = dd;
+                            best = j;
+                        }
+                    }
+                } else if (best >= 0) {
                     // Seeded search: the previous iteration's (or level's) match bounds the distance, and only the
                     // cells that intersect the ball of that radius are visited — rows (z, y) and the x range inside
                     // a row are pruned with the current best, which only shrinks.  A sample whose true neighbour
@@ -586,30 +716,32 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_refine_kernel(const IcpArg
                 acc[28] += 1.0;
             }
             cluster_sum<NEQ>(cluster, acc, s_part, s_tot, s_red);
-            if (tid == 0) {
-                bool ok = s_tot[28] > 0.0;
-                double x[6];
-                if (ok) {
-                    double A[36], bb[6];
+            if (tid < 32) {  // the first warp solves; lane 0 does the scalar parts
+                if (tid == 0) {
                     int q = 0;
                     for (int r = 0; r < 6; ++r)
                         for (int c = r; c < 6; ++c) {
-                            A[r * 6 + c] = s_tot[q];
-                            A[c * 6 + r] = s_tot[q];
+                            s_A[r * 6 + c] = s_tot[q];
+                            s_A[c * 6 + r] = s_tot[q];
                             ++q;
                         }
-                    for (int r = 0; r < 6; ++r) bb[r] = s_tot[21 + r];
-                    ok = solve6(A, bb, x);
+                    for (int r = 0; r < 6; ++r) s_b6[r] = s_tot[21 + r];
                 }
-                if (ok) {
-                    pose_from_euler(x, x + 3, s_posex);
-                    const double fval = sqrt(s_tot[27]) / (double)m;
-                    s_fperc = fval / s_fold;
-                    s_fold = fval;
-                    if (fval < s_fmin) s_fmin = fval;
-                    ++s_iter;
+                __syncwarp();
+                bool ok = s_tot[28] > 0.0;
+                if (ok) ok = solve6_warp(s_A, s_V, s_b6, s_x6, (int)tid);
+                __syncwarp();
+                if (tid == 0) {
+                    if (ok) {
+                        pose_from_euler(s_x6, s_x6 + 3, s_posex);
+                        const double fval = sqrt(s_tot[27]) / (double)m;
+                        s_fperc = fval / s_fold;
+                        s_fold = fval;
+                        if (fval < s_fmin) s_fmin = fval;
+                        ++s_iter;
+                    }
+                    s_flag = ok ? 1 : 0;
                 }
-                s_flag = ok ? 1 : 0;
             }
             __syncthreads();
             if (!s_flag) break;
@@ -704,15 +836,21 @@ int k6_icp_refine(b200ppf_ctx *ctx, const b200ppf_cloud *model, const b200ppf_cl
     PPF_CUDA(ctx, cudaMemsetAsync(a.iterations, 0, sizeof(unsigned long long), ctx->stream));
     cudaEventRecord(ctx->ev[0], ctx->stream);
     {
-        // one cluster of ICP_CLUSTER CTAs per pose: grid (ICP_CLUSTER, n_poses), cluster dimension (ICP_CLUSTER, 1, 1)
+        // One cluster per pose: grid (csize, n_poses), cluster dimension (csize, 1, 1).  An iteration is a chain of ~20
+        // cluster-wide synchronisations around little arithmetic, so the cluster is only as large as the model needs:
+        // one CTA per 1 024 model points, at most ICP_CLUSTER (the reference's 543-point bottle runs in a single CTA,
+        // whose cluster barrier is a block barrier).
+        int csize = 1;
+        while (csize < ICP_CLUSTER && (size_t)csize * ICP_THREADS < model->n) csize *= 2;
+        if (const char *e = getenv("B200PPF_ICP_CLUSTER")) csize = std::max(1, std::min(ICP_CLUSTER, atoi(e)));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ICP_CLUSTER, (unsigned)P, 1);
+        cfg.gridDim = dim3((unsigned)csize, (unsigned)P, 1);
         cfg.blockDim = dim3(ICP_THREADS, 1, 1);
         cfg.dynamicSmemBytes = 0;
         cfg.stream = ctx->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = ICP_CLUSTER;
+        attr[0].val.clusterDim.x = (unsigned)csize;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
