@@ -15,8 +15,8 @@
 //   match    one CTA per reference point (persistent over the references): lanes compute pair features, the warp walks
 //            each lane's bucket together, votes are L2 reductions into the CTA's own M x numAngles accumulator, the peak is
 //            the first maximum in (model point, alpha index) order, the pose Tsg^-1 Rx(alpha) Tmg is assembled in double;
-//   cluster  the per-reference poses (a few hundred to a few thousand: the engine subsamples the scene) are sorted and
-//            assigned greedily on the host inside this library, as upstream does on one thread, then averaged.
+//   cluster  one CTA: the per-reference poses (a few hundred to a few thousand: the engine subsamples the scene) are ranked
+//            by votes, assigned greedily — each pose against all cluster leaders at once — and averaged (cv_cluster_kernel).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -507,7 +507,7 @@ struct DevGuard {
 };
 
 // the voting launch of match / match_S2B over the detector's sampled clouds
-int cv_vote(b200cv_detector *d, uint32_t step, uint32_t refs, uint32_t *acc_dump_host, uint32_t dump_ref) {
+int cv_vote(b200cv_detector *d, uint32_t step, uint32_t refs, uint32_t *acc_dump_host, uint32_t dump_ref, b200cv_pose **d_poses_out) {
     b200ppf_ctx *ctx = d->ctx;
     const int num_angles = (int)std::floor(2 * PI_D / d->angle_step);
     const size_t acc_len = d->m * (size_t)num_angles;
@@ -551,80 +551,180 @@ int cv_vote(b200cv_detector *d, uint32_t step, uint32_t refs, uint32_t *acc_dump
         PPF_CUDA(ctx, cudaMemcpyAsync(acc_dump_host, dump, acc_len * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->timings.vote_ms, ctx->ev[0], ctx->ev[1]);
+    if (d_poses_out) *d_poses_out = poses.release();  // the caller clusters them on the device and frees them
     return B200PPF_OK;
 }
 
 // PPF3DDetector::clusterPoses on the per-reference poses: sorted by votes (ties: reference order), each pose joins the
 // first cluster whose FIRST pose matches (|angle difference| < rotation threshold and |t difference| < position
-// threshold), clusters sorted by their vote sums, plain average of quaternions and translations
-void cv_cluster(const b200cv_detector *d, std::vector<b200cv_pose> &out, size_t *n_clusters) {
-    const std::vector<b200cv_pose> &poses = d->raw;
-    const size_t refs = poses.size();
-    std::vector<uint32_t> order(refs);
-    for (size_t k = 0; k < refs; ++k) order[k] = (uint32_t)k;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return poses[x].num_votes > poses[y].num_votes; });
-    std::vector<std::vector<uint32_t>> clusters;
-    std::vector<uint64_t> cluster_votes;
-    for (uint32_t k : order) {
-        const b200cv_pose &p = poses[k];
-        bool assigned = false;
-        for (size_t c = 0; c < clusters.size() && !assigned; ++c) {
-            const b200cv_pose &centre = poses[clusters[c][0]];
-            const double dv[3] = {centre.t[0] - p.t[0], centre.t[1] - p.t[1], centre.t[2] - p.t[2]};
-            const double dn = std::sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
-            const double phi = std::fabs(p.angle - centre.angle);
-            if (phi < d->rotation_threshold && dn < d->position_threshold) {
-                clusters[c].push_back(k);
-                cluster_votes[c] += p.num_votes;
-                assigned = true;
-            }
+// threshold), clusters sorted by their vote sums, plain average of quaternions and translations.
+// One CTA: the engine produces a few hundred to a few thousand poses per match, and upstream's greedy loop is sequential
+// in the poses — each step tests the pose against all cluster leaders in parallel and takes the lowest matching cluster.
+// Both sorts are rank counts (stable: ties keep reference / creation order); the sums of a cluster run over its members
+// in the order they joined, as upstream's loop adds them.
+constexpr int CV_CLUSTER_THREADS = 1024;
+struct CvClusterArgs {
+    const b200cv_pose *poses;  // per reference point
+    uint32_t n;
+    double position_threshold, rotation_threshold;
+    uint32_t *order;           // [n] sorted position -> pose
+    uint32_t *member_of;       // [n] sorted position -> cluster (creation index)
+    double4 *lead;             // [n] cluster -> (t, angle) of its first pose
+    uint32_t *lead_pose;       // [n] cluster -> its first pose
+    uint32_t *size;            // [n] members per cluster
+    unsigned long long *votes; // [n] vote sum per cluster
+    uint32_t *corder;          // [n] output position -> cluster
+    b200cv_pose *out;          // [n] clusters, best first
+    uint32_t *n_clusters;
+};
+
+__global__ void __launch_bounds__(CV_CLUSTER_THREADS) cv_cluster_kernel(const CvClusterArgs a) {
+    __shared__ uint32_t s_first, s_ncl;
+    const uint32_t tid = threadIdx.x, n = a.n;
+    // poses by votes, descending; ties in reference order
+    for (uint32_t i = tid; i < n; i += CV_CLUSTER_THREADS) {
+        const uint32_t v = a.poses[i].num_votes;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t w = a.poses[j].num_votes;
+            rank += (w > v || (w == v && j < i)) ? 1u : 0u;
         }
-        if (!assigned) {
-            clusters.push_back({k});
-            cluster_votes.push_back(p.num_votes);
-        }
+        a.order[rank] = i;
     }
-    std::vector<uint32_t> corder(clusters.size());
-    for (size_t c = 0; c < clusters.size(); ++c) corder[c] = (uint32_t)c;
-    std::stable_sort(corder.begin(), corder.end(), [&](uint32_t x, uint32_t y) { return cluster_votes[x] > cluster_votes[y]; });
-    out.clear();
-    for (size_t o = 0; o < clusters.size(); ++o) {
-        const auto &cl = clusters[corder[o]];
+    if (tid == 0) {
+        s_first = 0xFFFFFFFFu;
+        s_ncl = 0;
+    }
+    __syncthreads();
+    // the greedy assignment
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t pi = a.order[k];
+        const b200cv_pose &p = a.poses[pi];
+        const double px = p.t[0], py = p.t[1], pz = p.t[2], pa = p.angle;
+        const uint32_t ncl = s_ncl;
+        for (uint32_t c = tid; c < ncl; c += CV_CLUSTER_THREADS) {
+            const double4 l = a.lead[c];
+            const double dx = l.x - px, dy = l.y - py, dz = l.z - pz;
+            const double dn = sqrt(dx * dx + dy * dy + dz * dz);
+            const double phi = fabs(pa - l.w);
+            if (phi < a.rotation_threshold && dn < a.position_threshold) atomicMin(&s_first, c);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t c = s_first;
+            if (c == 0xFFFFFFFFu) {
+                c = ncl;
+                a.lead[c] = make_double4(px, py, pz, pa);
+                a.lead_pose[c] = pi;
+                a.size[c] = 0;
+                a.votes[c] = 0;
+                s_ncl = ncl + 1;
+            }
+            a.member_of[k] = c;
+            a.size[c] += 1;
+            a.votes[c] += p.num_votes;
+            s_first = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+    }
+    const uint32_t ncl = s_ncl;
+    if (tid == 0) *a.n_clusters = ncl;
+    // clusters by vote sum, descending; ties in creation order
+    for (uint32_t c = tid; c < ncl; c += CV_CLUSTER_THREADS) {
+        const unsigned long long v = a.votes[c];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < ncl; ++j) {
+            const unsigned long long w = a.votes[j];
+            rank += (w > v || (w == v && j < c)) ? 1u : 0u;
+        }
+        a.corder[rank] = c;
+    }
+    __syncthreads();
+    // averages (updatePoseQuat: the averaged quaternion normalised, then the rotation matrix)
+    for (uint32_t o = tid; o < ncl; o += CV_CLUSTER_THREADS) {
+        const uint32_t c = a.corder[o];
         double q[4] = {0, 0, 0, 0}, t[3] = {0, 0, 0};
-        for (uint32_t k : cl) {
-            for (int e = 0; e < 4; ++e) q[e] += poses[k].q[e];
-            for (int e = 0; e < 3; ++e) t[e] += poses[k].t[e];
+        for (uint32_t k = 0; k < n; ++k) {
+            if (a.member_of[k] != c) continue;
+            const b200cv_pose &m = a.poses[a.order[k]];
+            for (int e = 0; e < 4; ++e) q[e] += m.q[e];
+            for (int e = 0; e < 3; ++e) t[e] += m.t[e];
         }
-        const double inv = 1.0 / (double)cl.size();
-        for (double &v : q) v *= inv;
-        for (double &v : t) v *= inv;
+        const double inv = 1.0 / (double)a.size[c];
+        for (int e = 0; e < 4; ++e) q[e] *= inv;
+        for (int e = 0; e < 3; ++e) t[e] *= inv;
         b200cv_pose P;
-        memset(&P, 0, sizeof(P));
-        {   // updatePoseQuat: the averaged quaternion normalised, then the rotation matrix
-            const double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-            if (nq > 0)
-                for (double &v : q) v /= nq;
-            const double w = q[0], x = q[1], y = q[2], z = q[3];
-            double *R = P.pose;
-            R[0] = 1 - 2 * (y * y + z * z), R[1] = 2 * (x * y - z * w), R[2] = 2 * (x * z + y * w);
-            R[4] = 2 * (x * y + z * w), R[5] = 1 - 2 * (x * x + z * z), R[6] = 2 * (y * z - x * w);
-            R[8] = 2 * (x * z - y * w), R[9] = 2 * (y * z + x * w), R[10] = 1 - 2 * (x * x + y * y);
-            R[3] = t[0], R[7] = t[1], R[11] = t[2], R[15] = 1.0;
-        }
-        const double trace = P.pose[0] + P.pose[5] + P.pose[10];
-        if (std::fabs(trace - 3) <= CV_EPS) P.angle = 0;
-        else if (std::fabs(trace + 1) <= CV_EPS) P.angle = PI_D;
-        else P.angle = std::acos((trace - 1) / 2);
+        for (int e = 0; e < 16; ++e) P.pose[e] = 0.0;
+        const double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        if (nq > 0)
+            for (int e = 0; e < 4; ++e) q[e] /= nq;
+        const double w = q[0], x = q[1], y = q[2], z = q[3];
+        double *R = P.pose;
+        R[0] = 1 - 2 * (y * y + z * z), R[1] = 2 * (x * y - z * w), R[2] = 2 * (x * z + y * w);
+        R[4] = 2 * (x * y + z * w), R[5] = 1 - 2 * (x * x + z * z), R[6] = 2 * (y * z - x * w);
+        R[8] = 2 * (x * z - y * w), R[9] = 2 * (y * z + x * w), R[10] = 1 - 2 * (x * x + y * y);
+        R[3] = t[0], R[7] = t[1], R[11] = t[2], R[15] = 1.0;
+        const double trace = R[0] + R[5] + R[10];
+        if (fabs(trace - 3) <= CV_EPS) P.angle = 0;
+        else if (fabs(trace + 1) <= CV_EPS) P.angle = PI_D;
+        else P.angle = acos((trace - 1) / 2);
         for (int e = 0; e < 3; ++e) P.t[e] = t[e];
         for (int e = 0; e < 4; ++e) P.q[e] = q[e];
-        P.num_votes = (uint32_t)std::min<uint64_t>(cluster_votes[corder[o]], 0xFFFFFFFFull);
-        P.model_index = poses[cl[0]].model_index;
-        P.alpha = poses[cl[0]].alpha;
-        P.alpha_index = poses[cl[0]].alpha_index;
-        P.reference_index = poses[cl[0]].reference_index;
-        out.push_back(P);
+        const unsigned long long vs = a.votes[c];
+        P.num_votes = vs > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)vs;
+        const b200cv_pose &first = a.poses[a.lead_pose[c]];
+        P.model_index = first.model_index;
+        P.alpha = first.alpha;
+        P.residual = 0.0;
+        P.alpha_index = first.alpha_index;
+        P.reference_index = first.reference_index;
+        a.out[o] = P;
     }
-    if (n_clusters) *n_clusters = clusters.size();
+}
+
+int cv_cluster(b200cv_detector *d, const b200cv_pose *d_poses, uint32_t refs, b200cv_pose *results, size_t cap, size_t *n_clusters) {
+    b200ppf_ctx *ctx = d->ctx;
+    StreamBuf<uint32_t> order(ctx), member_of(ctx), lead_pose(ctx), size(ctx), corder(ctx), ncl(ctx);
+    StreamBuf<double4> lead(ctx);
+    StreamBuf<unsigned long long> votes(ctx);
+    StreamBuf<b200cv_pose> out(ctx);
+    PPF_CUDA(ctx, order.alloc(refs));
+    PPF_CUDA(ctx, member_of.alloc(refs));
+    PPF_CUDA(ctx, lead_pose.alloc(refs));
+    PPF_CUDA(ctx, size.alloc(refs));
+    PPF_CUDA(ctx, corder.alloc(refs));
+    PPF_CUDA(ctx, ncl.alloc(1));
+    PPF_CUDA(ctx, lead.alloc(refs));
+    PPF_CUDA(ctx, votes.alloc(refs));
+    PPF_CUDA(ctx, out.alloc(refs));
+    CvClusterArgs a;
+    a.poses = d_poses;
+    a.n = refs;
+    a.position_threshold = d->position_threshold;
+    a.rotation_threshold = d->rotation_threshold;
+    a.order = order;
+    a.member_of = member_of;
+    a.lead = lead;
+    a.lead_pose = lead_pose;
+    a.size = size;
+    a.votes = votes;
+    a.corder = corder;
+    a.out = out;
+    a.n_clusters = ncl;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    PPF_LAUNCH(ctx, cv_cluster_kernel, 1, CV_CLUSTER_THREADS, 0, a);
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    uint32_t h_ncl = 0;
+    PPF_CUDA(ctx, cudaMemcpyAsync(&h_ncl, ncl.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t take = std::min<size_t>(h_ncl, cap);
+    if (take) {
+        PPF_CUDA(ctx, cudaMemcpyAsync(results, out.p, take * sizeof(b200cv_pose), cudaMemcpyDeviceToHost, ctx->stream));
+        PPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaEventElapsedTime(&ctx->timings.cluster_ms, ctx->ev[2], ctx->ev[3]);
+    *n_clusters = h_ncl;
+    return B200PPF_OK;
 }
 
 }  // namespace
@@ -815,13 +915,14 @@ static int cv_match_impl(b200cv_detector *d, const float *scene, size_t n, size_
     const size_t refs = (d->n_scene + step - 1) / step;
     d->raw.clear();
     if (refs == 0) return B200PPF_OK;
-    rc = cv_vote(d, (uint32_t)step, (uint32_t)refs, acc_dump, (uint32_t)dump_ref);
+    b200cv_pose *d_poses = nullptr;
+    rc = cv_vote(d, (uint32_t)step, (uint32_t)refs, acc_dump, (uint32_t)dump_ref, &d_poses);
     if (rc) return rc;
-    std::vector<b200cv_pose> clusters;
     size_t ncl = 0;
-    cv_cluster(d, clusters, &ncl);
+    rc = cv_cluster(d, d_poses, (uint32_t)refs, results, cap, &ncl);
+    cudaFreeAsync(d_poses, ctx->stream);
+    if (rc) return rc;
     *n_results = ncl;
-    for (size_t k = 0; k < clusters.size() && k < cap; ++k) results[k] = clusters[k];
     return B200PPF_OK;
 }
 
