@@ -301,7 +301,10 @@ int b200ppf_transform(b200ppf_ctx *ctx, const b200ppf_cloud *cloud, const float 
  * (opencv_contrib surface_matching/src/icp.cpp: multi-resolution "picky" point-to-plane ICP).
  * poses16: n_poses row-major 4x4 doubles, model -> scene, refined in place (Pose3D::appendPose);
  * residuals (n_poses) and iterations (total over poses) may be NULL.  params NULL = the reference's
- * (100, 0.005, 2.5, 8).  All poses are refined concurrently, one CTA each, in a single launch. */
+ * (100, 0.005, 2.5, 8).  All poses are refined concurrently, one thread-block cluster each, in a single launch.
+ * The point-to-plane system is solved as upstream's cv::solve(DECOMP_SVD) solves it — least squares of minimum norm —
+ * so levels that keep fewer correspondences than unknowns (a 543-point model has 4 samples at level 7) move the pose
+ * only where the data constrain it. */
 typedef struct b200ppf_icp_params {
     int max_iterations;    /* ICP(iterations = 100, ...) */
     float tolerance;       /* 0.005 */
