@@ -140,6 +140,22 @@ public:
         for (std::size_t e = 0; e < found; ++e) indices.emplace_back(buf[2 * e], buf[2 * e + 1]);
     }
 
+    // PCL's makeShared(): a copy of the search object — here a device-to-device copy of the table (b200ppf_table_clone)
+    Ptr makeShared() const {
+        Ptr copy(new PPFHashMapSearch(angle_discretization_step_, distance_discretization_step_));
+        if (!internals_initialized_) return copy;
+        b200ppf_ctx *ctx = b200::defaultContext();
+        if (!ctx || b200ppf_table_clone(ctx, table_.h, &copy->table_.h) != B200PPF_OK) {
+            PCL_ERROR("[pcl::PPFHashMapSearch::makeShared] %s\n", b200ppf_last_error(ctx));
+            copy->table_.reset();
+            return copy;
+        }
+        copy->alpha_m_ = alpha_m_;
+        copy->max_dist_ = max_dist_;
+        copy->internals_initialized_ = true;
+        return copy;
+    }
+
     float getAngleDiscretizationStep() const { return angle_discretization_step_; }
     float getDistanceDiscretizationStep() const { return distance_discretization_step_; }
     float getModelDiameter() const { return max_dist_; }
@@ -150,7 +166,7 @@ public:
     const b200ppf_table *deviceTable() const { return internals_initialized_ ? table_.h : nullptr; }
 
 private:
-    PPFHashMapSearch(const PPFHashMapSearch &) = delete;  // owns a device table (PCL's makeShared() copy is not offered)
+    PPFHashMapSearch(const PPFHashMapSearch &) = delete;  // owns a device table: copies go through makeShared()
     float angle_discretization_step_, distance_discretization_step_;
     float max_dist_ = -1.0f;
     bool internals_initialized_ = false;

@@ -96,5 +96,19 @@ int main(int argc, char **argv) {
                       loaded->getModelDiameter() == hashmap_search->getModelDiameter() &&
                       loaded->getDistanceDiscretizationStep() == 0.01f;
     std::printf("reloaded_table_same_pose %d\n", same ? 1 : 0);
+
+    // PPFHashMapSearch::makeShared(): the copy owns its own device table and answers like the original
+    pcl::PPFHashMapSearch::Ptr copy = hashmap_search->makeShared();
+    hashmap_search.reset();
+    std::vector<std::pair<std::size_t, std::size_t>> nn2;
+    copy->nearestNeighborSearch(f1, f2, f3, f4, nn2);
+    pcl::PPFRegistration<pcl::PointNormal, pcl::PointNormal> third;
+    third.setSceneReferencePointSamplingRate(5);
+    third.setSearchMethod(copy);
+    third.setInputSource(model);
+    third.setInputTarget(scene);
+    pcl::PointCloud<pcl::PointNormal> out3;
+    third.align(out3);
+    std::printf("copied_table_same_answers %d\n", (nn2 == nn && third.hasConverged() && third.getFinalTransformation() == mat) ? 1 : 0);
     return 0;
 }

@@ -1032,9 +1032,10 @@ def test_cpp_pcl_shim_end_to_end(tmp_path, ctx, bottle, scene_crop, dev_bottle, 
     bucket = lines[5].split()
     assert int(bucket[1]) >= 1 and (int(bucket[3]), int(bucket[4])) <= (0, 1)
     assert lines[7].split() == ["reloaded_table_same_pose", "1"]
+    assert lines[8].split() == ["copied_table_same_answers", "1"]  # PPFHashMapSearch::makeShared()
     # the same binary with B200PPF_DEVICES=0,0: PPFRegistration::align goes through b200ppf_multi_* (two contexts on
     # this GPU stand in for two GPUs) — same table copied device to device, same poses, same output
     r2 = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300,
                         env=dict(os.environ, B200PPF_DEVICES="0,0"))
     assert r2.returncode == 0, r2.stdout + r2.stderr
-    assert r2.stdout.strip().splitlines()[:8] == lines[:8]
+    assert r2.stdout.strip().splitlines()[:9] == lines[:9]
